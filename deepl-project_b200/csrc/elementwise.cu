@@ -1,0 +1,434 @@
+// HBM-bound kernels of the TransVAE hot path (vectorised 128-bit accesses, warp-shuffle reductions):
+// first-layer direct convolution, GroupNorm(+SiLU), per-token RMS/LayerNorm statistics, layout conversion,
+// reparameterisation and the L1+KL loss.  All activations are NHWC bf16; statistics are fp32.
+#include "../../include/transvae_sm100.h"
+#include "common.cuh"
+
+namespace tvae {
+
+// -------------------------------------------------------------------------------------------------
+// conv_in: 3x3, pad 1, Cin (3) -> Cout, NCHW fp32 input, NHWC bf16 output.
+// Replaces nn.Conv2d at encoder.py:52 (0.03 % of the model's FLOPs; bound by the 2*Cout bytes/pixel it writes).
+// One thread per pixel keeps its 9*Cin inputs in registers and sweeps the output channels 8 at a time with
+// the weights broadcast from shared memory.
+// -------------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(128) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                      int B, int H, int W, int Cout) {
+  extern __shared__ float sw[];  // [9*CIN][Cout] + bias[Cout]
+  float* sb = sw + 9 * CIN * Cout;
+  for (int i = threadIdx.x; i < 9 * CIN * Cout; i += blockDim.x) {
+    const int co = i % Cout, k = i / Cout;        // k = (ci*3 + dy)*3 + dx in OIHW order
+    sw[i] = w[(size_t)co * 9 * CIN + k];
+  }
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.0f;
+  __syncthreads();
+  const long long npix = (long long)B * H * W;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int wq = (int)(pix % W), hq = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+    float in[9 * CIN];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int yy = hq + dy - 1, xx = wq + dx - 1;
+          in[(ci * 3 + dy) * 3 + dx] =
+              (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + (((size_t)b * CIN + ci) * H + yy) * W + xx) : 0.0f;
+        }
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)pix * Cout);
+    for (int c0 = 0; c0 < Cout; c0 += 8) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = sb[c0 + j];
+#pragma unroll
+      for (int k = 0; k < 9 * CIN; ++k) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + k * Cout + c0);
+        const float4 w1 = *reinterpret_cast<const float4*>(sw + k * Cout + c0 + 4);
+        const float v = in[k];
+        acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+        acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+        acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+        acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+      }
+      uint4 pk;
+      pk.x = pack_bf16(acc[0], acc[1]); pk.y = pack_bf16(acc[2], acc[3]);
+      pk.z = pack_bf16(acc[4], acc[5]); pk.w = pack_bf16(acc[6], acc[7]);
+      o[c0 >> 3] = pk;
+    }
+  }
+}
+
+int conv_in_run(const float* x, const float* w, const float* bias, void* out, int B, int Cin, int H, int W, int Cout,
+                cudaStream_t stream) {
+  TVAE_REQUIRE(Cin == 3, "conv_in: only 3 input channels are supported (got %d)", Cin);
+  TVAE_REQUIRE(Cout % 8 == 0, "conv_in: Cout %d must be a multiple of 8", Cout);
+  const size_t smem = (size_t)(9 * 3 * Cout + Cout) * sizeof(float);
+  TVAE_REQUIRE(smem <= 200 * 1024, "conv_in: Cout %d too large", Cout);
+  static bool configured = false;
+  if (!configured) {
+    TVAE_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  const long long npix = (long long)B * H * W;
+  int grid = (int)((npix + 127) / 128);
+  const int cap = num_sms() * 8;
+  if (grid > cap) grid = cap;
+  conv_in_kernel<3><<<grid, 128, smem, stream>>>(x, w, bias, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, Cout);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// GroupNorm statistics over NHWC bf16: sums[b][g] = (sum x, sum x^2) over the group's channels and all pixels.
+// Replaces the reduction half of nn.GroupNorm(32, C) (blocks.py:33,36; decoder.py:93).
+// Algorithmic bytes: 2*C per pixel (one read).
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ sums, int HW,
+                                                       int C, int G, int pix_per_block) {
+  __shared__ float s_acc[2 * 128];
+  const int nvec = C >> 3;
+  const int ppb = blockDim.x / nvec;           // pixels processed per pass
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.0f;
+  __syncthreads();
+  const int v = threadIdx.x % nvec, pv = threadIdx.x / nvec;
+  float s[8], ss[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.0f;
+  if (pv < ppb) {
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(HW, p0 + pix_per_block);
+    const uint4* base = x + (size_t)b * HW * nvec + v;
+    for (int p = p0 + pv; p < p1; p += ppb) {
+      const uint4 u = __ldg(base + (size_t)p * nvec);
+      float2 t;
+      t = unpack_bf16(u.x); s[0] += t.x; ss[0] += t.x * t.x; s[1] += t.y; ss[1] += t.y * t.y;
+      t = unpack_bf16(u.y); s[2] += t.x; ss[2] += t.x * t.x; s[3] += t.y; ss[3] += t.y * t.y;
+      t = unpack_bf16(u.z); s[4] += t.x; ss[4] += t.x * t.x; s[5] += t.y; ss[5] += t.y * t.y;
+      t = unpack_bf16(u.w); s[6] += t.x; ss[6] += t.x * t.x; s[7] += t.y; ss[7] += t.y * t.y;
+    }
+    const int cpg = C / G;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (v * 8 + i) / cpg;
+      atomicAdd(&s_acc[2 * g], s[i]);
+      atomicAdd(&s_acc[2 * g + 1], ss[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&sums[(size_t)b * 2 * G + i], s_acc[i]);
+}
+
+int gn_stats_run(const void* x, float* sums, int B, int HW, int C, int G, cudaStream_t stream) {
+  TVAE_REQUIRE(C % 8 == 0 && C % G == 0 && G <= 128 && C / 8 <= 256, "groupnorm: unsupported C=%d G=%d", C, G);
+  TVAE_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * G * 2 * sizeof(float), stream));
+  const int nvec = C / 8;
+  const int threads = (256 / nvec) * nvec;
+  int ppb = 2048;
+  while (ppb > 64 && (long long)((HW + ppb - 1) / ppb) * B < 2LL * num_sms()) ppb >>= 1;
+  dim3 grid((HW + ppb - 1) / ppb, B);
+  gn_stats_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<const uint4*>(x), sums, HW, C, G, ppb);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// y = act((x - mean_g) * rstd_g * gamma_c + beta_c), act = SiLU or identity.  NHWC bf16 in / out.
+// Replaces the affine half of nn.GroupNorm + F.silu (blocks.py:60-66; decoder.py:128-129).
+// Algorithmic bytes: 4*C per pixel (read + write).
+__global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ sums,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       uint4* __restrict__ y, int HW, int C, int G, float eps,
+                                                       int apply_silu, int vec_per_block) {
+  extern __shared__ float s_ab[];  // scale[C], shift[C]
+  const int b = blockIdx.y;
+  const int cpg = C / G;
+  const float inv_n = 1.0f / ((float)cpg * (float)HW);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mean = sums[((size_t)b * G + g) * 2] * inv_n;
+    const float var = fmaxf(sums[((size_t)b * G + g) * 2 + 1] * inv_n - mean * mean, 0.0f);
+    const float rstd = rsqrtf(var + eps);
+    const float a = rstd * gamma[c];
+    s_ab[c] = a;
+    s_ab[C + c] = beta[c] - mean * a;
+  }
+  __syncthreads();
+  const int nvec = C >> 3;
+  const long long total = (long long)HW * nvec;
+  const long long i0 = (long long)blockIdx.x * vec_per_block;
+  const long long i1 = min(total, i0 + vec_per_block);
+  // blockDim.x is a multiple of nvec and vec_per_block too, so each thread always sees the same 8 channels
+  const int v = threadIdx.x % nvec;
+  float a[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = s_ab[v * 8 + i];
+    sh[i] = s_ab[C + v * 8 + i];
+  }
+  const uint4* xb = x + (size_t)b * total;
+  uint4* yb = y + (size_t)b * total;
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    const uint4 u = __ldg(xb + i);
+    float f[8];
+    float2 t;
+    t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float z = fmaf(f[k], a[k], sh[k]);
+      f[k] = apply_silu ? silu(z) : z;
+    }
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+    o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+    yb[i] = o;
+  }
+}
+
+int gn_apply_run(const void* x, const float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
+                 int G, float eps, int apply_silu, cudaStream_t stream) {
+  TVAE_REQUIRE(C % 8 == 0 && C % G == 0 && C / 8 <= 256, "groupnorm: unsupported C=%d G=%d", C, G);
+  const int nvec = C / 8;
+  const int threads = (256 / nvec) * nvec;
+  const long long total = (long long)HW * nvec;
+  long long vpb = (long long)threads * 16;
+  while (vpb > threads && ((total + vpb - 1) / vpb) * B < 4LL * num_sms()) vpb >>= 1;
+  vpb = (vpb / threads) * threads;
+  if (vpb < threads) vpb = threads;
+  dim3 grid((unsigned)((total + vpb - 1) / vpb), B);
+  gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(
+      reinterpret_cast<const uint4*>(x), sums, gamma, beta, reinterpret_cast<uint4*>(y), HW, C, G, eps, apply_silu,
+      (int)vpb);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Per-token statistics (one warp per token, row of C bf16 values):
+//   mode 0 (FFN, blocks.py:149 RMSNorm):            out_a = 1/sqrt(mean(x^2) + 1e-6)
+//   mode 1 (attention, blocks.py:146 RMSNorm followed by the three LayerNorms of attention.py:71-73, which
+//           all see the same input h = x*w1/rms):    out_a = 1/(sigma*rms),  out_b = mu/sigma
+//           with mu = mean(h), sigma = sqrt(var(h) + 1e-5).
+// The normalised tensor is never materialised: the projection GEMM applies out_a / out_b in its epilogue
+// (row_scale / row_shift of tvae_mtgemm) with the norm weights folded into the projection weights.
+// Algorithmic bytes: 2*C per token.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) row_stats_kernel(const uint4* __restrict__ x, const float* __restrict__ w1,
+                                                        float* __restrict__ out_a, float* __restrict__ out_b,
+                                                        long long M, int C, int mode) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= M) return;
+  const int nvec = C >> 3;
+  const uint4* xr = x + row * nvec;
+  float s2 = 0.0f, sw = 0.0f, sw2 = 0.0f;
+  for (int v = lane; v < nvec; v += 32) {
+    const uint4 u = __ldg(xr + v);
+    float f[8];
+    float2 t;
+    t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+    if (mode == 1) {
+      const float4 wa = __ldg(reinterpret_cast<const float4*>(w1) + 2 * v);
+      const float4 wb = __ldg(reinterpret_cast<const float4*>(w1) + 2 * v + 1);
+      const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float h = f[k] * wv[k];
+        s2 = fmaf(f[k], f[k], s2);
+        sw += h;
+        sw2 = fmaf(h, h, sw2);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s2 = fmaf(f[k], f[k], s2);
+    }
+  }
+  s2 = warp_sum(s2);
+  if (mode == 1) {
+    sw = warp_sum(sw);
+    sw2 = warp_sum(sw2);
+  }
+  if (lane == 0) {
+    const float invC = 1.0f / (float)C;
+    const float rms = sqrtf(s2 * invC + 1e-6f);
+    if (mode == 0) {
+      out_a[row] = 1.0f / rms;
+    } else {
+      const float mu = sw * invC / rms;
+      const float var = fmaxf(sw2 * invC / (rms * rms) - mu * mu, 0.0f);
+      const float sigma = sqrtf(var + 1e-5f);
+      out_a[row] = 1.0f / (sigma * rms);
+      out_b[row] = mu / sigma;
+    }
+  }
+}
+
+int row_stats_run(const void* x, const float* w1, float* out_a, float* out_b, long long M, int C, int mode,
+                  cudaStream_t stream) {
+  TVAE_REQUIRE(C % 8 == 0, "row_stats: C=%d must be a multiple of 8", C);
+  TVAE_REQUIRE(mode == 0 || (w1 != nullptr && out_b != nullptr), "row_stats: mode 1 needs w1 and out_b");
+  const long long threads = M * 32;
+  const int grid = (int)((threads + 255) / 256);
+  row_stats_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), w1, out_a, out_b, M, C, mode);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC bf16 with zero channel padding (latent z -> decoder.conv_in operand).
+// -------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int C, int HW,
+                                    int Cpad) {
+  const long long total = (long long)B * HW * Cpad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cpad);
+    const long long bp = i / Cpad;
+    const int p = (int)(bp % HW);
+    const int b = (int)(bp / HW);
+    out[i] = __float2bfloat16(c < C ? in[((size_t)b * C + c) * HW + p] : 0.0f);
+  }
+}
+
+int nchw_to_nhwc_run(const float* in, void* out, int B, int C, int H, int W, int Cpad, cudaStream_t stream) {
+  const long long total = (long long)B * H * W * Cpad;
+  int grid = (int)((total + 255) / 256);
+  if (grid > num_sms() * 16) grid = num_sms() * 16;
+  nchw_to_nhwc_kernel<<<grid, 256, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out), B, C, H * W, Cpad);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// NHWC bf16 -> NCHW fp32 (first C of Cs channels); used to hand intermediate activations back to torch callers.
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int B, int C, int HW,
+                                    int Cs) {
+  const long long total = (long long)B * C * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const long long bc = i / HW;
+    const int c = (int)(bc % C);
+    const int b = (int)(bc / C);
+    out[i] = __bfloat162float(in[((size_t)b * HW + p) * Cs + c]);
+  }
+}
+
+int nhwc_to_nchw_run(const void* in, float* out, int B, int C, int H, int W, int Cs, cudaStream_t stream) {
+  const long long total = (long long)B * C * H * W;
+  int grid = (int)((total + 255) / 256);
+  if (grid > num_sms() * 16) grid = num_sms() * 16;
+  nhwc_to_nchw_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, B, C, H * W, Cs);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Reparameterisation (transvae.py:186-199; patched :186-196 and the clamps of :244-245).
+//   patched: mu_c = clamp(mu, -50, 50), lv_c = clamp(logvar, -30, 20), z = mu_c + eps * exp(0.5 * lv_c)
+//   main   : z = mu + eps * exp(0.5 * logvar)
+// eps is drawn by the caller (torch generator) so that a seed reproduces the reference's sample.
+// -------------------------------------------------------------------------------------------------
+__global__ void reparam_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
+                               const float* __restrict__ eps, float* __restrict__ z, float* __restrict__ mu_out,
+                               float* __restrict__ lv_out, long long n, int patched) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float m = mu[i], lv = logvar[i];
+    if (patched) {
+      m = fminf(fmaxf(m, -50.0f), 50.0f);
+      lv = fminf(fmaxf(lv, -30.0f), 20.0f);
+    }
+    z[i] = m + eps[i] * expf(0.5f * lv);
+    if (mu_out) mu_out[i] = m;
+    if (lv_out) lv_out[i] = lv;
+  }
+}
+
+int reparam_run(const float* mu, const float* logvar, const float* eps, float* z, float* mu_out, float* lv_out,
+                long long n, int patched, cudaStream_t stream) {
+  int grid = (int)((n + 255) / 256);
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  reparam_kernel<<<grid, 256, 0, stream>>>(mu, logvar, eps, z, mu_out, lv_out, n, patched);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// L1 + KL partial sums (vae_loss.py:83, :94-95; patched :80-104).
+//   acc[0] += sum |f(recon) - target|   (f = sigmoid when patched)
+//   acc[1] += sum -0.5 * (1 + lv - mu^2 - exp(lv))   (lv clamped when patched)
+//   acc[2] += number of non-finite terms (cheap isfinite flag, no host sync)
+// The caller divides by the element counts the reference uses.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ recon, const float* __restrict__ target,
+                                                   const float* __restrict__ mu, const float* __restrict__ logvar,
+                                                   float* __restrict__ acc, long long n_img, long long n_lat,
+                                                   int patched, float clip_lo, float clip_hi) {
+  float l1 = 0.0f, kl = 0.0f, bad = 0.0f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n4 = n_img >> 2;
+  for (long long i = t0; i < n4; i += stride) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(recon) + i);
+    const float4 t = __ldg(reinterpret_cast<const float4*>(target) + i);
+    float rv[4] = {r.x, r.y, r.z, r.w};
+    const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (patched) rv[k] = 1.0f / (1.0f + __expf(-rv[k]));
+      const float d = fabsf(rv[k] - tv[k]);
+      if (!isfinite(d)) bad += 1.0f;
+      l1 += d;
+    }
+  }
+  for (long long i = (n4 << 2) + t0; i < n_img; i += stride) {
+    float rv = recon[i];
+    if (patched) rv = 1.0f / (1.0f + __expf(-rv));
+    l1 += fabsf(rv - target[i]);
+  }
+  for (long long i = t0; i < n_lat; i += stride) {
+    const float m = mu[i];
+    float lv = logvar[i];
+    if (patched) lv = fminf(fmaxf(lv, clip_lo), clip_hi);
+    const float v = -0.5f * (1.0f + lv - m * m - expf(lv));
+    if (!isfinite(v)) bad += 1.0f;
+    kl += v;
+  }
+  __shared__ float red[3][8];
+  l1 = warp_sum(l1); kl = warp_sum(kl); bad = warp_sum(bad);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = l1; red[1][warp] = kl; red[2][warp] = bad; }
+  __syncthreads();
+  if (warp == 0) {
+    l1 = lane < 8 ? red[0][lane] : 0.0f;
+    kl = lane < 8 ? red[1][lane] : 0.0f;
+    bad = lane < 8 ? red[2][lane] : 0.0f;
+    l1 = warp_sum(l1); kl = warp_sum(kl); bad = warp_sum(bad);
+    if (lane == 0) {
+      atomicAdd(acc + 0, l1);
+      atomicAdd(acc + 1, kl);
+      atomicAdd(acc + 2, bad);
+    }
+  }
+}
+
+int loss_run(const float* recon, const float* target, const float* mu, const float* logvar, float* acc,
+             long long n_img, long long n_lat, int patched, float clip_lo, float clip_hi, cudaStream_t stream) {
+  TVAE_CHECK_CUDA(cudaMemsetAsync(acc, 0, 4 * sizeof(float), stream));
+  int grid = (int)((n_img / 4 + 255) / 256);
+  if (grid > num_sms() * 4) grid = num_sms() * 4;
+  if (grid < 1) grid = 1;
+  loss_kernel<<<grid, 256, 0, stream>>>(recon, target, mu, logvar, acc, n_img, n_lat, patched, clip_lo, clip_hi);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tvae

@@ -1,0 +1,467 @@
+// Fused multi-tap implicit GEMM for sm_100a.
+//
+//   out[tile] = epilogue( sum_taps  A_tap[128 pixels x 64k] * W[BLOCK_N x 64k]^T )
+//
+// One persistent CTA per SM, 8 warps, warp-specialised:
+//   warp 0  TMA producer   : per K block one 5-D pixel-box load (A; zero-filled halo = conv padding) and one
+//                            2-D weight box load (B) into a STAGES-deep 128B-swizzled smem ring
+//   warp 1  MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16, fp32 accumulators in
+//                            TMEM, double buffered (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
+//                            main loop of tile i+1
+//   warp 2  residual loader: TMA-loads the residual tile straight into the output staging buffer
+//   warp 3  idle
+//   warps 4-7 epilogue     : tcgen05.ld -> row/col affine, bias, GELU/SiLU, RoPE, residual -> bf16 -> swizzled
+//                            smem -> TMA store (or direct fp32 NCHW store for the 3-/64-channel heads)
+//
+// Every convolution, linear layer, pixel (un)shuffle and nearest-2x upsample of the reference is one launch of
+// this kernel with a different tap table (see include/transvae_sm100.h and transvae/_taps.py).
+#include "../../include/transvae_sm100.h"
+#include "common.cuh"
+#include "tmap.cuh"
+
+namespace tvae {
+
+struct MtTap {
+  int32_t c_off;
+  int32_t wk_off;
+  int16_t kblocks;
+  int8_t map, dw, p, dh;
+  int8_t pad_[2];
+};
+static_assert(sizeof(MtTap) == 16, "MtTap must be 16 bytes");
+
+struct MtParams {
+  int tiles_w, tiles_h, tiles_b, n_tiles;
+  int tw, th, nb;
+  int num_phases;
+  int ntaps[TVAE_MAX_PHASES];
+  int out_p[TVAE_MAX_PHASES];
+  int out_c_off[TVAE_MAX_PHASES];
+  MtTap taps[TVAE_MAX_PHASES][TVAE_MAX_TAPS];
+  const float* bias;
+  int n_total;
+  int act;
+  const float* row_scale;
+  const float* row_shift;
+  const float* col_sum;
+  int has_residual;
+  const float2* rope_tab;
+  int rope_C, rope_H, rope_W;
+  float q_scale;
+  float* out_f32;
+  int out_n;
+  int vB, vH, vW;  // output view extents (pixels) for row indexing / bounds
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kThreads = 256;
+
+template <int BLOCK_N>
+struct MtCfg {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kOutBytes = kBlockM * BLOCK_N * 2;
+  static constexpr int kStages = (227 * 1024 - 2048 - kOutBytes) / (kABytes + kBBytes) > 8
+                                     ? 8
+                                     : (227 * 1024 - 2048 - kOutBytes) / (kABytes + kBBytes);
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
+  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kOutBytes + 1024 /*align slack*/ + 256 /*bars*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+              const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ MtParams P) {
+#ifdef TVAE_DEVICE_OK
+  using Cfg = MtCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + STAGES * kABytes;
+  uint8_t* sOut = sB + STAGES * Cfg::kBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + Cfg::kOutBytes);
+  uint64_t* full = bars;                   // [STAGES]
+  uint64_t* empty = bars + STAGES;         // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES; // [2]
+  uint64_t* tmem_empty = tmem_full + 2;    // [2]
+  uint64_t* res_full = tmem_empty + 2;     // [1]
+  uint64_t* out_free = res_full + 1;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_free + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    tma_prefetch_desc(&tmRes);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    mbar_init(res_full, 1);
+    mbar_init(out_free, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
+  const int total_tiles = P.num_phases * m_tiles * P.n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_t = tile % P.n_tiles;
+        const int t2 = tile / P.n_tiles;
+        const int m_t = t2 % m_tiles;
+        const int ph = t2 / m_tiles;
+        const int w0 = (m_t % P.tiles_w) * P.tw;
+        const int h0 = ((m_t / P.tiles_w) % P.tiles_h) * P.th;
+        const int b0 = (m_t / (P.tiles_w * P.tiles_h)) * P.nb;
+        const int nt = P.ntaps[ph];
+        for (int t = 0; t < nt; ++t) {
+          const MtTap tap = P.taps[ph][t];
+          const CUtensorMap* mapA = tap.map ? &tmA1 : &tmA0;
+          for (int kb = 0; kb < tap.kblocks; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], kABytes + Cfg::kBBytes);
+            tma_load_5d(sA + stage * kABytes, mapA, &full[stage], tap.c_off + kb * kBlockK, w0 + tap.dw, tap.p,
+                        h0 + tap.dh, b0);
+            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], tap.wk_off + kb * kBlockK, n_t * BLOCK_N);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int ph = (tile / P.n_tiles) / m_tiles;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        int kblocks = 0;
+        for (int t = 0; t < P.ntaps[ph]; ++t) kblocks += P.taps[ph][t].kblocks;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + stage * kABytes);
+          const uint32_t b_base = smem_u32(sB + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            umma_f16(d_tmem, umma_desc_kmajor_sw128(a_base + k * 32), umma_desc_kmajor_sw128(b_base + k * 32), idesc,
+                     (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ residual loader
+    if (lane == 0 && P.has_residual) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int n_t = tile % P.n_tiles;
+        const int t2 = tile / P.n_tiles;
+        const int m_t = t2 % m_tiles;
+        const int ph = t2 / m_tiles;
+        const int w0 = (m_t % P.tiles_w) * P.tw;
+        const int h0 = ((m_t / P.tiles_w) % P.tiles_h) * P.th;
+        const int b0 = (m_t / (P.tiles_w * P.tiles_h)) * P.nb;
+        mbar_wait(out_free, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(res_full, Cfg::kOutBytes);
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / 64; ++j)
+          tma_load_5d(sOut + j * kABytes, &tmRes, res_full, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph],
+                      h0, b0);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;       // row of the tile owned by this thread
+    const bool store_leader = (threadIdx.x == 128);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n_t = tile % P.n_tiles;
+      const int t2 = tile / P.n_tiles;
+      const int m_t = t2 % m_tiles;
+      const int ph = t2 / m_tiles;
+      const int w0 = (m_t % P.tiles_w) * P.tw;
+      const int h0 = ((m_t / P.tiles_w) % P.tiles_h) * P.th;
+      const int b0 = (m_t / (P.tiles_w * P.tiles_h)) * P.nb;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+
+      // pixel owned by this row
+      const int wi = r % P.tw, hi = (r / P.tw) % P.th, bi = r / (P.tw * P.th);
+      const int pw = w0 + wi, phh = h0 + hi, pb = b0 + bi;
+      const bool row_ok = (pw < P.vW) && (phh < P.vH) && (pb < P.vB);
+      const long long grow = ((long long)pb * P.vH + phh) * P.vW + pw;  // flattened output-view pixel index
+
+      float rs = 1.0f, rsh = 0.0f;
+      if (P.row_scale != nullptr && row_ok) rs = __ldg(P.row_scale + grow);
+      if (P.row_shift != nullptr && row_ok) rsh = __ldg(P.row_shift + grow);
+      const float* bias = P.bias ? P.bias + (size_t)ph * P.n_total : nullptr;
+
+      // RoPE position of this row (flat [B*S, C] GEMM: token = row % (H*W))
+      int rope_r = 0, rope_c = 0;
+      if (P.rope_tab != nullptr) {
+        const int tok = (int)(grow % ((long long)P.rope_H * P.rope_W));
+        rope_r = tok / P.rope_W;
+        rope_c = tok % P.rope_W;
+      }
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      if (P.has_residual) mbar_wait(res_full, it & 1);
+
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c32 = 0; c32 < BLOCK_N / 32; ++c32) {
+        uint32_t v[32];
+        tmem_ld32(t_row + c32 * 32, v);
+        tmem_ld_wait();
+        const int n0 = n_t * BLOCK_N + c32 * 32;  // first global output column of this 32-wide slab
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(v[i]) * rs;
+          if (P.row_shift != nullptr) x -= rsh * __ldg(P.col_sum + n0 + i);
+          if (bias != nullptr) x += __ldg(bias + n0 + i);
+          if (P.act == TVAE_ACT_GELU) x = gelu_erf(x);
+          else if (P.act == TVAE_ACT_SILU) x = silu(x);
+          f[i] = x;
+        }
+        if (P.rope_tab != nullptr && n0 < 2 * P.rope_C) {
+          // columns n0..n0+31 are one half of a 64-wide head: first half rotates with the row index,
+          // second half with the column index (attention.py:161-170); pair (2i, 2i+1) uses the angle of
+          // slot 2i for the even output and of slot 2i+1 for the odd output (attention.py:178-197).
+          const int pos = ((n0 & 32) == 0) ? rope_r : rope_c;
+          const float2* tab = P.rope_tab + (size_t)pos * 16;
+          const float qs = (n0 < P.rope_C) ? P.q_scale : 1.0f;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float2 ca = __ldg(tab + (i & 15));
+            const float2 cb = __ldg(tab + ((i + 1) & 15));
+            const float a = f[i], b = f[i + 1];
+            f[i] = (a * ca.x - b * ca.y) * qs;
+            f[i + 1] = (a * cb.y + b * cb.x) * qs;
+          }
+        }
+        if (P.out_f32 != nullptr) {
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int n = n0 + i;
+              if (n < P.out_n) P.out_f32[(((long long)pb * P.out_n + n) * P.vH + phh) * P.vW + pw] = f[i];
+            }
+          }
+        } else {
+          uint8_t* chunk = sOut + (c32 >> 1) * kABytes + r * 128;
+          const int cbase = (c32 & 1) * 4;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4* p16 = reinterpret_cast<uint4*>(chunk + (((cbase + g) ^ (r & 7)) << 4));
+            if (P.has_residual) {
+              const uint4 rv = *p16;
+              float2 t;
+              t = unpack_bf16(rv.x); f[g * 8 + 0] += t.x; f[g * 8 + 1] += t.y;
+              t = unpack_bf16(rv.y); f[g * 8 + 2] += t.x; f[g * 8 + 3] += t.y;
+              t = unpack_bf16(rv.z); f[g * 8 + 4] += t.x; f[g * 8 + 5] += t.y;
+              t = unpack_bf16(rv.w); f[g * 8 + 6] += t.x; f[g * 8 + 7] += t.y;
+            }
+            uint4 o;
+            o.x = pack_bf16(f[g * 8 + 0], f[g * 8 + 1]);
+            o.y = pack_bf16(f[g * 8 + 2], f[g * 8 + 3]);
+            o.z = pack_bf16(f[g * 8 + 4], f[g * 8 + 5]);
+            o.w = pack_bf16(f[g * 8 + 6], f[g * 8 + 7]);
+            *p16 = o;
+          }
+        }
+      }
+      // TMEM accumulator drained -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+
+      if (P.out_f32 == nullptr) {
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (store_leader) {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_store_5d(&tmOut, sOut + j * kABytes, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph], h0, b0);
+          tma_store_commit();
+          tma_store_wait_read<0>();
+          if (P.has_residual) mbar_arrive(out_free);
+        }
+        // staging buffer may be overwritten only after the bulk store has read it
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+    if (store_leader) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+#endif
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+template <int BLOCK_N>
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+                  const CUtensorMap& r, const MtParams& P, cudaStream_t stream) {
+  using Cfg = MtCfg<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    TVAE_CHECK_CUDA(cudaFuncSetAttribute(mtgemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int total = P.num_phases * P.tiles_w * P.tiles_h * P.tiles_b * P.n_tiles;
+  int grid = num_sms();
+  if (grid <= 0) grid = 148;
+  if (total < grid) grid = total;
+  mtgemm_kernel<BLOCK_N><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b, o, r, P);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static void view_extents(const tvae_view& v, int* vW, int* vH, int* vB) {
+  *vW = v.split ? v.W / 2 : v.W;
+  *vH = v.split ? v.H / 2 : v.H;
+  *vB = v.B;
+}
+
+int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
+  TVAE_REQUIRE(d != nullptr, "null descriptor");
+  TVAE_REQUIRE(d->a0.ptr != nullptr && d->w != nullptr, "mtgemm: missing operand");
+  TVAE_REQUIRE(d->num_phases >= 1 && d->num_phases <= TVAE_MAX_PHASES, "mtgemm: bad num_phases %d", d->num_phases);
+  TVAE_REQUIRE(d->n_total % 64 == 0 && d->k_total % 64 == 0, "mtgemm: n_total %d / k_total %d must be multiples of 64",
+               d->n_total, d->k_total);
+  const bool direct = d->out_f32 != nullptr;
+  TVAE_REQUIRE(direct || d->out.ptr != nullptr, "mtgemm: no output");
+
+  MtParams P;
+  memset(&P, 0, sizeof(P));
+  // the tile grid is defined on the output view (for a direct store: on a0's view, which must match)
+  const tvae_view& gv = direct ? d->a0 : d->out;
+  view_extents(gv, &P.vW, &P.vH, &P.vB);
+  P.tw = pow2_ceil(P.vW) < 128 ? pow2_ceil(P.vW) : 128;
+  P.th = pow2_ceil(P.vH) < 128 / P.tw ? pow2_ceil(P.vH) : 128 / P.tw;
+  P.nb = 128 / (P.tw * P.th);
+  P.tiles_w = (P.vW + P.tw - 1) / P.tw;
+  P.tiles_h = (P.vH + P.th - 1) / P.th;
+  P.tiles_b = (P.vB + P.nb - 1) / P.nb;
+
+  int block_n = 64;
+  if (d->n_total % 256 == 0) block_n = 256;
+  else if (d->n_total % 192 == 0) block_n = 192;
+  else if (d->n_total % 128 == 0) block_n = 128;
+  P.n_tiles = d->n_total / block_n;
+  P.n_total = d->n_total;
+  P.num_phases = d->num_phases;
+  for (int ph = 0; ph < d->num_phases; ++ph) {
+    TVAE_REQUIRE(d->ntaps[ph] >= 1 && d->ntaps[ph] <= TVAE_MAX_TAPS, "mtgemm: bad ntaps[%d]=%d", ph, d->ntaps[ph]);
+    P.ntaps[ph] = d->ntaps[ph];
+    P.out_p[ph] = d->out_p[ph];
+    P.out_c_off[ph] = d->out_c_off[ph];
+    for (int t = 0; t < d->ntaps[ph]; ++t) {
+      const tvae_tap& s = d->taps[ph][t];
+      const tvae_view& av = s.map ? d->a1 : d->a0;
+      TVAE_REQUIRE(av.ptr != nullptr, "mtgemm: tap uses absent view %d", s.map);
+      TVAE_REQUIRE(s.kblocks >= 1 && s.c_off >= 0 && s.c_off + s.kblocks * 64 <= (av.split ? 2 : 1) * av.C,
+                   "mtgemm: tap channel range [%d, +%d*64) exceeds view", s.c_off, s.kblocks);
+      TVAE_REQUIRE(s.wk_off >= 0 && s.wk_off + s.kblocks * 64 <= d->k_total, "mtgemm: tap weight range out of bounds");
+      MtTap& o = P.taps[ph][t];
+      o.c_off = s.c_off; o.wk_off = s.wk_off; o.kblocks = (int16_t)s.kblocks;
+      o.map = (int8_t)s.map; o.dw = (int8_t)s.dw; o.p = (int8_t)s.p; o.dh = (int8_t)s.dh;
+    }
+  }
+  P.bias = d->bias;
+  P.act = d->act;
+  P.row_scale = d->row_scale;
+  P.row_shift = d->row_shift;
+  P.col_sum = d->col_sum;
+  TVAE_REQUIRE(d->row_shift == nullptr || d->col_sum != nullptr, "mtgemm: row_shift needs col_sum");
+  P.has_residual = d->res.ptr != nullptr;
+  P.rope_tab = reinterpret_cast<const float2*>(d->rope_tab);
+  P.rope_C = d->rope_C; P.rope_H = d->rope_H; P.rope_W = d->rope_W;
+  P.q_scale = d->q_scale;
+  P.out_f32 = d->out_f32;
+  P.out_n = d->out_n;
+  TVAE_REQUIRE(!(direct && P.has_residual), "mtgemm: residual not supported with direct fp32 store");
+
+  CUtensorMap mA0, mA1, mB, mO, mR;
+  int rc;
+  if ((rc = make_tmap_pix(&mA0, d->a0.ptr, d->a0.B, d->a0.H, d->a0.W, d->a0.C, d->a0.split, P.tw, P.th, P.nb))) return rc;
+  if (d->a1.ptr) {
+    if ((rc = make_tmap_pix(&mA1, d->a1.ptr, d->a1.B, d->a1.H, d->a1.W, d->a1.C, d->a1.split, P.tw, P.th, P.nb))) return rc;
+  } else {
+    mA1 = mA0;
+  }
+  if ((rc = make_tmap_2d(&mB, d->w, d->n_total, d->k_total, d->k_total, block_n))) return rc;
+  if (!direct) {
+    TVAE_REQUIRE(((d->out.split ? 2 : 1) * d->out.C) % 64 == 0, "mtgemm: output channels must be a multiple of 64");
+    if ((rc = make_tmap_pix(&mO, d->out.ptr, d->out.B, d->out.H, d->out.W, d->out.C, d->out.split, P.tw, P.th, P.nb))) return rc;
+  } else {
+    mO = mA0;
+  }
+  if (P.has_residual) {
+    if ((rc = make_tmap_pix(&mR, d->res.ptr, d->res.B, d->res.H, d->res.W, d->res.C, d->res.split, P.tw, P.th, P.nb))) return rc;
+  } else {
+    mR = mO;
+  }
+  switch (block_n) {
+    case 256: return launch<256>(mA0, mA1, mB, mO, mR, P, stream);
+    case 192: return launch<192>(mA0, mA1, mB, mO, mR, P, stream);
+    case 128: return launch<128>(mA0, mA1, mB, mO, mR, P, stream);
+    default: return launch<64>(mA0, mA1, mB, mO, mR, P, stream);
+  }
+}
+
+}  // namespace tvae

@@ -1,0 +1,115 @@
+// Library runtime: last-error string, device queries, TMA tensor-map encoding.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "tmap.cuh"
+
+namespace tvae {
+
+static thread_local char g_err[1024] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_last_error() { return g_err; }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+    n = p.multiProcessorCount;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode(CUtensorMap* out, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                  const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode();
+  TVAE_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  TVAE_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base address %p not 16-byte aligned", ptr);
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_b, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d): rank=%d dims=(%llu,%llu,%llu,%llu,%llu) box=(%u,%u,%u,%u,%u)",
+                   (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                   (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                   (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+                   rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0);
+    return -3;
+  }
+  return 0;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                 uint32_t box_rows, uint32_t box_cols) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t str[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  TVAE_REQUIRE(box_rows <= 256 && box_cols * 2 <= 128, "bad 2-D TMA box %u x %u", box_rows, box_cols);
+  TVAE_REQUIRE((row_stride_elems * 2) % 16 == 0, "TMA row stride %llu not a multiple of 16 bytes",
+               (unsigned long long)(row_stride_elems * 2));
+  return encode(out, ptr, 2, dims, str, box);
+}
+
+int make_tmap_pix(CUtensorMap* out, const void* ptr, int B, int H, int W, int C, int split, int tw, int th, int nb) {
+  TVAE_REQUIRE(C % 8 == 0, "NHWC channel count %d must be a multiple of 8", C);
+  cuuint64_t dims[5];
+  cuuint64_t str[4];
+  const uint64_t e = 2;
+  if (split) {
+    TVAE_REQUIRE(H % 2 == 0 && W % 2 == 0, "phase view needs even H, W (got %d x %d)", H, W);
+    dims[0] = 2 * (uint64_t)C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = B;
+    str[0] = 2 * (uint64_t)C * e;            // w2
+    str[1] = (uint64_t)W * C * e;            // p
+    str[2] = 2 * (uint64_t)W * C * e;        // h2
+    str[3] = (uint64_t)H * W * C * e;        // b
+  } else {
+    dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = B;
+    str[0] = (uint64_t)C * e;
+    str[1] = (uint64_t)W * C * e;
+    str[2] = (uint64_t)W * C * e;
+    str[3] = (uint64_t)H * W * C * e;
+  }
+  cuuint32_t box[5] = {64, (cuuint32_t)tw, 1, (cuuint32_t)th, (cuuint32_t)nb};
+  TVAE_REQUIRE(tw * th * nb == 128 && tw <= 256 && th <= 256 && nb <= 256, "bad pixel box %d x %d x %d", tw, th, nb);
+  return encode(out, ptr, 5, dims, str, box);
+}
+
+int make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+                 uint64_t stride2_elems, uint32_t box1) {
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t str[2] = {stride1_elems * 2, stride2_elems * 2};
+  cuuint32_t box[3] = {64, box1, 1};
+  TVAE_REQUIRE((stride1_elems * 2) % 16 == 0 && (stride2_elems * 2) % 16 == 0, "3-D TMA strides must be 16-byte multiples");
+  return encode(out, ptr, 3, dims, str, box);
+}
+
+}  // namespace tvae
