@@ -1,0 +1,81 @@
+"""Autograd-aware kernel layer used by the modules.
+
+Without autograd (inference) each function is a direct launch from ``ops``.  With autograd enabled the same
+entry points route through ``torch.autograd.Function`` wrappers (``_autograd.py``) whose backward passes are
+again hand-written kernels.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import ops
+from ._lib import ACT_GELU, ACT_NONE, ACT_SILU  # noqa: F401
+
+Tensor = torch.Tensor
+
+
+def _needs_grad(*ts) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
+
+
+def _ag():
+    from . import _autograd
+    return _autograd
+
+
+def nchw_to_nhwc(x: Tensor, cpad: int) -> Tensor:
+    if _needs_grad(x):
+        return _ag().NchwToNhwc.apply(x, cpad)
+    return ops.nchw_to_nhwc(x, cpad)
+
+
+def nhwc_to_nchw(x: Tensor, c: Optional[int] = None) -> Tensor:
+    if _needs_grad(x):
+        return _ag().NhwcToNchw.apply(x, c)
+    return ops.nhwc_to_nchw(x, c)
+
+
+def conv_in(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
+    if _needs_grad(x, w, b):
+        return _ag().ConvIn.apply(x, w, b)
+    return ops.conv_in(x, w, b)
+
+
+def mtgemm(plan, a0: Tensor, w: Tensor, **kw) -> Tensor:
+    if _needs_grad(a0, w, kw.get("a1"), kw.get("bias"), kw.get("residual")):
+        return _ag().mtgemm(plan, a0, w, **kw)
+    return ops.mtgemm(plan, a0, w, **kw)
+
+
+def linear(x: Tensor, w: Tensor, plan, **kw) -> Tensor:
+    lead = x.shape[:-1]
+    m = x.numel() // x.shape[-1]
+    res = kw.pop("residual", None)
+    if res is not None:
+        res = res.reshape(1, 1, m, w.shape[0])
+    y = mtgemm(plan, x.reshape(1, 1, m, x.shape[-1]), w, out_shape=(1, 1, m, w.shape[0]), residual=res, **kw)
+    return y.reshape(*lead, w.shape[0])
+
+
+def groupnorm_silu(x: Tensor, gamma: Tensor, beta: Tensor, silu: bool = True) -> Tensor:
+    if _needs_grad(x, gamma, beta):
+        return _ag().GroupNormSilu.apply(x, gamma, beta, silu)
+    return ops.groupnorm_silu(x, gamma, beta, silu=silu)
+
+
+def row_stats(x: Tensor, w1: Optional[Tensor] = None):
+    return ops.row_stats(x, w1)
+
+
+def attention(qkv: Tensor, B: int, S: int, C: int) -> Tensor:
+    if _needs_grad(qkv):
+        return _ag().Attention.apply(qkv, B, S, C)
+    return ops.attn_fwd(qkv, B, S, C)[0]
+
+
+def reparam(mu: Tensor, logvar: Tensor, eps: Tensor, patched: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    if _needs_grad(mu, logvar):
+        return _ag().Reparam.apply(mu, logvar, eps, patched)
+    return ops.reparam(mu, logvar, eps, patched)

@@ -1,0 +1,122 @@
+"""ResBlock, TransVAEBlock, RMSNorm -- B200-native mirrors of transvae/modules/blocks.py.
+
+Parameter names / shapes equal the reference's (state_dict compatible).  Forward math:
+  ResBlock      (blocks.py:48-68):   x + conv2(silu(GN2(conv1(silu(GN1(x))))))
+  TransVAEBlock (blocks.py:135-151): x += attn(RMSNorm1(x)); x += ffn(RMSNorm2(x))
+  RMSNorm       (blocks.py:168-204): x / sqrt(mean_c(x^2) + 1e-6) * w
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import _taps as T
+from .. import kernels as K
+from .._pack import bf16c, f32c
+from ._base import HotModule
+from .attention import FlashAttentionWithRoPE
+from .conv import ConvFFN
+
+
+class _Conv2dParams(nn.Module):
+    """Holds ``weight`` [O, I, k, k] and ``bias`` [O] under the reference's names (nn.Conv2d defaults for init)."""
+
+    def __init__(self, cin: int, cout: int, k: int):
+        super().__init__()
+        self.in_channels, self.out_channels, self.kernel_size = cin, cout, (k, k)
+        ref = nn.Conv2d(cin, cout, k)
+        self.weight = nn.Parameter(ref.weight.detach().clone())
+        self.bias = nn.Parameter(ref.bias.detach().clone())
+
+    def extra_repr(self):
+        return f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}"
+
+
+class _LinearParams(nn.Module):
+    def __init__(self, cin: int, cout: int, bias: bool = True):
+        super().__init__()
+        self.in_features, self.out_features = cin, cout
+        ref = nn.Linear(cin, cout, bias=bias)
+        self.weight = nn.Parameter(ref.weight.detach().clone())
+        if bias:
+            self.bias = nn.Parameter(ref.bias.detach().clone())
+        else:
+            self.register_parameter("bias", None)
+
+    def extra_repr(self):
+        return f"{self.in_features}, {self.out_features}, bias={self.bias is not None}"
+
+
+class _NormParams(nn.Module):
+    """weight / bias of a GroupNorm or LayerNorm."""
+
+    def __init__(self, dim: int, groups: int = 0, eps: float = 1e-5):
+        super().__init__()
+        self.num_channels, self.num_groups, self.eps = dim, groups, eps
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.bias = nn.Parameter(torch.zeros(dim))
+
+
+class ResBlock(HotModule):
+    def __init__(self, in_channels: int, out_channels: int, use_conv_shortcut: bool = False):
+        super().__init__()
+        if in_channels != out_channels:
+            raise NotImplementedError("ResBlock with in_channels != out_channels is not reachable from the shipped "
+                                      "configs (encoder.py:70) and is not built on the B200 path yet")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.norm1 = _NormParams(in_channels, 32)
+        self.conv1 = _Conv2dParams(in_channels, out_channels, 3)
+        self.norm2 = _NormParams(out_channels, 32)
+        self.conv2 = _Conv2dParams(out_channels, out_channels, 3)
+        self.shortcut = nn.Identity()
+
+    def forward_nhwc(self, x: torch.Tensor) -> torch.Tensor:
+        B, H, W, C = x.shape
+        plan = T.plan_conv3x3(C)
+        w1 = self._packs.get("w1", [self.conv1.weight], lambda: bf16c(T.pack_conv3x3(self.conv1.weight)))
+        w2 = self._packs.get("w2", [self.conv2.weight], lambda: bf16c(T.pack_conv3x3(self.conv2.weight)))
+        h = K.groupnorm_silu(x, self.norm1.weight, self.norm1.bias)
+        h = K.mtgemm(plan, h, w1, out_shape=(B, H, W, C), bias=f32c(self.conv1.bias))
+        h = K.groupnorm_silu(h, self.norm2.weight, self.norm2.bias)
+        return K.mtgemm(plan, h, w2, out_shape=(B, H, W, C), bias=f32c(self.conv2.bias), residual=x)
+
+
+class RMSNorm(nn.Module):
+    """Channel RMSNorm.  Inside TransVAEBlock it is never materialised: the per-token 1/rms comes from the
+    ``tvae_row_stats`` kernel and the weight is folded into the following projection.  The standalone
+    ``forward`` (reference signature, not on the hot path) applies the same statistics kernel."""
+
+    def __init__(self, dim: int, eps: float = 1e-6):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(dim))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() == 4:
+            xn = K.nchw_to_nhwc(x, x.shape[1])
+            rstd, _ = K.row_stats(xn)
+            B, C, H, W = x.shape
+            return (x * rstd.view(B, 1, H, W) * self.weight.view(1, -1, 1, 1)).to(x.dtype)
+        if x.dim() == 3:
+            rstd, _ = K.row_stats(x.to(torch.bfloat16).contiguous())
+            return (x * rstd.view(*x.shape[:-1], 1) * self.weight).to(x.dtype)
+        raise ValueError(f"RMSNorm expects 3D or 4D input, got {x.dim()}D")
+
+
+class TransVAEBlock(HotModule):
+    def __init__(self, dim: int, mlp_ratio: float = 1.0, head_dim: int = 64, use_rope: bool = True,
+                 use_conv_ffn: bool = True, dropout: float = 0.0):
+        super().__init__()
+        if not use_conv_ffn:
+            raise NotImplementedError("use_conv_ffn=False (plain FFN ablation) is not built on the B200 path yet")
+        if dropout != 0.0:
+            raise NotImplementedError("dropout > 0 is not used by any shipped config and is not built")
+        self.dim, self.mlp_ratio = dim, mlp_ratio
+        self.norm1 = RMSNorm(dim)
+        self.attn = FlashAttentionWithRoPE(dim=dim, head_dim=head_dim, use_rope=use_rope, dropout=dropout)
+        self.norm2 = RMSNorm(dim)
+        self.ffn = ConvFFN(dim=dim, mlp_ratio=mlp_ratio, dropout=dropout)
+
+    def forward_nhwc(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.attn.forward_fused(x, self.norm1.weight)      # x + attn(norm1(x))
+        return self.ffn.forward_fused(x, self.norm2.weight)    # x + ffn(norm2(x))

@@ -1,0 +1,62 @@
+"""ConvFFN -- B200-native mirror of transvae/modules/conv.py (conv_type='full', the only variant the shipped
+configs reach; conv.py:30, blocks.py:119-123).
+
+forward (conv.py:79-105):  u = gelu(proj_in(x));  u = u + conv(u),  conv = 1x1 -> GELU -> 3x3 -> GELU -> 1x1;
+out = proj_out(u).  Five tcgen05 GEMM launches with bias / GELU / residual fused into the epilogues; the
+preceding RMSNorm is folded into proj_in (row scale 1/rms in the epilogue, weight into the columns).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import _taps as T
+from .. import kernels as K
+from .._pack import bf16c, f32c
+from ._base import HotModule
+
+
+class ConvFFN(HotModule):
+    def __init__(self, dim: int, mlp_ratio: float = 1.0, conv_type: str = "full", dropout: float = 0.0):
+        super().__init__()
+        from .blocks import _Conv2dParams, _LinearParams
+        if conv_type != "full":
+            raise NotImplementedError("only conv_type='full' (the reference default) is built on the B200 path")
+        self.dim = dim
+        hidden = int(dim * mlp_ratio * 4)
+        mid = int(dim * mlp_ratio)
+        self.hidden_dim, self.conv_hidden = hidden, mid
+        self.proj_in = _LinearParams(dim, hidden)
+        self.conv = nn.Sequential(_Conv2dParams(hidden, mid, 1), nn.GELU(), _Conv2dParams(mid, mid, 3), nn.GELU(),
+                                  _Conv2dParams(mid, hidden, 1))
+        self.proj_out = _LinearParams(hidden, dim)
+        self.dropout = nn.Dropout(dropout)
+
+    def forward_fused(self, x: torch.Tensor, w2) -> torch.Tensor:
+        """x + ffn(RMSNorm(x; w2)) for NHWC bf16 x; ``w2 is None`` = no norm (bare module)."""
+        B, H, W, C = x.shape
+        M = B * H * W
+        hid, mid = self.hidden_dim, self.conv_hidden
+        xf = x.reshape(M, C)
+        if w2 is not None:
+            w_in = self._packs.get("in", [self.proj_in.weight, w2], lambda: bf16c(self.proj_in.weight * w2))
+            rstd, _ = K.row_stats(x)
+        else:
+            w_in = self._packs.get("in_raw", [self.proj_in.weight], lambda: bf16c(self.proj_in.weight))
+            rstd = None
+        u = K.linear(xf, w_in, T.plan_linear(C), bias=f32c(self.proj_in.bias), row_scale=rstd, act=K.ACT_GELU)
+        c0, c2, c4 = self.conv[0], self.conv[2], self.conv[4]
+        w0 = self._packs.get("c0", [c0.weight], lambda: bf16c(T.pack_conv1x1(c0.weight)))
+        w2_ = self._packs.get("c2", [c2.weight], lambda: bf16c(T.pack_conv3x3(c2.weight)))
+        w4 = self._packs.get("c4", [c4.weight], lambda: bf16c(T.pack_conv1x1(c4.weight)))
+        t = K.linear(u, w0, T.plan_linear(hid), bias=f32c(c0.bias), act=K.ACT_GELU)
+        t = K.mtgemm(T.plan_conv3x3(mid), t.reshape(B, H, W, mid), w2_, out_shape=(B, H, W, mid), bias=f32c(c2.bias),
+                     act=K.ACT_GELU)
+        u = K.linear(t.reshape(M, mid), w4, T.plan_linear(mid), bias=f32c(c4.bias), residual=u)
+        wo = self._packs.get("out", [self.proj_out.weight], lambda: bf16c(self.proj_out.weight))
+        y = K.linear(u, wo, T.plan_linear(hid), bias=f32c(self.proj_out.bias), residual=xf)
+        return y.reshape(B, H, W, C)
+
+    def forward_nhwc(self, x: torch.Tensor) -> torch.Tensor:
+        y = self.forward_fused(x, None)
+        return (y.float() - x.float()).to(torch.bfloat16)

@@ -1,0 +1,191 @@
+"""Per-kernel parity on a real B200: every C-ABI entry point against plain fp32 torch ops on the same inputs.
+
+Tolerances: operands are rounded to bf16 once (inputs/weights) and accumulated in fp32 by both sides, outputs are
+bf16 -> max|ours-ref|/max|ref| <= 1e-2 (2 bf16 ulps = 7.8e-3) unless stated.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from transvae import _taps as T  # noqa: E402
+from transvae import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 64), (256, 128, 128), (1000, 192, 192), (4096, 384, 1152),
+                                   (300, 1536, 256), (2048, 768, 3072), (77, 64, 320)])
+def test_gemm_plain(M, K, N):
+    x, w, b = bf(rnd(M, K)), bf(rnd(N, K, seed=1, scale=0.05)), rnd(N, seed=2)
+    y = ops.linear(x, w, T.plan_linear(K), bias=b)
+    ref = x.float() @ w.float().t() + b
+    assert y.shape == (M, N)
+    assert rel(y, ref) < 1e-2, rel(y, ref)
+
+
+def test_gemm_epilogues():
+    M, K, N = 640, 256, 384
+    x, w, b = bf(rnd(M, K)), bf(rnd(N, K, seed=1, scale=0.05)), rnd(N, seed=2)
+    res = bf(rnd(M, N, seed=3))
+    rs, rsh, cs = rnd(M, seed=4).abs() + 0.5, rnd(M, seed=5), rnd(N, seed=6)
+    acc = x.float() @ w.float().t()
+    y = ops.linear(x, w, T.plan_linear(K), bias=b, act=ops.ACT_GELU)
+    assert rel(y, F.gelu(acc + b)) < 1e-2
+    y = ops.linear(x, w, T.plan_linear(K), bias=b, act=ops.ACT_SILU)
+    assert rel(y, F.silu(acc + b)) < 1e-2
+    y = ops.linear(x, w, T.plan_linear(K), bias=b, residual=res)
+    assert rel(y, acc + b + res.float()) < 1e-2
+    y = ops.linear(x, w, T.plan_linear(K), bias=b, row_scale=rs, row_shift=rsh, col_sum=cs, act=ops.ACT_GELU, residual=res)
+    ref = F.gelu(acc * rs[:, None] - rsh[:, None] * cs[None] + b) + res.float()
+    assert rel(y, ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,C,H,W,N", [(2, 64, 16, 16, 64), (1, 192, 128, 128, 192), (3, 128, 32, 32, 256),
+                                       (2, 64, 8, 8, 128), (1, 64, 4, 4, 64), (2, 128, 64, 64, 128)])
+def test_conv3x3(B, C, H, W, N):
+    x, w, b = bf(rnd(B, C, H, W)), bf(rnd(N, C, 3, 3, seed=1, scale=0.05)), rnd(N, seed=2)
+    res = bf(rnd(B, N, H, W, seed=3))
+    y = ops.mtgemm(T.plan_conv3x3(C), nhwc(x), T.pack_conv3x3(w).contiguous(), out_shape=(B, H, W, N), bias=b,
+                   residual=nhwc(res), act=ops.ACT_SILU)
+    ref = F.silu(F.conv2d(x.float(), w.float(), b, padding=1)) + res.float()
+    assert rel(nchw(y), ref) < 1e-2, rel(nchw(y), ref)
+
+
+@pytest.mark.parametrize("B,C,Co,H", [(2, 64, 128, 16), (1, 192, 192, 64), (2, 128, 256, 8)])
+def test_downsample(B, C, Co, H):
+    x, y1 = bf(rnd(B, C, H, H)), bf(rnd(B, C, H, H, seed=9))
+    w2, b2 = bf(rnd(Co, C, 3, 3, seed=1, scale=0.05)), rnd(Co, seed=2)
+    wdc, bdc = bf(rnd(Co, 4 * C, 1, 1, seed=3, scale=0.05)), rnd(Co, seed=4)
+    out = ops.mtgemm(T.plan_downsample(C), nhwc(y1), T.pack_downsample(w2, wdc).contiguous(), a1=nhwc(x),
+                     out_shape=(B, H // 2, H // 2, Co), bias=(b2 + bdc))
+    ref = F.conv2d(y1.float(), w2.float(), b2, stride=2, padding=1) + F.conv2d(F.pixel_unshuffle(x.float(), 2), wdc.float(), bdc)
+    assert rel(nchw(out), ref) < 1e-2, rel(nchw(out), ref)
+
+
+@pytest.mark.parametrize("B,Ci,Co,H", [(2, 128, 64, 8), (1, 192, 192, 64), (2, 256, 128, 4)])
+def test_upsample(B, Ci, Co, H):
+    x = bf(rnd(B, Ci, H, H))
+    w1, b1 = bf(rnd(Co, Ci, 3, 3, seed=1, scale=0.05)), rnd(Co, seed=2)
+    w2, b2 = bf(rnd(Co, Co, 3, 3, seed=3, scale=0.05)), rnd(Co, seed=4)
+    wdc, bdc = bf(rnd(4 * Co, Ci, 1, 1, seed=5, scale=0.05)), rnd(4 * Co, seed=6)
+    xn = nhwc(x)
+    y = ops.mtgemm(T.plan_upsample_conv1(Ci, Co), xn, bf(T.pack_upsample_conv1(w1.float())).contiguous(),
+                   out_shape=(B, 2 * H, 2 * H, Co), bias=b1[None].expand(4, -1).contiguous(), act=ops.ACT_SILU)
+    ref_y = F.silu(F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), w1.float(), b1, padding=1))
+    assert rel(nchw(y), ref_y) < 2e-2, rel(nchw(y), ref_y)   # summed taps are re-rounded to bf16
+    out = ops.mtgemm(T.plan_upsample_conv2(Co, Ci), y, T.pack_upsample_conv2(w2, wdc).contiguous(), a1=xn,
+                     out_shape=(B, 2 * H, 2 * H, Co), bias=T.bias_upsample_conv2(b2, bdc).contiguous())
+    ref = F.conv2d(nchw(y).float(), w2.float(), b2, padding=1) + F.pixel_shuffle(F.conv2d(x.float(), wdc.float(), bdc), 2)
+    assert rel(nchw(out), ref) < 1e-2, rel(nchw(out), ref)
+
+
+def test_direct_fp32_heads():
+    B, C, H = 2, 128, 16
+    x, w, b = bf(rnd(B, C, H, H)), bf(rnd(3, C, 3, 3, seed=1, scale=0.05)), rnd(3, seed=2)
+    out = torch.zeros(B, 3, H, H, device=DEV)
+    bias = torch.zeros(64, device=DEV)
+    bias[:3] = b
+    ops.mtgemm(T.plan_conv3x3(C), nhwc(x), T.pack_conv3x3(w, cout_pad=64).contiguous(), bias=bias, out_f32=out, out_n=3)
+    assert rel(out, F.conv2d(x.float(), w.float(), b, padding=1)) < 2e-3
+
+
+def test_qkv_rope_epilogue():
+    import transvae_oracle as O
+    B, C, H, W = 2, 128, 8, 4
+    S = H * W
+    inv = 1.0 / (10000 ** (torch.arange(0, 32, 2).float() / 32)).to(DEV)
+    x, w = bf(rnd(B * S, C)), bf(rnd(3 * C, C, seed=1, scale=0.1))
+    tab = T.rope_table(H, W, inv)
+    qs = 0.125 * math.log2(math.e)
+    y = ops.linear(x, w, T.plan_linear(C), rope=(tab, C, H, W, qs)).float()
+    ref = (x.float() @ w.float().t()).view(B, S, 3, C // 64, 64).permute(2, 0, 3, 1, 4)   # [3, B, nh, S, 64]
+    q = O.rope2d(ref[0].cpu(), H, W, inv.cpu()).to(DEV) * qs
+    k = O.rope2d(ref[1].cpu(), H, W, inv.cpu()).to(DEV)
+    ours = y.view(B, S, 3, C // 64, 64).permute(2, 0, 3, 1, 4)
+    assert rel(ours[0], q) < 1e-2 and rel(ours[1], k) < 1e-2 and rel(ours[2], ref[2]) < 1e-2
+
+
+@pytest.mark.parametrize("B,S,C", [(2, 256, 128), (1, 1024, 64), (2, 16, 128), (1, 64, 64), (1, 4096, 128), (2, 200, 64)])
+def test_attention_fwd(B, S, C):
+    nh = C // 64
+    qkv = bf(rnd(B, S, 3 * C, scale=1.0))
+    out, lse = ops.attn_fwd(qkv, B, S, C, need_lse=True)
+    t = qkv.float().view(B, S, 3, nh, 64).permute(2, 0, 3, 1, 4)
+    sc = (t[0] @ t[1].transpose(-1, -2)) * math.log(2.0)       # q is pre-scaled to log2 units
+    ref = torch.softmax(sc, dim=-1) @ t[2]
+    ref = ref.permute(0, 2, 1, 3).reshape(B, S, C)
+    assert rel(out, ref) < 2e-2, rel(out, ref)
+    ref_lse = torch.logsumexp(sc, dim=-1) / math.log(2.0)
+    assert float((lse - ref_lse).abs().max()) < 2e-2
+
+
+def test_conv_in():
+    x, w, b = rnd(2, 3, 32, 48), rnd(64, 3, 3, 3, seed=1, scale=0.3), rnd(64, seed=2)
+    y = ops.conv_in(x, w, b)
+    assert rel(nchw(y), F.conv2d(x, w, b, padding=1)) < 8e-3
+
+
+@pytest.mark.parametrize("B,C,H", [(2, 192, 32), (3, 64, 16), (1, 128, 64)])
+def test_groupnorm_silu(B, C, H):
+    x = bf(rnd(B, C, H, H, scale=3.0) + 0.7)
+    g, b = rnd(C, seed=1) * 0.2 + 1, rnd(C, seed=2) * 0.1
+    y = ops.groupnorm_silu(nhwc(x), g, b)
+    ref = F.silu(F.group_norm(x.float(), 32, g, b, 1e-5))
+    assert rel(nchw(y), ref) < 1e-2, rel(nchw(y), ref)
+
+
+def test_row_stats():
+    M, C = 777, 384
+    x = bf(rnd(M, C, scale=4.0) + 0.3)
+    w1 = rnd(C, seed=1) * 0.2 + 1
+    a, _ = ops.row_stats(x)
+    xf = x.float()
+    rms = torch.sqrt((xf ** 2).mean(-1) + 1e-6)
+    assert rel(a, 1 / rms) < 1e-4
+    a, b = ops.row_stats(x, w1)
+    h = xf / rms[:, None] * w1
+    mu, sigma = h.mean(-1), torch.sqrt(h.var(-1, unbiased=False) + 1e-5)
+    assert rel(a, 1 / (sigma * rms)) < 1e-3 and float((b - mu / sigma).abs().max()) < 1e-3
+
+
+def test_layout_reparam_loss():
+    z = rnd(2, 32, 4, 4)
+    zn = ops.nchw_to_nhwc(z, 64)
+    assert zn.shape == (2, 4, 4, 64) and float(zn[..., 32:].abs().max()) == 0
+    assert rel(ops.nhwc_to_nchw(zn, 32), bf(z).float()) == 0
+    mu, lv, eps = rnd(2, 32, 4, 4, scale=40), rnd(2, 32, 4, 4, seed=1, scale=20), rnd(2, 32, 4, 4, seed=2)
+    zz, mo, lo = ops.reparam(mu, lv, eps, patched=True)
+    mc, lc = mu.clamp(-50, 50), lv.clamp(-30, 20)
+    assert rel(zz, mc + eps * torch.exp(0.5 * lc)) < 1e-5 and torch.equal(mo, mc) and torch.equal(lo, lc)
+    recon, tgt = rnd(2, 3, 16, 16, scale=3), torch.rand(2, 3, 16, 16, device=DEV)
+    acc = ops.loss_sums(recon, tgt, mu, lv, patched=True)
+    l1 = (recon.sigmoid() - tgt).abs().sum()
+    kl = (-0.5 * (1 + lc - mu.pow(2) - lc.exp())).sum()
+    assert abs(float(acc[0] - l1)) / float(l1) < 1e-4 and abs(float(acc[1] - kl)) / abs(float(kl)) < 1e-4
+    assert float(acc[2]) == 0
