@@ -215,6 +215,7 @@ int gn_apply_run(const void* x, const float* sums, const float* gamma, const flo
 //   mode 1 (attention, blocks.py:146 RMSNorm followed by the three LayerNorms of attention.py:71-73, which
 //           all see the same input h = x*w1/rms):    out_a = 1/(sigma*rms),  out_b = mu/sigma
 //           with mu = mean(h), sigma = sqrt(var(h) + 1e-5).
+//   mode 2 (bare attention module, no RMSNorm in front): as mode 1 with rms := 1.
 // The normalised tensor is never materialised: the projection GEMM applies out_a / out_b in its epilogue
 // (row_scale / row_shift of tvae_mtgemm) with the norm weights folded into the projection weights.
 // Algorithmic bytes: 2*C per token.
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const uint4* __restrict_
     t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
     t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
     t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
-    if (mode == 1) {
+    if (mode != 0) {
       const float4 wa = __ldg(reinterpret_cast<const float4*>(w1) + 2 * v);
       const float4 wb = __ldg(reinterpret_cast<const float4*>(w1) + 2 * v + 1);
       const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
@@ -253,13 +254,13 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const uint4* __restrict_
     }
   }
   s2 = warp_sum(s2);
-  if (mode == 1) {
+  if (mode != 0) {
     sw = warp_sum(sw);
     sw2 = warp_sum(sw2);
   }
   if (lane == 0) {
     const float invC = 1.0f / (float)C;
-    const float rms = sqrtf(s2 * invC + 1e-6f);
+    const float rms = (mode == 2) ? 1.0f : sqrtf(s2 * invC + 1e-6f);
     if (mode == 0) {
       out_a[row] = 1.0f / rms;
     } else {
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const uint4* __restrict_
 int row_stats_run(const void* x, const float* w1, float* out_a, float* out_b, long long M, int C, int mode,
                   cudaStream_t stream) {
   TVAE_REQUIRE(C % 8 == 0, "row_stats: C=%d must be a multiple of 8", C);
-  TVAE_REQUIRE(mode == 0 || (w1 != nullptr && out_b != nullptr), "row_stats: mode 1 needs w1 and out_b");
+  TVAE_REQUIRE(mode == 0 || (w1 != nullptr && out_b != nullptr), "row_stats: modes 1/2 need w1 and out_b");
   const long long threads = M * 32;
   const int grid = (int)((threads + 255) / 256);
   row_stats_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), w1, out_a, out_b, M, C, mode);

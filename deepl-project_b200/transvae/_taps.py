@@ -40,6 +40,7 @@ class Plan:
     out_split: bool = False
     k_total: int = 0
     name: str = ""
+    algo_k: int = 0   # K per output element at the REFERENCE's cost (2*M*N*algo_k = algorithmic FLOPs)
 
     @property
     def num_phases(self) -> int:
@@ -57,13 +58,13 @@ def _kb(c: int) -> int:
 # ----------------------------------------------------------------------------------------------
 def plan_linear(k: int) -> Plan:
     """nn.Linear / 1x1 conv on a flat [M, K] token matrix."""
-    return Plan([[TapSpec(0, 0, 0, 0, 0, _kb(k), 0)]], [0], [0], k_total=k, name="linear")
+    return Plan([[TapSpec(0, 0, 0, 0, 0, _kb(k), 0)]], [0], [0], k_total=k, name="linear", algo_k=k)
 
 
 def plan_conv3x3(c: int) -> Plan:
     """3x3, stride 1, pad 1 (blocks.py:34,37; conv.py:57; upsample.py:34,97; heads; conv_out)."""
     taps = [TapSpec(0, 0, dx - 1, 0, dy - 1, _kb(c), (dy * 3 + dx) * c) for dy in range(3) for dx in range(3)]
-    return Plan([taps], [0], [0], k_total=9 * c, name="conv3x3")
+    return Plan([taps], [0], [0], k_total=9 * c, name="conv3x3", algo_k=9 * c)
 
 
 def _s2(d: int) -> Tuple[int, int]:
@@ -83,7 +84,7 @@ def plan_downsample(c: int) -> Plan:
     for i in range(2):
         for j in range(2):
             taps.append(TapSpec(1, j * c, 0, i, 0, _kb(c), (9 + i * 2 + j) * c))
-    return Plan([taps], [0], [0], a0_split=True, a1_split=True, k_total=13 * c, name="downsample")
+    return Plan([taps], [0], [0], a0_split=True, a1_split=True, k_total=13 * c, name="downsample", algo_k=13 * c)
 
 
 # nearest-2x followed by 3x3 pad 1: output row 2h+py reads upsampled rows 2h+py+dy-1, i.e. source rows
@@ -106,7 +107,7 @@ def plan_upsample_conv1(cin: int, cout: int) -> Plan:
             phases.append(taps)
             out_p.append(py)
             out_c.append(px * cout)
-    return Plan(phases, out_p, out_c, out_split=True, k_total=16 * cin, name="upsample_conv1")
+    return Plan(phases, out_p, out_c, out_split=True, k_total=16 * cin, name="upsample_conv1", algo_k=9 * cin)
 
 
 def plan_upsample_conv2(cmid: int, cin: int, with_dc: bool = True) -> Plan:
@@ -128,7 +129,8 @@ def plan_upsample_conv2(cmid: int, cin: int, with_dc: bool = True) -> Plan:
             out_p.append(py)
             out_c.append(px * cmid)
     return Plan(phases, out_p, out_c, a0_split=True, out_split=True,
-                k_total=9 * cmid + (4 * cin if with_dc else 0), name="upsample_conv2")
+                k_total=9 * cmid + (4 * cin if with_dc else 0), name="upsample_conv2",
+                algo_k=9 * cmid + (cin if with_dc else 0))
 
 
 # ----------------------------------------------------------------------------------------------

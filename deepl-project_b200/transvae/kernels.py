@@ -17,7 +17,10 @@ Tensor = torch.Tensor
 
 
 def _needs_grad(*ts) -> bool:
-    return torch.is_grad_enabled() and any(t is not None and isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
+    for t in ts:
+        if isinstance(t, torch.Tensor) and not t.is_cuda:
+            raise RuntimeError("TransVAE B200 path needs CUDA tensors on an sm_100 device (there is no CPU fallback)")
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
 
 
 def _ag():
@@ -65,8 +68,8 @@ def groupnorm_silu(x: Tensor, gamma: Tensor, beta: Tensor, silu: bool = True) ->
     return ops.groupnorm_silu(x, gamma, beta, silu=silu)
 
 
-def row_stats(x: Tensor, w1: Optional[Tensor] = None):
-    return ops.row_stats(x, w1)
+def row_stats(x: Tensor, w1: Optional[Tensor] = None, mode: Optional[int] = None):
+    return ops.row_stats(x, w1, mode)
 
 
 def attention(qkv: Tensor, B: int, S: int, C: int) -> Tensor:
@@ -79,3 +82,11 @@ def reparam(mu: Tensor, logvar: Tensor, eps: Tensor, patched: bool) -> Tuple[Ten
     if _needs_grad(mu, logvar):
         return _ag().Reparam.apply(mu, logvar, eps, patched)
     return ops.reparam(mu, logvar, eps, patched)
+
+
+def loss_sums(recon: Tensor, target: Tensor, mu: Tensor, logvar: Tensor, patched: bool, clip=(-30.0, 20.0)):
+    """(sum |f(recon) - target|, sum KL terms, #non-finite terms) as 0-dim fp32 tensors."""
+    if _needs_grad(recon, mu, logvar):
+        return _ag().LossSums.apply(recon, target, mu, logvar, patched, float(clip[0]), float(clip[1]))
+    acc = ops.loss_sums(recon, target, mu, logvar, patched, clip)
+    return acc[0], acc[1], acc[2]

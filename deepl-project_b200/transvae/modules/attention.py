@@ -71,24 +71,23 @@ class FlashAttentionWithRoPE(HotModule):
             return bf16c(W), f32c(cs), f32c(b)
         return self._packs.get("qkv", srcs, make)
 
-    def forward_fused(self, x: torch.Tensor, w1: torch.Tensor) -> torch.Tensor:
-        """x + proj(SDPA(...)) with the preceding RMSNorm (weight ``w1``) folded in.  x: NHWC bf16."""
+    def forward_fused(self, x: torch.Tensor, w1: torch.Tensor, add_residual: bool = True, rms: bool = True) -> torch.Tensor:
+        """x + proj(SDPA(...)) with the preceding RMSNorm (weight ``w1``) folded in.  x: NHWC bf16.
+        ``rms=False``: no RMSNorm in front (bare module); ``add_residual=False``: return the branch only."""
         B, H, W, C = x.shape
         S = H * W
         wqkv, colsum, bias = self._folded(w1)
-        a, b = K.row_stats(x, w1.detach())
+        a, b = K.row_stats(x, w1.detach(), 1 if rms else 2)
         rope = (self._rope_tab(H, W), C, H, W, self.scale * math.log2(math.e))
         qkv = K.linear(x.reshape(B * S, C), wqkv, T.plan_linear(C), bias=bias, row_scale=a, row_shift=b,
                        col_sum=colsum, rope=rope)
         o = K.attention(qkv, B, S, C)
         wp = self._packs.get("proj", [self.proj.weight], lambda: bf16c(self.proj.weight))
-        y = K.linear(o.reshape(B * S, C), wp, T.plan_linear(C), bias=f32c(self.proj.bias), residual=x.reshape(B * S, C))
+        y = K.linear(o.reshape(B * S, C), wp, T.plan_linear(C), bias=f32c(self.proj.bias),
+                     residual=x.reshape(B * S, C) if add_residual else None)
         return y.reshape(B, H, W, C)
 
     def forward_nhwc(self, x: torch.Tensor) -> torch.Tensor:
         """Reference semantics of the bare module (no RMSNorm before, no residual after): attn(x)."""
         ones = torch.ones(self.dim, device=x.device)
-        # RMSNorm with unit weight is NOT the identity, so fold an exact inverse: LN(x) is invariant to a
-        # positive per-token rescale of its input, hence LN(x/rms) == LN(x) up to eps handling.
-        y = self.forward_fused(x, ones)
-        return (y.float() - x.float()).to(torch.bfloat16)
+        return self.forward_fused(x, ones, add_residual=False, rms=False)

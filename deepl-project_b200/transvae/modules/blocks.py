@@ -70,7 +70,7 @@ class ResBlock(HotModule):
         self.conv2 = _Conv2dParams(out_channels, out_channels, 3)
         self.shortcut = nn.Identity()
 
-    def forward_nhwc(self, x: torch.Tensor) -> torch.Tensor:
+    def forward_nhwc(self, x: torch.Tensor, add_residual: bool = True) -> torch.Tensor:
         B, H, W, C = x.shape
         plan = T.plan_conv3x3(C)
         w1 = self._packs.get("w1", [self.conv1.weight], lambda: bf16c(T.pack_conv3x3(self.conv1.weight)))
@@ -78,7 +78,8 @@ class ResBlock(HotModule):
         h = K.groupnorm_silu(x, self.norm1.weight, self.norm1.bias)
         h = K.mtgemm(plan, h, w1, out_shape=(B, H, W, C), bias=f32c(self.conv1.bias))
         h = K.groupnorm_silu(h, self.norm2.weight, self.norm2.bias)
-        return K.mtgemm(plan, h, w2, out_shape=(B, H, W, C), bias=f32c(self.conv2.bias), residual=x)
+        return K.mtgemm(plan, h, w2, out_shape=(B, H, W, C), bias=f32c(self.conv2.bias),
+                        residual=x if add_residual else None)
 
 
 class RMSNorm(nn.Module):

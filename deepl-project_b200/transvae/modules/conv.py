@@ -32,7 +32,7 @@ class ConvFFN(HotModule):
         self.proj_out = _LinearParams(hidden, dim)
         self.dropout = nn.Dropout(dropout)
 
-    def forward_fused(self, x: torch.Tensor, w2) -> torch.Tensor:
+    def forward_fused(self, x: torch.Tensor, w2, add_residual: bool = True) -> torch.Tensor:
         """x + ffn(RMSNorm(x; w2)) for NHWC bf16 x; ``w2 is None`` = no norm (bare module)."""
         B, H, W, C = x.shape
         M = B * H * W
@@ -54,9 +54,8 @@ class ConvFFN(HotModule):
                      act=K.ACT_GELU)
         u = K.linear(t.reshape(M, mid), w4, T.plan_linear(mid), bias=f32c(c4.bias), residual=u)
         wo = self._packs.get("out", [self.proj_out.weight], lambda: bf16c(self.proj_out.weight))
-        y = K.linear(u, wo, T.plan_linear(hid), bias=f32c(self.proj_out.bias), residual=xf)
+        y = K.linear(u, wo, T.plan_linear(hid), bias=f32c(self.proj_out.bias), residual=xf if add_residual else None)
         return y.reshape(B, H, W, C)
 
     def forward_nhwc(self, x: torch.Tensor) -> torch.Tensor:
-        y = self.forward_fused(x, None)
-        return (y.float() - x.float()).to(torch.bfloat16)
+        return self.forward_fused(x, None, add_residual=False)

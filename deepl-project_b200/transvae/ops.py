@@ -19,6 +19,9 @@ BF16 = torch.bfloat16
 
 # launch counter (bench.py reports it as gpu_launches)
 LAUNCHES = 0
+# optional per-launch device timing of the tensor-core kernel (bench.py roofline): list of
+# (name, algorithmic_flops, start_event, end_event); None = off
+PROFILE = None
 
 
 def _stream() -> int:
@@ -54,7 +57,7 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
            out_shape: Optional[Sequence[int]] = None, bias: Optional[Tensor] = None, act: int = ACT_NONE,
            residual: Optional[Tensor] = None, row_scale: Optional[Tensor] = None, row_shift: Optional[Tensor] = None,
            col_sum: Optional[Tensor] = None, rope: Optional[Tuple[Tensor, int, int, int, float]] = None,
-           out_f32: Optional[Tensor] = None, out_n: int = 0) -> Tensor:
+           out_f32: Optional[Tensor] = None, out_f32_shape: Optional[Sequence[int]] = None, out_n: int = 0) -> Tensor:
     """Launch ``tvae_mtgemm``.  a0 / a1 / out / residual are NHWC bf16 4-D tensors (flat matrices as
     [1, 1, M, K]); ``w`` is the packed bf16 [N, K_total] weight; ``bias`` fp32 [phases, N] (or [N])."""
     _need_cuda(a0, w, a1, out, bias, residual, row_scale, row_shift, col_sum, out_f32)
@@ -63,6 +66,8 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
     _set_view(d.a0, a0, plan.a0_split)
     _set_view(d.a1, a1, plan.a1_split)
     n_total = w.shape[0]
+    if out_f32 is None and out_f32_shape is not None:
+        out_f32 = torch.empty(tuple(out_f32_shape), dtype=torch.float32, device=a0.device)
     if out_f32 is None:
         if out is None:
             out = torch.empty(tuple(out_shape), dtype=BF16, device=a0.device)
@@ -100,7 +105,16 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
         d.rope_tab, d.q_scale = None, 1.0
     d.out_f32 = _ptr(out_f32)
     d.out_n = out_n
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(_lib.load().tvae_mtgemm(C.byref(d), _stream()), f"tvae_mtgemm[{plan.name}]")
+    if PROFILE is not None:
+        e1.record()
+        o = out if out_f32 is None else out_f32
+        n_real = out_n if out_f32 is not None else n_total
+        m_out = o.numel() // (o.shape[1] if out_f32 is not None else o.shape[-1])
+        PROFILE.append((plan.name, 2.0 * m_out * n_real * plan.algo_k, e0, e1))
     _count()
     return out if out_f32 is None else out_f32
 
@@ -121,7 +135,13 @@ def attn_fwd(qkv: Tensor, B: int, S: int, C_: int, need_lse: bool = False) -> Tu
     assert qkv.dtype == BF16 and qkv.is_contiguous() and qkv.numel() == B * S * 3 * C_
     out = torch.empty(B, S, C_, dtype=BF16, device=qkv.device)
     lse = torch.empty(B, C_ // 64, S, dtype=torch.float32, device=qkv.device) if need_lse else None
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(_lib.load().tvae_attn_fwd(qkv.data_ptr(), out.data_ptr(), _ptr(lse), B, S, C_, _stream()), "tvae_attn_fwd")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append(("attn_fwd", 4.0 * B * S * S * C_, e0, e1))
     _count()
     return out, lse
 
@@ -167,16 +187,19 @@ def groupnorm_silu(x: Tensor, gamma: Tensor, beta: Tensor, groups: int = 32, eps
     return y
 
 
-def row_stats(x: Tensor, w1: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
-    """mode 0 (w1 None): rstd of RMSNorm.  mode 1: (1/(sigma*rms), mu/sigma) of LayerNorm(RMSNorm(x)*w1)."""
+def row_stats(x: Tensor, w1: Optional[Tensor] = None, mode: Optional[int] = None) -> Tuple[Tensor, Optional[Tensor]]:
+    """mode 0 (w1 None): rstd of RMSNorm.  mode 1: (1/(sigma*rms), mu/sigma) of LayerNorm(RMSNorm(x)*w1).
+    mode 2: (1/sigma, mu/sigma) of LayerNorm(x*w1) (no RMSNorm in front)."""
     _need_cuda(x, w1)
     assert x.dtype == BF16 and x.is_contiguous()
     C_ = x.shape[-1]
     M = x.numel() // C_
+    if mode is None:
+        mode = 0 if w1 is None else 1
     a = torch.empty(M, dtype=torch.float32, device=x.device)
-    b = torch.empty(M, dtype=torch.float32, device=x.device) if w1 is not None else None
+    b = torch.empty(M, dtype=torch.float32, device=x.device) if mode != 0 else None
     w1f = None if w1 is None else w1.float().contiguous()
-    _lib.check(_lib.load().tvae_row_stats(x.data_ptr(), _ptr(w1f), a.data_ptr(), _ptr(b), M, C_, 0 if w1 is None else 1,
+    _lib.check(_lib.load().tvae_row_stats(x.data_ptr(), _ptr(w1f), a.data_ptr(), _ptr(b), M, C_, mode,
                                           _stream()), "tvae_row_stats")
     _count()
     return a, b

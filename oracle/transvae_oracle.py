@@ -182,7 +182,7 @@ def init_state_dict(cfg: dict, seed: int = 0, mode: str = "reference") -> StateD
             fan_out = shape[0] * shape[2] * shape[3]
             t = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_out)
         elif kind == "linear":
-            t = torch.randn(shape, generator=g).clamp_(-2.0, 2.0) * 0.02
+            t = (torch.randn(shape, generator=g) * 0.02).clamp_(-2.0, 2.0)   # trunc_normal_(std=.02, a=-2, b=2)
         elif kind == "norm_w":
             t = torch.ones(shape)
             if mode == "tamed":

@@ -1,0 +1,164 @@
+"""Model-level parity on a real B200 against the golden reference outputs and the oracle.
+
+Tolerances (BASELINE.json north_star): bf16 activations within 2e-2 max relative error per block -- checked on
+the block output AND on the residual branch, each block fed with the oracle's fp32 input so errors do
+not accumulate; reconstruction PSNR within 0.05 dB of the fp32 reference.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import transvae_oracle as O  # noqa: E402
+from util import build_model, load_golden, nchw_f32, nhwc_bf16, rel  # noqa: E402
+
+BLOCK_TOL = 2e-2
+PSNR_TOL = 0.05
+
+
+def psnr_pair(recon, x):
+    return O.psnr(recon.clamp(0, 1), x), O.psnr(recon.sigmoid(), x)
+
+
+@pytest.mark.parametrize("name", ["mini_ref", "mini_tamed", "mini_tamed_128"])
+def test_golden_encode_decode(name):
+    blob, sd = load_golden(name)
+    m = build_model(blob["cfg"], sd)
+    x = blob["x"].cuda()
+    with torch.no_grad():
+        mu, logvar = m.encode(x)
+        recon = m.decode(blob["mu"].cuda())          # decoder fed with the reference's mu: isolates the decoder
+        recon_e2e = m.decode(mu)
+    e = dict(mu=rel(mu, blob["mu"]), logvar=rel(logvar, blob["logvar"]), recon=rel(recon, blob["recon_from_mu"]),
+             recon_e2e=rel(recon_e2e, blob["recon_from_mu"]))
+    print(name, e)
+    assert mu.dtype == torch.float32 and mu.shape == blob["mu"].shape and recon.shape == blob["x"].shape
+    assert e["mu"] < 5e-2 and e["logvar"] < 5e-2 and e["recon"] < 5e-2 and e["recon_e2e"] < 8e-2, e
+    for ours, ref in zip(psnr_pair(recon_e2e.cpu(), blob["x"]), psnr_pair(blob["recon_from_mu"], blob["x"])):
+        assert abs(ours - ref) < PSNR_TOL, (ours, ref)
+
+
+@pytest.mark.parametrize("name", ["mini_ref", "mini_tamed"])
+def test_golden_patched_forward_and_loss(name):
+    import transvae
+    blob, sd = load_golden(name)
+    m = build_model(blob["cfg"], sd, patched=True)
+    x = blob["x"].cuda()
+    with torch.no_grad():
+        recon, mu, logvar = m(x, eps=blob["eps"].cuda())
+        out = m(x, return_dict=True, eps=blob["eps"].cuda())
+        loss = transvae.TransVAELoss(l1_weight=1.0, lpips_weight=0.0, kl_weight=1e-8, vf_weight=0.0, gan_weight=0.0)(
+            recon, x, mu, logvar)
+    assert set(out) == {"reconstruction", "mu", "logvar", "z"}
+    assert float(mu.abs().max()) <= 50 and float(logvar.max()) <= 20 and float(logvar.min()) >= -30
+    e = dict(recon=rel(recon, blob["recon_patched"]), mu=rel(mu, blob["mu_patched"]), logvar=rel(logvar, blob["logvar_patched"]))
+    print(name, e, float(loss["total"]), float(blob["loss_total"]))
+    if name == "mini_tamed":
+        assert e["recon"] < 8e-2 and e["mu"] < 5e-2 and e["logvar"] < 5e-2, e
+        assert abs(float(loss["l1"]) - float(blob["loss_l1"])) < 2e-3
+        assert abs(float(loss["kl"]) - float(blob["loss_kl"])) <= 5e-2 * abs(float(blob["loss_kl"])) + 1e-12
+    assert torch.isfinite(recon).all() and set(loss) == {"l1", "lpips", "kl", "vf", "gan", "total"}
+    # the loss kernel itself, on the reference's tensors: exact formula check
+    with torch.no_grad():
+        l2 = transvae.TransVAELoss(lpips_weight=0.0, vf_weight=0.0, gan_weight=0.0)(
+            blob["recon_patched"].cuda(), x, blob["mu_patched"].cuda(), blob["logvar_patched"].cuda())
+    assert abs(float(l2["l1"]) - float(blob["loss_l1"])) < 1e-5
+    assert abs(float(l2["kl"]) - float(blob["loss_kl"])) <= 1e-4 * abs(float(blob["loss_kl"]))
+
+
+@pytest.mark.parametrize("name", ["mini_ref", "mini_tamed", "mini_tamed_128"])
+def test_per_block_parity(name):
+    """Every block of the model, fed with the ORACLE's input for that block, within 2e-2 on output and branch."""
+    blob, sd = load_golden(name)
+    cfg = blob["cfg"]
+    m = build_model(cfg, sd)
+    tr = {}
+    with torch.no_grad():
+        mu_o, _ = O.encode(sd, cfg, blob["x"], tr)
+        O.decode(sd, cfg, mu_o, tr)
+    worst = {}
+
+    def check(key, ours_nhwc, ref):
+        worst[key] = rel(nchw_f32(ours_nhwc), ref)
+
+    with torch.no_grad():
+        for side, mod in (("encoder", m.encoder), ("decoder", m.decoder)):
+            prev = tr[f"{side}.conv_in"]
+            n_res = (0, 1) if side == "encoder" else (len(cfg["depths"]) - 2, len(cfg["depths"]) - 1)
+            for i, stage in enumerate(mod.stages):
+                for j, block in enumerate(stage):
+                    key = f"{side}.stages.{i}.{j}"
+                    xin = nhwc_bf16(prev).cuda()
+                    check(key, block.forward_nhwc(xin), tr[key])
+                    # residual branches in isolation (the stream dwarfs them)
+                    if i in n_res:
+                        check(key + "#branch", block.forward_nhwc(xin, add_residual=False), tr[key + ".branch"])
+                    else:
+                        a = block.attn.forward_fused(xin, block.norm1.weight, add_residual=False)
+                        check(key + "#attn_branch", a, tr[key + ".attn_branch"])
+                        x1 = nhwc_bf16(prev + tr[key + ".attn_branch"]).cuda()
+                        f = block.ffn.forward_fused(x1, block.norm2.weight, add_residual=False)
+                        check(key + "#ffn_branch", f, tr[key + ".ffn_branch"])
+                    prev = tr[key]
+                samplers = mod.downsamples if side == "encoder" else mod.upsamples
+                if i < len(samplers):
+                    key = f"{side}.{'downsamples' if side == 'encoder' else 'upsamples'}.{i}"
+                    check(key, samplers[i].forward_nhwc(nhwc_bf16(prev).cuda()), tr[key])
+                    prev = tr[key]
+    bad = {k: v for k, v in worst.items() if v > BLOCK_TOL}
+    print(name, "worst block error:", max(worst.items(), key=lambda kv: kv[1]))
+    assert not bad, bad
+
+
+def test_public_module_forward_nchw():
+    """The reference's per-module public signature (NCHW in, NCHW out) on a bare block / attention / FFN."""
+    blob, sd = load_golden("mini_tamed")
+    cfg = blob["cfg"]
+    m = build_model(cfg, sd)
+    x = torch.randn(2, 64, 16, 16, generator=torch.Generator().manual_seed(3)) * 2
+    with torch.no_grad():
+        for key, mod, ref in [
+            ("block", m.encoder.stages[2][0], O.transvae_block(sd, "encoder.stages.2.0.", x, 64)),
+            ("attn", m.encoder.stages[2][0].attn, O.attention(sd, "encoder.stages.2.0.attn.", x, 64)),
+            ("ffn", m.encoder.stages[2][0].ffn, O.conv_ffn(sd, "encoder.stages.2.0.ffn.", x)),
+            ("res", m.encoder.stages[0][0], O.resblock(sd, "encoder.stages.0.0.", x)),
+            ("down", m.encoder.downsamples[2], O.downsample(sd, "encoder.downsamples.2.", x)),
+            ("rms", m.encoder.stages[2][0].norm1, O.rmsnorm(x, sd["encoder.stages.2.0.norm1.weight"])),
+        ]:
+            out = mod(x.cuda())
+            assert out.shape == ref.shape and out.dtype == torch.float32
+            assert rel(out, ref) < BLOCK_TOL, (key, rel(out, ref))
+
+
+def test_resolutions_and_batch_shapes():
+    """T/test_installation.py:90-113 (resolutions 128/256/512 -> latent H/16) on the tiny variant."""
+    import transvae
+    torch.manual_seed(0)
+    m = transvae.TransVAE(variant="tiny", compression_ratio=16, latent_dim=32, input_resolution=256).cuda().eval()
+    with torch.no_grad():
+        for res, B in ((128, 3), (256, 2), (512, 1)):
+            x = torch.rand(B, 3, res, res, device="cuda")
+            mu, logvar = m.encode(x)
+            assert mu.shape == (B, 32, res // 16, res // 16) == logvar.shape
+            rec = m.decode(mu)
+            assert rec.shape == x.shape and torch.isfinite(rec).all()
+
+
+def test_large_f16d32_parity_at_256():
+    """BASELINE.json configs[1] model at full size (B=1 so the CPU oracle finishes in seconds)."""
+    cfg = O.variant_config("large")
+    sd = O.init_state_dict(cfg, seed=0, mode="reference")
+    m = build_model(cfg, sd)
+    x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        mu_o, lv_o = O.encode(sd, cfg, x)
+        rec_o = O.decode(sd, cfg, mu_o)
+        mu, lv = m.encode(x.cuda())
+        rec = m.decode(mu)
+        rec_dec = m.decode(mu_o.cuda())
+    e = dict(mu=rel(mu, mu_o), logvar=rel(lv, lv_o), recon_e2e=rel(rec, rec_o), recon_dec=rel(rec_dec, rec_o))
+    print("large@256:", e)
+    assert max(e.values()) < 8e-2, e
+    for ours, ref in zip(psnr_pair(rec.cpu(), x), psnr_pair(rec_o, x)):
+        print("PSNR ours/ref", ours, ref)
+        assert abs(ours - ref) < PSNR_TOL
