@@ -229,7 +229,7 @@ def run_ours(args, rank, world, local):
     pk = peaks()
     by = {}
     for name, fl, a, b in prof:
-        d = by.setdefault("attn_fwd" if name == "attn_fwd" else "mtgemm", [0.0, 0.0, 0])
+        d = by.setdefault("attn_fwd" if name.startswith("attn_fwd") else "mtgemm", [0.0, 0.0, 0])
         d[0] += fl
         d[1] += a.elapsed_time(b)
         d[2] += 1
@@ -239,9 +239,9 @@ def run_ours(args, rank, world, local):
             d = tab.setdefault((name, round(fl / 1e9, 1)), [0.0, 0])
             d[0] += a.elapsed_time(b)
             d[1] += 1
-        print("kernel               GFLOP/launch   launches/step   ms/step   TFLOP/s", file=sys.stderr)
+        print(f"{'kernel':78s} GFLOP/launch launches/step   ms/step   TFLOP/s", file=sys.stderr)
         for (name, gf), (t, n) in sorted(tab.items(), key=lambda kv: -kv[1][0]):
-            print(f"{name:20s} {gf:12.1f} {n // 2:10d} {t / 2:14.3f} {gf * n / t if t else 0:9.1f}", file=sys.stderr)
+            print(f"{name:78s} {gf:10.1f} {n // 2:8d} {t / 2:12.3f} {gf * n / t if t else 0:9.1f}", file=sys.stderr)
     gm = by.get("mtgemm", [0.0, 1e-9, 0])
     at = by.get("attn_fwd", [0.0, 1e-9, 0])
     step_ms_prof = sum(a.elapsed_time(b) for _, _, a, b in prof) / 2

@@ -18,6 +18,32 @@ int reparam_run(const float* mu, const float* logvar, const float* eps, float* z
                 long long n, int patched, cudaStream_t stream);
 int loss_run(const float* recon, const float* target, const float* mu, const float* logvar, float* acc,
              long long n_img, long long n_lat, int patched, float clip_lo, float clip_hi, cudaStream_t stream);
+int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, cudaStream_t stream);
+int bias_act_bwd_run(const void* dy, const void* z, void* dz, float* colsum, long long R0, int Pn, int R1, int Q, int act,
+                     cudaStream_t stream);
+int bias_act_bwd_matrix_run(const void* dy, const void* z, void* dz, float* colsum, long long M, int N, int act,
+                            cudaStream_t stream);
+int act_fwd_run(const void* z, void* y, long long n, int act, cudaStream_t stream);
+int gn_bwd_run(const void* x, const void* dh, const void* add, const float* sums, const float* gamma, const float* beta,
+               float* part, void* dx, int B, int HW, int C, int G, float eps, int apply_silu, cudaStream_t stream);
+int token_norm_fwd_run(const void* x, const float* w, void* y, long long M, int C, int mode, cudaStream_t stream);
+int token_norm_bwd_run(const void* x, const float* w, const void* dy, const void* add, void* dx, float* dw, long long M,
+                       int C, int mode, cudaStream_t stream);
+int attn_delta_run(const void* o, const void* dout, float* delta, int B, int S, int C, cudaStream_t stream);
+int attn_bwd_run(const void* qkv, const void* dout, const float* lse, const float* delta, float* dq_acc, void* dqkv, int B,
+                 int S, int C, cudaStream_t stream);
+int rope_bwd_run(const float* dq_acc, void* dqkv, const float* tab, long long M, int C, int H, int W, float q_scale,
+                 cudaStream_t stream);
+int conv_in_wgrad_run(const float* x, const void* dy, float* dw, float* db, int B, int H, int W, int Cout,
+                      cudaStream_t stream);
+int loss_bwd_run(const float* recon, const float* target, const float* mu, const float* logvar, const float* scal,
+                 float* drecon, float* dmu, float* dlv, long long n_img, long long n_lat, int patched, float clip_lo,
+                 float clip_hi, cudaStream_t stream);
+int latent_bwd_run(const float* mu, const float* logvar, const float* eps, const float* dz, const float* dmu_ret,
+                   const float* dlv_ret, float* dmu, float* dlv, long long n, int patched, cudaStream_t stream);
+int sumsq_run(const float* g, long long n, float* out, cudaStream_t stream);
+int adamw_run(float* p, const float* g, float* m, float* v, long long n, const float* ctrl, float lr, float b1, float b2,
+              float eps, float wd, int step, cudaStream_t stream);
 }  // namespace tvae
 
 using namespace tvae;
@@ -91,6 +117,57 @@ int tvae_reparam(const float* mu, const float* logvar, const float* eps, float* 
 int tvae_loss_l1_kl(const float* recon, const float* target, const float* mu, const float* logvar, float* acc,
                     int64_t n_img, int64_t n_lat, int32_t patched, float clip_lo, float clip_hi, void* stream) {
   GUARD(); return loss_run(recon, target, mu, logvar, acc, n_img, n_lat, patched, clip_lo, clip_hi, S_(stream));
+}
+
+int tvae_mtgemm_wgrad(const tvae_mtgemm_desc* desc, float* dw, void* stream) { GUARD(); return mtwgrad_run(desc, dw, S_(stream)); }
+int tvae_bias_act_bwd(const void* dy, const void* z, void* dz, float* colsum, int64_t M, int32_t N, int32_t act, void* stream) {
+  GUARD(); return bias_act_bwd_matrix_run(dy, z, dz, colsum, M, N, act, S_(stream));
+}
+int tvae_bias_act_bwd_4d(const void* dy, const void* z, void* dz, float* colsum, int64_t R0, int32_t P, int32_t R1, int32_t Q,
+                         int32_t act, void* stream) {
+  GUARD(); return bias_act_bwd_run(dy, z, dz, colsum, R0, P, R1, Q, act, S_(stream));
+}
+int tvae_act_fwd(const void* z, void* y, int64_t n, int32_t act, void* stream) { GUARD(); return act_fwd_run(z, y, n, act, S_(stream)); }
+int tvae_groupnorm_bwd(const void* x, const void* dh, const void* add, const float* sums, const float* gamma, const float* beta,
+                       float* part, void* dx, int32_t B, int32_t HW, int32_t C, int32_t G, float eps, int32_t apply_silu,
+                       void* stream) {
+  GUARD(); return gn_bwd_run(x, dh, add, sums, gamma, beta, part, dx, B, HW, C, G, eps, apply_silu, S_(stream));
+}
+int tvae_token_norm_fwd(const void* x, const float* w, void* y, int64_t M, int32_t C, int32_t mode, void* stream) {
+  GUARD(); return token_norm_fwd_run(x, w, y, M, C, mode, S_(stream));
+}
+int tvae_token_norm_bwd(const void* x, const float* w, const void* dy, const void* add, void* dx, float* dw, int64_t M,
+                        int32_t C, int32_t mode, void* stream) {
+  GUARD(); return token_norm_bwd_run(x, w, dy, add, dx, dw, M, C, mode, S_(stream));
+}
+int tvae_attn_delta(const void* out, const void* dout, float* delta, int32_t B, int32_t S, int32_t C, void* stream) {
+  GUARD(); return attn_delta_run(out, dout, delta, B, S, C, S_(stream));
+}
+int tvae_attn_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, float* dq_acc, void* dqkv, int32_t B,
+                  int32_t S, int32_t C, void* stream) {
+  GUARD(); return attn_bwd_run(qkv, dout, lse, delta, dq_acc, dqkv, B, S, C, S_(stream));
+}
+int tvae_rope_bwd(const float* dq_acc, void* dqkv, const float* rope_tab, int64_t M, int32_t C, int32_t H, int32_t W,
+                  float q_scale, void* stream) {
+  GUARD(); return rope_bwd_run(dq_acc, dqkv, rope_tab, M, C, H, W, q_scale, S_(stream));
+}
+int tvae_conv_in_wgrad(const float* x, const void* dy, float* dw, float* db, int32_t B, int32_t H, int32_t W, int32_t Cout,
+                       void* stream) {
+  GUARD(); return conv_in_wgrad_run(x, dy, dw, db, B, H, W, Cout, S_(stream));
+}
+int tvae_loss_bwd(const float* recon, const float* target, const float* mu, const float* logvar, const float* scal,
+                  float* drecon, float* dmu, float* dlogvar, int64_t n_img, int64_t n_lat, int32_t patched, float clip_lo,
+                  float clip_hi, void* stream) {
+  GUARD(); return loss_bwd_run(recon, target, mu, logvar, scal, drecon, dmu, dlogvar, n_img, n_lat, patched, clip_lo, clip_hi, S_(stream));
+}
+int tvae_latent_bwd(const float* mu, const float* logvar, const float* eps, const float* dz, const float* dmu_ret,
+                    const float* dlv_ret, float* dmu, float* dlogvar, int64_t n, int32_t patched, void* stream) {
+  GUARD(); return latent_bwd_run(mu, logvar, eps, dz, dmu_ret, dlv_ret, dmu, dlogvar, n, patched, S_(stream));
+}
+int tvae_sumsq(const float* g, int64_t n, float* out, void* stream) { GUARD(); return sumsq_run(g, n, out, S_(stream)); }
+int tvae_adamw(float* p, const float* g, float* m, float* v, int64_t n, const float* ctrl, float lr, float beta1, float beta2,
+               float eps, float weight_decay, int32_t step, void* stream) {
+  GUARD(); return adamw_run(p, g, m, v, n, ctrl, lr, beta1, beta2, eps, weight_decay, step, S_(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,827 @@
+// HBM-bound kernels of the backward pass and the materialised training-path norms (vectorised 128-bit accesses,
+// warp-shuffle / shared-memory reductions, fp32 statistics).  Activations and their gradients are NHWC bf16.
+#include "../../include/transvae_sm100.h"
+#include "common.cuh"
+
+namespace tvae {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+  o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  return o;
+}
+
+// -------------------------------------------------------------------------------------------------
+// dZ = dY * act'(Z)  and  colsum[p][q] += sum dZ  over a 4-D contiguous bf16 tensor [R0, P, R1, Q]
+// (plain [M, N] matrix: R0 = M, P = R1 = 1, Q = N; phase view of [B, 2H, 2W, C]: R0 = B*H, P = 2, R1 = W, Q = 2C).
+// Backward of the bias add + GELU / SiLU epilogues of tvae_mtgemm (conv.py:86,56,58; upsample.py:35,96).
+// Algorithmic bytes per element: 2 (dY) [+ 2 (Z) + 2 (dZ) when act != none].
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bias_act_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ z,
+                                                           uint4* __restrict__ dz, float* __restrict__ colsum,
+                                                           long long R0, int Pn, int R1, int Q, int act,
+                                                           int rows_per_block) {
+  extern __shared__ float s_col[];  // [Pn * Q]
+  const int nvec = Q >> 3;
+  const int ncol = Pn * Q;
+  for (int i = threadIdx.x; i < ncol; i += blockDim.x) s_col[i] = 0.0f;
+  __syncthreads();
+  const int v = threadIdx.x % nvec, rl = threadIdx.x / nvec, rpp = blockDim.x / nvec;
+  // a "row" here is one (r0, p, r1) triple; rows are contiguous Q-vectors
+  const long long nrows = R0 * Pn * R1;
+  const long long r_begin = (long long)blockIdx.x * rows_per_block;
+  const long long r_end = min(nrows, r_begin + rows_per_block);
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.0f;
+  if (rl < rpp) {
+    for (long long r = r_begin + rl; r < r_end; r += rpp) {
+      const int p = (int)((r / R1) % Pn);
+      float g[8];
+      unpack8(__ldg(dy + r * nvec + v), g);
+      if (act != TVAE_ACT_NONE) {
+        float zz[8];
+        unpack8(__ldg(z + r * nvec + v), zz);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] *= (act == TVAE_ACT_GELU) ? gelu_erf_grad(zz[i]) : silu_grad(zz[i]);
+        dz[r * nvec + v] = pack8(g);
+        // the column sums must see the bf16-rounded dZ that the GEMMs will read
+        unpack8(pack8(g), g);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[p & 1][i] += g[i];
+    }
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp)
+      if (pp < Pn)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&s_col[pp * Q + v * 8 + i], acc[pp][i]);
+  }
+  __syncthreads();
+  if (colsum != nullptr)
+    for (int i = threadIdx.x; i < ncol; i += blockDim.x) atomicAdd(colsum + i, s_col[i]);
+}
+
+int bias_act_bwd_run(const void* dy, const void* z, void* dz, float* colsum, long long R0, int Pn, int R1, int Q, int act,
+                     cudaStream_t stream) {
+  TVAE_REQUIRE(Q % 8 == 0 && Q / 8 <= 256 * 8, "bias_act_bwd: Q=%d unsupported", Q);
+  TVAE_REQUIRE(Pn == 1 || Pn == 2, "bias_act_bwd: P must be 1 or 2");
+  TVAE_REQUIRE(act == TVAE_ACT_NONE || (z != nullptr && dz != nullptr), "bias_act_bwd: activation needs z and dz");
+  if (colsum) TVAE_CHECK_CUDA(cudaMemsetAsync(colsum, 0, (size_t)Pn * Q * sizeof(float), stream));
+  const int nvec = Q / 8;
+  int threads = nvec >= 256 ? 256 : (256 / nvec) * nvec;
+  // wide rows: several passes of 256 vectors per row are handled by treating each 256-vector slab as its own column set
+  TVAE_REQUIRE(nvec <= 256 || nvec % 256 == 0, "bias_act_bwd: Q=%d must be <= 2048 or a multiple of 2048", Q);
+  if (nvec > 256) {
+    // split wide matrices into column slabs of 2048: [R0*.., Q] -> treat as Pn=1 rows with stride; simple loop
+    TVAE_REQUIRE(Pn == 1 && R1 == 1, "bias_act_bwd: wide rows only for plain matrices");
+    // handled by the strided kernel below
+  }
+  const long long nrows = R0 * Pn * R1;
+  int rpb = 1024;
+  while (rpb > 32 && (nrows + rpb - 1) / rpb < 2LL * num_sms()) rpb >>= 1;
+  if (nvec <= 256) {
+    const int grid = (int)((nrows + rpb - 1) / rpb);
+    bias_act_bwd_kernel<<<grid, threads, (size_t)Pn * Q * sizeof(float), stream>>>(
+        reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(z), reinterpret_cast<uint4*>(dz), colsum, R0,
+        Pn, R1, Q, act, rpb);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  set_last_error("bias_act_bwd: Q=%d > 2048 must be issued per 2048-column slab by the caller", Q);
+  return -2;
+}
+
+// Strided variant for wide matrices: processes columns [c0, c0+Qs) of a row-major [M, Qfull] matrix.
+__global__ void __launch_bounds__(256) bias_act_bwd_slab_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ z,
+                                                                uint4* __restrict__ dz, float* __restrict__ colsum,
+                                                                long long M, int Qfull, int c0, int Qs, int act,
+                                                                int rows_per_block) {
+  extern __shared__ float s_col[];
+  const int nvec = Qs >> 3, nvf = Qfull >> 3, v0 = c0 >> 3;
+  for (int i = threadIdx.x; i < Qs; i += blockDim.x) s_col[i] = 0.0f;
+  __syncthreads();
+  const int v = threadIdx.x % nvec, rl = threadIdx.x / nvec, rpp = blockDim.x / nvec;
+  const long long r_begin = (long long)blockIdx.x * rows_per_block;
+  const long long r_end = min(M, r_begin + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  if (rl < rpp) {
+    for (long long r = r_begin + rl; r < r_end; r += rpp) {
+      const long long idx = r * nvf + v0 + v;
+      float g[8];
+      unpack8(__ldg(dy + idx), g);
+      if (act != TVAE_ACT_NONE) {
+        float zz[8];
+        unpack8(__ldg(z + idx), zz);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] *= (act == TVAE_ACT_GELU) ? gelu_erf_grad(zz[i]) : silu_grad(zz[i]);
+        dz[idx] = pack8(g);
+        unpack8(pack8(g), g);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += g[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&s_col[v * 8 + i], acc[i]);
+  }
+  __syncthreads();
+  if (colsum != nullptr)
+    for (int i = threadIdx.x; i < Qs; i += blockDim.x) atomicAdd(colsum + c0 + i, s_col[i]);
+}
+
+int bias_act_bwd_matrix_run(const void* dy, const void* z, void* dz, float* colsum, long long M, int N, int act,
+                            cudaStream_t stream) {
+  TVAE_REQUIRE(N % 8 == 0, "bias_act_bwd: N=%d must be a multiple of 8", N);
+  TVAE_REQUIRE(act == TVAE_ACT_NONE || (z != nullptr && dz != nullptr), "bias_act_bwd: activation needs z and dz");
+  if (colsum) TVAE_CHECK_CUDA(cudaMemsetAsync(colsum, 0, (size_t)N * sizeof(float), stream));
+  int rpb = 1024;
+  while (rpb > 32 && (M + rpb - 1) / rpb < 2LL * num_sms()) rpb >>= 1;
+  const int grid = (int)((M + rpb - 1) / rpb);
+  for (int c0 = 0; c0 < N; c0 += 2048) {
+    const int qs = (N - c0) < 2048 ? (N - c0) : 2048;
+    const int nvec = qs / 8;
+    const int threads = nvec >= 256 ? 256 : (256 / nvec) * nvec;
+    bias_act_bwd_slab_kernel<<<grid, threads, (size_t)qs * sizeof(float), stream>>>(
+        reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(z), reinterpret_cast<uint4*>(dz), colsum, M, N,
+        c0, qs, act, rpb);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// y = act(z) elementwise (training path: the GEMM stores the pre-activation z that the backward pass needs, the
+// activation output is produced by this pass).  Algorithmic bytes: 4 per element.
+__global__ void __launch_bounds__(256) act_fwd_kernel(const uint4* __restrict__ z, uint4* __restrict__ y, long long n8,
+                                                      int act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8(__ldg(z + i), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = (act == TVAE_ACT_GELU) ? gelu_erf(f[k]) : silu(f[k]);
+    y[i] = pack8(f);
+  }
+}
+
+int act_fwd_run(const void* z, void* y, long long n, int act, cudaStream_t stream) {
+  TVAE_REQUIRE(n % 8 == 0, "act_fwd: element count must be a multiple of 8");
+  TVAE_REQUIRE(act == TVAE_ACT_GELU || act == TVAE_ACT_SILU, "act_fwd: unknown activation %d", act);
+  int grid = (int)((n / 8 + 255) / 256);
+  if (grid > num_sms() * 16) grid = num_sms() * 16;
+  act_fwd_kernel<<<grid < 1 ? 1 : grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(z), reinterpret_cast<uint4*>(y),
+                                                          n / 8, act);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// GroupNorm(+SiLU) backward.  h = act(y), y = xhat*gamma + beta, xhat = (x - mean_g) * rstd_g.
+//   pass A: part[b][c] = (sum_p dy, sum_p dy*xhat) with dy = dh * act'(y)            (reads x, dh)
+//   pass B: dx = rstd * (dy*gamma - m1_g - xhat*m2_g) [+ add],  m1_g = mean_g(dy*gamma), m2_g = mean_g(dy*gamma*xhat)
+// dgamma[c] = sum_b part[b][c][1], dbeta[c] = sum_b part[b][c][0] (tiny, reduced by the caller).
+// Backward of nn.GroupNorm + F.silu (blocks.py:60-66; decoder.py:128-129).  Algorithmic bytes: 10*C per pixel.
+// -------------------------------------------------------------------------------------------------
+struct GnCoef {
+  float mean, rstd;
+};
+
+__device__ __forceinline__ void gn_group_coef(const float* sums, int b, int G, int g, float inv_n, float eps, float& mean,
+                                              float& rstd) {
+  mean = sums[((size_t)b * G + g) * 2] * inv_n;
+  const float var = fmaxf(sums[((size_t)b * G + g) * 2 + 1] * inv_n - mean * mean, 0.0f);
+  rstd = rsqrtf(var + eps);
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dh,
+                                                            const float* __restrict__ sums,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float* __restrict__ part, int HW, int C, int G, float eps,
+                                                            int apply_silu, int pix_per_block) {
+  const int nvec = C >> 3, cpg = C / G;
+  const int b = blockIdx.y;
+  const int v = threadIdx.x % nvec, pv = threadIdx.x / nvec, ppb = blockDim.x / nvec;
+  const float inv_n = 1.0f / ((float)cpg * (float)HW);
+  float mean[8], rstd[8], ga[8], be[8], s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = v * 8 + i;
+    gn_group_coef(sums, b, G, c / cpg, inv_n, eps, mean[i], rstd[i]);
+    ga[i] = gamma[c];
+    be[i] = beta[c];
+    s1[i] = s2[i] = 0.0f;
+  }
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+  const size_t base = (size_t)b * HW * nvec + v;
+  for (int p = p0 + pv; p < p1; p += ppb) {
+    float xf[8], g[8];
+    unpack8(__ldg(x + base + (size_t)p * nvec), xf);
+    unpack8(__ldg(dh + base + (size_t)p * nvec), g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (xf[i] - mean[i]) * rstd[i];
+      const float dy = apply_silu ? g[i] * silu_grad(fmaf(xh, ga[i], be[i])) : g[i];
+      s1[i] += dy;
+      s2[i] = fmaf(dy, xh, s2[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(part + ((size_t)b * C + v * 8 + i) * 2, s1[i]);
+    atomicAdd(part + ((size_t)b * C + v * 8 + i) * 2 + 1, s2[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dh,
+                                                           const uint4* __restrict__ add, const float* __restrict__ sums,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ part, uint4* __restrict__ dx, int HW,
+                                                           int C, int G, float eps, int apply_silu, int vec_per_block) {
+  extern __shared__ float s_g[];  // per group: m1, m2
+  const int nvec = C >> 3, cpg = C / G;
+  const int b = blockIdx.y;
+  const float inv_n = 1.0f / ((float)cpg * (float)HW);
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float m1 = 0.0f, m2 = 0.0f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      m1 = fmaf(gamma[c], part[((size_t)b * C + c) * 2], m1);
+      m2 = fmaf(gamma[c], part[((size_t)b * C + c) * 2 + 1], m2);
+    }
+    s_g[2 * g] = m1 * inv_n;
+    s_g[2 * g + 1] = m2 * inv_n;
+  }
+  __syncthreads();
+  const int v = threadIdx.x % nvec;
+  float mean[8], rstd[8], ga[8], be[8], m1[8], m2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = v * 8 + i, g = c / cpg;
+    gn_group_coef(sums, b, G, g, inv_n, eps, mean[i], rstd[i]);
+    ga[i] = gamma[c];
+    be[i] = beta[c];
+    m1[i] = s_g[2 * g];
+    m2[i] = s_g[2 * g + 1];
+  }
+  const long long total = (long long)HW * nvec;
+  const long long i0 = (long long)blockIdx.x * vec_per_block, i1 = min(total, i0 + vec_per_block);
+  const size_t off = (size_t)b * total;
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    float xf[8], g[8], r[8];
+    unpack8(__ldg(x + off + i), xf);
+    unpack8(__ldg(dh + off + i), g);
+    if (add != nullptr) unpack8(__ldg(add + off + i), r);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (xf[k] - mean[k]) * rstd[k];
+      const float dy = apply_silu ? g[k] * silu_grad(fmaf(xh, ga[k], be[k])) : g[k];
+      float o = rstd[k] * (dy * ga[k] - m1[k] - xh * m2[k]);
+      if (add != nullptr) o += r[k];
+      g[k] = o;
+    }
+    dx[off + i] = pack8(g);
+  }
+}
+
+int gn_bwd_run(const void* x, const void* dh, const void* add, const float* sums, const float* gamma, const float* beta,
+               float* part, void* dx, int B, int HW, int C, int G, float eps, int apply_silu, cudaStream_t stream) {
+  TVAE_REQUIRE(C % 8 == 0 && C % G == 0 && C / 8 <= 256 && G <= 128, "groupnorm_bwd: unsupported C=%d G=%d", C, G);
+  TVAE_CHECK_CUDA(cudaMemsetAsync(part, 0, (size_t)B * C * 2 * sizeof(float), stream));
+  const int nvec = C / 8;
+  const int threads = (256 / nvec) * nvec;
+  int ppb = 2048;
+  while (ppb > 64 && (long long)((HW + ppb - 1) / ppb) * B < 2LL * num_sms()) ppb >>= 1;
+  dim3 g1((HW + ppb - 1) / ppb, B);
+  gn_bwd_reduce_kernel<<<g1, threads, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dh),
+                                                   sums, gamma, beta, part, HW, C, G, eps, apply_silu, ppb);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  const long long total = (long long)HW * nvec;
+  long long vpb = (long long)threads * 16;
+  while (vpb > threads && ((total + vpb - 1) / vpb) * B < 4LL * num_sms()) vpb >>= 1;
+  vpb = (vpb / threads) * threads;
+  if (vpb < threads) vpb = threads;
+  dim3 g2((unsigned)((total + vpb - 1) / vpb), B);
+  gn_bwd_apply_kernel<<<g2, threads, 2 * G * sizeof(float), stream>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dh), reinterpret_cast<const uint4*>(add), sums,
+      gamma, beta, part, reinterpret_cast<uint4*>(dx), HW, C, G, eps, apply_silu, (int)vpb);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Token norms of the training path (materialised; the inference path folds them into the GEMM epilogue).
+//   mode 0: y = x * rstd * w                                  (RMSNorm, blocks.py:168-201)
+//   mode 1: h = x * rstd * w;  y = (h - mean(h)) / sqrt(var(h) + 1e-5)   (RMSNorm followed by the shared, affine-free
+//           part of the three LayerNorms of attention.py:71-73; their gamma / beta are folded into the projection)
+// One warp per token.  Forward bytes: 4*C per token; backward: 8*C (+2*C when `add`).
+// -------------------------------------------------------------------------------------------------
+constexpr int kMaxVecPerLane = 10;  // C <= 2560
+
+__global__ void __launch_bounds__(256) token_norm_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ w,
+                                                             uint4* __restrict__ y, long long M, int C, int mode) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= M) return;
+  const int nvec = C >> 3;
+  float h[kMaxVecPerLane][8];
+  float s2 = 0.0f;
+  int cnt = 0;
+  for (int v = lane; v < nvec; v += 32, ++cnt) {
+    unpack8(__ldg(x + row * nvec + v), h[cnt]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s2 = fmaf(h[cnt][k], h[cnt][k], s2);
+  }
+  s2 = warp_sum(s2);
+  const float rstd = rsqrtf(s2 / (float)C + 1e-6f);
+  float sm = 0.0f, sq = 0.0f;
+  cnt = 0;
+  for (int v = lane; v < nvec; v += 32, ++cnt) {
+    const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * v);
+    const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
+    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      h[cnt][k] *= rstd * wv[k];
+      sm += h[cnt][k];
+      sq = fmaf(h[cnt][k], h[cnt][k], sq);
+    }
+  }
+  float mu = 0.0f, rs = 1.0f;
+  if (mode == 1) {
+    sm = warp_sum(sm);
+    sq = warp_sum(sq);
+    mu = sm / (float)C;
+    rs = rsqrtf(fmaxf(sq / (float)C - mu * mu, 0.0f) + 1e-5f);
+  }
+  cnt = 0;
+  for (int v = lane; v < nvec; v += 32, ++cnt) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h[cnt][k] = (h[cnt][k] - mu) * rs;
+    y[row * nvec + v] = pack8(h[cnt]);
+  }
+}
+
+int token_norm_fwd_run(const void* x, const float* w, void* y, long long M, int C, int mode, cudaStream_t stream) {
+  TVAE_REQUIRE(C % 8 == 0 && C / 8 <= 32 * kMaxVecPerLane, "token_norm: C=%d unsupported", C);
+  const int grid = (int)((M * 32 + 255) / 256);
+  token_norm_fwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), w, reinterpret_cast<uint4*>(y), M, C,
+                                                  mode);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// dx = d(norm)/dx^T dy [+ add];  dw[c] += sum_rows (...)  (fp32 atomics, one flush per warp).
+__global__ void __launch_bounds__(256) token_norm_bwd_kernel(const uint4* __restrict__ x, const float* __restrict__ w,
+                                                             const uint4* __restrict__ dy, const uint4* __restrict__ add,
+                                                             uint4* __restrict__ dx, float* __restrict__ dw, long long M,
+                                                             int C, int mode, int rows_per_warp) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nvec = C >> 3;
+  float dwacc[kMaxVecPerLane][8];
+#pragma unroll
+  for (int c = 0; c < kMaxVecPerLane; ++c)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dwacc[c][k] = 0.0f;
+  const float invC = 1.0f / (float)C;
+  for (int rr = 0; rr < rows_per_warp; ++rr) {
+    const long long row = warp_id * rows_per_warp + rr;
+    if (row >= M) break;
+    float xr[kMaxVecPerLane][8], g[kMaxVecPerLane][8];
+    float s2 = 0.0f;
+    int cnt = 0;
+    for (int v = lane; v < nvec; v += 32, ++cnt) {
+      unpack8(__ldg(x + row * nvec + v), xr[cnt]);
+      unpack8(__ldg(dy + row * nvec + v), g[cnt]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s2 = fmaf(xr[cnt][k], xr[cnt][k], s2);
+    }
+    s2 = warp_sum(s2);
+    const float rstd = rsqrtf(s2 * invC + 1e-6f);
+    // xr <- xhat_r = x*rstd ; for mode 1 also need h = xhat_r*w, mu, rs
+    float sm = 0.0f, sq = 0.0f;
+    cnt = 0;
+    for (int v = lane; v < nvec; v += 32, ++cnt) {
+      const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * v);
+      const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
+      const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        xr[cnt][k] *= rstd;
+        const float h = xr[cnt][k] * wv[k];
+        sm += h;
+        sq = fmaf(h, h, sq);
+      }
+    }
+    float mu = 0.0f, rs = 1.0f;
+    if (mode == 1) {
+      sm = warp_sum(sm);
+      sq = warp_sum(sq);
+      mu = sm * invC;
+      rs = rsqrtf(fmaxf(sq * invC - mu * mu, 0.0f) + 1e-5f);
+      // LayerNorm (no affine) backward: dh = rs * (g - mean(g) - yhat * mean(g*yhat))
+      float a1 = 0.0f, a2 = 0.0f;
+      cnt = 0;
+      for (int v = lane; v < nvec; v += 32, ++cnt) {
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * v);
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float yh = (xr[cnt][k] * wv[k] - mu) * rs;
+          a1 += g[cnt][k];
+          a2 = fmaf(g[cnt][k], yh, a2);
+        }
+      }
+      a1 = warp_sum(a1) * invC;
+      a2 = warp_sum(a2) * invC;
+      cnt = 0;
+      for (int v = lane; v < nvec; v += 32, ++cnt) {
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * v);
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float yh = (xr[cnt][k] * wv[k] - mu) * rs;
+          g[cnt][k] = rs * (g[cnt][k] - a1 - yh * a2);   // g is now dh
+        }
+      }
+    }
+    // RMSNorm backward: dx = rstd * (dh*w - xhat_r * mean(dh*w*xhat_r));  dw += dh * xhat_r
+    float a3 = 0.0f;
+    cnt = 0;
+    for (int v = lane; v < nvec; v += 32, ++cnt) {
+      const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * v);
+      const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
+      const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        dwacc[cnt][k] = fmaf(g[cnt][k], xr[cnt][k], dwacc[cnt][k]);
+        g[cnt][k] *= wv[k];
+        a3 = fmaf(g[cnt][k], xr[cnt][k], a3);
+      }
+    }
+    a3 = warp_sum(a3) * invC;
+    cnt = 0;
+    for (int v = lane; v < nvec; v += 32, ++cnt) {
+      float r[8];
+      if (add != nullptr) unpack8(__ldg(add + row * nvec + v), r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float o = rstd * (g[cnt][k] - xr[cnt][k] * a3);
+        if (add != nullptr) o += r[k];
+        g[cnt][k] = o;
+      }
+      dx[row * nvec + v] = pack8(g[cnt]);
+    }
+  }
+  int cnt = 0;
+  for (int v = lane; v < nvec; v += 32, ++cnt)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(dw + v * 8 + k, dwacc[cnt][k]);
+}
+
+int token_norm_bwd_run(const void* x, const float* w, const void* dy, const void* add, void* dx, float* dw, long long M,
+                       int C, int mode, cudaStream_t stream) {
+  TVAE_REQUIRE(C % 8 == 0 && C / 8 <= 32 * kMaxVecPerLane, "token_norm_bwd: C=%d unsupported", C);
+  TVAE_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)C * sizeof(float), stream));
+  int rpw = 16;
+  while (rpw > 1 && (M + rpw - 1) / rpw < 8LL * 4 * num_sms()) rpw >>= 1;
+  const long long warps = (M + rpw - 1) / rpw;
+  const int grid = (int)((warps * 32 + 255) / 256);
+  token_norm_bwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), w, reinterpret_cast<const uint4*>(dy),
+                                                  reinterpret_cast<const uint4*>(add), reinterpret_cast<uint4*>(dx), dw, M, C,
+                                                  mode, rpw);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Attention backward helpers.
+//   delta[b][h][s] = sum_d dO[b,s,h,d] * O[b,s,h,d]                                  (one warp per 4 (token, head) pairs)
+//   rope_bwd: dqkv[:, 0:C]   = q_scale * R^T dQ_rot  (dQ accumulated in fp32 by the attention backward kernel)
+//             dqkv[:, C:2C]  = R^T dK_rot   (in place, bf16)
+//   with R the reference's per-pair matrix [[cos a, -sin a], [sin b, cos b]] (attention.py:178-197).
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attn_delta_kernel(const uint4* __restrict__ o, const uint4* __restrict__ dout,
+                                                         float* __restrict__ delta, int B, int S, int C) {
+  // 8 lanes cover one head's 64 channels (8 x uint4)
+  const int nh = C / 64;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pair = gid >> 3;            // (token, head) index
+  const int sub = (int)(gid & 7);
+  const long long total = (long long)B * S * nh;
+  float acc = 0.0f;
+  if (pair < total) {
+    const long long tok = pair / nh;
+    const int h = (int)(pair % nh);
+    float a[8], g[8];
+    unpack8(__ldg(o + tok * (C / 8) + h * 8 + sub), a);
+    unpack8(__ldg(dout + tok * (C / 8) + h * 8 + sub), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc = fmaf(a[k], g[k], acc);
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (sub == 0 && pair < total) {
+    const long long tok = pair / nh;
+    const int h = (int)(pair % nh);
+    const int b = (int)(tok / S), s = (int)(tok % S);
+    delta[((size_t)b * nh + h) * S + s] = acc;
+  }
+}
+
+int attn_delta_run(const void* o, const void* dout, float* delta, int B, int S, int C, cudaStream_t stream) {
+  const long long threads = (long long)B * S * (C / 64) * 8;
+  attn_delta_kernel<<<(int)((threads + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(o),
+                                                                     reinterpret_cast<const uint4*>(dout), delta, B, S, C);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) rope_bwd_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv,
+                                                       const float2* __restrict__ tab, long long M, int C, int H, int W,
+                                                       float q_scale) {
+  // one thread per (token, part in {q,k}, 8-channel vector)
+  const int nvec = C >> 3;
+  const long long total = M * 2 * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const int part = (int)((i / nvec) % 2);
+    const long long tok = i / (2 * nvec);
+    const int t = (int)(tok % ((long long)H * W));
+    const int j0 = (v * 8) & 63;                       // channel inside the head
+    const int pos = (j0 < 32) ? t / W : t % W;
+    const float2* tb = tab + (size_t)pos * 16;
+    float g[8];
+    __nv_bfloat16* dst = dqkv + tok * 3 * C + part * C + v * 8;
+    if (part == 0) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(dq_acc + tok * C + v * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(dq_acc + tok * C + v * 8) + 1);
+      g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+    } else {
+      unpack8(*reinterpret_cast<const uint4*>(dst), g);
+    }
+    const float sc = part == 0 ? q_scale : 1.0f;
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      const float2 ca = __ldg(tb + ((j0 + k) & 15));
+      const float2 cb = __ldg(tb + ((j0 + k + 1) & 15));
+      const float d1 = g[k], d2 = g[k + 1];
+      g[k] = (d1 * ca.x + d2 * cb.y) * sc;
+      g[k + 1] = (d2 * cb.x - d1 * ca.y) * sc;
+    }
+    *reinterpret_cast<uint4*>(dst) = pack8(g);
+  }
+}
+
+int rope_bwd_run(const float* dq_acc, void* dqkv, const float* tab, long long M, int C, int H, int W, float q_scale,
+                 cudaStream_t stream) {
+  const long long total = M * 2 * (C / 8);
+  int grid = (int)((total + 255) / 256);
+  if (grid > num_sms() * 16) grid = num_sms() * 16;
+  rope_bwd_kernel<<<grid, 256, 0, stream>>>(dq_acc, reinterpret_cast<__nv_bfloat16*>(dqkv),
+                                            reinterpret_cast<const float2*>(tab), M, C, H, W, q_scale);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// conv_in weight gradient (Cin = 3): dW[co][ci][dy][dx] += sum_pixels dY[pixel][co] * x[b][ci][y+dy-1][x+dx-1],
+// dbias[co] += sum dY.  Each block reduces a pixel range into shared memory, then flushes with atomics.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_in_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                            float* __restrict__ dw, float* __restrict__ db, int B, int H,
+                                                            int W, int Cout, int pix_per_block) {
+  extern __shared__ float s_in[];  // [pix_chunk][28] (27 inputs + 1.0 for the bias)
+  constexpr int CH = 64;           // pixels staged per round
+  const long long npix = (long long)B * H * W;
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  const long long p1 = min(npix, p0 + pix_per_block);
+  // thread -> (co, k-slice): 256 threads cover Cout x (28 / ks) ... simple mapping: each thread owns one co and 7 of the
+  // 28 taps when Cout*4 <= 256, otherwise loops over co.
+  const int nco_par = blockDim.x / 4;
+  const int kq = threadIdx.x & 3;
+  float acc[8][7];
+  for (int a = 0; a < 8; ++a)
+    for (int k = 0; k < 7; ++k) acc[a][k] = 0.0f;
+  for (long long base = p0; base < p1; base += CH) {
+    const int n = (int)min((long long)CH, p1 - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * 28; i += blockDim.x) {
+      const int pp = i / 28, k = i % 28;
+      const long long pix = base + pp;
+      float val = 1.0f;
+      if (k < 27) {
+        const int ci = k / 9, dyy = (k % 9) / 3, dxx = k % 3;
+        const int wq = (int)(pix % W), hq = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+        const int yy = hq + dyy - 1, xx = wq + dxx - 1;
+        val = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + (((size_t)b * 3 + ci) * H + yy) * W + xx) : 0.0f;
+      }
+      s_in[pp * 28 + k] = val;
+    }
+    __syncthreads();
+    int a = 0;
+    for (int co = threadIdx.x >> 2; co < Cout; co += nco_par, ++a) {
+      for (int pp = 0; pp < n; ++pp) {
+        const float g = __bfloat162float(dy[(size_t)(base + pp) * Cout + co]);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) acc[a][k] = fmaf(g, s_in[pp * 28 + kq * 7 + k], acc[a][k]);
+      }
+    }
+  }
+  int a = 0;
+  for (int co = threadIdx.x >> 2; co < Cout; co += nco_par, ++a) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int kk = kq * 7 + k;
+      if (kk < 27) atomicAdd(dw + (size_t)co * 27 + kk, acc[a][k]);
+      else if (db != nullptr) atomicAdd(db + co, acc[a][k]);
+    }
+  }
+}
+
+int conv_in_wgrad_run(const float* x, const void* dy, float* dw, float* db, int B, int H, int W, int Cout,
+                      cudaStream_t stream) {
+  TVAE_REQUIRE(Cout <= 8 * 64, "conv_in_wgrad: Cout %d too large", Cout);
+  TVAE_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)Cout * 27 * sizeof(float), stream));
+  if (db) TVAE_CHECK_CUDA(cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), stream));
+  const long long npix = (long long)B * H * W;
+  int ppb = 4096;
+  while (ppb > 256 && (npix + ppb - 1) / ppb < 4LL * num_sms()) ppb >>= 1;
+  const int grid = (int)((npix + ppb - 1) / ppb);
+  conv_in_wgrad_kernel<<<grid, 256, 64 * 28 * sizeof(float), stream>>>(x, reinterpret_cast<const __nv_bfloat16*>(dy), dw, db,
+                                                                       B, H, W, Cout, ppb);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Loss / reparameterisation backward (transvae.py:186-199, :244-245 patched; vae_loss.py:80-104 patched / :83,:94 main).
+//   drecon = g_l1 * sign(f(r) - t) * f'(r)                      f = sigmoid (patched) or identity
+//   dmu    = g_kl * mu            * [clamp passes]  + dz * [..]
+//   dlv    = g_kl * -0.5*(1 - e^lv) * [..]          + dz * eps * 0.5 * exp(0.5*lv) * [..]
+// g_l1 = l1_weight / numel(recon) * dLoss, g_kl = kl_weight / norm * dLoss (device scalars, no host sync).
+// -------------------------------------------------------------------------------------------------
+__global__ void loss_bwd_kernel(const float* __restrict__ recon, const float* __restrict__ target,
+                                const float* __restrict__ scal /*[g_l1, g_kl]*/, float* __restrict__ drecon, long long n,
+                                int patched) {
+  const float g = scal[0];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float r = recon[i];
+    float d = 1.0f;
+    if (patched) {
+      const float s = 1.0f / (1.0f + __expf(-r));
+      d = s * (1.0f - s);
+      r = s;
+    }
+    const float diff = r - target[i];
+    drecon[i] = g * d * (diff > 0.0f ? 1.0f : (diff < 0.0f ? -1.0f : 0.0f));
+  }
+}
+
+__global__ void latent_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
+                                  const float* __restrict__ eps, const float* __restrict__ dz,
+                                  const float* __restrict__ dmu_ret, const float* __restrict__ dlv_ret,
+                                  float* __restrict__ dmu, float* __restrict__ dlv, long long n, int patched) {
+  // (z, mu_c, lv_c) = reparam(mu, logvar): gradients arriving on all three outputs are folded back onto (mu, logvar)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float m = mu[i], lv = logvar[i];
+    float pm = 1.0f, pl = 1.0f, lvc = lv;
+    if (patched) {
+      pm = (m >= -50.0f && m <= 50.0f) ? 1.0f : 0.0f;
+      pl = (lv >= -30.0f && lv <= 20.0f) ? 1.0f : 0.0f;
+      lvc = fminf(fmaxf(lv, -30.0f), 20.0f);
+    }
+    const float gz = dz ? dz[i] : 0.0f;
+    float gm = gz, gl = gz * eps[i] * 0.5f * expf(0.5f * lvc);
+    if (dmu_ret) gm += dmu_ret[i];
+    if (dlv_ret) gl += dlv_ret[i];
+    dmu[i] = gm * pm;
+    dlv[i] = gl * pl;
+  }
+}
+
+__global__ void kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
+                              const float* __restrict__ scal, float* __restrict__ dmu, float* __restrict__ dlv,
+                              long long n, int patched, float clip_lo, float clip_hi) {
+  const float g = scal[1];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float lv = logvar[i];
+    float pl = 1.0f, lvc = lv;
+    if (patched) {
+      pl = (lv >= clip_lo && lv <= clip_hi) ? 1.0f : 0.0f;
+      lvc = fminf(fmaxf(lv, clip_lo), clip_hi);
+    }
+    dmu[i] = g * mu[i];
+    dlv[i] = g * -0.5f * (1.0f - expf(lvc)) * pl;
+  }
+}
+
+static int grid_for(long long n) {
+  int g = (int)((n + 255) / 256);
+  const int cap = num_sms() * 8;
+  return g > cap ? cap : (g < 1 ? 1 : g);
+}
+
+int loss_bwd_run(const float* recon, const float* target, const float* mu, const float* logvar, const float* scal,
+                 float* drecon, float* dmu, float* dlv, long long n_img, long long n_lat, int patched, float clip_lo,
+                 float clip_hi, cudaStream_t stream) {
+  loss_bwd_kernel<<<grid_for(n_img), 256, 0, stream>>>(recon, target, scal, drecon, n_img, patched);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  kl_bwd_kernel<<<grid_for(n_lat), 256, 0, stream>>>(mu, logvar, scal, dmu, dlv, n_lat, patched, clip_lo, clip_hi);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int latent_bwd_run(const float* mu, const float* logvar, const float* eps, const float* dz, const float* dmu_ret,
+                   const float* dlv_ret, float* dmu, float* dlv, long long n, int patched, cudaStream_t stream) {
+  latent_bwd_kernel<<<grid_for(n), 256, 0, stream>>>(mu, logvar, eps, dz, dmu_ret, dlv_ret, dmu, dlv, n, patched);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Optimiser: fused AdamW over flat fp32 buffers + gradient sum of squares (for clip_grad_norm_).
+// Replaces clip_grad_norm_(1.0) + fused AdamW(lr, betas=(0.9, 0.95), wd) of the training step
+// (train.py:608-620; train_working.py:384-397).  Algorithmic bytes: 16 read + 12 written per parameter.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ g, long long n4, float* __restrict__ out) {
+  float acc = 0.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(g + i);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  __shared__ float red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < 8 ? red[threadIdx.x] : 0.0f;
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) atomicAdd(out, acc);
+  }
+}
+
+int sumsq_run(const float* g, long long n, float* out, cudaStream_t stream) {
+  TVAE_REQUIRE(n % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0, "sumsq: buffer must be float4-aligned/padded");
+  int grid = (int)((n / 4 + 255) / 256);
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  sumsq_kernel<<<grid < 1 ? 1 : grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(g), n / 4, out);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ctrl (device, fp32[4]) = {sum of squared grads (global), max_norm, grad_scale (e.g. 1/world or 1/accum), skip flag}
+__global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                                                    float4* __restrict__ v, long long n4, const float* __restrict__ ctrl,
+                                                    float lr, float b1, float b2, float eps, float wd, float bc1, float bc2) {
+  const float gs = ctrl[2];
+  const float norm = sqrtf(ctrl[0]) * gs;
+  const float maxn = ctrl[1];
+  float clip = 1.0f;
+  if (maxn > 0.0f) clip = fminf(1.0f, maxn / (norm + 1e-6f));
+  if (!isfinite(norm) || ctrl[3] != 0.0f) return;   // non-finite step is skipped (train_2.py:329-338)
+  const float s = gs * clip;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = p[i], gg = __ldg(g + i), mm = m[i], vv = v[i];
+    float* P4 = reinterpret_cast<float*>(&pp);
+    float* G4 = reinterpret_cast<float*>(&gg);
+    float* M4 = reinterpret_cast<float*>(&mm);
+    float* V4 = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = G4[k] * s;
+      M4[k] = b1 * M4[k] + (1.0f - b1) * gr;
+      V4[k] = b2 * V4[k] + (1.0f - b2) * gr * gr;
+      const float mh = M4[k] / bc1;
+      const float vh = V4[k] / bc2;
+      P4[k] = P4[k] * (1.0f - lr * wd) - lr * mh / (sqrtf(vh) + eps);
+    }
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+}
+
+int adamw_run(float* p, const float* g, float* m, float* v, long long n, const float* ctrl, float lr, float b1, float b2,
+              float eps, float wd, int step, cudaStream_t stream) {
+  TVAE_REQUIRE(n % 4 == 0, "adamw: buffer length must be a multiple of 4");
+  const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
+  int grid = (int)((n / 4 + 255) / 256);
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  adamw_kernel<<<grid < 1 ? 1 : grid, 256, 0, stream>>>(reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g),
+                                                        reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n / 4,
+                                                        ctrl, lr, b1, b2, eps, wd, bc1, bc2);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tvae

@@ -69,7 +69,92 @@ struct MtCfg {
   static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kOutBytes + 1024 /*align slack*/ + 256 /*bars*/;
 };
 
-template <int BLOCK_N>
+// Epilogue variants (compile-time, so each kernel's epilogue is a few hundred instructions: the first version kept
+// every option as a run-time branch inside a 32x unrolled loop and was instruction-fetch bound -- ncu showed
+// stall_no_inst on the epilogue warps and the MMA warp waiting on tmem_empty).
+enum Epi : int {
+  kEpiBias = 0,        // v = acc + bias
+  kEpiBiasRes = 1,     // v = acc + bias + residual
+  kEpiBiasGelu = 2,    // v = gelu(acc + bias)
+  kEpiBiasSilu = 3,    // v = silu(acc + bias)
+  kEpiRsBiasGelu = 4,  // v = gelu(rs[m] * acc + bias)                      (RMSNorm folded into proj_in)
+  kEpiAffineRope = 5,  // v = rope(rs[m] * acc - rsh[m] * cs[n] + bias)     (RMSNorm + LayerNorm folded into QKV)
+  kEpiDirect = 6,      // fp32 NCHW direct store of acc + bias
+  kEpiRsBias = 7,      // v = rs[m] * acc - rsh[m] * cs[n] + bias [+ residual] (generic, tests / bare modules)
+};
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+struct EpiRow {
+  float rs, rsh;
+  int rope_r, rope_c;
+  bool row_ok;
+  int pw, phh, pb;
+};
+
+// Epilogue math for 8 consecutive output columns [n, n+8) of one row.
+template <int EPI>
+__device__ __forceinline__ void epi_math8(const MtParams& P, const float* __restrict__ bias, const EpiRow& R, int n,
+                                          const uint32_t (&v)[8], float (&f)[8]) {
+  float bv[8];
+  if (bias != nullptr) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n) + 1);
+    bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bv[k] = 0.0f;
+  }
+  if constexpr (EPI == kEpiRsBiasGelu) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = fmaf(__uint_as_float(v[k]), R.rs, bv[k]);
+  } else if constexpr (EPI == kEpiAffineRope || EPI == kEpiRsBias) {
+    if (P.row_shift != nullptr) {
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(P.col_sum + n));
+      const float4 c1 = __ldg(reinterpret_cast<const float4*>(P.col_sum + n) + 1);
+      const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) bv[k] = fmaf(-R.rsh, cv[k], bv[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = fmaf(__uint_as_float(v[k]), R.rs, bv[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[k]) + bv[k];
+  }
+  if constexpr (EPI == kEpiBiasGelu || EPI == kEpiRsBiasGelu) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = gelu_erf(f[k]);
+  } else if constexpr (EPI == kEpiBiasSilu) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = silu(f[k]);
+  }
+  if constexpr (EPI == kEpiAffineRope) {
+    if (P.rope_tab != nullptr && n < 2 * P.rope_C) {
+      // columns n..n+7 sit in one half of a 64-wide head: the first half rotates with the row index, the second with
+      // the column index (attention.py:161-170); pair (2i, 2i+1) uses the angle of slot 2i for the even output and of
+      // slot 2i+1 for the odd output (attention.py:178-197).
+      const int j0 = n & 63;
+      const int pos = (j0 < 32) ? R.rope_r : R.rope_c;
+      const float4* tab = reinterpret_cast<const float4*>(P.rope_tab + (size_t)pos * 16 + (j0 & 15));
+      const float qs = (n < P.rope_C) ? P.q_scale : 1.0f;
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        const float4 t = __ldg(tab + (k >> 1));   // (cos a, sin a, cos b, sin b)
+        const float a = f[k], b = f[k + 1];
+        f[k] = (a * t.x - b * t.y) * qs;
+        f[k + 1] = (a * t.w + b * t.z) * qs;
+      }
+    }
+  }
+}
+
+template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -77,6 +162,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 #ifdef TVAE_DEVICE_OK
   using Cfg = MtCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::kStages;
+  constexpr bool kHasRes = (EPI == kEpiBiasRes || EPI == kEpiRsBias);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -93,6 +179,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool has_res = kHasRes && P.has_residual;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -192,7 +279,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ residual loader
-    if (lane == 0 && P.has_residual) {
+    if (lane == 0 && has_res) {
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int n_t = tile % P.n_tiles;
@@ -227,91 +314,78 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
 
-      // pixel owned by this row
-      const int wi = r % P.tw, hi = (r / P.tw) % P.th, bi = r / (P.tw * P.th);
-      const int pw = w0 + wi, phh = h0 + hi, pb = b0 + bi;
-      const bool row_ok = (pw < P.vW) && (phh < P.vH) && (pb < P.vB);
-      const long long grow = ((long long)pb * P.vH + phh) * P.vW + pw;  // flattened output-view pixel index
-
-      float rs = 1.0f, rsh = 0.0f;
-      if (P.row_scale != nullptr && row_ok) rs = __ldg(P.row_scale + grow);
-      if (P.row_shift != nullptr && row_ok) rsh = __ldg(P.row_shift + grow);
-      const float* bias = P.bias ? P.bias + (size_t)ph * P.n_total : nullptr;
-
-      // RoPE position of this row (flat [B*S, C] GEMM: token = row % (H*W))
-      int rope_r = 0, rope_c = 0;
-      if (P.rope_tab != nullptr) {
-        const int tok = (int)(grow % ((long long)P.rope_H * P.rope_W));
-        rope_r = tok / P.rope_W;
-        rope_c = tok % P.rope_W;
+      EpiRow R;
+      {
+        const int wi = r % P.tw, hi = (r / P.tw) % P.th, bi = r / (P.tw * P.th);
+        R.pw = w0 + wi; R.phh = h0 + hi; R.pb = b0 + bi;
+        R.row_ok = (R.pw < P.vW) && (R.phh < P.vH) && (R.pb < P.vB);
+        const long long grow = ((long long)R.pb * P.vH + R.phh) * P.vW + R.pw;  // flattened output-view pixel index
+        R.rs = 1.0f; R.rsh = 0.0f; R.rope_r = 0; R.rope_c = 0;
+        if constexpr (EPI == kEpiRsBiasGelu || EPI == kEpiAffineRope || EPI == kEpiRsBias) {
+          if (P.row_scale != nullptr && R.row_ok) R.rs = __ldg(P.row_scale + grow);
+          if (P.row_shift != nullptr && R.row_ok) R.rsh = __ldg(P.row_shift + grow);
+        }
+        if constexpr (EPI == kEpiAffineRope) {
+          if (P.rope_tab != nullptr) {
+            const int tok = (int)(grow % ((long long)P.rope_H * P.rope_W));
+            R.rope_r = tok / P.rope_W;
+            R.rope_c = tok % P.rope_W;
+          }
+        }
       }
+      const float* bias = P.bias ? P.bias + (size_t)ph * P.n_total : nullptr;
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      if (P.has_residual) mbar_wait(res_full, it & 1);
+      if (has_res) mbar_wait(res_full, it & 1);
 
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+      const int n_base = n_t * BLOCK_N;
 #pragma unroll 1
-      for (int c32 = 0; c32 < BLOCK_N / 32; ++c32) {
-        uint32_t v[32];
-        tmem_ld32(t_row + c32 * 32, v);
+      for (int c16 = 0; c16 < BLOCK_N / 16; ++c16) {
+        uint32_t va[8], vb[8];
+        tmem_ld8(t_row + c16 * 16, va);
+        tmem_ld8(t_row + c16 * 16 + 8, vb);
         tmem_ld_wait();
-        const int n0 = n_t * BLOCK_N + c32 * 32;  // first global output column of this 32-wide slab
-        float f[32];
+        float fa[8], fb[8];
+        epi_math8<EPI>(P, bias, R, n_base + c16 * 16, va, fa);
+        epi_math8<EPI>(P, bias, R, n_base + c16 * 16 + 8, vb, fb);
+        if constexpr (EPI == kEpiDirect) {
+          if (R.row_ok) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(v[i]) * rs;
-          if (P.row_shift != nullptr) x -= rsh * __ldg(P.col_sum + n0 + i);
-          if (bias != nullptr) x += __ldg(bias + n0 + i);
-          if (P.act == TVAE_ACT_GELU) x = gelu_erf(x);
-          else if (P.act == TVAE_ACT_SILU) x = silu(x);
-          f[i] = x;
-        }
-        if (P.rope_tab != nullptr && n0 < 2 * P.rope_C) {
-          // columns n0..n0+31 are one half of a 64-wide head: first half rotates with the row index,
-          // second half with the column index (attention.py:161-170); pair (2i, 2i+1) uses the angle of
-          // slot 2i for the even output and of slot 2i+1 for the odd output (attention.py:178-197).
-          const int pos = ((n0 & 32) == 0) ? rope_r : rope_c;
-          const float2* tab = P.rope_tab + (size_t)pos * 16;
-          const float qs = (n0 < P.rope_C) ? P.q_scale : 1.0f;
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float2 ca = __ldg(tab + (i & 15));
-            const float2 cb = __ldg(tab + ((i + 1) & 15));
-            const float a = f[i], b = f[i + 1];
-            f[i] = (a * ca.x - b * ca.y) * qs;
-            f[i + 1] = (a * cb.y + b * cb.x) * qs;
-          }
-        }
-        if (P.out_f32 != nullptr) {
-          if (row_ok) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int n = n0 + i;
-              if (n < P.out_n) P.out_f32[(((long long)pb * P.out_n + n) * P.vH + phh) * P.vW + pw] = f[i];
+            for (int k = 0; k < 8; ++k) {
+              const int n = n_base + c16 * 16 + k;
+              if (n < P.out_n) P.out_f32[(((long long)R.pb * P.out_n + n) * P.vH + R.phh) * P.vW + R.pw] = fa[k];
+              if (n + 8 < P.out_n) P.out_f32[(((long long)R.pb * P.out_n + n + 8) * P.vH + R.phh) * P.vW + R.pw] = fb[k];
             }
           }
         } else {
-          uint8_t* chunk = sOut + (c32 >> 1) * kABytes + r * 128;
-          const int cbase = (c32 & 1) * 4;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4* p16 = reinterpret_cast<uint4*>(chunk + (((cbase + g) ^ (r & 7)) << 4));
-            if (P.has_residual) {
-              const uint4 rv = *p16;
+          // 16 columns = two 16-byte groups of this thread's 128-byte row inside 64-column chunk (c16 / 4)
+          uint8_t* chunk = sOut + (c16 >> 2) * kABytes + r * 128;
+          const int g0 = (c16 & 3) * 2;
+          uint4* pa = reinterpret_cast<uint4*>(chunk + (((g0) ^ (r & 7)) << 4));
+          uint4* pb = reinterpret_cast<uint4*>(chunk + (((g0 + 1) ^ (r & 7)) << 4));
+          if constexpr (kHasRes) {
+            if (has_res) {
+              const uint4 ra = *pa, rb = *pb;
               float2 t;
-              t = unpack_bf16(rv.x); f[g * 8 + 0] += t.x; f[g * 8 + 1] += t.y;
-              t = unpack_bf16(rv.y); f[g * 8 + 2] += t.x; f[g * 8 + 3] += t.y;
-              t = unpack_bf16(rv.z); f[g * 8 + 4] += t.x; f[g * 8 + 5] += t.y;
-              t = unpack_bf16(rv.w); f[g * 8 + 6] += t.x; f[g * 8 + 7] += t.y;
+              t = unpack_bf16(ra.x); fa[0] += t.x; fa[1] += t.y;
+              t = unpack_bf16(ra.y); fa[2] += t.x; fa[3] += t.y;
+              t = unpack_bf16(ra.z); fa[4] += t.x; fa[5] += t.y;
+              t = unpack_bf16(ra.w); fa[6] += t.x; fa[7] += t.y;
+              t = unpack_bf16(rb.x); fb[0] += t.x; fb[1] += t.y;
+              t = unpack_bf16(rb.y); fb[2] += t.x; fb[3] += t.y;
+              t = unpack_bf16(rb.z); fb[4] += t.x; fb[5] += t.y;
+              t = unpack_bf16(rb.w); fb[6] += t.x; fb[7] += t.y;
             }
-            uint4 o;
-            o.x = pack_bf16(f[g * 8 + 0], f[g * 8 + 1]);
-            o.y = pack_bf16(f[g * 8 + 2], f[g * 8 + 3]);
-            o.z = pack_bf16(f[g * 8 + 4], f[g * 8 + 5]);
-            o.w = pack_bf16(f[g * 8 + 6], f[g * 8 + 7]);
-            *p16 = o;
           }
+          uint4 o;
+          o.x = pack_bf16(fa[0], fa[1]); o.y = pack_bf16(fa[2], fa[3]);
+          o.z = pack_bf16(fa[4], fa[5]); o.w = pack_bf16(fa[6], fa[7]);
+          *pa = o;
+          o.x = pack_bf16(fb[0], fb[1]); o.y = pack_bf16(fb[2], fb[3]);
+          o.z = pack_bf16(fb[4], fb[5]); o.w = pack_bf16(fb[6], fb[7]);
+          *pb = o;
         }
       }
       // TMEM accumulator drained -> hand it back to the MMA warp
@@ -319,7 +393,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
 
-      if (P.out_f32 == nullptr) {
+      if constexpr (EPI != kEpiDirect) {
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (store_leader) {
@@ -328,7 +402,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             tma_store_5d(&tmOut, sOut + j * kABytes, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph], h0, b0);
           tma_store_commit();
           tma_store_wait_read<0>();
-          if (P.has_residual) mbar_arrive(out_free);
+          if (has_res) mbar_arrive(out_free);
         }
         // staging buffer may be overwritten only after the bulk store has read it
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -339,7 +413,10 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 #endif
 }
 
@@ -352,13 +429,13 @@ static int pow2_ceil(int v) {
   return p;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI>
 static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                   const CUtensorMap& r, const MtParams& P, cudaStream_t stream) {
   using Cfg = MtCfg<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    TVAE_CHECK_CUDA(cudaFuncSetAttribute(mtgemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TVAE_CHECK_CUDA(cudaFuncSetAttribute(mtgemm_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
     configured = true;
   }
@@ -366,9 +443,20 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
   int grid = num_sms();
   if (grid <= 0) grid = 148;
   if (total < grid) grid = total;
-  mtgemm_kernel<BLOCK_N><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b, o, r, P);
+  mtgemm_kernel<BLOCK_N, EPI><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b, o, r, P);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int EPI>
+static int launch_n(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+                    const CUtensorMap& r, const MtParams& P, cudaStream_t stream) {
+  switch (block_n) {
+    case 256: return launch<256, EPI>(a0, a1, b, o, r, P, stream);
+    case 192: return launch<192, EPI>(a0, a1, b, o, r, P, stream);
+    case 128: return launch<128, EPI>(a0, a1, b, o, r, P, stream);
+    default: return launch<64, EPI>(a0, a1, b, o, r, P, stream);
+  }
 }
 
 static void view_extents(const tvae_view& v, int* vW, int* vH, int* vB) {
@@ -456,11 +544,36 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
   } else {
     mR = mO;
   }
-  switch (block_n) {
-    case 256: return launch<256>(mA0, mA1, mB, mO, mR, P, stream);
-    case 192: return launch<192>(mA0, mA1, mB, mO, mR, P, stream);
-    case 128: return launch<128>(mA0, mA1, mB, mO, mR, P, stream);
-    default: return launch<64>(mA0, mA1, mB, mO, mR, P, stream);
+  // pick the compile-time epilogue variant
+  const bool affine = d->row_scale != nullptr || d->row_shift != nullptr;
+  int epi;
+  if (direct) {
+    TVAE_REQUIRE(!affine && d->act == TVAE_ACT_NONE && d->rope_tab == nullptr, "mtgemm: direct store supports bias only");
+    epi = kEpiDirect;
+  } else if (d->rope_tab != nullptr) {
+    TVAE_REQUIRE(d->act == TVAE_ACT_NONE && !P.has_residual, "mtgemm: rope epilogue excludes act / residual");
+    epi = kEpiAffineRope;
+  } else if (affine) {
+    if (d->act == TVAE_ACT_GELU && d->row_shift == nullptr && !P.has_residual) epi = kEpiRsBiasGelu;
+    else {
+      TVAE_REQUIRE(d->act == TVAE_ACT_NONE, "mtgemm: row-affine epilogue supports GELU (row_scale only) or no activation");
+      epi = kEpiRsBias;
+    }
+  } else if (P.has_residual) {
+    TVAE_REQUIRE(d->act == TVAE_ACT_NONE, "mtgemm: residual epilogue excludes an activation");
+    epi = kEpiBiasRes;
+  } else {
+    epi = d->act == TVAE_ACT_GELU ? kEpiBiasGelu : (d->act == TVAE_ACT_SILU ? kEpiBiasSilu : kEpiBias);
+  }
+  switch (epi) {
+    case kEpiBias: return launch_n<kEpiBias>(block_n, mA0, mA1, mB, mO, mR, P, stream);
+    case kEpiBiasRes: return launch_n<kEpiBiasRes>(block_n, mA0, mA1, mB, mO, mR, P, stream);
+    case kEpiBiasGelu: return launch_n<kEpiBiasGelu>(block_n, mA0, mA1, mB, mO, mR, P, stream);
+    case kEpiBiasSilu: return launch_n<kEpiBiasSilu>(block_n, mA0, mA1, mB, mO, mR, P, stream);
+    case kEpiRsBiasGelu: return launch_n<kEpiRsBiasGelu>(block_n, mA0, mA1, mB, mO, mR, P, stream);
+    case kEpiAffineRope: return launch_n<kEpiAffineRope>(block_n, mA0, mA1, mB, mO, mR, P, stream);
+    case kEpiDirect: return launch_n<kEpiDirect>(block_n, mA0, mA1, mB, mO, mR, P, stream);
+    default: return launch_n<kEpiRsBias>(block_n, mA0, mA1, mB, mO, mR, P, stream);
   }
 }
 

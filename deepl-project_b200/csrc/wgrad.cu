@@ -1,0 +1,275 @@
+// Weight gradient of the fused multi-tap implicit GEMM (sm_100a, tcgen05 + TMA + TMEM).
+//
+//   dW[n, wk_off_tap + k] += sum_pixels dZ[pixel, n] * A_tap[pixel, k]
+//
+// Same pixel views / tap tables as the forward kernel (mtgemm.cu), but the reduction runs over PIXELS: both
+// operands are TMA-loaded as [128 pixels x 64 channels] 128B-swizzled tiles and fed to the tensor core as
+// MN-major operands (channels contiguous, pixels = MMA K dimension).  One CTA owns one
+// (phase, tap, 128-wide n tile, KT-wide k tile) output block for a strided subset of the pixel tiles ("split-K over
+// pixels"), accumulates it in TMEM over its whole loop and adds it to the fp32 dW matrix with vectorised
+// red.global.add at the end.  Replaces the weight-gradient half of autograd for every nn.Conv2d / nn.Linear the
+// forward kernel replaces (reference call sites: include/transvae_sm100.h, tvae_mtgemm).
+#include "../../include/transvae_sm100.h"
+#include "common.cuh"
+#include "tmap.cuh"
+
+namespace tvae {
+
+struct WgTap {
+  int32_t c_off;
+  int32_t wk_off;
+  int16_t kblocks;
+  int8_t map, dw, p, dh;
+  int8_t ph;      // phase this tap belongs to
+  int8_t pad_;
+};
+static_assert(sizeof(WgTap) == 16, "WgTap must be 16 bytes");
+
+struct WgParams {
+  int tiles_w, tiles_h, tiles_b;
+  int tw, th, nb;
+  int ntaps;                 // flattened over phases
+  int n_tiles;               // ceil(n_total / 128)
+  int n_total, k_total;
+  int splits;
+  int out_p[TVAE_MAX_PHASES];
+  int out_c_off[TVAE_MAX_PHASES];
+  WgTap taps[TVAE_MAX_PHASES * TVAE_MAX_TAPS];
+  float* dw;
+};
+
+constexpr int kWgTile = 128 * 64 * 2;  // one [128 pixels x 64 channels] bf16 box
+
+template <int KT>
+struct WgCfg {
+  static constexpr int kStageBytes = (2 + KT / 64) * kWgTile;
+  static constexpr int kStages = (220 * 1024) / kStageBytes > 4 ? 4 : (220 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = KT <= 64 ? 64 : (KT <= 128 ? 128 : 256);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 128;
+};
+
+template <int KT>
+__global__ void __launch_bounds__(256, 1)
+mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ WgParams P) {
+#ifdef TVAE_DEVICE_OK
+  using Cfg = WgCfg<KT>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* acc_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmDZ);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- decode the work item of this CTA: (tap, k tile, n tile) x pixel split
+  const int split = blockIdx.x % P.splits;
+  int item = blockIdx.x / P.splits;
+  int ti = 0, kt = 0, nt = 0;
+  for (; ti < P.ntaps; ++ti) {
+    const int cnt = (P.taps[ti].kblocks * 64 / KT) * P.n_tiles;
+    if (item < cnt) {
+      kt = item / P.n_tiles;
+      nt = item % P.n_tiles;
+      break;
+    }
+    item -= cnt;
+  }
+  const WgTap tap = P.taps[ti];
+  const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
+  const int my_tiles = (m_tiles - split + P.splits - 1) / P.splits;   // tiles split, split+splits, ...
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* mapA = tap.map ? &tmA1 : &tmA0;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int m_t = split + i * P.splits;
+        const int w0 = (m_t % P.tiles_w) * P.tw;
+        const int h0 = ((m_t / P.tiles_w) % P.tiles_h) * P.th;
+        const int b0 = (m_t / (P.tiles_w * P.tiles_h)) * P.nb;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+        uint8_t* s = smem + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          tma_load_5d(s + j * kWgTile, &tmDZ, &full[stage], P.out_c_off[tap.ph] + nt * 128 + j * 64, w0, P.out_p[tap.ph], h0,
+                      b0);
+#pragma unroll
+        for (int j = 0; j < KT / 64; ++j)
+          tma_load_5d(s + (2 + j) * kWgTile, mapA, &full[stage], tap.c_off + kt * KT + j * 64, w0 + tap.dw, tap.p,
+                      h0 + tap.dh, b0);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, KT, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t dz_base = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t a_base = dz_base + 2 * kWgTile;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // 16 pixels per MMA
+          umma_f16(tmem_base, umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024),
+                   umma_desc_mnmajor_sw128(a_base + k * 2048, kWgTile, 1024), idesc, (i | k) != 0);
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int n = nt * 128 + q * 32 + lane;
+    if (my_tiles > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      float* dst = P.dw + (size_t)n * P.k_total + tap.wk_off + kt * KT;
+#pragma unroll 1
+      for (int c = 0; c < KT / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+        tmem_ld_wait();
+        if (n < P.n_total) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 f = make_float4(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1]),
+                                   __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
+            atomicAdd(reinterpret_cast<float4*>(dst + c * 32 + g * 4), f);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+#endif
+}
+
+static int pow2_ceil_w(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+template <int KT>
+static int launch_wg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& dz, const WgParams& P, int grid,
+                     cudaStream_t stream) {
+  using Cfg = WgCfg<KT>;
+  static bool configured = false;
+  if (!configured) {
+    TVAE_CHECK_CUDA(cudaFuncSetAttribute(mtwgrad_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  mtwgrad_kernel<KT><<<grid, 256, Cfg::kSmemBytes, stream>>>(a0, a1, dz, P);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// d->out is the dZ view (gradient w.r.t. the forward kernel's pre-activation output); dw: fp32 [n_total, k_total],
+// accumulated into (the caller zeroes it).
+int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, cudaStream_t stream) {
+  TVAE_REQUIRE(d != nullptr && dw != nullptr, "wgrad: null argument");
+  TVAE_REQUIRE(d->a0.ptr != nullptr && d->out.ptr != nullptr, "wgrad: missing operand");
+  TVAE_REQUIRE(d->k_total % 64 == 0, "wgrad: k_total %d must be a multiple of 64", d->k_total);
+  TVAE_REQUIRE((reinterpret_cast<uintptr_t>(dw) & 15) == 0, "wgrad: dw must be 16-byte aligned");
+  WgParams P;
+  memset(&P, 0, sizeof(P));
+  const tvae_view& gv = d->out;
+  const int vW = gv.split ? gv.W / 2 : gv.W, vH = gv.split ? gv.H / 2 : gv.H, vB = gv.B;
+  P.tw = pow2_ceil_w(vW) < 128 ? pow2_ceil_w(vW) : 128;
+  P.th = pow2_ceil_w(vH) < 128 / P.tw ? pow2_ceil_w(vH) : 128 / P.tw;
+  P.nb = 128 / (P.tw * P.th);
+  P.tiles_w = (vW + P.tw - 1) / P.tw;
+  P.tiles_h = (vH + P.th - 1) / P.th;
+  P.tiles_b = (vB + P.nb - 1) / P.nb;
+  P.n_total = d->n_total;
+  P.k_total = d->k_total;
+  P.n_tiles = (d->n_total + 127) / 128;
+  P.dw = dw;
+  int kt = 256;
+  int nt = 0;
+  for (int ph = 0; ph < d->num_phases; ++ph) {
+    P.out_p[ph] = d->out_p[ph];
+    P.out_c_off[ph] = d->out_c_off[ph];
+    for (int t = 0; t < d->ntaps[ph]; ++t) {
+      const tvae_tap& s = d->taps[ph][t];
+      const tvae_view& av = s.map ? d->a1 : d->a0;
+      TVAE_REQUIRE(av.ptr != nullptr, "wgrad: tap uses absent view %d", s.map);
+      TVAE_REQUIRE(s.kblocks >= 1 && s.wk_off >= 0 && s.wk_off + s.kblocks * 64 <= d->k_total, "wgrad: bad tap");
+      WgTap& o = P.taps[nt++];
+      o.c_off = s.c_off; o.wk_off = s.wk_off; o.kblocks = (int16_t)s.kblocks;
+      o.map = (int8_t)s.map; o.dw = (int8_t)s.dw; o.p = (int8_t)s.p; o.dh = (int8_t)s.dh; o.ph = (int8_t)ph;
+      const int c = s.kblocks * 64;
+      while (c % kt) kt -= 64;
+    }
+  }
+  P.ntaps = nt;
+  long long items = 0;
+  for (int i = 0; i < nt; ++i) items += (long long)(P.taps[i].kblocks * 64 / kt) * P.n_tiles;
+  const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  long long splits = (2LL * sms + items - 1) / items;
+  if (splits > m_tiles) splits = m_tiles;
+  if (splits < 1) splits = 1;
+  // keep at least ~8 pixel tiles per CTA so the TMEM drain + atomics are amortised
+  while (splits > 1 && m_tiles / splits < 8) --splits;
+  P.splits = (int)splits;
+  const long long grid = items * splits;
+  TVAE_REQUIRE(grid < (1LL << 31), "wgrad: grid too large");
+
+  CUtensorMap mA0, mA1, mDZ;
+  int rc;
+  if ((rc = make_tmap_pix(&mA0, d->a0.ptr, d->a0.B, d->a0.H, d->a0.W, d->a0.C, d->a0.split, P.tw, P.th, P.nb))) return rc;
+  if (d->a1.ptr) {
+    if ((rc = make_tmap_pix(&mA1, d->a1.ptr, d->a1.B, d->a1.H, d->a1.W, d->a1.C, d->a1.split, P.tw, P.th, P.nb))) return rc;
+  } else {
+    mA1 = mA0;
+  }
+  if ((rc = make_tmap_pix(&mDZ, d->out.ptr, d->out.B, d->out.H, d->out.W, d->out.C, d->out.split, P.tw, P.th, P.nb))) return rc;
+  switch (kt) {
+    case 256: return launch_wg<256>(mA0, mA1, mDZ, P, (int)grid, stream);
+    case 192: return launch_wg<192>(mA0, mA1, mDZ, P, (int)grid, stream);
+    case 128: return launch_wg<128>(mA0, mA1, mDZ, P, (int)grid, stream);
+    default: return launch_wg<64>(mA0, mA1, mDZ, P, (int)grid, stream);
+  }
+}
+
+}  // namespace tvae

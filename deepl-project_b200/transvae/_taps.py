@@ -218,3 +218,91 @@ def rope_table(H: int, W: int, inv_freq: Tensor) -> Tensor:
     pos = torch.arange(max(H, W), device=inv_freq.device, dtype=torch.float32)
     ang = torch.outer(pos, inv_freq.float())
     return torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# input-gradient ("dgrad") plans: the same kernel with the taps transposed.  A = dZ (gradient w.r.t. the forward
+# pre-activation output, N channels), output = dX (C channels), weights = per-tap W^T packed as [C, taps*N].
+# ----------------------------------------------------------------------------------------------
+def plan_conv3x3_dgrad(n: int) -> Plan:
+    """dX[p] = sum_taps dZ[p - off] W_tap^T for a 3x3 stride-1 conv with ``n`` output channels."""
+    taps = [TapSpec(0, 0, -(dx - 1), 0, -(dy - 1), _kb(n), (dy * 3 + dx) * n) for dy in range(3) for dx in range(3)]
+    return Plan([taps], [0], [0], k_total=9 * n, name="conv3x3_dgrad", algo_k=9 * n)
+
+
+def pack_conv3x3_dgrad(w: Tensor, cin_pad: Optional[int] = None, cout_pad: Optional[int] = None) -> Tensor:
+    """OIHW [O, I, 3, 3] -> [I(pad), 9*O(pad)] with K index (dy*3+dx)*O + o."""
+    o, i = w.shape[0], w.shape[1]
+    t = w.permute(1, 2, 3, 0)              # [I, 3, 3, O]
+    if cout_pad is not None and cout_pad > o:
+        t = torch.nn.functional.pad(t, (0, cout_pad - o))
+        o = cout_pad
+    t = t.reshape(i, 9 * o)
+    if cin_pad is not None and cin_pad > i:
+        t = torch.nn.functional.pad(t, (0, 0, 0, cin_pad - i))
+    return t
+
+
+def plan_downsample_dgrad_main(c: int, n: int) -> Plan:
+    """Gradient w.r.t. the stride-2 conv's input: four output phases of the [B, H, W, c] tensor, each fed by the taps
+    of the forward conv that read that phase.  A = dZ [B, H/2, W/2, n] (plain)."""
+    phases, out_p, out_c = [], [], []
+    for p in range(2):
+        for q in range(2):
+            taps = []
+            for dy in range(3):
+                pp, dh = _s2(dy)
+                if pp != p:
+                    continue
+                for dx in range(3):
+                    qq, dw = _s2(dx)
+                    if qq != q:
+                        continue
+                    taps.append(TapSpec(0, 0, -dw, 0, -dh, _kb(n), (dy * 3 + dx) * n))
+            phases.append(taps)
+            out_p.append(p)
+            out_c.append(q * c)
+    return Plan(phases, out_p, out_c, out_split=True, k_total=9 * n, name="downsample_dgrad_main", algo_k=9 * n // 4)
+
+
+def plan_downsample_dgrad_dc(c: int, n: int) -> Plan:
+    """Gradient w.r.t. x through pixel_unshuffle + 1x1 conv: phase (i, j) of dX = dZ * Wdc[:, c*4+i*2+j]."""
+    phases = [[TapSpec(0, 0, 0, 0, 0, _kb(n), (i * 2 + j) * n)] for i in range(2) for j in range(2)]
+    return Plan(phases, [0, 0, 1, 1], [0, c, 0, c], out_split=True, k_total=4 * n, name="downsample_dgrad_dc", algo_k=n)
+
+
+def pack_downsample_dgrad_dc(w_dc: Tensor) -> Tensor:
+    """dc_conv weight [N, 4C, 1, 1] (input channel c*4+i*2+j) -> [C, 4N] with K index (i*2+j)*N + n."""
+    n, c4 = w_dc.shape[0], w_dc.shape[1]
+    return w_dc.reshape(n, c4 // 4, 2, 2).permute(1, 2, 3, 0).reshape(c4 // 4, 4 * n)
+
+
+def plan_upsample_conv1_dgrad(cin: int, cout: int) -> Plan:
+    """Gradient w.r.t. the low-res input of nearest2x+conv3x3: 16 taps over the phase view of dZ [B, 2H, 2W, cout]."""
+    taps = []
+    wk = 0
+    for py in range(2):
+        for px in range(2):
+            for dh, _ in _UP_ROWS[py]:
+                for dw, _ in _UP_ROWS[px]:
+                    taps.append(TapSpec(0, px * cout, -dw, py, -dh, _kb(cout), wk))
+                    wk += cout
+    return Plan([taps], [0], [0], a0_split=True, k_total=16 * cout, name="upsample_conv1_dgrad", algo_k=9 * cout * 4)
+
+
+def pack_upsample_conv1_dgrad(w: Tensor) -> Tensor:
+    """[Cin, 16*Co] with K index (phase*4 + tap)*Co + o, from the summed phase taps of pack_upsample_conv1."""
+    co, cin = w.shape[0], w.shape[1]
+    return pack_upsample_conv1(w).reshape(co, 16, cin).permute(2, 1, 0).reshape(cin, 16 * co)
+
+
+def plan_upsample_dc_dgrad(cout: int) -> Plan:
+    """Gradient w.r.t. x through conv1x1 + pixel_shuffle: dX = sum over the four phases of dZ_phase * Wdc_phase^T."""
+    taps = [TapSpec(0, j * cout, 0, i, 0, _kb(cout), (i * 2 + j) * cout) for i in range(2) for j in range(2)]
+    return Plan([taps], [0], [0], a0_split=True, k_total=4 * cout, name="upsample_dc_dgrad", algo_k=4 * cout)
+
+
+def pack_upsample_dc_dgrad(w_dc: Tensor) -> Tensor:
+    """dc_conv weight [4Co, Cin, 1, 1] (output channel c*4+i*2+j) -> [Cin, 4Co] with K index (i*2+j)*Co + c."""
+    co4, cin = w_dc.shape[0], w_dc.shape[1]
+    return w_dc.reshape(co4 // 4, 2, 2, cin).permute(3, 1, 2, 0).reshape(cin, co4)

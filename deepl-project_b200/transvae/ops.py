@@ -53,6 +53,17 @@ def _set_view(v, t: Optional[Tensor], split: bool) -> None:
     v.split = 1 if split else 0
 
 
+def _fill_taps(d, plan: Plan) -> None:
+    d.num_phases = plan.num_phases
+    for ph, taps in enumerate(plan.phases):
+        d.ntaps[ph] = len(taps)
+        d.out_p[ph] = plan.out_p[ph]
+        d.out_c_off[ph] = plan.out_c_off[ph]
+        for i, t in enumerate(taps):
+            dt = d.taps[ph][i]
+            dt.map, dt.c_off, dt.dw, dt.p, dt.dh, dt.kblocks, dt.wk_off = t.map, t.c_off, t.dw, t.p, t.dh, t.kblocks, t.wk_off
+
+
 def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, out: Optional[Tensor] = None,
            out_shape: Optional[Sequence[int]] = None, bias: Optional[Tensor] = None, act: int = ACT_NONE,
            residual: Optional[Tensor] = None, row_scale: Optional[Tensor] = None, row_shift: Optional[Tensor] = None,
@@ -65,6 +76,7 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
     d = MtGemmDesc()
     _set_view(d.a0, a0, plan.a0_split)
     _set_view(d.a1, a1, plan.a1_split)
+    _fill_taps(d, plan)
     n_total = w.shape[0]
     if out_f32 is None and out_f32_shape is not None:
         out_f32 = torch.empty(tuple(out_f32_shape), dtype=torch.float32, device=a0.device)
@@ -80,14 +92,6 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
         assert residual.shape == out.shape
     d.w = w.data_ptr()
     d.n_total, d.k_total = n_total, plan.k_total
-    d.num_phases = plan.num_phases
-    for ph, taps in enumerate(plan.phases):
-        d.ntaps[ph] = len(taps)
-        d.out_p[ph] = plan.out_p[ph]
-        d.out_c_off[ph] = plan.out_c_off[ph]
-        for i, t in enumerate(taps):
-            dt = d.taps[ph][i]
-            dt.map, dt.c_off, dt.dw, dt.p, dt.dh, dt.kblocks, dt.wk_off = t.map, t.c_off, t.dw, t.p, t.dh, t.kblocks, t.wk_off
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == plan.num_phases * n_total, \
             (bias.shape, plan.num_phases, n_total)
@@ -114,7 +118,8 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
         o = out if out_f32 is None else out_f32
         n_real = out_n if out_f32 is not None else n_total
         m_out = o.numel() // (o.shape[1] if out_f32 is not None else o.shape[-1])
-        PROFILE.append((plan.name, 2.0 * m_out * n_real * plan.algo_k, e0, e1))
+        tag = f"{plan.name} M={m_out} N={n_total} K={plan.k_total} act={act} res={int(residual is not None)} rs={int(row_scale is not None)} rope={int(rope is not None)}"
+        PROFILE.append((tag, 2.0 * m_out * n_real * plan.algo_k, e0, e1))
     _count()
     return out if out_f32 is None else out_f32
 
@@ -253,3 +258,180 @@ def loss_sums(recon: Tensor, target: Tensor, mu: Tensor, logvar: Tensor, patched
                                            float(clip[0]), float(clip[1]), _stream()), "tvae_loss_l1_kl")
     _count(2)
     return acc
+
+
+# ------------------------------------------------------------------------------------------------
+# backward pass
+# ------------------------------------------------------------------------------------------------
+def mtgemm_wgrad(plan: Plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[Tensor] = None) -> Tensor:
+    """dW [n_total, k_total] fp32 of the forward ``mtgemm(plan, a0, w, a1=a1)`` given dZ (the gradient w.r.t. its
+    pre-activation output, same NHWC bf16 layout / view as the forward output)."""
+    _need_cuda(a0, dz, a1)
+    d = MtGemmDesc()
+    _set_view(d.a0, a0, plan.a0_split)
+    _set_view(d.a1, a1, plan.a1_split)
+    _set_view(d.out, dz, plan.out_split)
+    _fill_taps(d, plan)
+    d.n_total, d.k_total = n_total, plan.k_total
+    dw = torch.zeros(n_total, plan.k_total, dtype=torch.float32, device=a0.device)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.check(_lib.load().tvae_mtgemm_wgrad(C.byref(d), dw.data_ptr(), _stream()), f"tvae_mtgemm_wgrad[{plan.name}]")
+    if PROFILE is not None:
+        e1.record()
+        m_out = dz.numel() // dz.shape[-1]
+        PROFILE.append((f"wgrad {plan.name} M={m_out} N={n_total} K={plan.k_total}", 2.0 * m_out * n_total * plan.algo_k, e0, e1))
+    _count(2)
+    return dw
+
+
+def bias_act_bwd(dy: Tensor, z: Optional[Tensor], act: int, phase_view: bool = False) -> Tuple[Tensor, Tensor]:
+    """(dZ, column sums of dZ).  dy / z: bf16 with channels last.  ``phase_view``: dy is [B, 2H, 2W, C] and the sums
+    are returned per output phase as fp32 [2, 2, C] (p, q, c)."""
+    _need_cuda(dy, z)
+    assert dy.dtype == BF16 and dy.is_contiguous()
+    dz = torch.empty_like(dy) if act != ACT_NONE else dy
+    zp = _ptr(z) if act != ACT_NONE else None
+    dzp = dz.data_ptr() if act != ACT_NONE else None
+    if phase_view:
+        B, H2, W2, Cc = dy.shape
+        cs = torch.empty(2, 2 * Cc, dtype=torch.float32, device=dy.device)
+        _lib.check(_lib.load().tvae_bias_act_bwd_4d(dy.data_ptr(), zp, dzp, cs.data_ptr(), B * (H2 // 2), 2, W2 // 2,
+                                                    2 * Cc, act, _stream()), "tvae_bias_act_bwd_4d")
+        _count(2)
+        return dz, cs.view(2, 2, Cc)
+    N = dy.shape[-1]
+    M = dy.numel() // N
+    cs = torch.empty(N, dtype=torch.float32, device=dy.device)
+    _lib.check(_lib.load().tvae_bias_act_bwd(dy.data_ptr(), zp, dzp, cs.data_ptr(), M, N, act, _stream()),
+               "tvae_bias_act_bwd")
+    _count(2)
+    return dz, cs
+
+
+def act_fwd(z: Tensor, act: int) -> Tensor:
+    _need_cuda(z)
+    assert z.dtype == BF16 and z.is_contiguous()
+    y = torch.empty_like(z)
+    _lib.check(_lib.load().tvae_act_fwd(z.data_ptr(), y.data_ptr(), z.numel(), act, _stream()), "tvae_act_fwd")
+    _count()
+    return y
+
+
+def groupnorm_bwd(x: Tensor, dh: Tensor, sums: Tensor, gamma: Tensor, beta: Tensor, add: Optional[Tensor] = None,
+                  groups: int = 32, eps: float = 1e-5, silu: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
+    """Backward of h = act(GroupNorm(x)): returns (dx [+ add], dgamma, dbeta)."""
+    _need_cuda(x, dh, sums, gamma, beta, add)
+    B, H, W, Cc = x.shape
+    g, b = gamma.float().contiguous(), beta.float().contiguous()
+    part = torch.empty(B, Cc, 2, dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x)
+    _lib.check(_lib.load().tvae_groupnorm_bwd(x.data_ptr(), dh.data_ptr(), _ptr(add), sums.data_ptr(), g.data_ptr(),
+                                              b.data_ptr(), part.data_ptr(), dx.data_ptr(), B, H * W, Cc, groups, eps,
+                                              1 if silu else 0, _stream()), "tvae_groupnorm_bwd")
+    _count(3)
+    red = part.sum(0)          # [C, 2]: tiny (B x C) reduction of the per-image partials
+    return dx, red[:, 1].contiguous(), red[:, 0].contiguous()
+
+
+def token_norm_fwd(x: Tensor, w: Tensor, mode: int) -> Tensor:
+    _need_cuda(x, w)
+    assert x.dtype == BF16 and x.is_contiguous()
+    Cc = x.shape[-1]
+    y = torch.empty_like(x)
+    wf = w.float().contiguous()
+    _lib.check(_lib.load().tvae_token_norm_fwd(x.data_ptr(), wf.data_ptr(), y.data_ptr(), x.numel() // Cc, Cc, mode,
+                                               _stream()), "tvae_token_norm_fwd")
+    _count()
+    return y
+
+
+def token_norm_bwd(x: Tensor, w: Tensor, dy: Tensor, add: Optional[Tensor], mode: int) -> Tuple[Tensor, Tensor]:
+    _need_cuda(x, w, dy, add)
+    Cc = x.shape[-1]
+    dx = torch.empty_like(x)
+    dw = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    wf = w.float().contiguous()
+    _lib.check(_lib.load().tvae_token_norm_bwd(x.data_ptr(), wf.data_ptr(), dy.data_ptr(), _ptr(add), dx.data_ptr(),
+                                               dw.data_ptr(), x.numel() // Cc, Cc, mode, _stream()), "tvae_token_norm_bwd")
+    _count(2)
+    return dx, dw
+
+
+def attn_bwd(qkv: Tensor, out: Tensor, dout: Tensor, lse: Tensor, rope_tab: Tensor, B: int, S: int, C_: int, H: int,
+             W: int, q_scale: float) -> Tensor:
+    """Gradient w.r.t. the PRE-RoPE, pre-scale q | k | v projection output, bf16 [B, S, 3C]."""
+    _need_cuda(qkv, out, dout, lse, rope_tab)
+    lib = _lib.load()
+    dev = qkv.device
+    delta = torch.empty(B, C_ // 64, S, dtype=torch.float32, device=dev)
+    dq_acc = torch.empty(B, S, C_, dtype=torch.float32, device=dev)
+    dqkv = torch.empty(B, S, 3 * C_, dtype=BF16, device=dev)
+    dout = dout.contiguous()
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.check(lib.tvae_attn_delta(out.data_ptr(), dout.data_ptr(), delta.data_ptr(), B, S, C_, _stream()), "tvae_attn_delta")
+    _lib.check(lib.tvae_attn_bwd(qkv.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(), dq_acc.data_ptr(),
+                                 dqkv.data_ptr(), B, S, C_, _stream()), "tvae_attn_bwd")
+    _lib.check(lib.tvae_rope_bwd(dq_acc.data_ptr(), dqkv.data_ptr(), rope_tab.data_ptr(), B * S, C_, H, W, q_scale,
+                                 _stream()), "tvae_rope_bwd")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append(("attn_bwd", 10.0 * B * S * S * C_, e0, e1))
+    _count(4)
+    return dqkv
+
+
+def conv_in_wgrad(x: Tensor, dy: Tensor) -> Tuple[Tensor, Tensor]:
+    _need_cuda(x, dy)
+    x = x.float().contiguous()
+    B, Cin, H, W = x.shape
+    Co = dy.shape[-1]
+    dw = torch.empty(Co, Cin, 3, 3, dtype=torch.float32, device=x.device)
+    db = torch.empty(Co, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().tvae_conv_in_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), B, H, W, Co,
+                                              _stream()), "tvae_conv_in_wgrad")
+    _count(3)
+    return dw, db
+
+
+def loss_bwd(recon: Tensor, target: Tensor, mu: Tensor, logvar: Tensor, scal: Tensor, patched: bool,
+             clip: Tuple[float, float]) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda(recon, target, mu, logvar, scal)
+    drecon, dmu, dlv = torch.empty_like(recon), torch.empty_like(mu), torch.empty_like(logvar)
+    _lib.check(_lib.load().tvae_loss_bwd(recon.data_ptr(), target.data_ptr(), mu.data_ptr(), logvar.data_ptr(),
+                                         scal.data_ptr(), drecon.data_ptr(), dmu.data_ptr(), dlv.data_ptr(), recon.numel(),
+                                         mu.numel(), 1 if patched else 0, float(clip[0]), float(clip[1]), _stream()),
+               "tvae_loss_bwd")
+    _count(2)
+    return drecon, dmu, dlv
+
+
+def latent_bwd(mu: Tensor, logvar: Tensor, eps: Tensor, dz: Optional[Tensor], dmu_ret: Optional[Tensor],
+               dlv_ret: Optional[Tensor], patched: bool) -> Tuple[Tensor, Tensor]:
+    _need_cuda(mu, logvar, eps, dz, dmu_ret, dlv_ret)
+    dmu, dlv = torch.empty_like(mu), torch.empty_like(mu)
+    c = lambda t: None if t is None else t.float().contiguous()
+    dz, dmu_ret, dlv_ret = c(dz), c(dmu_ret), c(dlv_ret)
+    _lib.check(_lib.load().tvae_latent_bwd(mu.data_ptr(), logvar.data_ptr(), eps.data_ptr(), _ptr(dz), _ptr(dmu_ret),
+                                           _ptr(dlv_ret), dmu.data_ptr(), dlv.data_ptr(), mu.numel(), 1 if patched else 0,
+                                           _stream()), "tvae_latent_bwd")
+    _count()
+    return dmu, dlv
+
+
+def sumsq(g: Tensor, out: Tensor) -> None:
+    """out[0] += sum(g^2) for a flat fp32 buffer (length % 4 == 0)."""
+    _need_cuda(g, out)
+    _lib.check(_lib.load().tvae_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream()), "tvae_sumsq")
+    _count()
+
+
+def adamw(p: Tensor, g: Tensor, m: Tensor, v: Tensor, ctrl: Tensor, lr: float, betas=(0.9, 0.95), eps: float = 1e-8,
+          weight_decay: float = 0.0, step: int = 1) -> None:
+    _need_cuda(p, g, m, v, ctrl)
+    _lib.check(_lib.load().tvae_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), ctrl.data_ptr(),
+                                      lr, betas[0], betas[1], eps, weight_decay, step, _stream()), "tvae_adamw")
+    _count()

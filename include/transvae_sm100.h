@@ -127,6 +127,59 @@ int tvae_reparam(const float* mu, const float* logvar, const float* eps, float* 
 int tvae_loss_l1_kl(const float* recon, const float* target, const float* mu, const float* logvar, float* acc,
                     int64_t n_img, int64_t n_lat, int32_t patched, float clip_lo, float clip_hi, void* stream);
 
+/* ---- backward pass ------------------------------------------------------------------------------
+ * Weight gradient of tvae_mtgemm: dw[n, wk_off + k] += sum_pixels dZ[pixel, n] * A_tap[pixel, k] for every tap of
+ * `desc` (same a0 / a1 / taps / n_total / k_total as the forward call; desc->out is the dZ view, i.e. the gradient
+ * w.r.t. the forward pre-activation output; bias / act / rope / residual fields are ignored).  dw: fp32
+ * [n_total, k_total], accumulated into (caller zeroes).  Replaces autograd's weight-gradient convolution / matmul for
+ * every nn.Conv2d / nn.Linear listed at tvae_mtgemm.  Input gradients are tvae_mtgemm launches with transposed taps. */
+int tvae_mtgemm_wgrad(const tvae_mtgemm_desc* desc /* HOST pointer */, float* dw, void* stream);
+/* dZ = dY * act'(Z) and colsum[n] = sum_m dZ[m, n] (= bias gradient) for a row-major bf16 [M, N] matrix.
+ * act == TVAE_ACT_NONE: z / dz may be NULL, only the column sums are produced. */
+int tvae_bias_act_bwd(const void* dy, const void* z, void* dz, float* colsum, int64_t M, int32_t N, int32_t act,
+                      void* stream);
+/* Same over a 4-D contiguous bf16 tensor [R0, P, R1, Q] with colsum fp32 [P, Q] (phase views: P = 2). */
+int tvae_bias_act_bwd_4d(const void* dy, const void* z, void* dz, float* colsum, int64_t R0, int32_t P, int32_t R1,
+                         int32_t Q, int32_t act, void* stream);
+/* y = act(z), bf16, n elements (n % 8 == 0). */
+int tvae_act_fwd(const void* z, void* y, int64_t n, int32_t act, void* stream);
+/* GroupNorm(+SiLU) backward (blocks.py:60-66): dx = dGN(dh) [+ add]; part fp32 [B, C, 2] = per-(image, channel)
+ * (sum dy, sum dy*xhat) from which the caller reduces dgamma / dbeta.  sums = tvae_groupnorm_stats(x). */
+int tvae_groupnorm_bwd(const void* x, const void* dh, const void* add, const float* sums, const float* gamma,
+                       const float* beta, float* part, void* dx, int32_t B, int32_t HW, int32_t C, int32_t G, float eps,
+                       int32_t apply_silu, void* stream);
+/* Materialised token norms of the training path: mode 0 RMSNorm (blocks.py:168-201), mode 1 RMSNorm followed by the
+ * affine-free LayerNorm shared by norm_q/k/v (attention.py:71-73).  x, y, dy, add, dx: bf16 [M, C]; w, dw: fp32 [C]. */
+int tvae_token_norm_fwd(const void* x, const float* w, void* y, int64_t M, int32_t C, int32_t mode, void* stream);
+int tvae_token_norm_bwd(const void* x, const float* w, const void* dy, const void* add, void* dx, float* dw, int64_t M,
+                        int32_t C, int32_t mode, void* stream);
+/* Attention backward (attention.py:88-92).  delta fp32 [B, C/64, S] = rowsum(dout * out); dq_acc fp32 [B, S, C]
+ * (zeroed inside); dqkv bf16 [B, S, 3C]: k / v thirds written by tvae_attn_bwd (rotated space), q third and the
+ * transposed RoPE of q and k by tvae_rope_bwd (q_scale = head_dim^-0.5). */
+int tvae_attn_delta(const void* out, const void* dout, float* delta, int32_t B, int32_t S, int32_t C, void* stream);
+int tvae_attn_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, float* dq_acc, void* dqkv,
+                  int32_t B, int32_t S, int32_t C, void* stream);
+int tvae_rope_bwd(const float* dq_acc, void* dqkv, const float* rope_tab, int64_t M, int32_t C, int32_t H, int32_t W,
+                  float q_scale, void* stream);
+/* encoder.conv_in weight / bias gradient (Cin = 3): dw fp32 [Cout, 3, 3, 3], db fp32 [Cout] (zeroed inside). */
+int tvae_conv_in_wgrad(const float* x_nchw, const void* dy_nhwc, float* dw, float* db, int32_t B, int32_t H, int32_t W,
+                       int32_t Cout, void* stream);
+/* Loss backward: scal (device fp32[2]) = {dLoss * l1_weight / numel(recon), dLoss * kl_weight / kl_norm}. */
+int tvae_loss_bwd(const float* recon, const float* target, const float* mu, const float* logvar, const float* scal,
+                  float* drecon, float* dmu, float* dlogvar, int64_t n_img, int64_t n_lat, int32_t patched, float clip_lo,
+                  float clip_hi, void* stream);
+/* Reparameterisation backward: folds the gradients arriving on (z, mu', logvar') back onto (mu, logvar). */
+int tvae_latent_bwd(const float* mu, const float* logvar, const float* eps, const float* dz, const float* dmu_ret,
+                    const float* dlv_ret, float* dmu, float* dlogvar, int64_t n, int32_t patched, void* stream);
+
+/* ---- optimiser (train.py:608-620: clip_grad_norm_ + fused AdamW) ----------------------------------
+ * tvae_sumsq: out[0] += sum g^2 over a flat fp32 buffer (n % 4 == 0).
+ * tvae_adamw: one fused step over flat fp32 p / g / m / v.  ctrl (device fp32[4]) = {global sum of squared grads,
+ * max_norm (<= 0: no clipping), gradient pre-scale, skip flag}; a non-finite norm skips the step (train_2.py:329-338). */
+int tvae_sumsq(const float* g, int64_t n, float* out, void* stream);
+int tvae_adamw(float* p, const float* g, float* m, float* v, int64_t n, const float* ctrl, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int32_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

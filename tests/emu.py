@@ -47,3 +47,20 @@ def emulate(plan, a0, a1, wp, out_shape, bias=None):
             acc = acc + bias[ph]
         o5[:, :, plan.out_p[ph], :, plan.out_c_off[ph]:plan.out_c_off[ph] + N] = acc
     return out
+
+
+def emulate_wgrad(plan, a0, a1, dz, n_total):
+    """dW_packed [n_total, k_total] exactly as tvae_mtgemm_wgrad computes it (fp32)."""
+    v0 = view5(a0, plan.a0_split)
+    v1 = view5(a1, plan.a1_split) if a1 is not None else None
+    z5 = view5(dz, plan.out_split)
+    dw = torch.zeros(n_total, plan.k_total)
+    for ph, taps in enumerate(plan.phases):
+        g = z5[:, :, plan.out_p[ph], :, plan.out_c_off[ph]:plan.out_c_off[ph] + n_total]   # [B, Hv, Wv, N]
+        g2 = g.reshape(-1, n_total)
+        for t in taps:
+            src = v1 if t.map else v0
+            kc = t.kblocks * 64
+            a = fetch(src, t.c_off, kc, t.dw, t.p, t.dh).reshape(-1, kc)
+            dw[:, t.wk_off:t.wk_off + kc] += g2.t() @ a
+    return dw

@@ -61,9 +61,13 @@ def test_gemm_epilogues():
     assert rel(y, F.silu(acc + b)) < 1e-2
     y = ops.linear(x, w, T.plan_linear(K), bias=b, residual=res)
     assert rel(y, acc + b + res.float()) < 1e-2
-    y = ops.linear(x, w, T.plan_linear(K), bias=b, row_scale=rs, row_shift=rsh, col_sum=cs, act=ops.ACT_GELU, residual=res)
-    ref = F.gelu(acc * rs[:, None] - rsh[:, None] * cs[None] + b) + res.float()
+    y = ops.linear(x, w, T.plan_linear(K), bias=b, row_scale=rs, row_shift=rsh, col_sum=cs, residual=res)
+    ref = acc * rs[:, None] - rsh[:, None] * cs[None] + b + res.float()
     assert rel(y, ref) < 1e-2
+    y = ops.linear(x, w, T.plan_linear(K), bias=b, row_scale=rs, act=ops.ACT_GELU)
+    assert rel(y, F.gelu(acc * rs[:, None] + b)) < 1e-2
+    y = ops.linear(x, w, T.plan_linear(K))
+    assert rel(y, acc) < 1e-2
 
 
 @pytest.mark.parametrize("B,C,H,W,N", [(2, 64, 16, 16, 64), (1, 192, 128, 128, 192), (3, 128, 32, 32, 256),
@@ -71,10 +75,14 @@ def test_gemm_epilogues():
 def test_conv3x3(B, C, H, W, N):
     x, w, b = bf(rnd(B, C, H, W)), bf(rnd(N, C, 3, 3, seed=1, scale=0.05)), rnd(N, seed=2)
     res = bf(rnd(B, N, H, W, seed=3))
-    y = ops.mtgemm(T.plan_conv3x3(C), nhwc(x), T.pack_conv3x3(w).contiguous(), out_shape=(B, H, W, N), bias=b,
-                   residual=nhwc(res), act=ops.ACT_SILU)
-    ref = F.silu(F.conv2d(x.float(), w.float(), b, padding=1)) + res.float()
-    assert rel(nchw(y), ref) < 1e-2, rel(nchw(y), ref)
+    wp = T.pack_conv3x3(w).contiguous()
+    conv = F.conv2d(x.float(), w.float(), b, padding=1)
+    y = ops.mtgemm(T.plan_conv3x3(C), nhwc(x), wp, out_shape=(B, H, W, N), bias=b, residual=nhwc(res))
+    assert rel(nchw(y), conv + res.float()) < 1e-2, rel(nchw(y), conv + res.float())
+    y = ops.mtgemm(T.plan_conv3x3(C), nhwc(x), wp, out_shape=(B, H, W, N), bias=b, act=ops.ACT_SILU)
+    assert rel(nchw(y), F.silu(conv)) < 1e-2
+    y = ops.mtgemm(T.plan_conv3x3(C), nhwc(x), wp, out_shape=(B, H, W, N), bias=b, act=ops.ACT_GELU)
+    assert rel(nchw(y), F.gelu(conv)) < 1e-2
 
 
 @pytest.mark.parametrize("B,C,Co,H", [(2, 64, 128, 16), (1, 192, 192, 64), (2, 128, 256, 8)])
