@@ -1,0 +1,370 @@
+"""Training path: block-level ``torch.autograd.Function``s whose forward AND backward are hand-written kernels.
+
+Granularity is one Function per reference module (ResBlock, Downsample, Upsample, the attention half and the FFN half
+of a TransVAEBlock, the first / last convolutions, the latent heads, reparameterisation, loss) so that residual adds,
+bias gradients and activation derivatives stay fused inside the kernels and autograd only chains block to block.
+
+Weights enter as fp32 *packed* tensors produced by differentiable torch ops on the reference-layout parameters
+(``_taps.pack_*`` -- weight-side plumbing); the Functions return fp32 gradients for them (tcgen05 wgrad kernel) and
+autograd maps those back to the parameters.  Activations and their gradients are NHWC bf16.
+
+Unlike the inference path (which folds RMSNorm / LayerNorm into GEMM epilogues), the training path materialises the
+normalised token tensors with ``tvae_token_norm_fwd`` so that the projections stay plain GEMMs in the backward pass.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _taps as T
+from . import ops
+from ._lib import ACT_GELU, ACT_NONE, ACT_SILU
+
+Tensor = torch.Tensor
+BF16 = torch.bfloat16
+Fn = torch.autograd.Function
+
+
+def _bf(w: Tensor) -> Tensor:
+    return w.detach().to(BF16).contiguous()
+
+
+def _tr(wp: Tensor, taps: int) -> Tensor:
+    """Packed forward weight [N, taps*C] -> dgrad weight [C, taps*N] (bf16)."""
+    n = wp.shape[0]
+    c = wp.shape[1] // taps
+    return wp.detach().view(n, taps, c).permute(2, 1, 0).reshape(c, taps * n).to(BF16).contiguous()
+
+
+def _f32(t: Tensor) -> Tensor:
+    return t.detach().float().contiguous()
+
+
+def _colsum(dy: Tensor) -> Tensor:
+    return ops.bias_act_bwd(dy, None, ACT_NONE)[1]
+
+
+def _flat(x: Tensor) -> Tensor:
+    return x.reshape(1, 1, -1, x.shape[-1])
+
+
+# ------------------------------------------------------------------------------------------------
+class ResBlockFn(Fn):
+    """x + conv2(silu(GN2(conv1(silu(GN1(x))))))  (blocks.py:58-68)."""
+
+    @staticmethod
+    def forward(ctx, x, g1, b1, w1p, c1b, g2, b2, w2p, c2b):
+        B, H, W, C = x.shape
+        plan = T.plan_conv3x3(C)
+        s1 = ops.groupnorm_stats(x)
+        h0 = ops.groupnorm_silu(x, g1, b1, sums=s1)
+        h1 = ops.mtgemm(plan, h0, _bf(w1p), out_shape=(B, H, W, C), bias=_f32(c1b))
+        s2 = ops.groupnorm_stats(h1)
+        h2 = ops.groupnorm_silu(h1, g2, b2, sums=s2)
+        out = ops.mtgemm(plan, h2, _bf(w2p), out_shape=(B, H, W, C), bias=_f32(c2b), residual=x)
+        ctx.save_for_backward(x, s1, h0, h1, s2, h2, g1, b1, w1p, g2, b2, w2p)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, s1, h0, h1, s2, h2, g1, b1, w1p, g2, b2, w2p = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, H, W, C = x.shape
+        dplan = T.plan_conv3x3_dgrad(C)
+        dc2b = _colsum(dout)
+        dw2 = ops.mtgemm_wgrad(T.plan_conv3x3(C), h2, dout, C)
+        dh2 = ops.mtgemm(dplan, dout, _tr(w2p, 9), out_shape=(B, H, W, C))
+        dh1, dg2, db2 = ops.groupnorm_bwd(h1, dh2, s2, g2, b2)
+        dc1b = _colsum(dh1)
+        dw1 = ops.mtgemm_wgrad(T.plan_conv3x3(C), h0, dh1, C)
+        dh0 = ops.mtgemm(dplan, dh1, _tr(w1p, 9), out_shape=(B, H, W, C))
+        dx, dg1, db1 = ops.groupnorm_bwd(x, dh0, s1, g1, b1, add=dout)
+        return dx, dg1, db1, dw1, dc1b, dg2, db2, dw2, dc2b
+
+
+class DownsampleFn(Fn):
+    """conv3x3 s2 (silu(conv3x3(x))) + conv1x1(pixel_unshuffle(x))  (upsample.py:55-66)."""
+
+    @staticmethod
+    def forward(ctx, x, w0p, b0, wdp, bd):
+        B, H, W, C = x.shape
+        N = wdp.shape[0]
+        z0 = ops.mtgemm(T.plan_conv3x3(C), x, _bf(w0p), out_shape=(B, H, W, C), bias=_f32(b0))
+        y = ops.act_fwd(z0, ACT_SILU)
+        out = ops.mtgemm(T.plan_downsample(C), y, _bf(wdp), a1=x, out_shape=(B, H // 2, W // 2, N), bias=_f32(bd))
+        ctx.save_for_backward(x, z0, y, w0p, wdp)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, z0, y, w0p, wdp = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, H, W, C = x.shape
+        N = wdp.shape[0]
+        dbd = _colsum(dout)
+        dwd = ops.mtgemm_wgrad(T.plan_downsample(C), y, dout, N, a1=x)
+        dy = ops.mtgemm(T.plan_downsample_dgrad_main(C, N), dout, _tr(wdp[:, :9 * C], 9), out_shape=(B, H, W, C))
+        dx_dc = ops.mtgemm(T.plan_downsample_dgrad_dc(C, N), dout, _tr(wdp[:, 9 * C:], 4), out_shape=(B, H, W, C))
+        dz0, db0 = ops.bias_act_bwd(dy, z0, ACT_SILU)
+        dw0 = ops.mtgemm_wgrad(T.plan_conv3x3(C), x, dz0, C)
+        dx = ops.mtgemm(T.plan_conv3x3_dgrad(C), dz0, _tr(w0p, 9), out_shape=(B, H, W, C), residual=dx_dc)
+        return dx, dw0, db0, dwd, dbd
+
+
+class UpsampleFn(Fn):
+    """conv3x3(silu(conv3x3(nearest2x(x)))) + pixel_shuffle(conv1x1(x))  (upsample.py:116-126)."""
+
+    @staticmethod
+    def forward(ctx, x, w1p, b1, w2p, b2p):
+        B, H, W, Ci = x.shape
+        Co = w1p.shape[0]
+        b1e = _f32(b1).unsqueeze(0).expand(4, -1).contiguous()
+        z1 = ops.mtgemm(T.plan_upsample_conv1(Ci, Co), x, _bf(w1p), out_shape=(B, 2 * H, 2 * W, Co), bias=b1e)
+        y = ops.act_fwd(z1, ACT_SILU)
+        out = ops.mtgemm(T.plan_upsample_conv2(Co, Ci), y, _bf(w2p), a1=x, out_shape=(B, 2 * H, 2 * W, Co), bias=_f32(b2p))
+        ctx.save_for_backward(x, z1, y, w1p, w2p)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, z1, y, w1p, w2p = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, H, W, Ci = x.shape
+        Co = w1p.shape[0]
+        _, cs = ops.bias_act_bwd(dout, None, ACT_NONE, phase_view=True)       # [2, 2, Co] per output phase
+        db2p = cs.reshape(4, Co)
+        dw2 = ops.mtgemm_wgrad(T.plan_upsample_conv2(Co, Ci), y, dout, Co, a1=x)
+        dy = ops.mtgemm(T.plan_conv3x3_dgrad(Co), dout, _tr(w2p[:, :9 * Co], 9), out_shape=(B, 2 * H, 2 * W, Co))
+        dx_dc = ops.mtgemm(T.plan_upsample_dc_dgrad(Co), dout, _tr(w2p[:, 9 * Co:], 4), out_shape=(B, H, W, Ci))
+        dz1, db1 = ops.bias_act_bwd(dy, z1, ACT_SILU)
+        dw1 = ops.mtgemm_wgrad(T.plan_upsample_conv1(Ci, Co), x, dz1, Co)
+        dx = ops.mtgemm(T.plan_upsample_conv1_dgrad(Ci, Co), dz1, _tr(w1p, 16), out_shape=(B, H, W, Ci), residual=dx_dc)
+        return dx, dw1, db1, dw2, db2p
+
+
+class AttnFn(Fn):
+    """x + proj(SDPA(rope(q), rope(k), v)), q|k|v = [Wq g_q; Wk g_k; Wv g_v] LNhat(RMSNorm(x; w1)) + [Wq b_q; ...]
+    (blocks.py:146, attention.py:65-104).  ``wqkv`` / ``bqkv`` already contain the LayerNorm affines."""
+
+    @staticmethod
+    def forward(ctx, x, w1, wqkv, bqkv, wproj, bproj, rope_tab, scale):
+        B, H, W, C = x.shape
+        S = H * W
+        xh = ops.token_norm_fwd(x, w1, 1)
+        rope = (rope_tab, C, H, W, scale * math.log2(math.e))
+        qkv = ops.mtgemm(T.plan_linear(C), _flat(xh), _bf(wqkv), out_shape=(1, 1, B * S, 3 * C), bias=_f32(bqkv), rope=rope)
+        o, lse = ops.attn_fwd(qkv.view(B, S, 3 * C), B, S, C, need_lse=True)
+        out = ops.mtgemm(T.plan_linear(C), _flat(o), _bf(wproj), out_shape=(1, 1, B * S, C), bias=_f32(bproj),
+                         residual=_flat(x))
+        ctx.save_for_backward(x, w1, xh, qkv, o, lse, wqkv, wproj, rope_tab)
+        ctx.scale = scale
+        return out.view(B, H, W, C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w1, xh, qkv, o, lse, wqkv, wproj, rope_tab = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, H, W, C = x.shape
+        S = H * W
+        df = _flat(dout)
+        dbp = _colsum(df)
+        dwp = ops.mtgemm_wgrad(T.plan_linear(C), _flat(o), df, C)
+        do = ops.mtgemm(T.plan_linear(C), df, _bf(wproj.detach().t()), out_shape=(1, 1, B * S, C))
+        dqkv = ops.attn_bwd(qkv.view(B, S, 3 * C), o, do.view(B, S, C), lse, rope_tab, B, S, C, H, W, ctx.scale)
+        dq = _flat(dqkv)
+        dbq = _colsum(dq)
+        dwq = ops.mtgemm_wgrad(T.plan_linear(C), _flat(xh), dq, 3 * C)
+        dxh = ops.mtgemm(T.plan_linear(3 * C), dq, _bf(wqkv.detach().t()), out_shape=(1, 1, B * S, C))
+        dx, dw1 = ops.token_norm_bwd(x, w1, dxh.view(B, H, W, C), dout, 1)
+        return dx, dw1, dwq, dbq, dwp, dbp, None, None
+
+
+class FfnFn(Fn):
+    """x + proj_out(u + conv(u)), u = gelu(proj_in(RMSNorm(x; w2)))  (blocks.py:149, conv.py:79-105)."""
+
+    @staticmethod
+    def forward(ctx, x, w2n, win, bin_, wc0, bc0, wc2p, bc2, wc4, bc4, wout, bout):
+        B, H, W, C = x.shape
+        M = B * H * W
+        hid, mid = win.shape[0], wc0.shape[0]
+        xn = ops.token_norm_fwd(x, w2n, 0)
+        z_in = ops.mtgemm(T.plan_linear(C), _flat(xn), _bf(win), out_shape=(1, 1, M, hid), bias=_f32(bin_))
+        u = ops.act_fwd(z_in, ACT_GELU)
+        z0 = ops.mtgemm(T.plan_linear(hid), u, _bf(wc0), out_shape=(1, 1, M, mid), bias=_f32(bc0))
+        t0 = ops.act_fwd(z0, ACT_GELU)
+        z2 = ops.mtgemm(T.plan_conv3x3(mid), t0.view(B, H, W, mid), _bf(wc2p), out_shape=(B, H, W, mid), bias=_f32(bc2))
+        t2 = ops.act_fwd(z2, ACT_GELU)
+        u2 = ops.mtgemm(T.plan_linear(mid), _flat(t2), _bf(wc4), out_shape=(1, 1, M, hid), bias=_f32(bc4), residual=u)
+        out = ops.mtgemm(T.plan_linear(hid), u2, _bf(wout), out_shape=(1, 1, M, C), bias=_f32(bout), residual=_flat(x))
+        ctx.save_for_backward(x, w2n, xn, z_in, u, z0, t0, z2, t2, u2, win, wc0, wc2p, wc4, wout)
+        return out.view(B, H, W, C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w2n, xn, z_in, u, z0, t0, z2, t2, u2, win, wc0, wc2p, wc4, wout = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, H, W, C = x.shape
+        M = B * H * W
+        hid, mid = win.shape[0], wc0.shape[0]
+        df = _flat(dout)
+        dbout = _colsum(df)
+        dwout = ops.mtgemm_wgrad(T.plan_linear(hid), u2, df, C)
+        du2 = ops.mtgemm(T.plan_linear(C), df, _bf(wout.detach().t()), out_shape=(1, 1, M, hid))
+        dbc4 = _colsum(du2)
+        dwc4 = ops.mtgemm_wgrad(T.plan_linear(mid), _flat(t2), du2, hid)
+        dt2 = ops.mtgemm(T.plan_linear(hid), du2, _bf(wc4.detach().t()), out_shape=(1, 1, M, mid))
+        dz2, dbc2 = ops.bias_act_bwd(dt2, z2.view(1, 1, M, mid), ACT_GELU)
+        dz2i = dz2.view(B, H, W, mid)
+        dwc2 = ops.mtgemm_wgrad(T.plan_conv3x3(mid), t0.view(B, H, W, mid), dz2i, mid)
+        dt0 = ops.mtgemm(T.plan_conv3x3_dgrad(mid), dz2i, _tr(wc2p, 9), out_shape=(B, H, W, mid))
+        dz0, dbc0 = ops.bias_act_bwd(_flat(dt0), z0, ACT_GELU)
+        dwc0 = ops.mtgemm_wgrad(T.plan_linear(hid), u, dz0, mid)
+        du = ops.mtgemm(T.plan_linear(mid), dz0, _bf(wc0.detach().t()), out_shape=(1, 1, M, hid), residual=du2)
+        dzin, dbin = ops.bias_act_bwd(du, z_in, ACT_GELU)
+        dwin = ops.mtgemm_wgrad(T.plan_linear(C), _flat(xn), dzin, hid)
+        dxn = ops.mtgemm(T.plan_linear(hid), dzin, _bf(win.detach().t()), out_shape=(1, 1, M, C))
+        dx, dw2n = ops.token_norm_bwd(x, w2n, dxn.view(B, H, W, C), dout, 0)
+        return dx, dw2n, dwin, dbin, dwc0, dbc0, dwc2, dbc2, dwc4, dbc4, dwout, dbout
+
+
+class ConvInFn(Fn):
+    """encoder.conv_in (encoder.py:111): NCHW fp32 image -> NHWC bf16 features; no input gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x)
+        return ops.conv_in(x, w.detach(), None if b is None else b.detach())
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dw, db = ops.conv_in_wgrad(x, dy.contiguous())
+        return None, dw, db
+
+
+class Conv3x3Fn(Fn):
+    """Plain 3x3 conv on an NHWC bf16 input whose channel count is already padded to 64 (decoder.conv_in)."""
+
+    @staticmethod
+    def forward(ctx, xn, wp, b):
+        B, H, W, C = xn.shape
+        out = ops.mtgemm(T.plan_conv3x3(C), xn, _bf(wp), out_shape=(B, H, W, wp.shape[0]), bias=_f32(b))
+        ctx.save_for_backward(xn, wp)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xn, wp = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, H, W, C = xn.shape
+        N = wp.shape[0]
+        db = _colsum(dout)
+        dw = ops.mtgemm_wgrad(T.plan_conv3x3(C), xn, dout, N)
+        dx = ops.mtgemm(T.plan_conv3x3_dgrad(N), dout, _tr(wp, 9), out_shape=(B, H, W, C)) if ctx.needs_input_grad[0] else None
+        return dx, dw, db
+
+
+class HeadFn(Fn):
+    """3x3 conv to a few fp32 NCHW channels (conv_mu | conv_logvar fused, transvae.py:182-183; decoder.conv_out,
+    decoder.py:130).  ``wp`` / ``b`` are padded to 64 output rows; the first ``n_out`` are real."""
+
+    @staticmethod
+    def forward(ctx, h, wp, b, n_out):
+        B, H, W, C = h.shape
+        out = ops.mtgemm(T.plan_conv3x3(C), h, _bf(wp), bias=_f32(b), out_f32_shape=(B, n_out, H, W), out_n=n_out)
+        ctx.save_for_backward(h, wp)
+        ctx.n_out = n_out
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, wp = ctx.saved_tensors
+        B, H, W, C = h.shape
+        npad = wp.shape[0]
+        dz = ops.nchw_to_nhwc(dout.float().contiguous(), npad)      # zero-padded channels
+        db = _colsum(dz)
+        dw = ops.mtgemm_wgrad(T.plan_conv3x3(C), h, dz, npad)
+        dh = ops.mtgemm(T.plan_conv3x3_dgrad(npad), dz, _tr(wp, 9), out_shape=(B, H, W, C))
+        return dh, dw, db, None
+
+
+class GroupNormSilu(Fn):
+    """silu(GroupNorm(x)) standalone (decoder.norm_out, decoder.py:128-129)."""
+
+    @staticmethod
+    def forward(ctx, x, g, b, silu):
+        s = ops.groupnorm_stats(x)
+        ctx.save_for_backward(x, s, g, b)
+        ctx.silu = silu
+        return ops.groupnorm_silu(x, g, b, silu=silu, sums=s)
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, s, g, b = ctx.saved_tensors
+        dx, dg, db = ops.groupnorm_bwd(x, dh.contiguous(), s, g, b, silu=ctx.silu)
+        return dx, dg, db, None
+
+
+class NchwToNhwc(Fn):
+    @staticmethod
+    def forward(ctx, x, cpad):
+        ctx.c = x.shape[1]
+        return ops.nchw_to_nhwc(x, cpad)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.nhwc_to_nchw(dy.contiguous(), ctx.c), None
+
+
+class NhwcToNchw(Fn):
+    @staticmethod
+    def forward(ctx, x, c):
+        ctx.cs = x.shape[-1]
+        return ops.nhwc_to_nchw(x, c)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.nchw_to_nhwc(dy.contiguous(), ctx.cs), None
+
+
+class Reparam(Fn):
+    """(z, mu', logvar') = reparameterise(mu, logvar; eps)  (transvae.py:186-199, patched :186-196 / :244-245)."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, eps, patched):
+        z, mu_c, lv_c = ops.reparam(mu, logvar, eps, patched)
+        ctx.save_for_backward(mu, logvar, eps)
+        ctx.patched = patched
+        if not patched:
+            mu_c, lv_c = mu.clone(), logvar.clone()
+        return z, mu_c, lv_c
+
+    @staticmethod
+    def backward(ctx, dz, dmu_c, dlv_c):
+        mu, logvar, eps = ctx.saved_tensors
+        dmu, dlv = ops.latent_bwd(mu.float().contiguous(), logvar.float().contiguous(), eps.float().contiguous(), dz, dmu_c,
+                                  dlv_c, ctx.patched)
+        return dmu, dlv, None, None
+
+
+class LossSums(Fn):
+    """(sum |f(recon) - target|, sum KL terms, #non-finite)  (vae_loss.py:83, :94-95; patched :80-104)."""
+
+    @staticmethod
+    def forward(ctx, recon, target, mu, logvar, patched, clip_lo, clip_hi):
+        acc = ops.loss_sums(recon, target, mu, logvar, patched, (clip_lo, clip_hi))
+        ctx.save_for_backward(recon, target, mu, logvar)
+        ctx.cfg = (patched, clip_lo, clip_hi)
+        ctx.mark_non_differentiable(acc[2])
+        return acc[0], acc[1], acc[2]
+
+    @staticmethod
+    def backward(ctx, g_l1, g_kl, _g_bad):
+        recon, target, mu, logvar = ctx.saved_tensors
+        patched, lo, hi = ctx.cfg
+        scal = torch.stack([g_l1.float().reshape(()), g_kl.float().reshape(())]).contiguous()
+        dr, dmu, dlv = ops.loss_bwd(recon.float().contiguous(), target.float().contiguous(), mu.float().contiguous(),
+                                    logvar.float().contiguous(), scal, patched, (lo, hi))
+        return dr, None, dmu, dlv, None, None, None

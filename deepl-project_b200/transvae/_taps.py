@@ -212,6 +212,13 @@ def fold_qkv(wq: Tensor, wk: Tensor, wv: Tensor, gq: Tensor, bq: Tensor, gk: Ten
     return wg * w1, wg.sum(dim=1), bias
 
 
+def fold_qkv_affine(wq: Tensor, wk: Tensor, wv: Tensor, gq: Tensor, bq: Tensor, gk: Tensor, bk: Tensor, gv: Tensor,
+                    bv: Tensor) -> Tuple[Tensor, Tensor]:
+    """Training path: only the LayerNorm affines are folded (the normalised tensor is materialised):
+    ([Wq g_q; Wk g_k; Wv g_v] [3C, C], [Wq b_q; Wk b_k; Wv b_v] [3C])."""
+    return torch.cat([wq * gq, wk * gk, wv * gv], dim=0), torch.cat([wq @ bq, wk @ bk, wv @ bv], dim=0)
+
+
 def rope_table(H: int, W: int, inv_freq: Tensor) -> Tensor:
     """[max(H, W), 16, 2] fp32 (cos, sin) of pos * inv_freq[k] -- attention.py:149-174 builds the same angles
     (positions in fp32, outer product with inv_freq, then cos / sin)."""

@@ -40,15 +40,21 @@ def nhwc_to_nchw(x: Tensor, c: Optional[int] = None) -> Tensor:
     return ops.nhwc_to_nchw(x, c)
 
 
+def needs_grad(*ts) -> bool:
+    """True when the training path (block-level autograd Functions) must be taken."""
+    return _needs_grad(*ts)
+
+
 def conv_in(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
     if _needs_grad(x, w, b):
-        return _ag().ConvIn.apply(x, w, b)
+        return _ag().ConvInFn.apply(x, w, b)
     return ops.conv_in(x, w, b)
 
 
 def mtgemm(plan, a0: Tensor, w: Tensor, **kw) -> Tensor:
     if _needs_grad(a0, w, kw.get("a1"), kw.get("bias"), kw.get("residual")):
-        return _ag().mtgemm(plan, a0, w, **kw)
+        raise RuntimeError("internal: a bare mtgemm launch was reached with autograd enabled; the training path goes "
+                           "through the block-level Functions of transvae._autograd")
     return ops.mtgemm(plan, a0, w, **kw)
 
 
@@ -73,8 +79,6 @@ def row_stats(x: Tensor, w1: Optional[Tensor] = None, mode: Optional[int] = None
 
 
 def attention(qkv: Tensor, B: int, S: int, C: int) -> Tensor:
-    if _needs_grad(qkv):
-        return _ag().Attention.apply(qkv, B, S, C)
     return ops.attn_fwd(qkv, B, S, C)[0]
 
 

@@ -58,9 +58,14 @@ class TransVAEDecoder(nn.Module):
         B, D, H, W = z.shape
         cpad = (D + 63) // 64 * 64
         C0 = self.base_dims[0]
+        train = K.needs_grad(z, *self.parameters())
         zn = K.nchw_to_nhwc(z, cpad)
-        w_in = self._packs.get("in", [self.conv_in.weight], lambda: bf16c(T.pack_conv3x3(self.conv_in.weight, cin_pad=cpad)))
-        h = K.mtgemm(T.plan_conv3x3(cpad), zn, w_in, out_shape=(B, H, W, C0), bias=f32c(self.conv_in.bias))
+        if train:
+            from .._autograd import Conv3x3Fn
+            h = Conv3x3Fn.apply(zn, T.pack_conv3x3(self.conv_in.weight, cin_pad=cpad), self.conv_in.bias)
+        else:
+            w_in = self._packs.get("in", [self.conv_in.weight], lambda: bf16c(T.pack_conv3x3(self.conv_in.weight, cin_pad=cpad)))
+            h = K.mtgemm(T.plan_conv3x3(cpad), zn, w_in, out_shape=(B, H, W, C0), bias=f32c(self.conv_in.bias))
         if trace is not None:
             trace["decoder.conv_in"] = h
         ckpt = self.gradient_checkpointing and self.training
@@ -77,6 +82,10 @@ class TransVAEDecoder(nn.Module):
         Bh, Hh, Wh, Ch = h.shape
         oc = self.output_channels
         npad = (oc + 63) // 64 * 64
+        if train:
+            from .._autograd import HeadFn
+            return HeadFn.apply(h, T.pack_conv3x3(self.conv_out.weight, cout_pad=npad),
+                                torch.nn.functional.pad(self.conv_out.bias, (0, npad - oc)), oc)
         w_out = self._packs.get("out", [self.conv_out.weight], lambda: bf16c(T.pack_conv3x3(self.conv_out.weight, cout_pad=npad)))
         b_out = self._packs.get("bout", [self.conv_out.bias],
                                 lambda: f32c(torch.nn.functional.pad(self.conv_out.bias, (0, npad - oc))))

@@ -90,6 +90,12 @@ class TransVAE(nn.Module):
         B, H, W, C = h.shape
         d = self.latent_dim
         npad = (2 * d + 63) // 64 * 64
+        if K.needs_grad(h, self.conv_mu.weight, self.conv_logvar.weight):
+            from .._autograd import HeadFn
+            both = HeadFn.apply(h, T.pack_conv3x3(torch.cat([self.conv_mu.weight, self.conv_logvar.weight], 0), cout_pad=npad),
+                                torch.nn.functional.pad(torch.cat([self.conv_mu.bias, self.conv_logvar.bias]), (0, npad - 2 * d)),
+                                2 * d)
+            return both[:, :d], both[:, d:]
         w = self._packs.get("heads", [self.conv_mu.weight, self.conv_logvar.weight], lambda: bf16c(
             T.pack_conv3x3(torch.cat([self.conv_mu.weight, self.conv_logvar.weight], 0), cout_pad=npad)))
         b = self._packs.get("heads_b", [self.conv_mu.bias, self.conv_logvar.bias], lambda: f32c(

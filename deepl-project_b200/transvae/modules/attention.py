@@ -76,6 +76,14 @@ class FlashAttentionWithRoPE(HotModule):
         ``rms=False``: no RMSNorm in front (bare module); ``add_residual=False``: return the branch only."""
         B, H, W, C = x.shape
         S = H * W
+        if K.needs_grad(x, w1, *self.parameters()):
+            if not (add_residual and rms):
+                raise NotImplementedError("bare attention (no RMSNorm / no residual) is an inference-only hook")
+            from .._autograd import AttnFn
+            wg, bg = T.fold_qkv_affine(self.to_q.weight, self.to_k.weight, self.to_v.weight, self.norm_q.weight,
+                                       self.norm_q.bias, self.norm_k.weight, self.norm_k.bias, self.norm_v.weight,
+                                       self.norm_v.bias)
+            return AttnFn.apply(x, w1, wg, bg, self.proj.weight, self.proj.bias, self._rope_tab(H, W), self.scale)
         wqkv, colsum, bias = self._folded(w1)
         a, b = K.row_stats(x, w1.detach(), 1 if rms else 2)
         rope = (self._rope_tab(H, W), C, H, W, self.scale * math.log2(math.e))

@@ -37,6 +37,14 @@ class ConvFFN(HotModule):
         B, H, W, C = x.shape
         M = B * H * W
         hid, mid = self.hidden_dim, self.conv_hidden
+        if K.needs_grad(x, w2, *self.parameters()):
+            if w2 is None or not add_residual:
+                raise NotImplementedError("bare ConvFFN (no RMSNorm / no residual) is an inference-only hook")
+            from .._autograd import FfnFn
+            c0, c2, c4 = self.conv[0], self.conv[2], self.conv[4]
+            return FfnFn.apply(x, w2, self.proj_in.weight, self.proj_in.bias, T.pack_conv1x1(c0.weight), c0.bias,
+                               T.pack_conv3x3(c2.weight), c2.bias, T.pack_conv1x1(c4.weight), c4.bias,
+                               self.proj_out.weight, self.proj_out.bias)
         xf = x.reshape(M, C)
         if w2 is not None:
             w_in = self._packs.get("in", [self.proj_in.weight, w2], lambda: bf16c(self.proj_in.weight * w2))

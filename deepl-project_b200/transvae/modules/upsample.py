@@ -30,6 +30,10 @@ class Downsample(HotModule):
     def forward_nhwc(self, x: torch.Tensor) -> torch.Tensor:
         B, H, W, C = x.shape
         m0, m2 = self.main_path[0], self.main_path[2]
+        if K.needs_grad(x, *self.parameters()):
+            from .._autograd import DownsampleFn
+            return DownsampleFn.apply(x, T.pack_conv3x3(m0.weight), m0.bias,
+                                      T.pack_downsample(m2.weight, self.dc_conv.weight), m2.bias + self.dc_conv.bias)
         w0 = self._packs.get("m0", [m0.weight], lambda: bf16c(T.pack_conv3x3(m0.weight)))
         wd = self._packs.get("down", [m2.weight, self.dc_conv.weight],
                              lambda: bf16c(T.pack_downsample(m2.weight, self.dc_conv.weight)))
@@ -55,6 +59,11 @@ class Upsample(HotModule):
         B, H, W, Ci = x.shape
         Co = self.out_channels
         m1, m3 = self.main_path[1], self.main_path[3]
+        if K.needs_grad(x, *self.parameters()):
+            from .._autograd import UpsampleFn
+            return UpsampleFn.apply(x, T.pack_upsample_conv1(m1.weight), m1.bias,
+                                    T.pack_upsample_conv2(m3.weight, self.dc_conv.weight),
+                                    T.bias_upsample_conv2(m3.bias, self.dc_conv.bias))
         w1 = self._packs.get("m1", [m1.weight], lambda: bf16c(T.pack_upsample_conv1(m1.weight)))
         b1 = self._packs.get("b1", [m1.bias], lambda: f32c(m1.bias.unsqueeze(0).expand(4, -1)))
         w2 = self._packs.get("m3", [m3.weight, self.dc_conv.weight],

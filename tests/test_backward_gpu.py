@@ -1,0 +1,232 @@
+"""Per-kernel parity of the backward pass on a real B200: every backward C-ABI entry point against torch.autograd
+through the plain fp32 torch op it differentiates (inputs rounded to bf16 once; fp32 accumulation on both sides).
+Tolerance: max|ours-ref|/max|ref| <= 1e-2 for bf16 outputs, 2e-3 for fp32 outputs (weight gradients)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from transvae import _taps as T  # noqa: E402
+from transvae import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def grads(fn, inputs, dout):
+    inputs = [t.float().clone().requires_grad_(True) for t in inputs]
+    fn(*inputs).backward(dout.float())
+    return [t.grad for t in inputs]
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 128, 192), (4096, 384, 1536), (300, 1536, 256), (8192, 64, 64), (77, 256, 320)])
+def test_linear_backward(M, K, N):
+    x, w, dz = bf(rnd(M, K)), bf(rnd(N, K, seed=1, scale=0.05)), bf(rnd(M, N, seed=2))
+    gx, gw = grads(lambda x, w: x @ w.t(), [x, w], dz)
+    dx = ops.linear(dz, w.t().contiguous(), T.plan_linear(N))
+    assert rel(dx, gx) < 1e-2
+    dw = ops.mtgemm_wgrad(T.plan_linear(K), x.reshape(1, 1, M, K), dz.reshape(1, 1, M, N), N)
+    assert rel(dw, gw) < 2e-3, rel(dw, gw)
+
+
+@pytest.mark.parametrize("B,C,H,W,N", [(2, 64, 16, 16, 64), (1, 192, 128, 128, 192), (3, 128, 32, 32, 256), (2, 64, 8, 8, 128)])
+def test_conv3x3_backward(B, C, H, W, N):
+    x, w, dz = bf(rnd(B, C, H, W)), bf(rnd(N, C, 3, 3, seed=1, scale=0.05)), bf(rnd(B, N, H, W, seed=2))
+    gx, gw = grads(lambda x, w: F.conv2d(x, w, padding=1), [x, w], dz)
+    dx = ops.mtgemm(T.plan_conv3x3_dgrad(N), nhwc(dz), bf(T.pack_conv3x3_dgrad(w.float())).contiguous(), out_shape=(B, H, W, C))
+    assert rel(nchw(dx), gx) < 1e-2
+    dw = ops.mtgemm_wgrad(T.plan_conv3x3(C), nhwc(x), nhwc(dz), N)
+    assert rel(dw, T.pack_conv3x3(gw)) < 2e-3, rel(dw, T.pack_conv3x3(gw))
+
+
+@pytest.mark.parametrize("B,C,N,H", [(2, 64, 128, 16), (1, 192, 192, 64)])
+def test_downsample_backward(B, C, N, H):
+    x, y = bf(rnd(B, C, H, H)), bf(rnd(B, C, H, H, seed=5))
+    w2, wdc = bf(rnd(N, C, 3, 3, seed=1, scale=0.05)), bf(rnd(N, 4 * C, 1, 1, seed=3, scale=0.05))
+    dz = bf(rnd(B, N, H // 2, H // 2, seed=7))
+    gy, gx, gw2, gwdc = grads(lambda y, x, w2, wdc: F.conv2d(y, w2, stride=2, padding=1) +
+                              F.conv2d(F.pixel_unshuffle(x, 2), wdc), [y, x, w2, wdc], dz)
+    dzn = nhwc(dz)
+    dy = ops.mtgemm(T.plan_downsample_dgrad_main(C, N), dzn, bf(T.pack_conv3x3_dgrad(w2.float())).contiguous(), out_shape=(B, H, H, C))
+    assert rel(nchw(dy), gy) < 1e-2
+    dx = ops.mtgemm(T.plan_downsample_dgrad_dc(C, N), dzn, bf(T.pack_downsample_dgrad_dc(wdc.float())).contiguous(), out_shape=(B, H, H, C))
+    assert rel(nchw(dx), gx) < 1e-2
+    dw = ops.mtgemm_wgrad(T.plan_downsample(C), nhwc(y), dzn, N, a1=nhwc(x))
+    assert rel(dw, T.pack_downsample(gw2, gwdc)) < 2e-3
+
+
+@pytest.mark.parametrize("B,Ci,Co,H", [(2, 128, 64, 8), (1, 192, 192, 32)])
+def test_upsample_backward(B, Ci, Co, H):
+    x = bf(rnd(B, Ci, H, H))
+    w1, w2 = bf(rnd(Co, Ci, 3, 3, seed=1, scale=0.05)), bf(rnd(Co, Co, 3, 3, seed=2, scale=0.05))
+    wdc = bf(rnd(4 * Co, Ci, 1, 1, seed=3, scale=0.05))
+    dz1 = bf(rnd(B, Co, 2 * H, 2 * H, seed=4))
+    gx, gw1 = grads(lambda x, w: F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, padding=1), [x, w1], dz1)
+    dx = ops.mtgemm(T.plan_upsample_conv1_dgrad(Ci, Co), nhwc(dz1), bf(T.pack_upsample_conv1_dgrad(w1.float())).contiguous(),
+                    out_shape=(B, H, H, Ci))
+    assert rel(nchw(dx), gx) < 2e-2     # summed taps are re-rounded to bf16
+    dwp = ops.mtgemm_wgrad(T.plan_upsample_conv1(Ci, Co), nhwc(x), nhwc(dz1), Co)
+    w1r = w1.float().clone().requires_grad_(True)
+    (T.pack_upsample_conv1(w1r) * dwp).sum().backward()
+    assert rel(w1r.grad, gw1) < 2e-3
+    y, dz2 = bf(rnd(B, Co, 2 * H, 2 * H, seed=6)), bf(rnd(B, Co, 2 * H, 2 * H, seed=8))
+    gy, gx2, gw2, gwdc = grads(lambda y, x, w, wdc: F.conv2d(y, w, padding=1) + F.pixel_shuffle(F.conv2d(x, wdc), 2),
+                               [y, x, w2, wdc], dz2)
+    dx2 = ops.mtgemm(T.plan_upsample_dc_dgrad(Co), nhwc(dz2), bf(T.pack_upsample_dc_dgrad(wdc.float())).contiguous(),
+                     out_shape=(B, H, H, Ci))
+    assert rel(nchw(dx2), gx2) < 1e-2
+    dw2 = ops.mtgemm_wgrad(T.plan_upsample_conv2(Co, Ci), nhwc(y), nhwc(dz2), Co, a1=nhwc(x))
+    assert rel(dw2, T.pack_upsample_conv2(gw2, gwdc)) < 2e-3
+
+
+def test_bias_act_bwd_and_act_fwd():
+    for (M, N) in [(777, 192), (300, 6144), (512, 64)]:
+        z, dy = bf(rnd(M, N, scale=2.0)), bf(rnd(M, N, seed=1))
+        for act, f in ((ops.ACT_GELU, F.gelu), (ops.ACT_SILU, F.silu)):
+            zf = z.float().clone().requires_grad_(True)
+            f(zf).backward(dy.float())
+            dz, cs = ops.bias_act_bwd(dy, z, act)
+            assert rel(dz, zf.grad) < 1e-2
+            assert rel(cs, dz.float().sum(0)) < 1e-4
+            assert rel(ops.act_fwd(z, act), f(z.float())) < 1e-2
+        dz, cs = ops.bias_act_bwd(dy, None, ops.ACT_NONE)
+        assert dz is dy and rel(cs, dy.float().sum(0)) < 1e-4
+    dy = bf(rnd(2, 8, 12, 64))                       # phase view sums: [p, q, c]
+    _, cs = ops.bias_act_bwd(dy, None, ops.ACT_NONE, phase_view=True)
+    ref = dy.float().view(2, 4, 2, 6, 2, 64).sum(dim=(0, 1, 3))
+    assert rel(cs, ref) < 1e-4
+
+
+@pytest.mark.parametrize("B,C,H", [(2, 192, 32), (3, 64, 16)])
+def test_groupnorm_backward(B, C, H):
+    x, dh = bf(rnd(B, C, H, H, scale=3.0) + 0.7), bf(rnd(B, C, H, H, seed=3))
+    g, b = rnd(C, seed=1) * 0.2 + 1, rnd(C, seed=2) * 0.1
+    add = bf(rnd(B, C, H, H, seed=4))
+    gx, gg, gb = grads(lambda x, g, b: F.silu(F.group_norm(x, 32, g, b, 1e-5)), [x, g, b], dh)
+    xn = nhwc(x)
+    sums = ops.groupnorm_stats(xn)
+    dx, dg, db = ops.groupnorm_bwd(xn, nhwc(dh), sums, g, b, add=nhwc(add))
+    assert rel(nchw(dx), gx + add.float()) < 1e-2
+    assert rel(dg, gg) < 5e-3 and rel(db, gb) < 5e-3
+
+
+@pytest.mark.parametrize("M,C", [(500, 384), (64, 1536), (1000, 64)])
+def test_token_norms(M, C):
+    x, dy = bf(rnd(M, C, scale=4.0) + 0.3), bf(rnd(M, C, seed=2))
+    w = rnd(C, seed=1) * 0.2 + 1
+    add = bf(rnd(M, C, seed=3))
+
+    def rms(x, w):
+        return x / torch.sqrt((x ** 2).mean(-1, keepdim=True) + 1e-6) * w
+
+    def rmsln(x, w):
+        return F.layer_norm(rms(x, w), (C,), None, None, 1e-5)
+
+    for mode, f in ((0, rms), (1, rmsln)):
+        y = ops.token_norm_fwd(x, w, mode)
+        assert rel(y, f(x.float(), w)) < 1e-2
+        gx, gw = grads(f, [x, w], dy)
+        dx, dw = ops.token_norm_bwd(x, w, dy, add, mode)
+        assert rel(dx, gx + add.float()) < 1e-2, (mode, rel(dx, gx + add.float()))
+        assert rel(dw, gw) < 5e-3, (mode, rel(dw, gw))
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 128), (1, 32, 32, 64), (2, 4, 4, 128), (1, 10, 20, 64)])
+def test_attention_backward(B, H, W, C):
+    """d(pre-RoPE q|k|v) of softmax(rope(q) rope(k)^T / 8) v against autograd through the oracle's RoPE + SDPA."""
+    import transvae_oracle as O
+    S, nh = H * W, C // 64
+    inv = (1.0 / (10000 ** (torch.arange(0, 32, 2).float() / 32))).to(DEV)
+    tab = T.rope_table(H, W, inv)
+    qs = 0.125 * math.log2(math.e)
+    raw = bf(rnd(B, S, 3 * C, scale=1.0))            # pre-RoPE projection output
+    dout = bf(rnd(B, S, C, seed=1))
+    # forward through our kernels: identity "projection" with the rope epilogue, then attention
+    eye = bf(torch.eye(3 * C, device=DEV))
+    qkv = ops.linear(raw.reshape(B * S, 3 * C), eye, T.plan_linear(3 * C), rope=(tab, C, H, W, qs)).reshape(B, S, 3 * C)
+    out, lse = ops.attn_fwd(qkv, B, S, C, need_lse=True)
+    dqkv = ops.attn_bwd(qkv, out, dout, lse, tab, B, S, C, H, W, 0.125)
+
+    def ref_fn(r):
+        t = r.view(B, S, 3, nh, 64).permute(2, 0, 3, 1, 4)
+        q = O.rope2d(t[0], H, W, inv)
+        k = O.rope2d(t[1], H, W, inv)
+        o = F.scaled_dot_product_attention(q, k, t[2], scale=0.125)
+        return o.permute(0, 2, 1, 3).reshape(B, S, C)
+
+    r = raw.float().clone().requires_grad_(True)
+    o_ref = ref_fn(r)
+    o_ref.backward(dout.float())
+    assert rel(out, o_ref) < 2e-2
+    g = r.grad.view(B, S, 3, C)
+    ours = dqkv.float().view(B, S, 3, C)
+    errs = [rel(ours[:, :, i], g[:, :, i]) for i in range(3)]
+    assert max(errs) < 3e-2, errs
+
+
+def test_conv_in_wgrad():
+    x, dy = rnd(2, 3, 32, 48), bf(rnd(2, 64, 32, 48, seed=1))
+    w = rnd(64, 3, 3, 3, seed=2)
+    b = rnd(64, seed=3)
+    _, gw, gb = grads(lambda x, w, b: F.conv2d(x, w, b, padding=1), [x, w, b], dy)
+    dw, db = ops.conv_in_wgrad(x, nhwc(dy))
+    assert rel(dw, gw) < 2e-3 and rel(db, gb) < 2e-3
+
+
+def test_loss_and_latent_backward():
+    recon, tgt = rnd(2, 3, 16, 16, scale=3), torch.rand(2, 3, 16, 16, device=DEV)
+    mu, lv, eps = rnd(2, 32, 4, 4, scale=30), rnd(2, 32, 4, 4, seed=1, scale=15), rnd(2, 32, 4, 4, seed=2)
+    dz = rnd(2, 32, 4, 4, seed=3)
+    r, m, l = [t.clone().requires_grad_(True) for t in (recon, mu, lv)]
+    mc, lc = m.clamp(-50, 50), l.clamp(-30, 20)
+    z = mc + eps * torch.exp(0.5 * lc.clamp(-30, 20))
+    loss = (r.sigmoid() - tgt).abs().mean() + 1e-3 * (-0.5 * (1 + lc.clamp(-30, 20) - mc.pow(2) - lc.clamp(-30, 20).exp())).mean()
+    (loss * 2.0 + (z * dz).sum()).backward()
+    scal = torch.tensor([2.0 / recon.numel(), 2.0 * 1e-3 / mu.numel()], device=DEV)
+    dr, dmu_c, dlv_c = ops.loss_bwd(recon, tgt, mu.clamp(-50, 50), lv.clamp(-30, 20), scal, True, (-30.0, 20.0))
+    assert rel(dr, r.grad) < 1e-4
+    dmu, dlv = ops.latent_bwd(mu, lv, eps, dz, dmu_c, dlv_c, True)
+    assert rel(dmu, m.grad) < 1e-4 and rel(dlv, l.grad) < 1e-4
+
+
+def test_adamw_and_sumsq():
+    n = 4096 * 3
+    p, g = rnd(n), rnd(n, seed=1)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-2, betas=(0.9, 0.95), weight_decay=0.01)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    ours = p.clone()
+    for step in range(1, 4):
+        ref.grad = g.clone() * step
+        torch.nn.utils.clip_grad_norm_([ref], 1.0)
+        opt.step()
+        ctrl = torch.zeros(4, device=DEV)
+        gg = g * step
+        ops.sumsq(gg, ctrl)
+        ctrl[1], ctrl[2] = 1.0, 1.0
+        ops.adamw(ours, gg, m, v, ctrl, 1e-2, (0.9, 0.95), 1e-8, 0.01, step)
+    assert rel(ours, ref.data) < 1e-4
