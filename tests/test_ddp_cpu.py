@@ -1,0 +1,81 @@
+"""Host logic of the data-parallel step, world_size 2 over gloo on CPU: GradBuckets' bucketing, hook-driven all-reduce,
+gradient-accumulation gating and flat views (no kernels involved; the AdamW kernel has its own GPU test)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from transvae.trainer import GradBuckets
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _mlp():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(8, 32), torch.nn.Tanh(), torch.nn.Linear(32, 16), torch.nn.Tanh(),
+                               torch.nn.Linear(16, 4))
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m = _mlp()
+        gb = GradBuckets(m.parameters(), bucket_bytes=1024)       # tiny buckets -> several all-reduces
+        assert len(gb.buckets) > 1
+        x = torch.randn(6, 8, generator=torch.Generator().manual_seed(1))
+        xs = x[rank * 3:(rank + 1) * 3]
+        # two micro-steps with accumulation: only the second one may communicate
+        gb.sync_grads = False
+        (m(xs[:1]).pow(2).sum()).backward()
+        assert not gb._handles
+        gb.sync_grads = True
+        (m(xs[1:]).pow(2).sum()).backward()
+        assert len(gb._handles) == len(gb.buckets)
+        gb.wait()
+        if rank == 0:
+            out.put({k: p.grad.clone() for k, p in m.named_parameters()})
+        # parameters are views of the flat buffer; an in-place flat update moves them
+        w_before = m[0].weight.clone()
+        gb.flat_p.add_(1.0)
+        assert torch.allclose(m[0].weight, w_before + 1.0)
+        gb.zero_grad()
+        assert float(m[0].weight.grad.abs().sum()) == 0.0
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_matches_single_process():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    m = _mlp()
+    x = torch.randn(6, 8, generator=torch.Generator().manual_seed(1))
+    m(x).pow(2).sum().backward()            # sum over all samples == sum of the per-rank sums
+    for k, p in m.named_parameters():
+        assert torch.allclose(got[k], p.grad, atol=1e-5), k
+
+
+def test_buckets_are_contiguous_and_reverse_ordered():
+    m = _mlp()
+    gb = GradBuckets(m.parameters(), bucket_bytes=512)
+    assert gb.buckets[0][0] == 0 and gb.buckets[-1][1] == gb.numel
+    for (s0, e0), (s1, e1) in zip(gb.buckets, gb.buckets[1:]):
+        assert e0 == s1
+    # last registered parameter (whose gradient is produced first) sits at the front of the flat buffer
+    last = list(m.parameters())[-1]
+    assert last.data_ptr() == gb.flat_p.data_ptr()
