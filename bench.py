@@ -48,6 +48,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="per-shape kernel table on stderr")
+    ap.add_argument("--no-train", action="store_true", help="skip the fwd+bwd (BASELINE configs[2]) measurement")
+    ap.add_argument("--train-global-batch", type=int, default=256)
+    ap.add_argument("--train-micro-batch", type=int, default=32)
+    ap.add_argument("--train-steps", type=int, default=2)
     return ap.parse_args()
 
 
@@ -263,6 +267,10 @@ def run_ours(args, rank, world, local):
         e2e = {"value": B * world * args.steps / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e / args.steps}
 
+    train = None
+    if not args.no_train:
+        train = run_train(args, model, rank, world, dev, dist, pk)
+
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -282,9 +290,62 @@ def run_ours(args, rank, world, local):
                    "l2_policy": "activations per step (>2 GB) exceed the 126 MB L2; no flush needed",
                    "gflop_per_image": gflop},
         "model_tflops": value * gflop / 1e3, "model_frac_of_peak": value * gflop / 1e3 / (pk["tflops"] * world),
-        "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "train": train,
     }
     print(json.dumps(line), flush=True)
+
+
+def run_train(args, model, rank, world, dev, dist, pk):
+    """BASELINE configs[2]: stage-1 training step (fwd + L1/KL loss + bwd + gradient all-reduce + clip + AdamW) on a fixed
+    global batch (strong scaling: per-GPU batch = global / N, processed in micro-batches).  One step = one optimiser
+    step over the whole global batch; timed on the device, MAX over ranks."""
+    import transvae
+    from transvae import ops
+    from transvae.trainer import Trainer
+    per_gpu = max(1, args.train_global_batch // world)
+    mb = min(args.train_micro_batch, per_gpu)
+    accum = max(1, per_gpu // mb)
+    loss_fn = transvae.TransVAELoss(l1_weight=1.0, lpips_weight=0.0, kl_weight=1e-8, vf_weight=0.0, gan_weight=0.0)
+    tr = Trainer(model, loss_fn, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0, grad_clip=1.0, accumulation_steps=accum)
+    g = torch.Generator(device="cpu").manual_seed(4321 + rank)
+    xs = [torch.rand(mb, 3, args.res, args.res, generator=g).to(dev) for _ in range(min(accum, 2))]
+
+    def step():
+        for i in range(accum):
+            out = tr.train_step(xs[i % len(xs)])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    torch.cuda.reset_peak_memory_stats()
+    step()                                  # warm-up (allocator, NCCL channels)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = ops.LAUNCHES
+    e0.record()
+    for _ in range(args.train_steps):
+        out = step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / args.train_steps
+    imgs = mb * accum * world
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import transvae_oracle as O
+    gflop = 3.0 * O.forward_flops_per_image(O.variant_config(args.variant), args.res) / 1e9
+    rate = imgs / ms * 1e3
+    return {"metric": "images_per_sec_fwd_bwd_256", "value": rate, "unit": UNIT, "ms_per_step": ms, "scaling": "strong",
+            "global_batch": imgs, "per_gpu_micro_batch": mb, "accumulation": accum, "steps": args.train_steps,
+            "loss": float(out["total"]), "gflop_per_image_fwd_bwd": gflop, "model_tflops": rate * gflop / 1e3,
+            "model_frac_of_peak": rate * gflop / 1e3 / (pk["tflops"] * world),
+            "gpu_launches_per_step": (ops.LAUNCHES - n0) // args.train_steps,
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+            "includes": "fwd, L1+KL loss, bwd, bucketed NCCL all-reduce overlapped with bwd, clip, fused AdamW"}
 
 
 def main():

