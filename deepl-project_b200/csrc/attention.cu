@@ -5,14 +5,16 @@
 // [0, C), k in [C, 2C), v in [2C, 3C), head h at columns h*64..h*64+63.  The QKV GEMM epilogue has already
 // applied the reference's RoPE to q and k and multiplied q by scale*log2(e), so scores are in log2 units.
 //
-// One CTA per (128-query tile, head, image):
-//   warp 0   TMA producer : Q once, then K/V tiles through a 3-stage ring
-//   warp 1   MMA issuer   : S_j = Q K_j^T  (tcgen05, M=128 N=128 K=64, fp32 in TMEM, double buffered)
-//                           O_j = P_j V_j  (M=128 N=64 K=128; P from smem, V as an MN-major operand)
-//   warps 4-7 softmax     : one query row per thread: tcgen05.ld S, online max/sum with exp2, P -> bf16 ->
-//                           swizzled smem, O accumulated in registers (rescaled by exp2(m_old-m_new)),
-//                           final O/l -> bf16 -> TMA store; log-sum-exp kept for the backward pass.
-// S_{j+1} and P_{j-1}V_{j-1} run on the tensor pipe while the softmax warps work on block j.
+// One CTA per (256-query tile = two 128-row Q tiles, head, image), 12 warps:
+//   warp 0     TMA producer : both Q tiles once, then K/V tiles through a 3-stage ring
+//   warp 1     MMA issuer   : per K/V block and Q tile t:  S_t = Q_t K^T (tcgen05, M=128 N=128 K=64 -> TMEM) and
+//                             O_t = P_t V (M=128 N=64 K=128; P from smem, V as an MN-major operand)
+//   warps 4-7  softmax for Q tile 0, warps 8-11 for Q tile 1 : one query row per thread: tcgen05.ld S, online
+//              max / sum with exp2, P -> bf16 -> swizzled smem, O accumulated in registers (rescaled by
+//              exp2(m_old - m_new)), final O / l -> bf16 -> TMA store; log-sum-exp kept for the backward pass.
+// The two softmax warpgroups ping-pong: while one exponentiates, the tensor pipe runs the other tile's S / PV
+// and the TMEM-load latency of one warp hides behind the other warp on the same scheduler.  (The first version -- one
+// Q tile, one softmax warpgroup -- reached 310-340 TFLOP/s at S=4096; profiles/r1_breakdown_*.txt.)
 #include "../../include/transvae_sm100.h"
 #include "common.cuh"
 #include "tmap.cuh"
@@ -21,30 +23,40 @@ namespace tvae {
 
 constexpr int kAttStages = 3;
 constexpr int kTileBytes = 128 * 64 * 2;  // 16 KiB: 128 rows x 64 bf16
-constexpr int kAttSmem = kTileBytes /*Q*/ + kAttStages * 2 * kTileBytes /*K,V*/ + 2 * kTileBytes /*P*/ + 1024 + 256;
+constexpr int kAttThreads = 384;
+constexpr int kAttSmem = 2 * kTileBytes /*Q0,Q1*/ + kAttStages * 2 * kTileBytes /*K,V*/ + 2 * 2 * kTileBytes /*P0,P1*/ +
+                         1024 + 256;
 
-__global__ void __launch_bounds__(256, 1)
+__device__ __forceinline__ void att_tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kAttThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                 float* __restrict__ lse, int S, int C, int nh) {
 #ifdef TVAE_DEVICE_OK
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kTileBytes;                     // [stages]
+  uint8_t* sQ = smem;                                // [2 tiles]
+  uint8_t* sK = sQ + 2 * kTileBytes;                 // [stages]
   uint8_t* sV = sK + kAttStages * kTileBytes;        // [stages]
-  uint8_t* sP = sV + kAttStages * kTileBytes;        // 2 x 16 KiB (keys 0-63, 64-127)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTileBytes);
+  uint8_t* sP = sV + kAttStages * kTileBytes;        // [2 tiles] x 2 chunks (keys 0-63, 64-127)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kTileBytes);
   uint64_t* q_full = bars;                           // 1
   uint64_t* kv_full = bars + 1;                      // [stages]
   uint64_t* kv_empty = kv_full + kAttStages;         // [stages]
-  uint64_t* s_full = kv_empty + kAttStages;          // [2]
-  uint64_t* s_empty = s_full + 2;                    // [2]
-  uint64_t* p_full = s_empty + 2;                    // 1
-  uint64_t* o_full = p_full + 1;                     // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* s_full = kv_empty + kAttStages;          // [2 tiles]
+  uint64_t* s_empty = s_full + 2;                    // [2 tiles]
+  uint64_t* p_full = s_empty + 2;                    // [2 tiles]
+  uint64_t* o_full = p_full + 2;                     // [2 tiles]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128;
+  const int q0 = blockIdx.x * 256;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int nblk = (S + 127) / 128;
@@ -57,12 +69,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&s_full[a], 1);
-      mbar_init(&s_empty[a], 4);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_empty[t], 4);
+      mbar_init(&p_full[t], 4);
+      mbar_init(&o_full[t], 1);
     }
-    mbar_init(p_full, 4);
-    mbar_init(o_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -73,32 +85,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // 2 x 128 columns
-  const uint32_t tmem_O = tmem_base + 256;  // 64 columns
+  // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kTileBytes);
-      asm volatile(
-          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
-              "r"(smem_u32(sQ)), "l"(reinterpret_cast<uint64_t>(&tmQKV)), "r"(smem_u32(q_full)), "r"(h * 64), "r"(q0),
-          "r"(b)
-          : "memory");
+      mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+      att_tma_load_3d(sQ, &tmQKV, q_full, h * 64, q0, b);
+      att_tma_load_3d(sQ + kTileBytes, &tmQKV, q_full, h * 64, q0 + 128, b);
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < nblk; ++j) {
         mbar_wait(&kv_empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&kv_full[stage], 2 * kTileBytes);
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
-                "r"(smem_u32(sK + stage * kTileBytes)), "l"(reinterpret_cast<uint64_t>(&tmQKV)),
-            "r"(smem_u32(&kv_full[stage])), "r"(C + h * 64), "r"(j * 128), "r"(b)
-            : "memory");
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
-                "r"(smem_u32(sV + stage * kTileBytes)), "l"(reinterpret_cast<uint64_t>(&tmQKV)),
-            "r"(smem_u32(&kv_full[stage])), "r"(2 * C + h * 64), "r"(j * 128), "r"(b)
-            : "memory");
+        att_tma_load_3d(sK + stage * kTileBytes, &tmQKV, &kv_full[stage], C + h * 64, j * 128, b);
+        att_tma_load_3d(sV + stage * kTileBytes, &tmQKV, &kv_full[stage], 2 * C + h * 64, j * 128, b);
         if (++stage == kAttStages) {
           stage = 0;
           phase ^= 1;
@@ -109,51 +109,58 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
-      const uint32_t q_base = smem_u32(sQ);
-      const uint32_t p_base = smem_u32(sP);
-      auto issue_qk = [&](int j) {
+      auto issue_qk = [&](int j, int t) {
         const int stage = j % kAttStages;
-        const uint32_t ph = (j / kAttStages) & 1;
-        mbar_wait(&kv_full[stage], ph);
-        mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+        if (t == 0) mbar_wait(&kv_full[stage], (j / kAttStages) & 1);
+        mbar_wait(&s_empty[t], (j & 1) ^ 1);
         tc_fence_after();
+        const uint32_t q_base = smem_u32(sQ + t * kTileBytes);
         const uint32_t k_base = smem_u32(sK + stage * kTileBytes);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_S + (j & 1) * 128, umma_desc_kmajor_sw128(q_base + k * 32),
-                   umma_desc_kmajor_sw128(k_base + k * 32), idesc_qk, k != 0);
-        umma_commit(&s_full[j & 1]);
+          umma_f16(tmem_base + t * 128, umma_desc_kmajor_sw128(q_base + k * 32), umma_desc_kmajor_sw128(k_base + k * 32),
+                   idesc_qk, k != 0);
+        umma_commit(&s_full[t]);
       };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      if (nblk > 1) issue_qk(1);
-      for (int j = 0; j < nblk; ++j) {
+      auto issue_pv = [&](int j, int t) {
         const int stage = j % kAttStages;
-        mbar_wait(p_full, j & 1);
+        mbar_wait(&p_full[t], j & 1);
         tc_fence_after();
+        const uint32_t p_base = smem_u32(sP + t * 2 * kTileBytes);
         const uint32_t v_base = smem_u32(sV + stage * kTileBytes);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_f16(tmem_O, umma_desc_kmajor_sw128(p_base + (k >> 2) * kTileBytes + (k & 3) * 32),
+          umma_f16(tmem_base + 256 + t * 64, umma_desc_kmajor_sw128(p_base + (k >> 2) * kTileBytes + (k & 3) * 32),
                    umma_desc_mnmajor_sw128(v_base + k * 2048, 1024, 1024), idesc_pv, k != 0);
-        umma_commit(&kv_empty[stage]);
-        umma_commit(o_full);
-        if (j + 2 < nblk) issue_qk(j + 2);
+        umma_commit(&o_full[t]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0, 0);
+      issue_qk(0, 1);
+      for (int j = 0; j < nblk; ++j) {
+        issue_pv(j, 0);
+        if (j + 1 < nblk) issue_qk(j + 1, 0);
+        issue_pv(j, 1);
+        umma_commit(&kv_empty[j % kAttStages]);
+        if (j + 1 < nblk) issue_qk(j + 1, 1);
       }
     }
   } else if (warp >= 4) {
+    const int t = (warp - 4) >> 2;       // Q tile of this warpgroup
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_off + t * 128;
+    const uint32_t t_o = tmem_base + lane_off + 256 + t * 64;
+    uint8_t* sPt = sP + t * 2 * kTileBytes;
     float o_acc[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) o_acc[i] = 0.0f;
     float m_run = -INFINITY, l_run = 0.0f, alpha_prev = 1.0f;
 
     for (int j = 0; j < nblk; ++j) {
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      const uint32_t t_s = tmem_S + lane_off + (j & 1) * 128;
       const int key0 = j * 128;
       // pass 1: row max
       float m_blk = -INFINITY;
@@ -172,12 +179,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const float alpha = exp2f(m_run - m_new);   // m_run = -inf on the first block -> 0
       // the previous block's P V must be complete before sP is overwritten; fold it into the accumulator now
       if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
+        mbar_wait(&o_full[t], (j - 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t v[32];
-          tmem_ld32(tmem_O + lane_off + c * 32, v);
+          tmem_ld32(t_o + c * 32, v);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
@@ -197,7 +204,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           p[i] = exp2f(s - m_new);
           l_blk += p[i];
         }
-        uint8_t* row = sP + (c >> 1) * kTileBytes + r * 128;
+        uint8_t* row = sPt + (c >> 1) * kTileBytes + r * 128;
         const int cbase = (c & 1) * 4;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -217,24 +224,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&s_empty[j & 1]);
-        mbar_arrive(p_full);
+        mbar_arrive(&s_empty[t]);
+        mbar_arrive(&p_full[t]);
       }
     }
     // last block's P V
-    mbar_wait(o_full, (nblk - 1) & 1);
+    mbar_wait(&o_full[t], (nblk - 1) & 1);
     tc_fence_after();
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
-      tmem_ld32(tmem_O + lane_off + c * 32, v);
+      tmem_ld32(t_o + c * 32, v);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
     }
     const float inv_l = 1.0f / l_run;
-    // stage O (bf16) in sP[0] and store with TMA (rows beyond S are clipped by the tensor map)
-    uint8_t* row = sP + r * 128;
+    // stage O (bf16) in this tile's P buffer and store with TMA (rows beyond S are clipped by the tensor map)
+    uint8_t* row = sPt + r * 128;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       uint4 o;
@@ -244,13 +251,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       o.w = pack_bf16(o_acc[g * 8 + 6] * inv_l, o_acc[g * 8 + 7] * inv_l);
       *reinterpret_cast<uint4*>(row + ((g ^ (r & 7)) << 4)) = o;
     }
-    if (lse != nullptr && q0 + r < S) lse[((size_t)b * nh + h) * S + q0 + r] = m_run + log2f(l_run);
+    const int qrow = q0 + t * 128 + r;
+    if (lse != nullptr && qrow < S) lse[((size_t)b * nh + h) * S + qrow] = m_run + log2f(l_run);
     fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (threadIdx.x == 128) {
+    if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (qd == 0 && lane == 0 && q0 + t * 128 < S) {
       asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                        reinterpret_cast<uint64_t>(&tmO)),
-                   "r"(smem_u32(sP)), "r"(h * 64), "r"(q0), "r"(b)
+                   "r"(smem_u32(sPt)), "r"(h * 64), "r"(q0 + t * 128), "r"(b)
                    : "memory");
       tma_store_commit();
       tma_store_wait<0>();
@@ -277,8 +286,8 @@ int attn_fwd_run(const void* qkv, void* out, float* lse, int B, int S, int C, cu
     TVAE_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
     configured = true;
   }
-  dim3 grid((S + 127) / 128, nh, B);
-  attn_fwd_kernel<<<grid, 256, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh);
+  dim3 grid((S + 255) / 256, nh, B);
+  attn_fwd_kernel<<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -2,7 +2,7 @@
 //
 //   out[tile] = epilogue( sum_taps  A_tap[128 pixels x 64k] * W[BLOCK_N x 64k]^T )
 //
-// One persistent CTA per SM, 8 warps, warp-specialised:
+// One persistent CTA per SM, 12 warps, warp-specialised:
 //   warp 0  TMA producer   : per K block one 5-D pixel-box load (A; zero-filled halo = conv padding) and one
 //                            2-D weight box load (B) into a STAGES-deep 128B-swizzled smem ring
 //   warp 1  MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16, fp32 accumulators in
@@ -10,8 +10,9 @@
 //                            main loop of tile i+1
 //   warp 2  residual loader: TMA-loads the residual tile straight into the output staging buffer
 //   warp 3  idle
-//   warps 4-7 epilogue     : tcgen05.ld -> row/col affine, bias, GELU/SiLU, RoPE, residual -> bf16 -> swizzled
-//                            smem -> TMA store (or direct fp32 NCHW store for the 3-/64-channel heads)
+//   warps 4-11 epilogue    : tcgen05.ld -> row/col affine, bias, GELU/SiLU, RoPE, residual -> bf16 -> swizzled
+//                            smem -> TMA store (or direct fp32 NCHW store for the 3-/64-channel heads); two warps
+//                            per TMEM lane quarter, each taking every other 16-column group
 //
 // Every convolution, linear layer, pixel (un)shuffle and nearest-2x upsample of the reference is one launch of
 // this kernel with a different tap table (see include/transvae_sm100.h and transvae/_taps.py).
@@ -56,7 +57,7 @@ struct MtParams {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps
 
 template <int BLOCK_N>
 struct MtCfg {
@@ -193,7 +194,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], 8);
     }
     mbar_init(res_full, 1);
     mbar_init(out_free, 1);
@@ -299,8 +300,10 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
+    // 8 epilogue warps: warps w and w+4 share TMEM lane quarter (w & 3) and split the tile's columns between them
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;       // row of the tile owned by this thread
+    const int half = (warp - 4) >> 2;  // which interleaved half of the 16-column groups this warp handles
     const bool store_leader = (threadIdx.x == 128);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -342,7 +345,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
       const int n_base = n_t * BLOCK_N;
 #pragma unroll 1
-      for (int c16 = 0; c16 < BLOCK_N / 16; ++c16) {
+      for (int c16 = half; c16 < BLOCK_N / 16; c16 += 2) {
         uint32_t va[8], vb[8];
         tmem_ld8(t_row + c16 * 16, va);
         tmem_ld8(t_row + c16 * 16 + 8, vb);
@@ -395,7 +398,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 
       if constexpr (EPI != kEpiDirect) {
         fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (store_leader) {
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
@@ -405,7 +408,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           if (has_res) mbar_arrive(out_free);
         }
         // staging buffer may be overwritten only after the bulk store has read it
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
     if (store_leader) tma_store_wait<0>();

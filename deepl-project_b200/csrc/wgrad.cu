@@ -246,11 +246,12 @@ int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, cudaStream_t stream) {
   const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
   int sms = num_sms();
   if (sms <= 0) sms = 148;
-  long long splits = (2LL * sms + items - 1) / items;
+  // pixel splits: fill (at most) two full waves of CTAs -- rounding DOWN so the last wave is not nearly empty
+  long long splits = (2LL * sms) / items;
   if (splits > m_tiles) splits = m_tiles;
   if (splits < 1) splits = 1;
-  // keep at least ~8 pixel tiles per CTA so the TMEM drain + atomics are amortised
-  while (splits > 1 && m_tiles / splits < 8) --splits;
+  // keep at least ~4 pixel tiles per CTA so the TMEM drain + atomics are amortised
+  while (splits > 1 && m_tiles / splits < 4) --splits;
   P.splits = (int)splits;
   const long long grid = items * splits;
   TVAE_REQUIRE(grid < (1LL << 31), "wgrad: grid too large");

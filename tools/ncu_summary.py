@@ -1,0 +1,21 @@
+"""Summarise an .ncu-rep (raw page) into the handful of metrics the roofline discussion needs."""
+import csv, subprocess, sys
+rep, out = sys.argv[1], sys.argv[2]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second", "sm__cycles_elapsed.max",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed.sum", "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct",
+        "smsp__cycles_active.avg"]
+with open(out, "w") as f:
+    f.write(f"# ncu --set full --clock-control none summary of {rep}\n")
+    for r in rows[2:]:
+        f.write("----\n")
+        for h, u, v in zip(hdr, units, r):
+            if h in want:
+                f.write(f"{h} [{u}] = {v}\n")
+print(open(out).read())
