@@ -35,6 +35,58 @@ __device__ __forceinline__ void att_tma_load_3d(void* smem, const CUtensorMap* m
       : "memory");
 }
 
+// Row maximum of one 128-wide score block (one row per thread).  MASK: the block reaches past the sequence end.
+template <bool MASK>
+__device__ __forceinline__ float att_row_max(uint32_t t_s, int key0, int S) {
+  float m = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld32(t_s + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float s = __uint_as_float(v[i]);
+      if (MASK) s = (key0 + c * 32 + i < S) ? s : -INFINITY;
+      m = fmaxf(m, s);
+    }
+  }
+  return m;
+}
+
+// P = exp2(S - m_new) -> bf16 -> swizzled smem (K-major A operand of the P V product); returns the row sum.
+template <bool MASK>
+__device__ __forceinline__ float att_exp_store(uint32_t t_s, uint8_t* sPt, int r, int key0, int S, float m_new) {
+  float l = 0.0f;
+  const float neg_m = -m_new;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld32(t_s + c * 32, v);
+    tmem_ld_wait();
+    float p[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float e = exp2f(__uint_as_float(v[i]) + neg_m);
+      if (MASK) e = (key0 + c * 32 + i < S) ? e : 0.0f;
+      p[i] = e;
+      l += e;
+    }
+    uint8_t* row = sPt + (c >> 1) * kTileBytes + r * 128;
+    const int cbase = (c & 1) * 4;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 o;
+      o.x = pack_bf16(p[g * 8 + 0], p[g * 8 + 1]);
+      o.y = pack_bf16(p[g * 8 + 2], p[g * 8 + 3]);
+      o.z = pack_bf16(p[g * 8 + 4], p[g * 8 + 5]);
+      o.w = pack_bf16(p[g * 8 + 6], p[g * 8 + 7]);
+      *reinterpret_cast<uint4*>(row + (((cbase + g) ^ (r & 7)) << 4)) = o;
+    }
+  }
+  return l;
+}
+
 __global__ void __launch_bounds__(kAttThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                 float* __restrict__ lse, int S, int C, int nh) {
@@ -162,19 +214,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       const int key0 = j * 128;
+      const bool partial = key0 + 128 > S;     // only the last block can reach past the sequence end
       // pass 1: row max
-      float m_blk = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_s + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (key0 + c * 32 + i < S) ? __uint_as_float(v[i]) : -INFINITY;
-          m_blk = fmaxf(m_blk, s);
-        }
-      }
+      const float m_blk = partial ? att_row_max<true>(t_s, key0, S) : att_row_max<false>(t_s, key0, S);
       const float m_new = fmaxf(m_run, m_blk);
       const float alpha = exp2f(m_run - m_new);   // m_run = -inf on the first block -> 0
       // the previous block's P V must be complete before sP is overwritten; fold it into the accumulator now
@@ -190,32 +232,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
         }
       }
-      // pass 2: P = exp2(S - m_new) -> bf16 -> swizzled smem (K-major A operand of the P V product)
-      float l_blk = 0.0f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_s + c * 32, v);
-        tmem_ld_wait();
-        float p[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (key0 + c * 32 + i < S) ? __uint_as_float(v[i]) : -INFINITY;
-          p[i] = exp2f(s - m_new);
-          l_blk += p[i];
-        }
-        uint8_t* row = sPt + (c >> 1) * kTileBytes + r * 128;
-        const int cbase = (c & 1) * 4;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o;
-          o.x = pack_bf16(p[g * 8 + 0], p[g * 8 + 1]);
-          o.y = pack_bf16(p[g * 8 + 2], p[g * 8 + 3]);
-          o.z = pack_bf16(p[g * 8 + 4], p[g * 8 + 5]);
-          o.w = pack_bf16(p[g * 8 + 6], p[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(row + (((cbase + g) ^ (r & 7)) << 4)) = o;
-        }
-      }
+      // pass 2: P = exp2(S - m_new) -> bf16 -> swizzled smem
+      const float l_blk = partial ? att_exp_store<true>(t_s, sPt, r, key0, S, m_new)
+                                  : att_exp_store<false>(t_s, sPt, r, key0, S, m_new);
       l_run = l_run * alpha + l_blk;
       m_run = m_new;
       alpha_prev = alpha;

@@ -175,11 +175,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tmem_ld32(t_dP + lane_off + c * 32, pv);
         tmem_ld_wait();
         float p[32], dz[32];
+        if (k0 + 128 <= S) {       // full key tile: no masking (saves 3 instructions per element)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const bool ok = (k0 + c * 32 + j) < S;
-          p[j] = ok ? exp2f(__uint_as_float(sv[j]) - l2) : 0.0f;
-          dz[j] = p[j] * (__uint_as_float(pv[j]) - dl);
+          for (int j = 0; j < 32; ++j) {
+            p[j] = exp2f(__uint_as_float(sv[j]) - l2);
+            dz[j] = p[j] * (__uint_as_float(pv[j]) - dl);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool ok = (k0 + c * 32 + j) < S;
+            p[j] = ok ? exp2f(__uint_as_float(sv[j]) - l2) : 0.0f;
+            dz[j] = p[j] * (__uint_as_float(pv[j]) - dl);
+          }
         }
         uint8_t* prow = sP + (c >> 1) * kBT + r * 128;
         uint8_t* zrow = sDZ + (c >> 1) * kBT + r * 128;
