@@ -6,7 +6,7 @@
 // applied the reference's RoPE to q and k and multiplied q by scale*log2(e), so scores are in log2 units.
 //
 // One CTA per (256-query tile = two 128-row Q tiles, head, image), 12 warps:
-//   warp 0     TMA producer : both Q tiles once, then K/V tiles through a 3-stage ring
+//   warp 0     TMA producer : both Q tiles once, then K/V tiles through a 4-stage ring
 //   warp 1     MMA issuer   : per K/V block and Q tile t:  S_t = Q_t K^T (tcgen05, M=128 N=128 K=64 -> TMEM) and
 //                             O_t = P_t V (M=128 N=64 K=128; P from smem, V as an MN-major operand)
 //   warps 4-7  softmax for Q tile 0, warps 8-11 for Q tile 1 : one query row per thread: tcgen05.ld S, online
@@ -21,7 +21,7 @@
 
 namespace tvae {
 
-constexpr int kAttStages = 3;
+constexpr int kAttStages = 4;
 constexpr int kTileBytes = 128 * 64 * 2;  // 16 KiB: 128 rows x 64 bf16
 constexpr int kAttThreads = 384;
 constexpr int kAttSmem = 2 * kTileBytes /*Q0,Q1*/ + kAttStages * 2 * kTileBytes /*K,V*/ + 2 * 2 * kTileBytes /*P0,P1*/ +
@@ -101,9 +101,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* q_full = bars;                           // 1
   uint64_t* kv_full = bars + 1;                      // [stages]
   uint64_t* kv_empty = kv_full + kAttStages;         // [stages]
-  uint64_t* s_full = kv_empty + kAttStages;          // [2 tiles]
-  uint64_t* s_empty = s_full + 2;                    // [2 tiles]
-  uint64_t* p_full = s_empty + 2;                    // [2 tiles]
+  uint64_t* s_full = kv_empty + kAttStages;          // [2 tiles][2 buffers]
+  uint64_t* b_free = s_full + 4;                     // [2 tiles][2 buffers]
+  uint64_t* p_full = b_free + 4;                     // [2 tiles]
   uint64_t* o_full = p_full + 2;                     // [2 tiles]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
@@ -122,8 +122,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_init(&kv_empty[s], 1);
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&s_empty[t], 4);
+      for (int u = 0; u < 2; ++u) {
+        mbar_init(&s_full[t * 2 + u], 1);
+        mbar_init(&b_free[t * 2 + u], 4);
+      }
       mbar_init(&p_full[t], 4);
       mbar_init(&o_full[t], 1);
     }
@@ -137,7 +139,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
+  // TMEM: tile t, buffer u at columns t*256 + u*128: S_t(j) fills buffer j&1 (128 columns); O_t(j) = P_t(j) V_j is
+  // written over the first 64 columns of the same buffer once the softmax warps have consumed S_t(j).  All 512 columns
+  // are in use, and S_t(j+1) is computed while the softmax of block j is still running.
 
   if (warp == 0) {
     if (lane == 0) {
@@ -163,16 +167,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
       auto issue_qk = [&](int j, int t) {
         const int stage = j % kAttStages;
+        const int u = j & 1;
         if (t == 0) mbar_wait(&kv_full[stage], (j / kAttStages) & 1);
-        mbar_wait(&s_empty[t], (j & 1) ^ 1);
+        mbar_wait(&b_free[t * 2 + u], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t q_base = smem_u32(sQ + t * kTileBytes);
         const uint32_t k_base = smem_u32(sK + stage * kTileBytes);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_base + t * 128, umma_desc_kmajor_sw128(q_base + k * 32), umma_desc_kmajor_sw128(k_base + k * 32),
-                   idesc_qk, k != 0);
-        umma_commit(&s_full[t]);
+          umma_f16(tmem_base + t * 256 + u * 128, umma_desc_kmajor_sw128(q_base + k * 32),
+                   umma_desc_kmajor_sw128(k_base + k * 32), idesc_qk, k != 0);
+        umma_commit(&s_full[t * 2 + u]);
       };
       auto issue_pv = [&](int j, int t) {
         const int stage = j % kAttStages;
@@ -182,19 +187,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const uint32_t v_base = smem_u32(sV + stage * kTileBytes);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_f16(tmem_base + 256 + t * 64, umma_desc_kmajor_sw128(p_base + (k >> 2) * kTileBytes + (k & 3) * 32),
+          umma_f16(tmem_base + t * 256 + (j & 1) * 128, umma_desc_kmajor_sw128(p_base + (k >> 2) * kTileBytes + (k & 3) * 32),
                    umma_desc_mnmajor_sw128(v_base + k * 2048, 1024, 1024), idesc_pv, k != 0);
         umma_commit(&o_full[t]);
       };
       mbar_wait(q_full, 0);
-      issue_qk(0, 0);
-      issue_qk(0, 1);
+      for (int j = 0; j < 2 && j < nblk; ++j) {
+        issue_qk(j, 0);
+        issue_qk(j, 1);
+      }
       for (int j = 0; j < nblk; ++j) {
         issue_pv(j, 0);
-        if (j + 1 < nblk) issue_qk(j + 1, 0);
         issue_pv(j, 1);
         umma_commit(&kv_empty[j % kAttStages]);
-        if (j + 1 < nblk) issue_qk(j + 1, 1);
+        if (j + 2 < nblk) {
+          issue_qk(j + 2, 0);
+          issue_qk(j + 2, 1);
+        }
       }
     }
   } else if (warp >= 4) {
@@ -202,8 +211,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_off + t * 128;
-    const uint32_t t_o = tmem_base + lane_off + 256 + t * 64;
+    const uint32_t t_tile = tmem_base + lane_off + t * 256;
     uint8_t* sPt = sP + t * 2 * kTileBytes;
     float o_acc[64];
 #pragma unroll
@@ -211,7 +219,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     float m_run = -INFINITY, l_run = 0.0f, alpha_prev = 1.0f;
 
     for (int j = 0; j < nblk; ++j) {
-      mbar_wait(&s_full[t], j & 1);
+      const uint32_t t_s = t_tile + (j & 1) * 128;
+      mbar_wait(&s_full[t * 2 + (j & 1)], (j >> 1) & 1);
       tc_fence_after();
       const int key0 = j * 128;
       const bool partial = key0 + 128 > S;     // only the last block can reach past the sequence end
@@ -223,6 +232,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if (j > 0) {
         mbar_wait(&o_full[t], (j - 1) & 1);
         tc_fence_after();
+        const uint32_t t_o = t_tile + ((j - 1) & 1) * 128;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t v[32];
@@ -231,6 +241,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
         }
+        // buffer (j-1)&1 of this tile may now receive S_t(j+1)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&b_free[t * 2 + ((j - 1) & 1)]);
       }
       // pass 2: P = exp2(S - m_new) -> bf16 -> swizzled smem
       const float l_blk = partial ? att_exp_store<true>(t_s, sPt, r, key0, S, m_new)
@@ -242,14 +256,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_empty[t]);
-        mbar_arrive(&p_full[t]);
-      }
+      if (lane == 0) mbar_arrive(&p_full[t]);
     }
     // last block's P V
     mbar_wait(&o_full[t], (nblk - 1) & 1);
     tc_fence_after();
+    const uint32_t t_o = t_tile + ((nblk - 1) & 1) * 128;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t v[32];

@@ -25,18 +25,16 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // Backward of the bias add + GELU / SiLU epilogues of tvae_mtgemm (conv.py:86,56,58; upsample.py:35,96).
 // Algorithmic bytes per element: 2 (dY) [+ 2 (Z) + 2 (dZ) when act != none].
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bias_act_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ z,
-                                                           uint4* __restrict__ dz, float* __restrict__ colsum,
-                                                           long long R0, int Pn, int R1, int Q, int act,
-                                                           int rows_per_block) {
-  extern __shared__ float s_col[];  // [Pn * Q]
-  const int nvec = Q >> 3;
-  const int ncol = Pn * Q;
-  for (int i = threadIdx.x; i < ncol; i += blockDim.x) s_col[i] = 0.0f;
+// Processes columns [c0, c0+Qs) of the row-major [R0*Pn*R1, Qfull] matrix; row r belongs to phase (r / R1) % Pn.
+__global__ void __launch_bounds__(256) bias_act_bwd_slab_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ z,
+                                                                uint4* __restrict__ dz, float* __restrict__ colsum,
+                                                                long long nrows, int Pn, int R1, int Qfull, int c0, int Qs,
+                                                                int act, int rows_per_block) {
+  extern __shared__ float s_col[];   // [Pn][Qs]
+  const int nvec = Qs >> 3, nvf = Qfull >> 3, v0 = c0 >> 3;
+  for (int i = threadIdx.x; i < Pn * Qs; i += blockDim.x) s_col[i] = 0.0f;
   __syncthreads();
   const int v = threadIdx.x % nvec, rl = threadIdx.x / nvec, rpp = blockDim.x / nvec;
-  // a "row" here is one (r0, p, r1) triple; rows are contiguous Q-vectors
-  const long long nrows = R0 * Pn * R1;
   const long long r_begin = (long long)blockIdx.x * rows_per_block;
   const long long r_end = min(nrows, r_begin + rows_per_block);
   float acc[2][8];
@@ -44,79 +42,7 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const uint4* __restri
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.0f;
   if (rl < rpp) {
     for (long long r = r_begin + rl; r < r_end; r += rpp) {
-      const int p = (int)((r / R1) % Pn);
-      float g[8];
-      unpack8(__ldg(dy + r * nvec + v), g);
-      if (act != TVAE_ACT_NONE) {
-        float zz[8];
-        unpack8(__ldg(z + r * nvec + v), zz);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] *= (act == TVAE_ACT_GELU) ? gelu_erf_grad(zz[i]) : silu_grad(zz[i]);
-        dz[r * nvec + v] = pack8(g);
-        // the column sums must see the bf16-rounded dZ that the GEMMs will read
-        unpack8(pack8(g), g);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[p & 1][i] += g[i];
-    }
-#pragma unroll
-    for (int pp = 0; pp < 2; ++pp)
-      if (pp < Pn)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(&s_col[pp * Q + v * 8 + i], acc[pp][i]);
-  }
-  __syncthreads();
-  if (colsum != nullptr)
-    for (int i = threadIdx.x; i < ncol; i += blockDim.x) atomicAdd(colsum + i, s_col[i]);
-}
-
-int bias_act_bwd_run(const void* dy, const void* z, void* dz, float* colsum, long long R0, int Pn, int R1, int Q, int act,
-                     cudaStream_t stream) {
-  TVAE_REQUIRE(Q % 8 == 0 && Q / 8 <= 256 * 8, "bias_act_bwd: Q=%d unsupported", Q);
-  TVAE_REQUIRE(Pn == 1 || Pn == 2, "bias_act_bwd: P must be 1 or 2");
-  TVAE_REQUIRE(act == TVAE_ACT_NONE || (z != nullptr && dz != nullptr), "bias_act_bwd: activation needs z and dz");
-  if (colsum) TVAE_CHECK_CUDA(cudaMemsetAsync(colsum, 0, (size_t)Pn * Q * sizeof(float), stream));
-  const int nvec = Q / 8;
-  int threads = nvec >= 256 ? 256 : (256 / nvec) * nvec;
-  // wide rows: several passes of 256 vectors per row are handled by treating each 256-vector slab as its own column set
-  TVAE_REQUIRE(nvec <= 256 || nvec % 256 == 0, "bias_act_bwd: Q=%d must be <= 2048 or a multiple of 2048", Q);
-  if (nvec > 256) {
-    // split wide matrices into column slabs of 2048: [R0*.., Q] -> treat as Pn=1 rows with stride; simple loop
-    TVAE_REQUIRE(Pn == 1 && R1 == 1, "bias_act_bwd: wide rows only for plain matrices");
-    // handled by the strided kernel below
-  }
-  const long long nrows = R0 * Pn * R1;
-  int rpb = 1024;
-  while (rpb > 32 && (nrows + rpb - 1) / rpb < 2LL * num_sms()) rpb >>= 1;
-  if (nvec <= 256) {
-    const int grid = (int)((nrows + rpb - 1) / rpb);
-    bias_act_bwd_kernel<<<grid, threads, (size_t)Pn * Q * sizeof(float), stream>>>(
-        reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(z), reinterpret_cast<uint4*>(dz), colsum, R0,
-        Pn, R1, Q, act, rpb);
-    TVAE_CHECK_CUDA(cudaGetLastError());
-    return 0;
-  }
-  set_last_error("bias_act_bwd: Q=%d > 2048 must be issued per 2048-column slab by the caller", Q);
-  return -2;
-}
-
-// Strided variant for wide matrices: processes columns [c0, c0+Qs) of a row-major [M, Qfull] matrix.
-__global__ void __launch_bounds__(256) bias_act_bwd_slab_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ z,
-                                                                uint4* __restrict__ dz, float* __restrict__ colsum,
-                                                                long long M, int Qfull, int c0, int Qs, int act,
-                                                                int rows_per_block) {
-  extern __shared__ float s_col[];
-  const int nvec = Qs >> 3, nvf = Qfull >> 3, v0 = c0 >> 3;
-  for (int i = threadIdx.x; i < Qs; i += blockDim.x) s_col[i] = 0.0f;
-  __syncthreads();
-  const int v = threadIdx.x % nvec, rl = threadIdx.x / nvec, rpp = blockDim.x / nvec;
-  const long long r_begin = (long long)blockIdx.x * rows_per_block;
-  const long long r_end = min(M, r_begin + rows_per_block);
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-  if (rl < rpp) {
-    for (long long r = r_begin + rl; r < r_end; r += rpp) {
+      const int p = (Pn == 1) ? 0 : (int)((r / R1) % Pn);
       const long long idx = r * nvf + v0 + v;
       float g[8];
       unpack8(__ldg(dy + idx), g);
@@ -126,37 +52,48 @@ __global__ void __launch_bounds__(256) bias_act_bwd_slab_kernel(const uint4* __r
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] *= (act == TVAE_ACT_GELU) ? gelu_erf_grad(zz[i]) : silu_grad(zz[i]);
         dz[idx] = pack8(g);
-        unpack8(pack8(g), g);
+        unpack8(pack8(g), g);   // the column sums must see the bf16-rounded dZ that the GEMMs will read
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += g[i];
+      for (int i = 0; i < 8; ++i) acc[p & 1][i] += g[i];
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&s_col[v * 8 + i], acc[i]);
+    for (int pp = 0; pp < 2; ++pp)
+      if (pp < Pn)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&s_col[pp * Qs + v * 8 + i], acc[pp][i]);
   }
   __syncthreads();
   if (colsum != nullptr)
-    for (int i = threadIdx.x; i < Qs; i += blockDim.x) atomicAdd(colsum + c0 + i, s_col[i]);
+    for (int i = threadIdx.x; i < Pn * Qs; i += blockDim.x)
+      atomicAdd(colsum + (size_t)(i / Qs) * Qfull + c0 + (i % Qs), s_col[i]);
+}
+
+int bias_act_bwd_run(const void* dy, const void* z, void* dz, float* colsum, long long R0, int Pn, int R1, int Q, int act,
+                     cudaStream_t stream) {
+  TVAE_REQUIRE(Q % 8 == 0, "bias_act_bwd: Q=%d must be a multiple of 8", Q);
+  TVAE_REQUIRE(Pn == 1 || Pn == 2, "bias_act_bwd: P must be 1 or 2");
+  TVAE_REQUIRE(act == TVAE_ACT_NONE || (z != nullptr && dz != nullptr), "bias_act_bwd: activation needs z and dz");
+  if (colsum) TVAE_CHECK_CUDA(cudaMemsetAsync(colsum, 0, (size_t)Pn * Q * sizeof(float), stream));
+  const long long nrows = R0 * Pn * R1;
+  int rpb = 1024;
+  while (rpb > 32 && (nrows + rpb - 1) / rpb < 2LL * num_sms()) rpb >>= 1;
+  const int grid = (int)((nrows + rpb - 1) / rpb);
+  for (int c0 = 0; c0 < Q; c0 += 2048) {
+    const int qs = (Q - c0) < 2048 ? (Q - c0) : 2048;
+    const int nvec = qs / 8;
+    const int threads = nvec >= 256 ? 256 : (256 / nvec) * nvec;
+    bias_act_bwd_slab_kernel<<<grid, threads, (size_t)Pn * qs * sizeof(float), stream>>>(
+        reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(z), reinterpret_cast<uint4*>(dz), colsum, nrows,
+        Pn, R1, Q, c0, qs, act, rpb);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
 }
 
 int bias_act_bwd_matrix_run(const void* dy, const void* z, void* dz, float* colsum, long long M, int N, int act,
                             cudaStream_t stream) {
-  TVAE_REQUIRE(N % 8 == 0, "bias_act_bwd: N=%d must be a multiple of 8", N);
-  TVAE_REQUIRE(act == TVAE_ACT_NONE || (z != nullptr && dz != nullptr), "bias_act_bwd: activation needs z and dz");
-  if (colsum) TVAE_CHECK_CUDA(cudaMemsetAsync(colsum, 0, (size_t)N * sizeof(float), stream));
-  int rpb = 1024;
-  while (rpb > 32 && (M + rpb - 1) / rpb < 2LL * num_sms()) rpb >>= 1;
-  const int grid = (int)((M + rpb - 1) / rpb);
-  for (int c0 = 0; c0 < N; c0 += 2048) {
-    const int qs = (N - c0) < 2048 ? (N - c0) : 2048;
-    const int nvec = qs / 8;
-    const int threads = nvec >= 256 ? 256 : (256 / nvec) * nvec;
-    bias_act_bwd_slab_kernel<<<grid, threads, (size_t)qs * sizeof(float), stream>>>(
-        reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(z), reinterpret_cast<uint4*>(dz), colsum, M, N,
-        c0, qs, act, rpb);
-    TVAE_CHECK_CUDA(cudaGetLastError());
-  }
-  return 0;
+  return bias_act_bwd_run(dy, z, dz, colsum, M, 1, 1, N, act, stream);
 }
 
 // y = act(z) elementwise (training path: the GEMM stores the pre-activation z that the backward pass needs, the

@@ -21,6 +21,13 @@ for i in range(2):
     out = tr.train_step(x)
 torch.cuda.synchronize()
 print("loss", {k: float(v) for k, v in out.items()}, "peak GB", torch.cuda.max_memory_allocated() / 2**30, flush=True)
+if os.environ.get("TVAE_PROFILE_RANGE"):
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    tr.train_step(x)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    sys.exit(0)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ops.PROFILE = []
 n0 = ops.LAUNCHES
