@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__
     const int p0 = blockIdx.x * pix_per_block;
     const int p1 = min(HW, p0 + pix_per_block);
     const uint4* base = x + (size_t)b * HW * nvec + v;
+#pragma unroll 4
     for (int p = p0 + pv; p < p1; p += ppb) {
       const uint4 u = __ldg(base + (size_t)p * nvec);
       float2 t;
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__
   }
   const uint4* xb = x + (size_t)b * total;
   uint4* yb = y + (size_t)b * total;
+#pragma unroll 4
   for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     const uint4 u = __ldg(xb + i);
     float f[8];
