@@ -38,27 +38,31 @@ __device__ __forceinline__ void att_tma_load_3d(void* smem, const CUtensorMap* m
 // Row maximum of one 128-wide score block (one row per thread).  MASK: the block reaches past the sequence end.
 template <bool MASK>
 __device__ __forceinline__ float att_row_max(uint32_t t_s, int key0, int S) {
-  float m = -INFINITY;
+  float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     uint32_t v[32];
     tmem_ld32(t_s + c * 32, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float s = __uint_as_float(v[i]);
-      if (MASK) s = (key0 + c * 32 + i < S) ? s : -INFINITY;
-      m = fmaxf(m, s);
+    for (int i = 0; i < 32; i += 2) {
+      float a = __uint_as_float(v[i]), b = __uint_as_float(v[i + 1]);
+      if (MASK) {
+        a = (key0 + c * 32 + i < S) ? a : -INFINITY;
+        b = (key0 + c * 32 + i + 1 < S) ? b : -INFINITY;
+      }
+      m0 = fmaxf(m0, a);
+      m1 = fmaxf(m1, b);
     }
   }
-  return m;
+  return fmaxf(m0, m1);
 }
 
 // P = exp2(S - m_new) -> bf16 -> swizzled smem (K-major A operand of the P V product); returns the row sum.
 template <bool MASK>
 __device__ __forceinline__ float att_exp_store(uint32_t t_s, uint8_t* sPt, int r, int key0, int S, float m_new) {
-  float l = 0.0f;
-  const float neg_m = -m_new;
+  float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;   // four independent chains: a single running sum is a 32-deep
+  const float neg_m = -m_new;                          // dependent FADD chain per chunk
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     uint32_t v[32];
@@ -70,7 +74,13 @@ __device__ __forceinline__ float att_exp_store(uint32_t t_s, uint8_t* sPt, int r
       float e = exp2f(__uint_as_float(v[i]) + neg_m);
       if (MASK) e = (key0 + c * 32 + i < S) ? e : 0.0f;
       p[i] = e;
-      l += e;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      l0 += p[i];
+      l1 += p[i + 1];
+      l2 += p[i + 2];
+      l3 += p[i + 3];
     }
     uint8_t* row = sPt + (c >> 1) * kTileBytes + r * 128;
     const int cbase = (c & 1) * 4;
@@ -84,7 +94,7 @@ __device__ __forceinline__ float att_exp_store(uint32_t t_s, uint8_t* sPt, int r
       *reinterpret_cast<uint4*>(row + (((cbase + g) ^ (r & 7)) << 4)) = o;
     }
   }
-  return l;
+  return (l0 + l1) + (l2 + l3);
 }
 
 __global__ void __launch_bounds__(kAttThreads, 1)

@@ -17,7 +17,7 @@
 namespace tvae {
 
 constexpr int kBT = 128 * 64 * 2;  // 16 KiB tile
-constexpr int kBwdSmem = 2 * kBT /*K,V*/ + 2 * 2 * kBT /*Q,dO ring*/ + 2 * 2 * kBT /*P, dZ*/ + 1024 + 256;
+constexpr int kBwdSmem = 2 * kBT /*K,V*/ + 2 * 2 * kBT /*Q,dO ring*/ + 2 * 2 * 2 * kBT /*P, dZ double buffered*/ + 1024 + 256;
 
 __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
@@ -38,16 +38,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint8_t* sV = sK + kBT;
   uint8_t* sQ = sV + kBT;            // [2 stages]
   uint8_t* sDO = sQ + 2 * kBT;       // [2 stages]
-  uint8_t* sP = sDO + 2 * kBT;       // 2 chunks (keys 0-63, 64-127)
-  uint8_t* sDZ = sP + 2 * kBT;       // 2 chunks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDZ + 2 * kBT);
+  uint8_t* sP = sDO + 2 * kBT;       // [2 buffers] x 2 chunks (keys 0-63, 64-127)
+  uint8_t* sDZ = sP + 4 * kBT;       // [2 buffers] x 2 chunks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDZ + 4 * kBT);
   uint64_t* kv_full = bars;          // 1
   uint64_t* qdo_full = bars + 1;     // [2]
   uint64_t* qdo_empty = bars + 3;    // [2]
   uint64_t* sdp_full = bars + 5;     // 1
   uint64_t* pds_full = bars + 6;     // 1 (4 warp arrivals)
-  uint64_t* mma_done = bars + 7;     // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* mma_done = bars + 7;     // [2] (alternating, so a waiter never lags two phases)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128;
@@ -65,7 +65,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
     mbar_init(sdp_full, 1);
     mbar_init(pds_full, 4);
-    mbar_init(mma_done, 1);
+    mbar_init(&mma_done[0], 1);
+    mbar_init(&mma_done[1], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -97,7 +98,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       constexpr uint32_t id_kk = umma_idesc_bf16(128, 128, 0, 0);   // S~, dP : both operands K-major (d contiguous)
       constexpr uint32_t id_mm = umma_idesc_bf16(128, 64, 1, 1);    // dV, dK : both MN-major (reduction over queries)
       constexpr uint32_t id_km = umma_idesc_bf16(128, 64, 0, 1);    // dQ     : A = dZ K-major, B = K_j MN-major
-      const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV), p_base = smem_u32(sP), dz_base = smem_u32(sDZ);
+      const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV);
       auto issue_sdp = [&](int i) {
         const int st = i & 1;
         mbar_wait(&qdo_full[st], (i >> 1) & 1);
@@ -118,6 +119,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         mbar_wait(pds_full, i & 1);
         tc_fence_after();
         const uint32_t q_base = smem_u32(sQ + st * kBT), do_base = smem_u32(sDO + st * kBT);
+        const uint32_t p_base = smem_u32(sP + (i & 1) * 2 * kBT), dz_base = smem_u32(sDZ + (i & 1) * 2 * kBT);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {   // 16 queries per MMA
           umma_f16(t_dV, umma_desc_mnmajor_sw128(p_base + k * 2048, kBT, 1024),
@@ -130,7 +132,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           umma_f16(t_dQ + (i & 1) * 64, umma_desc_kmajor_sw128(dz_base + (k >> 2) * kBT + (k & 3) * 32),
                    umma_desc_mnmajor_sw128(k_base + k * 2048, kBT, 1024), id_km, k != 0);
         umma_commit(&qdo_empty[st]);
-        umma_commit(mma_done);
+        umma_commit(&mma_done[i & 1]);
         if (i + 1 < nq) issue_sdp(i + 1);
       }
     }
@@ -164,10 +166,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const float dl = (qrow < S) ? __ldg(delta + stat_base + qrow) : 0.0f;
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
-      if (i > 0) {
-        mbar_wait(mma_done, (i - 1) & 1);   // P / dZ smem free, dQ_{i-1} complete
-        tc_fence_after();
-      }
+      if (i >= 2) mbar_wait(&mma_done[i & 1], ((i - 2) >> 1) & 1);   // P / dZ buffer i&1 no longer read by MMA(i-2)
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t sv[32], pv[32];
@@ -189,8 +188,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             dz[j] = p[j] * (__uint_as_float(pv[j]) - dl);
           }
         }
-        uint8_t* prow = sP + (c >> 1) * kBT + r * 128;
-        uint8_t* zrow = sDZ + (c >> 1) * kBT + r * 128;
+        uint8_t* prow = sP + ((i & 1) * 2 + (c >> 1)) * kBT + r * 128;
+        uint8_t* zrow = sDZ + ((i & 1) * 2 + (c >> 1)) * kBT + r * 128;
         const int cbase = (c & 1) * 4;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -208,9 +207,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      if (i > 0) drain_dq(i - 1);
+      if (i > 0) {
+        mbar_wait(&mma_done[(i - 1) & 1], ((i - 1) >> 1) & 1);   // dQ_{i-1} complete
+        tc_fence_after();
+        drain_dq(i - 1);
+      }
     }
-    mbar_wait(mma_done, (nq - 1) & 1);
+    mbar_wait(&mma_done[(nq - 1) & 1], ((nq - 1) >> 1) & 1);
     tc_fence_after();
     drain_dq(nq - 1);
     // dV and dK~ of this key tile (row r = key k0 + r)
