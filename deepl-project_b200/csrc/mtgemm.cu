@@ -16,144 +16,14 @@
 //
 // Every convolution, linear layer, pixel (un)shuffle and nearest-2x upsample of the reference is one launch of
 // this kernel with a different tap table (see include/transvae_sm100.h and transvae/_taps.py).
-#include "../../include/transvae_sm100.h"
-#include "common.cuh"
-#include "tmap.cuh"
+#include <cstdlib>
+
+#include "mtgemm_common.cuh"
 
 namespace tvae {
 
-struct MtTap {
-  int32_t c_off;
-  int32_t wk_off;
-  int16_t kblocks;
-  int8_t map, dw, p, dh;
-  int8_t pad_[2];
-};
-static_assert(sizeof(MtTap) == 16, "MtTap must be 16 bytes");
-
-struct MtParams {
-  int tiles_w, tiles_h, tiles_b, n_tiles;
-  int tw, th, nb;
-  int num_phases;
-  int ntaps[TVAE_MAX_PHASES];
-  int out_p[TVAE_MAX_PHASES];
-  int out_c_off[TVAE_MAX_PHASES];
-  MtTap taps[TVAE_MAX_PHASES][TVAE_MAX_TAPS];
-  const float* bias;
-  int n_total;
-  int act;
-  const float* row_scale;
-  const float* row_shift;
-  const float* col_sum;
-  int has_residual;
-  const float2* rope_tab;
-  int rope_C, rope_H, rope_W;
-  float q_scale;
-  float* out_f32;
-  int out_n;
-  int vB, vH, vW;  // output view extents (pixels) for row indexing / bounds
-};
-
-constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;
-constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
-constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps
-
-template <int BLOCK_N>
-struct MtCfg {
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kOutBytes = kBlockM * BLOCK_N * 2;
-  static constexpr int kStages = (227 * 1024 - 2048 - kOutBytes) / (kABytes + kBBytes) > 8
-                                     ? 8
-                                     : (227 * 1024 - 2048 - kOutBytes) / (kABytes + kBBytes);
-  static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kOutBytes + 1024 /*align slack*/ + 256 /*bars*/;
-};
-
-// Epilogue variants (compile-time, so each kernel's epilogue is a few hundred instructions: the first version kept
-// every option as a run-time branch inside a 32x unrolled loop and was instruction-fetch bound -- ncu showed
-// stall_no_inst on the epilogue warps and the MMA warp waiting on tmem_empty).
-enum Epi : int {
-  kEpiBias = 0,        // v = acc + bias
-  kEpiBiasRes = 1,     // v = acc + bias + residual
-  kEpiBiasGelu = 2,    // v = gelu(acc + bias)
-  kEpiBiasSilu = 3,    // v = silu(acc + bias)
-  kEpiRsBiasGelu = 4,  // v = gelu(rs[m] * acc + bias)                      (RMSNorm folded into proj_in)
-  kEpiAffineRope = 5,  // v = rope(rs[m] * acc - rsh[m] * cs[n] + bias)     (RMSNorm + LayerNorm folded into QKV)
-  kEpiDirect = 6,      // fp32 NCHW direct store of acc + bias
-  kEpiRsBias = 7,      // v = rs[m] * acc - rsh[m] * cs[n] + bias [+ residual] (generic, tests / bare modules)
-};
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr)
-               : "memory");
-}
-
-struct EpiRow {
-  float rs, rsh;
-  int rope_r, rope_c;
-  bool row_ok;
-  int pw, phh, pb;
-};
-
-// Epilogue math for 8 consecutive output columns [n, n+8) of one row.
-template <int EPI>
-__device__ __forceinline__ void epi_math8(const MtParams& P, const float* __restrict__ bias, const EpiRow& R, int n,
-                                          const uint32_t (&v)[8], float (&f)[8]) {
-  float bv[8];
-  if (bias != nullptr) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n) + 1);
-    bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
-  } else {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) bv[k] = 0.0f;
-  }
-  if constexpr (EPI == kEpiRsBiasGelu) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = fmaf(__uint_as_float(v[k]), R.rs, bv[k]);
-  } else if constexpr (EPI == kEpiAffineRope || EPI == kEpiRsBias) {
-    if (P.row_shift != nullptr) {
-      const float4 c0 = __ldg(reinterpret_cast<const float4*>(P.col_sum + n));
-      const float4 c1 = __ldg(reinterpret_cast<const float4*>(P.col_sum + n) + 1);
-      const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-      for (int k = 0; k < 8; ++k) bv[k] = fmaf(-R.rsh, cv[k], bv[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = fmaf(__uint_as_float(v[k]), R.rs, bv[k]);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[k]) + bv[k];
-  }
-  if constexpr (EPI == kEpiBiasGelu || EPI == kEpiRsBiasGelu) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = gelu_erf(f[k]);
-  } else if constexpr (EPI == kEpiBiasSilu) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = silu(f[k]);
-  }
-  if constexpr (EPI == kEpiAffineRope) {
-    if (P.rope_tab != nullptr && n < 2 * P.rope_C) {
-      // columns n..n+7 sit in one half of a 64-wide head: the first half rotates with the row index, the second with
-      // the column index (attention.py:161-170); pair (2i, 2i+1) uses the angle of slot 2i for the even output and of
-      // slot 2i+1 for the odd output (attention.py:178-197).
-      const int j0 = n & 63;
-      const int pos = (j0 < 32) ? R.rope_r : R.rope_c;
-      const float4* tab = reinterpret_cast<const float4*>(P.rope_tab + (size_t)pos * 16 + (j0 & 15));
-      const float qs = (n < P.rope_C) ? P.q_scale : 1.0f;
-#pragma unroll
-      for (int k = 0; k < 8; k += 2) {
-        const float4 t = __ldg(tab + (k >> 1));   // (cos a, sin a, cos b, sin b)
-        const float a = f[k], b = f[k + 1];
-        f[k] = (a * t.x - b * t.y) * qs;
-        f[k + 1] = (a * t.w + b * t.z) * qs;
-      }
-    }
-  }
-}
+int mtgemm2_dispatch(int epi, int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                     const CUtensorMap& o, const CUtensorMap& r, const MtParams& P, cudaStream_t stream);
 
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -567,6 +437,13 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
     epi = kEpiBiasRes;
   } else {
     epi = d->act == TVAE_ACT_GELU ? kEpiBiasGelu : (d->act == TVAE_ACT_SILU ? kEpiBiasSilu : kEpiBias);
+  }
+  // CTA-pair kernel (cta_group::2, weight tile split across the pair) whenever the tile is wide enough to matter
+  static const bool use_pair = !(getenv("TVAE_2CTA") && atoi(getenv("TVAE_2CTA")) == 0);
+  if (use_pair && block_n >= 128 && P.tiles_w * P.tiles_h * P.tiles_b >= 2) {
+    CUtensorMap mBh;
+    if ((rc = make_tmap_2d(&mBh, d->w, d->n_total, d->k_total, d->k_total, block_n / 2))) return rc;
+    return mtgemm2_dispatch(epi, block_n, mA0, mA1, mBh, mO, mR, P, stream);
   }
   switch (epi) {
     case kEpiBias: return launch_n<kEpiBias>(block_n, mA0, mA1, mB, mO, mR, P, stream);

@@ -1,0 +1,400 @@
+// CTA-pair (cta_group::2) variant of the fused multi-tap implicit GEMM.
+//
+// Two CTAs of a 2-CTA cluster (one TPC) work on one 256 x BLOCK_N output tile: CTA r owns rows [128 r, 128 r + 128)
+// (its own pixel tile, its own TMEM accumulator, its own epilogue / residual / store), but the weight tile B is
+// SPLIT between them -- each CTA TMA-loads only BLOCK_N / 2 rows of it and the leader's
+// tcgen05.mma.cta_group::2 (M = 256) reads both halves across the pair.  Per 64-wide K block a CTA therefore pulls
+// 16 KiB (A) + BLOCK_N * 64 B (half of B) from L2 instead of 16 KiB + BLOCK_N * 128 B.  ncu on the 1-CTA kernel
+// showed every large GEMM pinned at ~15 TB/s of L2->SM traffic (0.023-0.026 B/MAC) and, for N = 192, at the 128 B/clk
+// shared-memory read port; halving B relieves both.
+//
+// Protocol (per pipeline stage):
+//   both producers: wait own empty[s]; TMA A + B-half into OWN smem with .cta_group::2, completing on the LEADER's
+//                   full[s]; the leader alone arms full[s] with the byte count of both CTAs;
+//   leader MMA    : wait full[s]; 4 x tcgen05.mma.cta_group::2; tcgen05.commit ... multicast -> empty[s] of BOTH CTAs;
+//                   after the last K block: commit multicast -> tmem_full[acc] of both CTAs;
+//   epilogues     : each CTA drains its own accumulator half; all 16 epilogue warps arrive (remotely for the peer) on
+//                   the leader's tmem_empty[acc].
+// A pair whose second pixel tile lies beyond the tensor (odd tile count) runs it as a phantom: its loads are zero-filled
+// by TMA, its stores clipped.
+#include "mtgemm_common.cuh"
+
+namespace tvae {
+
+template <int BLOCK_N>
+struct Mt2Cfg {
+  static constexpr int kBHalfBytes = (BLOCK_N / 2) * kBlockK * 2;
+  static constexpr int kOutBytes = kBlockM * BLOCK_N * 2;
+  static constexpr int kStagesRaw = (227 * 1024 - 2048 - kOutBytes) / (kABytes + kBHalfBytes);
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
+  static constexpr int kSmemBytes = kStages * (kABytes + kBHalfBytes) + kOutBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+__device__ __forceinline__ void tma2_load_5d(void* smem, const CUtensorMap* m, uint64_t* leader_bar, int c0, int c1, int c2,
+                                             int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6, %7}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* smem, const CUtensorMap* m, uint64_t* leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {   // arrive on `bar` in BOTH CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+template <int BLOCK_N, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+               const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ MtParams P) {
+#ifdef TVAE_DEVICE_OK
+  using Cfg = Mt2Cfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr bool kHasRes = (EPI == kEpiBiasRes || EPI == kEpiRsBias);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + STAGES * kABytes;
+  uint8_t* sOut = sB + STAGES * Cfg::kBHalfBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + Cfg::kOutBytes);
+  uint64_t* full = bars;                   // [STAGES] (leader's are used)
+  uint64_t* empty = bars + STAGES;         // [STAGES] (each CTA's own)
+  uint64_t* tmem_full = bars + 2 * STAGES; // [2]      (each CTA's own)
+  uint64_t* tmem_empty = tmem_full + 2;    // [2]      (leader's are used, 16 arrivals)
+  uint64_t* res_full = tmem_empty + 2;     // [1]
+  uint64_t* out_free = res_full + 1;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_free + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const bool has_res = kHasRes && P.has_residual;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    tma_prefetch_desc(&tmRes);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 16);
+    }
+    mbar_init(res_full, 1);
+    mbar_init(out_free, 1);
+    fence_mbar_init();
+  }
+  cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / cross-CTA TMA completion
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(static_cast<uint32_t>(Cfg::kTmemCols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
+  const int m_pairs = (m_tiles + 1) >> 1;
+  const int total_pairs = P.num_phases * m_pairs * P.n_tiles;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  // pair tile -> (n tile, this CTA's pixel tile, phase); the pixel tile may be a phantom beyond the tensor
+#define TVAE_DECODE_PAIR(pt)                                              \
+  const int n_t = (pt) % P.n_tiles;                                       \
+  const int t2 = (pt) / P.n_tiles;                                        \
+  const int m_t = 2 * (t2 % m_pairs) + (int)rank;                         \
+  const int ph = t2 / m_pairs;                                            \
+  const int w0 = (m_t % P.tiles_w) * P.tw;                                \
+  const int h0 = ((m_t / P.tiles_w) % P.tiles_h) * P.th;                  \
+  const int b0 = (m_t / (P.tiles_w * P.tiles_h)) * P.nb;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+        TVAE_DECODE_PAIR(pt)
+        const int nt = P.ntaps[ph];
+        for (int t = 0; t < nt; ++t) {
+          const MtTap tap = P.taps[ph][t];
+          const CUtensorMap* mapA = tap.map ? &tmA1 : &tmA0;
+          for (int kb = 0; kb < tap.kblocks; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (kABytes + Cfg::kBHalfBytes));
+            tma2_load_5d(sA + stage * kABytes, mapA, &full[stage], tap.c_off + kb * kBlockK, w0 + tap.dw, tap.p,
+                         h0 + tap.dh, b0);
+            tma2_load_2d(sB + stage * Cfg::kBHalfBytes, &tmB, &full[stage], tap.wk_off + kb * kBlockK,
+                         n_t * BLOCK_N + (int)rank * (BLOCK_N / 2));
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++it) {
+        const int ph = (pt / P.n_tiles) / m_pairs;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        int kblocks = 0;
+        for (int t = 0; t < P.ntaps[ph]; ++t) kblocks += P.taps[ph][t].kblocks;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + stage * kABytes);
+          const uint32_t b_base = smem_u32(sB + stage * Cfg::kBHalfBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            umma2_f16(d_tmem, umma_desc_kmajor_sw128(a_base + k * 32), umma_desc_kmajor_sw128(b_base + k * 32), idesc,
+                      (kb | k) != 0);
+          }
+          umma2_commit_mc(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma2_commit_mc(&tmem_full[acc]);
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ residual loader (each CTA, own tile)
+    if (lane == 0 && has_res) {
+      int it = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++it) {
+        TVAE_DECODE_PAIR(pt)
+        mbar_wait(out_free, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(res_full, Cfg::kOutBytes);
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / 64; ++j)
+          tma_load_5d(sOut + j * kABytes, &tmRes, res_full, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph],
+                      h0, b0);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (each CTA, own 128 rows)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int half = (warp - 4) >> 2;
+    const bool store_leader = (threadIdx.x == 128);
+    int it = 0;
+    for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++it) {
+      TVAE_DECODE_PAIR(pt)
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+
+      EpiRow R;
+      {
+        const int wi = r % P.tw, hi = (r / P.tw) % P.th, bi = r / (P.tw * P.th);
+        R.pw = w0 + wi; R.phh = h0 + hi; R.pb = b0 + bi;
+        R.row_ok = (R.pw < P.vW) && (R.phh < P.vH) && (R.pb < P.vB);
+        const long long grow = ((long long)R.pb * P.vH + R.phh) * P.vW + R.pw;
+        R.rs = 1.0f; R.rsh = 0.0f; R.rope_r = 0; R.rope_c = 0;
+        if constexpr (EPI == kEpiRsBiasGelu || EPI == kEpiAffineRope || EPI == kEpiRsBias) {
+          if (P.row_scale != nullptr && R.row_ok) R.rs = __ldg(P.row_scale + grow);
+          if (P.row_shift != nullptr && R.row_ok) R.rsh = __ldg(P.row_shift + grow);
+        }
+        if constexpr (EPI == kEpiAffineRope) {
+          if (P.rope_tab != nullptr) {
+            const int tok = (int)(grow % ((long long)P.rope_H * P.rope_W));
+            R.rope_r = tok / P.rope_W;
+            R.rope_c = tok % P.rope_W;
+          }
+        }
+      }
+      const float* bias = P.bias ? P.bias + (size_t)ph * P.n_total : nullptr;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      if (has_res) mbar_wait(res_full, it & 1);
+
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+      const int n_base = n_t * BLOCK_N;
+#pragma unroll 1
+      for (int c16 = half; c16 < BLOCK_N / 16; c16 += 2) {
+        uint32_t va[8], vb[8];
+        tmem_ld8(t_row + c16 * 16, va);
+        tmem_ld8(t_row + c16 * 16 + 8, vb);
+        tmem_ld_wait();
+        float fa[8], fb[8];
+        epi_math8<EPI>(P, bias, R, n_base + c16 * 16, va, fa);
+        epi_math8<EPI>(P, bias, R, n_base + c16 * 16 + 8, vb, fb);
+        if constexpr (EPI == kEpiDirect) {
+          if (R.row_ok) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int n = n_base + c16 * 16 + k;
+              if (n < P.out_n) P.out_f32[(((long long)R.pb * P.out_n + n) * P.vH + R.phh) * P.vW + R.pw] = fa[k];
+              if (n + 8 < P.out_n) P.out_f32[(((long long)R.pb * P.out_n + n + 8) * P.vH + R.phh) * P.vW + R.pw] = fb[k];
+            }
+          }
+        } else {
+          uint8_t* chunk = sOut + (c16 >> 2) * kABytes + r * 128;
+          const int g0 = (c16 & 3) * 2;
+          uint4* pa = reinterpret_cast<uint4*>(chunk + (((g0) ^ (r & 7)) << 4));
+          uint4* pb = reinterpret_cast<uint4*>(chunk + (((g0 + 1) ^ (r & 7)) << 4));
+          if constexpr (kHasRes) {
+            if (has_res) {
+              const uint4 ra = *pa, rb = *pb;
+              float2 t;
+              t = unpack_bf16(ra.x); fa[0] += t.x; fa[1] += t.y;
+              t = unpack_bf16(ra.y); fa[2] += t.x; fa[3] += t.y;
+              t = unpack_bf16(ra.z); fa[4] += t.x; fa[5] += t.y;
+              t = unpack_bf16(ra.w); fa[6] += t.x; fa[7] += t.y;
+              t = unpack_bf16(rb.x); fb[0] += t.x; fb[1] += t.y;
+              t = unpack_bf16(rb.y); fb[2] += t.x; fb[3] += t.y;
+              t = unpack_bf16(rb.z); fb[4] += t.x; fb[5] += t.y;
+              t = unpack_bf16(rb.w); fb[6] += t.x; fb[7] += t.y;
+            }
+          }
+          uint4 o;
+          o.x = pack_bf16(fa[0], fa[1]); o.y = pack_bf16(fa[2], fa[3]);
+          o.z = pack_bf16(fa[4], fa[5]); o.w = pack_bf16(fa[6], fa[7]);
+          *pa = o;
+          o.x = pack_bf16(fb[0], fb[1]); o.y = pack_bf16(fb[2], fb[3]);
+          o.z = pack_bf16(fb[4], fb[5]); o.w = pack_bf16(fb[6], fb[7]);
+          *pb = o;
+        }
+      }
+      // accumulator half drained -> tell the leader's MMA warp (remote arrive from the peer CTA)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+
+      if constexpr (EPI != kEpiDirect) {
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (store_leader) {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_store_5d(&tmOut, sOut + j * kABytes, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph], h0, b0);
+          tma_store_commit();
+          tma_store_wait_read<0>();
+          if (has_res) mbar_arrive(out_free);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+    }
+    if (store_leader) tma_store_wait<0>();
+  }
+#undef TVAE_DECODE_PAIR
+
+  // the peer's smem / barriers / TMEM are touched by the leader's MMAs and multicast commits until the very end
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(Cfg::kTmemCols))
+                 : "memory");
+  }
+#endif
+}
+
+template <int BLOCK_N, int EPI>
+static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+                   const CUtensorMap& r, const MtParams& P, cudaStream_t stream) {
+  using Cfg = Mt2Cfg<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    TVAE_CHECK_CUDA(cudaFuncSetAttribute(mtgemm2_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
+  const int total_pairs = P.num_phases * ((m_tiles + 1) / 2) * P.n_tiles;
+  int clusters = num_sms() / 2;
+  if (clusters <= 0) clusters = 74;
+  if (total_pairs < clusters) clusters = total_pairs;
+  mtgemm2_kernel<BLOCK_N, EPI><<<2 * clusters, kThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b, o, r, P);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int EPI>
+static int launch2_n(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+                     const CUtensorMap& r, const MtParams& P, cudaStream_t stream) {
+  switch (block_n) {
+    case 256: return launch2<256, EPI>(a0, a1, b, o, r, P, stream);
+    case 192: return launch2<192, EPI>(a0, a1, b, o, r, P, stream);
+    default: return launch2<128, EPI>(a0, a1, b, o, r, P, stream);
+  }
+}
+
+// Called by mtgemm_run (mtgemm.cu) when the CTA-pair kernel applies (block_n >= 128).  `b` must be a weight map with
+// box rows = block_n / 2.
+int mtgemm2_dispatch(int epi, int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                     const CUtensorMap& o, const CUtensorMap& r, const MtParams& P, cudaStream_t stream) {
+  switch (epi) {
+    case kEpiBias: return launch2_n<kEpiBias>(block_n, a0, a1, b, o, r, P, stream);
+    case kEpiBiasRes: return launch2_n<kEpiBiasRes>(block_n, a0, a1, b, o, r, P, stream);
+    case kEpiBiasGelu: return launch2_n<kEpiBiasGelu>(block_n, a0, a1, b, o, r, P, stream);
+    case kEpiBiasSilu: return launch2_n<kEpiBiasSilu>(block_n, a0, a1, b, o, r, P, stream);
+    case kEpiRsBiasGelu: return launch2_n<kEpiRsBiasGelu>(block_n, a0, a1, b, o, r, P, stream);
+    case kEpiAffineRope: return launch2_n<kEpiAffineRope>(block_n, a0, a1, b, o, r, P, stream);
+    case kEpiDirect: return launch2_n<kEpiDirect>(block_n, a0, a1, b, o, r, P, stream);
+    default: return launch2_n<kEpiRsBias>(block_n, a0, a1, b, o, r, P, stream);
+  }
+}
+
+}  // namespace tvae
