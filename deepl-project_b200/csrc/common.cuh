@@ -284,9 +284,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
 // ---- math -----------------------------------------------------------------------------------
 // erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 resolution): 2 MUFU + ~10 FMA instead of the
 // ~40-instruction branchy erff -- the GELU epilogues were bound by it.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // one MUFU.RCP (__frcp_rn expands to a Newton-corrected sequence)
+  return r;
+}
 __device__ __forceinline__ float fast_erf(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
@@ -301,9 +306,9 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float pdf = 0.3989422804014327f * exp2f(-0.7213475204444817f * x * x);
   return fmaf(x, pdf, cdf);
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return x * rcp_approx(1.0f + __expf(-x)); }
 __device__ __forceinline__ float silu_grad(float x) {
-  float s = 1.0f / (1.0f + __expf(-x));
+  float s = rcp_approx(1.0f + __expf(-x));
   return s * (1.0f + x * (1.0f - s));
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
