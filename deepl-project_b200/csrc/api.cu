@@ -44,6 +44,8 @@ int latent_bwd_run(const float* mu, const float* logvar, const float* eps, const
 int sumsq_run(const float* g, long long n, float* out, cudaStream_t stream);
 int adamw_run(float* p, const float* g, float* m, float* v, long long n, const float* ctrl, float lr, float b1, float b2,
               float eps, float wd, int step, cudaStream_t stream);
+int metrics_run(const float* recon, const float* target, float* acc, int B, int C, int H, int W, int mode,
+                cudaStream_t stream);
 }  // namespace tvae
 
 using namespace tvae;
@@ -170,4 +172,8 @@ int tvae_adamw(float* p, const float* g, float* m, float* v, int64_t n, const fl
   GUARD(); return adamw_run(p, g, m, v, n, ctrl, lr, beta1, beta2, eps, weight_decay, step, S_(stream));
 }
 
+int tvae_metrics(const float* recon, const float* target, float* acc, int32_t B, int32_t C, int32_t H, int32_t W,
+                 int32_t mode, void* stream) {
+  GUARD(); return metrics_run(recon, target, acc, B, C, H, W, mode, S_(stream));
+}
 }  // extern "C"

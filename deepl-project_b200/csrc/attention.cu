@@ -15,6 +15,8 @@
 // The two softmax warpgroups ping-pong: while one exponentiates, the tensor pipe runs the other tile's S / PV
 // and the TMEM-load latency of one warp hides behind the other warp on the same scheduler.  (The first version -- one
 // Q tile, one softmax warpgroup -- reached 310-340 TFLOP/s at S=4096; profiles/r1_breakdown_*.txt.)
+#include <cstdlib>
+
 #include "../../include/transvae_sm100.h"
 #include "common.cuh"
 #include "tmap.cuh"
@@ -315,6 +317,353 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #endif
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// v6: S held in registers, O resident in TMEM with lazy rescaling, double-buffered P
+// -------------------------------------------------------------------------------------------------
+// Same CTA shape as above (two 128-row Q tiles, 8 softmax warps, one query row per thread), but per K/V block a
+// softmax thread
+//   * reads its 128 scores from TMEM ONCE into registers and frees the S buffer at once, so S_t(j+1) = Q_t K_{j+1}^T
+//     is on the tensor pipe while block j is still being exponentiated (single S buffer per tile, 128 columns);
+//   * keeps O_t in TMEM (64 columns per tile): P_t(j) V_j accumulates there directly (tcgen05.mma accumulate flag),
+//     and O is only touched by the softmax warps when the running row maximum grew by more than 2^8 since the
+//     reference maximum was last fixed ("lazy rescale": P = exp2(S - m_ref) stays <= 256, exact after the final
+//     division by l, which is accumulated against the same m_ref);
+//   * writes P into one of two smem buffers per tile, so block j never waits for the P V product of block j-1
+//     (ncu on the single-buffer version: 24 % of the softmax warps' samples sat on that wait);
+//   * uses packed f32x2 adds (FADD2) for the subtraction of the maximum and the row sum, FMNMX3 for the maximum.
+// K and V travel through separate 2-stage rings: K_j is released after S(j) has been issued, V_j after P(j) V_j.
+// Per block and thread this is ~440 issue slots instead of ~670, of which 128 are MUFU.EX2 -- the unit that bounds
+// head_dim-64 attention (16 exp2 / clk / SM against 8192 MMA flop / clk / SM).
+constexpr int kLazyLog2 = 8;
+constexpr int kKvStages6 = 2;
+
+// Optional phase trace (build with -DTVAE_ATT_TRACE, read with tvae_debug_att_trace): SM-clock stamps of CTA (0,0,0),
+// lane 0 of the first warp of each softmax warpgroup, six stamps per K/V block.
+#ifdef TVAE_ATT_TRACE
+__device__ long long g_att_trace[2 * 64 * 8];
+#define ATT_STAMP(slot)                                                                                     \
+  if (trace_on && j < 64) g_att_trace[(t * 64 + j) * 8 + (slot)] = clock64();
+#else
+#define ATT_STAMP(slot)
+#endif
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// 2^x for two lanes on the FMA pipe (no MUFU): round-to-nearest split x = n + r with the 1.5*2^23 trick, degree-3
+// minimax polynomial for 2^r on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P), exponent
+// added into the float bits.  x is clamped at -126 so the exponent arithmetic cannot wrap (-inf -> 1.2e-38).
+__device__ __forceinline__ float2 exp2_fma2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 xf = __fadd2_rn(x, make_float2(12582912.0f, 12582912.0f));
+  const float2 n = __fadd2_rn(xf, make_float2(-12582912.0f, -12582912.0f));
+  const float2 r = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
+  float2 p = __ffma2_rn(make_float2(0.0551716685f, 0.0551716685f), r, make_float2(0.242611125f, 0.242611125f));
+  p = __ffma2_rn(p, r, make_float2(0.693260968f, 0.693260968f));
+  p = __ffma2_rn(p, r, make_float2(0.999928057f, 0.999928057f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(xf.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(xf.y) << 23));
+  return p;
+}
+
+// POLY: every POLY-th pair of scores is exponentiated on the FMA pipe instead of MUFU (0 = never).
+template <int POLY>
+__global__ void __launch_bounds__(kAttThreads, 1)
+attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
+                 float* __restrict__ lse, int S, int C, int nh) {
+#ifdef TVAE_DEVICE_OK
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                // [2 tiles]
+  uint8_t* sK = sQ + 2 * kTileBytes;                 // [2 stages]
+  uint8_t* sV = sK + kKvStages6 * kTileBytes;        // [2 stages]
+  uint8_t* sP = sV + kKvStages6 * kTileBytes;        // [2 tiles][2 buffers] x 2 chunks (keys 0-63, 64-127)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 8 * kTileBytes);
+  uint64_t* q_full = bars;                           // 1
+  uint64_t* k_full = bars + 1;                       // [2]
+  uint64_t* k_empty = k_full + 2;                    // [2]
+  uint64_t* v_full = k_empty + 2;                    // [2]
+  uint64_t* v_empty = v_full + 2;                    // [2]
+  uint64_t* s_full = v_empty + 2;                    // [2 tiles]
+  uint64_t* s_free = s_full + 2;                     // [2 tiles]
+  uint64_t* p_full = s_free + 2;                     // [2 tiles][2 buffers]
+  uint64_t* o_full = p_full + 4;                     // [2 tiles][2 buffers]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nblk = (S + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmO);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKvStages6; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 2);     // one tcgen05.commit per Q tile's MMA thread
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 2);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_free[t], 4);
+      for (int u = 0; u < 2; ++u) {
+        mbar_init(&p_full[t * 2 + u], 4);
+        mbar_init(&o_full[t * 2 + u], 1);
+      }
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: tile t: S_t at t*256 (128 columns), O_t at t*256 + 128 (64 columns)
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");     // control warpgroup: TMA / MMA issue only
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+        att_tma_load_3d(sQ, &tmQKV, q_full, h * 64, q0, b);
+        att_tma_load_3d(sQ + kTileBytes, &tmQKV, q_full, h * 64, q0 + 128, b);
+        for (int j = 0; j < nblk; ++j) {
+          const int stage = j & 1;
+          const uint32_t ph = (j >> 1) & 1;
+          mbar_wait(&k_empty[stage], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[stage], kTileBytes);
+          att_tma_load_3d(sK + stage * kTileBytes, &tmQKV, &k_full[stage], C + h * 64, j * 128, b);
+          mbar_wait(&v_empty[stage], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[stage], kTileBytes);
+          att_tma_load_3d(sV + stage * kTileBytes, &tmQKV, &v_full[stage], 2 * C + h * 64, j * 128, b);
+        }
+      }
+    } else if (warp == 1 || warp == 2) {
+      // one MMA-issuing thread per Q tile, so a slow tile never holds back the other tile's S / P V products
+      if (lane == 0) {
+        const int t = warp - 1;
+        constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
+        const uint32_t q_base = smem_u32(sQ + t * kTileBytes);
+        auto issue_qk = [&](int j) {
+          const uint32_t k_base = smem_u32(sK + (j & 1) * kTileBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + t * 256, umma_desc_kmajor_sw128(q_base + k * 32),
+                     umma_desc_kmajor_sw128(k_base + k * 32), idesc_qk, k != 0);
+          umma_commit(&s_full[t]);
+          umma_commit(&k_empty[j & 1]);                // second arrival (other tile) releases the K stage
+        };
+        auto issue_pv = [&](int j) {
+          const uint32_t p_base = smem_u32(sP + (t * 2 + (j & 1)) * 2 * kTileBytes);
+          const uint32_t v_base = smem_u32(sV + (j & 1) * kTileBytes);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_f16(tmem_base + t * 256 + 128, umma_desc_kmajor_sw128(p_base + (k >> 2) * kTileBytes + (k & 3) * 32),
+                     umma_desc_mnmajor_sw128(v_base + k * 2048, 1024, 1024), idesc_pv, (j | k) != 0);
+          umma_commit(&o_full[t * 2 + (j & 1)]);
+          umma_commit(&v_empty[j & 1]);
+        };
+        mbar_wait(q_full, 0);
+        mbar_wait(&k_full[0], 0);
+        tc_fence_after();
+        issue_qk(0);
+        for (int j = 0; j < nblk; ++j) {
+          if (j + 1 < nblk) {
+            mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+            mbar_wait(&s_free[t], j & 1);            // the softmax warps hold S_t(j) in registers
+            tc_fence_after();
+            issue_qk(j + 1);
+          }
+          mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+          mbar_wait(&p_full[t * 2 + (j & 1)], (j >> 1) & 1);
+          tc_fence_after();
+          issue_pv(j);
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");    // softmax warpgroups hold 128 scores per thread
+    const int t = (warp - 4) >> 2;       // Q tile of this warpgroup
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_off + t * 256;
+    const uint32_t t_o = t_s + 128;
+    uint8_t* sPt = sP + t * 4 * kTileBytes;          // this tile's two P buffers
+    const uint32_t sPt_row = smem_u32(sPt) + r * 128;
+    float m_ref = -INFINITY, l_run = 0.0f;
+#ifdef TVAE_ATT_TRACE
+    const bool trace_on = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && qd == 0 && lane == 0;
+#endif
+    if (t == 1) asm volatile("bar.arrive 3, 256;" ::: "memory");   // tile 0 exponentiates first
+
+    for (int j = 0; j < nblk; ++j) {
+      ATT_STAMP(0)
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      ATT_STAMP(1)
+      uint32_t v[128];
+      {
+        uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+        uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+        uint32_t(&v2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[64]);
+        uint32_t(&v3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[96]);
+        tmem_ld32(t_s, v0);
+        tmem_ld32(t_s + 32, v1);
+        tmem_ld32(t_s + 64, v2);
+        tmem_ld32(t_s + 96, v3);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[t]);      // S buffer may receive S_t(j+1)
+      ATT_STAMP(2)
+
+      const int key0 = j * 128;
+      if (key0 + 128 > S) {                         // only the last block can reach past the sequence end
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (key0 + i >= S) v[i] = 0xff800000u;    // -inf
+      }
+      float mx[8];                                  // eight independent FMNMX3 chains (a two-chain version spent
+#pragma unroll                                      // ~400 clocks per block on dependent-issue latency)
+      for (int c = 0; c < 8; ++c) mx[c] = fmaxf(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+#pragma unroll
+      for (int i = 16; i < 128; i += 16) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          mx[c] = fmaxf(mx[c], fmaxf(__uint_as_float(v[i + 2 * c]), __uint_as_float(v[i + 2 * c + 1])));
+      }
+      const float m_blk = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+      if (j == 0) {
+        m_ref = m_blk;
+      } else {
+        const bool grow = m_blk > m_ref + static_cast<float>(kLazyLog2);
+        if (__any_sync(0xffffffffu, grow)) {
+          // rare: bring O_t and l to the new reference maximum (the previous P V must have landed first)
+          mbar_wait(&o_full[t * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+          tc_fence_after();
+          const float m_new = grow ? m_blk : m_ref;
+          const float sc = exp2f(m_ref - m_new);
+          l_run *= sc;
+          m_ref = m_new;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(t_o + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+            tmem_st32(t_o + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // P buffer (j & 1) was last read by the P V product of block j-2
+      ATT_STAMP(3)
+      if (j >= 2) mbar_wait(&o_full[t * 2 + (j & 1)], ((j - 2) >> 1) & 1);
+      ATT_STAMP(4)
+      // MUFU token: the exp2 phases of the two warpgroups strictly alternate, so one tile exponentiates (MUFU-bound)
+      // while the other loads / reduces / synchronises.  Without it the tiles ran in lockstep (trace: 1300 clocks
+      // with the MUFU idle, then 2400 clocks with both tiles fighting for it).
+      if (t == 0) asm volatile("bar.sync 3, 256;" ::: "memory");
+      else asm volatile("bar.sync 4, 256;" ::: "memory");
+      const uint32_t prow = sPt_row + (j & 1) * 2 * kTileBytes;
+      const float2 nm2 = make_float2(-m_ref, -m_ref);
+      float2 la = make_float2(0.0f, 0.0f), lb = make_float2(0.0f, 0.0f);
+      // Software-pipelined by hand: pair i is exponentiated kExpAhead pairs before it is summed / packed / stored, so
+      // the in-order warp never sits on the MUFU result latency (the straightforward loop left the consumer 2 MUFUs
+      // behind its producer and the exp phase took 1600 clocks instead of the 1024 the MUFU needs).
+      constexpr int kExpAhead = 6;
+#pragma unroll
+      for (int i = 0; i < 64 + kExpAhead; ++i) {
+        if (i < 64) {
+          float2 x = __fadd2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), nm2);
+          if (POLY > 0 && POLY < 100 && (i % (POLY > 0 ? POLY : 1)) == POLY - 1) {
+            x = exp2_fma2(x);
+          } else if (POLY == 102) {                  // trace experiment: no MUFU at all
+            x = __ffma2_rn(x, make_float2(1e-3f, 1e-3f), make_float2(1.0f, 1.0f));
+          } else {
+            x.x = exp2f(x.x);
+            x.y = exp2f(x.y);
+          }
+          v[2 * i] = __float_as_uint(x.x);
+          v[2 * i + 1] = __float_as_uint(x.y);
+        }
+        const int d = i - kExpAhead;
+        if (d >= 0) {
+          const float2 e = make_float2(__uint_as_float(v[2 * d]), __uint_as_float(v[2 * d + 1]));
+          if (d & 1) lb = __fadd2_rn(lb, e);
+          else la = __fadd2_rn(la, e);
+          v[d] = pack_bf16(e.x, e.y);              // packed P reuses the low registers of the score array
+          if ((d & 3) == 3 && POLY != 101) {         // (101: trace experiment without the P stores)
+            const int c = d >> 4, g = (d >> 2) & 3;   // 32-column chunk, 8-column group
+            const uint32_t row = prow + (c >> 1) * kTileBytes;
+            st_shared_v4(row + ((((c & 1) * 4 + g) ^ (r & 7)) << 4), v[d - 3], v[d - 2], v[d - 1], v[d]);
+          }
+        }
+      }
+      if (t == 0) asm volatile("bar.arrive 4, 256;" ::: "memory");
+      else if (j + 1 < nblk) asm volatile("bar.arrive 3, 256;" ::: "memory");
+      l_run += (la.x + la.y) + (lb.x + lb.y);
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t * 2 + (j & 1)]);
+      ATT_STAMP(5)
+    }
+    // O_t is complete once the last P V has landed (MMAs complete in order)
+    mbar_wait(&o_full[t * 2 + ((nblk - 1) & 1)], ((nblk - 1) >> 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const uint32_t orow = sPt_row;                   // stage O (bf16) in P buffer 0 of this tile (all P V products done)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(t_o + c * 32, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        st_shared_v4(orow + (((c * 4 + g) ^ (r & 7)) << 4),
+                     pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l),
+                     pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l),
+                     pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l),
+                     pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l));
+      }
+    }
+    const int qrow = q0 + t * 128 + r;
+    if (lse != nullptr && qrow < S) lse[((size_t)b * nh + h) * S + qrow] = m_ref + log2f(l_run);
+    fence_proxy_async_smem();
+    if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (qd == 0 && lane == 0 && q0 + t * 128 < S) {
+      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                       reinterpret_cast<uint64_t>(&tmO)),
+                   "r"(smem_u32(sPt)), "r"(h * 64), "r"(q0 + t * 128), "r"(b)
+                   : "memory");
+      tma_store_commit();
+      tma_store_wait<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+#endif
+}
+
 int attn_fwd_run(const void* qkv, void* out, float* lse, int B, int S, int C, cudaStream_t stream) {
   TVAE_REQUIRE(C % 64 == 0, "attention: C=%d must be a multiple of head_dim 64", C);
   const int nh = C / 64;
@@ -328,9 +677,39 @@ int attn_fwd_run(const void* qkv, void* out, float* lse, int B, int S, int C, cu
     configured = true;
   }
   dim3 grid((S + 255) / 256, nh, B);
+  static const int version = getenv("TVAE_ATTN") ? atoi(getenv("TVAE_ATTN")) : 6;
+  if (version == 6) {
+    static const int poly = getenv("TVAE_ATTN_POLY") ? atoi(getenv("TVAE_ATTN_POLY")) : 4;
+    static bool configured6 = false;
+    if (!configured6) {
+      TVAE_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd6_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
+      TVAE_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd6_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
+      TVAE_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd6_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
+      configured6 = true;
+    }
+#ifdef TVAE_ATT_TRACE
+    if (poly == 101 || poly == 102) {
+      auto kern = poly == 101 ? attn_fwd6_kernel<101> : attn_fwd6_kernel<102>;
+      TVAE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
+      kern<<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh);
+      return 0;
+    }
+#endif
+    if (poly == 3) attn_fwd6_kernel<3><<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh);
+    else if (poly == 4) attn_fwd6_kernel<4><<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh);
+    else attn_fwd6_kernel<0><<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   attn_fwd_kernel<<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+#ifdef TVAE_ATT_TRACE
+extern "C" int tvae_debug_att_trace(long long* dst) {
+  return cudaMemcpyFromSymbol(dst, g_att_trace, sizeof(g_att_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 }  // namespace tvae

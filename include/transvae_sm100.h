@@ -127,6 +127,14 @@ int tvae_reparam(const float* mu, const float* logvar, const float* eps, float* 
 int tvae_loss_l1_kl(const float* recon, const float* target, const float* mu, const float* logvar, float* acc,
                     int64_t n_img, int64_t n_lat, int32_t patched, float clip_lo, float clip_hi, void* stream);
 
+/* Reconstruction metrics on the device (evaluate_transvae.py:47-77 calculate_psnr / calculate_ssim and the per-image
+ * loops at :131-146; test_rope_extrapolation.py:28-51).  recon / target: fp32 NCHW [B, C, H, W]; the reconstruction
+ * is first mapped through `mode` (0 identity, 1 clamp(0,1) as evaluate.py:108-110, 2 sigmoid as
+ * evaluate_transvae.py:131).  acc fp32 [B, 4], zeroed inside: per image {sum squared error, sum absolute error,
+ * sum of the 11x11 box-filter SSIM map (zero padded, C1 = 0.01^2, C2 = 0.03^2), 0}. */
+int tvae_metrics(const float* recon, const float* target, float* acc, int32_t B, int32_t C, int32_t H, int32_t W,
+                 int32_t mode, void* stream);
+
 /* ---- backward pass ------------------------------------------------------------------------------
  * Weight gradient of tvae_mtgemm: dw[n, wk_off + k] += sum_pixels dZ[pixel, n] * A_tap[pixel, k] for every tap of
  * `desc` (same a0 / a1 / taps / n_total / k_total as the forward call; desc->out is the dZ view, i.e. the gradient

@@ -153,6 +153,33 @@ def test_attention_fwd(B, S, C):
     assert float((lse - ref_lse).abs().max()) < 2e-2
 
 
+@pytest.mark.parametrize("order", ["rising", "falling", "flat"])
+def test_attention_fwd_running_max(order):
+    """Scores that rise / fall steadily along the key axis: the rising case forces the lazy O rescale of the forward
+    kernel at (almost) every key block, the falling case never does, the flat case has all-equal scores."""
+    B, S, C = 1, 1024, 64
+    g = torch.Generator(device="cpu").manual_seed(5)
+    q = torch.randn(B, S, 64, generator=g) * 0.2
+    k = torch.randn(B, S, 64, generator=g) * 0.2
+    v = torch.randn(B, S, 64, generator=g)
+    ramp = torch.linspace(0.0, 40.0, S)
+    if order == "falling":
+        ramp = ramp.flip(0)
+    if order == "flat":
+        q.zero_()
+    else:
+        q[..., 0] = 1.0
+        k[..., 0] = ramp                    # score(i, j) ~ ramp[j] + noise (log2 units)
+    qkv = bf(torch.cat([q, k, v], dim=-1).to(DEV))
+    out, lse = ops.attn_fwd(qkv, B, S, C, need_lse=True)
+    t = qkv.float().view(B, S, 3, 1, 64).permute(2, 0, 3, 1, 4)
+    sc = (t[0] @ t[1].transpose(-1, -2)) * math.log(2.0)
+    ref = (torch.softmax(sc, dim=-1) @ t[2]).permute(0, 2, 1, 3).reshape(B, S, C)
+    assert rel(out, ref) < 2e-2, rel(out, ref)
+    ref_lse = torch.logsumexp(sc, dim=-1) / math.log(2.0)
+    assert float((lse - ref_lse).abs().max()) < 2e-2
+
+
 def test_conv_in():
     x, w, b = rnd(2, 3, 32, 48), rnd(64, 3, 3, 3, seed=1, scale=0.3), rnd(64, seed=2)
     y = ops.conv_in(x, w, b)
