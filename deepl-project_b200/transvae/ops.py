@@ -435,3 +435,19 @@ def adamw(p: Tensor, g: Tensor, m: Tensor, v: Tensor, ctrl: Tensor, lr: float, b
     _lib.check(_lib.load().tvae_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), ctrl.data_ptr(),
                                       lr, betas[0], betas[1], eps, weight_decay, step, _stream()), "tvae_adamw")
     _count()
+
+
+METRIC_MODES = {None: 0, "none": 0, "identity": 0, "clamp": 1, "sigmoid": 2}
+
+
+def metrics_sums(recon: Tensor, target: Tensor, mode: str = "clamp") -> Tensor:
+    """fp32 [B, 4] = per image (sum squared error, sum |error|, sum of the 11x11 SSIM map, 0) of f(recon) vs target."""
+    _need_cuda(recon, target)
+    recon, target = recon.float().contiguous(), target.float().contiguous()
+    assert recon.shape == target.shape and recon.dim() == 4
+    B, C_, H, W = recon.shape
+    acc = torch.empty(B, 4, dtype=torch.float32, device=recon.device)
+    _lib.check(_lib.load().tvae_metrics(recon.data_ptr(), target.data_ptr(), acc.data_ptr(), B, C_, H, W,
+                                        METRIC_MODES[mode], _stream()), "tvae_metrics")
+    _count()
+    return acc

@@ -121,13 +121,55 @@ class FusedAdamW:
                   self.eps, self.wd, self.step_count)
         return self.ctrl
 
+    # ---- checkpoint interchange --------------------------------------------------------------------------------
+    # The reference saves ``torch.optim.AdamW.state_dict()`` (train.py:753-769, train_2.py:245-260).  The same schema
+    # is produced / accepted here -- state[i] = {step, exp_avg, exp_avg_sq} with i the index of the parameter in
+    # ``model.parameters()`` order (trainable ones only), one param group -- so a run can move between the reference's
+    # trainer and this one in either direction.
     def state_dict(self) -> dict:
-        return {"m": self.m, "v": self.v, "step": self.step_count, "lr": self.lr}
+        state = {}
+        for i, p in enumerate(self.b.params):
+            o, n = self.b._slices[p]
+            state[i] = {"step": torch.tensor(float(self.step_count)),
+                        "exp_avg": self.m[o:o + n].view(p.shape).clone(),
+                        "exp_avg_sq": self.v[o:o + n].view(p.shape).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": list(range(len(self.b.params)))}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd: dict) -> None:
-        self.m.copy_(sd["m"])
-        self.v.copy_(sd["v"])
-        self.step_count = int(sd["step"])
+        if "state" not in sd:                       # flat layout written by early versions of this trainer
+            self.m.copy_(sd["m"])
+            self.v.copy_(sd["v"])
+            self.step_count = int(sd["step"])
+            return
+        groups = sd["param_groups"]
+        ids = [i for g in groups for i in g["params"]]
+        if len(ids) != len(self.b.params):
+            raise ValueError(f"optimizer state has {len(ids)} parameters, the model has {len(self.b.params)} trainable ones")
+        steps = set()
+        with torch.no_grad():
+            for pid, p in zip(ids, self.b.params):
+                st = sd["state"].get(pid)
+                o, n = self.b._slices[p]
+                if st is None:                      # parameter never updated: moments stay zero
+                    self.m[o:o + n].zero_()
+                    self.v[o:o + n].zero_()
+                    continue
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"optimizer state {pid}: shape {tuple(st['exp_avg'].shape)} != {tuple(p.shape)}")
+                self.m[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                self.v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"per-parameter step counts differ ({sorted(steps)}); the fused optimiser keeps one")
+        self.step_count = steps.pop() if steps else 0
+        g0 = groups[0]
+        self.lr = float(g0.get("initial_lr", g0.get("lr", self.lr)))      # LambdaLR keeps the base rate in initial_lr
+        self.betas = tuple(g0.get("betas", self.betas))
+        self.eps = float(g0.get("eps", self.eps))
+        self.wd = float(g0.get("weight_decay", self.wd))
 
 
 class Trainer:
@@ -146,8 +188,9 @@ class Trainer:
         self.world = self.buckets.world
 
     def _lr(self) -> float:
-        if self.warmup_steps > 0:      # linear warm-up (train_2.py:266-274)
-            return self.opt.lr * min(1.0, (self.opt.step_count + 1) / self.warmup_steps)
+        # linear warm-up then constant (train_2.py:266-274: LambdaLR with step / warmup, so update k uses k / warmup)
+        if self.warmup_steps > 0:
+            return self.opt.lr * min(1.0, self.opt.step_count / self.warmup_steps)
         return self.opt.lr
 
     def train_step(self, images: Tensor, eps: Optional[Tensor] = None) -> dict:
@@ -165,11 +208,25 @@ class Trainer:
             self.buckets.zero_grad()
         return {k: v.detach() for k, v in losses.items()}
 
-    # checkpoint schema of the reference (train.py:753-769): model_state_dict / optimizer_state_dict / global_step
-    def state_dict(self) -> dict:
-        return {"model_state_dict": self.model.state_dict(), "optimizer_state_dict": self.opt.state_dict(),
-                "global_step": self.opt.step_count}
+    # checkpoint schema of the reference (train.py:753-769, train_2.py:245-260)
+    def state_dict(self, epoch: int = 0, args: Optional[dict] = None) -> dict:
+        return {"epoch": epoch, "global_step": self.opt.step_count, "model_state_dict": self.model.state_dict(),
+                "optimizer_state_dict": self.opt.state_dict(),
+                "scheduler_state_dict": {"last_epoch": self.opt.step_count, "warmup_steps": self.warmup_steps},
+                "args": dict(args or {})}
 
     def load_state_dict(self, sd: dict) -> None:
+        """Accepts checkpoints written by this trainer or by the reference's train.py / train_2.py."""
         self.model.load_state_dict(sd["model_state_dict"])
+        # load_state_dict copies into the existing (flat-buffer backed) parameter storage, so the views stay valid
         self.opt.load_state_dict(sd["optimizer_state_dict"])
+        if "global_step" in sd and not sd["optimizer_state_dict"].get("state"):
+            self.opt.step_count = int(sd["global_step"])
+
+    def save(self, path: str, epoch: int = 0, args: Optional[dict] = None) -> None:
+        torch.save(self.state_dict(epoch, args), path)
+
+    def load(self, path: str) -> dict:
+        sd = torch.load(path, map_location=self.buckets.flat_p.device, weights_only=False)
+        self.load_state_dict(sd)
+        return sd

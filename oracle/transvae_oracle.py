@@ -439,6 +439,23 @@ def psnr(a: Tensor, b: Tensor, max_val: float = 1.0) -> float:
     return float(20 * torch.log10(torch.tensor(max_val) / torch.sqrt(mse)))
 
 
+def ssim(img1: Tensor, img2: Tensor, window_size: int = 11, size_average: bool = True):
+    """patched/evaluate_transvae.py:56-77: box-filter SSIM (avg_pool2d, zero padding counted in the mean)."""
+    img1, img2 = img1.float(), img2.float()
+    pad = window_size // 2
+    pool = lambda t: F.avg_pool2d(t, window_size, stride=1, padding=pad)
+    mu1, mu2 = pool(img1), pool(img2)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    sigma1_sq = pool(img1 * img1) - mu1_sq
+    sigma2_sq = pool(img2 * img2) - mu2_sq
+    sigma12 = pool(img1 * img2) - mu1_mu2
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    ssim_map = ((2 * mu1_mu2 + c1) * (2 * sigma12 + c2)) / ((mu1_sq + mu2_sq + c1) * (sigma1_sq + sigma2_sq + c2))
+    if size_average:
+        return float(ssim_map.mean())
+    return ssim_map.mean(1).mean(1).mean(1)
+
+
 def max_rel_err(ours: Tensor, ref: Tensor) -> float:
     """Parity metric of SURVEY 8c: max|ours-ref| / max|ref|."""
     ref = ref.float()
