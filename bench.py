@@ -107,6 +107,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def hbm_table(prof_hbm, steps, pk):
+    """Per-kernel HBM roofline of the bandwidth-bound launches: algorithmic bytes / CUDA-event time vs the measured
+    copy bandwidth (MEASURED_PEAKS.json hbm_gbs)."""
+    agg = {}
+    for name, nbytes, a, b in prof_hbm or []:
+        d = agg.setdefault(name, [0.0, 0.0, 0])
+        d[0] += nbytes
+        d[1] += a.elapsed_time(b)
+        d[2] += 1
+    out = []
+    for name, (nbytes, ms, n) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        out.append({"kernel": name, "launches_per_step": n / steps, "ms_per_step": ms / steps, "achieved_gbs": gbs,
+                    "frac_of_hbm_peak": gbs / pk["hbm"]})
+    return out
+
+
 def dist_setup(n):
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -204,7 +221,7 @@ def run_ours(args, rank, world, local):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if profile:
-            ops.PROFILE = []
+            ops.PROFILE, ops.PROFILE_HBM = [], []
         n0 = ops.LAUNCHES
         e0.record()
         for _ in range(steps):
@@ -213,6 +230,9 @@ def run_ours(args, rank, world, local):
         barrier()
         ms = e0.elapsed_time(e1)
         prof, ops.PROFILE = ops.PROFILE, None
+        hbm, ops.PROFILE_HBM = ops.PROFILE_HBM, None
+        if profile:
+            prof = (prof, hbm)
         t = torch.tensor([ms], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -229,7 +249,7 @@ def run_ours(args, rank, world, local):
 
     # roofline of the dominant kernel from per-launch CUDA events (separate instrumented steps so the event records do
     # not perturb `value`; same stream, same inputs, directly after the timed region)
-    _, _, prof = timed(step_resident, 2, profile=True)
+    _, _, (prof, prof_hbm) = timed(step_resident, 2, profile=True)
     pk = peaks()
     by = {}
     for name, fl, a, b in prof:
@@ -257,7 +277,8 @@ def run_ours(args, rank, world, local):
                 "attention": {"achieved": at[0] / (at[1] * 1e-3) / 1e12, "unit": "TFLOP/s",
                               "frac": at[0] / (at[1] * 1e-3) / 1e12 / pk["tflops"], "ms_per_step_in_kernel": at[1] / 2,
                               "launches_per_step": at[2] // 2},
-                "sum_of_timed_kernels_ms": step_ms_prof}
+                "sum_of_timed_kernels_ms": step_ms_prof,
+                "hbm_kernels": hbm_table(prof_hbm, 2, pk)}
 
     e2e = None
     if not args.no_e2e:
@@ -334,6 +355,37 @@ def run_train(args, model, rank, world, dev, dist, pk):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0]) / args.train_steps
+    # one instrumented micro-step (forward + backward, no optimiser step) for the per-kernel tables
+    ops.PROFILE, ops.PROFILE_HBM = [], []
+    tr._micro = 0
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    tr.train_step(xs[0])
+    e3.record()
+    barrier()
+    prof_t, ops.PROFILE = ops.PROFILE, None
+    prof_h, ops.PROFILE_HBM = ops.PROFILE_HBM, None
+    tens = {}
+    for name, fl, a, b in prof_t:
+        key = "attn_fwd" if name.startswith("attn_fwd") else "attn_bwd" if name.startswith("attn_bwd") else \
+            "wgrad" if name.startswith("wgrad") else "mtgemm (fwd + dgrad)"
+        d = tens.setdefault(key, [0.0, 0.0, 0])
+        d[0] += fl
+        d[1] += a.elapsed_time(b)
+        d[2] += 1
+    tensor_tab = [{"kernel": k, "launches": n, "ms": t_ms, "achieved_tflops": fl / (t_ms * 1e-3) / 1e12,
+                   "frac_of_tensor_peak": fl / (t_ms * 1e-3) / 1e12 / pk["tflops"]}
+                  for k, (fl, t_ms, n) in sorted(tens.items(), key=lambda kv: -kv[1][1])]
+    if args.breakdown and rank == 0:
+        tab = {}
+        for name, fl, a, b in prof_t:
+            d = tab.setdefault((name, round(fl / 1e9, 1)), [0.0, 0])
+            d[0] += a.elapsed_time(b)
+            d[1] += 1
+        print(f"\n[training micro-step, micro-batch {mb}] {'kernel':60s} GFLOP/launch launches   ms   TFLOP/s", file=sys.stderr)
+        for (name, gf), (tt, n) in sorted(tab.items(), key=lambda kv: -kv[1][0]):
+            print(f"{name:78s} {gf:10.1f} {n:8d} {tt:12.3f} {gf * n / tt if tt else 0:9.1f}", file=sys.stderr)
+    micro = {"micro_batch": mb, "ms": e2.elapsed_time(e3), "tensor_kernels": tensor_tab, "hbm_kernels": hbm_table(prof_h, 1, pk)}
     imgs = mb * accum * world
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import transvae_oracle as O
@@ -345,7 +397,8 @@ def run_train(args, model, rank, world, dev, dist, pk):
             "model_frac_of_peak": rate * gflop / 1e3 / (pk["tflops"] * world),
             "gpu_launches_per_step": (ops.LAUNCHES - n0) // args.train_steps,
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
-            "includes": "fwd, L1+KL loss, bwd, bucketed NCCL all-reduce overlapped with bwd, clip, fused AdamW"}
+            "includes": "fwd, L1+KL loss, bwd, bucketed NCCL all-reduce overlapped with bwd, clip, fused AdamW",
+            "profiled_micro_step": micro}
 
 
 def main():

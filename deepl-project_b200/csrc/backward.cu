@@ -2,6 +2,7 @@
 // warp-shuffle / shared-memory reductions, fp32 statistics).  Activations and their gradients are NHWC bf16.
 #include "../../include/transvae_sm100.h"
 #include "common.cuh"
+#include "ew_common.cuh"
 
 namespace tvae {
 
@@ -26,10 +27,13 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // Algorithmic bytes per element: 2 (dY) [+ 2 (Z) + 2 (dZ) when act != none].
 // -------------------------------------------------------------------------------------------------
 // Processes columns [c0, c0+Qs) of the row-major [R0*Pn*R1, Qfull] matrix; row r belongs to phase (r / R1) % Pn.
+constexpr int kEwBatch = 4;   // independent 16-byte loads per stream a thread keeps in flight
+
+template <int ACT>
 __global__ void __launch_bounds__(256) bias_act_bwd_slab_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ z,
                                                                 uint4* __restrict__ dz, float* __restrict__ colsum,
                                                                 long long nrows, int Pn, int R1, int Qfull, int c0, int Qs,
-                                                                int act, int rows_per_block) {
+                                                                int rows_per_block) {
   extern __shared__ float s_col[];   // [Pn][Qs]
   const int nvec = Qs >> 3, nvf = Qfull >> 3, v0 = c0 >> 3;
   for (int i = threadIdx.x; i < Pn * Qs; i += blockDim.x) s_col[i] = 0.0f;
@@ -37,32 +41,54 @@ __global__ void __launch_bounds__(256) bias_act_bwd_slab_kernel(const uint4* __r
   const int v = threadIdx.x % nvec, rl = threadIdx.x / nvec, rpp = blockDim.x / nvec;
   const long long r_begin = (long long)blockIdx.x * rows_per_block;
   const long long r_end = min(nrows, r_begin + rows_per_block);
-  float acc[2][8];
+  float2 acc[2][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.0f;
+  for (int i = 0; i < 4; ++i) acc[0][i] = acc[1][i] = f2(0.0f);
   if (rl < rpp) {
-#pragma unroll 4
-    for (long long r = r_begin + rl; r < r_end; r += rpp) {
-      const int p = (Pn == 1) ? 0 : (int)((r / R1) % Pn);
-      const long long idx = r * nvf + v0 + v;
-      float g[8];
-      unpack8(__ldg(dy + idx), g);
-      if (act != TVAE_ACT_NONE) {
-        float zz[8];
-        unpack8(__ldg(z + idx), zz);
+    for (long long r = r_begin + rl; r < r_end; r += (long long)rpp * kEwBatch) {
+      uint4 ug[kEwBatch], uz[kEwBatch];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] *= (act == TVAE_ACT_GELU) ? gelu_erf_grad(zz[i]) : silu_grad(zz[i]);
-        dz[idx] = pack8(g);
-        unpack8(pack8(g), g);   // the column sums must see the bf16-rounded dZ that the GEMMs will read
+      for (int k = 0; k < kEwBatch; ++k) {
+        const long long rr = r + (long long)k * rpp;
+        if (rr < r_end) {
+          ug[k] = __ldg(dy + rr * nvf + v0 + v);
+          if (ACT != TVAE_ACT_NONE) uz[k] = __ldg(z + rr * nvf + v0 + v);
+        }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[p & 1][i] += g[i];
+      for (int k = 0; k < kEwBatch; ++k) {
+        const long long rr = r + (long long)k * rpp;
+        if (rr < r_end) {
+          const int p = (Pn == 1) ? 0 : (int)((rr / R1) % Pn);
+          float2 g[4];
+          unpack8_2(ug[k], g);
+          if (ACT != TVAE_ACT_NONE) {
+            float2 zz[4];
+            unpack8_2(uz[k], zz);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) g[i] = __fmul2_rn(g[i], ACT == TVAE_ACT_GELU ? gelu_grad2(zz[i]) : silu_grad2(zz[i]));
+            const uint4 o = pack8_2(g);
+            dz[rr * nvf + v0 + v] = o;
+            unpack8_2(o, g);   // the column sums must see the bf16-rounded dZ that the GEMMs will read
+          }
+          if (p & 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[1][i] = __fadd2_rn(acc[1][i], g[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[0][i] = __fadd2_rn(acc[0][i], g[i]);
+          }
+        }
+      }
     }
 #pragma unroll
     for (int pp = 0; pp < 2; ++pp)
       if (pp < Pn)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(&s_col[pp * Qs + v * 8 + i], acc[pp][i]);
+        for (int i = 0; i < 4; ++i) {
+          atomicAdd(&s_col[pp * Qs + v * 8 + 2 * i], acc[pp][i].x);
+          atomicAdd(&s_col[pp * Qs + v * 8 + 2 * i + 1], acc[pp][i].y);
+        }
   }
   __syncthreads();
   if (colsum != nullptr)
@@ -75,18 +101,29 @@ int bias_act_bwd_run(const void* dy, const void* z, void* dz, float* colsum, lon
   TVAE_REQUIRE(Q % 8 == 0, "bias_act_bwd: Q=%d must be a multiple of 8", Q);
   TVAE_REQUIRE(Pn == 1 || Pn == 2, "bias_act_bwd: P must be 1 or 2");
   TVAE_REQUIRE(act == TVAE_ACT_NONE || (z != nullptr && dz != nullptr), "bias_act_bwd: activation needs z and dz");
+  TVAE_REQUIRE(act == TVAE_ACT_NONE || act == TVAE_ACT_GELU || act == TVAE_ACT_SILU, "bias_act_bwd: unknown activation %d", act);
   if (colsum) TVAE_CHECK_CUDA(cudaMemsetAsync(colsum, 0, (size_t)Pn * Q * sizeof(float), stream));
   const long long nrows = R0 * Pn * R1;
-  int rpb = 1024;
-  while (rpb > 32 && (nrows + rpb - 1) / rpb < 2LL * num_sms()) rpb >>= 1;
-  const int grid = (int)((nrows + rpb - 1) / rpb);
   for (int c0 = 0; c0 < Q; c0 += 2048) {
     const int qs = (Q - c0) < 2048 ? (Q - c0) : 2048;
     const int nvec = qs / 8;
     const int threads = nvec >= 256 ? 256 : (256 / nvec) * nvec;
-    bias_act_bwd_slab_kernel<<<grid, threads, (size_t)Pn * qs * sizeof(float), stream>>>(
-        reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(z), reinterpret_cast<uint4*>(dz), colsum, nrows,
-        Pn, R1, Q, c0, qs, act, rpb);
+    const int rpp = threads / nvec > 0 ? threads / nvec : 1;
+    // ~4 resident blocks per SM, each sweeping a contiguous run of rows: the column sums leave a block as one global
+    // atomic per column, so fewer, longer blocks mean fewer contended atomics (thousands of short blocks put
+    // 6500 atomics on each of 192 addresses)
+    const long long unit = (long long)rpp * kEwBatch;
+    long long rpb = ((nrows + 4LL * num_sms() - 1) / (4LL * num_sms()) + unit - 1) / unit * unit;
+    if (rpb < unit) rpb = unit;
+    const int grid = (int)((nrows + rpb - 1) / rpb);
+    const size_t smem = (size_t)Pn * qs * sizeof(float);
+    auto args = [&](auto kern) {
+      kern<<<grid, threads, smem, stream>>>(reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(z),
+                                            reinterpret_cast<uint4*>(dz), colsum, nrows, Pn, R1, Q, c0, qs, (int)rpb);
+    };
+    if (act == TVAE_ACT_GELU) args(bias_act_bwd_slab_kernel<TVAE_ACT_GELU>);
+    else if (act == TVAE_ACT_SILU) args(bias_act_bwd_slab_kernel<TVAE_ACT_SILU>);
+    else args(bias_act_bwd_slab_kernel<TVAE_ACT_NONE>);
     TVAE_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
@@ -99,24 +136,37 @@ int bias_act_bwd_matrix_run(const void* dy, const void* z, void* dz, float* cols
 
 // y = act(z) elementwise (training path: the GEMM stores the pre-activation z that the backward pass needs, the
 // activation output is produced by this pass).  Algorithmic bytes: 4 per element.
-__global__ void __launch_bounds__(256) act_fwd_kernel(const uint4* __restrict__ z, uint4* __restrict__ y, long long n8,
-                                                      int act) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
-    float f[8];
-    unpack8(__ldg(z + i), f);
+template <int ACT>
+__global__ void __launch_bounds__(256) act_fwd_kernel(const uint4* __restrict__ z, uint4* __restrict__ y, long long n8) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride * kEwBatch) {
+    uint4 u[kEwBatch];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = (act == TVAE_ACT_GELU) ? gelu_erf(f[k]) : silu(f[k]);
-    y[i] = pack8(f);
+    for (int k = 0; k < kEwBatch; ++k)
+      if (i + k * stride < n8) u[k] = __ldg(z + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < kEwBatch; ++k) {
+      if (i + k * stride < n8) {
+        float2 f[4];
+        unpack8_2(u[k], f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) f[q] = (ACT == TVAE_ACT_GELU) ? gelu2(f[q]) : silu2(f[q]);
+        y[i + k * stride] = pack8_2(f);
+      }
+    }
   }
 }
 
 int act_fwd_run(const void* z, void* y, long long n, int act, cudaStream_t stream) {
   TVAE_REQUIRE(n % 8 == 0, "act_fwd: element count must be a multiple of 8");
   TVAE_REQUIRE(act == TVAE_ACT_GELU || act == TVAE_ACT_SILU, "act_fwd: unknown activation %d", act);
-  int grid = (int)((n / 8 + 255) / 256);
-  if (grid > num_sms() * 16) grid = num_sms() * 16;
-  act_fwd_kernel<<<grid < 1 ? 1 : grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(z), reinterpret_cast<uint4*>(y),
-                                                          n / 8, act);
+  long long grid = (n / 8 + 256 * kEwBatch - 1) / (256 * kEwBatch);
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  if (grid < 1) grid = 1;
+  if (act == TVAE_ACT_GELU)
+    act_fwd_kernel<TVAE_ACT_GELU><<<(int)grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(z), reinterpret_cast<uint4*>(y), n / 8);
+  else
+    act_fwd_kernel<TVAE_ACT_SILU><<<(int)grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(z), reinterpret_cast<uint4*>(y), n / 8);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -139,51 +189,92 @@ __device__ __forceinline__ void gn_group_coef(const float* sums, int b, int G, i
   rstd = rsqrtf(var + eps);
 }
 
+// per-thread constants of its 8 channels, packed in pairs: xhat = x * a + b (a = rstd, b = -mean * rstd), y = xhat * ga + be
+struct GnChan {
+  float2 a[4], b[4], ga[4], be[4];
+};
+__device__ __forceinline__ void gn_load_chan(GnChan& ch, const float* sums, const float* gamma, const float* beta, int b,
+                                             int G, int cpg, int v, float inv_n, float eps) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float m0, r0, m1, r1;
+    const int c = v * 8 + 2 * i;
+    gn_group_coef(sums, b, G, c / cpg, inv_n, eps, m0, r0);
+    gn_group_coef(sums, b, G, (c + 1) / cpg, inv_n, eps, m1, r1);
+    ch.a[i] = make_float2(r0, r1);
+    ch.b[i] = make_float2(-m0 * r0, -m1 * r1);
+    ch.ga[i] = make_float2(gamma[c], gamma[c + 1]);
+    ch.be[i] = make_float2(beta[c], beta[c + 1]);
+  }
+}
+
+template <bool SILU>
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dh,
                                                             const float* __restrict__ sums,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ part, int HW, int C, int G, float eps,
-                                                            int apply_silu, int pix_per_block) {
+                                                            int pix_per_block) {
+  extern __shared__ float s_part[];   // [C][2]
   const int nvec = C >> 3, cpg = C / G;
   const int b = blockIdx.y;
   const int v = threadIdx.x % nvec, pv = threadIdx.x / nvec, ppb = blockDim.x / nvec;
   const float inv_n = 1.0f / ((float)cpg * (float)HW);
-  float mean[8], rstd[8], ga[8], be[8], s1[8], s2[8];
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_part[i] = 0.0f;
+  __syncthreads();
+  GnChan ch;
+  gn_load_chan(ch, sums, gamma, beta, b, G, cpg, v, inv_n, eps);
+  float2 s1[4], s2[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = v * 8 + i;
-    gn_group_coef(sums, b, G, c / cpg, inv_n, eps, mean[i], rstd[i]);
-    ga[i] = gamma[c];
-    be[i] = beta[c];
-    s1[i] = s2[i] = 0.0f;
-  }
+  for (int i = 0; i < 4; ++i) s1[i] = s2[i] = f2(0.0f);
   const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
   const size_t base = (size_t)b * HW * nvec + v;
-#pragma unroll 4
-  for (int p = p0 + pv; p < p1; p += ppb) {
-    float xf[8], g[8];
-    unpack8(__ldg(x + base + (size_t)p * nvec), xf);
-    unpack8(__ldg(dh + base + (size_t)p * nvec), g);
+  for (int p = p0 + pv; p < p1; p += ppb * kEwBatch) {
+    uint4 ux[kEwBatch], ug[kEwBatch];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float xh = (xf[i] - mean[i]) * rstd[i];
-      const float dy = apply_silu ? g[i] * silu_grad(fmaf(xh, ga[i], be[i])) : g[i];
-      s1[i] += dy;
-      s2[i] = fmaf(dy, xh, s2[i]);
+    for (int k = 0; k < kEwBatch; ++k) {
+      const int pp = p + k * ppb;
+      if (pp < p1) {
+        ux[k] = __ldg(x + base + (size_t)pp * nvec);
+        ug[k] = __ldg(dh + base + (size_t)pp * nvec);
+      } else {
+        ux[k] = ug[k] = make_uint4(0, 0, 0, 0);        // dh = 0 contributes nothing
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kEwBatch; ++k) {
+      float2 xf[4], g[4];
+      unpack8_2(ux[k], xf);
+      unpack8_2(ug[k], g);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 xh = __ffma2_rn(xf[i], ch.a[i], ch.b[i]);
+        const float2 dy = SILU ? __fmul2_rn(g[i], silu_grad2(__ffma2_rn(xh, ch.ga[i], ch.be[i]))) : g[i];
+        s1[i] = __fadd2_rn(s1[i], dy);
+        s2[i] = __ffma2_rn(dy, xh, s2[i]);
+      }
     }
   }
+  // block-level reduction in shared memory, then ONE global atomic per (channel, statistic) and block: the first version
+  // sent every thread's 16 partials straight to global memory -- 320 contended atomics per address and launch, which
+  // held the kernel at 2.1 TB/s while the (atomic-free) apply pass ran at 5.5 TB/s
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    atomicAdd(part + ((size_t)b * C + v * 8 + i) * 2, s1[i]);
-    atomicAdd(part + ((size_t)b * C + v * 8 + i) * 2 + 1, s2[i]);
+  for (int i = 0; i < 4; ++i) {
+    float* pp = s_part + (v * 8 + 2 * i) * 2;
+    atomicAdd(pp, s1[i].x);
+    atomicAdd(pp + 1, s2[i].x);
+    atomicAdd(pp + 2, s1[i].y);
+    atomicAdd(pp + 3, s2[i].y);
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(part + (size_t)b * C * 2 + i, s_part[i]);
 }
 
+template <bool SILU, bool ADD>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dh,
                                                            const uint4* __restrict__ add, const float* __restrict__ sums,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ part, uint4* __restrict__ dx, int HW,
-                                                           int C, int G, float eps, int apply_silu, int vec_per_block) {
+                                                           int C, int G, float eps, int vec_per_block) {
   extern __shared__ float s_g[];  // per group: m1, m2
   const int nvec = C >> 3, cpg = C / G;
   const int b = blockIdx.y;
@@ -199,34 +290,51 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restri
   }
   __syncthreads();
   const int v = threadIdx.x % nvec;
-  float mean[8], rstd[8], ga[8], be[8], m1[8], m2[8];
+  GnChan ch;
+  gn_load_chan(ch, sums, gamma, beta, b, G, cpg, v, inv_n, eps);
+  // dx = rstd * (dy * gamma - m1 - xhat * m2) = dy * A - M1 - xhat * M2 with A = rstd * gamma, M1 = rstd * m1, M2 = rstd * m2
+  float2 A[4], nM1[4], nM2[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = v * 8 + i, g = c / cpg;
-    gn_group_coef(sums, b, G, g, inv_n, eps, mean[i], rstd[i]);
-    ga[i] = gamma[c];
-    be[i] = beta[c];
-    m1[i] = s_g[2 * g];
-    m2[i] = s_g[2 * g + 1];
+  for (int i = 0; i < 4; ++i) {
+    const int c = v * 8 + 2 * i, g0 = c / cpg, g1 = (c + 1) / cpg;
+    A[i] = __fmul2_rn(ch.a[i], ch.ga[i]);
+    nM1[i] = make_float2(-ch.a[i].x * s_g[2 * g0], -ch.a[i].y * s_g[2 * g1]);
+    nM2[i] = make_float2(-ch.a[i].x * s_g[2 * g0 + 1], -ch.a[i].y * s_g[2 * g1 + 1]);
   }
   const long long total = (long long)HW * nvec;
   const long long i0 = (long long)blockIdx.x * vec_per_block, i1 = min(total, i0 + vec_per_block);
   const size_t off = (size_t)b * total;
-#pragma unroll 2
-  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-    float xf[8], g[8], r[8];
-    unpack8(__ldg(x + off + i), xf);
-    unpack8(__ldg(dh + off + i), g);
-    if (add != nullptr) unpack8(__ldg(add + off + i), r);
+  const long long stride = blockDim.x;
+  for (long long i = i0 + threadIdx.x; i < i1; i += stride * kEwBatch) {
+    uint4 ux[kEwBatch], ug[kEwBatch], ur[kEwBatch];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float xh = (xf[k] - mean[k]) * rstd[k];
-      const float dy = apply_silu ? g[k] * silu_grad(fmaf(xh, ga[k], be[k])) : g[k];
-      float o = rstd[k] * (dy * ga[k] - m1[k] - xh * m2[k]);
-      if (add != nullptr) o += r[k];
-      g[k] = o;
+    for (int k = 0; k < kEwBatch; ++k) {
+      const long long ii = i + k * stride;
+      if (ii < i1) {
+        ux[k] = __ldg(x + off + ii);
+        ug[k] = __ldg(dh + off + ii);
+        if (ADD) ur[k] = __ldg(add + off + ii);
+      }
     }
-    dx[off + i] = pack8(g);
+#pragma unroll
+    for (int k = 0; k < kEwBatch; ++k) {
+      const long long ii = i + k * stride;
+      if (ii < i1) {
+        float2 xf[4], g[4], r[4];
+        unpack8_2(ux[k], xf);
+        unpack8_2(ug[k], g);
+        if (ADD) unpack8_2(ur[k], r);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 xh = __ffma2_rn(xf[q], ch.a[q], ch.b[q]);
+          const float2 dy = SILU ? __fmul2_rn(g[q], silu_grad2(__ffma2_rn(xh, ch.ga[q], ch.be[q]))) : g[q];
+          float2 o = __ffma2_rn(dy, A[q], nM1[q]);
+          o = __ffma2_rn(xh, nM2[q], o);
+          g[q] = ADD ? __fadd2_rn(o, r[q]) : o;
+        }
+        dx[off + ii] = pack8_2(g);
+      }
+    }
   }
 }
 
@@ -236,21 +344,32 @@ int gn_bwd_run(const void* x, const void* dh, const void* add, const float* sums
   TVAE_CHECK_CUDA(cudaMemsetAsync(part, 0, (size_t)B * C * 2 * sizeof(float), stream));
   const int nvec = C / 8;
   const int threads = (256 / nvec) * nvec;
-  int ppb = 2048;
-  while (ppb > 64 && (long long)((HW + ppb - 1) / ppb) * B < 2LL * num_sms()) ppb >>= 1;
+  int ppb = 1024;
+  while (ppb > 64 && (long long)((HW + ppb - 1) / ppb) * B < 8LL * num_sms()) ppb >>= 1;
   dim3 g1((HW + ppb - 1) / ppb, B);
-  gn_bwd_reduce_kernel<<<g1, threads, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dh),
-                                                   sums, gamma, beta, part, HW, C, G, eps, apply_silu, ppb);
+  const uint4* xp = reinterpret_cast<const uint4*>(x);
+  const uint4* dp = reinterpret_cast<const uint4*>(dh);
+  const uint4* ap = reinterpret_cast<const uint4*>(add);
+  const size_t smem_r = 2 * (size_t)C * sizeof(float);
+  if (apply_silu) gn_bwd_reduce_kernel<true><<<g1, threads, smem_r, stream>>>(xp, dp, sums, gamma, beta, part, HW, C, G, eps, ppb);
+  else gn_bwd_reduce_kernel<false><<<g1, threads, smem_r, stream>>>(xp, dp, sums, gamma, beta, part, HW, C, G, eps, ppb);
   TVAE_CHECK_CUDA(cudaGetLastError());
   const long long total = (long long)HW * nvec;
-  long long vpb = (long long)threads * 16;
-  while (vpb > threads && ((total + vpb - 1) / vpb) * B < 4LL * num_sms()) vpb >>= 1;
+  long long vpb = (long long)threads * kEwBatch * 4;
+  while (vpb > threads && ((total + vpb - 1) / vpb) * B < 8LL * num_sms()) vpb >>= 1;
   vpb = (vpb / threads) * threads;
   if (vpb < threads) vpb = threads;
   dim3 g2((unsigned)((total + vpb - 1) / vpb), B);
-  gn_bwd_apply_kernel<<<g2, threads, 2 * G * sizeof(float), stream>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dh), reinterpret_cast<const uint4*>(add), sums,
-      gamma, beta, part, reinterpret_cast<uint4*>(dx), HW, C, G, eps, apply_silu, (int)vpb);
+  const size_t smem = 2 * G * sizeof(float);
+  uint4* op = reinterpret_cast<uint4*>(dx);
+#define TVAE_GN_APPLY(S, A) \
+  gn_bwd_apply_kernel<S, A><<<g2, threads, smem, stream>>>(xp, dp, ap, sums, gamma, beta, part, op, HW, C, G, eps, (int)vpb)
+  if (apply_silu) {
+    if (add) TVAE_GN_APPLY(true, true); else TVAE_GN_APPLY(true, false);
+  } else {
+    if (add) TVAE_GN_APPLY(false, true); else TVAE_GN_APPLY(false, false);
+  }
+#undef TVAE_GN_APPLY
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -3,6 +3,7 @@
 // reparameterisation and the L1+KL loss.  All activations are NHWC bf16; statistics are fp32.
 #include "../../include/transvae_sm100.h"
 #include "common.cuh"
+#include "ew_common.cuh"
 
 namespace tvae {
 
@@ -87,6 +88,8 @@ int conv_in_run(const float* x, const float* w, const float* bias, void* out, in
 // Replaces the reduction half of nn.GroupNorm(32, C) (blocks.py:33,36; decoder.py:93).
 // Algorithmic bytes: 2*C per pixel (one read).
 // -------------------------------------------------------------------------------------------------
+constexpr int kGnBatch = 8;   // independent 16-byte loads a thread keeps in flight
+
 __global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ sums, int HW,
                                                        int C, int G, int pix_per_block) {
   __shared__ float s_acc[2 * 128];
@@ -96,29 +99,36 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__
   for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.0f;
   __syncthreads();
   const int v = threadIdx.x % nvec, pv = threadIdx.x / nvec;
-  float s[8], ss[8];
+  float2 s[4], ss[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.0f;
-  if (pv < ppb) {
-    const int p0 = blockIdx.x * pix_per_block;
-    const int p1 = min(HW, p0 + pix_per_block);
-    const uint4* base = x + (size_t)b * HW * nvec + v;
-#pragma unroll 4
-    for (int p = p0 + pv; p < p1; p += ppb) {
-      const uint4 u = __ldg(base + (size_t)p * nvec);
-      float2 t;
-      t = unpack_bf16(u.x); s[0] += t.x; ss[0] += t.x * t.x; s[1] += t.y; ss[1] += t.y * t.y;
-      t = unpack_bf16(u.y); s[2] += t.x; ss[2] += t.x * t.x; s[3] += t.y; ss[3] += t.y * t.y;
-      t = unpack_bf16(u.z); s[4] += t.x; ss[4] += t.x * t.x; s[5] += t.y; ss[5] += t.y * t.y;
-      t = unpack_bf16(u.w); s[6] += t.x; ss[6] += t.x * t.x; s[7] += t.y; ss[7] += t.y * t.y;
-    }
-    const int cpg = C / G;
+  for (int i = 0; i < 4; ++i) s[i] = ss[i] = f2(0.0f);
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const uint4* base = x + (size_t)b * HW * nvec + v;
+  for (int p = p0 + pv; p < p1; p += ppb * kGnBatch) {
+    uint4 u[kGnBatch];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int g = (v * 8 + i) / cpg;
-      atomicAdd(&s_acc[2 * g], s[i]);
-      atomicAdd(&s_acc[2 * g + 1], ss[i]);
+    for (int k = 0; k < kGnBatch; ++k)
+      u[k] = (p + k * ppb < p1) ? __ldg(base + (size_t)(p + k * ppb) * nvec) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < kGnBatch; ++k) {
+      float2 f[4];
+      unpack8_2(u[k], f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        s[i] = __fadd2_rn(s[i], f[i]);
+        ss[i] = __ffma2_rn(f[i], f[i], ss[i]);
+      }
     }
+  }
+  const int cpg = C / G;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int g0 = (v * 8 + 2 * i) / cpg, g1 = (v * 8 + 2 * i + 1) / cpg;
+    atomicAdd(&s_acc[2 * g0], s[i].x);
+    atomicAdd(&s_acc[2 * g0 + 1], ss[i].x);
+    atomicAdd(&s_acc[2 * g1], s[i].y);
+    atomicAdd(&s_acc[2 * g1 + 1], ss[i].y);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&sums[(size_t)b * 2 * G + i], s_acc[i]);
@@ -129,8 +139,8 @@ int gn_stats_run(const void* x, float* sums, int B, int HW, int C, int G, cudaSt
   TVAE_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * G * 2 * sizeof(float), stream));
   const int nvec = C / 8;
   const int threads = (256 / nvec) * nvec;
-  int ppb = 2048;
-  while (ppb > 64 && (long long)((HW + ppb - 1) / ppb) * B < 2LL * num_sms()) ppb >>= 1;
+  int ppb = 1024;
+  while (ppb > 64 && (long long)((HW + ppb - 1) / ppb) * B < 8LL * num_sms()) ppb >>= 1;
   dim3 grid((HW + ppb - 1) / ppb, B);
   gn_stats_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<const uint4*>(x), sums, HW, C, G, ppb);
   TVAE_CHECK_CUDA(cudaGetLastError());
@@ -139,11 +149,12 @@ int gn_stats_run(const void* x, float* sums, int B, int HW, int C, int G, cudaSt
 
 // y = act((x - mean_g) * rstd_g * gamma_c + beta_c), act = SiLU or identity.  NHWC bf16 in / out.
 // Replaces the affine half of nn.GroupNorm + F.silu (blocks.py:60-66; decoder.py:128-129).
-// Algorithmic bytes: 4*C per pixel (read + write).
+// Algorithmic bytes: 4*C per pixel (read + write).  Packed fp32 math: 4 instructions per element.
+template <bool SILU>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ sums,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        uint4* __restrict__ y, int HW, int C, int G, float eps,
-                                                       int apply_silu, int vec_per_block) {
+                                                       int vec_per_block) {
   extern __shared__ float s_ab[];  // scale[C], shift[C]
   const int b = blockIdx.y;
   const int cpg = C / G;
@@ -164,32 +175,33 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__
   const long long i1 = min(total, i0 + vec_per_block);
   // blockDim.x is a multiple of nvec and vec_per_block too, so each thread always sees the same 8 channels
   const int v = threadIdx.x % nvec;
-  float a[8], sh[8];
+  float2 a[4], sh[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    a[i] = s_ab[v * 8 + i];
-    sh[i] = s_ab[C + v * 8 + i];
+  for (int i = 0; i < 4; ++i) {
+    a[i] = make_float2(s_ab[v * 8 + 2 * i], s_ab[v * 8 + 2 * i + 1]);
+    sh[i] = make_float2(s_ab[C + v * 8 + 2 * i], s_ab[C + v * 8 + 2 * i + 1]);
   }
   const uint4* xb = x + (size_t)b * total;
   uint4* yb = y + (size_t)b * total;
-#pragma unroll 4
-  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-    const uint4 u = __ldg(xb + i);
-    float f[8];
-    float2 t;
-    t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
-    t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
-    t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
-    t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+  const long long stride = blockDim.x;
+  for (long long i = i0 + threadIdx.x; i < i1; i += stride * kGnBatch) {
+    uint4 u[kGnBatch];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float z = fmaf(f[k], a[k], sh[k]);
-      f[k] = apply_silu ? silu(z) : z;
+    for (int k = 0; k < kGnBatch; ++k)
+      if (i + k * stride < i1) u[k] = __ldg(xb + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < kGnBatch; ++k) {
+      if (i + k * stride < i1) {
+        float2 f[4];
+        unpack8_2(u[k], f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 z = __ffma2_rn(f[q], a[q], sh[q]);
+          f[q] = SILU ? silu2(z) : z;
+        }
+        yb[i + k * stride] = pack8_2(f);
+      }
     }
-    uint4 o;
-    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-    o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-    yb[i] = o;
   }
 }
 
@@ -199,14 +211,17 @@ int gn_apply_run(const void* x, const float* sums, const float* gamma, const flo
   const int nvec = C / 8;
   const int threads = (256 / nvec) * nvec;
   const long long total = (long long)HW * nvec;
-  long long vpb = (long long)threads * 16;
-  while (vpb > threads && ((total + vpb - 1) / vpb) * B < 4LL * num_sms()) vpb >>= 1;
+  long long vpb = (long long)threads * 4 * kGnBatch;
+  while (vpb > threads && ((total + vpb - 1) / vpb) * B < 8LL * num_sms()) vpb >>= 1;
   vpb = (vpb / threads) * threads;
   if (vpb < threads) vpb = threads;
   dim3 grid((unsigned)((total + vpb - 1) / vpb), B);
-  gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(
-      reinterpret_cast<const uint4*>(x), sums, gamma, beta, reinterpret_cast<uint4*>(y), HW, C, G, eps, apply_silu,
-      (int)vpb);
+  if (apply_silu)
+    gn_apply_kernel<true><<<grid, threads, 2 * C * sizeof(float), stream>>>(
+        reinterpret_cast<const uint4*>(x), sums, gamma, beta, reinterpret_cast<uint4*>(y), HW, C, G, eps, (int)vpb);
+  else
+    gn_apply_kernel<false><<<grid, threads, 2 * C * sizeof(float), stream>>>(
+        reinterpret_cast<const uint4*>(x), sums, gamma, beta, reinterpret_cast<uint4*>(y), HW, C, G, eps, (int)vpb);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

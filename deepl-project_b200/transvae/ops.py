@@ -22,6 +22,30 @@ LAUNCHES = 0
 # optional per-launch device timing of the tensor-core kernel (bench.py roofline): list of
 # (name, algorithmic_flops, start_event, end_event); None = off
 PROFILE = None
+# same for the HBM-bound kernels: (name, algorithmic_bytes, start_event, end_event); None = off
+PROFILE_HBM = None
+
+
+class _hbm:
+    """with _hbm(name, algorithmic_bytes): launch(...) -- CUDA-event timing of one bandwidth-bound launch when
+    ``PROFILE_HBM`` is a list (bench.py's HBM roofline table); free otherwise."""
+    __slots__ = ("name", "nbytes", "e0")
+
+    def __init__(self, name: str, nbytes: float):
+        self.name, self.nbytes, self.e0 = name, nbytes, None
+
+    def __enter__(self):
+        if PROFILE_HBM is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE_HBM.append((self.name, float(self.nbytes), self.e0, e1))
+        return False
 
 
 def _stream() -> int:
@@ -159,8 +183,9 @@ def conv_in(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
     out = torch.empty(B, H, W, w.shape[0], dtype=BF16, device=x.device)
     wf = w.float().contiguous()
     bf = None if b is None else b.float().contiguous()
-    _lib.check(_lib.load().tvae_conv_in(x.data_ptr(), wf.data_ptr(), _ptr(bf), out.data_ptr(), B, Cin, H, W, w.shape[0],
-                                        _stream()), "tvae_conv_in")
+    with _hbm("conv_in", x.numel() * 4 + out.numel() * 2):
+        _lib.check(_lib.load().tvae_conv_in(x.data_ptr(), wf.data_ptr(), _ptr(bf), out.data_ptr(), B, Cin, H, W, w.shape[0],
+                                            _stream()), "tvae_conv_in")
     _count()
     return out
 
@@ -169,8 +194,9 @@ def groupnorm_stats(x: Tensor, groups: int = 32) -> Tensor:
     _need_cuda(x)
     B, H, W, C_ = x.shape
     sums = torch.empty(B, groups, 2, dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().tvae_groupnorm_stats(x.data_ptr(), sums.data_ptr(), B, H * W, C_, groups, _stream()),
-               "tvae_groupnorm_stats")
+    with _hbm("gn_stats", x.numel() * 2):
+        _lib.check(_lib.load().tvae_groupnorm_stats(x.data_ptr(), sums.data_ptr(), B, H * W, C_, groups, _stream()),
+                   "tvae_groupnorm_stats")
     _count(2)
     return sums
 
@@ -185,9 +211,10 @@ def groupnorm_silu(x: Tensor, gamma: Tensor, beta: Tensor, groups: int = 32, eps
         sums = groupnorm_stats(x, groups)
     y = torch.empty_like(x)
     g, b = gamma.float().contiguous(), beta.float().contiguous()
-    _lib.check(_lib.load().tvae_groupnorm_apply(x.data_ptr(), sums.data_ptr(), g.data_ptr(), b.data_ptr(), y.data_ptr(),
-                                                B, H * W, C_, groups, eps, 1 if silu else 0, _stream()),
-               "tvae_groupnorm_apply")
+    with _hbm("gn_apply_silu", x.numel() * 4):
+        _lib.check(_lib.load().tvae_groupnorm_apply(x.data_ptr(), sums.data_ptr(), g.data_ptr(), b.data_ptr(), y.data_ptr(),
+                                                    B, H * W, C_, groups, eps, 1 if silu else 0, _stream()),
+                   "tvae_groupnorm_apply")
     _count()
     return y
 
@@ -204,8 +231,9 @@ def row_stats(x: Tensor, w1: Optional[Tensor] = None, mode: Optional[int] = None
     a = torch.empty(M, dtype=torch.float32, device=x.device)
     b = torch.empty(M, dtype=torch.float32, device=x.device) if mode != 0 else None
     w1f = None if w1 is None else w1.float().contiguous()
-    _lib.check(_lib.load().tvae_row_stats(x.data_ptr(), _ptr(w1f), a.data_ptr(), _ptr(b), M, C_, mode,
-                                          _stream()), "tvae_row_stats")
+    with _hbm("row_stats", x.numel() * 2):
+        _lib.check(_lib.load().tvae_row_stats(x.data_ptr(), _ptr(w1f), a.data_ptr(), _ptr(b), M, C_, mode,
+                                              _stream()), "tvae_row_stats")
     _count()
     return a, b
 
@@ -215,8 +243,9 @@ def nchw_to_nhwc(x: Tensor, cpad: int) -> Tensor:
     x = x.float().contiguous()
     B, C_, H, W = x.shape
     out = torch.empty(B, H, W, cpad, dtype=BF16, device=x.device)
-    _lib.check(_lib.load().tvae_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, C_, H, W, cpad, _stream()),
-               "tvae_nchw_to_nhwc")
+    with _hbm("nchw_to_nhwc", x.numel() * 4 + out.numel() * 2):
+        _lib.check(_lib.load().tvae_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, C_, H, W, cpad, _stream()),
+                   "tvae_nchw_to_nhwc")
     _count()
     return out
 
@@ -227,8 +256,9 @@ def nhwc_to_nchw(x: Tensor, c: Optional[int] = None) -> Tensor:
     B, H, W, Cs = x.shape
     c = Cs if c is None else c
     out = torch.empty(B, c, H, W, dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().tvae_nhwc_to_nchw(x.data_ptr(), out.data_ptr(), B, c, H, W, Cs, _stream()),
-               "tvae_nhwc_to_nchw")
+    with _hbm("nhwc_to_nchw", x.numel() * 2 + out.numel() * 4):
+        _lib.check(_lib.load().tvae_nhwc_to_nchw(x.data_ptr(), out.data_ptr(), B, c, H, W, Cs, _stream()),
+                   "tvae_nhwc_to_nchw")
     _count()
     return out
 
@@ -240,8 +270,9 @@ def reparam(mu: Tensor, logvar: Tensor, eps: Tensor, patched: bool) -> Tuple[Ten
     z = torch.empty_like(mu)
     mu_o = torch.empty_like(mu) if patched else None
     lv_o = torch.empty_like(mu) if patched else None
-    _lib.check(_lib.load().tvae_reparam(mu.data_ptr(), logvar.data_ptr(), eps.data_ptr(), z.data_ptr(), _ptr(mu_o),
-                                        _ptr(lv_o), mu.numel(), 1 if patched else 0, _stream()), "tvae_reparam")
+    with _hbm("reparam", mu.numel() * (24 if patched else 16)):
+        _lib.check(_lib.load().tvae_reparam(mu.data_ptr(), logvar.data_ptr(), eps.data_ptr(), z.data_ptr(), _ptr(mu_o),
+                                            _ptr(lv_o), mu.numel(), 1 if patched else 0, _stream()), "tvae_reparam")
     _count()
     return z, (mu_o if patched else mu), (lv_o if patched else logvar)
 
@@ -253,9 +284,10 @@ def loss_sums(recon: Tensor, target: Tensor, mu: Tensor, logvar: Tensor, patched
     recon, target = recon.float().contiguous(), target.float().contiguous()
     mu, logvar = mu.float().contiguous(), logvar.float().contiguous()
     acc = torch.empty(4, dtype=torch.float32, device=recon.device)
-    _lib.check(_lib.load().tvae_loss_l1_kl(recon.data_ptr(), target.data_ptr(), mu.data_ptr(), logvar.data_ptr(),
-                                           acc.data_ptr(), recon.numel(), mu.numel(), 1 if patched else 0,
-                                           float(clip[0]), float(clip[1]), _stream()), "tvae_loss_l1_kl")
+    with _hbm("loss_l1_kl", (recon.numel() * 2 + mu.numel() * 2) * 4):
+        _lib.check(_lib.load().tvae_loss_l1_kl(recon.data_ptr(), target.data_ptr(), mu.data_ptr(), logvar.data_ptr(),
+                                               acc.data_ptr(), recon.numel(), mu.numel(), 1 if patched else 0,
+                                               float(clip[0]), float(clip[1]), _stream()), "tvae_loss_l1_kl")
     _count(2)
     return acc
 
@@ -297,15 +329,17 @@ def bias_act_bwd(dy: Tensor, z: Optional[Tensor], act: int, phase_view: bool = F
     if phase_view:
         B, H2, W2, Cc = dy.shape
         cs = torch.empty(2, 2 * Cc, dtype=torch.float32, device=dy.device)
-        _lib.check(_lib.load().tvae_bias_act_bwd_4d(dy.data_ptr(), zp, dzp, cs.data_ptr(), B * (H2 // 2), 2, W2 // 2,
-                                                    2 * Cc, act, _stream()), "tvae_bias_act_bwd_4d")
+        with _hbm("bias_act_bwd" if act != ACT_NONE else "bias_grad (column sums)", dy.numel() * (6 if act != ACT_NONE else 2)):
+            _lib.check(_lib.load().tvae_bias_act_bwd_4d(dy.data_ptr(), zp, dzp, cs.data_ptr(), B * (H2 // 2), 2, W2 // 2,
+                                                        2 * Cc, act, _stream()), "tvae_bias_act_bwd_4d")
         _count(2)
         return dz, cs.view(2, 2, Cc)
     N = dy.shape[-1]
     M = dy.numel() // N
     cs = torch.empty(N, dtype=torch.float32, device=dy.device)
-    _lib.check(_lib.load().tvae_bias_act_bwd(dy.data_ptr(), zp, dzp, cs.data_ptr(), M, N, act, _stream()),
-               "tvae_bias_act_bwd")
+    with _hbm("bias_act_bwd" if act != ACT_NONE else "bias_grad (column sums)", dy.numel() * (6 if act != ACT_NONE else 2)):
+        _lib.check(_lib.load().tvae_bias_act_bwd(dy.data_ptr(), zp, dzp, cs.data_ptr(), M, N, act, _stream()),
+                   "tvae_bias_act_bwd")
     _count(2)
     return dz, cs
 
@@ -314,7 +348,8 @@ def act_fwd(z: Tensor, act: int) -> Tensor:
     _need_cuda(z)
     assert z.dtype == BF16 and z.is_contiguous()
     y = torch.empty_like(z)
-    _lib.check(_lib.load().tvae_act_fwd(z.data_ptr(), y.data_ptr(), z.numel(), act, _stream()), "tvae_act_fwd")
+    with _hbm("act_fwd", z.numel() * 4):
+        _lib.check(_lib.load().tvae_act_fwd(z.data_ptr(), y.data_ptr(), z.numel(), act, _stream()), "tvae_act_fwd")
     _count()
     return y
 
@@ -327,9 +362,10 @@ def groupnorm_bwd(x: Tensor, dh: Tensor, sums: Tensor, gamma: Tensor, beta: Tens
     g, b = gamma.float().contiguous(), beta.float().contiguous()
     part = torch.empty(B, Cc, 2, dtype=torch.float32, device=x.device)
     dx = torch.empty_like(x)
-    _lib.check(_lib.load().tvae_groupnorm_bwd(x.data_ptr(), dh.data_ptr(), _ptr(add), sums.data_ptr(), g.data_ptr(),
-                                              b.data_ptr(), part.data_ptr(), dx.data_ptr(), B, H * W, Cc, groups, eps,
-                                              1 if silu else 0, _stream()), "tvae_groupnorm_bwd")
+    with _hbm("gn_bwd (reduce + apply)", x.numel() * (10 if add is not None else 8)):
+        _lib.check(_lib.load().tvae_groupnorm_bwd(x.data_ptr(), dh.data_ptr(), _ptr(add), sums.data_ptr(), g.data_ptr(),
+                                                  b.data_ptr(), part.data_ptr(), dx.data_ptr(), B, H * W, Cc, groups, eps,
+                                                  1 if silu else 0, _stream()), "tvae_groupnorm_bwd")
     _count(3)
     red = part.sum(0)          # [C, 2]: tiny (B x C) reduction of the per-image partials
     return dx, red[:, 1].contiguous(), red[:, 0].contiguous()
@@ -341,8 +377,9 @@ def token_norm_fwd(x: Tensor, w: Tensor, mode: int) -> Tensor:
     Cc = x.shape[-1]
     y = torch.empty_like(x)
     wf = w.float().contiguous()
-    _lib.check(_lib.load().tvae_token_norm_fwd(x.data_ptr(), wf.data_ptr(), y.data_ptr(), x.numel() // Cc, Cc, mode,
-                                               _stream()), "tvae_token_norm_fwd")
+    with _hbm("token_norm_fwd", x.numel() * 4):
+        _lib.check(_lib.load().tvae_token_norm_fwd(x.data_ptr(), wf.data_ptr(), y.data_ptr(), x.numel() // Cc, Cc, mode,
+                                                   _stream()), "tvae_token_norm_fwd")
     _count()
     return y
 
@@ -353,8 +390,9 @@ def token_norm_bwd(x: Tensor, w: Tensor, dy: Tensor, add: Optional[Tensor], mode
     dx = torch.empty_like(x)
     dw = torch.empty(Cc, dtype=torch.float32, device=x.device)
     wf = w.float().contiguous()
-    _lib.check(_lib.load().tvae_token_norm_bwd(x.data_ptr(), wf.data_ptr(), dy.data_ptr(), _ptr(add), dx.data_ptr(),
-                                               dw.data_ptr(), x.numel() // Cc, Cc, mode, _stream()), "tvae_token_norm_bwd")
+    with _hbm("token_norm_bwd", x.numel() * (8 if add is not None else 6)):
+        _lib.check(_lib.load().tvae_token_norm_bwd(x.data_ptr(), wf.data_ptr(), dy.data_ptr(), _ptr(add), dx.data_ptr(),
+                                                   dw.data_ptr(), x.numel() // Cc, Cc, mode, _stream()), "tvae_token_norm_bwd")
     _count(2)
     return dx, dw
 
@@ -401,10 +439,11 @@ def loss_bwd(recon: Tensor, target: Tensor, mu: Tensor, logvar: Tensor, scal: Te
              clip: Tuple[float, float]) -> Tuple[Tensor, Tensor, Tensor]:
     _need_cuda(recon, target, mu, logvar, scal)
     drecon, dmu, dlv = torch.empty_like(recon), torch.empty_like(mu), torch.empty_like(logvar)
-    _lib.check(_lib.load().tvae_loss_bwd(recon.data_ptr(), target.data_ptr(), mu.data_ptr(), logvar.data_ptr(),
-                                         scal.data_ptr(), drecon.data_ptr(), dmu.data_ptr(), dlv.data_ptr(), recon.numel(),
-                                         mu.numel(), 1 if patched else 0, float(clip[0]), float(clip[1]), _stream()),
-               "tvae_loss_bwd")
+    with _hbm("loss_bwd", (recon.numel() * 3 + mu.numel() * 4) * 4):
+        _lib.check(_lib.load().tvae_loss_bwd(recon.data_ptr(), target.data_ptr(), mu.data_ptr(), logvar.data_ptr(),
+                                             scal.data_ptr(), drecon.data_ptr(), dmu.data_ptr(), dlv.data_ptr(), recon.numel(),
+                                             mu.numel(), 1 if patched else 0, float(clip[0]), float(clip[1]), _stream()),
+                   "tvae_loss_bwd")
     _count(2)
     return drecon, dmu, dlv
 
@@ -425,15 +464,17 @@ def latent_bwd(mu: Tensor, logvar: Tensor, eps: Tensor, dz: Optional[Tensor], dm
 def sumsq(g: Tensor, out: Tensor) -> None:
     """out[0] += sum(g^2) for a flat fp32 buffer (length % 4 == 0)."""
     _need_cuda(g, out)
-    _lib.check(_lib.load().tvae_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream()), "tvae_sumsq")
+    with _hbm("sumsq (grad norm)", g.numel() * 4):
+        _lib.check(_lib.load().tvae_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream()), "tvae_sumsq")
     _count()
 
 
 def adamw(p: Tensor, g: Tensor, m: Tensor, v: Tensor, ctrl: Tensor, lr: float, betas=(0.9, 0.95), eps: float = 1e-8,
           weight_decay: float = 0.0, step: int = 1) -> None:
     _need_cuda(p, g, m, v, ctrl)
-    _lib.check(_lib.load().tvae_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), ctrl.data_ptr(),
-                                      lr, betas[0], betas[1], eps, weight_decay, step, _stream()), "tvae_adamw")
+    with _hbm("adamw", p.numel() * 28):
+        _lib.check(_lib.load().tvae_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), ctrl.data_ptr(),
+                                          lr, betas[0], betas[1], eps, weight_decay, step, _stream()), "tvae_adamw")
     _count()
 
 
@@ -447,7 +488,8 @@ def metrics_sums(recon: Tensor, target: Tensor, mode: str = "clamp") -> Tensor:
     assert recon.shape == target.shape and recon.dim() == 4
     B, C_, H, W = recon.shape
     acc = torch.empty(B, 4, dtype=torch.float32, device=recon.device)
-    _lib.check(_lib.load().tvae_metrics(recon.data_ptr(), target.data_ptr(), acc.data_ptr(), B, C_, H, W,
-                                        METRIC_MODES[mode], _stream()), "tvae_metrics")
+    with _hbm("metrics (psnr/ssim)", recon.numel() * 8):
+        _lib.check(_lib.load().tvae_metrics(recon.data_ptr(), target.data_ptr(), acc.data_ptr(), B, C_, H, W,
+                                            METRIC_MODES[mode], _stream()), "tvae_metrics")
     _count()
     return acc
