@@ -5,8 +5,7 @@
 namespace tvae {
 int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream);
 int attn_fwd_run(const void* qkv, void* out, float* lse, int B, int S, int C, cudaStream_t stream);
-int conv_in_run(const float* x, const float* w, const float* bias, void* out, int B, int Cin, int H, int W, int Cout,
-                cudaStream_t stream);
+int im2col_in_run(const float* x, void* cols, int B, int H, int W, cudaStream_t stream);
 int gn_stats_run(const void* x, float* sums, int B, int HW, int C, int G, cudaStream_t stream);
 int gn_apply_run(const void* x, const float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
                  int G, float eps, int apply_silu, cudaStream_t stream);
@@ -34,8 +33,6 @@ int attn_bwd_run(const void* qkv, const void* dout, const float* lse, const floa
                  int S, int C, cudaStream_t stream);
 int rope_bwd_run(const float* dq_acc, void* dqkv, const float* tab, long long M, int C, int H, int W, float q_scale,
                  cudaStream_t stream);
-int conv_in_wgrad_run(const float* x, const void* dy, float* dw, float* db, int B, int H, int W, int Cout,
-                      cudaStream_t stream);
 int loss_bwd_run(const float* recon, const float* target, const float* mu, const float* logvar, const float* scal,
                  float* drecon, float* dmu, float* dlv, long long n_img, long long n_lat, int patched, float clip_lo,
                  float clip_hi, cudaStream_t stream);
@@ -89,9 +86,8 @@ int tvae_mtgemm(const tvae_mtgemm_desc* desc, void* stream) { GUARD(); return mt
 int tvae_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t S, int32_t C, void* stream) {
   GUARD(); return attn_fwd_run(qkv, out, lse, B, S, C, S_(stream));
 }
-int tvae_conv_in(const float* x, const float* w, const float* bias, void* out, int32_t B, int32_t Cin, int32_t H,
-                 int32_t W, int32_t Cout, void* stream) {
-  GUARD(); return conv_in_run(x, w, bias, out, B, Cin, H, W, Cout, S_(stream));
+int tvae_im2col_in(const float* x_nchw, void* cols, int32_t B, int32_t H, int32_t W, void* stream) {
+  GUARD(); return im2col_in_run(x_nchw, cols, B, H, W, S_(stream));
 }
 int tvae_groupnorm_stats(const void* x, float* sums, int32_t B, int32_t HW, int32_t C, int32_t G, void* stream) {
   GUARD(); return gn_stats_run(x, sums, B, HW, C, G, S_(stream));
@@ -152,10 +148,6 @@ int tvae_attn_bwd(const void* qkv, const void* dout, const float* lse, const flo
 int tvae_rope_bwd(const float* dq_acc, void* dqkv, const float* rope_tab, int64_t M, int32_t C, int32_t H, int32_t W,
                   float q_scale, void* stream) {
   GUARD(); return rope_bwd_run(dq_acc, dqkv, rope_tab, M, C, H, W, q_scale, S_(stream));
-}
-int tvae_conv_in_wgrad(const float* x, const void* dy, float* dw, float* db, int32_t B, int32_t H, int32_t W, int32_t Cout,
-                       void* stream) {
-  GUARD(); return conv_in_wgrad_run(x, dy, dw, db, B, H, W, Cout, S_(stream));
 }
 int tvae_loss_bwd(const float* recon, const float* target, const float* mu, const float* logvar, const float* scal,
                   float* drecon, float* dmu, float* dlogvar, int64_t n_img, int64_t n_lat, int32_t patched, float clip_lo,

@@ -383,57 +383,124 @@ int gn_bwd_run(const void* x, const void* dh, const void* add, const float* sums
 // -------------------------------------------------------------------------------------------------
 constexpr int kMaxVecPerLane = 10;  // C <= 2560
 
+// Interleaved warp reductions of N independent values (the shuffles of different rows / statistics overlap).
+template <int N>
+__device__ __forceinline__ void warp_sum_n(float (&v)[N]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+}
+
+// One warp normalises R rows at a time (VPL 16-byte vectors per lane and row, C <= 256 * VPL): all R * VPL loads are
+// issued before the first reduction and the warp reductions of the R rows are interleaved, in a persistent
+// grid-stride loop.  (The first version -- one short-lived warp per row, 16 K blocks per launch -- reached 1.6 TB/s.)
+template <int VPL, int R>
 __global__ void __launch_bounds__(256) token_norm_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ w,
                                                              uint4* __restrict__ y, long long M, int C, int mode) {
   const int lane = threadIdx.x & 31;
-  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= M) return;
   const int nvec = C >> 3;
-  float h[kMaxVecPerLane][8];
-  float s2 = 0.0f;
-  int cnt = 0;
-  for (int v = lane; v < nvec; v += 32, ++cnt) {
-    unpack8(__ldg(x + row * nvec + v), h[cnt]);
+  const float invC = 1.0f / (float)C;
+  float2 wv[VPL][4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s2 = fmaf(h[cnt][k], h[cnt][k], s2);
-  }
-  s2 = warp_sum(s2);
-  const float rstd = rsqrtf(s2 / (float)C + 1e-6f);
-  float sm = 0.0f, sq = 0.0f;
-  cnt = 0;
-  for (int v = lane; v < nvec; v += 32, ++cnt) {
-    const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * v);
-    const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
-    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+  for (int c = 0; c < VPL; ++c) {
+    const int v = lane + c * 32;
+    if (v < nvec) {
+      const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * v);
+      const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
+      wv[c][0] = make_float2(wa.x, wa.y); wv[c][1] = make_float2(wa.z, wa.w);
+      wv[c][2] = make_float2(wb.x, wb.y); wv[c][3] = make_float2(wb.z, wb.w);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      h[cnt][k] *= rstd * wv[k];
-      sm += h[cnt][k];
-      sq = fmaf(h[cnt][k], h[cnt][k], sq);
+      for (int q = 0; q < 4; ++q) wv[c][q] = f2(0.0f);
     }
   }
-  float mu = 0.0f, rs = 1.0f;
-  if (mode == 1) {
-    sm = warp_sum(sm);
-    sq = warp_sum(sq);
-    mu = sm / (float)C;
-    rs = rsqrtf(fmaxf(sq / (float)C - mu * mu, 0.0f) + 1e-5f);
-  }
-  cnt = 0;
-  for (int v = lane; v < nvec; v += 32, ++cnt) {
+  const long long groups = (M + R - 1) / R;
+  const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long grp = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5); grp < groups; grp += warps_total) {
+    const long long row0 = grp * R;
+    uint4 u[R][VPL];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) h[cnt][k] = (h[cnt][k] - mu) * rs;
-    y[row * nvec + v] = pack8(h[cnt]);
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < VPL; ++c) {
+        const int v = lane + c * 32;
+        u[r][c] = (v < nvec && row0 + r < M) ? __ldg(x + (row0 + r) * nvec + v) : make_uint4(0, 0, 0, 0);
+      }
+    float2 h[R][VPL][4];
+    float s2[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float2 acc = f2(0.0f);
+#pragma unroll
+      for (int c = 0; c < VPL; ++c) {
+        unpack8_2(u[r][c], h[r][c]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc = __ffma2_rn(h[r][c][q], h[r][c][q], acc);
+      }
+      s2[r] = acc.x + acc.y;
+    }
+    warp_sum_n<R>(s2);
+    float st[2 * R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float2 rstd = f2(rsqrtf(s2[r] * invC + 1e-6f));
+      float2 sm = f2(0.0f), sq = f2(0.0f);
+#pragma unroll
+      for (int c = 0; c < VPL; ++c)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          h[r][c][q] = __fmul2_rn(h[r][c][q], __fmul2_rn(rstd, wv[c][q]));
+          sm = __fadd2_rn(sm, h[r][c][q]);
+          sq = __ffma2_rn(h[r][c][q], h[r][c][q], sq);
+        }
+      st[2 * r] = sm.x + sm.y;
+      st[2 * r + 1] = sq.x + sq.y;
+    }
+    if (mode == 1) {
+      warp_sum_n<2 * R>(st);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float mu = st[2 * r] * invC;
+        const float rs = rsqrtf(fmaxf(st[2 * r + 1] * invC - mu * mu, 0.0f) + 1e-5f);
+        const float2 a = f2(rs), bsh = f2(-mu * rs);
+#pragma unroll
+        for (int c = 0; c < VPL; ++c)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) h[r][c][q] = __ffma2_rn(h[r][c][q], a, bsh);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < VPL; ++c) {
+        const int v = lane + c * 32;
+        if (v < nvec && row0 + r < M) y[(row0 + r) * nvec + v] = pack8_2(h[r][c]);
+      }
   }
+}
+
+template <int VPL, int R>
+static int launch_tnf(const void* x, const float* w, void* y, long long M, int C, int mode, cudaStream_t stream) {
+  const long long groups = (M + R - 1) / R;
+  long long blocks = (groups + 7) / 8;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  token_norm_fwd_kernel<VPL, R><<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), w,
+                                                                 reinterpret_cast<uint4*>(y), M, C, mode);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int token_norm_fwd_run(const void* x, const float* w, void* y, long long M, int C, int mode, cudaStream_t stream) {
   TVAE_REQUIRE(C % 8 == 0 && C / 8 <= 32 * kMaxVecPerLane, "token_norm: C=%d unsupported", C);
-  const int grid = (int)((M * 32 + 255) / 256);
-  token_norm_fwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), w, reinterpret_cast<uint4*>(y), M, C,
-                                                  mode);
-  TVAE_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  const int vpl = (C / 8 + 31) / 32;
+  if (vpl <= 1) return launch_tnf<1, 4>(x, w, y, M, C, mode, stream);
+  if (vpl == 2) return launch_tnf<2, 2>(x, w, y, M, C, mode, stream);
+  if (vpl == 3) return launch_tnf<3, 1>(x, w, y, M, C, mode, stream);
+  if (vpl == 4) return launch_tnf<4, 1>(x, w, y, M, C, mode, stream);
+  if (vpl <= 6) return launch_tnf<6, 1>(x, w, y, M, C, mode, stream);
+  return launch_tnf<kMaxVecPerLane, 1>(x, w, y, M, C, mode, stream);
 }
 
 // dx = d(norm)/dx^T dy [+ add];  dw[c] += sum_rows (...).
@@ -451,119 +518,152 @@ __global__ void __launch_bounds__(256) token_norm_bwd_reg_kernel(const uint4* __
   const int nvec = C >> 3;
   for (int i = threadIdx.x; i < C; i += blockDim.x) s_dw[i] = 0.0f;
   __syncthreads();
-  float dwacc[VPL][8];
+  float2 wv[VPL][4], dwacc[VPL][4];
 #pragma unroll
-  for (int c = 0; c < VPL; ++c)
+  for (int c = 0; c < VPL; ++c) {
+    const int v = lane + c * 32;
+    float4 wa = make_float4(0, 0, 0, 0), wb = wa;
+    if (v < nvec) {
+      wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * v);
+      wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
+    }
+    wv[c][0] = make_float2(wa.x, wa.y); wv[c][1] = make_float2(wa.z, wa.w);
+    wv[c][2] = make_float2(wb.x, wb.y); wv[c][3] = make_float2(wb.z, wb.w);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) dwacc[c][k] = 0.0f;
+    for (int q = 0; q < 4; ++q) dwacc[c][q] = f2(0.0f);
+  }
   const float invC = 1.0f / (float)C;
   const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp; row < M; row += warps_total) {
-    float xr[VPL][8], g[VPL][8];
-    float s2 = 0.0f;
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  // software prefetch (narrow rows only -- wide rows have enough loads per lane and no registers to spare): the next
+  // row's x / dy are in flight while this row is reduced
+  constexpr bool kPrefetch = VPL <= 3;
+  uint4 nx[VPL], ng[VPL];
+  if (kPrefetch) {
 #pragma unroll
     for (int c = 0; c < VPL; ++c) {
       const int v = lane + c * 32;
-      if (v < nvec) {
-        unpack8(__ldg(x + row * nvec + v), xr[c]);
-        unpack8(__ldg(dy + row * nvec + v), g[c]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) xr[c][k] = g[c][k] = 0.0f;
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s2 = fmaf(xr[c][k], xr[c][k], s2);
+      const bool ok = v < nvec && row < M;
+      nx[c] = ok ? __ldg(x + row * nvec + v) : make_uint4(0, 0, 0, 0);
+      ng[c] = ok ? __ldg(dy + row * nvec + v) : make_uint4(0, 0, 0, 0);
     }
-    s2 = warp_sum(s2);
-    const float rstd = rsqrtf(s2 * invC + 1e-6f);
+  }
+  for (; row < M; row += warps_total) {
+    float2 xr[VPL][4], g[VPL][4];
+    uint4 ua[VPL];
+    float s2[1];
+    if (!kPrefetch) {
+#pragma unroll
+      for (int c = 0; c < VPL; ++c) {
+        const int v = lane + c * 32;
+        nx[c] = (v < nvec) ? __ldg(x + row * nvec + v) : make_uint4(0, 0, 0, 0);
+        ng[c] = (v < nvec) ? __ldg(dy + row * nvec + v) : make_uint4(0, 0, 0, 0);
+      }
+    }
+    {
+      float2 acc = f2(0.0f);
+#pragma unroll
+      for (int c = 0; c < VPL; ++c) {
+        unpack8_2(nx[c], xr[c]);
+        unpack8_2(ng[c], g[c]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc = __ffma2_rn(xr[c][q], xr[c][q], acc);
+      }
+      s2[0] = acc.x + acc.y;
+    }
+    if (kPrefetch) {
+      const long long nrow = row + warps_total;
+#pragma unroll
+      for (int c = 0; c < VPL; ++c) {
+        const int v = lane + c * 32;
+        const bool ok = v < nvec && nrow < M;
+        nx[c] = ok ? __ldg(x + nrow * nvec + v) : make_uint4(0, 0, 0, 0);
+        ng[c] = ok ? __ldg(dy + nrow * nvec + v) : make_uint4(0, 0, 0, 0);
+        if (add != nullptr) ua[c] = (v < nvec) ? __ldg(add + row * nvec + v) : make_uint4(0, 0, 0, 0);
+      }
+    }
+    warp_sum_n<1>(s2);
+    const float rstd = rsqrtf(s2[0] * invC + 1e-6f);
 #pragma unroll
     for (int c = 0; c < VPL; ++c)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) xr[c][k] *= rstd;          // xhat_r
+      for (int q = 0; q < 4; ++q) xr[c][q] = __fmul2_rn(xr[c][q], f2(rstd));          // xhat_r
     if (mode == 1) {
-      float sm = 0.0f, sq = 0.0f;
+      float st[2];
+      {
+        float2 sm = f2(0.0f), sq = f2(0.0f);
 #pragma unroll
-      for (int c = 0; c < VPL; ++c) {
-        const int v = lane + c * 32;
-        if (v < nvec) {
-          const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * v);
-          const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
-          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        for (int c = 0; c < VPL; ++c)
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float h = xr[c][k] * wv[k];
-            sm += h;
-            sq = fmaf(h, h, sq);
+          for (int q = 0; q < 4; ++q) {
+            const float2 h = __fmul2_rn(xr[c][q], wv[c][q]);
+            sm = __fadd2_rn(sm, h);
+            sq = __ffma2_rn(h, h, sq);
           }
-        }
+        st[0] = sm.x + sm.y;
+        st[1] = sq.x + sq.y;
       }
-      sm = warp_sum(sm);
-      sq = warp_sum(sq);
-      const float mu = sm * invC;
-      const float rs = rsqrtf(fmaxf(sq * invC - mu * mu, 0.0f) + 1e-5f);
-      float a1 = 0.0f, a2 = 0.0f;
+      warp_sum_n<2>(st);
+      const float mu = st[0] * invC;
+      const float rs = rsqrtf(fmaxf(st[1] * invC - mu * mu, 0.0f) + 1e-5f);
+      const float2 rs2 = f2(rs), sh2 = f2(-mu * rs);
+      float a[2];
+      {
+        float2 a1 = f2(0.0f), a2 = f2(0.0f);
 #pragma unroll
-      for (int c = 0; c < VPL; ++c) {
-        const int v = lane + c * 32;
-        if (v < nvec) {
-          const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * v);
-          const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
-          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        for (int c = 0; c < VPL; ++c)
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float yh = (xr[c][k] * wv[k] - mu) * rs;
-            a1 += g[c][k];
-            a2 = fmaf(g[c][k], yh, a2);
+          for (int q = 0; q < 4; ++q) {
+            const float2 yh = __ffma2_rn(__fmul2_rn(xr[c][q], wv[c][q]), rs2, sh2);
+            a1 = __fadd2_rn(a1, g[c][q]);
+            a2 = __ffma2_rn(g[c][q], yh, a2);
           }
-        }
+        a[0] = a1.x + a1.y;
+        a[1] = a2.x + a2.y;
       }
-      a1 = warp_sum(a1) * invC;
-      a2 = warp_sum(a2) * invC;
+      warp_sum_n<2>(a);
+      // LayerNorm (no affine) backward: dh = rs * (g - mean(g) - yhat * mean(g * yhat))
+      const float2 na1 = f2(-a[0] * invC), na2rs = f2(-a[1] * invC * rs);
 #pragma unroll
-      for (int c = 0; c < VPL; ++c) {
-        const int v = lane + c * 32;
-        if (v < nvec) {
-          const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * v);
-          const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
-          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+      for (int c = 0; c < VPL; ++c)
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float yh = (xr[c][k] * wv[k] - mu) * rs;
-            g[c][k] = rs * (g[c][k] - a1 - yh * a2);   // dh
-          }
+        for (int q = 0; q < 4; ++q) {
+          const float2 yh = __ffma2_rn(__fmul2_rn(xr[c][q], wv[c][q]), rs2, sh2);
+          g[c][q] = __ffma2_rn(yh, na2rs, __fmul2_rn(__fadd2_rn(g[c][q], na1), rs2));
         }
-      }
     }
-    float a3 = 0.0f;
+    // RMSNorm backward: dw += dh * xhat_r ; dx = rstd * (dh * w - xhat_r * mean(dh * w * xhat_r)) [+ add]
+    float a3[1];
+    {
+      float2 acc = f2(0.0f);
+#pragma unroll
+      for (int c = 0; c < VPL; ++c)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          dwacc[c][q] = __ffma2_rn(g[c][q], xr[c][q], dwacc[c][q]);
+          g[c][q] = __fmul2_rn(g[c][q], wv[c][q]);
+          acc = __ffma2_rn(g[c][q], xr[c][q], acc);
+        }
+      a3[0] = acc.x + acc.y;
+    }
+    warp_sum_n<1>(a3);
+    const float2 na3 = f2(-a3[0] * invC), rstd2 = f2(rstd);
 #pragma unroll
     for (int c = 0; c < VPL; ++c) {
       const int v = lane + c * 32;
       if (v < nvec) {
-        const float4 wa = __ldg(reinterpret_cast<const float4*>(w) + 2 * v);
-        const float4 wb = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
-        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          dwacc[c][k] = fmaf(g[c][k], xr[c][k], dwacc[c][k]);
-          g[c][k] *= wv[k];
-          a3 = fmaf(g[c][k], xr[c][k], a3);
+        float2 r[4];
+        if (add != nullptr) {
+          if (!kPrefetch) ua[c] = __ldg(add + row * nvec + v);
+          unpack8_2(ua[c], r);
         }
-      }
-    }
-    a3 = warp_sum(a3) * invC;
 #pragma unroll
-    for (int c = 0; c < VPL; ++c) {
-      const int v = lane + c * 32;
-      if (v < nvec) {
-        float r[8];
-        if (add != nullptr) unpack8(__ldg(add + row * nvec + v), r);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float o = rstd * (g[c][k] - xr[c][k] * a3);
-          if (add != nullptr) o += r[k];
-          g[c][k] = o;
+        for (int q = 0; q < 4; ++q) {
+          float2 o = __fmul2_rn(__ffma2_rn(xr[c][q], na3, g[c][q]), rstd2);
+          if (add != nullptr) o = __fadd2_rn(o, r[q]);
+          g[c][q] = o;
         }
-        dx[row * nvec + v] = pack8(g[c]);
+        dx[row * nvec + v] = pack8_2(g[c]);
       }
     }
   }
@@ -572,7 +672,10 @@ __global__ void __launch_bounds__(256) token_norm_bwd_reg_kernel(const uint4* __
     const int v = lane + c * 32;
     if (v < nvec)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) atomicAdd(&s_dw[v * 8 + k], dwacc[c][k]);
+      for (int q = 0; q < 4; ++q) {
+        atomicAdd(&s_dw[v * 8 + 2 * q], dwacc[c][q].x);
+        atomicAdd(&s_dw[v * 8 + 2 * q + 1], dwacc[c][q].y);
+      }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dw + i, s_dw[i]);
@@ -815,75 +918,6 @@ int rope_bwd_run(const float* dq_acc, void* dqkv, const float* tab, long long M,
   return 0;
 }
 
-// -------------------------------------------------------------------------------------------------
-// conv_in weight gradient (Cin = 3): dW[co][ci][dy][dx] += sum_pixels dY[pixel][co] * x[b][ci][y+dy-1][x+dx-1],
-// dbias[co] += sum dY.  Each block reduces a pixel range into shared memory, then flushes with atomics.
-// -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) conv_in_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                                                            float* __restrict__ dw, float* __restrict__ db, int B, int H,
-                                                            int W, int Cout, int pix_per_block) {
-  extern __shared__ float s_in[];  // [pix_chunk][28] (27 inputs + 1.0 for the bias)
-  constexpr int CH = 64;           // pixels staged per round
-  const long long npix = (long long)B * H * W;
-  const long long p0 = (long long)blockIdx.x * pix_per_block;
-  const long long p1 = min(npix, p0 + pix_per_block);
-  // thread -> (co, k-slice): 256 threads cover Cout x (28 / ks) ... simple mapping: each thread owns one co and 7 of the
-  // 28 taps when Cout*4 <= 256, otherwise loops over co.
-  const int nco_par = blockDim.x / 4;
-  const int kq = threadIdx.x & 3;
-  float acc[8][7];
-  for (int a = 0; a < 8; ++a)
-    for (int k = 0; k < 7; ++k) acc[a][k] = 0.0f;
-  for (long long base = p0; base < p1; base += CH) {
-    const int n = (int)min((long long)CH, p1 - base);
-    __syncthreads();
-    for (int i = threadIdx.x; i < n * 28; i += blockDim.x) {
-      const int pp = i / 28, k = i % 28;
-      const long long pix = base + pp;
-      float val = 1.0f;
-      if (k < 27) {
-        const int ci = k / 9, dyy = (k % 9) / 3, dxx = k % 3;
-        const int wq = (int)(pix % W), hq = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
-        const int yy = hq + dyy - 1, xx = wq + dxx - 1;
-        val = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + (((size_t)b * 3 + ci) * H + yy) * W + xx) : 0.0f;
-      }
-      s_in[pp * 28 + k] = val;
-    }
-    __syncthreads();
-    int a = 0;
-    for (int co = threadIdx.x >> 2; co < Cout; co += nco_par, ++a) {
-      for (int pp = 0; pp < n; ++pp) {
-        const float g = __bfloat162float(dy[(size_t)(base + pp) * Cout + co]);
-#pragma unroll
-        for (int k = 0; k < 7; ++k) acc[a][k] = fmaf(g, s_in[pp * 28 + kq * 7 + k], acc[a][k]);
-      }
-    }
-  }
-  int a = 0;
-  for (int co = threadIdx.x >> 2; co < Cout; co += nco_par, ++a) {
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      const int kk = kq * 7 + k;
-      if (kk < 27) atomicAdd(dw + (size_t)co * 27 + kk, acc[a][k]);
-      else if (db != nullptr) atomicAdd(db + co, acc[a][k]);
-    }
-  }
-}
-
-int conv_in_wgrad_run(const float* x, const void* dy, float* dw, float* db, int B, int H, int W, int Cout,
-                      cudaStream_t stream) {
-  TVAE_REQUIRE(Cout <= 8 * 64, "conv_in_wgrad: Cout %d too large", Cout);
-  TVAE_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)Cout * 27 * sizeof(float), stream));
-  if (db) TVAE_CHECK_CUDA(cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), stream));
-  const long long npix = (long long)B * H * W;
-  int ppb = 4096;
-  while (ppb > 256 && (npix + ppb - 1) / ppb < 4LL * num_sms()) ppb >>= 1;
-  const int grid = (int)((npix + ppb - 1) / ppb);
-  conv_in_wgrad_kernel<<<grid, 256, 64 * 28 * sizeof(float), stream>>>(x, reinterpret_cast<const __nv_bfloat16*>(dy), dw, db,
-                                                                       B, H, W, Cout, ppb);
-  TVAE_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
 
 // -------------------------------------------------------------------------------------------------
 // Loss / reparameterisation backward (transvae.py:186-199, :244-245 patched; vae_loss.py:80-104 patched / :83,:94 main).

@@ -8,77 +8,52 @@
 namespace tvae {
 
 // -------------------------------------------------------------------------------------------------
-// conv_in: 3x3, pad 1, Cin (3) -> Cout, NCHW fp32 input, NHWC bf16 output.
-// Replaces nn.Conv2d at encoder.py:52 (0.03 % of the model's FLOPs; bound by the 2*Cout bytes/pixel it writes).
-// One thread per pixel keeps its 9*Cin inputs in registers and sweeps the output channels 8 at a time with
-// the weights broadcast from shared memory.
+// im2col of the 3-channel input image for encoder.conv_in (encoder.py:52, 3x3 pad 1, 3 -> C0).
+// NCHW fp32 [B, 3, H, W] -> bf16 [B*H*W, 64] with, per pixel,
+//   columns  0..26  hi = bf16(x[ci, h+dy-1, w+dx-1])          (k = ci*9 + dy*3 + dx, zero outside the image)
+//   columns 27..53  lo = bf16(x - hi)                          (the split keeps ~16 mantissa bits of the fp32 image)
+//   column  54      1.0                                        (bias column)
+//   columns 55..63  0
+// so the first convolution and its weight gradient become K = 64 launches of the tcgen05 GEMM kernels (tvae_mtgemm /
+// tvae_mtgemm_wgrad with a packed [C0, 64] weight [w | w | bias | 0]) instead of CUDA-core loops: the direct kernels
+// ran at 13 % of the HBM roofline forward and took 4.4 ms per training micro-step for the weight gradient.
+// Algorithmic bytes: 12 read + 128 written per pixel.
 // -------------------------------------------------------------------------------------------------
-template <int CIN>
-__global__ void __launch_bounds__(128) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                      int B, int H, int W, int Cout) {
-  extern __shared__ float sw[];  // [9*CIN][Cout] + bias[Cout]
-  float* sb = sw + 9 * CIN * Cout;
-  for (int i = threadIdx.x; i < 9 * CIN * Cout; i += blockDim.x) {
-    const int co = i % Cout, k = i / Cout;        // k = (ci*3 + dy)*3 + dx in OIHW order
-    sw[i] = w[(size_t)co * 9 * CIN + k];
-  }
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.0f;
-  __syncthreads();
+__global__ void __launch_bounds__(256) im2col_in_kernel(const float* __restrict__ x, uint4* __restrict__ cols, int B, int H,
+                                                        int W) {
   const long long npix = (long long)B * H * W;
   for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
        pix += (long long)gridDim.x * blockDim.x) {
     const int wq = (int)(pix % W), hq = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
-    float in[9 * CIN];
+    __align__(16) __nv_bfloat16 v[64];
 #pragma unroll
-    for (int ci = 0; ci < CIN; ++ci)
+    for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
           const int yy = hq + dy - 1, xx = wq + dx - 1;
-          in[(ci * 3 + dy) * 3 + dx] =
-              (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + (((size_t)b * CIN + ci) * H + yy) * W + xx) : 0.0f;
+          const float f = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + (((size_t)b * 3 + ci) * H + yy) * W + xx) : 0.0f;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(f);
+          v[(ci * 3 + dy) * 3 + dx] = hi;
+          v[27 + (ci * 3 + dy) * 3 + dx] = __float2bfloat16_rn(f - __bfloat162float(hi));
         }
-    uint4* o = reinterpret_cast<uint4*>(out + (size_t)pix * Cout);
-    for (int c0 = 0; c0 < Cout; c0 += 8) {
-      float acc[8];
+    v[54] = __float2bfloat16_rn(1.0f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = sb[c0 + j];
+    for (int k = 55; k < 64; ++k) v[k] = __float2bfloat16_rn(0.0f);
+    const uint4* src = reinterpret_cast<const uint4*>(v);
+    uint4* dst = cols + pix * 8;
 #pragma unroll
-      for (int k = 0; k < 9 * CIN; ++k) {
-        const float4 w0 = *reinterpret_cast<const float4*>(sw + k * Cout + c0);
-        const float4 w1 = *reinterpret_cast<const float4*>(sw + k * Cout + c0 + 4);
-        const float v = in[k];
-        acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
-        acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-        acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
-        acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
-      }
-      uint4 pk;
-      pk.x = pack_bf16(acc[0], acc[1]); pk.y = pack_bf16(acc[2], acc[3]);
-      pk.z = pack_bf16(acc[4], acc[5]); pk.w = pack_bf16(acc[6], acc[7]);
-      o[c0 >> 3] = pk;
-    }
+    for (int k = 0; k < 8; ++k) dst[k] = src[k];
   }
 }
 
-int conv_in_run(const float* x, const float* w, const float* bias, void* out, int B, int Cin, int H, int W, int Cout,
-                cudaStream_t stream) {
-  TVAE_REQUIRE(Cin == 3, "conv_in: only 3 input channels are supported (got %d)", Cin);
-  TVAE_REQUIRE(Cout % 8 == 0, "conv_in: Cout %d must be a multiple of 8", Cout);
-  const size_t smem = (size_t)(9 * 3 * Cout + Cout) * sizeof(float);
-  TVAE_REQUIRE(smem <= 200 * 1024, "conv_in: Cout %d too large", Cout);
-  static bool configured = false;
-  if (!configured) {
-    TVAE_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+int im2col_in_run(const float* x, void* cols, int B, int H, int W, cudaStream_t stream) {
+  TVAE_REQUIRE(x && cols && B > 0 && H > 0 && W > 0, "im2col_in: bad arguments");
   const long long npix = (long long)B * H * W;
-  int grid = (int)((npix + 127) / 128);
-  const int cap = num_sms() * 8;
-  if (grid > cap) grid = cap;
-  conv_in_kernel<3><<<grid, 128, smem, stream>>>(x, w, bias, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, Cout);
+  long long grid = (npix + 255) / 256;
+  if (grid > num_sms() * 16LL) grid = num_sms() * 16LL;
+  im2col_in_kernel<<<(int)grid, 256, 0, stream>>>(x, reinterpret_cast<uint4*>(cols), B, H, W);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -139,8 +114,9 @@ int gn_stats_run(const void* x, float* sums, int B, int HW, int C, int G, cudaSt
   TVAE_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * G * 2 * sizeof(float), stream));
   const int nvec = C / 8;
   const int threads = (256 / nvec) * nvec;
+  // >= 32 blocks per SM: with ~6 resident blocks per SM a 2.3-wave launch lost a quarter of its time to the tail
   int ppb = 1024;
-  while (ppb > 64 && (long long)((HW + ppb - 1) / ppb) * B < 8LL * num_sms()) ppb >>= 1;
+  while (ppb > 64 && (long long)((HW + ppb - 1) / ppb) * B < 32LL * num_sms()) ppb >>= 1;
   dim3 grid((HW + ppb - 1) / ppb, B);
   gn_stats_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<const uint4*>(x), sums, HW, C, G, ppb);
   TVAE_CHECK_CUDA(cudaGetLastError());

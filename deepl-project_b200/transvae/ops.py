@@ -175,19 +175,32 @@ def attn_fwd(qkv: Tensor, B: int, S: int, C_: int, need_lse: bool = False) -> Tu
     return out, lse
 
 
-def conv_in(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
-    """NCHW fp32 image -> NHWC bf16 features."""
-    _need_cuda(x, w, b)
+def im2col_in(x: Tensor) -> Tensor:
+    """NCHW fp32 image [B, 3, H, W] -> bf16 [B*H*W, 64] im2col rows (hi | lo | 1 | 0) for the first convolution."""
+    _need_cuda(x)
     x = x.float().contiguous()
     B, Cin, H, W = x.shape
-    out = torch.empty(B, H, W, w.shape[0], dtype=BF16, device=x.device)
-    wf = w.float().contiguous()
-    bf = None if b is None else b.float().contiguous()
-    with _hbm("conv_in", x.numel() * 4 + out.numel() * 2):
-        _lib.check(_lib.load().tvae_conv_in(x.data_ptr(), wf.data_ptr(), _ptr(bf), out.data_ptr(), B, Cin, H, W, w.shape[0],
-                                            _stream()), "tvae_conv_in")
+    if Cin != 3:
+        raise ValueError(f"conv_in: 3 input channels expected, got {Cin}")
+    cols = torch.empty(B * H * W, 64, dtype=BF16, device=x.device)
+    with _hbm("im2col_in", x.numel() * 4 + cols.numel() * 2):
+        _lib.check(_lib.load().tvae_im2col_in(x.data_ptr(), cols.data_ptr(), B, H, W, _stream()), "tvae_im2col_in")
     _count()
-    return out
+    return cols
+
+
+def conv_in(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
+    """encoder.conv_in: NCHW fp32 image -> NHWC bf16 features (im2col + K = 64 tensor-core GEMM, bias in column 54)."""
+    _need_cuda(x, w, b)
+    from . import _taps as T
+    B, _, H, W = x.shape
+    co = w.shape[0]
+    cols = im2col_in(x)
+    w27 = w.detach().float().reshape(co, 27)
+    bias = torch.zeros(co, 1, dtype=torch.float32, device=w.device) if b is None else b.detach().float().reshape(co, 1)
+    wp = torch.cat([w27, w27, bias, torch.zeros(co, 9, dtype=torch.float32, device=w.device)], dim=1).to(BF16).contiguous()
+    out = mtgemm(T.plan_linear(64), cols.view(1, 1, B * H * W, 64), wp, out_shape=(1, 1, B * H * W, co))
+    return out.view(B, H, W, co)
 
 
 def groupnorm_stats(x: Tensor, groups: int = 32) -> Tensor:
@@ -423,16 +436,15 @@ def attn_bwd(qkv: Tensor, out: Tensor, dout: Tensor, lse: Tensor, rope_tab: Tens
 
 
 def conv_in_wgrad(x: Tensor, dy: Tensor) -> Tuple[Tensor, Tensor]:
+    """(dW [Co, 3, 3, 3], dbias [Co]) of encoder.conv_in from dY (NHWC bf16): one tcgen05 wgrad launch on the im2col rows."""
     _need_cuda(x, dy)
-    x = x.float().contiguous()
-    B, Cin, H, W = x.shape
-    Co = dy.shape[-1]
-    dw = torch.empty(Co, Cin, 3, 3, dtype=torch.float32, device=x.device)
-    db = torch.empty(Co, dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().tvae_conv_in_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), B, H, W, Co,
-                                              _stream()), "tvae_conv_in_wgrad")
-    _count(3)
-    return dw, db
+    from . import _taps as T
+    B, _, H, W = x.shape
+    co = dy.shape[-1]
+    cols = im2col_in(x)
+    dwp = mtgemm_wgrad(T.plan_linear(64), cols.view(1, 1, B * H * W, 64), dy.reshape(1, 1, B * H * W, co), co)
+    dw = (dwp[:, :27] + dwp[:, 27:54]).reshape(co, 3, 3, 3).contiguous()
+    return dw, dwp[:, 54].contiguous()
 
 
 def loss_bwd(recon: Tensor, target: Tensor, mu: Tensor, logvar: Tensor, scal: Tensor, patched: bool,

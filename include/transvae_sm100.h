@@ -101,9 +101,11 @@ int tvae_mtgemm(const tvae_mtgemm_desc* desc /* HOST pointer */, void* stream);
 int tvae_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t S, int32_t C, void* stream);
 
 /* ---- HBM-bound kernels ------------------------------------------------------------------------ */
-/* encoder.conv_in (encoder.py:52): 3x3 pad 1, NCHW fp32 [B,3,H,W] -> NHWC bf16 [B,H,W,Cout]; w fp32 OIHW. */
-int tvae_conv_in(const float* x_nchw, const float* w_oihw, const float* bias, void* out_nhwc, int32_t B, int32_t Cin,
-                 int32_t H, int32_t W, int32_t Cout, void* stream);
+/* encoder.conv_in (encoder.py:52, nn.Conv2d(3, C0, 3, padding=1)) as a tensor-core GEMM: im2col of the NCHW fp32 image
+ * [B,3,H,W] into bf16 cols [B*H*W, 64] = [27 taps hi | 27 taps lo | 1.0 | 0 x 9] (tap k = ci*9 + dy*3 + dx, hi + lo = the
+ * fp32 pixel split in two bf16, zero outside the image).  The convolution is then tvae_mtgemm with a 1-tap K = 64 plan
+ * and the packed weight [C0, 64] = [w | w | bias | 0]; its weight / bias gradient is tvae_mtgemm_wgrad on the same cols. */
+int tvae_im2col_in(const float* x_nchw, void* cols, int32_t B, int32_t H, int32_t W, void* stream);
 /* nn.GroupNorm(G, C) statistics (blocks.py:33,36; decoder.py:93): sums fp32 [B, G, 2] = (sum x, sum x^2). */
 int tvae_groupnorm_stats(const void* x_nhwc, float* sums, int32_t B, int32_t HW, int32_t C, int32_t G, void* stream);
 /* y = act(GroupNorm(x)) with act = SiLU (apply_silu=1) or identity; NHWC bf16 in/out (blocks.py:60-66). */
@@ -169,9 +171,6 @@ int tvae_attn_bwd(const void* qkv, const void* dout, const float* lse, const flo
                   int32_t B, int32_t S, int32_t C, void* stream);
 int tvae_rope_bwd(const float* dq_acc, void* dqkv, const float* rope_tab, int64_t M, int32_t C, int32_t H, int32_t W,
                   float q_scale, void* stream);
-/* encoder.conv_in weight / bias gradient (Cin = 3): dw fp32 [Cout, 3, 3, 3], db fp32 [Cout] (zeroed inside). */
-int tvae_conv_in_wgrad(const float* x_nchw, const void* dy_nhwc, float* dw, float* db, int32_t B, int32_t H, int32_t W,
-                       int32_t Cout, void* stream);
 /* Loss backward: scal (device fp32[2]) = {dLoss * l1_weight / numel(recon), dLoss * kl_weight / kl_norm}. */
 int tvae_loss_bwd(const float* recon, const float* target, const float* mu, const float* logvar, const float* scal,
                   float* drecon, float* dmu, float* dlogvar, int64_t n_img, int64_t n_lat, int32_t patched, float clip_lo,
