@@ -17,7 +17,7 @@ int reparam_run(const float* mu, const float* logvar, const float* eps, float* z
                 long long n, int patched, cudaStream_t stream);
 int loss_run(const float* recon, const float* target, const float* mu, const float* logvar, float* acc,
              long long n_img, long long n_lat, int patched, float clip_lo, float clip_hi, cudaStream_t stream);
-int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, cudaStream_t stream);
+int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, float* db, cudaStream_t stream);
 int bias_act_bwd_run(const void* dy, const void* z, void* dz, float* colsum, long long R0, int Pn, int R1, int Q, int act,
                      cudaStream_t stream);
 int bias_act_bwd_matrix_run(const void* dy, const void* z, void* dz, float* colsum, long long M, int N, int act,
@@ -117,7 +117,12 @@ int tvae_loss_l1_kl(const float* recon, const float* target, const float* mu, co
   GUARD(); return loss_run(recon, target, mu, logvar, acc, n_img, n_lat, patched, clip_lo, clip_hi, S_(stream));
 }
 
-int tvae_mtgemm_wgrad(const tvae_mtgemm_desc* desc, float* dw, void* stream) { GUARD(); return mtwgrad_run(desc, dw, S_(stream)); }
+int tvae_mtgemm_wgrad(const tvae_mtgemm_desc* desc, float* dw, void* stream) {
+  GUARD(); return mtwgrad_run(desc, dw, nullptr, S_(stream));
+}
+int tvae_mtgemm_wgrad_bias(const tvae_mtgemm_desc* desc, float* dw, float* db, void* stream) {
+  GUARD(); return mtwgrad_run(desc, dw, db, S_(stream));
+}
 int tvae_bias_act_bwd(const void* dy, const void* z, void* dz, float* colsum, int64_t M, int32_t N, int32_t act, void* stream) {
   GUARD(); return bias_act_bwd_matrix_run(dy, z, dz, colsum, M, N, act, S_(stream));
 }

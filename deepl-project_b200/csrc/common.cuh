@@ -282,35 +282,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
 }
 
 // ---- math -----------------------------------------------------------------------------------
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 resolution): 2 MUFU + ~10 FMA instead of the
-// ~40-instruction branchy erff -- the GELU epilogues were bound by it.
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // one MUFU.RCP (__frcp_rn expands to a Newton-corrected sequence)
-  return r;
-}
-__device__ __forceinline__ float fast_erf(float x) {
-  const float ax = fabsf(x);
-  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = exp2f(-1.4426950408889634f * ax * ax);
-  return copysignf(fmaf(-p, e, 1.0f), x);
-}
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * exp2f(-0.7213475204444817f * x * x);
-  return fmaf(x, pdf, cdf);
-}
-__device__ __forceinline__ float silu(float x) { return x * rcp_approx(1.0f + __expf(-x)); }
-__device__ __forceinline__ float silu_grad(float x) {
-  float s = rcp_approx(1.0f + __expf(-x));
-  return s * (1.0f + x * (1.0f - s));
-}
+// (activation math lives in ew_common.cuh: packed fp32, one MUFU per element)
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -114,9 +114,8 @@ int gn_stats_run(const void* x, float* sums, int B, int HW, int C, int G, cudaSt
   TVAE_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * G * 2 * sizeof(float), stream));
   const int nvec = C / 8;
   const int threads = (256 / nvec) * nvec;
-  // >= 32 blocks per SM: with ~6 resident blocks per SM a 2.3-wave launch lost a quarter of its time to the tail
   int ppb = 1024;
-  while (ppb > 64 && (long long)((HW + ppb - 1) / ppb) * B < 32LL * num_sms()) ppb >>= 1;
+  while (ppb > 64 && (long long)((HW + ppb - 1) / ppb) * B < 8LL * num_sms()) ppb >>= 1;
   dim3 grid((HW + ppb - 1) / ppb, B);
   gn_stats_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<const uint4*>(x), sums, HW, C, G, ppb);
   TVAE_CHECK_CUDA(cudaGetLastError());

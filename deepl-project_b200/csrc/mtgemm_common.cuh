@@ -3,6 +3,7 @@
 #pragma once
 #include "../../include/transvae_sm100.h"
 #include "common.cuh"
+#include "ew_common.cuh"
 #include "tmap.cuh"
 
 namespace tvae {
@@ -115,10 +116,18 @@ __device__ __forceinline__ void epi_math8(const MtParams& P, const float* __rest
   }
   if constexpr (EPI == kEpiBiasGelu || EPI == kEpiRsBiasGelu) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = gelu_erf(f[k]);
+    for (int k = 0; k < 8; k += 2) {       // packed fp32, one MUFU per element (ew_common.cuh)
+      const float2 r = gelu2(make_float2(f[k], f[k + 1]));
+      f[k] = r.x;
+      f[k + 1] = r.y;
+    }
   } else if constexpr (EPI == kEpiBiasSilu) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = silu(f[k]);
+    for (int k = 0; k < 8; k += 2) {
+      const float2 r = silu2(make_float2(f[k], f[k + 1]));
+      f[k] = r.x;
+      f[k + 1] = r.y;
+    }
   }
   if constexpr (EPI == kEpiAffineRope) {
     if (P.rope_tab != nullptr && n < 2 * P.rope_C) {

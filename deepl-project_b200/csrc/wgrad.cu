@@ -36,6 +36,8 @@ struct WgParams {
   int out_c_off[TVAE_MAX_PHASES];
   WgTap taps[TVAE_MAX_PHASES * TVAE_MAX_TAPS];
   float* dw;
+  float* db;                 // optional bias gradient [phases][n_total] (column sums of dZ), accumulated into
+  int first_tap[TVAE_MAX_PHASES];   // index of the first tap of each phase (its k-tile-0 CTAs also produce db)
 };
 
 constexpr int kWgTile = 128 * 64 * 2;  // one [128 pixels x 64 channels] bf16 box
@@ -44,8 +46,10 @@ template <int KT>
 struct WgCfg {
   static constexpr int kStageBytes = (2 + KT / 64) * kWgTile;
   static constexpr int kStages = (220 * 1024) / kStageBytes > 4 ? 4 : (220 * 1024) / kStageBytes;
-  static constexpr int kTmemCols = KT <= 64 ? 64 : (KT <= 128 ? 128 : 256);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 128;
+  // KT accumulator columns + 16 for the bias gradient (dZ^T x ones), rounded up to a power of two
+  static constexpr int kTmemCols = KT + 16 <= 128 ? 128 : (KT + 16 <= 256 ? 256 : 512);
+  static constexpr int kOnesBytes = 2048;   // a [16 pixels x 64 channels] block of bf16 1.0 (layout-free: all equal)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOnesBytes + 1024 + 128;
 };
 
 template <int KT>
@@ -57,7 +61,8 @@ mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint8_t* s_ones = smem + STAGES * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ones + Cfg::kOnesBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* acc_full = bars + 2 * STAGES;
@@ -79,6 +84,10 @@ mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  if (P.db != nullptr) {
+    for (int i = threadIdx.x; i < Cfg::kOnesBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3f803f80u;
+    fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core's async-proxy reads
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -98,6 +107,10 @@ mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     item -= cnt;
   }
   const WgTap tap = P.taps[ti];
+  // Bias gradient db[n] = sum_pixels dZ[pixel, n]: the CTAs of the first tap / first k tile of each phase run one extra
+  // N = 16 MMA per 16 pixels against a block of ones and keep dZ^T x 1 in 16 more TMEM columns -- the column sums cost
+  // 16 / KT more tensor work on 1 / (taps * k tiles) of the CTAs instead of a separate pass over dZ.
+  const bool do_bias = P.db != nullptr && kt == 0 && ti == P.first_tap[tap.ph];
   const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
   const int my_tiles = (m_tiles - split + P.splits - 1) / P.splits;   // tiles split, split+splits, ...
 
@@ -131,6 +144,8 @@ mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, KT, 1, 1);
+      constexpr uint32_t idesc_ones = umma_idesc_bf16(128, 16, 1, 1);
+      const uint64_t ones_desc = umma_desc_mnmajor_sw128(smem_u32(s_ones), kWgTile, 1024);
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < my_tiles; ++i) {
@@ -142,6 +157,12 @@ mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int k = 0; k < 8; ++k)   // 16 pixels per MMA
           umma_f16(tmem_base, umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024),
                    umma_desc_mnmajor_sw128(a_base + k * 2048, kWgTile, 1024), idesc, (i | k) != 0);
+        if (do_bias) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_f16(tmem_base + KT, umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024), ones_desc, idesc_ones,
+                     (i | k) != 0);
+        }
         umma_commit(&empty[stage]);
         if (++stage == STAGES) {
           stage = 0;
@@ -170,6 +191,12 @@ mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             atomicAdd(reinterpret_cast<float4*>(dst + c * 32 + g * 4), f);
           }
         }
+      }
+      if (do_bias) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + KT, v);
+        tmem_ld_wait();
+        if (n < P.n_total) atomicAdd(P.db + (size_t)tap.ph * P.n_total + n, __uint_as_float(v[0]));
       }
     }
   }
@@ -203,8 +230,8 @@ static int launch_wg(const CUtensorMap& a0, const CUtensorMap& a1, const CUtenso
 }
 
 // d->out is the dZ view (gradient w.r.t. the forward kernel's pre-activation output); dw: fp32 [n_total, k_total],
-// accumulated into (the caller zeroes it).
-int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, cudaStream_t stream) {
+// accumulated into (the caller zeroes it); db: optional fp32 [num_phases, n_total] bias gradient, accumulated into.
+int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, float* db, cudaStream_t stream) {
   TVAE_REQUIRE(d != nullptr && dw != nullptr, "wgrad: null argument");
   TVAE_REQUIRE(d->a0.ptr != nullptr && d->out.ptr != nullptr, "wgrad: missing operand");
   TVAE_REQUIRE(d->k_total % 64 == 0, "wgrad: k_total %d must be a multiple of 64", d->k_total);
@@ -223,11 +250,13 @@ int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, cudaStream_t stream) {
   P.k_total = d->k_total;
   P.n_tiles = (d->n_total + 127) / 128;
   P.dw = dw;
+  P.db = db;
   int kt = 256;
   int nt = 0;
   for (int ph = 0; ph < d->num_phases; ++ph) {
     P.out_p[ph] = d->out_p[ph];
     P.out_c_off[ph] = d->out_c_off[ph];
+    P.first_tap[ph] = nt;
     for (int t = 0; t < d->ntaps[ph]; ++t) {
       const tvae_tap& s = d->taps[ph][t];
       const tvae_view& av = s.map ? d->a1 : d->a0;

@@ -42,8 +42,11 @@ def _f32(t: Tensor) -> Tensor:
     return t.detach().float().contiguous()
 
 
-def _colsum(dy: Tensor) -> Tensor:
-    return ops.bias_act_bwd(dy, None, ACT_NONE)[1]
+def _wgrad_b(plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[Tensor] = None):
+    """(dW, dbias) of a single-phase plan in one launch: the bias gradient (column sums of dZ) rides on the wgrad
+    kernel's tensor-core pass instead of a separate sweep over dZ."""
+    dw, db = ops.mtgemm_wgrad(plan, a0, dz, n_total, a1=a1, bias=True)
+    return dw, db[0]
 
 
 def _flat(x: Tensor) -> Tensor:
@@ -73,12 +76,10 @@ class ResBlockFn(Fn):
         dout = dout.contiguous()
         B, H, W, C = x.shape
         dplan = T.plan_conv3x3_dgrad(C)
-        dc2b = _colsum(dout)
-        dw2 = ops.mtgemm_wgrad(T.plan_conv3x3(C), h2, dout, C)
+        dw2, dc2b = _wgrad_b(T.plan_conv3x3(C), h2, dout, C)
         dh2 = ops.mtgemm(dplan, dout, _tr(w2p, 9), out_shape=(B, H, W, C))
         dh1, dg2, db2 = ops.groupnorm_bwd(h1, dh2, s2, g2, b2)
-        dc1b = _colsum(dh1)
-        dw1 = ops.mtgemm_wgrad(T.plan_conv3x3(C), h0, dh1, C)
+        dw1, dc1b = _wgrad_b(T.plan_conv3x3(C), h0, dh1, C)
         dh0 = ops.mtgemm(dplan, dh1, _tr(w1p, 9), out_shape=(B, H, W, C))
         dx, dg1, db1 = ops.groupnorm_bwd(x, dh0, s1, g1, b1, add=dout)
         return dx, dg1, db1, dw1, dc1b, dg2, db2, dw2, dc2b
@@ -103,8 +104,7 @@ class DownsampleFn(Fn):
         dout = dout.contiguous()
         B, H, W, C = x.shape
         N = wdp.shape[0]
-        dbd = _colsum(dout)
-        dwd = ops.mtgemm_wgrad(T.plan_downsample(C), y, dout, N, a1=x)
+        dwd, dbd = _wgrad_b(T.plan_downsample(C), y, dout, N, a1=x)
         dy = ops.mtgemm(T.plan_downsample_dgrad_main(C, N), dout, _tr(wdp[:, :9 * C], 9), out_shape=(B, H, W, C))
         dx_dc = ops.mtgemm(T.plan_downsample_dgrad_dc(C, N), dout, _tr(wdp[:, 9 * C:], 4), out_shape=(B, H, W, C))
         dz0, db0 = ops.bias_act_bwd(dy, z0, ACT_SILU)
@@ -133,9 +133,7 @@ class UpsampleFn(Fn):
         dout = dout.contiguous()
         B, H, W, Ci = x.shape
         Co = w1p.shape[0]
-        _, cs = ops.bias_act_bwd(dout, None, ACT_NONE, phase_view=True)       # [2, 2, Co] per output phase
-        db2p = cs.reshape(4, Co)
-        dw2 = ops.mtgemm_wgrad(T.plan_upsample_conv2(Co, Ci), y, dout, Co, a1=x)
+        dw2, db2p = ops.mtgemm_wgrad(T.plan_upsample_conv2(Co, Ci), y, dout, Co, a1=x, bias=True)   # db per output phase [4, Co]
         dy = ops.mtgemm(T.plan_conv3x3_dgrad(Co), dout, _tr(w2p[:, :9 * Co], 9), out_shape=(B, 2 * H, 2 * W, Co))
         dx_dc = ops.mtgemm(T.plan_upsample_dc_dgrad(Co), dout, _tr(w2p[:, 9 * Co:], 4), out_shape=(B, H, W, Ci))
         dz1, db1 = ops.bias_act_bwd(dy, z1, ACT_SILU)
@@ -169,13 +167,11 @@ class AttnFn(Fn):
         B, H, W, C = x.shape
         S = H * W
         df = _flat(dout)
-        dbp = _colsum(df)
-        dwp = ops.mtgemm_wgrad(T.plan_linear(C), _flat(o), df, C)
+        dwp, dbp = _wgrad_b(T.plan_linear(C), _flat(o), df, C)
         do = ops.mtgemm(T.plan_linear(C), df, _bf(wproj.detach().t()), out_shape=(1, 1, B * S, C))
         dqkv = ops.attn_bwd(qkv.view(B, S, 3 * C), o, do.view(B, S, C), lse, rope_tab, B, S, C, H, W, ctx.scale)
         dq = _flat(dqkv)
-        dbq = _colsum(dq)
-        dwq = ops.mtgemm_wgrad(T.plan_linear(C), _flat(xh), dq, 3 * C)
+        dwq, dbq = _wgrad_b(T.plan_linear(C), _flat(xh), dq, 3 * C)
         dxh = ops.mtgemm(T.plan_linear(3 * C), dq, _bf(wqkv.detach().t()), out_shape=(1, 1, B * S, C))
         dx, dw1 = ops.token_norm_bwd(x, w1, dxh.view(B, H, W, C), dout, 1)
         return dx, dw1, dwq, dbq, dwp, dbp, None, None
@@ -209,11 +205,9 @@ class FfnFn(Fn):
         M = B * H * W
         hid, mid = win.shape[0], wc0.shape[0]
         df = _flat(dout)
-        dbout = _colsum(df)
-        dwout = ops.mtgemm_wgrad(T.plan_linear(hid), u2, df, C)
+        dwout, dbout = _wgrad_b(T.plan_linear(hid), u2, df, C)
         du2 = ops.mtgemm(T.plan_linear(C), df, _bf(wout.detach().t()), out_shape=(1, 1, M, hid))
-        dbc4 = _colsum(du2)
-        dwc4 = ops.mtgemm_wgrad(T.plan_linear(mid), _flat(t2), du2, hid)
+        dwc4, dbc4 = _wgrad_b(T.plan_linear(mid), _flat(t2), du2, hid)
         dt2 = ops.mtgemm(T.plan_linear(hid), du2, _bf(wc4.detach().t()), out_shape=(1, 1, M, mid))
         dz2, dbc2 = ops.bias_act_bwd(dt2, z2.view(1, 1, M, mid), ACT_GELU)
         dz2i = dz2.view(B, H, W, mid)
@@ -260,8 +254,7 @@ class Conv3x3Fn(Fn):
         dout = dout.contiguous()
         B, H, W, C = xn.shape
         N = wp.shape[0]
-        db = _colsum(dout)
-        dw = ops.mtgemm_wgrad(T.plan_conv3x3(C), xn, dout, N)
+        dw, db = _wgrad_b(T.plan_conv3x3(C), xn, dout, N)
         dx = ops.mtgemm(T.plan_conv3x3_dgrad(N), dout, _tr(wp, 9), out_shape=(B, H, W, C)) if ctx.needs_input_grad[0] else None
         return dx, dw, db
 
@@ -284,8 +277,7 @@ class HeadFn(Fn):
         B, H, W, C = h.shape
         npad = wp.shape[0]
         dz = ops.nchw_to_nhwc(dout.float().contiguous(), npad)      # zero-padded channels
-        db = _colsum(dz)
-        dw = ops.mtgemm_wgrad(T.plan_conv3x3(C), h, dz, npad)
+        dw, db = _wgrad_b(T.plan_conv3x3(C), h, dz, npad)
         dh = ops.mtgemm(T.plan_conv3x3_dgrad(npad), dz, _tr(wp, 9), out_shape=(B, H, W, C))
         return dh, dw, db, None
 

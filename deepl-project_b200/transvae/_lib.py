@@ -66,6 +66,7 @@ _PROTOS = {
     "tvae_loss_l1_kl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                   C.c_int32, C.c_float, C.c_float, C.c_void_p]),
     "tvae_mtgemm_wgrad": (C.c_int, [C.POINTER(MtGemmDesc), C.c_void_p, C.c_void_p]),
+    "tvae_mtgemm_wgrad_bias": (C.c_int, [C.POINTER(MtGemmDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "tvae_bias_act_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                     C.c_void_p]),
     "tvae_bias_act_bwd_4d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,

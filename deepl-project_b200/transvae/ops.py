@@ -308,9 +308,10 @@ def loss_sums(recon: Tensor, target: Tensor, mu: Tensor, logvar: Tensor, patched
 # ------------------------------------------------------------------------------------------------
 # backward pass
 # ------------------------------------------------------------------------------------------------
-def mtgemm_wgrad(plan: Plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[Tensor] = None) -> Tensor:
+def mtgemm_wgrad(plan: Plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[Tensor] = None, bias: bool = False):
     """dW [n_total, k_total] fp32 of the forward ``mtgemm(plan, a0, w, a1=a1)`` given dZ (the gradient w.r.t. its
-    pre-activation output, same NHWC bf16 layout / view as the forward output)."""
+    pre-activation output, same NHWC bf16 layout / view as the forward output).  ``bias=True`` also returns the bias
+    gradient fp32 [num_phases, n_total] (per-phase column sums of dZ), produced by the same launch."""
     _need_cuda(a0, dz, a1)
     d = MtGemmDesc()
     _set_view(d.a0, a0, plan.a0_split)
@@ -319,16 +320,21 @@ def mtgemm_wgrad(plan: Plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[
     _fill_taps(d, plan)
     d.n_total, d.k_total = n_total, plan.k_total
     dw = torch.zeros(n_total, plan.k_total, dtype=torch.float32, device=a0.device)
+    db = torch.zeros(plan.num_phases, n_total, dtype=torch.float32, device=a0.device) if bias else None
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _lib.check(_lib.load().tvae_mtgemm_wgrad(C.byref(d), dw.data_ptr(), _stream()), f"tvae_mtgemm_wgrad[{plan.name}]")
+    if bias:
+        _lib.check(_lib.load().tvae_mtgemm_wgrad_bias(C.byref(d), dw.data_ptr(), db.data_ptr(), _stream()),
+                   f"tvae_mtgemm_wgrad_bias[{plan.name}]")
+    else:
+        _lib.check(_lib.load().tvae_mtgemm_wgrad(C.byref(d), dw.data_ptr(), _stream()), f"tvae_mtgemm_wgrad[{plan.name}]")
     if PROFILE is not None:
         e1.record()
         m_out = dz.numel() // dz.shape[-1]
         PROFILE.append((f"wgrad {plan.name} M={m_out} N={n_total} K={plan.k_total}", 2.0 * m_out * n_total * plan.algo_k, e0, e1))
     _count(2)
-    return dw
+    return (dw, db) if bias else dw
 
 
 def bias_act_bwd(dy: Tensor, z: Optional[Tensor], act: int, phase_view: bool = False) -> Tuple[Tensor, Tensor]:

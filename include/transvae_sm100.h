@@ -144,6 +144,10 @@ int tvae_metrics(const float* recon, const float* target, float* acc, int32_t B,
  * [n_total, k_total], accumulated into (caller zeroes).  Replaces autograd's weight-gradient convolution / matmul for
  * every nn.Conv2d / nn.Linear listed at tvae_mtgemm.  Input gradients are tvae_mtgemm launches with transposed taps. */
 int tvae_mtgemm_wgrad(const tvae_mtgemm_desc* desc /* HOST pointer */, float* dw, void* stream);
+/* Same, and the bias gradient in the same launch: db fp32 [num_phases, n_total] += per-phase column sums of dZ (an extra
+ * N = 16 tcgen05.mma against a block of ones on the CTAs of each phase's first tap).  Replaces the bias half of autograd
+ * for the same layers (a separate pass over dZ otherwise). */
+int tvae_mtgemm_wgrad_bias(const tvae_mtgemm_desc* desc /* HOST pointer */, float* dw, float* db, void* stream);
 /* dZ = dY * act'(Z) and colsum[n] = sum_m dZ[m, n] (= bias gradient) for a row-major bf16 [M, N] matrix.
  * act == TVAE_ACT_NONE: z / dz may be NULL, only the column sums are produced. */
 int tvae_bias_act_bwd(const void* dy, const void* z, void* dz, float* colsum, int64_t M, int32_t N, int32_t act,

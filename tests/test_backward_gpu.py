@@ -51,6 +51,10 @@ def test_linear_backward(M, K, N):
     assert rel(dx, gx) < 1e-2
     dw = ops.mtgemm_wgrad(T.plan_linear(K), x.reshape(1, 1, M, K), dz.reshape(1, 1, M, N), N)
     assert rel(dw, gw) < 2e-3, rel(dw, gw)
+    # bias gradient fused into the same launch (dZ^T x ones on the tensor core)
+    dw2, db = ops.mtgemm_wgrad(T.plan_linear(K), x.reshape(1, 1, M, K), dz.reshape(1, 1, M, N), N, bias=True)
+    assert torch.equal(dw2, dw) or rel(dw2, dw) < 1e-5
+    assert db.shape == (1, N) and rel(db[0], dz.float().sum(0)) < 1e-4, rel(db[0], dz.float().sum(0))
 
 
 @pytest.mark.parametrize("B,C,H,W,N", [(2, 64, 16, 16, 64), (1, 192, 128, 128, 192), (3, 128, 32, 32, 256), (2, 64, 8, 8, 128)])
@@ -59,8 +63,9 @@ def test_conv3x3_backward(B, C, H, W, N):
     gx, gw = grads(lambda x, w: F.conv2d(x, w, padding=1), [x, w], dz)
     dx = ops.mtgemm(T.plan_conv3x3_dgrad(N), nhwc(dz), bf(T.pack_conv3x3_dgrad(w.float())).contiguous(), out_shape=(B, H, W, C))
     assert rel(nchw(dx), gx) < 1e-2
-    dw = ops.mtgemm_wgrad(T.plan_conv3x3(C), nhwc(x), nhwc(dz), N)
+    dw, db = ops.mtgemm_wgrad(T.plan_conv3x3(C), nhwc(x), nhwc(dz), N, bias=True)
     assert rel(dw, T.pack_conv3x3(gw)) < 2e-3, rel(dw, T.pack_conv3x3(gw))
+    assert rel(db[0], dz.float().sum(dim=(0, 2, 3))) < 1e-4
 
 
 @pytest.mark.parametrize("B,C,N,H", [(2, 64, 128, 16), (1, 192, 192, 64)])
@@ -75,8 +80,9 @@ def test_downsample_backward(B, C, N, H):
     assert rel(nchw(dy), gy) < 1e-2
     dx = ops.mtgemm(T.plan_downsample_dgrad_dc(C, N), dzn, bf(T.pack_downsample_dgrad_dc(wdc.float())).contiguous(), out_shape=(B, H, H, C))
     assert rel(nchw(dx), gx) < 1e-2
-    dw = ops.mtgemm_wgrad(T.plan_downsample(C), nhwc(y), dzn, N, a1=nhwc(x))
+    dw, db = ops.mtgemm_wgrad(T.plan_downsample(C), nhwc(y), dzn, N, a1=nhwc(x), bias=True)
     assert rel(dw, T.pack_downsample(gw2, gwdc)) < 2e-3
+    assert rel(db[0], dz.float().sum(dim=(0, 2, 3))) < 1e-4
 
 
 @pytest.mark.parametrize("B,Ci,Co,H", [(2, 128, 64, 8), (1, 192, 192, 32)])
@@ -89,7 +95,10 @@ def test_upsample_backward(B, Ci, Co, H):
     dx = ops.mtgemm(T.plan_upsample_conv1_dgrad(Ci, Co), nhwc(dz1), bf(T.pack_upsample_conv1_dgrad(w1.float())).contiguous(),
                     out_shape=(B, H, H, Ci))
     assert rel(nchw(dx), gx) < 2e-2     # summed taps are re-rounded to bf16
-    dwp = ops.mtgemm_wgrad(T.plan_upsample_conv1(Ci, Co), nhwc(x), nhwc(dz1), Co)
+    dwp, dbp = ops.mtgemm_wgrad(T.plan_upsample_conv1(Ci, Co), nhwc(x), nhwc(dz1), Co, bias=True)
+    # four output phases (p, q): db[2p + q] = sum over pixels (2h + p, 2w + q); their total is the conv bias gradient
+    ph = dz1.float().view(B, Co, H, 2, H, 2).sum(dim=(0, 2, 4)).permute(1, 2, 0).reshape(4, Co)
+    assert rel(dbp, ph) < 1e-4, rel(dbp, ph)
     w1r = w1.float().clone().requires_grad_(True)
     (T.pack_upsample_conv1(w1r) * dwp).sum().backward()
     assert rel(w1r.grad, gw1) < 2e-3
@@ -99,8 +108,10 @@ def test_upsample_backward(B, Ci, Co, H):
     dx2 = ops.mtgemm(T.plan_upsample_dc_dgrad(Co), nhwc(dz2), bf(T.pack_upsample_dc_dgrad(wdc.float())).contiguous(),
                      out_shape=(B, H, H, Ci))
     assert rel(nchw(dx2), gx2) < 1e-2
-    dw2 = ops.mtgemm_wgrad(T.plan_upsample_conv2(Co, Ci), nhwc(y), nhwc(dz2), Co, a1=nhwc(x))
+    dw2, db2 = ops.mtgemm_wgrad(T.plan_upsample_conv2(Co, Ci), nhwc(y), nhwc(dz2), Co, a1=nhwc(x), bias=True)
     assert rel(dw2, T.pack_upsample_conv2(gw2, gwdc)) < 2e-3
+    ph2 = dz2.float().view(B, Co, H, 2, H, 2).sum(dim=(0, 2, 4)).permute(1, 2, 0).reshape(4, Co)
+    assert rel(db2, ph2) < 1e-4, rel(db2, ph2)
 
 
 def test_bias_act_bwd_and_act_fwd():
