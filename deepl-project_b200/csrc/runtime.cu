@@ -49,12 +49,12 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode(CUtensorMap* out, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   EncodeTiledFn fn = get_encode();
   TVAE_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   TVAE_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base address %p not 16-byte aligned", ptr);
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_b, box, estr,
+  CUresult r = fn(out, dtype, rank, const_cast<void*>(ptr), dims, strides_b, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -110,6 +110,15 @@ int make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, ui
   cuuint32_t box[3] = {64, box1, 1};
   TVAE_REQUIRE((stride1_elems * 2) % 16 == 0 && (stride2_elems * 2) % 16 == 0, "3-D TMA strides must be 16-byte multiples");
   return encode(out, ptr, 3, dims, str, box);
+}
+
+int make_tmap_3d_f32(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+                     uint64_t stride2_elems, uint32_t box1) {
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t str[2] = {stride1_elems * 4, stride2_elems * 4};
+  cuuint32_t box[3] = {32, box1, 1};
+  TVAE_REQUIRE((stride1_elems * 4) % 16 == 0 && (stride2_elems * 4) % 16 == 0, "3-D TMA strides must be 16-byte multiples");
+  return encode(out, ptr, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 
 }  // namespace tvae

@@ -22,4 +22,9 @@ int make_tmap_pix(CUtensorMap* out, const void* ptr, int B, int H, int W, int C,
 int make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
                  uint64_t stride2_elems, uint32_t box1);
 
+// 3-D fp32 tensor (d0 contiguous); box = (32, box1, 1) = 128 bytes wide, 128-byte swizzle.  Used for bulk reduce-add
+// (cp.reduce.async.bulk.tensor) of fp32 accumulator tiles.
+int make_tmap_3d_f32(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+                     uint64_t stride2_elems, uint32_t box1);
+
 }  // namespace tvae

@@ -20,3 +20,12 @@ for (S, C) in [(4096, 384), (1024, 768), (256, 1536)]:
     fl = 4.0 * B * S * S * C
     t = timeit(lambda: ops.attn_fwd(qkv, B, S, C, need_lse=True))
     print(f"attn_fwd B={B} S={S} C={C}: {t:.3f} ms  {fl / t / 1e9:.0f} TFLOP/s", flush=True)
+    if "--bwd" in sys.argv:
+        from transvae import _taps as T
+        H = W = int(math.isqrt(S))
+        inv = 1.0 / (10000 ** (torch.arange(0, 32, 2, device="cuda").float() / 32))
+        tab = T.rope_table(H, W, inv)
+        o, lse = ops.attn_fwd(qkv, B, S, C, need_lse=True)
+        do = torch.randn_like(o)
+        tb = timeit(lambda: ops.attn_bwd(qkv, o, do, lse, tab, B, S, C, H, W, 0.125))
+        print(f"attn_bwd B={B} S={S} C={C}: {tb:.3f} ms  {2.5 * fl / tb / 1e9:.0f} TFLOP/s (incl. delta + rope_bwd kernels)", flush=True)
