@@ -92,9 +92,11 @@ class DownsampleFn(Fn):
     def forward(ctx, x, w0p, b0, wdp, bd):
         B, H, W, C = x.shape
         N = wdp.shape[0]
+        dc = wdp.shape[1] == 13 * C            # [N, 9C] without the DC path (use_dc_path=False)
         z0 = ops.mtgemm(T.plan_conv3x3(C), x, _bf(w0p), out_shape=(B, H, W, C), bias=_f32(b0))
         y = ops.act_fwd(z0, ACT_SILU)
-        out = ops.mtgemm(T.plan_downsample(C), y, _bf(wdp), a1=x, out_shape=(B, H // 2, W // 2, N), bias=_f32(bd))
+        out = ops.mtgemm(T.plan_downsample(C, with_dc=dc), y, _bf(wdp), a1=x if dc else None,
+                         out_shape=(B, H // 2, W // 2, N), bias=_f32(bd))
         ctx.save_for_backward(x, z0, y, w0p, wdp)
         return out
 
@@ -104,9 +106,10 @@ class DownsampleFn(Fn):
         dout = dout.contiguous()
         B, H, W, C = x.shape
         N = wdp.shape[0]
-        dwd, dbd = _wgrad_b(T.plan_downsample(C), y, dout, N, a1=x)
+        dc = wdp.shape[1] == 13 * C
+        dwd, dbd = _wgrad_b(T.plan_downsample(C, with_dc=dc), y, dout, N, a1=x if dc else None)
         dy = ops.mtgemm(T.plan_downsample_dgrad_main(C, N), dout, _tr(wdp[:, :9 * C], 9), out_shape=(B, H, W, C))
-        dx_dc = ops.mtgemm(T.plan_downsample_dgrad_dc(C, N), dout, _tr(wdp[:, 9 * C:], 4), out_shape=(B, H, W, C))
+        dx_dc = ops.mtgemm(T.plan_downsample_dgrad_dc(C, N), dout, _tr(wdp[:, 9 * C:], 4), out_shape=(B, H, W, C)) if dc else None
         dz0, db0 = ops.bias_act_bwd(dy, z0, ACT_SILU)
         dw0 = ops.mtgemm_wgrad(T.plan_conv3x3(C), x, dz0, C)
         dx = ops.mtgemm(T.plan_conv3x3_dgrad(C), dz0, _tr(w0p, 9), out_shape=(B, H, W, C), residual=dx_dc)
@@ -121,9 +124,11 @@ class UpsampleFn(Fn):
         B, H, W, Ci = x.shape
         Co = w1p.shape[0]
         b1e = _f32(b1).unsqueeze(0).expand(4, -1).contiguous()
+        dc = w2p.shape[1] == 9 * Co + 4 * Ci   # [Co, 9 Co] without the DC path (use_dc_path=False)
         z1 = ops.mtgemm(T.plan_upsample_conv1(Ci, Co), x, _bf(w1p), out_shape=(B, 2 * H, 2 * W, Co), bias=b1e)
         y = ops.act_fwd(z1, ACT_SILU)
-        out = ops.mtgemm(T.plan_upsample_conv2(Co, Ci), y, _bf(w2p), a1=x, out_shape=(B, 2 * H, 2 * W, Co), bias=_f32(b2p))
+        out = ops.mtgemm(T.plan_upsample_conv2(Co, Ci, with_dc=dc), y, _bf(w2p), a1=x if dc else None,
+                         out_shape=(B, 2 * H, 2 * W, Co), bias=_f32(b2p))
         ctx.save_for_backward(x, z1, y, w1p, w2p)
         return out
 
@@ -133,9 +138,11 @@ class UpsampleFn(Fn):
         dout = dout.contiguous()
         B, H, W, Ci = x.shape
         Co = w1p.shape[0]
-        dw2, db2p = ops.mtgemm_wgrad(T.plan_upsample_conv2(Co, Ci), y, dout, Co, a1=x, bias=True)   # db per output phase [4, Co]
+        dc = w2p.shape[1] == 9 * Co + 4 * Ci
+        dw2, db2p = ops.mtgemm_wgrad(T.plan_upsample_conv2(Co, Ci, with_dc=dc), y, dout, Co, a1=x if dc else None,
+                                     bias=True)                                                # db per output phase [4, Co]
         dy = ops.mtgemm(T.plan_conv3x3_dgrad(Co), dout, _tr(w2p[:, :9 * Co], 9), out_shape=(B, 2 * H, 2 * W, Co))
-        dx_dc = ops.mtgemm(T.plan_upsample_dc_dgrad(Co), dout, _tr(w2p[:, 9 * Co:], 4), out_shape=(B, H, W, Ci))
+        dx_dc = ops.mtgemm(T.plan_upsample_dc_dgrad(Co), dout, _tr(w2p[:, 9 * Co:], 4), out_shape=(B, H, W, Ci)) if dc else None
         dz1, db1 = ops.bias_act_bwd(dy, z1, ACT_SILU)
         dw1 = ops.mtgemm_wgrad(T.plan_upsample_conv1(Ci, Co), x, dz1, Co)
         dx = ops.mtgemm(T.plan_upsample_conv1_dgrad(Ci, Co), dz1, _tr(w1p, 16), out_shape=(B, H, W, Ci), residual=dx_dc)

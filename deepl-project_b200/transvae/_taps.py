@@ -72,15 +72,18 @@ def _s2(d: int) -> Tuple[int, int]:
     return ((d - 1) % 2, (d - 1) // 2)
 
 
-def plan_downsample(c: int) -> Plan:
+def plan_downsample(c: int, with_dc: bool = True) -> Plan:
     """Downsample (upsample.py:55-66): conv3x3 s2 over map 0 (= silu(conv3x3(x))) + 1x1 conv over
-    pixel_unshuffle(x) (map 1), both as phase views of [B, H, W, c]; one accumulator, plain output."""
+    pixel_unshuffle(x) (map 1), both as phase views of [B, H, W, c]; one accumulator, plain output.
+    ``with_dc=False``: the main path only (use_dc_path=False, upsample.py:40-42)."""
     taps = []
     for dy in range(3):
         p, dh = _s2(dy)
         for dx in range(3):
             q, dw = _s2(dx)
             taps.append(TapSpec(0, q * c, dw, p, dh, _kb(c), (dy * 3 + dx) * c))
+    if not with_dc:
+        return Plan([taps], [0], [0], a0_split=True, k_total=9 * c, name="downsample", algo_k=9 * c)
     for i in range(2):
         for j in range(2):
             taps.append(TapSpec(1, j * c, 0, i, 0, _kb(c), (9 + i * 2 + j) * c))
@@ -153,9 +156,12 @@ def pack_conv1x1(w: Tensor) -> Tensor:
     return w.reshape(w.shape[0], w.shape[1])
 
 
-def pack_downsample(w_s2: Tensor, w_dc: Tensor) -> Tensor:
+def pack_downsample(w_s2: Tensor, w_dc: Optional[Tensor]) -> Tensor:
     """[O, 13*C]: 9 conv taps then the 4 pixel_unshuffle slabs.  pixel_unshuffle channel order is c*4+i*2+j
-    (SURVEY 8 a14); the phase view delivers (i, j, c), so dc_conv's input channels are permuted here."""
+    (SURVEY 8 a14); the phase view delivers (i, j, c), so dc_conv's input channels are permuted here.
+    ``w_dc=None`` (no DC path): [O, 9*C]."""
+    if w_dc is None:
+        return pack_conv3x3(w_s2)
     o, c = w_s2.shape[0], w_s2.shape[1]
     dc = w_dc.reshape(o, c, 2, 2).permute(0, 2, 3, 1).reshape(o, 4 * c)
     return torch.cat([pack_conv3x3(w_s2), dc], dim=1)

@@ -38,8 +38,6 @@ class FlashAttentionWithRoPE(HotModule):
         from .blocks import _LinearParams, _NormParams
         if head_dim != 64:
             raise NotImplementedError("the sm_100a attention kernel is specialised for head_dim 64 (every reference config)")
-        if not use_rope:
-            raise NotImplementedError("use_rope=False (ablation) is not built on the B200 path yet")
         self.dim, self.head_dim, self.num_heads = dim, head_dim, dim // head_dim
         self.scale = head_dim ** -0.5
         self.use_rope = use_rope
@@ -49,10 +47,21 @@ class FlashAttentionWithRoPE(HotModule):
         self.to_v = _LinearParams(dim, dim, bias=False)
         self.proj = _LinearParams(dim, dim)
         self.dropout = nn.Dropout(dropout)
-        self.rope = RoPE2D(head_dim)
+        if use_rope:                          # attention.py:50-53: no RoPE2D submodule (and no inv_freq buffer) otherwise
+            self.rope = RoPE2D(head_dim)
         self._rope_cache = {}
 
     def _rope_tab(self, H: int, W: int) -> torch.Tensor:
+        if not self.use_rope:
+            # identity rotation (cos 1, sin 0): the QKV epilogue and the attention backward then leave q, k untouched
+            dev = self.to_q.weight.device
+            key = (H, W, dev, -1)
+            tab = self._rope_cache.get(key)
+            if tab is None:
+                tab = torch.zeros(max(H, W), self.head_dim // 4, 2, dtype=torch.float32, device=dev)
+                tab[..., 0] = 1.0
+                self._rope_cache = {key: tab}
+            return tab
         key = (H, W, self.rope.inv_freq.device, self.rope.inv_freq._version)
         tab = self._rope_cache.get(key)
         if tab is None:

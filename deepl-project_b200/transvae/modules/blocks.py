@@ -116,7 +116,11 @@ class TransVAEBlock(HotModule):
                  use_conv_ffn: bool = True, dropout: float = 0.0):
         super().__init__()
         if not use_conv_ffn:
-            raise NotImplementedError("use_conv_ffn=False (plain FFN ablation) is not built on the B200 path yet")
+            # blocks.py:124-133 applies nn.Linear to the LAST axis of the NCHW tensor (blocks.py:149), so the reference
+            # itself raises "mat1 and mat2 shapes cannot be multiplied" for every shipped shape: there is no behaviour
+            # to reproduce (oracle/validate_against_reference.py records this)
+            raise NotImplementedError("use_conv_ffn=False is not functional in the reference (its nn.Sequential FFN is "
+                                      "applied along W of an NCHW tensor and fails); nothing to mirror")
         if dropout != 0.0:
             raise NotImplementedError("dropout > 0 is not used by any shipped config and is not built")
         self.dim, self.mlp_ratio = dim, mlp_ratio

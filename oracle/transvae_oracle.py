@@ -73,16 +73,33 @@ def normalise_config(cfg: dict) -> dict:
     out.setdefault("head_dim", 64)
     out.setdefault("latent_dim", 32)
     out.setdefault("input_channels", 3)
+    # ablation switches of the reference constructor (transvae.py:36-38); defaults = the shipped configs
+    out.setdefault("use_rope", True)
+    out.setdefault("use_conv_ffn", True)
+    out.setdefault("use_dc_path", True)
     return out
 
 
 # ----------------------------------------------------------------------------
 # parameter inventory: key -> shape, in the reference's state_dict naming
 # ----------------------------------------------------------------------------
-def _block_shapes(prefix: str, dim: int, mlp_ratio: float, head_dim: int) -> List[Tuple[str, Tuple[int, ...], str]]:
+def _block_shapes(prefix: str, dim: int, mlp_ratio: float, head_dim: int, use_rope: bool = True,
+                  use_conv_ffn: bool = True) -> List[Tuple[str, Tuple[int, ...], str]]:
     hid = int(dim * mlp_ratio * 4)
     mid = int(dim * mlp_ratio)
     p = prefix
+    out = _block_shapes_full(p, dim, hid, mid, head_dim)
+    if not use_rope:                       # attention.py:50-53: no RoPE2D submodule, hence no inv_freq buffer
+        out = [e for e in out if not e[0].endswith("attn.rope.inv_freq")]
+    if not use_conv_ffn:                   # blocks.py:124-133: nn.Sequential(Linear, GELU, Dropout, Linear, Dropout)
+        out = [e for e in out if ".ffn." not in e[0]]
+        h2 = int(dim * mlp_ratio)
+        out += [(p + "ffn.0.weight", (h2, dim), "linear"), (p + "ffn.0.bias", (h2,), "bias"),
+                (p + "ffn.3.weight", (dim, h2), "linear"), (p + "ffn.3.bias", (dim,), "bias")]
+    return out
+
+
+def _block_shapes_full(p: str, dim: int, hid: int, mid: int, head_dim: int) -> List[Tuple[str, Tuple[int, ...], str]]:
     return [
         (p + "norm1.weight", (dim,), "norm_w"),
         (p + "attn.norm_q.weight", (dim,), "norm_w"), (p + "attn.norm_q.bias", (dim,), "bias"),
@@ -120,20 +137,22 @@ def param_shapes(cfg: dict) -> List[Tuple[str, Tuple[int, ...], str]]:
     cfg = normalise_config(cfg)
     depths, dims = cfg["depths"], cfg["base_dims"]
     mr, hd, d, cin = cfg["mlp_ratio"], cfg["head_dim"], cfg["latent_dim"], cfg["input_channels"]
+    rope, cffn, dc = cfg["use_rope"], cfg["use_conv_ffn"], cfg["use_dc_path"]
     n = len(depths)
     out: List[Tuple[str, Tuple[int, ...], str]] = []
     out += [("encoder.conv_in.weight", (dims[0], cin, 3, 3), "conv"), ("encoder.conv_in.bias", (dims[0],), "bias")]
     for i in range(n):
         for j in range(depths[i]):
             p = f"encoder.stages.{i}.{j}."
-            out += _resblock_shapes(p, dims[i], dims[i]) if i < 2 else _block_shapes(p, dims[i], mr, hd)
+            out += _resblock_shapes(p, dims[i], dims[i]) if i < 2 else _block_shapes(p, dims[i], mr, hd, rope, cffn)
     for i in range(n - 1):
         p = f"encoder.downsamples.{i}."
         out += [
             (p + "main_path.0.weight", (dims[i], dims[i], 3, 3), "conv"), (p + "main_path.0.bias", (dims[i],), "bias"),
             (p + "main_path.2.weight", (dims[i + 1], dims[i], 3, 3), "conv"), (p + "main_path.2.bias", (dims[i + 1],), "bias"),
-            (p + "dc_conv.weight", (dims[i + 1], dims[i] * 4, 1, 1), "conv"), (p + "dc_conv.bias", (dims[i + 1],), "bias"),
         ]
+        if dc:
+            out += [(p + "dc_conv.weight", (dims[i + 1], dims[i] * 4, 1, 1), "conv"), (p + "dc_conv.bias", (dims[i + 1],), "bias")]
     out += [("conv_mu.weight", (d, dims[-1], 3, 3), "conv"), ("conv_mu.bias", (d,), "bias"),
             ("conv_logvar.weight", (d, dims[-1], 3, 3), "conv"), ("conv_logvar.bias", (d,), "bias")]
     rd, rdep = dims[::-1], depths[::-1]
@@ -141,14 +160,15 @@ def param_shapes(cfg: dict) -> List[Tuple[str, Tuple[int, ...], str]]:
     for i in range(n):
         for j in range(rdep[i]):
             p = f"decoder.stages.{i}.{j}."
-            out += _block_shapes(p, rd[i], mr, hd) if i < n - 2 else _resblock_shapes(p, rd[i], rd[i])
+            out += _block_shapes(p, rd[i], mr, hd, rope, cffn) if i < n - 2 else _resblock_shapes(p, rd[i], rd[i])
     for i in range(n - 1):
         p = f"decoder.upsamples.{i}."
         out += [
             (p + "main_path.1.weight", (rd[i + 1], rd[i], 3, 3), "conv"), (p + "main_path.1.bias", (rd[i + 1],), "bias"),
             (p + "main_path.3.weight", (rd[i + 1], rd[i + 1], 3, 3), "conv"), (p + "main_path.3.bias", (rd[i + 1],), "bias"),
-            (p + "dc_conv.weight", (rd[i + 1] * 4, rd[i], 1, 1), "conv"), (p + "dc_conv.bias", (rd[i + 1] * 4,), "bias"),
         ]
+        if dc:
+            out += [(p + "dc_conv.weight", (rd[i + 1] * 4, rd[i], 1, 1), "conv"), (p + "dc_conv.bias", (rd[i + 1] * 4,), "bias")]
     out += [("decoder.norm_out.weight", (rd[-1],), "norm_w"), ("decoder.norm_out.bias", (rd[-1],), "bias"),
             ("decoder.conv_out.weight", (cin, rd[-1], 3, 3), "conv"), ("decoder.conv_out.bias", (cin,), "bias")]
     return out
@@ -255,7 +275,7 @@ def attention(sd: StateDict, p: str, x: Tensor, head_dim: int, use_rope: bool = 
     q = q.view(B, H * W, nh, head_dim).transpose(1, 2)
     k = k.view(B, H * W, nh, head_dim).transpose(1, 2)
     v = v.view(B, H * W, nh, head_dim).transpose(1, 2)
-    if use_rope:
+    if use_rope and (p + "rope.inv_freq") in sd:      # use_rope=False builds no RoPE2D module (attention.py:50-53)
         q = rope2d(q, H, W, sd[p + "rope.inv_freq"])
         k = rope2d(k, H, W, sd[p + "rope.inv_freq"])
     if trace is not None:
@@ -285,11 +305,21 @@ def conv_ffn(sd: StateDict, p: str, x: Tensor) -> Tensor:
     return o.transpose(1, 2).reshape(B, C, H, W)
 
 
+def plain_ffn(sd: StateDict, p: str, x: Tensor) -> Tensor:
+    """blocks.py:124-133 (use_conv_ffn=False): Linear -> GELU -> Linear applied to the LAST dimension of the NCHW tensor
+    exactly as the reference's nn.Sequential does (blocks.py:149) -- i.e. along W, which only type-checks when W == dim."""
+    h = F.gelu(F.linear(x, sd[p + "0.weight"], sd[p + "0.bias"]))
+    return F.linear(h, sd[p + "3.weight"], sd[p + "3.bias"])
+
+
 def transvae_block(sd: StateDict, p: str, x: Tensor, head_dim: int, trace: Optional[dict] = None) -> Tensor:
     """blocks.py:135-151."""
     a = attention(sd, p + "attn.", rmsnorm(x, sd[p + "norm1.weight"]), head_dim, trace=trace)
     x = x + a
-    f = conv_ffn(sd, p + "ffn.", rmsnorm(x, sd[p + "norm2.weight"]))
+    if (p + "ffn.proj_in.weight") in sd:
+        f = conv_ffn(sd, p + "ffn.", rmsnorm(x, sd[p + "norm2.weight"]))
+    else:
+        f = plain_ffn(sd, p + "ffn.", rmsnorm(x, sd[p + "norm2.weight"]))
     if trace is not None:
         trace[p + "attn_branch"], trace[p + "ffn_branch"] = a, f
     return x + f

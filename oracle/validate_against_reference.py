@@ -155,6 +155,31 @@ def main():
         print(f"  gradient parity over {len(list(ref_p.named_parameters()))} tensors: max|d|={worst:.3e}")
         assert worst == 0.0
 
+    # ablation switches of the constructor (transvae.py:36-38): use_rope=False and use_dc_path=False change the module
+    # tree and must stay bit-identical; use_conv_ffn=False is broken in the reference itself (nn.Linear along W of NCHW)
+    for flags in (dict(use_rope=False), dict(use_dc_path=False), dict(use_rope=False, use_dc_path=False)):
+        cfg = dict(MINI, **flags)
+        sda = O.init_state_dict(cfg, seed=4, mode="tamed")
+        ref = import_reference(REF_MAIN).TransVAE(config=MINI, variant="x", compression_ratio=16, latent_dim=32, **flags).eval()
+        assert list(ref.state_dict().keys()) == list(sda.keys()), flags
+        ref.load_state_dict(sda, strict=True)
+        xa = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(6))
+        with torch.no_grad():
+            mu_r, lv_r = ref.encode(xa)
+            rec_r = ref.decode(mu_r)
+            mu_o, lv_o = O.encode(sda, cfg, xa)
+            rec_o = O.decode(sda, cfg, mu_o)
+        check(f"ablation {flags} mu", mu_o, mu_r)
+        check(f"ablation {flags} logvar", lv_o, lv_r)
+        check(f"ablation {flags} recon", rec_o, rec_r)
+    try:
+        bad = import_reference(REF_MAIN).TransVAE(config=MINI, variant="x", compression_ratio=16, latent_dim=32, use_conv_ffn=False)
+        with torch.no_grad():
+            bad.encode(torch.rand(1, 3, 64, 64))
+        raise AssertionError("the reference was expected to fail with use_conv_ffn=False")
+    except RuntimeError as e:
+        print(f"  use_conv_ffn=False: the reference raises RuntimeError ({str(e)[:60]}...) -- nothing to mirror")
+
     # parameter counts and FLOP model vs SURVEY section 6 [measured] numbers
     for v, (f, d), want in [("tiny", (16, 32), 81.9e6), ("large", (16, 32), 1049.2e6), ("giant", (16, 32), 4837.3e6)]:
         n = O.count_params(O.variant_config(v, f, d))["total"]

@@ -113,3 +113,19 @@ def test_compute_entry_points_refuse_without_device():
     assert lib.tvae_device_ok() == 0
     rc = lib.tvae_attn_fwd(None, None, None, 1, 16, 64, None)
     assert rc != 0 and "no CPU fallback" in _lib.last_error()
+
+
+@pytest.mark.parametrize("flags", [dict(use_rope=False), dict(use_dc_path=False), dict(use_rope=False, use_dc_path=False)])
+def test_ablation_constructor_flags_match_reference_state_dict(flags):
+    """transvae.py:36-38: the ablation switches change the module tree (no rope.inv_freq buffer, no dc_conv); the key list
+    must be the one the reference builds (oracle.param_shapes is validated against it in validate_against_reference.py)."""
+    m = transvae.TransVAE(config=MINI, latent_dim=32, **flags)
+    want = O.init_state_dict(dict(MINI, **flags), seed=2)
+    assert list(m.state_dict().keys()) == list(want.keys())
+    assert all(tuple(v.shape) == tuple(want[k].shape) for k, v in m.state_dict().items())
+    m.load_state_dict(want, strict=True)
+
+
+def test_plain_ffn_ablation_is_rejected_like_the_reference():
+    with pytest.raises(NotImplementedError, match="not functional in the reference"):
+        transvae.TransVAE(config=MINI, latent_dim=32, use_conv_ffn=False)

@@ -9,6 +9,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+import transvae  # noqa: E402
 import transvae_oracle as O  # noqa: E402
 from util import build_model, load_golden, nchw_f32, nhwc_bf16, rel  # noqa: E402
 
@@ -192,3 +193,43 @@ def test_ragged_resolutions_and_batches_vs_oracle(shape):
     ref = O.loss_l1_kl(rec_p, x, mu_p, lv_p, 1.0, 1e-8, patched=True)
     assert abs(float(loss["total"].detach()) - float(ref["total"])) < 1e-2
     assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+@pytest.mark.parametrize("flags", [dict(use_rope=False), dict(use_dc_path=False), dict(use_rope=False, use_dc_path=False)])
+def test_ablation_variants_forward_and_backward(flags):
+    """use_rope=False / use_dc_path=False (transvae.py:36-38) against the oracle (bit-identical to the
+    reference for these flags, oracle/validate_against_reference.py): encode / decode within the bf16 block tolerance
+    accumulated over the mini model, PSNR within 0.05 dB, and a training step whose gradients are finite and close."""
+    cfg = dict(depths=[1, 1, 1, 1, 2], base_dims=[64, 64, 64, 128, 128], mlp_ratio=1.0, head_dim=64, latent_dim=32, **flags)
+    sd = O.init_state_dict(cfg, seed=2, mode="tamed")
+    m = build_model(cfg, sd)
+    x = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        mu, lv = m.encode(x.cuda())
+        rec = m.decode(mu)
+        mu_o, lv_o = O.encode(sd, cfg, x)
+        rec_o = O.decode(sd, cfg, mu_o)
+        rec_same_z = O.decode(sd, cfg, mu.float().cpu())
+    assert rel(mu, mu_o) < 5e-2 and rel(lv, lv_o) < 5e-2, (rel(mu, mu_o), rel(lv, lv_o))
+    assert rel(rec, rec_same_z) < 5e-2, rel(rec, rec_same_z)
+    for f in (lambda t: t.clamp(0, 1), torch.sigmoid):
+        assert abs(O.psnr(f(rec.float().cpu()), x) - O.psnr(f(rec_o), x)) < 0.05
+    # training path
+    m.train()
+    eps = torch.randn(mu.shape, generator=torch.Generator().manual_seed(9))
+    r, mu_t, lv_t = m(x.cuda(), eps=eps.cuda())
+    loss = transvae.TransVAELoss(lpips_weight=0.0, vf_weight=0.0, gan_weight=0.0)(r, x.cuda(), mu_t, lv_t)["total"]
+    loss.backward()
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "inv_freq" not in k else v) for k, v in sd.items()}
+    ro, muo, lvo, _ = O.forward(sdg, cfg, x, eps, patched=True)
+    lo = O.loss_l1_kl(ro, x, muo, lvo, 1.0, 1e-8, patched=True)["total"]
+    lo.backward()
+    assert abs(float(loss) - float(lo)) < 5e-3
+    cos = []
+    for k, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        g, go = p.grad.float().cpu().flatten(), sdg[k].grad.flatten()
+        if float(go.norm()) > 0:
+            cos.append(float(torch.dot(g, go) / (g.norm() * go.norm()).clamp_min(1e-30)))
+    cos.sort()
+    assert cos[len(cos) // 2] > 0.9, cos[len(cos) // 2]      # median direction agreement (L1 sign noise, see DESIGN 2)

@@ -27,7 +27,9 @@ def load_golden(name):
 
 def build_model(cfg, sd, device="cuda", patched=True):
     with torch.device("meta"):
-        m = transvae.TransVAE(config=cfg, latent_dim=cfg.get("latent_dim", 32), patched=patched)
+        m = transvae.TransVAE(config=cfg, latent_dim=cfg.get("latent_dim", 32), patched=patched,
+                              use_rope=cfg.get("use_rope", True), use_conv_ffn=cfg.get("use_conv_ffn", True),
+                              use_dc_path=cfg.get("use_dc_path", True))
     m = m.to_empty(device=device)
     m.load_state_dict(sd, strict=True)
     return m.eval()
