@@ -9,6 +9,8 @@
 // pixels"), accumulates it in TMEM over its whole loop and adds it to the fp32 dW matrix with vectorised
 // red.global.add at the end.  Replaces the weight-gradient half of autograd for every nn.Conv2d / nn.Linear the
 // forward kernel replaces (reference call sites: include/transvae_sm100.h, tvae_mtgemm).
+#include <cstdlib>
+
 #include "../../include/transvae_sm100.h"
 #include "common.cuh"
 #include "tmap.cuh"
@@ -38,6 +40,8 @@ struct WgParams {
   float* dw;
   float* db;                 // optional bias gradient [phases][n_total] (column sums of dZ), accumulated into
   int first_tap[TVAE_MAX_PHASES];   // index of the first tap of each phase (its k-tile-0 CTAs also produce db)
+  int num_phases;
+  int items_per_phase[TVAE_MAX_PHASES];   // transposed kernel: ceil((chunks + bias slot) / 2)
 };
 
 constexpr int kWgTile = 128 * 64 * 2;  // one [128 pixels x 64 channels] bf16 box
@@ -209,6 +213,208 @@ mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #endif
 }
 
+// -------------------------------------------------------------------------------------------------
+// Transposed variant for layers whose output-channel count is not a multiple of 128 (N = 64, 192: the ResBlock /
+// Downsample / Upsample convolutions at 192 channels and the 64-wide heads).
+//
+// The kernel above puts the n (output) channels on the MMA M dimension in tiles of 128, so N = 192 runs a second
+// tile that is half empty (25 % of the tensor work wasted, ResBlock wgrad ~720 TFLOP/s).  Here the roles are swapped:
+//   D[M = 2 x 64 k-channel chunks, N = all n channels] += [A_chunk0 | A_chunk1]^T (pixels x 128) . dZ (pixels x N)
+// and the two 64-row halves of an M tile are independent [128 pixels x 64 channels] smem tiles -- possibly of
+// DIFFERENT taps -- that the MN-major UMMA descriptor stitches together through its leading-dimension byte offset.
+// A phase with c chunks (taps x C_in / 64) needs ceil(c / 2) full-width MMAs instead of 2 x c half-empty ones.  The
+// bias gradient (dZ^T . 1) is one more "chunk" whose tile is a constant block of ones.
+// -------------------------------------------------------------------------------------------------
+template <int NT>
+struct WgtCfg {
+  static constexpr int kStageBytes = (2 + NT / 64) * kWgTile;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 4 ? 4 : (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = NT <= 64 ? 64 : (NT <= 128 ? 128 : 256);
+  static constexpr int kSmemBytes = kStages * kStageBytes + kWgTile /*ones*/ + 1024 + 128;
+};
+
+struct WgSlot {
+  int tap;      // index into P.taps, -1: ones (bias gradient), -2: empty
+  int chunk;    // 64-channel chunk within the tap
+};
+
+// slot s (0-based) of phase ph: chunks of its taps in order, then (optionally) the ones slot, then empty
+__device__ __forceinline__ WgSlot wgt_slot(const WgParams& P, int ph, int s) {
+  int t = P.first_tap[ph];
+  const int t_end = (ph + 1 < TVAE_MAX_PHASES && P.first_tap[ph + 1] > 0) ? P.first_tap[ph + 1] : P.ntaps;
+  for (; t < t_end; ++t) {
+    if (s < P.taps[t].kblocks) return WgSlot{t, s};
+    s -= P.taps[t].kblocks;
+  }
+  if (s == 0 && P.db != nullptr) return WgSlot{-1, 0};
+  return WgSlot{-2, 0};
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256, 1)
+mtwgrad_t_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ WgParams P) {
+#ifdef TVAE_DEVICE_OK
+  using Cfg = WgtCfg<NT>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_ones = smem + STAGES * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ones + kWgTile);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* acc_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmDZ);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  if (P.db != nullptr) {
+    for (int i = threadIdx.x; i < kWgTile / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3f803f80u;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- work item: (phase, pair of chunk slots) x pixel split
+  const int split = blockIdx.x % P.splits;
+  int item = blockIdx.x / P.splits;
+  int ph = 0;
+  for (; ph < P.num_phases; ++ph) {
+    if (item < P.items_per_phase[ph]) break;
+    item -= P.items_per_phase[ph];
+  }
+  const WgSlot s0 = wgt_slot(P, ph, 2 * item), s1 = wgt_slot(P, ph, 2 * item + 1);
+  const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
+  const int my_tiles = (m_tiles - split + P.splits - 1) / P.splits;
+  constexpr int kDzChunks = NT / 64;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int loaded = kDzChunks + (s0.tap >= 0 ? 1 : 0) + (s1.tap >= 0 ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int m_t = split + i * P.splits;
+        const int w0 = (m_t % P.tiles_w) * P.tw;
+        const int h0 = ((m_t / P.tiles_w) % P.tiles_h) * P.th;
+        const int b0 = (m_t / (P.tiles_w * P.tiles_h)) * P.nb;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], loaded * kWgTile);
+        uint8_t* s = smem + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int j = 0; j < kDzChunks; ++j)
+          tma_load_5d(s + j * kWgTile, &tmDZ, &full[stage], P.out_c_off[ph] + j * 64, w0, P.out_p[ph], h0, b0);
+        if (s0.tap >= 0) {     // (an item can consist of the ones slot alone)
+          const WgTap tp = P.taps[s0.tap];
+          tma_load_5d(s + kDzChunks * kWgTile, tp.map ? &tmA1 : &tmA0, &full[stage], tp.c_off + s0.chunk * 64, w0 + tp.dw, tp.p,
+                      h0 + tp.dh, b0);
+        }
+        if (s1.tap >= 0) {
+          const WgTap tp = P.taps[s1.tap];
+          tma_load_5d(s + (kDzChunks + 1) * kWgTile, tp.map ? &tmA1 : &tmA0, &full[stage], tp.c_off + s1.chunk * 64,
+                      w0 + tp.dw, tp.p, h0 + tp.dh, b0);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t dz_base = smem_u32(smem + stage * Cfg::kStageBytes);
+        // first 64-row half of the A operand: a tap chunk, or the block of ones when the bias slot stands alone;
+        // second half: the next tile (a tap chunk), the block of ones, or -- unpaired -- the first half again (ignored)
+        const uint32_t a_base = s0.tap >= 0 ? dz_base + kDzChunks * kWgTile : smem_u32(s_ones);
+        const uint32_t lbo = s1.tap >= 0 ? kWgTile : (s1.tap == -1 ? smem_u32(s_ones) - a_base : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // 16 pixels per MMA
+          umma_f16(tmem_base, umma_desc_mnmajor_sw128(a_base + k * 2048, lbo, 1024),
+                   umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024), idesc, (i | k) != 0);
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                 // M row of the accumulator = slot (row / 64), channel (row % 64)
+    const WgSlot sl = row < 64 ? s0 : s1;
+    if (my_tiles > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      float* dst = nullptr;
+      size_t stride = 0;
+      bool ok = false;
+      if (sl.tap >= 0) {                           // dW[n][wk_off + chunk * 64 + kk], consecutive lanes -> consecutive kk
+        dst = P.dw + P.taps[sl.tap].wk_off + sl.chunk * 64 + (row & 63);
+        stride = (size_t)P.k_total;
+        ok = true;
+      } else if (sl.tap == -1 && (row & 63) == 0) {   // all 64 rows of the ones slot hold the same column sums
+        dst = P.db + (size_t)ph * P.n_total;
+        stride = 1;
+        ok = true;
+      }
+#pragma unroll 1
+      for (int c = 0; c < NT / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)(c * 32 + j) * stride, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+#endif
+}
+
+template <int NT>
+static int launch_wgt(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& dz, const WgParams& P, int grid,
+                      cudaStream_t stream) {
+  using Cfg = WgtCfg<NT>;
+  static bool configured = false;
+  if (!configured) {
+    TVAE_CHECK_CUDA(cudaFuncSetAttribute(mtwgrad_t_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  mtwgrad_t_kernel<NT><<<grid, 256, Cfg::kSmemBytes, stream>>>(a0, a1, dz, P);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int pow2_ceil_w(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -270,8 +476,23 @@ int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, float* db, cudaStream_t st
     }
   }
   P.ntaps = nt;
+  P.num_phases = d->num_phases;
+  for (int ph = d->num_phases; ph < TVAE_MAX_PHASES; ++ph) P.first_tap[ph] = 0;
+  // N = 64 / 192: transposed kernel (no half-empty 128-row tiles); everything else: n channels on the M dimension
+  static const bool allow_t = !(getenv("TVAE_WGRAD_T") && atoi(getenv("TVAE_WGRAD_T")) == 0);
+  const bool transposed = allow_t && (d->n_total == 64 || d->n_total == 192);
   long long items = 0;
-  for (int i = 0; i < nt; ++i) items += (long long)(P.taps[i].kblocks * 64 / kt) * P.n_tiles;
+  if (transposed) {
+    for (int ph = 0; ph < d->num_phases; ++ph) {
+      int chunks = db != nullptr ? 1 : 0;
+      const int t_end = ph + 1 < d->num_phases ? P.first_tap[ph + 1] : nt;
+      for (int t = P.first_tap[ph]; t < t_end; ++t) chunks += P.taps[t].kblocks;
+      P.items_per_phase[ph] = (chunks + 1) / 2;
+      items += P.items_per_phase[ph];
+    }
+  } else {
+    for (int i = 0; i < nt; ++i) items += (long long)(P.taps[i].kblocks * 64 / kt) * P.n_tiles;
+  }
   const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
   int sms = num_sms();
   if (sms <= 0) sms = 148;
@@ -294,6 +515,10 @@ int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, float* db, cudaStream_t st
     mA1 = mA0;
   }
   if ((rc = make_tmap_pix(&mDZ, d->out.ptr, d->out.B, d->out.H, d->out.W, d->out.C, d->out.split, P.tw, P.th, P.nb))) return rc;
+  if (transposed) {
+    return d->n_total == 192 ? launch_wgt<192>(mA0, mA1, mDZ, P, (int)grid, stream)
+                             : launch_wgt<64>(mA0, mA1, mDZ, P, (int)grid, stream);
+  }
   switch (kt) {
     case 256: return launch_wg<256>(mA0, mA1, mDZ, P, (int)grid, stream);
     case 192: return launch_wg<192>(mA0, mA1, mDZ, P, (int)grid, stream);

@@ -195,12 +195,15 @@ def test_ragged_resolutions_and_batches_vs_oracle(shape):
     assert all(torch.isfinite(p.grad).all() for p in m.parameters())
 
 
-@pytest.mark.parametrize("flags", [dict(use_rope=False), dict(use_dc_path=False), dict(use_rope=False, use_dc_path=False)])
+@pytest.mark.parametrize("flags", [dict(use_rope=False), dict(use_dc_path=False), dict(use_rope=False, use_dc_path=False),
+                                   dict(depths=[1, 1, 1, 2], base_dims=[64, 64, 128, 128])])   # 4-stage (f8) layout
 def test_ablation_variants_forward_and_backward(flags):
-    """use_rope=False / use_dc_path=False (transvae.py:36-38) against the oracle (bit-identical to the
+    """use_rope=False / use_dc_path=False (transvae.py:36-38) and the 4-stage f8 layout
+    (transvae.py:141-146) against the oracle (bit-identical to the
     reference for these flags, oracle/validate_against_reference.py): encode / decode within the bf16 block tolerance
     accumulated over the mini model, PSNR within 0.05 dB, and a training step whose gradients are finite and close."""
-    cfg = dict(depths=[1, 1, 1, 1, 2], base_dims=[64, 64, 64, 128, 128], mlp_ratio=1.0, head_dim=64, latent_dim=32, **flags)
+    cfg = dict(depths=[1, 1, 1, 1, 2], base_dims=[64, 64, 64, 128, 128], mlp_ratio=1.0, head_dim=64, latent_dim=32)
+    cfg.update(flags)
     sd = O.init_state_dict(cfg, seed=2, mode="tamed")
     m = build_model(cfg, sd)
     x = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(8))

@@ -10,7 +10,9 @@ want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second", "sm__cycles_elapsed.max",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed.sum", "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct",
-        "smsp__cycles_active.avg"]
+        "smsp__cycles_active.avg", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.per_cycle_active", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum"]
 with open(out, "w") as f:
     f.write(f"# ncu --set full --clock-control none summary of {rep}\n")
     for r in rows[2:]:

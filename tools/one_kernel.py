@@ -1,0 +1,44 @@
+"""Run ONE hot kernel a few times at its BASELINE-size shape (for ncu --set full captures):
+    python tools/one_kernel.py conv192 | gn_apply | gn_bwd | attn_fwd | attn_bwd | wgrad192 | token_norm_bwd"""
+import math, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "deepl-project_b200"))
+import torch
+from transvae import ops, _taps as T
+
+which = sys.argv[1]
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+dev = "cuda"
+g = torch.Generator(device=dev).manual_seed(0)
+rnd = lambda *s: torch.randn(*s, device=dev, generator=g)
+if which in ("conv192", "wgrad192"):
+    x = rnd(B, 256, 256, 192).to(torch.bfloat16)
+    w = (rnd(192, 9 * 192) * 0.02).to(torch.bfloat16)
+    b = rnd(192)
+    dz = rnd(B, 256, 256, 192).to(torch.bfloat16)
+    fn = (lambda: ops.mtgemm(T.plan_conv3x3(192), x, w, out_shape=(B, 256, 256, 192), bias=b, residual=dz)) if which == "conv192" \
+        else (lambda: ops.mtgemm_wgrad(T.plan_conv3x3(192), x, dz, 192, bias=True))
+elif which in ("gn_apply", "gn_bwd"):
+    x = rnd(B, 256, 256, 192).to(torch.bfloat16)
+    dh = rnd(B, 256, 256, 192).to(torch.bfloat16)
+    ga, be = rnd(192), rnd(192)
+    s = ops.groupnorm_stats(x)
+    fn = (lambda: ops.groupnorm_silu(x, ga, be, sums=s)) if which == "gn_apply" else (lambda: ops.groupnorm_bwd(x, dh, s, ga, be, add=dh))
+elif which in ("attn_fwd", "attn_bwd"):
+    S, C = 4096, 384
+    qkv = (rnd(B, S, 3 * C) * 0.5).to(torch.bfloat16)
+    o, lse = ops.attn_fwd(qkv, B, S, C, need_lse=True)
+    do = torch.randn_like(o)
+    tab = T.rope_table(64, 64, 1.0 / (10000 ** (torch.arange(0, 32, 2, device=dev).float() / 32)))
+    fn = (lambda: ops.attn_fwd(qkv, B, S, C, need_lse=True)) if which == "attn_fwd" \
+        else (lambda: ops.attn_bwd(qkv, o, do, lse, tab, B, S, C, 64, 64, 0.125))
+elif which == "token_norm_bwd":
+    x, dy = rnd(B * 4096, 384).to(torch.bfloat16), rnd(B * 4096, 384).to(torch.bfloat16)
+    w = rnd(384)
+    fn = lambda: ops.token_norm_bwd(x, w, dy, dy, 1)
+else:
+    raise SystemExit(f"unknown kernel {which}")
+for _ in range(5):
+    fn()
+torch.cuda.synchronize()
+print("ok", which)
