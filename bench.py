@@ -270,8 +270,15 @@ def run_ours(args, rank, world, local):
     at = by.get("attn_fwd", [0.0, 1e-9, 0])
     step_ms_prof = sum(a.elapsed_time(b) for _, _, a, b in prof) / 2
     ach = gm[0] / (gm[1] * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "tvae::mtgemm_kernel (all conv / linear launches)", "achieved": ach,
-                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+    # DRAM traffic of the dominant launch shape from the committed ncu --set full capture (bytes per launch of that shape)
+    traffic, traffic_ref = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic_dominant_kernel.json")
+    if os.path.exists(tpath):
+        traffic_ref = json.load(open(tpath))
+        traffic = traffic_ref["dram_bytes"]
+    roofline = {"bound": "tensor", "kernel": "tvae::mtgemm2_kernel / mtgemm_kernel (all conv / linear launches)", "achieved": ach,
+                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": traffic,
+                "traffic_capture": traffic_ref,
                 "peak_source": pk["src"], "launches_per_step": gm[2] // 2, "ms_per_step_in_kernel": gm[1] / 2,
                 "share_of_step": gm[1] / 2 / (ms / args.steps),
                 "attention": {"achieved": at[0] / (at[1] * 1e-3) / 1e12, "unit": "TFLOP/s",
