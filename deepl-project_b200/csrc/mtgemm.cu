@@ -33,7 +33,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 #ifdef TVAE_DEVICE_OK
   using Cfg = MtCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::kStages;
-  constexpr bool kHasRes = (EPI == kEpiBiasRes || EPI == kEpiRsBias);
+  constexpr bool kHasRes = epi_has_res<EPI>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -188,12 +188,14 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const uint32_t acc_phase = (it >> 1) & 1;
 
       EpiRow R;
+      const __nv_bfloat16* zrow = nullptr;
       {
         const int wi = r % P.tw, hi = (r / P.tw) % P.th, bi = r / (P.tw * P.th);
         R.pw = w0 + wi; R.phh = h0 + hi; R.pb = b0 + bi;
         R.row_ok = (R.pw < P.vW) && (R.phh < P.vH) && (R.pb < P.vB);
         const long long grow = ((long long)R.pb * P.vH + R.phh) * P.vW + R.pw;  // flattened output-view pixel index
         R.rs = 1.0f; R.rsh = 0.0f; R.rope_r = 0; R.rope_c = 0;
+        if constexpr (EPI == kEpiResMulGeluGrad) zrow = P.z + (R.row_ok ? grow : 0) * P.n_total;
         if constexpr (EPI == kEpiRsBiasGelu || EPI == kEpiAffineRope || EPI == kEpiRsBias) {
           if (P.row_scale != nullptr && R.row_ok) R.rs = __ldg(P.row_scale + grow);
           if (P.row_shift != nullptr && R.row_ok) R.rsh = __ldg(P.row_shift + grow);
@@ -241,15 +243,8 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           if constexpr (kHasRes) {
             if (has_res) {
               const uint4 ra = *pa, rb = *pb;
-              float2 t;
-              t = unpack_bf16(ra.x); fa[0] += t.x; fa[1] += t.y;
-              t = unpack_bf16(ra.y); fa[2] += t.x; fa[3] += t.y;
-              t = unpack_bf16(ra.z); fa[4] += t.x; fa[5] += t.y;
-              t = unpack_bf16(ra.w); fa[6] += t.x; fa[7] += t.y;
-              t = unpack_bf16(rb.x); fb[0] += t.x; fb[1] += t.y;
-              t = unpack_bf16(rb.y); fb[2] += t.x; fb[3] += t.y;
-              t = unpack_bf16(rb.z); fb[4] += t.x; fb[5] += t.y;
-              t = unpack_bf16(rb.w); fb[6] += t.x; fb[7] += t.y;
+              epi_combine8<EPI>(fa, ra, zrow, n_base + c16 * 16);
+              epi_combine8<EPI>(fb, rb, zrow, n_base + c16 * 16 + 8);
             }
           }
           uint4 o;
@@ -395,6 +390,7 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
   P.q_scale = d->q_scale;
   P.out_f32 = d->out_f32;
   P.out_n = d->out_n;
+  P.z = reinterpret_cast<const __nv_bfloat16*>(d->z);
   TVAE_REQUIRE(!(direct && P.has_residual), "mtgemm: residual not supported with direct fp32 store");
 
   CUtensorMap mA0, mA1, mB, mO, mR;
@@ -420,7 +416,18 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
   // pick the compile-time epilogue variant
   const bool affine = d->row_scale != nullptr || d->row_shift != nullptr;
   int epi;
-  if (direct) {
+  if (d->act_grad != 0) {
+    TVAE_REQUIRE(!direct && !affine && d->bias == nullptr && d->rope_tab == nullptr && P.has_residual,
+                 "mtgemm: act_grad excludes bias / affine / rope / direct store and needs `res`");
+    if (d->act_grad == 1) {
+      TVAE_REQUIRE(d->act == TVAE_ACT_GELU || d->act == TVAE_ACT_SILU, "mtgemm: act_grad needs GELU or SiLU");
+      epi = d->act == TVAE_ACT_GELU ? kEpiMulGeluGrad : kEpiMulSiluGrad;
+    } else {
+      TVAE_REQUIRE(d->act_grad == 2 && d->act == TVAE_ACT_GELU && d->z != nullptr && !d->out.split,
+                   "mtgemm: act_grad 2 = (acc + res) * gelu'(z) on a plain output view");
+      epi = kEpiResMulGeluGrad;
+    }
+  } else if (direct) {
     TVAE_REQUIRE(!affine && d->act == TVAE_ACT_NONE && d->rope_tab == nullptr, "mtgemm: direct store supports bias only");
     epi = kEpiDirect;
   } else if (d->rope_tab != nullptr) {
@@ -453,6 +460,9 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
     case kEpiRsBiasGelu: return launch_n<kEpiRsBiasGelu>(block_n, mA0, mA1, mB, mO, mR, P, stream);
     case kEpiAffineRope: return launch_n<kEpiAffineRope>(block_n, mA0, mA1, mB, mO, mR, P, stream);
     case kEpiDirect: return launch_n<kEpiDirect>(block_n, mA0, mA1, mB, mO, mR, P, stream);
+    case kEpiMulGeluGrad: return launch_n<kEpiMulGeluGrad>(block_n, mA0, mA1, mB, mO, mR, P, stream);
+    case kEpiMulSiluGrad: return launch_n<kEpiMulSiluGrad>(block_n, mA0, mA1, mB, mO, mR, P, stream);
+    case kEpiResMulGeluGrad: return launch_n<kEpiResMulGeluGrad>(block_n, mA0, mA1, mB, mO, mR, P, stream);
     default: return launch_n<kEpiRsBias>(block_n, mA0, mA1, mB, mO, mR, P, stream);
   }
 }

@@ -89,7 +89,7 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #ifdef TVAE_DEVICE_OK
   using Cfg = Mt2Cfg<BLOCK_N>;
   constexpr int STAGES = Cfg::kStages;
-  constexpr bool kHasRes = (EPI == kEpiBiasRes || EPI == kEpiRsBias);
+  constexpr bool kHasRes = epi_has_res<EPI>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -244,12 +244,14 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t acc_phase = (it >> 1) & 1;
 
       EpiRow R;
+      const __nv_bfloat16* zrow = nullptr;
       {
         const int wi = r % P.tw, hi = (r / P.tw) % P.th, bi = r / (P.tw * P.th);
         R.pw = w0 + wi; R.phh = h0 + hi; R.pb = b0 + bi;
         R.row_ok = (R.pw < P.vW) && (R.phh < P.vH) && (R.pb < P.vB);
         const long long grow = ((long long)R.pb * P.vH + R.phh) * P.vW + R.pw;
         R.rs = 1.0f; R.rsh = 0.0f; R.rope_r = 0; R.rope_c = 0;
+        if constexpr (EPI == kEpiResMulGeluGrad) zrow = P.z + (R.row_ok ? grow : 0) * P.n_total;
         if constexpr (EPI == kEpiRsBiasGelu || EPI == kEpiAffineRope || EPI == kEpiRsBias) {
           if (P.row_scale != nullptr && R.row_ok) R.rs = __ldg(P.row_scale + grow);
           if (P.row_shift != nullptr && R.row_ok) R.rsh = __ldg(P.row_shift + grow);
@@ -296,15 +298,8 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if constexpr (kHasRes) {
             if (has_res) {
               const uint4 ra = *pa, rb = *pb;
-              float2 t;
-              t = unpack_bf16(ra.x); fa[0] += t.x; fa[1] += t.y;
-              t = unpack_bf16(ra.y); fa[2] += t.x; fa[3] += t.y;
-              t = unpack_bf16(ra.z); fa[4] += t.x; fa[5] += t.y;
-              t = unpack_bf16(ra.w); fa[6] += t.x; fa[7] += t.y;
-              t = unpack_bf16(rb.x); fb[0] += t.x; fb[1] += t.y;
-              t = unpack_bf16(rb.y); fb[2] += t.x; fb[3] += t.y;
-              t = unpack_bf16(rb.z); fb[4] += t.x; fb[5] += t.y;
-              t = unpack_bf16(rb.w); fb[6] += t.x; fb[7] += t.y;
+              epi_combine8<EPI>(fa, ra, zrow, n_base + c16 * 16);
+              epi_combine8<EPI>(fb, rb, zrow, n_base + c16 * 16 + 8);
             }
           }
           uint4 o;
@@ -393,6 +388,9 @@ int mtgemm2_dispatch(int epi, int block_n, const CUtensorMap& a0, const CUtensor
     case kEpiRsBiasGelu: return launch2_n<kEpiRsBiasGelu>(block_n, a0, a1, b, o, r, P, stream);
     case kEpiAffineRope: return launch2_n<kEpiAffineRope>(block_n, a0, a1, b, o, r, P, stream);
     case kEpiDirect: return launch2_n<kEpiDirect>(block_n, a0, a1, b, o, r, P, stream);
+    case kEpiMulGeluGrad: return launch2_n<kEpiMulGeluGrad>(block_n, a0, a1, b, o, r, P, stream);
+    case kEpiMulSiluGrad: return launch2_n<kEpiMulSiluGrad>(block_n, a0, a1, b, o, r, P, stream);
+    case kEpiResMulGeluGrad: return launch2_n<kEpiResMulGeluGrad>(block_n, a0, a1, b, o, r, P, stream);
     default: return launch2_n<kEpiRsBias>(block_n, a0, a1, b, o, r, P, stream);
   }
 }

@@ -38,6 +38,7 @@ struct MtParams {
   float* out_f32;
   int out_n;
   int vB, vH, vW;  // output view extents (pixels) for row indexing / bounds
+  const __nv_bfloat16* z;   // act_grad == 2: pre-activation matrix [M, n_total]
 };
 
 constexpr int kBlockM = 128;
@@ -68,7 +69,48 @@ enum Epi : int {
   kEpiAffineRope = 5,  // v = rope(rs[m] * acc - rsh[m] * cs[n] + bias)     (RMSNorm + LayerNorm folded into QKV)
   kEpiDirect = 6,      // fp32 NCHW direct store of acc + bias
   kEpiRsBias = 7,      // v = rs[m] * acc - rsh[m] * cs[n] + bias [+ residual] (generic, tests / bare modules)
+  // backward: the input-gradient GEMM applies the derivative of the producing layer's activation itself
+  kEpiMulGeluGrad = 8,     // v = acc * gelu'(z),          z tile staged like a residual
+  kEpiMulSiluGrad = 9,     // v = acc * silu'(z)
+  kEpiResMulGeluGrad = 10, // v = (acc + residual) * gelu'(z),  residual staged, z read from global memory
 };
+
+template <int EPI>
+__host__ __device__ constexpr bool epi_has_res() {
+  return EPI == kEpiBiasRes || EPI == kEpiRsBias || EPI == kEpiMulGeluGrad || EPI == kEpiMulSiluGrad || EPI == kEpiResMulGeluGrad;
+}
+
+// Combine 8 accumulator values with the 8 bf16 values of the staged tile (`r`): residual add, or multiplication by the
+// activation derivative; EPI 10 additionally reads the pre-activation from global memory (`zrow` -> this row, column n).
+template <int EPI>
+__device__ __forceinline__ void epi_combine8(float (&f)[8], const uint4& r, const __nv_bfloat16* zrow, int n) {
+  float2 t[4] = {bf16x2_to_f2(r.x), bf16x2_to_f2(r.y), bf16x2_to_f2(r.z), bf16x2_to_f2(r.w)};
+  if constexpr (EPI == kEpiMulGeluGrad || EPI == kEpiMulSiluGrad) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 g = EPI == kEpiMulGeluGrad ? gelu_grad2(t[k]) : silu_grad2(t[k]);
+      f[2 * k] *= g.x;
+      f[2 * k + 1] *= g.y;
+    }
+  } else if constexpr (EPI == kEpiResMulGeluGrad) {
+    const uint4 zu = __ldg(reinterpret_cast<const uint4*>(zrow + n));
+    const float2 z[4] = {bf16x2_to_f2(zu.x), bf16x2_to_f2(zu.y), bf16x2_to_f2(zu.z), bf16x2_to_f2(zu.w)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 g = gelu_grad2(z[k]);
+      f[2 * k] = (f[2 * k] + t[k].x) * g.x;
+      f[2 * k + 1] = (f[2 * k + 1] + t[k].y) * g.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      f[2 * k] += t[k].x;
+      f[2 * k + 1] += t[k].y;
+    }
+  }
+}
+
+enum : int { kEpiCount = 11 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"

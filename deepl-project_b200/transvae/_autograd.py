@@ -108,10 +108,11 @@ class DownsampleFn(Fn):
         N = wdp.shape[0]
         dc = wdp.shape[1] == 13 * C
         dwd, dbd = _wgrad_b(T.plan_downsample(C, with_dc=dc), y, dout, N, a1=x if dc else None)
-        dy = ops.mtgemm(T.plan_downsample_dgrad_main(C, N), dout, _tr(wdp[:, :9 * C], 9), out_shape=(B, H, W, C))
+        # dZ0 = dY * silu'(Z0) leaves the input-gradient GEMM directly (act_grad epilogue); its bias gradient rides on wgrad
+        dz0 = ops.mtgemm(T.plan_downsample_dgrad_main(C, N), dout, _tr(wdp[:, :9 * C], 9), out_shape=(B, H, W, C),
+                         act=ACT_SILU, act_grad_z=z0)
         dx_dc = ops.mtgemm(T.plan_downsample_dgrad_dc(C, N), dout, _tr(wdp[:, 9 * C:], 4), out_shape=(B, H, W, C)) if dc else None
-        dz0, db0 = ops.bias_act_bwd(dy, z0, ACT_SILU)
-        dw0 = ops.mtgemm_wgrad(T.plan_conv3x3(C), x, dz0, C)
+        dw0, db0 = _wgrad_b(T.plan_conv3x3(C), x, dz0, C)
         dx = ops.mtgemm(T.plan_conv3x3_dgrad(C), dz0, _tr(w0p, 9), out_shape=(B, H, W, C), residual=dx_dc)
         return dx, dw0, db0, dwd, dbd
 
@@ -141,10 +142,11 @@ class UpsampleFn(Fn):
         dc = w2p.shape[1] == 9 * Co + 4 * Ci
         dw2, db2p = ops.mtgemm_wgrad(T.plan_upsample_conv2(Co, Ci, with_dc=dc), y, dout, Co, a1=x if dc else None,
                                      bias=True)                                                # db per output phase [4, Co]
-        dy = ops.mtgemm(T.plan_conv3x3_dgrad(Co), dout, _tr(w2p[:, :9 * Co], 9), out_shape=(B, 2 * H, 2 * W, Co))
+        dz1 = ops.mtgemm(T.plan_conv3x3_dgrad(Co), dout, _tr(w2p[:, :9 * Co], 9), out_shape=(B, 2 * H, 2 * W, Co),
+                         act=ACT_SILU, act_grad_z=z1)
         dx_dc = ops.mtgemm(T.plan_upsample_dc_dgrad(Co), dout, _tr(w2p[:, 9 * Co:], 4), out_shape=(B, H, W, Ci)) if dc else None
-        dz1, db1 = ops.bias_act_bwd(dy, z1, ACT_SILU)
-        dw1 = ops.mtgemm_wgrad(T.plan_upsample_conv1(Ci, Co), x, dz1, Co)
+        dw1, db1p = ops.mtgemm_wgrad(T.plan_upsample_conv1(Ci, Co), x, dz1, Co, bias=True)
+        db1 = db1p.sum(0)                      # the forward bias is shared by the four output phases
         dx = ops.mtgemm(T.plan_upsample_conv1_dgrad(Ci, Co), dz1, _tr(w1p, 16), out_shape=(B, H, W, Ci), residual=dx_dc)
         return dx, dw1, db1, dw2, db2p
 
@@ -215,16 +217,18 @@ class FfnFn(Fn):
         dwout, dbout = _wgrad_b(T.plan_linear(hid), u2, df, C)
         du2 = ops.mtgemm(T.plan_linear(C), df, _bf(wout.detach().t()), out_shape=(1, 1, M, hid))
         dwc4, dbc4 = _wgrad_b(T.plan_linear(mid), _flat(t2), du2, hid)
-        dt2 = ops.mtgemm(T.plan_linear(hid), du2, _bf(wc4.detach().t()), out_shape=(1, 1, M, mid))
-        dz2, dbc2 = ops.bias_act_bwd(dt2, z2.view(1, 1, M, mid), ACT_GELU)
+        # every dZ = dY * gelu'(Z) of the block is produced by the epilogue of the GEMM that computes dY (act_grad), every
+        # bias gradient by the wgrad launch that consumes dZ: no separate pass over the [M, 4C] / [M, C] gradients
+        dz2 = ops.mtgemm(T.plan_linear(hid), du2, _bf(wc4.detach().t()), out_shape=(1, 1, M, mid), act=ACT_GELU,
+                         act_grad_z=z2.view(1, 1, M, mid))
         dz2i = dz2.view(B, H, W, mid)
-        dwc2 = ops.mtgemm_wgrad(T.plan_conv3x3(mid), t0.view(B, H, W, mid), dz2i, mid)
-        dt0 = ops.mtgemm(T.plan_conv3x3_dgrad(mid), dz2i, _tr(wc2p, 9), out_shape=(B, H, W, mid))
-        dz0, dbc0 = ops.bias_act_bwd(_flat(dt0), z0, ACT_GELU)
-        dwc0 = ops.mtgemm_wgrad(T.plan_linear(hid), u, dz0, mid)
-        du = ops.mtgemm(T.plan_linear(mid), dz0, _bf(wc0.detach().t()), out_shape=(1, 1, M, hid), residual=du2)
-        dzin, dbin = ops.bias_act_bwd(du, z_in, ACT_GELU)
-        dwin = ops.mtgemm_wgrad(T.plan_linear(C), _flat(xn), dzin, hid)
+        dwc2, dbc2 = _wgrad_b(T.plan_conv3x3(mid), t0.view(B, H, W, mid), dz2i, mid)
+        dz0 = ops.mtgemm(T.plan_conv3x3_dgrad(mid), dz2i, _tr(wc2p, 9), out_shape=(B, H, W, mid), act=ACT_GELU,
+                         act_grad_z=z0.view(B, H, W, mid)).view(1, 1, M, mid)
+        dwc0, dbc0 = _wgrad_b(T.plan_linear(hid), u, dz0, mid)
+        dzin = ops.mtgemm(T.plan_linear(mid), dz0, _bf(wc0.detach().t()), out_shape=(1, 1, M, hid), residual=du2,
+                          act=ACT_GELU, act_grad_z=z_in)
+        dwin, dbin = _wgrad_b(T.plan_linear(C), _flat(xn), dzin, hid)
         dxn = ops.mtgemm(T.plan_linear(hid), dzin, _bf(win.detach().t()), out_shape=(1, 1, M, C))
         dx, dw2n = ops.token_norm_bwd(x, w2n, dxn.view(B, H, W, C), dout, 0)
         return dx, dw2n, dwin, dbin, dwc0, dbc0, dwc2, dbc2, dwc4, dbc4, dwout, dbout

@@ -41,6 +41,7 @@ class MtGemmDesc(C.Structure):
         ("rope_tab", C.c_void_p), ("rope_C", C.c_int32), ("rope_H", C.c_int32), ("rope_W", C.c_int32),
         ("q_scale", C.c_float),
         ("out_f32", C.c_void_p), ("out_n", C.c_int32),
+        ("act_grad", C.c_int32), ("z", C.c_void_p),
     ]
 
 

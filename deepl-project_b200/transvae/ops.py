@@ -92,9 +92,13 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
            out_shape: Optional[Sequence[int]] = None, bias: Optional[Tensor] = None, act: int = ACT_NONE,
            residual: Optional[Tensor] = None, row_scale: Optional[Tensor] = None, row_shift: Optional[Tensor] = None,
            col_sum: Optional[Tensor] = None, rope: Optional[Tuple[Tensor, int, int, int, float]] = None,
-           out_f32: Optional[Tensor] = None, out_f32_shape: Optional[Sequence[int]] = None, out_n: int = 0) -> Tensor:
+           out_f32: Optional[Tensor] = None, out_f32_shape: Optional[Sequence[int]] = None, out_n: int = 0,
+           act_grad_z: Optional[Tensor] = None) -> Tensor:
     """Launch ``tvae_mtgemm``.  a0 / a1 / out / residual are NHWC bf16 4-D tensors (flat matrices as
-    [1, 1, M, K]); ``w`` is the packed bf16 [N, K_total] weight; ``bias`` fp32 [phases, N] (or [N])."""
+    [1, 1, M, K]); ``w`` is the packed bf16 [N, K_total] weight; ``bias`` fp32 [phases, N] (or [N]).
+
+    Backward fusion: with ``act_grad_z`` (the saved pre-activation, same shape as the output) and ``act`` set, the launch
+    returns ``acc * act'(z)`` -- or ``(acc + residual) * act'(z)`` when ``residual`` is given too (GELU, plain views)."""
     _need_cuda(a0, w, a1, out, bias, residual, row_scale, row_shift, col_sum, out_f32)
     assert w.dtype == BF16 and w.is_contiguous() and w.shape[1] == plan.k_total, (w.shape, plan.k_total)
     d = MtGemmDesc()
@@ -111,6 +115,14 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
     else:
         assert out_f32.dtype == torch.float32 and out_f32.is_contiguous()
         d.out.ptr = None
+    d.act_grad, d.z = 0, None
+    if act_grad_z is not None:
+        _need_cuda(act_grad_z)
+        assert act_grad_z.dtype == BF16 and act_grad_z.is_contiguous() and act_grad_z.shape == out.shape and act != ACT_NONE
+        if residual is None:
+            d.act_grad, residual = 1, act_grad_z             # z rides in the staged ("residual") tile
+        else:
+            d.act_grad, d.z = 2, act_grad_z.data_ptr()
     _set_view(d.res, residual, plan.out_split)
     if residual is not None:
         assert residual.shape == out.shape

@@ -62,6 +62,11 @@ enum { TVAE_ACT_NONE = 0, TVAE_ACT_GELU = 1, TVAE_ACT_SILU = 2 };
  *   v          = rope / q-scale (QKV projection only)
  *   out[m, n]  = v + residual[m, n]
  *
+ * Backward use (act_grad != 0, no bias / affine / rope): the same launch computes an input gradient and applies the
+ * derivative of the producing layer's activation, so dZ = dY * act'(Z) never needs its own pass over HBM:
+ *   act_grad == 1:  out = acc * act'(res)                 (`res` holds the saved pre-activation Z)
+ *   act_grad == 2:  out = (acc + res) * act'(z)           (`res` = a gradient to add first, `z` = plain [M, n_total] bf16)
+ *
  * Replaces (reference file:line): nn.Linear (attention.py:43-48, conv.py:39,65), nn.Conv2d 1x1
  * (conv.py:55,59; upsample.py:42,103), nn.Conv2d 3x3 s1/s2 (blocks.py:34,37; upsample.py:34,36,95,97;
  * conv.py:57; encoder.py:52; decoder.py:49,94; transvae.py:76-77), F.pixel_unshuffle / F.pixel_shuffle /
@@ -89,6 +94,8 @@ typedef struct {
   float q_scale;                      /* columns [0, rope_C) are multiplied by this after RoPE */
   float* out_f32;                     /* optional: write fp32 NCHW [B, out_n, H, W] directly */
   int32_t out_n;
+  int32_t act_grad;                   /* 0: forward epilogue; 1 / 2: multiply by act'(.) (see above), `act` names it */
+  const void* z;                      /* act_grad == 2: pre-activation [M, n_total] bf16, rows in output-pixel order */
 } tvae_mtgemm_desc;
 
 int tvae_mtgemm(const tvae_mtgemm_desc* desc /* HOST pointer */, void* stream);

@@ -114,6 +114,39 @@ def test_upsample_backward(B, Ci, Co, H):
     assert rel(db2, ph2) < 1e-4, rel(db2, ph2)
 
 
+@pytest.mark.parametrize("M,K,N", [(1000, 128, 192), (4096, 1536, 384), (2048, 384, 1536)])
+def test_dgrad_with_activation_gradient_epilogue(M, K, N):
+    """dZ = (dY W [+ R]) * act'(Z) in the epilogue of the input-gradient GEMM (act_grad 1 / 2) == the two-step reference."""
+    dy, w = bf(rnd(M, K)), bf(rnd(N, K, seed=1, scale=0.05))
+    z, r = bf(rnd(M, N, seed=2, scale=2.0)), bf(rnd(M, N, seed=3))
+    acc = dy.float() @ w.float().t()
+    for act, fn in ((ops.ACT_GELU, F.gelu), (ops.ACT_SILU, F.silu)):
+        zz = z.float().clone().requires_grad_(True)
+        fn(zz).sum().backward()
+        got = ops.mtgemm(T.plan_linear(K), dy.reshape(1, 1, M, K), w, out_shape=(1, 1, M, N), act=act,
+                         act_grad_z=z.reshape(1, 1, M, N))
+        assert rel(got.reshape(M, N), acc * zz.grad) < 1e-2, (act, rel(got.reshape(M, N), acc * zz.grad))
+    zz = z.float().clone().requires_grad_(True)
+    F.gelu(zz).sum().backward()
+    got = ops.mtgemm(T.plan_linear(K), dy.reshape(1, 1, M, K), w, out_shape=(1, 1, M, N), act=ops.ACT_GELU,
+                     residual=r.reshape(1, 1, M, N), act_grad_z=z.reshape(1, 1, M, N))
+    assert rel(got.reshape(M, N), (acc + r.float()) * zz.grad) < 1e-2
+
+
+def test_downsample_dgrad_with_silu_gradient_on_phase_view():
+    """act_grad on a phase-split output view (the stride-2 conv's input gradient): z is staged through the same view."""
+    B, C, N, H = 2, 64, 128, 16
+    w2 = bf(rnd(N, C, 3, 3, seed=1, scale=0.05))
+    dz, z0 = bf(rnd(B, N, H // 2, H // 2, seed=7)), bf(rnd(B, C, H, H, seed=8, scale=2.0))
+    y = torch.zeros(B, C, H, H, device=DEV, requires_grad=True)
+    F.conv2d(y, w2.float(), stride=2, padding=1).backward(dz.float())
+    zz = z0.float().clone().requires_grad_(True)
+    F.silu(zz).sum().backward()
+    got = ops.mtgemm(T.plan_downsample_dgrad_main(C, N), nhwc(dz), bf(T.pack_conv3x3_dgrad(w2.float())).contiguous(),
+                     out_shape=(B, H, H, C), act=ops.ACT_SILU, act_grad_z=nhwc(z0))
+    assert rel(nchw(got), y.grad * zz.grad) < 1e-2
+
+
 def test_bias_act_bwd_and_act_fwd():
     for (M, N) in [(777, 192), (300, 6144), (512, 64)]:
         z, dy = bf(rnd(M, N, scale=2.0)), bf(rnd(M, N, seed=1))
