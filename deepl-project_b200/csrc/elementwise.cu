@@ -114,8 +114,13 @@ int gn_stats_run(const void* x, float* sums, int B, int HW, int C, int G, cudaSt
   TVAE_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * G * 2 * sizeof(float), stream));
   const int nvec = C / 8;
   const int threads = (256 / nvec) * nvec;
-  int ppb = 1024;
-  while (ppb > 64 && (long long)((HW + ppb - 1) / ppb) * B < 8LL * num_sms()) ppb >>= 1;
+  // one full wave: ~6 resident blocks per SM (40 registers, 240 threads), each sweeping a contiguous pixel range; a
+  // 2.3-wave grid of short blocks lost a quarter of its time to the tail
+  const int slots = (num_sms() > 0 ? num_sms() : 148) * 6;
+  int gx = slots / B;
+  if (gx < 1) gx = 1;
+  int ppb = (HW + gx - 1) / gx;
+  if (ppb < 64) ppb = 64;
   dim3 grid((HW + ppb - 1) / ppb, B);
   gn_stats_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<const uint4*>(x), sums, HW, C, G, ppb);
   TVAE_CHECK_CUDA(cudaGetLastError());
@@ -212,68 +217,106 @@ int gn_apply_run(const void* x, const float* sums, const float* gamma, const flo
 // (row_scale / row_shift of tvae_mtgemm) with the norm weights folded into the projection weights.
 // Algorithmic bytes: 2*C per token.
 // -------------------------------------------------------------------------------------------------
+template <int VPL, int R>
 __global__ void __launch_bounds__(256) row_stats_kernel(const uint4* __restrict__ x, const float* __restrict__ w1,
                                                         float* __restrict__ out_a, float* __restrict__ out_b,
                                                         long long M, int C, int mode) {
+  // one warp handles R rows at a time (VPL 16-byte vectors per lane and row), all loads issued before the interleaved
+  // warp reductions, persistent grid-stride loop (the one-short-lived-warp-per-row version reached 2.5 TB/s)
   const int lane = threadIdx.x & 31;
-  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= M) return;
   const int nvec = C >> 3;
-  const uint4* xr = x + row * nvec;
-  float s2 = 0.0f, sw = 0.0f, sw2 = 0.0f;
-  for (int v = lane; v < nvec; v += 32) {
-    const uint4 u = __ldg(xr + v);
-    float f[8];
-    float2 t;
-    t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
-    t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
-    t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
-    t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
-    if (mode != 0) {
-      const float4 wa = __ldg(reinterpret_cast<const float4*>(w1) + 2 * v);
-      const float4 wb = __ldg(reinterpret_cast<const float4*>(w1) + 2 * v + 1);
-      const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+  const float invC = 1.0f / (float)C;
+  float2 wv[VPL][4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float h = f[k] * wv[k];
-        s2 = fmaf(f[k], f[k], s2);
-        sw += h;
-        sw2 = fmaf(h, h, sw2);
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s2 = fmaf(f[k], f[k], s2);
+  for (int c = 0; c < VPL; ++c) {
+    const int v = lane + c * 32;
+    float4 wa = make_float4(0, 0, 0, 0), wb = wa;
+    if (mode != 0 && v < nvec) {
+      wa = __ldg(reinterpret_cast<const float4*>(w1) + 2 * v);
+      wb = __ldg(reinterpret_cast<const float4*>(w1) + 2 * v + 1);
     }
+    wv[c][0] = make_float2(wa.x, wa.y); wv[c][1] = make_float2(wa.z, wa.w);
+    wv[c][2] = make_float2(wb.x, wb.y); wv[c][3] = make_float2(wb.z, wb.w);
   }
-  s2 = warp_sum(s2);
-  if (mode != 0) {
-    sw = warp_sum(sw);
-    sw2 = warp_sum(sw2);
-  }
-  if (lane == 0) {
-    const float invC = 1.0f / (float)C;
-    const float rms = (mode == 2) ? 1.0f : sqrtf(s2 * invC + 1e-6f);
-    if (mode == 0) {
-      out_a[row] = 1.0f / rms;
-    } else {
-      const float mu = sw * invC / rms;
-      const float var = fmaxf(sw2 * invC / (rms * rms) - mu * mu, 0.0f);
-      const float sigma = sqrtf(var + 1e-5f);
-      out_a[row] = 1.0f / (sigma * rms);
-      out_b[row] = mu / sigma;
+  const long long groups = (M + R - 1) / R;
+  const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long grp = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5); grp < groups; grp += warps_total) {
+    const long long row0 = grp * R;
+    uint4 u[R][VPL];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < VPL; ++c) {
+        const int v = lane + c * 32;
+        u[r][c] = (v < nvec && row0 + r < M) ? __ldg(x + (row0 + r) * nvec + v) : make_uint4(0, 0, 0, 0);
+      }
+    float st[3 * R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float2 s2 = f2(0.0f), sw = f2(0.0f), sw2 = f2(0.0f);
+#pragma unroll
+      for (int c = 0; c < VPL; ++c) {
+        float2 f[4];
+        unpack8_2(u[r][c], f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          s2 = __ffma2_rn(f[q], f[q], s2);
+          const float2 h = __fmul2_rn(f[q], wv[c][q]);
+          sw = __fadd2_rn(sw, h);
+          sw2 = __ffma2_rn(h, h, sw2);
+        }
+      }
+      st[3 * r] = s2.x + s2.y;
+      st[3 * r + 1] = sw.x + sw.y;
+      st[3 * r + 2] = sw2.x + sw2.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int i = 0; i < 3 * R; ++i) st[i] += __shfl_xor_sync(0xffffffffu, st[i], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (row0 + r < M) {
+          const float rms = (mode == 2) ? 1.0f : sqrtf(st[3 * r] * invC + 1e-6f);
+          if (mode == 0) {
+            out_a[row0 + r] = 1.0f / rms;
+          } else {
+            const float mu = st[3 * r + 1] * invC / rms;
+            const float var = fmaxf(st[3 * r + 2] * invC / (rms * rms) - mu * mu, 0.0f);
+            const float sigma = sqrtf(var + 1e-5f);
+            out_a[row0 + r] = 1.0f / (sigma * rms);
+            out_b[row0 + r] = mu / sigma;
+          }
+        }
+      }
     }
   }
 }
 
-int row_stats_run(const void* x, const float* w1, float* out_a, float* out_b, long long M, int C, int mode,
-                  cudaStream_t stream) {
-  TVAE_REQUIRE(C % 8 == 0, "row_stats: C=%d must be a multiple of 8", C);
-  TVAE_REQUIRE(mode == 0 || (w1 != nullptr && out_b != nullptr), "row_stats: modes 1/2 need w1 and out_b");
-  const long long threads = M * 32;
-  const int grid = (int)((threads + 255) / 256);
-  row_stats_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), w1, out_a, out_b, M, C, mode);
+template <int VPL, int R>
+static int launch_rs(const void* x, const float* w1, float* out_a, float* out_b, long long M, int C, int mode,
+                     cudaStream_t stream) {
+  const long long groups = (M + R - 1) / R;
+  long long blocks = (groups + 7) / 8;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  row_stats_kernel<VPL, R><<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), w1, out_a, out_b, M, C, mode);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+int row_stats_run(const void* x, const float* w1, float* out_a, float* out_b, long long M, int C, int mode,
+                  cudaStream_t stream) {
+  TVAE_REQUIRE(C % 8 == 0 && C / 8 <= 320, "row_stats: C=%d must be a multiple of 8, at most 2560", C);
+  TVAE_REQUIRE(mode == 0 || (w1 != nullptr && out_b != nullptr), "row_stats: modes 1/2 need w1 and out_b");
+  const int vpl = (C / 8 + 31) / 32;
+  if (vpl <= 1) return launch_rs<1, 4>(x, w1, out_a, out_b, M, C, mode, stream);
+  if (vpl == 2) return launch_rs<2, 4>(x, w1, out_a, out_b, M, C, mode, stream);
+  if (vpl == 3) return launch_rs<3, 2>(x, w1, out_a, out_b, M, C, mode, stream);
+  if (vpl == 4) return launch_rs<4, 2>(x, w1, out_a, out_b, M, C, mode, stream);
+  if (vpl <= 6) return launch_rs<6, 1>(x, w1, out_a, out_b, M, C, mode, stream);
+  return launch_rs<10, 1>(x, w1, out_a, out_b, M, C, mode, stream);
 }
 
 // -------------------------------------------------------------------------------------------------
