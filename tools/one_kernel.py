@@ -36,6 +36,14 @@ elif which == "token_norm_bwd":
     x, dy = rnd(B * 4096, 384).to(torch.bfloat16), rnd(B * 4096, 384).to(torch.bfloat16)
     w = rnd(384)
     fn = lambda: ops.token_norm_bwd(x, w, dy, dy, 1)
+elif which in ("lin384_gelu", "lin384_res"):
+    M = B * 4096
+    x = rnd(1, 1, M, 384).to(torch.bfloat16)
+    w = (rnd(1536, 384) * 0.05).to(torch.bfloat16)
+    b, rs = rnd(1536), torch.rand(M, device=dev) + 0.5
+    res = rnd(1, 1, M, 1536).to(torch.bfloat16)
+    fn = (lambda: ops.mtgemm(T.plan_linear(384), x, w, out_shape=(1, 1, M, 1536), bias=b, act=ops.ACT_GELU, row_scale=rs)) \
+        if which == "lin384_gelu" else (lambda: ops.mtgemm(T.plan_linear(384), x, w, out_shape=(1, 1, M, 1536), bias=b, residual=res))
 else:
     raise SystemExit(f"unknown kernel {which}")
 for _ in range(5):
