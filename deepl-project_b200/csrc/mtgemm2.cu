@@ -275,12 +275,9 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
       const int n_base = n_t * BLOCK_N;
-#pragma unroll 1
-      for (int c16 = half; c16 < BLOCK_N / 16; c16 += 2) {
-        uint32_t va[8], vb[8];
-        tmem_ld8(t_row + c16 * 16, va);
-        tmem_ld8(t_row + c16 * 16 + 8, vb);
-        tmem_ld_wait();
+      // software-pipelined over the 16-column groups: the tcgen05.ld of the next group is in flight while the current
+      // group goes through the epilogue math (two register sets, ping-pong)
+      auto process = [&](const int c16, const uint32_t (&va)[8], const uint32_t (&vb)[8]) {
         float fa[8], fb[8];
         epi_math8<EPI>(P, bias, R, n_base + c16 * 16, va, fa);
         epi_math8<EPI>(P, bias, R, n_base + c16 * 16 + 8, vb, fb);
@@ -312,6 +309,25 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           o.x = pack_bf16(fb[0], fb[1]); o.y = pack_bf16(fb[2], fb[3]);
           o.z = pack_bf16(fb[4], fb[5]); o.w = pack_bf16(fb[6], fb[7]);
           *pb = o;
+        }
+      };
+      {
+        constexpr int kGroups = BLOCK_N / 16;
+        uint32_t v0a[8], v0b[8], v1a[8], v1b[8];
+        tmem_ld8(t_row + half * 16, v0a);
+        tmem_ld8(t_row + half * 16 + 8, v0b);
+#pragma unroll 1
+        for (int c16 = half; c16 < kGroups; c16 += 4) {      // every warp owns an even number of groups
+          tmem_ld_wait_dep(v0a, v0b);
+          tmem_ld8(t_row + (c16 + 2) * 16, v1a);
+          tmem_ld8(t_row + (c16 + 2) * 16 + 8, v1b);
+          process(c16, v0a, v0b);
+          tmem_ld_wait_dep(v1a, v1b);
+          if (c16 + 4 < kGroups) {
+            tmem_ld8(t_row + (c16 + 4) * 16, v0a);
+            tmem_ld8(t_row + (c16 + 4) * 16 + 8, v0b);
+          }
+          process(c16 + 2, v1a, v1b);
         }
       }
       // accumulator half drained -> tell the leader's MMA warp (remote arrive from the peer CTA)

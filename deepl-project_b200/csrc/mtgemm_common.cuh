@@ -119,6 +119,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "memory");
 }
 
+// tcgen05.wait::ld that also "produces" the sixteen loaded registers, so the compiler cannot move a use of them above
+// the wait (needed once loads for the NEXT column group are in flight while the current group is being processed)
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&a)[8], uint32_t (&b)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(b[0]),
+                 "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7])
+               :
+               : "memory");
+}
+
 struct EpiRow {
   float rs, rsh;
   int rope_r, rope_c;
