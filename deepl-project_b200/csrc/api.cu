@@ -9,6 +9,8 @@ int im2col_in_run(const float* x, void* cols, int B, int H, int W, cudaStream_t 
 int gn_stats_run(const void* x, float* sums, int B, int HW, int C, int G, cudaStream_t stream);
 int gn_apply_run(const void* x, const float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
                  int G, float eps, int apply_silu, cudaStream_t stream);
+int gn_fwd_run(const void* x, float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C, int G,
+               float eps, int apply_silu, cudaStream_t stream);
 int row_stats_run(const void* x, const float* w1, float* out_a, float* out_b, long long M, int C, int mode,
                   cudaStream_t stream);
 int nchw_to_nhwc_run(const float* in, void* out, int B, int C, int H, int W, int Cpad, cudaStream_t stream);
@@ -95,6 +97,10 @@ int tvae_groupnorm_stats(const void* x, float* sums, int32_t B, int32_t HW, int3
 int tvae_groupnorm_apply(const void* x, const float* sums, const float* gamma, const float* beta, void* y, int32_t B,
                          int32_t HW, int32_t C, int32_t G, float eps, int32_t apply_silu, void* stream) {
   GUARD(); return gn_apply_run(x, sums, gamma, beta, y, B, HW, C, G, eps, apply_silu, S_(stream));
+}
+int tvae_groupnorm_silu(const void* x, const float* gamma, const float* beta, void* y, float* sums, int32_t B, int32_t HW,
+                        int32_t C, int32_t G, float eps, int32_t apply_silu, void* stream) {
+  GUARD(); return gn_fwd_run(x, sums, gamma, beta, y, B, HW, C, G, eps, apply_silu, S_(stream));
 }
 int tvae_row_stats(const void* x, const float* w1, float* out_a, float* out_b, int64_t M, int32_t C, int32_t mode,
                    void* stream) {

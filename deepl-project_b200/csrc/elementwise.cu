@@ -206,6 +206,20 @@ int gn_apply_run(const void* x, const float* sums, const float* gamma, const flo
   return 0;
 }
 
+// silu(GroupNorm(x)) in one call: statistics pass + apply pass; `sums` (fp32 [B, G, 2]) is an output (the backward pass
+// needs it).  (Running the two passes image by image so that the second read of x hits the 126 MB L2 was tried and is
+// slower on B200: a 25 MB image is too small a launch -- 23 ms instead of 13 ms per inference step.)
+int gn_stats_run(const void* x, float* sums, int B, int HW, int C, int G, cudaStream_t stream);
+int gn_apply_run(const void* x, const float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
+                 int G, float eps, int apply_silu, cudaStream_t stream);
+
+int gn_fwd_run(const void* x, float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C, int G,
+               float eps, int apply_silu, cudaStream_t stream) {
+  int rc;
+  if ((rc = gn_stats_run(x, sums, B, HW, C, G, stream))) return rc;
+  return gn_apply_run(x, sums, gamma, beta, y, B, HW, C, G, eps, apply_silu, stream);
+}
+
 // -------------------------------------------------------------------------------------------------
 // Per-token statistics (one warp per token, row of C bf16 values):
 //   mode 0 (FFN, blocks.py:149 RMSNorm):            out_a = 1/sqrt(mean(x^2) + 1e-6)

@@ -61,11 +61,9 @@ class ResBlockFn(Fn):
     def forward(ctx, x, g1, b1, w1p, c1b, g2, b2, w2p, c2b):
         B, H, W, C = x.shape
         plan = T.plan_conv3x3(C)
-        s1 = ops.groupnorm_stats(x)
-        h0 = ops.groupnorm_silu(x, g1, b1, sums=s1)
+        h0, s1 = ops.groupnorm_silu(x, g1, b1, return_sums=True)
         h1 = ops.mtgemm(plan, h0, _bf(w1p), out_shape=(B, H, W, C), bias=_f32(c1b))
-        s2 = ops.groupnorm_stats(h1)
-        h2 = ops.groupnorm_silu(h1, g2, b2, sums=s2)
+        h2, s2 = ops.groupnorm_silu(h1, g2, b2, return_sums=True)
         out = ops.mtgemm(plan, h2, _bf(w2p), out_shape=(B, H, W, C), bias=_f32(c2b), residual=x)
         ctx.save_for_backward(x, s1, h0, h1, s2, h2, g1, b1, w1p, g2, b2, w2p)
         return out
@@ -298,10 +296,10 @@ class GroupNormSilu(Fn):
 
     @staticmethod
     def forward(ctx, x, g, b, silu):
-        s = ops.groupnorm_stats(x)
+        y, s = ops.groupnorm_silu(x, g, b, silu=silu, return_sums=True)
         ctx.save_for_backward(x, s, g, b)
         ctx.silu = silu
-        return ops.groupnorm_silu(x, g, b, silu=silu, sums=s)
+        return y
 
     @staticmethod
     def backward(ctx, dh):

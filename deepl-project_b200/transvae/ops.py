@@ -227,21 +227,28 @@ def groupnorm_stats(x: Tensor, groups: int = 32) -> Tensor:
 
 
 def groupnorm_silu(x: Tensor, gamma: Tensor, beta: Tensor, groups: int = 32, eps: float = 1e-5, silu: bool = True,
-                   sums: Optional[Tensor] = None) -> Tensor:
-    """silu(GroupNorm(x)) on NHWC bf16."""
+                   sums: Optional[Tensor] = None, return_sums: bool = False):
+    """silu(GroupNorm(x)) on NHWC bf16.  Without precomputed ``sums`` both passes run in one call
+    (``tvae_groupnorm_silu``); ``return_sums`` also hands back the statistics for the backward pass."""
     _need_cuda(x, gamma, beta)
     assert x.dtype == BF16 and x.is_contiguous()
     B, H, W, C_ = x.shape
-    if sums is None:
-        sums = groupnorm_stats(x, groups)
     y = torch.empty_like(x)
     g, b = gamma.float().contiguous(), beta.float().contiguous()
-    with _hbm("gn_apply_silu", x.numel() * 4):
-        _lib.check(_lib.load().tvae_groupnorm_apply(x.data_ptr(), sums.data_ptr(), g.data_ptr(), b.data_ptr(), y.data_ptr(),
-                                                    B, H * W, C_, groups, eps, 1 if silu else 0, _stream()),
-                   "tvae_groupnorm_apply")
-    _count()
-    return y
+    if sums is None:
+        sums = torch.empty(B, groups, 2, dtype=torch.float32, device=x.device)
+        with _hbm("gn_stats + gn_apply_silu", x.numel() * 6):
+            _lib.check(_lib.load().tvae_groupnorm_silu(x.data_ptr(), g.data_ptr(), b.data_ptr(), y.data_ptr(), sums.data_ptr(),
+                                                       B, H * W, C_, groups, eps, 1 if silu else 0, _stream()),
+                       "tvae_groupnorm_silu")
+        _count(3)
+    else:
+        with _hbm("gn_apply_silu", x.numel() * 4):
+            _lib.check(_lib.load().tvae_groupnorm_apply(x.data_ptr(), sums.data_ptr(), g.data_ptr(), b.data_ptr(), y.data_ptr(),
+                                                        B, H * W, C_, groups, eps, 1 if silu else 0, _stream()),
+                       "tvae_groupnorm_apply")
+        _count()
+    return (y, sums) if return_sums else y
 
 
 def row_stats(x: Tensor, w1: Optional[Tensor] = None, mode: Optional[int] = None) -> Tuple[Tensor, Optional[Tensor]]:
@@ -393,7 +400,7 @@ def groupnorm_bwd(x: Tensor, dh: Tensor, sums: Tensor, gamma: Tensor, beta: Tens
     g, b = gamma.float().contiguous(), beta.float().contiguous()
     part = torch.empty(B, Cc, 2, dtype=torch.float32, device=x.device)
     dx = torch.empty_like(x)
-    with _hbm("gn_bwd (reduce + apply)", x.numel() * (10 if add is not None else 8)):
+    with _hbm("gn_bwd (reduce + apply)", x.numel() * (12 if add is not None else 10)):
         _lib.check(_lib.load().tvae_groupnorm_bwd(x.data_ptr(), dh.data_ptr(), _ptr(add), sums.data_ptr(), g.data_ptr(),
                                                   b.data_ptr(), part.data_ptr(), dx.data_ptr(), B, H * W, Cc, groups, eps,
                                                   1 if silu else 0, _stream()), "tvae_groupnorm_bwd")

@@ -118,6 +118,10 @@ int tvae_groupnorm_stats(const void* x_nhwc, float* sums, int32_t B, int32_t HW,
 /* y = act(GroupNorm(x)) with act = SiLU (apply_silu=1) or identity; NHWC bf16 in/out (blocks.py:60-66). */
 int tvae_groupnorm_apply(const void* x_nhwc, const float* sums, const float* gamma, const float* beta, void* y_nhwc,
                          int32_t B, int32_t HW, int32_t C, int32_t G, float eps, int32_t apply_silu, void* stream);
+/* Both passes in one call (statistics, then apply).  `sums` [B, G, 2] is an OUTPUT (the backward pass reuses it).
+ * Replaces nn.GroupNorm(32, C) + F.silu (blocks.py:60-66; decoder.py:128-129). */
+int tvae_groupnorm_silu(const void* x_nhwc, const float* gamma, const float* beta, void* y_nhwc, float* sums, int32_t B,
+                        int32_t HW, int32_t C, int32_t G, float eps, int32_t apply_silu, void* stream);
 /* Per-token statistics for the folded RMSNorm (mode 0; blocks.py:149) / RMSNorm+LayerNorm (mode 1;
  * blocks.py:146 + attention.py:71-73) epilogues of tvae_mtgemm.  x: bf16 [M, C]; w1: fp32 [C] (mode 1). */
 int tvae_row_stats(const void* x, const float* w1, float* out_a, float* out_b, int64_t M, int32_t C, int32_t mode,
