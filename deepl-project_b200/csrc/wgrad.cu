@@ -496,12 +496,28 @@ int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, float* db, cudaStream_t st
   const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
   int sms = num_sms();
   if (sms <= 0) sms = 148;
-  // pixel splits: fill (at most) two full waves of CTAs -- rounding DOWN so the last wave is not nearly empty
+  // pixel splits ("split-K over pixels"): fill (at most) two full waves of CTAs -- rounding DOWN so the last wave is
+  // not nearly empty -- and keep at least ~4 pixel tiles per CTA so the TMEM drain + atomics are amortised
   long long splits = (2LL * sms) / items;
   if (splits > m_tiles) splits = m_tiles;
   if (splits < 1) splits = 1;
-  // keep at least ~4 pixel tiles per CTA so the TMEM drain + atomics are amortised
   while (splits > 1 && m_tiles / splits < 4) --splits;
+  // more work items than SMs: an unsplit grid can end in a nearly empty wave (the 768-channel 3x3 wgrad has 162 items
+  // -> 148 + 14 CTAs, 55 % efficiency); if so, take the small split count with the best wave efficiency
+  if (splits == 1) {
+    auto eff = [&](long long sp) {
+      const long long g = items * sp;
+      return (double)g / (double)(((g + sms - 1) / sms) * sms);
+    };
+    if (eff(1) < 0.8) {
+      double best = eff(1);
+      for (long long sp = 2; sp <= 8 && m_tiles / sp >= 16; ++sp)
+        if (eff(sp) > best + 0.02) {
+          best = eff(sp);
+          splits = sp;
+        }
+    }
+  }
   P.splits = (int)splits;
   const long long grid = items * splits;
   TVAE_REQUIRE(grid < (1LL << 31), "wgrad: grid too large");
