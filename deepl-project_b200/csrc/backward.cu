@@ -509,7 +509,7 @@ int token_norm_fwd_run(const void* x, const float* w, void* y, long long M, int 
 // column per block.  (The first version indexed per-lane arrays dynamically -> local memory; ncu census of a training
 // step: 32.5 ms of 225 ms.)
 template <int VPL>
-__global__ void __launch_bounds__(256) token_norm_bwd_reg_kernel(const uint4* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, VPL <= 2 ? 2 : 1) token_norm_bwd_reg_kernel(const uint4* __restrict__ x, const float* __restrict__ w,
                                                                  const uint4* __restrict__ dy, const uint4* __restrict__ add,
                                                                  uint4* __restrict__ dx, float* __restrict__ dw, long long M,
                                                                  int C, int mode) {

@@ -326,7 +326,7 @@ int row_stats_run(const void* x, const float* w1, float* out_a, float* out_b, lo
   TVAE_REQUIRE(mode == 0 || (w1 != nullptr && out_b != nullptr), "row_stats: modes 1/2 need w1 and out_b");
   const int vpl = (C / 8 + 31) / 32;
   if (vpl <= 1) return launch_rs<1, 4>(x, w1, out_a, out_b, M, C, mode, stream);
-  if (vpl == 2) return launch_rs<2, 4>(x, w1, out_a, out_b, M, C, mode, stream);
+  if (vpl == 2) return launch_rs<2, 2>(x, w1, out_a, out_b, M, C, mode, stream);
   if (vpl == 3) return launch_rs<3, 2>(x, w1, out_a, out_b, M, C, mode, stream);
   if (vpl == 4) return launch_rs<4, 2>(x, w1, out_a, out_b, M, C, mode, stream);
   if (vpl <= 6) return launch_rs<6, 1>(x, w1, out_a, out_b, M, C, mode, stream);
