@@ -335,6 +335,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 // K and V travel through separate 2-stage rings: K_j is released after S(j) has been issued, V_j after P(j) V_j.
 // Per block and thread this is ~440 issue slots instead of ~670, of which 128 are MUFU.EX2 -- the unit that bounds
 // head_dim-64 attention (16 exp2 / clk / SM against 8192 MMA flop / clk / SM).
+#ifndef TVAE_ATT_TOKEN_PASS
+#define TVAE_ATT_TOKEN_PASS 32
+#endif
 constexpr int kLazyLog2 = 8;
 constexpr int kKvStages6 = 2;
 
@@ -585,6 +588,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       // the in-order warp never sits on the MUFU result latency (the straightforward loop left the consumer 2 MUFUs
       // behind its producer and the exp phase took 1600 clocks instead of the 1024 the MUFU needs).
       constexpr int kExpAhead = 6;
+      constexpr int kTokenPass = TVAE_ATT_TOKEN_PASS;   // pair index at which the token is handed on (64 = end of phase)
 #pragma unroll
       for (int i = 0; i < 64 + kExpAhead; ++i) {
         if (i < 64) {
@@ -600,6 +604,13 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           v[2 * i] = __float_as_uint(x.x);
           v[2 * i + 1] = __float_as_uint(x.y);
         }
+        if (i == kTokenPass) {
+          // pass the MUFU token on before this exp phase is over: one warp per scheduler cannot saturate the MUFU pipe
+          // (128 back-to-back EX2 from a single warp take ~1500 clocks, not 1024), so the second half of this phase
+          // overlaps the first half of the other tile's -- staggered by half a phase, never in lockstep
+          if (t == 0) asm volatile("bar.arrive 4, 256;" ::: "memory");
+          else if (j + 1 < nblk) asm volatile("bar.arrive 3, 256;" ::: "memory");
+        }
         const int d = i - kExpAhead;
         if (d >= 0) {
           const float2 e = make_float2(__uint_as_float(v[2 * d]), __uint_as_float(v[2 * d + 1]));
@@ -613,8 +624,6 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           }
         }
       }
-      if (t == 0) asm volatile("bar.arrive 4, 256;" ::: "memory");
-      else if (j + 1 < nblk) asm volatile("bar.arrive 3, 256;" ::: "memory");
       l_run += (la.x + la.y) + (lb.x + lb.y);
       tc_fence_before();
       fence_proxy_async_smem();

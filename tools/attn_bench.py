@@ -3,6 +3,9 @@ import math, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "deepl-project_b200"))
 import torch
+from transvae import _lib
+if os.environ.get("TVAE_LIB"):
+    _lib.LIB_PATH = os.environ["TVAE_LIB"]      # A/B builds of the library
 from transvae import ops
 
 def timeit(fn, n=10):
