@@ -24,6 +24,9 @@ namespace tvae {
 
 int mtgemm2_dispatch(int epi, int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                      const CUtensorMap& o, const CUtensorMap& r, const MtParams& P, cudaStream_t stream);
+static int mtgemm1_dispatch(int epi, int block_n, const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB,
+                            const CUtensorMap& mO, const CUtensorMap& mR, const MtParams& P, cudaStream_t stream);
+int gn_stats_run(const void* x, float* sums, int B, int HW, int C, int G, cudaStream_t stream);   // elementwise.cu
 
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -463,11 +466,39 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
   }
   // CTA-pair kernel (cta_group::2, weight tile split across the pair) whenever the tile is wide enough to matter
   static const bool use_pair = !(getenv("TVAE_2CTA") && atoi(getenv("TVAE_2CTA")) == 0);
-  if (use_pair && block_n >= 128 && P.tiles_w * P.tiles_h * P.tiles_b >= 2) {
+  const bool pair = use_pair && block_n >= 128 && P.tiles_w * P.tiles_h * P.tiles_b >= 2;
+  // GroupNorm statistics of the output: from the epilogue when the launch qualifies, else one tvae_groupnorm_stats pass
+  bool gn_fused = false;
+  if (d->gn_sums != nullptr) {
+    TVAE_REQUIRE(!direct && d->gn_groups >= 1 && d->n_total % d->gn_groups == 0 && d->out.C == d->n_total,
+                 "mtgemm: gn_sums needs a bf16 output with n_total = %d channels divisible into %d groups", d->n_total,
+                 d->gn_groups);
+    static const bool allow_fused = !(getenv("TVAE_GN_FUSED") && atoi(getenv("TVAE_GN_FUSED")) == 0);
+    gn_fused = allow_fused && pair && P.nb == 1 && (epi == kEpiBias || epi == kEpiBiasRes) && d->gn_groups <= 64;
+    if (gn_fused) {
+      TVAE_CHECK_CUDA(cudaMemsetAsync(d->gn_sums, 0, (size_t)d->out.B * d->gn_groups * 2 * sizeof(float), stream));
+      P.gn_sums = d->gn_sums;
+      P.gn_groups = d->gn_groups;
+      P.gn_cpg = d->n_total / d->gn_groups;
+    }
+  }
+  if (pair) {
     CUtensorMap mBh;
     if ((rc = make_tmap_2d(&mBh, d->w, d->n_total, d->k_total, d->k_total, block_n / 2))) return rc;
-    return mtgemm2_dispatch(epi, block_n, mA0, mA1, mBh, mO, mR, P, stream);
+    if ((rc = mtgemm2_dispatch(epi, block_n, mA0, mA1, mBh, mO, mR, P, stream))) return rc;
+    if (d->gn_sums != nullptr && !gn_fused)
+      return gn_stats_run(d->out.ptr, d->gn_sums, d->out.B, d->out.H * d->out.W, d->out.C, d->gn_groups, stream);
+    return 0;
   }
+  if (d->gn_sums != nullptr) {
+    if ((rc = mtgemm1_dispatch(epi, block_n, mA0, mA1, mB, mO, mR, P, stream))) return rc;
+    return gn_stats_run(d->out.ptr, d->gn_sums, d->out.B, d->out.H * d->out.W, d->out.C, d->gn_groups, stream);
+  }
+  return mtgemm1_dispatch(epi, block_n, mA0, mA1, mB, mO, mR, P, stream);
+}
+
+static int mtgemm1_dispatch(int epi, int block_n, const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB,
+                            const CUtensorMap& mO, const CUtensorMap& mR, const MtParams& P, cudaStream_t stream) {
   switch (epi) {
     case kEpiBias: return launch_n<kEpiBias>(block_n, mA0, mA1, mB, mO, mR, P, stream);
     case kEpiBiasRes: return launch_n<kEpiBiasRes>(block_n, mA0, mA1, mB, mO, mR, P, stream);

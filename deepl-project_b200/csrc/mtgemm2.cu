@@ -112,6 +112,13 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const bool has_res = kHasRes && P.has_residual;
+  // fused GroupNorm statistics of the output (bias / bias+residual epilogues only): per-CTA staging of (sum, sumsq)
+  constexpr bool kGn = (EPI == kEpiBias || EPI == kEpiBiasRes);
+  __shared__ float s_gn[kGn ? 128 : 1];
+  const bool gn = kGn && P.gn_sums != nullptr;
+  if constexpr (kGn) {
+    if (threadIdx.x < 128) s_gn[threadIdx.x] = 0.0f;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -268,6 +275,7 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
       const float* bias = P.bias ? P.bias + (size_t)ph * P.n_total : nullptr;
+      const bool gn_zero_row = gn && !R.row_ok;   // clipped rows must not reach the statistics (TMA drops them anyway)
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -300,6 +308,12 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const uint4 ra = *pa, rb = *pb;
               epi_combine8<EPI>(fa, ra, zrow, n_base + c16 * 16);
               epi_combine8<EPI>(fb, rb, zrow, n_base + c16 * 16 + 8);
+            }
+          }
+          if constexpr (kGn) {
+            if (gn_zero_row) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) fa[k] = fb[k] = 0.0f;
             }
           }
           uint4 o;
@@ -343,10 +357,70 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int j = 0; j < BLOCK_N / 64; ++j)
             tma_store_5d(&tmOut, sOut + j * kABytes, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph], h0, b0);
           tma_store_commit();
-          tma_store_wait_read<0>();
-          if (has_res) mbar_arrive(out_free);
         }
+        if constexpr (kGn) {
+          if (gn) {
+            // column sums of the staged bf16 tile (what the consumer's GroupNorm will read): thread = (8-channel vector,
+            // row slot); 16-byte reads of one row by 8 consecutive threads cover all 32 banks once (swizzled layout)
+            constexpr int kVec = BLOCK_N / 8;
+            constexpr int kSlots = 256 / kVec;
+            const int et = (int)threadIdx.x - 128;
+            if (et < kVec * kSlots) {
+              const int gc = et % kVec, rs0 = et / kVec;
+              const uint8_t* chunk = sOut + (gc >> 3) * kABytes;
+              const int g8 = gc & 7;
+              float2 s[4], ss[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) s[i] = ss[i] = make_float2(0.0f, 0.0f);
+#pragma unroll 4
+              for (int rr = rs0; rr < kBlockM; rr += kSlots) {
+                const uint4 u = *reinterpret_cast<const uint4*>(chunk + rr * 128 + ((g8 ^ (rr & 7)) << 4));
+                float2 f[4];
+                unpack8_2(u, f);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  s[i] = __fadd2_rn(s[i], f[i]);
+                  ss[i] = __ffma2_rn(f[i], f[i], ss[i]);
+                }
+              }
+              const float sv[8] = {s[0].x, s[0].y, s[1].x, s[1].y, s[2].x, s[2].y, s[3].x, s[3].y};
+              const float qv[8] = {ss[0].x, ss[0].y, ss[1].x, ss[1].y, ss[2].x, ss[2].y, ss[3].x, ss[3].y};
+              const int c0 = n_t * BLOCK_N + gc * 8;
+              int g = c0 / P.gn_cpg, rem = c0 - g * P.gn_cpg;
+              float as = 0.0f, aq = 0.0f;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                as += sv[k];
+                aq += qv[k];
+                if (++rem == P.gn_cpg || k == 7) {
+                  if (g < P.gn_groups) {
+                    atomicAdd(&s_gn[2 * g], as);
+                    atomicAdd(&s_gn[2 * g + 1], aq);
+                  }
+                  as = aq = 0.0f;
+                  rem = 0;
+                  ++g;
+                }
+              }
+            }
+          }
+        }
+        if (store_leader) tma_store_wait_read<0>();
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        // the staged tile has been read by the TMA store and by the statistics pass: the residual loader may refill it
+        if (store_leader && has_res) mbar_arrive(out_free);
+        if constexpr (kGn) {
+          if (gn) {
+            const int et = (int)threadIdx.x - 128;
+            if (et < 2 * P.gn_groups) {
+              const float v = s_gn[et];
+              if (v != 0.0f) {      // only the groups of this n tile; a phantom tile (b0 >= vB) contributes nothing
+                atomicAdd(P.gn_sums + (size_t)b0 * 2 * P.gn_groups + et, v);
+                s_gn[et] = 0.0f;
+              }
+            }
+          }
+        }
       }
     }
     if (store_leader) tma_store_wait<0>();

@@ -62,8 +62,8 @@ class ResBlockFn(Fn):
         B, H, W, C = x.shape
         plan = T.plan_conv3x3(C)
         h0, s1 = ops.groupnorm_silu(x, g1, b1, return_sums=True)
-        h1 = ops.mtgemm(plan, h0, _bf(w1p), out_shape=(B, H, W, C), bias=_f32(c1b))
-        h2, s2 = ops.groupnorm_silu(h1, g2, b2, return_sums=True)
+        h1 = ops.mtgemm(plan, h0, _bf(w1p), out_shape=(B, H, W, C), bias=_f32(c1b), gn_groups=32)   # + GN2's statistics
+        h2, s2 = ops.groupnorm_silu(h1, g2, b2, sums=h1._gn_sums, return_sums=True)
         out = ops.mtgemm(plan, h2, _bf(w2p), out_shape=(B, H, W, C), bias=_f32(c2b), residual=x)
         ctx.save_for_backward(x, s1, h0, h1, s2, h2, g1, b1, w1p, g2, b2, w2p)
         return out

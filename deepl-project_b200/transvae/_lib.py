@@ -42,6 +42,7 @@ class MtGemmDesc(C.Structure):
         ("q_scale", C.c_float),
         ("out_f32", C.c_void_p), ("out_n", C.c_int32),
         ("act_grad", C.c_int32), ("z", C.c_void_p),
+        ("gn_sums", C.c_void_p), ("gn_groups", C.c_int32),
     ]
 
 
@@ -119,7 +120,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.tvae_abi_version() != 1:
+    if lib.tvae_abi_version() != 2:
         raise RuntimeError("libtransvae_sm100.so ABI version mismatch")
     _lib = lib
     return lib

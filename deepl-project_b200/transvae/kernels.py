@@ -45,10 +45,10 @@ def needs_grad(*ts) -> bool:
     return _needs_grad(*ts)
 
 
-def conv_in(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
+def conv_in(x: Tensor, w: Tensor, b: Optional[Tensor], gn_groups: int = 0) -> Tensor:
     if _needs_grad(x, w, b):
         return _ag().ConvInFn.apply(x, w, b)
-    return ops.conv_in(x, w, b)
+    return ops.conv_in(x, w, b, gn_groups=gn_groups)
 
 
 def mtgemm(plan, a0: Tensor, w: Tensor, **kw) -> Tensor:
@@ -71,7 +71,15 @@ def linear(x: Tensor, w: Tensor, plan, **kw) -> Tensor:
 def groupnorm_silu(x: Tensor, gamma: Tensor, beta: Tensor, silu: bool = True) -> Tensor:
     if _needs_grad(x, gamma, beta):
         return _ag().GroupNormSilu.apply(x, gamma, beta, silu)
-    return ops.groupnorm_silu(x, gamma, beta, silu=silu)
+    # statistics left on the tensor by the convolution that produced it (ops.mtgemm(..., gn_groups=32)): apply pass only
+    return ops.groupnorm_silu(x, gamma, beta, silu=silu, sums=gn_sums_of(x))
+
+
+def gn_sums_of(x: Tensor, groups: int = 32) -> Optional[Tensor]:
+    s = getattr(x, "_gn_sums", None)
+    if s is not None and tuple(s.shape) == (x.shape[0], groups, 2) and s.device == x.device:
+        return s
+    return None
 
 
 def row_stats(x: Tensor, w1: Optional[Tensor] = None, mode: Optional[int] = None):

@@ -42,6 +42,8 @@ class TransVAEDecoder(nn.Module):
             self.stages.append(blocks)
             if i < self.num_stages - 1:
                 self.upsamples.append(Upsample(d, base_dims[i + 1], use_dc_path=use_dc_path))
+                if i + 1 >= n_tr:             # a ResBlock stage follows: hand it the statistics of its input
+                    self.upsamples[-1].gn_groups_out = 32
         self.norm_out = _NormParams(base_dims[-1], 32)
         self.conv_out = _Conv2dParams(base_dims[-1], output_channels, 3)
         self.gradient_checkpointing = False

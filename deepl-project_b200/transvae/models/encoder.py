@@ -45,6 +45,8 @@ class TransVAEEncoder(nn.Module):
             self.stages.append(blocks)
             if i < self.num_stages - 1:
                 self.downsamples.append(Downsample(d, base_dims[i + 1], use_dc_path=use_dc_path))
+                if i + 1 < 2:                 # the next stage is a ResBlock stage: hand it the statistics of its input
+                    self.downsamples[-1].gn_groups_out = 32
         self.gradient_checkpointing = False
 
     def enable_gradient_checkpointing(self):
@@ -52,7 +54,7 @@ class TransVAEEncoder(nn.Module):
 
     def forward_features(self, x: torch.Tensor, trace: dict = None) -> torch.Tensor:
         """NCHW float image -> NHWC bf16 features [B, H/f, W/f, C_last]."""
-        h = K.conv_in(x, self.conv_in.weight, self.conv_in.bias)
+        h = K.conv_in(x, self.conv_in.weight, self.conv_in.bias, gn_groups=32)
         if trace is not None:
             trace["encoder.conv_in"] = h
         ckpt = self.gradient_checkpointing and self.training

@@ -82,11 +82,13 @@ class ResBlock(HotModule):
         plan = T.plan_conv3x3(C)
         w1 = self._packs.get("w1", [self.conv1.weight], lambda: bf16c(T.pack_conv3x3(self.conv1.weight)))
         w2 = self._packs.get("w2", [self.conv2.weight], lambda: bf16c(T.pack_conv3x3(self.conv2.weight)))
+        # every convolution whose output feeds a GroupNorm takes that norm's statistics in its epilogue (gn_groups):
+        # conv1 for norm2, conv2 (+ residual) for the next ResBlock's norm1 / decoder.norm_out
         h = K.groupnorm_silu(x, self.norm1.weight, self.norm1.bias)
-        h = K.mtgemm(plan, h, w1, out_shape=(B, H, W, C), bias=f32c(self.conv1.bias))
+        h = K.mtgemm(plan, h, w1, out_shape=(B, H, W, C), bias=f32c(self.conv1.bias), gn_groups=32)
         h = K.groupnorm_silu(h, self.norm2.weight, self.norm2.bias)
         return K.mtgemm(plan, h, w2, out_shape=(B, H, W, C), bias=f32c(self.conv2.bias),
-                        residual=x if add_residual else None)
+                        residual=x if add_residual else None, gn_groups=32 if add_residual else 0)
 
 
 class RMSNorm(nn.Module):

@@ -21,6 +21,9 @@ class Downsample(HotModule):
         from .blocks import _Conv2dParams
         self.use_dc_path = use_dc_path
         self.in_channels, self.out_channels = in_channels, out_channels
+        # set by the encoder / decoder when a ResBlock stage follows: the last convolution then also produces the
+        # GroupNorm(32) statistics of its output (ops.mtgemm gn_groups)
+        self.gn_groups_out = 0
         self.main_path = nn.Sequential(_Conv2dParams(in_channels, in_channels, 3), nn.SiLU(),
                                        _Conv2dParams(in_channels, out_channels, 3))
         if use_dc_path:                      # upsample.py:40-42: no dc_conv parameters without the DC path
@@ -40,7 +43,7 @@ class Downsample(HotModule):
                              lambda: bf16c(T.pack_downsample(m2.weight, wdc)))
         y = K.mtgemm(T.plan_conv3x3(C), x, w0, out_shape=(B, H, W, C), bias=f32c(m0.bias), act=K.ACT_SILU)
         return K.mtgemm(T.plan_downsample(C, with_dc=dc is not None), y, wd, a1=x if dc is not None else None,
-                        out_shape=(B, H // 2, W // 2, self.out_channels), bias=f32c(bias2))
+                        out_shape=(B, H // 2, W // 2, self.out_channels), bias=f32c(bias2), gn_groups=self.gn_groups_out)
 
 
 class Upsample(HotModule):
@@ -49,6 +52,9 @@ class Upsample(HotModule):
         from .blocks import _Conv2dParams
         self.use_dc_path = use_dc_path
         self.in_channels, self.out_channels = in_channels, out_channels
+        # set by the encoder / decoder when a ResBlock stage follows: the last convolution then also produces the
+        # GroupNorm(32) statistics of its output (ops.mtgemm gn_groups)
+        self.gn_groups_out = 0
         self.main_path = nn.Sequential(nn.Upsample(scale_factor=2, mode="nearest"),
                                        _Conv2dParams(in_channels, out_channels, 3), nn.SiLU(),
                                        _Conv2dParams(out_channels, out_channels, 3))
@@ -73,4 +79,4 @@ class Upsample(HotModule):
                              lambda: f32c(T.bias_upsample_conv2(m3.bias, bdc)))
         y = K.mtgemm(T.plan_upsample_conv1(Ci, Co), x, w1, out_shape=(B, 2 * H, 2 * W, Co), bias=b1, act=K.ACT_SILU)
         return K.mtgemm(T.plan_upsample_conv2(Co, Ci, with_dc=dc is not None), y, w2, a1=x if dc is not None else None,
-                        out_shape=(B, 2 * H, 2 * W, Co), bias=b2)
+                        out_shape=(B, 2 * H, 2 * W, Co), bias=b2, gn_groups=self.gn_groups_out)

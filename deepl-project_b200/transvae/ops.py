@@ -93,9 +93,13 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
            residual: Optional[Tensor] = None, row_scale: Optional[Tensor] = None, row_shift: Optional[Tensor] = None,
            col_sum: Optional[Tensor] = None, rope: Optional[Tuple[Tensor, int, int, int, float]] = None,
            out_f32: Optional[Tensor] = None, out_f32_shape: Optional[Sequence[int]] = None, out_n: int = 0,
-           act_grad_z: Optional[Tensor] = None) -> Tensor:
+           act_grad_z: Optional[Tensor] = None, gn_groups: int = 0) -> Tensor:
     """Launch ``tvae_mtgemm``.  a0 / a1 / out / residual are NHWC bf16 4-D tensors (flat matrices as
     [1, 1, M, K]); ``w`` is the packed bf16 [N, K_total] weight; ``bias`` fp32 [phases, N] (or [N]).
+
+    ``gn_groups`` > 0: the launch also produces the GroupNorm statistics of its output (per image and group: sum and
+    sum of squares, fp32 [B, gn_groups, 2]) -- from the GEMM epilogue when the launch qualifies, see the header -- and
+    attaches them to the returned tensor as ``out._gn_sums`` for ``groupnorm_silu(..., sums=...)``.
 
     Backward fusion: with ``act_grad_z`` (the saved pre-activation, same shape as the output) and ``act`` set, the launch
     returns ``acc * act'(z)`` -- or ``(acc + residual) * act'(z)`` when ``residual`` is given too (GELU, plain views)."""
@@ -145,6 +149,11 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
         d.rope_tab, d.q_scale = None, 1.0
     d.out_f32 = _ptr(out_f32)
     d.out_n = out_n
+    gn_sums = None
+    if gn_groups:
+        assert out_f32 is None and out.shape[-1] == n_total
+        gn_sums = torch.empty(out.shape[0], gn_groups, 2, dtype=torch.float32, device=a0.device)
+    d.gn_sums, d.gn_groups = _ptr(gn_sums), gn_groups
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -157,6 +166,8 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
         tag = f"{plan.name} M={m_out} N={n_total} K={plan.k_total} act={act} res={int(residual is not None)} rs={int(row_scale is not None)} rope={int(rope is not None)}"
         PROFILE.append((tag, 2.0 * m_out * n_real * plan.algo_k, e0, e1))
     _count()
+    if gn_sums is not None:
+        out._gn_sums = gn_sums
     return out if out_f32 is None else out_f32
 
 
@@ -201,8 +212,9 @@ def im2col_in(x: Tensor) -> Tensor:
     return cols
 
 
-def conv_in(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
-    """encoder.conv_in: NCHW fp32 image -> NHWC bf16 features (im2col + K = 64 tensor-core GEMM, bias in column 54)."""
+def conv_in(x: Tensor, w: Tensor, b: Optional[Tensor], gn_groups: int = 0) -> Tensor:
+    """encoder.conv_in: NCHW fp32 image -> NHWC bf16 features (im2col + K = 64 tensor-core GEMM, bias in column 54).
+    ``gn_groups``: also take the GroupNorm statistics of the output (``out._gn_sums``, see ``mtgemm``)."""
     _need_cuda(x, w, b)
     from . import _taps as T
     B, _, H, W = x.shape
@@ -211,8 +223,12 @@ def conv_in(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
     w27 = w.detach().float().reshape(co, 27)
     bias = torch.zeros(co, 1, dtype=torch.float32, device=w.device) if b is None else b.detach().float().reshape(co, 1)
     wp = torch.cat([w27, w27, bias, torch.zeros(co, 9, dtype=torch.float32, device=w.device)], dim=1).to(BF16).contiguous()
-    out = mtgemm(T.plan_linear(64), cols.view(1, 1, B * H * W, 64), wp, out_shape=(1, 1, B * H * W, co))
-    return out.view(B, H, W, co)
+    # one image per row of the tile grid ([B, 1, H*W, .] views), so that a 128-pixel tile never straddles two images
+    out = mtgemm(T.plan_linear(64), cols.view(B, 1, H * W, 64), wp, out_shape=(B, 1, H * W, co), gn_groups=gn_groups)
+    o4 = out.view(B, H, W, co)
+    if gn_groups:
+        o4._gn_sums = out._gn_sums
+    return o4
 
 
 def groupnorm_stats(x: Tensor, groups: int = 32) -> Tensor:

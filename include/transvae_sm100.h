@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TVAE_ABI_VERSION 1
+#define TVAE_ABI_VERSION 2
 #define TVAE_MAX_TAPS 16
 #define TVAE_MAX_PHASES 4
 
@@ -96,6 +96,14 @@ typedef struct {
   int32_t out_n;
   int32_t act_grad;                   /* 0: forward epilogue; 1 / 2: multiply by act'(.) (see above), `act` names it */
   const void* z;                      /* act_grad == 2: pre-activation [M, n_total] bf16, rows in output-pixel order */
+  /* Optional GroupNorm statistics of the OUTPUT (blocks.py:60,64 / decoder.py:128: the nn.GroupNorm that consumes this
+   * convolution): gn_sums[B][gn_groups][2] fp32 receives (sum, sum of squares) of the stored bf16 values per image and
+   * channel group, so the consumer needs tvae_groupnorm_apply only.  The library zeroes the buffer.  The sums come out
+   * of the GEMM epilogue (no extra pass over HBM) when the launch runs on the CTA-pair kernel with a bias / bias+residual
+   * epilogue, one image per 128-pixel tile and gn_groups <= 64; otherwise the library runs tvae_groupnorm_stats on the
+   * output behind the GEMM.  Requires a bf16 output whose channel count equals n_total. */
+  float* gn_sums;
+  int32_t gn_groups;
 } tvae_mtgemm_desc;
 
 int tvae_mtgemm(const tvae_mtgemm_desc* desc /* HOST pointer */, void* stream);

@@ -180,6 +180,60 @@ def test_attention_fwd_running_max(order):
     assert float((lse - ref_lse).abs().max()) < 2e-2
 
 
+def _gn_ref(y_nhwc, groups):
+    """(sum, sum of squares) per image and channel group of the stored bf16 tensor, fp64."""
+    B, H, W, C = y_nhwc.shape
+    v = y_nhwc.double().reshape(B, H * W, groups, C // groups)
+    return torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1)
+
+
+@pytest.mark.parametrize("B,C,H,W,N,res", [
+    (2, 192, 32, 32, 192, True),     # CTA-pair kernel, N = 192 (6 channels per group straddle the 8-wide vectors): fused
+    (3, 128, 16, 24, 256, False),    # W not a power of two: clipped rows must stay out of the sums; odd tile count
+    (2, 64, 16, 16, 128, True),      # N = 128
+    (5, 64, 8, 8, 128, False),       # 64 pixels per image -> two images per tile -> library falls back to the stats pass
+    (1, 64, 16, 16, 64, True),       # N = 64: 1-CTA kernel -> fallback
+])
+def test_conv3x3_gn_sums(B, C, H, W, N, res):
+    """tvae_mtgemm with gn_sums: GroupNorm(32) statistics of the convolution output from the GEMM epilogue
+    (blocks.py:60,64: the norm that consumes the convolution) == statistics of the stored tensor."""
+    x, w, b = bf(rnd(B, C, H, W)), bf(rnd(N, C, 3, 3, seed=1, scale=0.05)), rnd(N, seed=2)
+    r = nhwc(bf(rnd(B, N, H, W, seed=3))) if res else None
+    wp = T.pack_conv3x3(w).contiguous()
+    y0 = ops.mtgemm(T.plan_conv3x3(C), nhwc(x), wp, out_shape=(B, H, W, N), bias=b, residual=r)
+    y = ops.mtgemm(T.plan_conv3x3(C), nhwc(x), wp, out_shape=(B, H, W, N), bias=b, residual=r, gn_groups=32)
+    assert torch.equal(y, y0)                          # the statistics do not disturb the output
+    ref = _gn_ref(y, 32)
+    got = y._gn_sums.double()
+    assert got.shape == (B, 32, 2)
+    err = float(((got - ref).abs() / (ref.abs() + 1.0)).max())
+    assert err < 1e-4, err
+    # and they drive the apply pass to the same result as the two-pass kernel
+    g, be = rnd(N, seed=4) * 0.2 + 1, rnd(N, seed=5) * 0.1
+    a = ops.groupnorm_silu(y, g, be, sums=y._gn_sums)
+    c = ops.groupnorm_silu(y, g, be)
+    assert rel(a, c) < 4e-3, rel(a, c)
+
+
+def test_upsample_and_conv_in_gn_sums():
+    """Phase-split output (Upsample conv2 + DC path) and the [B, 1, H*W, .] view of conv_in."""
+    B, Ci, Co, H = 2, 128, 192, 16
+    x, y1 = bf(rnd(B, Ci, H, H)), bf(rnd(B, Co, 2 * H, 2 * H, seed=7))
+    w2, b2 = bf(rnd(Co, Co, 3, 3, seed=3, scale=0.05)), rnd(Co, seed=4)
+    wdc, bdc = bf(rnd(4 * Co, Ci, 1, 1, seed=5, scale=0.05)), rnd(4 * Co, seed=6)
+    out = ops.mtgemm(T.plan_upsample_conv2(Co, Ci), nhwc(y1), T.pack_upsample_conv2(w2, wdc).contiguous(), a1=nhwc(x),
+                     out_shape=(B, 2 * H, 2 * H, Co), bias=T.bias_upsample_conv2(b2, bdc).contiguous(), gn_groups=32)
+    ref = _gn_ref(out, 32)
+    err = float(((out._gn_sums.double() - ref).abs() / (ref.abs() + 1.0)).max())
+    assert err < 1e-4, err
+    xi, w, b = rnd(3, 3, 16, 24), rnd(192, 3, 3, 3, seed=1, scale=0.3), rnd(192, seed=2)
+    y = ops.conv_in(xi, w, b, gn_groups=32)
+    assert rel(nchw(y), F.conv2d(xi, w, b, padding=1)) < 8e-3
+    ref = _gn_ref(y, 32)
+    err = float(((y._gn_sums.double() - ref).abs() / (ref.abs() + 1.0)).max())
+    assert err < 1e-4, err
+
+
 def test_conv_in():
     x, w, b = rnd(2, 3, 32, 48), rnd(64, 3, 3, 3, seed=1, scale=0.3), rnd(64, seed=2)
     y = ops.conv_in(x, w, b)
