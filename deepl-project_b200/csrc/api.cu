@@ -41,6 +41,8 @@ int loss_bwd_run(const float* recon, const float* target, const float* mu, const
 int latent_bwd_run(const float* mu, const float* logvar, const float* eps, const float* dz, const float* dmu_ret,
                    const float* dlv_ret, float* dmu, float* dlv, long long n, int patched, cudaStream_t stream);
 int sumsq_run(const float* g, long long n, float* out, cudaStream_t stream);
+int weight_pack_run(const float* w, void* fwd, void* dgr, int A, int B, int T, cudaStream_t stream);
+int wgrad_unpack_run(const float* g, float* out, int A, int B, int T, cudaStream_t stream);
 int adamw_run(float* p, const float* g, float* m, float* v, long long n, const float* ctrl, float lr, float b1, float b2,
               float eps, float wd, int step, cudaStream_t stream);
 int metrics_run(const float* recon, const float* target, float* acc, int B, int C, int H, int W, int mode,
@@ -168,6 +170,12 @@ int tvae_loss_bwd(const float* recon, const float* target, const float* mu, cons
 int tvae_latent_bwd(const float* mu, const float* logvar, const float* eps, const float* dz, const float* dmu_ret,
                     const float* dlv_ret, float* dmu, float* dlogvar, int64_t n, int32_t patched, void* stream) {
   GUARD(); return latent_bwd_run(mu, logvar, eps, dz, dmu_ret, dlv_ret, dmu, dlogvar, n, patched, S_(stream));
+}
+int tvae_weight_pack(const float* w, void* fwd_bf16, void* dgrad_bf16, int32_t A, int32_t B, int32_t T, void* stream) {
+  GUARD(); return weight_pack_run(w, fwd_bf16, dgrad_bf16, A, B, T, S_(stream));
+}
+int tvae_wgrad_unpack(const float* g_packed, float* g_ref, int32_t A, int32_t B, int32_t T, void* stream) {
+  GUARD(); return wgrad_unpack_run(g_packed, g_ref, A, B, T, S_(stream));
 }
 int tvae_sumsq(const float* g, int64_t n, float* out, void* stream) { GUARD(); return sumsq_run(g, n, out, S_(stream)); }
 int tvae_adamw(float* p, const float* g, float* m, float* v, int64_t n, const float* ctrl, float lr, float beta1, float beta2,

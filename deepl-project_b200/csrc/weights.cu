@@ -1,0 +1,159 @@
+// Weight-side re-layout kernels of the training step (HBM-bound, once per weight and micro-step).
+//
+// The reference keeps nn.Linear weights as [out, in] and nn.Conv2d weights as [out, in, kh, kw] fp32
+// (transvae/modules/conv.py:39-65, blocks.py:34-37, attention.py:43-48); the tensor-core kernels want bf16 operands
+// with K contiguous: the forward GEMM reads W_f[out][tap * in + i], the input-gradient GEMM reads
+// W_d[in][tap * out + o].  Doing these permutes with strided torch copies cost 24 ms per training micro-step
+// (1.05 G parameters, at:: elementwise kernels at a few hundred GB/s); here each is one coalesced tile transpose
+// through shared memory.
+//
+//   weight_pack   : fp32 ref[A][B][T]  ->  bf16 fwd[A][T][B]  and / or  bf16 dgr[B][T][A]      (T = 1 or 9)
+//   wgrad_unpack  : fp32 packed gradient g[A][T][B]  ->  fp32 ref-layout gradient [A][B][T]
+//
+// Algorithmic bytes: pack 4 + 2 (+ 2) per parameter, unpack 8 per parameter.
+#include "../../include/transvae_sm100.h"
+#include "common.cuh"
+
+namespace tvae {
+
+constexpr int kWpTile = 32;
+
+// One block = one 32 (a) x 32 (b) tile with all T taps.  smem row = one `a`: [b][t] as in memory, padded to an odd
+// number of floats so that both read-back patterns (b fastest with stride T, a fastest with the row stride) are
+// conflict-free for T = 1 and T = 9.
+template <int T>
+__global__ void __launch_bounds__(256) weight_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
+                                                          __nv_bfloat16* __restrict__ dgr, int A, int B) {
+  constexpr int kRow = kWpTile * T + 1;   // odd
+  __shared__ float tile[kWpTile][kRow];
+  const int a0 = blockIdx.y * kWpTile, b0 = blockIdx.x * kWpTile;
+  const int nb = min(kWpTile, B - b0), na = min(kWpTile, A - a0);
+  // load: for each a the segment w[a][b0 .. b0+nb)[0 .. T) is contiguous (nb * T floats)
+  for (int i = threadIdx.x; i < kWpTile * kWpTile * T; i += 256) {
+    const int a = i / (kWpTile * T), r = i - a * (kWpTile * T);
+    if (a < na && r < nb * T) tile[a][r] = __ldg(w + ((size_t)(a0 + a) * B + b0) * T + r);
+  }
+  __syncthreads();
+  if (fwd != nullptr) {
+    // fwd[a][t * B + b]: lanes run over pairs of b (one 4-byte store each, 64-byte runs per (a, t))
+    for (int i = threadIdx.x; i < kWpTile * T * (kWpTile / 2); i += 256) {
+      const int bp = i % (kWpTile / 2), at = i / (kWpTile / 2);
+      const int t = at % T, a = at / T;
+      const int b = 2 * bp;
+      if (a < na && b < nb) {
+        __nv_bfloat16* dst = fwd + ((size_t)(a0 + a) * T + t) * B + b0 + b;
+        if (b + 1 < nb) {
+          *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(tile[a][b * T + t], tile[a][(b + 1) * T + t]);
+        } else {
+          *dst = __float2bfloat16_rn(tile[a][b * T + t]);
+        }
+      }
+    }
+  }
+  if (dgr != nullptr) {
+    // dgr[b][t * A + a]: lanes run over pairs of a
+    for (int i = threadIdx.x; i < kWpTile * T * (kWpTile / 2); i += 256) {
+      const int ap = i % (kWpTile / 2), bt = i / (kWpTile / 2);
+      const int t = bt % T, b = bt / T;
+      const int a = 2 * ap;
+      if (b < nb && a < na) {
+        __nv_bfloat16* dst = dgr + ((size_t)(b0 + b) * T + t) * A + a0 + a;
+        if (a + 1 < na) {
+          *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(tile[a][b * T + t], tile[a + 1][b * T + t]);
+        } else {
+          *dst = __float2bfloat16_rn(tile[a][b * T + t]);
+        }
+      }
+    }
+  }
+}
+
+// T = 1 (nn.Linear): 64 x 64 tiles, 16-byte loads, 8-byte stores (128-byte runs on both outputs).
+__global__ void __launch_bounds__(256) weight_pack_lin_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
+                                                              __nv_bfloat16* __restrict__ dgr, int A, int B) {
+  __shared__ float tile[64][65];
+  const int a0 = blockIdx.y * 64, b0 = blockIdx.x * 64;
+  const int c4 = (threadIdx.x & 15) * 4, r0 = threadIdx.x >> 4;
+  float4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int a = a0 + r0 + 16 * k;
+    v[k] = (a < A && b0 + c4 < B) ? __ldg(reinterpret_cast<const float4*>(w + (size_t)a * B + b0 + c4))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + 16 * k;
+    tile[r][c4] = v[k].x; tile[r][c4 + 1] = v[k].y; tile[r][c4 + 2] = v[k].z; tile[r][c4 + 3] = v[k].w;
+    if (fwd != nullptr && a0 + r < A && b0 + c4 < B) {
+      uint2 o;
+      o.x = pack_bf16(v[k].x, v[k].y);
+      o.y = pack_bf16(v[k].z, v[k].w);
+      *reinterpret_cast<uint2*>(fwd + (size_t)(a0 + r) * B + b0 + c4) = o;
+    }
+  }
+  if (dgr == nullptr) return;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int b = r0 + 16 * k;     // row of the transposed tile
+    if (b0 + b < B && a0 + c4 < A) {
+      uint2 o;
+      o.x = pack_bf16(tile[c4][b], tile[c4 + 1][b]);
+      o.y = pack_bf16(tile[c4 + 2][b], tile[c4 + 3][b]);
+      *reinterpret_cast<uint2*>(dgr + (size_t)(b0 + b) * A + a0 + c4) = o;
+    }
+  }
+}
+
+int weight_pack_run(const float* w, void* fwd, void* dgr, int A, int B, int T, cudaStream_t stream) {
+  TVAE_REQUIRE(w != nullptr && (fwd != nullptr || dgr != nullptr), "weight_pack: missing operand");
+  TVAE_REQUIRE(A >= 1 && B >= 1 && (T == 1 || T == 9), "weight_pack: unsupported shape [%d][%d][%d] (T = 1 or 9)", A, B, T);
+  if (T == 1) {
+    // 16-byte loads / 8-byte stores need rows that are multiples of four elements
+    TVAE_REQUIRE(A % 4 == 0 && B % 4 == 0, "weight_pack: A = %d and B = %d must be multiples of 4 for a matrix", A, B);
+    dim3 grid((B + 63) / 64, (A + 63) / 64);
+    TVAE_REQUIRE(grid.y <= 65535, "weight_pack: A = %d too large", A);
+    weight_pack_lin_kernel<<<grid, 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(fwd),
+                                                     reinterpret_cast<__nv_bfloat16*>(dgr), A, B);
+  } else {
+    // the paired 4-byte stores need even row lengths
+    TVAE_REQUIRE(A % 2 == 0 && B % 2 == 0, "weight_pack: A = %d and B = %d must be even", A, B);
+    dim3 grid((B + kWpTile - 1) / kWpTile, (A + kWpTile - 1) / kWpTile);
+    TVAE_REQUIRE(grid.y <= 65535, "weight_pack: A = %d too large", A);
+    weight_pack_kernel<9><<<grid, 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(fwd),
+                                                    reinterpret_cast<__nv_bfloat16*>(dgr), A, B);
+  }
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// g[a][t][b] -> out[a][b][t]: one block = one `a` and 128 consecutive b; reads T runs of 512 bytes, writes one run of
+// 128 * T floats.
+template <int T>
+__global__ void __launch_bounds__(128) wgrad_unpack_kernel(const float* __restrict__ g, float* __restrict__ out, int A, int B) {
+  __shared__ float tile[T][128 + 1];
+  const int a = blockIdx.y, b0 = blockIdx.x * 128;
+  const int nb = min(128, B - b0);
+  const float* src = g + (size_t)a * T * B + b0;
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+    if ((int)threadIdx.x < nb) tile[t][threadIdx.x] = __ldg(src + (size_t)t * B + threadIdx.x);
+  __syncthreads();
+  float* dst = out + ((size_t)a * B + b0) * T;
+  for (int i = threadIdx.x; i < nb * T; i += 128) {
+    const int b = i / T, t = i - b * T;
+    dst[i] = tile[t][b];
+  }
+}
+
+int wgrad_unpack_run(const float* g, float* out, int A, int B, int T, cudaStream_t stream) {
+  TVAE_REQUIRE(g != nullptr && out != nullptr, "wgrad_unpack: missing operand");
+  TVAE_REQUIRE(A >= 1 && A <= 65535 && B >= 1 && T == 9, "wgrad_unpack: unsupported shape [%d][%d][%d] (T = 9)", A, T, B);
+  dim3 grid((B + 127) / 128, A);
+  wgrad_unpack_kernel<9><<<grid, 128, 0, stream>>>(g, out, A, B);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tvae

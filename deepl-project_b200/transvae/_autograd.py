@@ -14,6 +14,7 @@ normalised token tensors with ``tvae_token_norm_fwd`` so that the projections st
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -42,6 +43,40 @@ def _f32(t: Tensor) -> Tensor:
     return t.detach().float().contiguous()
 
 
+# Reference-layout weights ([out, in] linears, [out, in, 3, 3] convolutions) -> bf16 kernel operands and back.  fp32
+# contiguous weights take one coalesced ``tvae_weight_pack`` / ``tvae_wgrad_unpack`` pass; anything else the torch route
+# (TVAE_TORCH_PACK=1 forces it: A/B switch for the bench).
+_TORCH_PACK = os.environ.get("TVAE_TORCH_PACK", "0") == "1"
+
+
+def _packable(w: Tensor) -> bool:
+    if _TORCH_PACK or w.dtype != torch.float32 or not w.is_contiguous():
+        return False
+    if w.dim() == 2:
+        return w.shape[0] % 4 == 0 and w.shape[1] % 4 == 0
+    return w.dim() == 4 and tuple(w.shape[2:]) == (3, 3) and w.shape[0] % 2 == 0 and w.shape[1] % 2 == 0
+
+
+def _w_pack(w: Tensor):
+    """(forward operand [out, taps*in], input-gradient operand [in, taps*out]), both bf16, from ONE read of ``w``: the
+    second is kept for the backward pass."""
+    w = w.detach()
+    if _packable(w):
+        return ops.weight_pack(w, fwd=True, dgrad=True)
+    if w.dim() == 4:
+        return _bf(T.pack_conv3x3(w)), _bf(T.pack_conv3x3_dgrad(w))
+    return _bf(w), _bf(w.t())
+
+
+def _w_ungrad(gp: Tensor, w: Tensor) -> Tensor:
+    """packed fp32 gradient [out, taps*in] -> the layout of ``w``."""
+    if w.dim() == 2:
+        return gp
+    if gp.dtype == torch.float32 and gp.is_contiguous():
+        return ops.wgrad_unpack(gp, w.shape)
+    return gp.view(w.shape[0], 3, 3, w.shape[1]).permute(0, 3, 1, 2)
+
+
 def _wgrad_b(plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[Tensor] = None):
     """(dW, dbias) of a single-phase plan in one launch: the bias gradient (column sums of dZ) rides on the wgrad
     kernel's tensor-core pass instead of a separate sweep over dZ."""
@@ -58,29 +93,31 @@ class ResBlockFn(Fn):
     """x + conv2(silu(GN2(conv1(silu(GN1(x))))))  (blocks.py:58-68)."""
 
     @staticmethod
-    def forward(ctx, x, g1, b1, w1p, c1b, g2, b2, w2p, c2b):
+    def forward(ctx, x, g1, b1, w1, c1b, g2, b2, w2, c2b):
+        # w1 / w2: conv weights in the reference layout [C, C, 3, 3]
         B, H, W, C = x.shape
         plan = T.plan_conv3x3(C)
         h0, s1 = ops.groupnorm_silu(x, g1, b1, return_sums=True)
-        h1 = ops.mtgemm(plan, h0, _bf(w1p), out_shape=(B, H, W, C), bias=_f32(c1b), gn_groups=32)   # + GN2's statistics
+        (w1f, w1d), (w2f, w2d) = _w_pack(w1), _w_pack(w2)
+        h1 = ops.mtgemm(plan, h0, w1f, out_shape=(B, H, W, C), bias=_f32(c1b), gn_groups=32)   # + GN2's statistics
         h2, s2 = ops.groupnorm_silu(h1, g2, b2, sums=h1._gn_sums, return_sums=True)
-        out = ops.mtgemm(plan, h2, _bf(w2p), out_shape=(B, H, W, C), bias=_f32(c2b), residual=x)
-        ctx.save_for_backward(x, s1, h0, h1, s2, h2, g1, b1, w1p, g2, b2, w2p)
+        out = ops.mtgemm(plan, h2, w2f, out_shape=(B, H, W, C), bias=_f32(c2b), residual=x)
+        ctx.save_for_backward(x, s1, h0, h1, s2, h2, g1, b1, w1, g2, b2, w2, w1d, w2d)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, s1, h0, h1, s2, h2, g1, b1, w1p, g2, b2, w2p = ctx.saved_tensors
+        x, s1, h0, h1, s2, h2, g1, b1, w1, g2, b2, w2, w1d, w2d = ctx.saved_tensors
         dout = dout.contiguous()
         B, H, W, C = x.shape
         dplan = T.plan_conv3x3_dgrad(C)
         dw2, dc2b = _wgrad_b(T.plan_conv3x3(C), h2, dout, C)
-        dh2 = ops.mtgemm(dplan, dout, _tr(w2p, 9), out_shape=(B, H, W, C))
+        dh2 = ops.mtgemm(dplan, dout, w2d, out_shape=(B, H, W, C))
         dh1, dg2, db2 = ops.groupnorm_bwd(h1, dh2, s2, g2, b2)
         dw1, dc1b = _wgrad_b(T.plan_conv3x3(C), h0, dh1, C)
-        dh0 = ops.mtgemm(dplan, dh1, _tr(w1p, 9), out_shape=(B, H, W, C))
+        dh0 = ops.mtgemm(dplan, dh1, w1d, out_shape=(B, H, W, C))
         dx, dg1, db1 = ops.groupnorm_bwd(x, dh0, s1, g1, b1, add=dout)
-        return dx, dg1, db1, dw1, dc1b, dg2, db2, dw2, dc2b
+        return dx, dg1, db1, _w_ungrad(dw1, w1), dc1b, dg2, db2, _w_ungrad(dw2, w2), dc2b
 
 
 class DownsampleFn(Fn):
@@ -159,27 +196,28 @@ class AttnFn(Fn):
         S = H * W
         xh = ops.token_norm_fwd(x, w1, 1)
         rope = (rope_tab, C, H, W, scale * math.log2(math.e))
-        qkv = ops.mtgemm(T.plan_linear(C), _flat(xh), _bf(wqkv), out_shape=(1, 1, B * S, 3 * C), bias=_f32(bqkv), rope=rope)
+        (wqkv_f, wqkv_d), (wproj_f, wproj_d) = _w_pack(wqkv), _w_pack(wproj)
+        qkv = ops.mtgemm(T.plan_linear(C), _flat(xh), wqkv_f, out_shape=(1, 1, B * S, 3 * C), bias=_f32(bqkv), rope=rope)
         o, lse = ops.attn_fwd(qkv.view(B, S, 3 * C), B, S, C, need_lse=True)
-        out = ops.mtgemm(T.plan_linear(C), _flat(o), _bf(wproj), out_shape=(1, 1, B * S, C), bias=_f32(bproj),
+        out = ops.mtgemm(T.plan_linear(C), _flat(o), wproj_f, out_shape=(1, 1, B * S, C), bias=_f32(bproj),
                          residual=_flat(x))
-        ctx.save_for_backward(x, w1, xh, qkv, o, lse, wqkv, wproj, rope_tab)
+        ctx.save_for_backward(x, w1, xh, qkv, o, lse, wqkv_d, wproj_d, rope_tab)
         ctx.scale = scale
         return out.view(B, H, W, C)
 
     @staticmethod
     def backward(ctx, dout):
-        x, w1, xh, qkv, o, lse, wqkv, wproj, rope_tab = ctx.saved_tensors
+        x, w1, xh, qkv, o, lse, wqkv_d, wproj_d, rope_tab = ctx.saved_tensors
         dout = dout.contiguous()
         B, H, W, C = x.shape
         S = H * W
         df = _flat(dout)
         dwp, dbp = _wgrad_b(T.plan_linear(C), _flat(o), df, C)
-        do = ops.mtgemm(T.plan_linear(C), df, _bf(wproj.detach().t()), out_shape=(1, 1, B * S, C))
+        do = ops.mtgemm(T.plan_linear(C), df, wproj_d, out_shape=(1, 1, B * S, C))
         dqkv = ops.attn_bwd(qkv.view(B, S, 3 * C), o, do.view(B, S, C), lse, rope_tab, B, S, C, H, W, ctx.scale)
         dq = _flat(dqkv)
         dwq, dbq = _wgrad_b(T.plan_linear(C), _flat(xh), dq, 3 * C)
-        dxh = ops.mtgemm(T.plan_linear(3 * C), dq, _bf(wqkv.detach().t()), out_shape=(1, 1, B * S, C))
+        dxh = ops.mtgemm(T.plan_linear(3 * C), dq, wqkv_d, out_shape=(1, 1, B * S, C))
         dx, dw1 = ops.token_norm_bwd(x, w1, dxh.view(B, H, W, C), dout, 1)
         return dx, dw1, dwq, dbq, dwp, dbp, None, None
 
@@ -188,48 +226,52 @@ class FfnFn(Fn):
     """x + proj_out(u + conv(u)), u = gelu(proj_in(RMSNorm(x; w2)))  (blocks.py:149, conv.py:79-105)."""
 
     @staticmethod
-    def forward(ctx, x, w2n, win, bin_, wc0, bc0, wc2p, bc2, wc4, bc4, wout, bout):
+    def forward(ctx, x, w2n, win, bin_, wc0, bc0, wc2, bc2, wc4, bc4, wout, bout):
+        # win / wc0 / wc4 / wout: [out, in] matrices; wc2: the 3x3 conv weight in the reference layout [mid, mid, 3, 3]
         B, H, W, C = x.shape
         M = B * H * W
         hid, mid = win.shape[0], wc0.shape[0]
+        (win_f, win_d), (wc0_f, wc0_d), (wc2_f, wc2_d) = _w_pack(win), _w_pack(wc0), _w_pack(wc2)
+        (wc4_f, wc4_d), (wout_f, wout_d) = _w_pack(wc4), _w_pack(wout)
         xn = ops.token_norm_fwd(x, w2n, 0)
-        z_in = ops.mtgemm(T.plan_linear(C), _flat(xn), _bf(win), out_shape=(1, 1, M, hid), bias=_f32(bin_))
+        z_in = ops.mtgemm(T.plan_linear(C), _flat(xn), win_f, out_shape=(1, 1, M, hid), bias=_f32(bin_))
         u = ops.act_fwd(z_in, ACT_GELU)
-        z0 = ops.mtgemm(T.plan_linear(hid), u, _bf(wc0), out_shape=(1, 1, M, mid), bias=_f32(bc0))
+        z0 = ops.mtgemm(T.plan_linear(hid), u, wc0_f, out_shape=(1, 1, M, mid), bias=_f32(bc0))
         t0 = ops.act_fwd(z0, ACT_GELU)
-        z2 = ops.mtgemm(T.plan_conv3x3(mid), t0.view(B, H, W, mid), _bf(wc2p), out_shape=(B, H, W, mid), bias=_f32(bc2))
+        z2 = ops.mtgemm(T.plan_conv3x3(mid), t0.view(B, H, W, mid), wc2_f, out_shape=(B, H, W, mid), bias=_f32(bc2))
         t2 = ops.act_fwd(z2, ACT_GELU)
-        u2 = ops.mtgemm(T.plan_linear(mid), _flat(t2), _bf(wc4), out_shape=(1, 1, M, hid), bias=_f32(bc4), residual=u)
-        out = ops.mtgemm(T.plan_linear(hid), u2, _bf(wout), out_shape=(1, 1, M, C), bias=_f32(bout), residual=_flat(x))
-        ctx.save_for_backward(x, w2n, xn, z_in, u, z0, t0, z2, t2, u2, win, wc0, wc2p, wc4, wout)
+        u2 = ops.mtgemm(T.plan_linear(mid), _flat(t2), wc4_f, out_shape=(1, 1, M, hid), bias=_f32(bc4), residual=u)
+        out = ops.mtgemm(T.plan_linear(hid), u2, wout_f, out_shape=(1, 1, M, C), bias=_f32(bout), residual=_flat(x))
+        ctx.save_for_backward(x, w2n, xn, z_in, u, z0, t0, z2, t2, u2, wc2, win_d, wc0_d, wc2_d, wc4_d, wout_d)
+        ctx.dims = (hid, mid)
         return out.view(B, H, W, C)
 
     @staticmethod
     def backward(ctx, dout):
-        x, w2n, xn, z_in, u, z0, t0, z2, t2, u2, win, wc0, wc2p, wc4, wout = ctx.saved_tensors
+        x, w2n, xn, z_in, u, z0, t0, z2, t2, u2, wc2, win_d, wc0_d, wc2_d, wc4_d, wout_d = ctx.saved_tensors
         dout = dout.contiguous()
         B, H, W, C = x.shape
         M = B * H * W
-        hid, mid = win.shape[0], wc0.shape[0]
+        hid, mid = ctx.dims
         df = _flat(dout)
         dwout, dbout = _wgrad_b(T.plan_linear(hid), u2, df, C)
-        du2 = ops.mtgemm(T.plan_linear(C), df, _bf(wout.detach().t()), out_shape=(1, 1, M, hid))
+        du2 = ops.mtgemm(T.plan_linear(C), df, wout_d, out_shape=(1, 1, M, hid))
         dwc4, dbc4 = _wgrad_b(T.plan_linear(mid), _flat(t2), du2, hid)
         # every dZ = dY * gelu'(Z) of the block is produced by the epilogue of the GEMM that computes dY (act_grad), every
         # bias gradient by the wgrad launch that consumes dZ: no separate pass over the [M, 4C] / [M, C] gradients
-        dz2 = ops.mtgemm(T.plan_linear(hid), du2, _bf(wc4.detach().t()), out_shape=(1, 1, M, mid), act=ACT_GELU,
+        dz2 = ops.mtgemm(T.plan_linear(hid), du2, wc4_d, out_shape=(1, 1, M, mid), act=ACT_GELU,
                          act_grad_z=z2.view(1, 1, M, mid))
         dz2i = dz2.view(B, H, W, mid)
         dwc2, dbc2 = _wgrad_b(T.plan_conv3x3(mid), t0.view(B, H, W, mid), dz2i, mid)
-        dz0 = ops.mtgemm(T.plan_conv3x3_dgrad(mid), dz2i, _tr(wc2p, 9), out_shape=(B, H, W, mid), act=ACT_GELU,
+        dz0 = ops.mtgemm(T.plan_conv3x3_dgrad(mid), dz2i, wc2_d, out_shape=(B, H, W, mid), act=ACT_GELU,
                          act_grad_z=z0.view(B, H, W, mid)).view(1, 1, M, mid)
         dwc0, dbc0 = _wgrad_b(T.plan_linear(hid), u, dz0, mid)
-        dzin = ops.mtgemm(T.plan_linear(mid), dz0, _bf(wc0.detach().t()), out_shape=(1, 1, M, hid), residual=du2,
+        dzin = ops.mtgemm(T.plan_linear(mid), dz0, wc0_d, out_shape=(1, 1, M, hid), residual=du2,
                           act=ACT_GELU, act_grad_z=z_in)
         dwin, dbin = _wgrad_b(T.plan_linear(C), _flat(xn), dzin, hid)
-        dxn = ops.mtgemm(T.plan_linear(hid), dzin, _bf(win.detach().t()), out_shape=(1, 1, M, C))
+        dxn = ops.mtgemm(T.plan_linear(hid), dzin, win_d, out_shape=(1, 1, M, C))
         dx, dw2n = ops.token_norm_bwd(x, w2n, dxn.view(B, H, W, C), dout, 0)
-        return dx, dw2n, dwin, dbin, dwc0, dbc0, dwc2, dbc2, dwc4, dbc4, dwout, dbout
+        return dx, dw2n, dwin, dbin, dwc0, dbc0, _w_ungrad(dwc2, wc2), dbc2, dwc4, dbc4, dwout, dbout
 
 
 class ConvInFn(Fn):

@@ -514,6 +514,34 @@ def latent_bwd(mu: Tensor, logvar: Tensor, eps: Tensor, dz: Optional[Tensor], dm
     return dmu, dlv
 
 
+def weight_pack(w: Tensor, fwd: bool = True, dgrad: bool = False) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    """fp32 parameter in the reference layout -- nn.Linear [A, B] or nn.Conv2d 3x3 [A, B, 3, 3] -- to the bf16 operands of
+    the tensor-core kernels: forward [A, T*B] (== ``_taps.pack_conv3x3`` + cast) and / or input-gradient [B, T*A]
+    (== ``_taps.pack_conv3x3_dgrad`` + cast), one coalesced pass each (``tvae_weight_pack``)."""
+    _need_cuda(w)
+    assert w.dtype == torch.float32 and w.is_contiguous() and w.dim() in (2, 4), (w.dtype, w.shape)
+    A, B_ = w.shape[0], w.shape[1]
+    T_ = 1 if w.dim() == 2 else w.shape[2] * w.shape[3]
+    wf = torch.empty(A, T_ * B_, dtype=BF16, device=w.device) if fwd else None
+    wd = torch.empty(B_, T_ * A, dtype=BF16, device=w.device) if dgrad else None
+    with _hbm("weight_pack", w.numel() * (4 + 2 * (int(fwd) + int(dgrad)))):
+        _lib.check(_lib.load().tvae_weight_pack(w.data_ptr(), _ptr(wf), _ptr(wd), A, B_, T_, _stream()), "tvae_weight_pack")
+    _count()
+    return wf, wd
+
+
+def wgrad_unpack(g: Tensor, shape: Sequence[int]) -> Tensor:
+    """Packed weight gradient fp32 [A, 9*B] (``mtgemm_wgrad`` of a 3x3 convolution) -> parameter layout [A, B, 3, 3]."""
+    _need_cuda(g)
+    A, B_ = int(shape[0]), int(shape[1])
+    assert g.dtype == torch.float32 and g.is_contiguous() and tuple(g.shape) == (A, 9 * B_) and tuple(shape[2:]) == (3, 3)
+    out = torch.empty(A, B_, 3, 3, dtype=torch.float32, device=g.device)
+    with _hbm("wgrad_unpack", g.numel() * 8):
+        _lib.check(_lib.load().tvae_wgrad_unpack(g.data_ptr(), out.data_ptr(), A, B_, 9, _stream()), "tvae_wgrad_unpack")
+    _count()
+    return out
+
+
 def sumsq(g: Tensor, out: Tensor) -> None:
     """out[0] += sum(g^2) for a flat fp32 buffer (length % 4 == 0)."""
     _need_cuda(g, out)

@@ -202,6 +202,16 @@ int tvae_loss_bwd(const float* recon, const float* target, const float* mu, cons
 int tvae_latent_bwd(const float* mu, const float* logvar, const float* eps, const float* dz, const float* dmu_ret,
                     const float* dlv_ret, float* dmu, float* dlogvar, int64_t n, int32_t patched, void* stream);
 
+/* ---- weight-side re-layout (training step) --------------------------------------------------------------------
+ * The reference stores nn.Linear weights as [out, in] and nn.Conv2d 3x3 weights as [out, in, 3, 3] fp32
+ * (conv.py:39-65, blocks.py:34-37, attention.py:43-48).  tvae_weight_pack turns such a parameter w[A][B][T] (T = 1 or 9)
+ * into the bf16 operands of the tensor-core kernels: fwd[A][T*B] (K index t*B + b: the forward tvae_mtgemm weight) and /
+ * or dgr[B][T*A] (K index t*A + a: the weight of the input-gradient tvae_mtgemm); either output may be NULL.
+ * tvae_wgrad_unpack maps a packed weight gradient g[A][T*B] fp32 (tvae_mtgemm_wgrad output) back to the parameter
+ * layout [A][B][T] (T = 9).  Both replace strided torch permute / cast copies. */
+int tvae_weight_pack(const float* w, void* fwd_bf16, void* dgrad_bf16, int32_t A, int32_t B, int32_t T, void* stream);
+int tvae_wgrad_unpack(const float* g_packed, float* g_ref, int32_t A, int32_t B, int32_t T, void* stream);
+
 /* ---- optimiser (train.py:608-620: clip_grad_norm_ + fused AdamW) ----------------------------------
  * tvae_sumsq: out[0] += sum g^2 over a flat fp32 buffer (n % 4 == 0).
  * tvae_adamw: one fused step over flat fp32 p / g / m / v.  ctrl (device fp32[4]) = {global sum of squared grads,

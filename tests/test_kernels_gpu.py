@@ -234,6 +234,24 @@ def test_upsample_and_conv_in_gn_sums():
     assert err < 1e-4, err
 
 
+@pytest.mark.parametrize("A,B,taps", [(192, 192, 9), (384, 1536, 1), (1536, 384, 1), (64, 34, 9), (132, 68, 1), (768, 768, 9)])
+def test_weight_pack_and_unpack(A, B, taps):
+    """tvae_weight_pack / tvae_wgrad_unpack == the torch permutes of _taps.pack_conv3x3 / pack_conv3x3_dgrad (bit-exact:
+    pure data movement plus one round-to-nearest bf16 conversion)."""
+    w = rnd(A, B, 3, 3) if taps == 9 else rnd(A, B)
+    wf, wd = ops.weight_pack(w, fwd=True, dgrad=True)
+    if taps == 9:
+        assert torch.equal(wf, bf(T.pack_conv3x3(w)).contiguous())
+        assert torch.equal(wd, bf(T.pack_conv3x3_dgrad(w)).contiguous())
+        g = rnd(A, 9 * B, seed=5)
+        assert torch.equal(ops.wgrad_unpack(g, w.shape), g.view(A, 3, 3, B).permute(0, 3, 1, 2).contiguous())
+    else:
+        assert torch.equal(wf, bf(w))
+        assert torch.equal(wd, bf(w.t()).contiguous())
+    only_f, none_d = ops.weight_pack(w, fwd=True, dgrad=False)
+    assert none_d is None and torch.equal(only_f, wf)
+
+
 def test_conv_in():
     x, w, b = rnd(2, 3, 32, 48), rnd(64, 3, 3, 3, seed=1, scale=0.3), rnd(64, seed=2)
     y = ops.conv_in(x, w, b)
