@@ -47,6 +47,15 @@ def _f32(t: Tensor) -> Tensor:
 # contiguous weights take one coalesced ``tvae_weight_pack`` / ``tvae_wgrad_unpack`` pass; anything else the torch route
 # (TVAE_TORCH_PACK=1 forces it: A/B switch for the bench).
 _TORCH_PACK = os.environ.get("TVAE_TORCH_PACK", "0") == "1"
+# TVAE_DIRECT_GRAD=0: no per-step operand cache and no wgrad accumulation straight into the trainer's flat gradient slots
+_DIRECT = os.environ.get("TVAE_DIRECT_GRAD", "1") != "0"
+
+
+_PACKS: dict = {}          # id(parameter) -> (signature, (forward operand, input-gradient operand))
+
+
+def clear_pack_cache() -> None:
+    _PACKS.clear()
 
 
 def _packable(w: Tensor) -> bool:
@@ -60,9 +69,22 @@ def _packable(w: Tensor) -> bool:
 def _w_pack(w: Tensor):
     """(forward operand [out, taps*in], input-gradient operand [in, taps*out]), both bf16, from ONE read of ``w``: the
     second is kept for the backward pass."""
-    w = w.detach()
+    # parameters owned by trainer.GradBuckets only change in the optimizer step (which bumps ops.WEIGHT_EPOCH): with
+    # gradient accumulation their operands are packed once per step, not once per micro-step
+    cached = _DIRECT and getattr(w, "_tvae_direct_grad", False) and w.is_leaf
+    if cached:
+        sig = (ops.WEIGHT_EPOCH, w._version, w.data_ptr(), tuple(w.shape))
+        hit = _PACKS.get(id(w))
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+    w0, w = w, w.detach()
+    if w.dim() == 4 and w.shape[2] == 1 and w.shape[3] == 1:        # 1x1 convolution = matrix
+        w = w.reshape(w.shape[0], w.shape[1])
     if _packable(w):
-        return ops.weight_pack(w, fwd=True, dgrad=True)
+        out = ops.weight_pack(w, fwd=True, dgrad=True)
+        if cached:
+            _PACKS[id(w0)] = (sig, out)
+        return out
     if w.dim() == 4:
         return _bf(T.pack_conv3x3(w)), _bf(T.pack_conv3x3_dgrad(w))
     return _bf(w), _bf(w.t())
@@ -77,11 +99,30 @@ def _w_ungrad(gp: Tensor, w: Tensor) -> Tensor:
     return gp.view(w.shape[0], 3, 3, w.shape[1]).permute(0, 3, 1, 2)
 
 
-def _wgrad_b(plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[Tensor] = None):
+def _wgrad_b(plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[Tensor] = None, w: Optional[Tensor] = None):
     """(dW, dbias) of a single-phase plan in one launch: the bias gradient (column sums of dZ) rides on the wgrad
-    kernel's tensor-core pass instead of a separate sweep over dZ."""
-    dw, db = ops.mtgemm_wgrad(plan, a0, dz, n_total, a1=a1, bias=True)
+    kernel's tensor-core pass instead of a separate sweep over dZ.
+
+    ``w``: the weight the gradient belongs to.  When it is a matrix-shaped leaf whose ``.grad`` is a slot of the
+    trainer's flat gradient buffer (``trainer.GradBuckets`` marks those parameters), the kernel accumulates straight
+    into that slot -- no zero-filled temporary, no ``grad += dW`` pass -- dW is returned as None and the parameter's
+    post-accumulate hooks (the bucket all-reduce trigger) are run here, since autograd has nothing left to accumulate."""
+    slot = _direct_slot(w, n_total, plan.k_total) if w is not None else None
+    dw, db = ops.mtgemm_wgrad(plan, a0, dz, n_total, a1=a1, bias=True, dw_out=slot)
+    if slot is not None:
+        for hook in list((getattr(w, "_post_accumulate_grad_hooks", None) or {}).values()):
+            hook(w)
+        return None, db[0]
     return dw, db[0]
+
+
+def _direct_slot(w: Tensor, n: int, k: int) -> Optional[Tensor]:
+    g = w.grad if _DIRECT and getattr(w, "_tvae_direct_grad", False) and w.is_leaf else None
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.numel() != n * k or w.numel() != n * k:
+        return None
+    if not (w.dim() == 2 or (w.dim() == 4 and w.shape[2] == 1 and w.shape[3] == 1)):
+        return None
+    return g
 
 
 def _flat(x: Tensor) -> Tensor:
@@ -201,18 +242,18 @@ class AttnFn(Fn):
         o, lse = ops.attn_fwd(qkv.view(B, S, 3 * C), B, S, C, need_lse=True)
         out = ops.mtgemm(T.plan_linear(C), _flat(o), wproj_f, out_shape=(1, 1, B * S, C), bias=_f32(bproj),
                          residual=_flat(x))
-        ctx.save_for_backward(x, w1, xh, qkv, o, lse, wqkv_d, wproj_d, rope_tab)
+        ctx.save_for_backward(x, w1, xh, qkv, o, lse, wqkv_d, wproj_d, rope_tab, wproj)
         ctx.scale = scale
         return out.view(B, H, W, C)
 
     @staticmethod
     def backward(ctx, dout):
-        x, w1, xh, qkv, o, lse, wqkv_d, wproj_d, rope_tab = ctx.saved_tensors
+        x, w1, xh, qkv, o, lse, wqkv_d, wproj_d, rope_tab, wproj = ctx.saved_tensors
         dout = dout.contiguous()
         B, H, W, C = x.shape
         S = H * W
         df = _flat(dout)
-        dwp, dbp = _wgrad_b(T.plan_linear(C), _flat(o), df, C)
+        dwp, dbp = _wgrad_b(T.plan_linear(C), _flat(o), df, C, w=wproj)
         do = ops.mtgemm(T.plan_linear(C), df, wproj_d, out_shape=(1, 1, B * S, C))
         dqkv = ops.attn_bwd(qkv.view(B, S, 3 * C), o, do.view(B, S, C), lse, rope_tab, B, S, C, H, W, ctx.scale)
         dq = _flat(dqkv)
@@ -242,21 +283,21 @@ class FfnFn(Fn):
         t2 = ops.act_fwd(z2, ACT_GELU)
         u2 = ops.mtgemm(T.plan_linear(mid), _flat(t2), wc4_f, out_shape=(1, 1, M, hid), bias=_f32(bc4), residual=u)
         out = ops.mtgemm(T.plan_linear(hid), u2, wout_f, out_shape=(1, 1, M, C), bias=_f32(bout), residual=_flat(x))
-        ctx.save_for_backward(x, w2n, xn, z_in, u, z0, t0, z2, t2, u2, wc2, win_d, wc0_d, wc2_d, wc4_d, wout_d)
+        ctx.save_for_backward(x, w2n, xn, z_in, u, z0, t0, z2, t2, u2, wc2, win_d, wc0_d, wc2_d, wc4_d, wout_d, win, wc0, wc4, wout)
         ctx.dims = (hid, mid)
         return out.view(B, H, W, C)
 
     @staticmethod
     def backward(ctx, dout):
-        x, w2n, xn, z_in, u, z0, t0, z2, t2, u2, wc2, win_d, wc0_d, wc2_d, wc4_d, wout_d = ctx.saved_tensors
+        x, w2n, xn, z_in, u, z0, t0, z2, t2, u2, wc2, win_d, wc0_d, wc2_d, wc4_d, wout_d, win, wc0, wc4, wout = ctx.saved_tensors
         dout = dout.contiguous()
         B, H, W, C = x.shape
         M = B * H * W
         hid, mid = ctx.dims
         df = _flat(dout)
-        dwout, dbout = _wgrad_b(T.plan_linear(hid), u2, df, C)
+        dwout, dbout = _wgrad_b(T.plan_linear(hid), u2, df, C, w=wout)
         du2 = ops.mtgemm(T.plan_linear(C), df, wout_d, out_shape=(1, 1, M, hid))
-        dwc4, dbc4 = _wgrad_b(T.plan_linear(mid), _flat(t2), du2, hid)
+        dwc4, dbc4 = _wgrad_b(T.plan_linear(mid), _flat(t2), du2, hid, w=wc4)
         # every dZ = dY * gelu'(Z) of the block is produced by the epilogue of the GEMM that computes dY (act_grad), every
         # bias gradient by the wgrad launch that consumes dZ: no separate pass over the [M, 4C] / [M, C] gradients
         dz2 = ops.mtgemm(T.plan_linear(hid), du2, wc4_d, out_shape=(1, 1, M, mid), act=ACT_GELU,
@@ -265,13 +306,15 @@ class FfnFn(Fn):
         dwc2, dbc2 = _wgrad_b(T.plan_conv3x3(mid), t0.view(B, H, W, mid), dz2i, mid)
         dz0 = ops.mtgemm(T.plan_conv3x3_dgrad(mid), dz2i, wc2_d, out_shape=(B, H, W, mid), act=ACT_GELU,
                          act_grad_z=z0.view(B, H, W, mid)).view(1, 1, M, mid)
-        dwc0, dbc0 = _wgrad_b(T.plan_linear(hid), u, dz0, mid)
+        dwc0, dbc0 = _wgrad_b(T.plan_linear(hid), u, dz0, mid, w=wc0)
         dzin = ops.mtgemm(T.plan_linear(mid), dz0, wc0_d, out_shape=(1, 1, M, hid), residual=du2,
                           act=ACT_GELU, act_grad_z=z_in)
-        dwin, dbin = _wgrad_b(T.plan_linear(C), _flat(xn), dzin, hid)
+        dwin, dbin = _wgrad_b(T.plan_linear(C), _flat(xn), dzin, hid, w=win)
         dxn = ops.mtgemm(T.plan_linear(hid), dzin, win_d, out_shape=(1, 1, M, C))
         dx, dw2n = ops.token_norm_bwd(x, w2n, dxn.view(B, H, W, C), dout, 0)
-        return dx, dw2n, dwin, dbin, dwc0, dbc0, _w_ungrad(dwc2, wc2), dbc2, dwc4, dbc4, dwout, dbout
+        def _as(g, w):                      # 1x1 conv weights arrive as [out, in, 1, 1]
+            return g if g is None else g.view_as(w)
+        return dx, dw2n, dwin, dbin, _as(dwc0, wc0), dbc0, _w_ungrad(dwc2, wc2), dbc2, _as(dwc4, wc4), dbc4, dwout, dbout
 
 
 class ConvInFn(Fn):

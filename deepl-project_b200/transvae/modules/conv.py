@@ -42,8 +42,8 @@ class ConvFFN(HotModule):
                 raise NotImplementedError("bare ConvFFN (no RMSNorm / no residual) is an inference-only hook")
             from .._autograd import FfnFn
             c0, c2, c4 = self.conv[0], self.conv[2], self.conv[4]
-            return FfnFn.apply(x, w2, self.proj_in.weight, self.proj_in.bias, T.pack_conv1x1(c0.weight), c0.bias,
-                               c2.weight, c2.bias, T.pack_conv1x1(c4.weight), c4.bias,
+            return FfnFn.apply(x, w2, self.proj_in.weight, self.proj_in.bias, c0.weight, c0.bias,
+                               c2.weight, c2.bias, c4.weight, c4.bias,
                                self.proj_out.weight, self.proj_out.bias)
         xf = x.reshape(M, C)
         if w2 is not None:

@@ -24,6 +24,9 @@ LAUNCHES = 0
 PROFILE = None
 # same for the HBM-bound kernels: (name, algorithmic_bytes, start_event, end_event); None = off
 PROFILE_HBM = None
+# bumped by trainer.FusedAdamW whenever the (flat) parameters change behind autograd's back: invalidates the per-step
+# cache of packed weight operands (_autograd._w_pack)
+WEIGHT_EPOCH = 0
 
 
 class _hbm:
@@ -343,10 +346,12 @@ def loss_sums(recon: Tensor, target: Tensor, mu: Tensor, logvar: Tensor, patched
 # ------------------------------------------------------------------------------------------------
 # backward pass
 # ------------------------------------------------------------------------------------------------
-def mtgemm_wgrad(plan: Plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[Tensor] = None, bias: bool = False):
+def mtgemm_wgrad(plan: Plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[Tensor] = None, bias: bool = False,
+                 dw_out: Optional[Tensor] = None):
     """dW [n_total, k_total] fp32 of the forward ``mtgemm(plan, a0, w, a1=a1)`` given dZ (the gradient w.r.t. its
     pre-activation output, same NHWC bf16 layout / view as the forward output).  ``bias=True`` also returns the bias
-    gradient fp32 [num_phases, n_total] (per-phase column sums of dZ), produced by the same launch."""
+    gradient fp32 [num_phases, n_total] (per-phase column sums of dZ), produced by the same launch.
+    ``dw_out``: accumulate into this fp32 buffer (the kernel adds with ``red.global.add``) instead of a zeroed new one."""
     _need_cuda(a0, dz, a1)
     d = MtGemmDesc()
     _set_view(d.a0, a0, plan.a0_split)
@@ -354,7 +359,12 @@ def mtgemm_wgrad(plan: Plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[
     _set_view(d.out, dz, plan.out_split)
     _fill_taps(d, plan)
     d.n_total, d.k_total = n_total, plan.k_total
-    dw = torch.zeros(n_total, plan.k_total, dtype=torch.float32, device=a0.device)
+    if dw_out is None:
+        dw = torch.zeros(n_total, plan.k_total, dtype=torch.float32, device=a0.device)
+    else:
+        assert dw_out.dtype == torch.float32 and dw_out.is_contiguous() and dw_out.numel() == n_total * plan.k_total \
+            and dw_out.device == a0.device
+        dw = dw_out
     db = torch.zeros(plan.num_phases, n_total, dtype=torch.float32, device=a0.device) if bias else None
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -30,6 +30,9 @@ class GradBuckets:
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
+        from . import _autograd, ops
+        _autograd.clear_pack_cache()
+        ops.WEIGHT_EPOCH += 1
         dev = self.params[0].device
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -49,6 +52,8 @@ class GradBuckets:
                 self.flat_p[o:o + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat_p[o:o + n].view(p.shape)
                 p.grad = self.flat_g[o:o + n].view(p.shape)
+                # matrix-shaped weights: the wgrad kernel may accumulate straight into this slot (_autograd._wgrad_b)
+                p._tvae_direct_grad = True
                 self._slices[p] = (o, n)
         # contiguous buckets
         self.buckets: List[Tuple[int, int]] = []
@@ -119,6 +124,7 @@ class FusedAdamW:
         self.ctrl[2] = grad_scale
         ops.adamw(self.b.flat_p, self.b.flat_g, self.m, self.v, self.ctrl, self.lr if lr is None else lr, self.betas,
                   self.eps, self.wd, self.step_count)
+        ops.WEIGHT_EPOCH += 1           # the kernel rewrote flat_p: packed operands cached for this step are stale
         return self.ctrl
 
     # ---- checkpoint interchange --------------------------------------------------------------------------------
@@ -219,6 +225,8 @@ class Trainer:
         """Accepts checkpoints written by this trainer or by the reference's train.py / train_2.py."""
         self.model.load_state_dict(sd["model_state_dict"])
         # load_state_dict copies into the existing (flat-buffer backed) parameter storage, so the views stay valid
+        from . import ops
+        ops.WEIGHT_EPOCH += 1           # packed operands cached from the old weights are stale
         self.opt.load_state_dict(sd["optimizer_state_dict"])
         if "global_step" in sd and not sd["optimizer_state_dict"].get("state"):
             self.opt.step_count = int(sd["global_step"])
