@@ -360,21 +360,23 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         if constexpr (kGn) {
           if (gn) {
-            // column sums of the staged bf16 tile (what the consumer's GroupNorm will read): thread = (8-channel vector,
-            // row slot); 16-byte reads of one row by 8 consecutive threads cover all 32 banks once (swizzled layout)
+            // column sums of the staged bf16 tile (what the consumer's GroupNorm will read).  A warp takes four 8-channel
+            // column groups; its lanes are (column group, row mod 8), so the 16-byte reads of a quarter warp hit eight
+            // different slots of the 128-byte swizzle (conflict-free), the eight partial sums of a column group meet in a
+            // 3-step butterfly and ONE lane per column group folds its 8 channels into the per-group staging sums -- the
+            // first version (thread = column group x row slot, every thread flushing through shared-memory atomics) put
+            // 1200 ten-way contended CAS loops on the shared-memory port per tile and cost 8 % of the kernel
             constexpr int kVec = BLOCK_N / 8;
-            constexpr int kSlots = 256 / kVec;
-            const int et = (int)threadIdx.x - 128;
-            if (et < kVec * kSlots) {
-              const int gc = et % kVec, rs0 = et / kVec;
-              const uint8_t* chunk = sOut + (gc >> 3) * kABytes;
-              const int g8 = gc & 7;
+            const int gc = (warp - 4) * 4 + (lane >> 3);
+            const int rl = lane & 7;
+            if ((warp - 4) * 4 < kVec) {          // warp-uniform (kVec is a multiple of 4)
+              const uint8_t* col = sOut + (gc >> 3) * kABytes + rl * 128 + ((((gc & 7) ^ rl)) << 4);
               float2 s[4], ss[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) s[i] = ss[i] = make_float2(0.0f, 0.0f);
 #pragma unroll 4
-              for (int rr = rs0; rr < kBlockM; rr += kSlots) {
-                const uint4 u = *reinterpret_cast<const uint4*>(chunk + rr * 128 + ((g8 ^ (rr & 7)) << 4));
+              for (int rb = 0; rb < kBlockM / 8; ++rb) {
+                const uint4 u = *reinterpret_cast<const uint4*>(col + rb * 1024);
                 float2 f[4];
                 unpack8_2(u, f);
 #pragma unroll
@@ -383,23 +385,35 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                   ss[i] = __ffma2_rn(f[i], f[i], ss[i]);
                 }
               }
-              const float sv[8] = {s[0].x, s[0].y, s[1].x, s[1].y, s[2].x, s[2].y, s[3].x, s[3].y};
-              const float qv[8] = {ss[0].x, ss[0].y, ss[1].x, ss[1].y, ss[2].x, ss[2].y, ss[3].x, ss[3].y};
-              const int c0 = n_t * BLOCK_N + gc * 8;
-              int g = c0 / P.gn_cpg, rem = c0 - g * P.gn_cpg;
-              float as = 0.0f, aq = 0.0f;
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                as += sv[k];
-                aq += qv[k];
-                if (++rem == P.gn_cpg || k == 7) {
-                  if (g < P.gn_groups) {
-                    atomicAdd(&s_gn[2 * g], as);
-                    atomicAdd(&s_gn[2 * g + 1], aq);
+              for (int m = 1; m < 8; m <<= 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  s[i].x += __shfl_xor_sync(0xffffffffu, s[i].x, m);
+                  s[i].y += __shfl_xor_sync(0xffffffffu, s[i].y, m);
+                  ss[i].x += __shfl_xor_sync(0xffffffffu, ss[i].x, m);
+                  ss[i].y += __shfl_xor_sync(0xffffffffu, ss[i].y, m);
+                }
+              }
+              if (rl == 0) {
+                const float sv[8] = {s[0].x, s[0].y, s[1].x, s[1].y, s[2].x, s[2].y, s[3].x, s[3].y};
+                const float qv[8] = {ss[0].x, ss[0].y, ss[1].x, ss[1].y, ss[2].x, ss[2].y, ss[3].x, ss[3].y};
+                const int c0 = n_t * BLOCK_N + gc * 8;
+                int g = c0 / P.gn_cpg, rem = c0 - g * P.gn_cpg;
+                float as = 0.0f, aq = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  as += sv[k];
+                  aq += qv[k];
+                  if (++rem == P.gn_cpg || k == 7) {
+                    if (g < P.gn_groups) {
+                      atomicAdd(&s_gn[2 * g], as);
+                      atomicAdd(&s_gn[2 * g + 1], aq);
+                    }
+                    as = aq = 0.0f;
+                    rem = 0;
+                    ++g;
                   }
-                  as = aq = 0.0f;
-                  rem = 0;
-                  ++g;
                 }
               }
             }

@@ -56,6 +56,54 @@ def test_trainer_step_matches_reference_optimizer_recipe():
     assert moved > 0
 
 
+def test_direct_gradient_accumulation_matches_autograd():
+    """Trainer-owned parameters take the fast weight-gradient route (_autograd._wgrad_b: the wgrad kernel accumulates
+    straight into the flat gradient slot, packed operands cached per optimizer step, hooks fired by hand).  Two
+    accumulated micro-steps must leave the same gradients in the flat buffer as plain autograd accumulation on a twin
+    model (train.py:599-603 semantics: gradients of successive micro-batches add up).  A smooth (linear) loss keeps the
+    comparison free of the sign flips of L1; the run-to-run noise of the bf16 / fp32-atomic backward (large on the
+    ill-conditioned bias gradients in front of a normalisation layer) is measured with a second plain twin and the bar
+    is max(5e-3, 4 x that noise) per tensor -- a lost or doubled gradient is an error of order 1."""
+    from transvae import _autograd
+    blob, sd = load_golden("mini_tamed")
+    m1, m2, m3 = (build_model(blob["cfg"], sd).train() for _ in range(3))
+    xs, eps = _batches(blob, 2)
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        r0, mu0, _ = m2(xs[0], eps=eps[0])
+    G = torch.randn(r0.shape, generator=g).cuda() * 1e-3
+    Gm = torch.randn(mu0.shape, generator=g).cuda() * 1e-3
+
+    class Lin(torch.nn.Module):
+        def forward(self, recon, target, mu, logvar):
+            return {"total": (recon.float() * G).sum() + (mu.float() * Gm).sum() + (logvar.float() * Gm).sum()}
+
+    tr = Trainer(m1, Lin(), lr=1e-3, accumulation_steps=3)      # two micro-steps: no optimizer step, no zero_grad
+    for x, e in zip(xs, eps):
+        tr.train_step(x, eps=e)
+    assert len(_autograd._PACKS) > 0                            # the cached / direct route was taken
+    for m in (m2, m3):
+        for x, e in zip(xs, eps):
+            recon, mu, lv = m(x, eps=e)
+            Lin()(recon, x, mu, lv)["total"].backward()
+
+    def rel_l2(a, b):
+        a, b = a.float().reshape(-1), b.float().reshape(-1)
+        return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+    bad, n_direct = [], 0
+    for (k, p1), (_, p2), (_, p3) in zip(m1.named_parameters(), m2.named_parameters(), m3.named_parameters()):
+        o, n = tr.buckets._slices[p1]
+        assert p1.grad.data_ptr() == tr.buckets.flat_g.data_ptr() + 4 * o, k     # still the flat slot
+        assert p2.grad is not None and p3.grad is not None, k
+        e12, noise = rel_l2(p1.grad, p2.grad), rel_l2(p3.grad, p2.grad)
+        n_direct += int(p1.dim() in (2, 4) and p1.shape[0] % 4 == 0)
+        if e12 > max(5e-3, 4.0 * noise):
+            bad.append((k, e12, noise))
+    assert not bad, bad[:8]
+    assert n_direct > 0
+
+
 def test_resume_equals_uninterrupted(tmp_path):
     blob, sd = load_golden("mini_tamed")
     xs, eps = _batches(blob, 3)

@@ -1,5 +1,5 @@
 """Run ONE hot kernel a few times at its BASELINE-size shape (for ncu --set full captures):
-    python tools/one_kernel.py conv192 | gn_apply | gn_bwd | attn_fwd | attn_bwd | wgrad192 | token_norm_bwd"""
+    python tools/one_kernel.py conv192 | conv192gn | gn_apply | gn_bwd | attn_fwd | attn_bwd | wgrad192 | token_norm_bwd"""
 import math, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "deepl-project_b200"))
@@ -11,12 +11,14 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(0)
 rnd = lambda *s: torch.randn(*s, device=dev, generator=g)
-if which in ("conv192", "wgrad192"):
+if which in ("conv192", "conv192gn", "wgrad192"):
     x = rnd(B, 256, 256, 192).to(torch.bfloat16)
     w = (rnd(192, 9 * 192) * 0.02).to(torch.bfloat16)
     b = rnd(192)
     dz = rnd(B, 256, 256, 192).to(torch.bfloat16)
-    fn = (lambda: ops.mtgemm(T.plan_conv3x3(192), x, w, out_shape=(B, 256, 256, 192), bias=b, residual=dz)) if which == "conv192" \
+    # conv192gn: the same launch with the GroupNorm(32) statistics of its output taken in the epilogue (gn_sums)
+    fn = (lambda: ops.mtgemm(T.plan_conv3x3(192), x, w, out_shape=(B, 256, 256, 192), bias=b, residual=dz,
+                             gn_groups=32 if which == "conv192gn" else 0)) if which != "wgrad192" \
         else (lambda: ops.mtgemm_wgrad(T.plan_conv3x3(192), x, dz, 192, bias=True))
 elif which in ("gn_apply", "gn_bwd"):
     x = rnd(B, 256, 256, 192).to(torch.bfloat16)
