@@ -6,10 +6,10 @@ namespace tvae {
 int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream);
 int attn_fwd_run(const void* qkv, void* out, float* lse, int B, int S, int C, cudaStream_t stream);
 int im2col_in_run(const float* x, void* cols, int B, int H, int W, cudaStream_t stream);
-int gn_stats_run(const void* x, float* sums, int B, int HW, int C, int G, cudaStream_t stream);
-int gn_apply_run(const void* x, const float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
+int gn_stats_run(const void* x, double* sums, int B, int HW, int C, int G, cudaStream_t stream);
+int gn_apply_run(const void* x, const double* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
                  int G, float eps, int apply_silu, cudaStream_t stream);
-int gn_fwd_run(const void* x, float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C, int G,
+int gn_fwd_run(const void* x, double* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C, int G,
                float eps, int apply_silu, cudaStream_t stream);
 int row_stats_run(const void* x, const float* w1, float* out_a, float* out_b, long long M, int C, int mode,
                   cudaStream_t stream);
@@ -25,7 +25,7 @@ int bias_act_bwd_run(const void* dy, const void* z, void* dz, float* colsum, lon
 int bias_act_bwd_matrix_run(const void* dy, const void* z, void* dz, float* colsum, long long M, int N, int act,
                             cudaStream_t stream);
 int act_fwd_run(const void* z, void* y, long long n, int act, cudaStream_t stream);
-int gn_bwd_run(const void* x, const void* dh, const void* add, const float* sums, const float* gamma, const float* beta,
+int gn_bwd_run(const void* x, const void* dh, const void* add, const double* sums, const float* gamma, const float* beta,
                float* part, void* dx, int B, int HW, int C, int G, float eps, int apply_silu, cudaStream_t stream);
 int token_norm_fwd_run(const void* x, const float* w, void* y, long long M, int C, int mode, cudaStream_t stream);
 int token_norm_bwd_run(const void* x, const float* w, const void* dy, const void* add, void* dx, float* dw, long long M,
@@ -93,14 +93,14 @@ int tvae_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t S, 
 int tvae_im2col_in(const float* x_nchw, void* cols, int32_t B, int32_t H, int32_t W, void* stream) {
   GUARD(); return im2col_in_run(x_nchw, cols, B, H, W, S_(stream));
 }
-int tvae_groupnorm_stats(const void* x, float* sums, int32_t B, int32_t HW, int32_t C, int32_t G, void* stream) {
+int tvae_groupnorm_stats(const void* x, double* sums, int32_t B, int32_t HW, int32_t C, int32_t G, void* stream) {
   GUARD(); return gn_stats_run(x, sums, B, HW, C, G, S_(stream));
 }
-int tvae_groupnorm_apply(const void* x, const float* sums, const float* gamma, const float* beta, void* y, int32_t B,
+int tvae_groupnorm_apply(const void* x, const double* sums, const float* gamma, const float* beta, void* y, int32_t B,
                          int32_t HW, int32_t C, int32_t G, float eps, int32_t apply_silu, void* stream) {
   GUARD(); return gn_apply_run(x, sums, gamma, beta, y, B, HW, C, G, eps, apply_silu, S_(stream));
 }
-int tvae_groupnorm_silu(const void* x, const float* gamma, const float* beta, void* y, float* sums, int32_t B, int32_t HW,
+int tvae_groupnorm_silu(const void* x, const float* gamma, const float* beta, void* y, double* sums, int32_t B, int32_t HW,
                         int32_t C, int32_t G, float eps, int32_t apply_silu, void* stream) {
   GUARD(); return gn_fwd_run(x, sums, gamma, beta, y, B, HW, C, G, eps, apply_silu, S_(stream));
 }
@@ -139,7 +139,7 @@ int tvae_bias_act_bwd_4d(const void* dy, const void* z, void* dz, float* colsum,
   GUARD(); return bias_act_bwd_run(dy, z, dz, colsum, R0, P, R1, Q, act, S_(stream));
 }
 int tvae_act_fwd(const void* z, void* y, int64_t n, int32_t act, void* stream) { GUARD(); return act_fwd_run(z, y, n, act, S_(stream)); }
-int tvae_groupnorm_bwd(const void* x, const void* dh, const void* add, const float* sums, const float* gamma, const float* beta,
+int tvae_groupnorm_bwd(const void* x, const void* dh, const void* add, const double* sums, const float* gamma, const float* beta,
                        float* part, void* dx, int32_t B, int32_t HW, int32_t C, int32_t G, float eps, int32_t apply_silu,
                        void* stream) {
   GUARD(); return gn_bwd_run(x, dh, add, sums, gamma, beta, part, dx, B, HW, C, G, eps, apply_silu, S_(stream));

@@ -182,18 +182,16 @@ struct GnCoef {
   float mean, rstd;
 };
 
-__device__ __forceinline__ void gn_group_coef(const float* sums, int b, int G, int g, float inv_n, float eps, float& mean,
+__device__ __forceinline__ void gn_group_coef(const double* sums, int b, int G, int g, float inv_n, float eps, float& mean,
                                               float& rstd) {
-  mean = sums[((size_t)b * G + g) * 2] * inv_n;
-  const float var = fmaxf(sums[((size_t)b * G + g) * 2 + 1] * inv_n - mean * mean, 0.0f);
-  rstd = rsqrtf(var + eps);
+  gn_mean_rstd(sums, b, G, g, inv_n, eps, mean, rstd);
 }
 
 // per-thread constants of its 8 channels, packed in pairs: xhat = x * a + b (a = rstd, b = -mean * rstd), y = xhat * ga + be
 struct GnChan {
   float2 a[4], b[4], ga[4], be[4];
 };
-__device__ __forceinline__ void gn_load_chan(GnChan& ch, const float* sums, const float* gamma, const float* beta, int b,
+__device__ __forceinline__ void gn_load_chan(GnChan& ch, const double* sums, const float* gamma, const float* beta, int b,
                                              int G, int cpg, int v, float inv_n, float eps) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -210,7 +208,7 @@ __device__ __forceinline__ void gn_load_chan(GnChan& ch, const float* sums, cons
 
 template <bool SILU>
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dh,
-                                                            const float* __restrict__ sums,
+                                                            const double* __restrict__ sums,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ part, int HW, int C, int G, float eps,
                                                             int pix_per_block) {
@@ -271,7 +269,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const uint4* __restr
 
 template <bool SILU, bool ADD>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dh,
-                                                           const uint4* __restrict__ add, const float* __restrict__ sums,
+                                                           const uint4* __restrict__ add, const double* __restrict__ sums,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ part, uint4* __restrict__ dx, int HW,
                                                            int C, int G, float eps, int vec_per_block) {
@@ -338,7 +336,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restri
   }
 }
 
-int gn_bwd_run(const void* x, const void* dh, const void* add, const float* sums, const float* gamma, const float* beta,
+int gn_bwd_run(const void* x, const void* dh, const void* add, const double* sums, const float* gamma, const float* beta,
                float* part, void* dx, int B, int HW, int C, int G, float eps, int apply_silu, cudaStream_t stream) {
   TVAE_REQUIRE(C % 8 == 0 && C % G == 0 && C / 8 <= 256 && G <= 128, "groupnorm_bwd: unsupported C=%d G=%d", C, G);
   TVAE_CHECK_CUDA(cudaMemsetAsync(part, 0, (size_t)B * C * 2 * sizeof(float), stream));

@@ -65,7 +65,7 @@ int im2col_in_run(const float* x, void* cols, int B, int H, int W, cudaStream_t 
 // -------------------------------------------------------------------------------------------------
 constexpr int kGnBatch = 8;   // independent 16-byte loads a thread keeps in flight
 
-__global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ sums, int HW,
+__global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__ x, double* __restrict__ sums, int HW,
                                                        int C, int G, int pix_per_block) {
   __shared__ float s_acc[2 * 128];
   const int nvec = C >> 3;
@@ -106,12 +106,12 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__
     atomicAdd(&s_acc[2 * g1 + 1], ss[i].y);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&sums[(size_t)b * 2 * G + i], s_acc[i]);
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&sums[(size_t)b * 2 * G + i], (double)s_acc[i]);
 }
 
-int gn_stats_run(const void* x, float* sums, int B, int HW, int C, int G, cudaStream_t stream) {
+int gn_stats_run(const void* x, double* sums, int B, int HW, int C, int G, cudaStream_t stream) {
   TVAE_REQUIRE(C % 8 == 0 && C % G == 0 && G <= 128 && C / 8 <= 256, "groupnorm: unsupported C=%d G=%d", C, G);
-  TVAE_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * G * 2 * sizeof(float), stream));
+  TVAE_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * G * 2 * sizeof(double), stream));
   const int nvec = C / 8;
   const int threads = (256 / nvec) * nvec;
   // one full wave: ~6 resident blocks per SM (40 registers, 240 threads), each sweeping a contiguous pixel range; a
@@ -131,7 +131,7 @@ int gn_stats_run(const void* x, float* sums, int B, int HW, int C, int G, cudaSt
 // Replaces the affine half of nn.GroupNorm + F.silu (blocks.py:60-66; decoder.py:128-129).
 // Algorithmic bytes: 4*C per pixel (read + write).  Packed fp32 math: 4 instructions per element.
 template <bool SILU>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ sums,
+__global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__ x, const double* __restrict__ sums,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        uint4* __restrict__ y, int HW, int C, int G, float eps,
                                                        int vec_per_block) {
@@ -141,9 +141,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__
   const float inv_n = 1.0f / ((float)cpg * (float)HW);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
-    const float mean = sums[((size_t)b * G + g) * 2] * inv_n;
-    const float var = fmaxf(sums[((size_t)b * G + g) * 2 + 1] * inv_n - mean * mean, 0.0f);
-    const float rstd = rsqrtf(var + eps);
+    float mean, rstd;
+    gn_mean_rstd(sums, b, G, g, inv_n, eps, mean, rstd);
     const float a = rstd * gamma[c];
     s_ab[c] = a;
     s_ab[C + c] = beta[c] - mean * a;
@@ -185,7 +184,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__
   }
 }
 
-int gn_apply_run(const void* x, const float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
+int gn_apply_run(const void* x, const double* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
                  int G, float eps, int apply_silu, cudaStream_t stream) {
   TVAE_REQUIRE(C % 8 == 0 && C % G == 0 && C / 8 <= 256, "groupnorm: unsupported C=%d G=%d", C, G);
   const int nvec = C / 8;
@@ -210,10 +209,10 @@ int gn_apply_run(const void* x, const float* sums, const float* gamma, const flo
 // needs it).  (Running the two passes image by image so that the second read of x hits the 126 MB L2 was tried and is
 // slower on B200: a 25 MB image is too small a launch -- 23 ms instead of 13 ms per inference step.)
 int gn_stats_run(const void* x, float* sums, int B, int HW, int C, int G, cudaStream_t stream);
-int gn_apply_run(const void* x, const float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
+int gn_apply_run(const void* x, const double* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
                  int G, float eps, int apply_silu, cudaStream_t stream);
 
-int gn_fwd_run(const void* x, float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C, int G,
+int gn_fwd_run(const void* x, double* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C, int G,
                float eps, int apply_silu, cudaStream_t stream) {
   int rc;
   if ((rc = gn_stats_run(x, sums, B, HW, C, G, stream))) return rc;

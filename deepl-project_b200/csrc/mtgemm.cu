@@ -26,7 +26,7 @@ int mtgemm2_dispatch(int epi, int block_n, const CUtensorMap& a0, const CUtensor
                      const CUtensorMap& o, const CUtensorMap& r, const MtParams& P, cudaStream_t stream);
 static int mtgemm1_dispatch(int epi, int block_n, const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB,
                             const CUtensorMap& mO, const CUtensorMap& mR, const MtParams& P, cudaStream_t stream);
-int gn_stats_run(const void* x, float* sums, int B, int HW, int C, int G, cudaStream_t stream);   // elementwise.cu
+int gn_stats_run(const void* x, double* sums, int B, int HW, int C, int G, cudaStream_t stream);   // elementwise.cu
 
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -476,7 +476,7 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
     static const bool allow_fused = !(getenv("TVAE_GN_FUSED") && atoi(getenv("TVAE_GN_FUSED")) == 0);
     gn_fused = allow_fused && pair && P.nb == 1 && (epi == kEpiBias || epi == kEpiBiasRes) && d->gn_groups <= 64;
     if (gn_fused) {
-      TVAE_CHECK_CUDA(cudaMemsetAsync(d->gn_sums, 0, (size_t)d->out.B * d->gn_groups * 2 * sizeof(float), stream));
+      TVAE_CHECK_CUDA(cudaMemsetAsync(d->gn_sums, 0, (size_t)d->out.B * d->gn_groups * 2 * sizeof(double), stream));
       P.gn_sums = d->gn_sums;
       P.gn_groups = d->gn_groups;
       P.gn_cpg = d->n_total / d->gn_groups;

@@ -429,7 +429,7 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (et < 2 * P.gn_groups) {
               const float v = s_gn[et];
               if (v != 0.0f) {      // only the groups of this n tile; a phantom tile (b0 >= vB) contributes nothing
-                atomicAdd(P.gn_sums + (size_t)b0 * 2 * P.gn_groups + et, v);
+                atomicAdd(P.gn_sums + (size_t)b0 * 2 * P.gn_groups + et, (double)v);
                 s_gn[et] = 0.0f;
               }
             }

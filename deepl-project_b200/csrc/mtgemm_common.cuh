@@ -39,7 +39,7 @@ struct MtParams {
   int out_n;
   int vB, vH, vW;  // output view extents (pixels) for row indexing / bounds
   const __nv_bfloat16* z;   // act_grad == 2: pre-activation matrix [M, n_total]
-  float* gn_sums;           // fused GroupNorm statistics of the output: [vB][gn_groups][2] (sum, sumsq), or nullptr
+  double* gn_sums;          // fused GroupNorm statistics of the output: [vB][gn_groups][2] (sum, sumsq), or nullptr
   int gn_groups, gn_cpg;    // groups, channels per group
 };
 

@@ -99,28 +99,31 @@ def _w_ungrad(gp: Tensor, w: Tensor) -> Tensor:
     return gp.view(w.shape[0], 3, 3, w.shape[1]).permute(0, 3, 1, 2)
 
 
-def _wgrad_b(plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[Tensor] = None, w: Optional[Tensor] = None):
+def _wgrad_b(plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[Tensor] = None, w: Optional[Tensor] = None,
+             b: Optional[Tensor] = None):
     """(dW, dbias) of a single-phase plan in one launch: the bias gradient (column sums of dZ) rides on the wgrad
     kernel's tensor-core pass instead of a separate sweep over dZ.
 
-    ``w``: the weight the gradient belongs to.  When it is a matrix-shaped leaf whose ``.grad`` is a slot of the
-    trainer's flat gradient buffer (``trainer.GradBuckets`` marks those parameters), the kernel accumulates straight
-    into that slot -- no zero-filled temporary, no ``grad += dW`` pass -- dW is returned as None and the parameter's
-    post-accumulate hooks (the bucket all-reduce trigger) are run here, since autograd has nothing left to accumulate."""
-    slot = _direct_slot(w, n_total, plan.k_total) if w is not None else None
-    dw, db = ops.mtgemm_wgrad(plan, a0, dz, n_total, a1=a1, bias=True, dw_out=slot)
-    if slot is not None:
-        for hook in list((getattr(w, "_post_accumulate_grad_hooks", None) or {}).values()):
-            hook(w)
-        return None, db[0]
-    return dw, db[0]
+    ``w`` / ``b``: the weight / bias the gradients belong to.  When one is a leaf whose ``.grad`` is a slot of the
+    trainer's flat gradient buffer (``trainer.GradBuckets`` marks those parameters; weights must be matrix-shaped), the
+    kernel accumulates straight into that slot -- no zero-filled temporary, no ``grad += dW`` pass -- that gradient is
+    returned as None and the parameter's post-accumulate hooks (the bucket all-reduce trigger) are run here, since
+    autograd has nothing left to accumulate."""
+    wslot = _direct_slot(w, n_total * plan.k_total, True) if w is not None else None
+    bslot = _direct_slot(b, n_total, False) if b is not None and plan.num_phases == 1 else None
+    dw, db = ops.mtgemm_wgrad(plan, a0, dz, n_total, a1=a1, bias=True, dw_out=wslot, db_out=bslot)
+    for p, slot in ((w, wslot), (b, bslot)):
+        if slot is not None:
+            for hook in list((getattr(p, "_post_accumulate_grad_hooks", None) or {}).values()):
+                hook(p)
+    return (None if wslot is not None else dw), (None if bslot is not None else db[0])
 
 
-def _direct_slot(w: Tensor, n: int, k: int) -> Optional[Tensor]:
-    g = w.grad if _DIRECT and getattr(w, "_tvae_direct_grad", False) and w.is_leaf else None
-    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.numel() != n * k or w.numel() != n * k:
+def _direct_slot(p: Tensor, numel: int, matrix: bool) -> Optional[Tensor]:
+    g = p.grad if _DIRECT and getattr(p, "_tvae_direct_grad", False) and p.is_leaf else None
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.numel() != numel or p.numel() != numel:
         return None
-    if not (w.dim() == 2 or (w.dim() == 4 and w.shape[2] == 1 and w.shape[3] == 1)):
+    if matrix and not (p.dim() == 2 or (p.dim() == 4 and p.shape[2] == 1 and p.shape[3] == 1)):
         return None
     return g
 
@@ -143,19 +146,19 @@ class ResBlockFn(Fn):
         h1 = ops.mtgemm(plan, h0, w1f, out_shape=(B, H, W, C), bias=_f32(c1b), gn_groups=32)   # + GN2's statistics
         h2, s2 = ops.groupnorm_silu(h1, g2, b2, sums=h1._gn_sums, return_sums=True)
         out = ops.mtgemm(plan, h2, w2f, out_shape=(B, H, W, C), bias=_f32(c2b), residual=x)
-        ctx.save_for_backward(x, s1, h0, h1, s2, h2, g1, b1, w1, g2, b2, w2, w1d, w2d)
+        ctx.save_for_backward(x, s1, h0, h1, s2, h2, g1, b1, w1, g2, b2, w2, w1d, w2d, c1b, c2b)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, s1, h0, h1, s2, h2, g1, b1, w1, g2, b2, w2, w1d, w2d = ctx.saved_tensors
+        x, s1, h0, h1, s2, h2, g1, b1, w1, g2, b2, w2, w1d, w2d, c1b, c2b = ctx.saved_tensors
         dout = dout.contiguous()
         B, H, W, C = x.shape
         dplan = T.plan_conv3x3_dgrad(C)
-        dw2, dc2b = _wgrad_b(T.plan_conv3x3(C), h2, dout, C)
+        dw2, dc2b = _wgrad_b(T.plan_conv3x3(C), h2, dout, C, b=c2b)
         dh2 = ops.mtgemm(dplan, dout, w2d, out_shape=(B, H, W, C))
         dh1, dg2, db2 = ops.groupnorm_bwd(h1, dh2, s2, g2, b2)
-        dw1, dc1b = _wgrad_b(T.plan_conv3x3(C), h0, dh1, C)
+        dw1, dc1b = _wgrad_b(T.plan_conv3x3(C), h0, dh1, C, b=c1b)
         dh0 = ops.mtgemm(dplan, dh1, w1d, out_shape=(B, H, W, C))
         dx, dg1, db1 = ops.groupnorm_bwd(x, dh0, s1, g1, b1, add=dout)
         return dx, dg1, db1, _w_ungrad(dw1, w1), dc1b, dg2, db2, _w_ungrad(dw2, w2), dc2b
@@ -242,18 +245,18 @@ class AttnFn(Fn):
         o, lse = ops.attn_fwd(qkv.view(B, S, 3 * C), B, S, C, need_lse=True)
         out = ops.mtgemm(T.plan_linear(C), _flat(o), wproj_f, out_shape=(1, 1, B * S, C), bias=_f32(bproj),
                          residual=_flat(x))
-        ctx.save_for_backward(x, w1, xh, qkv, o, lse, wqkv_d, wproj_d, rope_tab, wproj)
+        ctx.save_for_backward(x, w1, xh, qkv, o, lse, wqkv_d, wproj_d, rope_tab, wproj, bproj)
         ctx.scale = scale
         return out.view(B, H, W, C)
 
     @staticmethod
     def backward(ctx, dout):
-        x, w1, xh, qkv, o, lse, wqkv_d, wproj_d, rope_tab, wproj = ctx.saved_tensors
+        x, w1, xh, qkv, o, lse, wqkv_d, wproj_d, rope_tab, wproj, bproj = ctx.saved_tensors
         dout = dout.contiguous()
         B, H, W, C = x.shape
         S = H * W
         df = _flat(dout)
-        dwp, dbp = _wgrad_b(T.plan_linear(C), _flat(o), df, C, w=wproj)
+        dwp, dbp = _wgrad_b(T.plan_linear(C), _flat(o), df, C, w=wproj, b=bproj)
         do = ops.mtgemm(T.plan_linear(C), df, wproj_d, out_shape=(1, 1, B * S, C))
         dqkv = ops.attn_bwd(qkv.view(B, S, 3 * C), o, do.view(B, S, C), lse, rope_tab, B, S, C, H, W, ctx.scale)
         dq = _flat(dqkv)
@@ -283,33 +286,34 @@ class FfnFn(Fn):
         t2 = ops.act_fwd(z2, ACT_GELU)
         u2 = ops.mtgemm(T.plan_linear(mid), _flat(t2), wc4_f, out_shape=(1, 1, M, hid), bias=_f32(bc4), residual=u)
         out = ops.mtgemm(T.plan_linear(hid), u2, wout_f, out_shape=(1, 1, M, C), bias=_f32(bout), residual=_flat(x))
-        ctx.save_for_backward(x, w2n, xn, z_in, u, z0, t0, z2, t2, u2, wc2, win_d, wc0_d, wc2_d, wc4_d, wout_d, win, wc0, wc4, wout)
+        ctx.save_for_backward(x, w2n, xn, z_in, u, z0, t0, z2, t2, u2, wc2, win_d, wc0_d, wc2_d, wc4_d, wout_d, win, wc0, wc4, wout,
+                              bin_, bc0, bc2, bc4, bout)
         ctx.dims = (hid, mid)
         return out.view(B, H, W, C)
 
     @staticmethod
     def backward(ctx, dout):
-        x, w2n, xn, z_in, u, z0, t0, z2, t2, u2, wc2, win_d, wc0_d, wc2_d, wc4_d, wout_d, win, wc0, wc4, wout = ctx.saved_tensors
+        x, w2n, xn, z_in, u, z0, t0, z2, t2, u2, wc2, win_d, wc0_d, wc2_d, wc4_d, wout_d, win, wc0, wc4, wout, bin_, bc0, bc2, bc4, bout = ctx.saved_tensors
         dout = dout.contiguous()
         B, H, W, C = x.shape
         M = B * H * W
         hid, mid = ctx.dims
         df = _flat(dout)
-        dwout, dbout = _wgrad_b(T.plan_linear(hid), u2, df, C, w=wout)
+        dwout, dbout = _wgrad_b(T.plan_linear(hid), u2, df, C, w=wout, b=bout)
         du2 = ops.mtgemm(T.plan_linear(C), df, wout_d, out_shape=(1, 1, M, hid))
-        dwc4, dbc4 = _wgrad_b(T.plan_linear(mid), _flat(t2), du2, hid, w=wc4)
+        dwc4, dbc4 = _wgrad_b(T.plan_linear(mid), _flat(t2), du2, hid, w=wc4, b=bc4)
         # every dZ = dY * gelu'(Z) of the block is produced by the epilogue of the GEMM that computes dY (act_grad), every
         # bias gradient by the wgrad launch that consumes dZ: no separate pass over the [M, 4C] / [M, C] gradients
         dz2 = ops.mtgemm(T.plan_linear(hid), du2, wc4_d, out_shape=(1, 1, M, mid), act=ACT_GELU,
                          act_grad_z=z2.view(1, 1, M, mid))
         dz2i = dz2.view(B, H, W, mid)
-        dwc2, dbc2 = _wgrad_b(T.plan_conv3x3(mid), t0.view(B, H, W, mid), dz2i, mid)
+        dwc2, dbc2 = _wgrad_b(T.plan_conv3x3(mid), t0.view(B, H, W, mid), dz2i, mid, b=bc2)
         dz0 = ops.mtgemm(T.plan_conv3x3_dgrad(mid), dz2i, wc2_d, out_shape=(B, H, W, mid), act=ACT_GELU,
                          act_grad_z=z0.view(B, H, W, mid)).view(1, 1, M, mid)
-        dwc0, dbc0 = _wgrad_b(T.plan_linear(hid), u, dz0, mid, w=wc0)
+        dwc0, dbc0 = _wgrad_b(T.plan_linear(hid), u, dz0, mid, w=wc0, b=bc0)
         dzin = ops.mtgemm(T.plan_linear(mid), dz0, wc0_d, out_shape=(1, 1, M, hid), residual=du2,
                           act=ACT_GELU, act_grad_z=z_in)
-        dwin, dbin = _wgrad_b(T.plan_linear(C), _flat(xn), dzin, hid, w=win)
+        dwin, dbin = _wgrad_b(T.plan_linear(C), _flat(xn), dzin, hid, w=win, b=bin_)
         dxn = ops.mtgemm(T.plan_linear(hid), dzin, win_d, out_shape=(1, 1, M, C))
         dx, dw2n = ops.token_norm_bwd(x, w2n, dxn.view(B, H, W, C), dout, 0)
         def _as(g, w):                      # 1x1 conv weights arrive as [out, in, 1, 1]

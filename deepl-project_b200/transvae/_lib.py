@@ -122,7 +122,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.tvae_abi_version() != 2:
+    if lib.tvae_abi_version() != 3:
         raise RuntimeError("libtransvae_sm100.so ABI version mismatch")
     _lib = lib
     return lib

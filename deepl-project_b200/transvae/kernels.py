@@ -77,7 +77,7 @@ def groupnorm_silu(x: Tensor, gamma: Tensor, beta: Tensor, silu: bool = True) ->
 
 def gn_sums_of(x: Tensor, groups: int = 32) -> Optional[Tensor]:
     s = getattr(x, "_gn_sums", None)
-    if s is not None and tuple(s.shape) == (x.shape[0], groups, 2) and s.device == x.device:
+    if s is not None and tuple(s.shape) == (x.shape[0], groups, 2) and s.device == x.device and s.dtype == torch.float64:
         return s
     return None
 

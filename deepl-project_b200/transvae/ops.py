@@ -101,7 +101,7 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
     [1, 1, M, K]); ``w`` is the packed bf16 [N, K_total] weight; ``bias`` fp32 [phases, N] (or [N]).
 
     ``gn_groups`` > 0: the launch also produces the GroupNorm statistics of its output (per image and group: sum and
-    sum of squares, fp32 [B, gn_groups, 2]) -- from the GEMM epilogue when the launch qualifies, see the header -- and
+    sum of squares, fp64 [B, gn_groups, 2]) -- from the GEMM epilogue when the launch qualifies, see the header -- and
     attaches them to the returned tensor as ``out._gn_sums`` for ``groupnorm_silu(..., sums=...)``.
 
     Backward fusion: with ``act_grad_z`` (the saved pre-activation, same shape as the output) and ``act`` set, the launch
@@ -155,7 +155,7 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
     gn_sums = None
     if gn_groups:
         assert out_f32 is None and out.shape[-1] == n_total
-        gn_sums = torch.empty(out.shape[0], gn_groups, 2, dtype=torch.float32, device=a0.device)
+        gn_sums = torch.empty(out.shape[0], gn_groups, 2, dtype=torch.float64, device=a0.device)
     d.gn_sums, d.gn_groups = _ptr(gn_sums), gn_groups
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -237,7 +237,7 @@ def conv_in(x: Tensor, w: Tensor, b: Optional[Tensor], gn_groups: int = 0) -> Te
 def groupnorm_stats(x: Tensor, groups: int = 32) -> Tensor:
     _need_cuda(x)
     B, H, W, C_ = x.shape
-    sums = torch.empty(B, groups, 2, dtype=torch.float32, device=x.device)
+    sums = torch.empty(B, groups, 2, dtype=torch.float64, device=x.device)
     with _hbm("gn_stats", x.numel() * 2):
         _lib.check(_lib.load().tvae_groupnorm_stats(x.data_ptr(), sums.data_ptr(), B, H * W, C_, groups, _stream()),
                    "tvae_groupnorm_stats")
@@ -255,13 +255,14 @@ def groupnorm_silu(x: Tensor, gamma: Tensor, beta: Tensor, groups: int = 32, eps
     y = torch.empty_like(x)
     g, b = gamma.float().contiguous(), beta.float().contiguous()
     if sums is None:
-        sums = torch.empty(B, groups, 2, dtype=torch.float32, device=x.device)
+        sums = torch.empty(B, groups, 2, dtype=torch.float64, device=x.device)
         with _hbm("gn_stats + gn_apply_silu", x.numel() * 6):
             _lib.check(_lib.load().tvae_groupnorm_silu(x.data_ptr(), g.data_ptr(), b.data_ptr(), y.data_ptr(), sums.data_ptr(),
                                                        B, H * W, C_, groups, eps, 1 if silu else 0, _stream()),
                        "tvae_groupnorm_silu")
         _count(3)
     else:
+        assert sums.dtype == torch.float64 and sums.is_contiguous() and tuple(sums.shape) == (B, groups, 2), (sums.dtype, sums.shape)
         with _hbm("gn_apply_silu", x.numel() * 4):
             _lib.check(_lib.load().tvae_groupnorm_apply(x.data_ptr(), sums.data_ptr(), g.data_ptr(), b.data_ptr(), y.data_ptr(),
                                                         B, H * W, C_, groups, eps, 1 if silu else 0, _stream()),
@@ -347,11 +348,12 @@ def loss_sums(recon: Tensor, target: Tensor, mu: Tensor, logvar: Tensor, patched
 # backward pass
 # ------------------------------------------------------------------------------------------------
 def mtgemm_wgrad(plan: Plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[Tensor] = None, bias: bool = False,
-                 dw_out: Optional[Tensor] = None):
+                 dw_out: Optional[Tensor] = None, db_out: Optional[Tensor] = None):
     """dW [n_total, k_total] fp32 of the forward ``mtgemm(plan, a0, w, a1=a1)`` given dZ (the gradient w.r.t. its
     pre-activation output, same NHWC bf16 layout / view as the forward output).  ``bias=True`` also returns the bias
     gradient fp32 [num_phases, n_total] (per-phase column sums of dZ), produced by the same launch.
-    ``dw_out``: accumulate into this fp32 buffer (the kernel adds with ``red.global.add``) instead of a zeroed new one."""
+    ``dw_out`` / ``db_out``: accumulate into these fp32 buffers (the kernel adds with ``red.global.add``) instead of
+    zeroed new ones."""
     _need_cuda(a0, dz, a1)
     d = MtGemmDesc()
     _set_view(d.a0, a0, plan.a0_split)
@@ -365,7 +367,12 @@ def mtgemm_wgrad(plan: Plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[
         assert dw_out.dtype == torch.float32 and dw_out.is_contiguous() and dw_out.numel() == n_total * plan.k_total \
             and dw_out.device == a0.device
         dw = dw_out
-    db = torch.zeros(plan.num_phases, n_total, dtype=torch.float32, device=a0.device) if bias else None
+    if bias and db_out is not None:
+        assert db_out.dtype == torch.float32 and db_out.is_contiguous() and db_out.numel() == plan.num_phases * n_total \
+            and db_out.device == a0.device
+        db = db_out.view(plan.num_phases, n_total)
+    else:
+        db = torch.zeros(plan.num_phases, n_total, dtype=torch.float32, device=a0.device) if bias else None
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -423,6 +430,7 @@ def groupnorm_bwd(x: Tensor, dh: Tensor, sums: Tensor, gamma: Tensor, beta: Tens
     """Backward of h = act(GroupNorm(x)): returns (dx [+ add], dgamma, dbeta)."""
     _need_cuda(x, dh, sums, gamma, beta, add)
     B, H, W, Cc = x.shape
+    assert sums.dtype == torch.float64 and sums.is_contiguous() and tuple(sums.shape) == (B, groups, 2), (sums.dtype, sums.shape)
     g, b = gamma.float().contiguous(), beta.float().contiguous()
     part = torch.empty(B, Cc, 2, dtype=torch.float32, device=x.device)
     dx = torch.empty_like(x)

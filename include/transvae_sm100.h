@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TVAE_ABI_VERSION 2
+#define TVAE_ABI_VERSION 3
 #define TVAE_MAX_TAPS 16
 #define TVAE_MAX_PHASES 4
 
@@ -97,12 +97,12 @@ typedef struct {
   int32_t act_grad;                   /* 0: forward epilogue; 1 / 2: multiply by act'(.) (see above), `act` names it */
   const void* z;                      /* act_grad == 2: pre-activation [M, n_total] bf16, rows in output-pixel order */
   /* Optional GroupNorm statistics of the OUTPUT (blocks.py:60,64 / decoder.py:128: the nn.GroupNorm that consumes this
-   * convolution): gn_sums[B][gn_groups][2] fp32 receives (sum, sum of squares) of the stored bf16 values per image and
-   * channel group, so the consumer needs tvae_groupnorm_apply only.  The library zeroes the buffer.  The sums come out
-   * of the GEMM epilogue (no extra pass over HBM) when the launch runs on the CTA-pair kernel with a bias / bias+residual
+   * convolution): gn_sums[B][gn_groups][2] receives (sum, sum of squares) of the stored bf16 values per image and
+   * channel group (fp64, see tvae_groupnorm_stats), so the consumer needs tvae_groupnorm_apply only.  The library zeroes
+   * the buffer.  The sums come out of the GEMM epilogue (no extra pass over HBM) when the launch runs on the CTA-pair kernel with a bias / bias+residual
    * epilogue, one image per 128-pixel tile and gn_groups <= 64; otherwise the library runs tvae_groupnorm_stats on the
    * output behind the GEMM.  Requires a bf16 output whose channel count equals n_total. */
-  float* gn_sums;
+  double* gn_sums;
   int32_t gn_groups;
 } tvae_mtgemm_desc;
 
@@ -121,14 +121,16 @@ int tvae_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t S, 
  * fp32 pixel split in two bf16, zero outside the image).  The convolution is then tvae_mtgemm with a 1-tap K = 64 plan
  * and the packed weight [C0, 64] = [w | w | bias | 0]; its weight / bias gradient is tvae_mtgemm_wgrad on the same cols. */
 int tvae_im2col_in(const float* x_nchw, void* cols, int32_t B, int32_t H, int32_t W, void* stream);
-/* nn.GroupNorm(G, C) statistics (blocks.py:33,36; decoder.py:93): sums fp32 [B, G, 2] = (sum x, sum x^2). */
-int tvae_groupnorm_stats(const void* x_nhwc, float* sums, int32_t B, int32_t HW, int32_t C, int32_t G, void* stream);
+/* nn.GroupNorm(G, C) statistics (blocks.py:33,36; decoder.py:93): sums fp64 [B, G, 2] = (sum x, sum x^2).  fp32 block
+ * partials (fixed order) are combined with fp64 atomics and the consumers form E[x^2] - mean^2 in fp64, so the result
+ * does not depend on the order of the atomics (in fp32 the cancellation made identical runs differ by 1e-4 in rstd). */
+int tvae_groupnorm_stats(const void* x_nhwc, double* sums, int32_t B, int32_t HW, int32_t C, int32_t G, void* stream);
 /* y = act(GroupNorm(x)) with act = SiLU (apply_silu=1) or identity; NHWC bf16 in/out (blocks.py:60-66). */
-int tvae_groupnorm_apply(const void* x_nhwc, const float* sums, const float* gamma, const float* beta, void* y_nhwc,
+int tvae_groupnorm_apply(const void* x_nhwc, const double* sums, const float* gamma, const float* beta, void* y_nhwc,
                          int32_t B, int32_t HW, int32_t C, int32_t G, float eps, int32_t apply_silu, void* stream);
 /* Both passes in one call (statistics, then apply).  `sums` [B, G, 2] is an OUTPUT (the backward pass reuses it).
  * Replaces nn.GroupNorm(32, C) + F.silu (blocks.py:60-66; decoder.py:128-129). */
-int tvae_groupnorm_silu(const void* x_nhwc, const float* gamma, const float* beta, void* y_nhwc, float* sums, int32_t B,
+int tvae_groupnorm_silu(const void* x_nhwc, const float* gamma, const float* beta, void* y_nhwc, double* sums, int32_t B,
                         int32_t HW, int32_t C, int32_t G, float eps, int32_t apply_silu, void* stream);
 /* Per-token statistics for the folded RMSNorm (mode 0; blocks.py:149) / RMSNorm+LayerNorm (mode 1;
  * blocks.py:146 + attention.py:71-73) epilogues of tvae_mtgemm.  x: bf16 [M, C]; w1: fp32 [C] (mode 1). */
@@ -178,7 +180,7 @@ int tvae_bias_act_bwd_4d(const void* dy, const void* z, void* dz, float* colsum,
 int tvae_act_fwd(const void* z, void* y, int64_t n, int32_t act, void* stream);
 /* GroupNorm(+SiLU) backward (blocks.py:60-66): dx = dGN(dh) [+ add]; part fp32 [B, C, 2] = per-(image, channel)
  * (sum dy, sum dy*xhat) from which the caller reduces dgamma / dbeta.  sums = tvae_groupnorm_stats(x). */
-int tvae_groupnorm_bwd(const void* x, const void* dh, const void* add, const float* sums, const float* gamma,
+int tvae_groupnorm_bwd(const void* x, const void* dh, const void* add, const double* sums, const float* gamma,
                        const float* beta, float* part, void* dx, int32_t B, int32_t HW, int32_t C, int32_t G, float eps,
                        int32_t apply_silu, void* stream);
 /* Materialised token norms of the training path: mode 0 RMSNorm (blocks.py:168-201), mode 1 RMSNorm followed by the

@@ -62,8 +62,9 @@ def test_direct_gradient_accumulation_matches_autograd():
     accumulated micro-steps must leave the same gradients in the flat buffer as plain autograd accumulation on a twin
     model (train.py:599-603 semantics: gradients of successive micro-batches add up).  A smooth (linear) loss keeps the
     comparison free of the sign flips of L1; the run-to-run noise of the bf16 / fp32-atomic backward (large on the
-    ill-conditioned bias gradients in front of a normalisation layer) is measured with a second plain twin and the bar
-    is max(5e-3, 4 x that noise) per tensor -- a lost or doubled gradient is an error of order 1."""
+    ill-conditioned bias gradients in front of a normalisation layer, and heavy-tailed in the small-token attention
+    blocks) is measured with a second plain twin and the bar is max(5e-3, 10 x that noise), at most 0.3, per tensor -- a
+    lost or doubled gradient is an error of 0.5 - 1."""
     from transvae import _autograd
     blob, sd = load_golden("mini_tamed")
     m1, m2, m3 = (build_model(blob["cfg"], sd).train() for _ in range(3))
@@ -98,7 +99,7 @@ def test_direct_gradient_accumulation_matches_autograd():
         assert p2.grad is not None and p3.grad is not None, k
         e12, noise = rel_l2(p1.grad, p2.grad), rel_l2(p3.grad, p2.grad)
         n_direct += int(p1.dim() in (2, 4) and p1.shape[0] % 4 == 0)
-        if e12 > max(5e-3, 4.0 * noise):
+        if e12 > min(0.3, max(5e-3, 10.0 * noise)):
             bad.append((k, e12, noise))
     assert not bad, bad[:8]
     assert n_direct > 0
