@@ -137,20 +137,23 @@ class ResBlockFn(Fn):
     """x + conv2(silu(GN2(conv1(silu(GN1(x))))))  (blocks.py:58-68)."""
 
     @staticmethod
-    def forward(ctx, x, g1, b1, w1, c1b, g2, b2, w2, c2b):
-        # w1 / w2: conv weights in the reference layout [C, C, 3, 3]
+    def forward(ctx, x, x_sums, g1, b1, w1, c1b, g2, b2, w2, c2b):
+        # w1 / w2: conv weights in the reference layout [C, C, 3, 3]; x_sums: GroupNorm statistics of x when the producer
+        # left them (the previous ResBlock's conv2 epilogue), else None.  Returns (out, statistics of out).
         B, H, W, C = x.shape
         plan = T.plan_conv3x3(C)
-        h0, s1 = ops.groupnorm_silu(x, g1, b1, return_sums=True)
+        h0, s1 = ops.groupnorm_silu(x, g1, b1, sums=x_sums, return_sums=True)
         (w1f, w1d), (w2f, w2d) = _w_pack(w1), _w_pack(w2)
         h1 = ops.mtgemm(plan, h0, w1f, out_shape=(B, H, W, C), bias=_f32(c1b), gn_groups=32)   # + GN2's statistics
         h2, s2 = ops.groupnorm_silu(h1, g2, b2, sums=h1._gn_sums, return_sums=True)
-        out = ops.mtgemm(plan, h2, w2f, out_shape=(B, H, W, C), bias=_f32(c2b), residual=x)
+        out = ops.mtgemm(plan, h2, w2f, out_shape=(B, H, W, C), bias=_f32(c2b), residual=x, gn_groups=32)
+        out_sums = out._gn_sums
         ctx.save_for_backward(x, s1, h0, h1, s2, h2, g1, b1, w1, g2, b2, w2, w1d, w2d, c1b, c2b)
-        return out
+        ctx.mark_non_differentiable(out_sums)
+        return out, out_sums
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, _dsums):
         x, s1, h0, h1, s2, h2, g1, b1, w1, g2, b2, w2, w1d, w2d, c1b, c2b = ctx.saved_tensors
         dout = dout.contiguous()
         B, H, W, C = x.shape
@@ -161,7 +164,7 @@ class ResBlockFn(Fn):
         dw1, dc1b = _wgrad_b(T.plan_conv3x3(C), h0, dh1, C, b=c1b)
         dh0 = ops.mtgemm(dplan, dh1, w1d, out_shape=(B, H, W, C))
         dx, dg1, db1 = ops.groupnorm_bwd(x, dh0, s1, g1, b1, add=dout)
-        return dx, dg1, db1, _w_ungrad(dw1, w1), dc1b, dg2, db2, _w_ungrad(dw2, w2), dc2b
+        return dx, None, dg1, db1, _w_ungrad(dw1, w1), dc1b, dg2, db2, _w_ungrad(dw2, w2), dc2b
 
 
 class DownsampleFn(Fn):
@@ -384,8 +387,8 @@ class GroupNormSilu(Fn):
     """silu(GroupNorm(x)) standalone (decoder.norm_out, decoder.py:128-129)."""
 
     @staticmethod
-    def forward(ctx, x, g, b, silu):
-        y, s = ops.groupnorm_silu(x, g, b, silu=silu, return_sums=True)
+    def forward(ctx, x, g, b, silu, x_sums=None):
+        y, s = ops.groupnorm_silu(x, g, b, silu=silu, sums=x_sums, return_sums=True)
         ctx.save_for_backward(x, s, g, b)
         ctx.silu = silu
         return y
@@ -394,7 +397,7 @@ class GroupNormSilu(Fn):
     def backward(ctx, dh):
         x, s, g, b = ctx.saved_tensors
         dx, dg, db = ops.groupnorm_bwd(x, dh.contiguous(), s, g, b, silu=ctx.silu)
-        return dx, dg, db, None
+        return dx, dg, db, None, None
 
 
 class NchwToNhwc(Fn):

@@ -70,7 +70,7 @@ def linear(x: Tensor, w: Tensor, plan, **kw) -> Tensor:
 
 def groupnorm_silu(x: Tensor, gamma: Tensor, beta: Tensor, silu: bool = True) -> Tensor:
     if _needs_grad(x, gamma, beta):
-        return _ag().GroupNormSilu.apply(x, gamma, beta, silu)
+        return _ag().GroupNormSilu.apply(x, gamma, beta, silu, gn_sums_of(x))
     # statistics left on the tensor by the convolution that produced it (ops.mtgemm(..., gn_groups=32)): apply pass only
     return ops.groupnorm_silu(x, gamma, beta, silu=silu, sums=gn_sums_of(x))
 

@@ -76,9 +76,11 @@ class ResBlock(HotModule):
             if not add_residual:
                 raise NotImplementedError("add_residual=False is an inference-only test hook")
             from .._autograd import ResBlockFn
-            return ResBlockFn.apply(x, self.norm1.weight, self.norm1.bias, self.conv1.weight,
-                                    self.conv1.bias, self.norm2.weight, self.norm2.bias,
-                                    self.conv2.weight, self.conv2.bias)
+            out, out_sums = ResBlockFn.apply(x, K.gn_sums_of(x), self.norm1.weight, self.norm1.bias, self.conv1.weight,
+                                             self.conv1.bias, self.norm2.weight, self.norm2.bias,
+                                             self.conv2.weight, self.conv2.bias)
+            out._gn_sums = out_sums           # statistics for the next ResBlock's norm1 / decoder.norm_out
+            return out
         plan = T.plan_conv3x3(C)
         w1 = self._packs.get("w1", [self.conv1.weight], lambda: bf16c(T.pack_conv3x3(self.conv1.weight)))
         w2 = self._packs.get("w2", [self.conv2.weight], lambda: bf16c(T.pack_conv3x3(self.conv2.weight)))
