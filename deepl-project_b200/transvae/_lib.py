@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_ROOT, "libtransvae_sm100.so")
+# TVAE_LIB: load another build of the same ABI (kernel experiments, tools/experiments/)
+LIB_PATH = os.environ.get("TVAE_LIB") or os.path.join(_PKG_ROOT, "libtransvae_sm100.so")
 
 MAX_TAPS = 16
 MAX_PHASES = 4

@@ -71,7 +71,8 @@ def test_gemm_epilogues():
 
 
 @pytest.mark.parametrize("B,C,H,W,N", [(2, 64, 16, 16, 64), (1, 192, 128, 128, 192), (3, 128, 32, 32, 256),
-                                       (2, 64, 8, 8, 128), (1, 64, 4, 4, 64), (2, 128, 64, 64, 128)])
+                                       (2, 64, 8, 8, 128), (1, 64, 4, 4, 64), (2, 128, 64, 64, 128),
+                                       (1, 64, 5, 256, 128), (2, 192, 3, 384, 192)])   # two / three 128-pixel tiles per row
 def test_conv3x3(B, C, H, W, N):
     x, w, b = bf(rnd(B, C, H, W)), bf(rnd(N, C, 3, 3, seed=1, scale=0.05)), rnd(N, seed=2)
     res = bf(rnd(B, N, H, W, seed=3))
