@@ -23,7 +23,8 @@
 namespace tvae {
 
 int mtgemm2_dispatch(int epi, int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                     const CUtensorMap& o, const CUtensorMap& r, const MtParams& P, cudaStream_t stream);
+                     const CUtensorMap& o, const CUtensorMap& r, const CUtensorMap& ah, const MtParams& P,
+                     cudaStream_t stream);
 static int mtgemm1_dispatch(int epi, int block_n, const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB,
                             const CUtensorMap& mO, const CUtensorMap& mR, const MtParams& P, cudaStream_t stream);
 int gn_stats_run(const void* x, double* sums, int B, int HW, int C, int G, cudaStream_t stream);   // elementwise.cu
@@ -483,9 +484,26 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
     }
   }
   if (pair) {
-    CUtensorMap mBh;
+    CUtensorMap mBh, mAh = mA0;
     if ((rc = make_tmap_2d(&mBh, d->w, d->n_total, d->k_total, d->k_total, block_n / 2))) return rc;
-    if ((rc = mtgemm2_dispatch(epi, block_n, mA0, mA1, mBh, mO, mR, P, stream))) return rc;
+    // halo mode: a plain 3x3 stride-1 convolution whose tiles are 128 pixels of one image row (W >= 128) loads ONE
+    // 130-pixel tile per (kernel row, K block) instead of three shifted 128-pixel tiles (TVAE_HALO=0 disables: A/B switch)
+    static const int halo_env = getenv("TVAE_HALO") ? atoi(getenv("TVAE_HALO")) : 1;
+    if (halo_env && P.tw == 128 && d->num_phases == 1 && d->ntaps[0] == 9 && !d->a0.split) {
+      bool ok = true;
+      for (int t = 0; t < 9; ++t) {       // three kernel rows of three taps: same dh, dw a permutation of {-1, 0, 1}
+        const tvae_tap& s = d->taps[0][t];
+        ok = ok && s.map == 0 && s.p == 0 && s.c_off == 0 && s.dw >= -1 && s.dw <= 1 && s.dh == d->taps[0][t - t % 3].dh &&
+             s.kblocks == d->taps[0][0].kblocks && s.kblocks * 64 == d->a0.C;
+        if (t % 3 == 2) ok = ok && d->taps[0][t].dw + d->taps[0][t - 1].dw + d->taps[0][t - 2].dw == 0 &&
+                               d->taps[0][t].dw != d->taps[0][t - 1].dw && d->taps[0][t - 1].dw != d->taps[0][t - 2].dw;
+      }
+      if (ok) {
+        if ((rc = make_tmap_pix_halo(&mAh, d->a0.ptr, d->a0.B, d->a0.H, d->a0.W, d->a0.C))) return rc;
+        P.halo = 1;
+      }
+    }
+    if ((rc = mtgemm2_dispatch(epi, block_n, mA0, mA1, mBh, mO, mR, mAh, P, stream))) return rc;
     if (d->gn_sums != nullptr && !gn_fused)
       return gn_stats_run(d->out.ptr, d->gn_sums, d->out.B, d->out.H * d->out.W, d->out.C, d->gn_groups, stream);
     return 0;

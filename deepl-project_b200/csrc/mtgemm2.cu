@@ -29,6 +29,9 @@ struct Mt2Cfg {
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
   static constexpr int kSmemBytes = kStages * (kABytes + kBHalfBytes) + kOutBytes + 1024 + 256;
+  // halo mode: a stage = one halo A tile + the B halves of the three dx taps, carved out of the same ring
+  static constexpr int kHaloStageBytes = kHaloABytes + 3 * kBHalfBytes;
+  static constexpr int kHaloStages = kStages * (kABytes + kBHalfBytes) / kHaloStageBytes;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -88,7 +91,8 @@ template <int BLOCK_N, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
-               const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ MtParams P) {
+               const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmAh,
+               const __grid_constant__ MtParams P) {
 #ifdef TVAE_DEVICE_OK
   using Cfg = Mt2Cfg<BLOCK_N>;
   constexpr int STAGES = Cfg::kStages;
@@ -126,6 +130,7 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
     tma_prefetch_desc(&tmRes);
+    tma_prefetch_desc(&tmAh);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -168,7 +173,32 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    if (lane == 0 && P.halo) {
+      // halo mode: per (kernel row dy, K block) one 130-pixel A tile [w0 - 1, w0 + 129) and three B halves
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+        TVAE_DECODE_PAIR(pt)
+        (void)ph;
+        const int kbs = P.taps[0][0].kblocks;
+        for (int dy = 0; dy < 3; ++dy) {
+          for (int kb = 0; kb < kbs; ++kb) {
+            uint8_t* st = smem + stage * Cfg::kHaloStageBytes;
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (kHaloATx + 3 * Cfg::kBHalfBytes));
+            tma2_load_5d(st, &tmAh, &full[stage], kb * kBlockK, w0 - 1, 0, h0 + P.taps[0][dy * 3].dh, b0);
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+              tma2_load_2d(st + kHaloABytes + dx * Cfg::kBHalfBytes, &tmB, &full[stage],
+                           P.taps[0][dy * 3 + dx].wk_off + kb * kBlockK, n_t * BLOCK_N + (int)rank * (BLOCK_N / 2));
+            if (++stage == Cfg::kHaloStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
@@ -194,7 +224,48 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && leader) {
+    if (lane == 0 && leader && P.halo) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N, 0, 0);
+      // descriptor base-offset field cleared: the 128-byte swizzle is a function of the shared-memory ADDRESS bits (as TMA
+      // wrote it), so a start address in the middle of a 1024-byte swizzle atom needs no correction -- with base offset =
+      // (addr >> 7) & 7 every row-shifted tap came out wrong, with 0 all are exact (tools/experiments/umma_row_offset.cu)
+      constexpr uint64_t bo_mask = ~(uint64_t(7) << 49);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      const int kbs = P.taps[0][0].kblocks;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int s3 = 0; s3 < 3 * kbs; ++s3) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * Cfg::kHaloStageBytes);
+          const uint32_t b_base = a_base + kHaloABytes;
+          const int dy = s3 / kbs;
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            // the tap with pixel offset dw reads halo rows [dw + 1, dw + 129): the K-major SW128 layout is linear in
+            // the row (128 B per row, SBO = 8 rows), so a tap is just a start address (dw + 1) rows further
+            const uint32_t a_tap = a_base + (P.taps[0][dy * 3 + dx].dw + 1) * 128;
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              umma2_f16(d_tmem, umma_desc_kmajor_sw128(a_tap + k * 32) & bo_mask,
+                        umma_desc_kmajor_sw128(b_base + dx * Cfg::kBHalfBytes + k * 32), idesc, (s3 | dx | k) != 0);
+            }
+          }
+          umma2_commit_mc(&empty[stage]);
+          if (++stage == Cfg::kHaloStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma2_commit_mc(&tmem_full[acc]);
+      }
+    } else if (lane == 0 && leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -455,7 +526,7 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
 template <int BLOCK_N, int EPI>
 static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
-                   const CUtensorMap& r, const MtParams& P, cudaStream_t stream) {
+                   const CUtensorMap& r, const CUtensorMap& ah, const MtParams& P, cudaStream_t stream) {
   using Cfg = Mt2Cfg<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
@@ -468,37 +539,38 @@ static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorM
   int clusters = num_sms() / 2;
   if (clusters <= 0) clusters = 74;
   if (total_pairs < clusters) clusters = total_pairs;
-  mtgemm2_kernel<BLOCK_N, EPI><<<2 * clusters, kThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b, o, r, P);
+  mtgemm2_kernel<BLOCK_N, EPI><<<2 * clusters, kThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b, o, r, ah, P);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int EPI>
 static int launch2_n(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
-                     const CUtensorMap& r, const MtParams& P, cudaStream_t stream) {
+                     const CUtensorMap& r, const CUtensorMap& ah, const MtParams& P, cudaStream_t stream) {
   switch (block_n) {
-    case 256: return launch2<256, EPI>(a0, a1, b, o, r, P, stream);
-    case 192: return launch2<192, EPI>(a0, a1, b, o, r, P, stream);
-    default: return launch2<128, EPI>(a0, a1, b, o, r, P, stream);
+    case 256: return launch2<256, EPI>(a0, a1, b, o, r, ah, P, stream);
+    case 192: return launch2<192, EPI>(a0, a1, b, o, r, ah, P, stream);
+    default: return launch2<128, EPI>(a0, a1, b, o, r, ah, P, stream);
   }
 }
 
 // Called by mtgemm_run (mtgemm.cu) when the CTA-pair kernel applies (block_n >= 128).  `b` must be a weight map with
 // box rows = block_n / 2.
 int mtgemm2_dispatch(int epi, int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                     const CUtensorMap& o, const CUtensorMap& r, const MtParams& P, cudaStream_t stream) {
+                     const CUtensorMap& o, const CUtensorMap& r, const CUtensorMap& ah, const MtParams& P,
+                     cudaStream_t stream) {
   switch (epi) {
-    case kEpiBias: return launch2_n<kEpiBias>(block_n, a0, a1, b, o, r, P, stream);
-    case kEpiBiasRes: return launch2_n<kEpiBiasRes>(block_n, a0, a1, b, o, r, P, stream);
-    case kEpiBiasGelu: return launch2_n<kEpiBiasGelu>(block_n, a0, a1, b, o, r, P, stream);
-    case kEpiBiasSilu: return launch2_n<kEpiBiasSilu>(block_n, a0, a1, b, o, r, P, stream);
-    case kEpiRsBiasGelu: return launch2_n<kEpiRsBiasGelu>(block_n, a0, a1, b, o, r, P, stream);
-    case kEpiAffineRope: return launch2_n<kEpiAffineRope>(block_n, a0, a1, b, o, r, P, stream);
-    case kEpiDirect: return launch2_n<kEpiDirect>(block_n, a0, a1, b, o, r, P, stream);
-    case kEpiMulGeluGrad: return launch2_n<kEpiMulGeluGrad>(block_n, a0, a1, b, o, r, P, stream);
-    case kEpiMulSiluGrad: return launch2_n<kEpiMulSiluGrad>(block_n, a0, a1, b, o, r, P, stream);
-    case kEpiResMulGeluGrad: return launch2_n<kEpiResMulGeluGrad>(block_n, a0, a1, b, o, r, P, stream);
-    default: return launch2_n<kEpiRsBias>(block_n, a0, a1, b, o, r, P, stream);
+    case kEpiBias: return launch2_n<kEpiBias>(block_n, a0, a1, b, o, r, ah, P, stream);
+    case kEpiBiasRes: return launch2_n<kEpiBiasRes>(block_n, a0, a1, b, o, r, ah, P, stream);
+    case kEpiBiasGelu: return launch2_n<kEpiBiasGelu>(block_n, a0, a1, b, o, r, ah, P, stream);
+    case kEpiBiasSilu: return launch2_n<kEpiBiasSilu>(block_n, a0, a1, b, o, r, ah, P, stream);
+    case kEpiRsBiasGelu: return launch2_n<kEpiRsBiasGelu>(block_n, a0, a1, b, o, r, ah, P, stream);
+    case kEpiAffineRope: return launch2_n<kEpiAffineRope>(block_n, a0, a1, b, o, r, ah, P, stream);
+    case kEpiDirect: return launch2_n<kEpiDirect>(block_n, a0, a1, b, o, r, ah, P, stream);
+    case kEpiMulGeluGrad: return launch2_n<kEpiMulGeluGrad>(block_n, a0, a1, b, o, r, ah, P, stream);
+    case kEpiMulSiluGrad: return launch2_n<kEpiMulSiluGrad>(block_n, a0, a1, b, o, r, ah, P, stream);
+    case kEpiResMulGeluGrad: return launch2_n<kEpiResMulGeluGrad>(block_n, a0, a1, b, o, r, ah, P, stream);
+    default: return launch2_n<kEpiRsBias>(block_n, a0, a1, b, o, r, ah, P, stream);
   }
 }
 

@@ -41,12 +41,18 @@ struct MtParams {
   const __nv_bfloat16* z;   // act_grad == 2: pre-activation matrix [M, n_total]
   double* gn_sums;          // fused GroupNorm statistics of the output: [vB][gn_groups][2] (sum, sumsq), or nullptr
   int gn_groups, gn_cpg;    // groups, channels per group
+  // halo mode (3x3 stride-1 convolution, 128-pixel-wide tiles): ONE (128 + 2)-pixel A tile per (kernel row, K block)
+  // serves the three dx taps through row-offset UMMA descriptors.  0 = off, 1 = on
+  int halo;
 };
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps
+constexpr int kHaloPix = kBlockM + 2;                       // pixels of a halo tile
+constexpr int kHaloATx = kHaloPix * kBlockK * 2;            // bytes one halo load delivers (16640)
+constexpr int kHaloABytes = (kHaloATx + 1023) / 1024 * 1024;  // its shared-memory slot (17408)
 
 template <int BLOCK_N>
 struct MtCfg {

@@ -103,6 +103,17 @@ int make_tmap_pix(CUtensorMap* out, const void* ptr, int B, int H, int W, int C,
   return encode(out, ptr, 5, dims, str, box);
 }
 
+// Plain pixel view with a (64 channels, 128 + 2 pixels of one image row) box: the halo tile of the 3x3 convolutions
+// (mtgemm2 halo mode).  Out-of-bounds pixels (w = -1, w = W, h = -1, h = H) are zero-filled: the convolution padding.
+int make_tmap_pix_halo(CUtensorMap* out, const void* ptr, int B, int H, int W, int C) {
+  TVAE_REQUIRE(C % 8 == 0, "NHWC channel count %d must be a multiple of 8", C);
+  const uint64_t e = 2;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, 1, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t str[4] = {(uint64_t)C * e, (uint64_t)W * C * e, (uint64_t)W * C * e, (uint64_t)H * W * C * e};
+  cuuint32_t box[5] = {64, 130, 1, 1, 1};
+  return encode(out, ptr, 5, dims, str, box);
+}
+
 int make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
                  uint64_t stride2_elems, uint32_t box1) {
   cuuint64_t dims[3] = {d0, d1, d2};

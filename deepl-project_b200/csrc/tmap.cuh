@@ -17,6 +17,9 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols
 // box = (64, tw, 1, th, nb), 128-byte swizzle, zero fill out of bounds (this is the conv halo).
 int make_tmap_pix(CUtensorMap* out, const void* ptr, int B, int H, int W, int C, int split, int tw, int th, int nb);
 
+// plain view, box = (64, 130, 1, 1, 1): 128 + 2 pixels of one image row (halo tile of the 3x3 convolutions)
+int make_tmap_pix_halo(CUtensorMap* out, const void* ptr, int B, int H, int W, int C);
+
 // 3-D bf16 tensor (d0 contiguous); box = (64, box1, 1), 128-byte swizzle.  Used for per-image token matrices
 // [B, S, C] so that rows beyond S are zero-filled / clipped instead of running into the next image.
 int make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
