@@ -467,7 +467,21 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
   }
   // CTA-pair kernel (cta_group::2, weight tile split across the pair) whenever the tile is wide enough to matter
   static const bool use_pair = !(getenv("TVAE_2CTA") && atoi(getenv("TVAE_2CTA")) == 0);
-  const bool pair = use_pair && block_n >= 128 && P.tiles_w * P.tiles_h * P.tiles_b >= 2;
+  // halo mode: a plain 3x3 stride-1 convolution whose tiles are 128 pixels of one image row (W >= 128) loads ONE
+  // 130-pixel tile per (kernel row, K block) instead of three shifted 128-pixel tiles (TVAE_HALO=0 disables: A/B switch)
+  static const int halo_env = getenv("TVAE_HALO") ? atoi(getenv("TVAE_HALO")) : 1;
+  bool halo_ok = halo_env && P.tw == 128 && d->num_phases == 1 && d->ntaps[0] == 9 && !d->a0.split;
+  for (int t = 0; halo_ok && t < 9; ++t) {       // three kernel rows of three taps: same dh, dw a permutation of {-1, 0, 1}
+    const tvae_tap& s = d->taps[0][t];
+    halo_ok = s.map == 0 && s.p == 0 && s.c_off == 0 && s.dw >= -1 && s.dw <= 1 && s.dh == d->taps[0][t - t % 3].dh &&
+              s.kblocks == d->taps[0][0].kblocks && s.kblocks * 64 == d->a0.C;
+    if (halo_ok && t % 3 == 2)
+      halo_ok = d->taps[0][t].dw + d->taps[0][t - 1].dw + d->taps[0][t - 2].dw == 0 &&
+                d->taps[0][t].dw != d->taps[0][t - 1].dw && d->taps[0][t - 1].dw != d->taps[0][t - 2].dw;
+  }
+  // narrow outputs (N = 64: the 3-channel output convolution, padded) are bound by the L2->SM traffic of their A tiles,
+  // so they take the pair kernel too when the halo tiles cut that traffic by 3x
+  const bool pair = use_pair && (block_n >= 128 || halo_ok) && P.tiles_w * P.tiles_h * P.tiles_b >= 2;
   // GroupNorm statistics of the output: from the epilogue when the launch qualifies, else one tvae_groupnorm_stats pass
   bool gn_fused = false;
   if (d->gn_sums != nullptr) {
@@ -486,22 +500,9 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
   if (pair) {
     CUtensorMap mBh, mAh = mA0;
     if ((rc = make_tmap_2d(&mBh, d->w, d->n_total, d->k_total, d->k_total, block_n / 2))) return rc;
-    // halo mode: a plain 3x3 stride-1 convolution whose tiles are 128 pixels of one image row (W >= 128) loads ONE
-    // 130-pixel tile per (kernel row, K block) instead of three shifted 128-pixel tiles (TVAE_HALO=0 disables: A/B switch)
-    static const int halo_env = getenv("TVAE_HALO") ? atoi(getenv("TVAE_HALO")) : 1;
-    if (halo_env && P.tw == 128 && d->num_phases == 1 && d->ntaps[0] == 9 && !d->a0.split) {
-      bool ok = true;
-      for (int t = 0; t < 9; ++t) {       // three kernel rows of three taps: same dh, dw a permutation of {-1, 0, 1}
-        const tvae_tap& s = d->taps[0][t];
-        ok = ok && s.map == 0 && s.p == 0 && s.c_off == 0 && s.dw >= -1 && s.dw <= 1 && s.dh == d->taps[0][t - t % 3].dh &&
-             s.kblocks == d->taps[0][0].kblocks && s.kblocks * 64 == d->a0.C;
-        if (t % 3 == 2) ok = ok && d->taps[0][t].dw + d->taps[0][t - 1].dw + d->taps[0][t - 2].dw == 0 &&
-                               d->taps[0][t].dw != d->taps[0][t - 1].dw && d->taps[0][t - 1].dw != d->taps[0][t - 2].dw;
-      }
-      if (ok) {
-        if ((rc = make_tmap_pix_halo(&mAh, d->a0.ptr, d->a0.B, d->a0.H, d->a0.W, d->a0.C))) return rc;
-        P.halo = 1;
-      }
+    if (halo_ok) {
+      if ((rc = make_tmap_pix_halo(&mAh, d->a0.ptr, d->a0.B, d->a0.H, d->a0.W, d->a0.C))) return rc;
+      P.halo = 1;
     }
     if ((rc = mtgemm2_dispatch(epi, block_n, mA0, mA1, mBh, mO, mR, mAh, P, stream))) return rc;
     if (d->gn_sums != nullptr && !gn_fused)

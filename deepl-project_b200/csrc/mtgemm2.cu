@@ -550,6 +550,7 @@ static int launch2_n(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, 
   switch (block_n) {
     case 256: return launch2<256, EPI>(a0, a1, b, o, r, ah, P, stream);
     case 192: return launch2<192, EPI>(a0, a1, b, o, r, ah, P, stream);
+    case 64: return launch2<64, EPI>(a0, a1, b, o, r, ah, P, stream);
     default: return launch2<128, EPI>(a0, a1, b, o, r, ah, P, stream);
   }
 }

@@ -114,10 +114,10 @@ def test_upsample(B, Ci, Co, H):
     assert rel(nchw(out), ref) < 1e-2, rel(nchw(out), ref)
 
 
-def test_direct_fp32_heads():
-    B, C, H = 2, 128, 16
-    x, w, b = bf(rnd(B, C, H, H)), bf(rnd(3, C, 3, 3, seed=1, scale=0.05)), rnd(3, seed=2)
-    out = torch.zeros(B, 3, H, H, device=DEV)
+@pytest.mark.parametrize("B,C,H,W", [(2, 128, 16, 16), (1, 192, 5, 256), (2, 64, 3, 384)])   # W >= 128: halo tiles, pair kernel
+def test_direct_fp32_heads(B, C, H, W):
+    x, w, b = bf(rnd(B, C, H, W)), bf(rnd(3, C, 3, 3, seed=1, scale=0.05)), rnd(3, seed=2)
+    out = torch.zeros(B, 3, H, W, device=DEV)
     bias = torch.zeros(64, device=DEV)
     bias[:3] = b
     ops.mtgemm(T.plan_conv3x3(C), nhwc(x), T.pack_conv3x3(w, cout_pad=64).contiguous(), bias=bias, out_f32=out, out_n=3)
