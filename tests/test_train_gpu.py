@@ -133,8 +133,12 @@ def test_training_loss_matches_golden(name):
     recon, mu, logvar = m(x, eps=blob["eps"].cuda())
     losses = loss_fn(recon, x, mu, logvar)
     losses["total"].backward()
-    assert abs(float(losses["total"].detach()) - float(blob["loss_total"])) < 5e-3
-    assert abs(float(losses["l1"].detach()) - float(blob["loss_l1"])) < 5e-3
+    # bf16 forward against the reference's fp32 loss.  The tamed fixture agrees to 1e-4; the untamed random init
+    # ("mini_ref": activations grow to 1e2, every block amplifies the bf16 rounding of the one before) sits at
+    # 0.30 - 0.33 % of its loss of 1.585, so its bar is 1e-2 absolute (0.6 %) rather than a coin flip at 5e-3
+    tol = 5e-3 if name == "mini_tamed" else 1e-2
+    assert abs(float(losses["total"].detach()) - float(blob["loss_total"])) < tol
+    assert abs(float(losses["l1"].detach()) - float(blob["loss_l1"])) < tol
     for k, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), k
 
