@@ -145,6 +145,24 @@ def test_streamed_reconstructor_matches_direct_calls():
         pipe.reconstruct(torch.rand(blob["x"].shape), outs[0])      # unpinned input
 
 
+def test_inference_forward_is_bit_reproducible():
+    """Two runs of encode -> decode on the same input give identical bits.  The only order-dependent reduction of the
+    inference path, the GroupNorm statistics, is accumulated in fp64 (fp32 tile partials in a fixed order + fp64
+    atomics, E[x^2] - mean^2 in fp64); with fp32 sums identical runs differed by 1.3 % (l2) on the reconstruction of
+    large-f16d32 (profiles/r1c_noise_probe_large_fp32_sums.txt)."""
+    blob, sd = load_golden("mini_tamed_128")
+    m = build_model(blob["cfg"], sd)
+    x = blob["x"].cuda()
+    with torch.no_grad():
+        outs = []
+        for _ in range(3):
+            mu, logvar = m.encode(x)
+            outs.append((mu.clone(), logvar.clone(), m.decode(mu).clone()))
+    for o in outs[1:]:
+        for a, b in zip(o, outs[0]):
+            assert torch.equal(a, b)
+
+
 def test_public_module_forward_nchw():
     """The reference's per-module public signature (NCHW in, NCHW out) on a bare block / attention / FFN."""
     blob, sd = load_golden("mini_tamed")
