@@ -52,17 +52,32 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_bucketed_allreduce_matches_single_process():
+def _run_two_ranks():
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
-    got = out.get(timeout=120)
+    try:
+        got = out.get(timeout=120)
+    except Exception:
+        got = None
+    ok = got is not None
     for p in procs:
         p.join(timeout=120)
-        assert p.exitcode == 0
+        if p.is_alive():
+            p.kill()
+            ok = False
+        ok = ok and p.exitcode == 0
+    return got if ok else None
+
+
+def test_bucketed_allreduce_matches_single_process():
+    # the rendezvous port is picked by bind(0) and released before the workers take it: retry once if something else
+    # grabbed it in between (seen once in ~50 runs on a loaded container)
+    got = _run_two_ranks() or _run_two_ranks()
+    assert got is not None
     m = _mlp()
     x = torch.randn(6, 8, generator=torch.Generator().manual_seed(1))
     m(x).pow(2).sum().backward()            # sum over all samples == sum of the per-rank sums
