@@ -67,11 +67,13 @@ constexpr int kGnBatch = 8;   // independent 16-byte loads a thread keeps in fli
 
 __global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__ x, double* __restrict__ sums, int HW,
                                                        int C, int G, int pix_per_block) {
-  __shared__ float s_acc[2 * 128];
+  // block-level staging in fp64 as well: hundreds of threads add into each slot in an arbitrary order, and in fp32 that
+  // order showed up as run-to-run differences of the statistics (the global sums are fp64 for the same reason)
+  __shared__ double s_acc[2 * 128];
   const int nvec = C >> 3;
   const int ppb = blockDim.x / nvec;           // pixels processed per pass
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.0f;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.0;
   __syncthreads();
   const int v = threadIdx.x % nvec, pv = threadIdx.x / nvec;
   float2 s[4], ss[4];
@@ -100,13 +102,13 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int g0 = (v * 8 + 2 * i) / cpg, g1 = (v * 8 + 2 * i + 1) / cpg;
-    atomicAdd(&s_acc[2 * g0], s[i].x);
-    atomicAdd(&s_acc[2 * g0 + 1], ss[i].x);
-    atomicAdd(&s_acc[2 * g1], s[i].y);
-    atomicAdd(&s_acc[2 * g1 + 1], ss[i].y);
+    atomicAdd(&s_acc[2 * g0], (double)s[i].x);
+    atomicAdd(&s_acc[2 * g0 + 1], (double)ss[i].x);
+    atomicAdd(&s_acc[2 * g1], (double)s[i].y);
+    atomicAdd(&s_acc[2 * g1 + 1], (double)ss[i].y);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&sums[(size_t)b * 2 * G + i], (double)s_acc[i]);
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&sums[(size_t)b * 2 * G + i], s_acc[i]);
 }
 
 int gn_stats_run(const void* x, double* sums, int B, int HW, int C, int G, cudaStream_t stream) {

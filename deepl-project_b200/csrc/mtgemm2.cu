@@ -118,10 +118,10 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const bool has_res = kHasRes && P.has_residual;
   // fused GroupNorm statistics of the output (bias / bias+residual epilogues only): per-CTA staging of (sum, sumsq)
   constexpr bool kGn = (EPI == kEpiBias || EPI == kEpiBiasRes);
-  __shared__ float s_gn[kGn ? 128 : 1];
+  __shared__ double s_gn[kGn ? 128 : 1];     // fp64 like the global sums: several column groups may add into one group
   const bool gn = kGn && P.gn_sums != nullptr;
   if constexpr (kGn) {
-    if (threadIdx.x < 128) s_gn[threadIdx.x] = 0.0f;
+    if (threadIdx.x < 128) s_gn[threadIdx.x] = 0.0;
   }
 
   if (warp == 0 && lane == 0) {
@@ -478,8 +478,8 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                   aq += qv[k];
                   if (++rem == P.gn_cpg || k == 7) {
                     if (g < P.gn_groups) {
-                      atomicAdd(&s_gn[2 * g], as);
-                      atomicAdd(&s_gn[2 * g + 1], aq);
+                      atomicAdd(&s_gn[2 * g], (double)as);
+                      atomicAdd(&s_gn[2 * g + 1], (double)aq);
                     }
                     as = aq = 0.0f;
                     rem = 0;
@@ -498,10 +498,10 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (gn) {
             const int et = (int)threadIdx.x - 128;
             if (et < 2 * P.gn_groups) {
-              const float v = s_gn[et];
-              if (v != 0.0f) {      // only the groups of this n tile; a phantom tile (b0 >= vB) contributes nothing
-                atomicAdd(P.gn_sums + (size_t)b0 * 2 * P.gn_groups + et, (double)v);
-                s_gn[et] = 0.0f;
+              const double v = s_gn[et];
+              if (v != 0.0) {       // only the groups of this n tile; a phantom tile (b0 >= vB) contributes nothing
+                atomicAdd(P.gn_sums + (size_t)b0 * 2 * P.gn_groups + et, v);
+                s_gn[et] = 0.0;
               }
             }
           }

@@ -1,6 +1,6 @@
 """Run-to-run reproducibility probe: the same encode (+ decode) twice on the same input, per-layer l2 / max difference
 (encoder / decoder `trace` hooks), to find which kernel introduces non-determinism.
-    python tools/noise_probe.py [mini|large] [batch]"""
+    python tools/noise_probe.py [mini|mini_tamed_128|large] [batch]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "deepl-project_b200"))
@@ -10,9 +10,9 @@ import torch
 import transvae
 
 which = sys.argv[1] if len(sys.argv) > 1 else "mini"
-if which == "mini":
+if which.startswith("mini"):
     from util import build_model, load_golden
-    blob, sd = load_golden("mini_tamed")
+    blob, sd = load_golden(which if which != "mini" else "mini_tamed")
     m = build_model(blob["cfg"], sd)
     x = blob["x"].cuda()
 else:
