@@ -8,10 +8,12 @@ on one batch.  N>1 (launched by torchrun, one rank per GPU): the batch dimension
 same per-GPU batch (weak scaling), no data-path collective; the timed region is bracketed by a barrier +
 torch.cuda.synchronize(), timed on the device with CUDA events, MAX over ranks.
 
-Printed JSON keys (one line, rank 0): metric/value/unit/..., `e2e` (same metric through the public API with pinned
-host buffers, H2D and D2H inside the timed region), `roofline` (tensor-pipe roofline of the dominant kernel,
-tvae::mtgemm_kernel, from per-launch CUDA events), `cpu_baseline` (the oracle port of the reference's PyTorch path
-on this box's host cores, bounded sample), `clocks`, `gpu_launches`.
+Printed JSON keys (one line, rank 0): metric/value/unit/..., `e2e` (same metric through the public host-to-host call
+transvae.streaming.StreamedReconstructor.reconstruct: every step uploads its pinned input and downloads its
+reconstruction inside the timed region, on side streams), `roofline` (tensor-pipe roofline of the dominant kernel,
+tvae::mtgemm2_kernel / mtgemm_kernel, from per-launch CUDA events; `traffic` from the committed ncu capture),
+`cpu_baseline` (the oracle port of the reference's PyTorch path on this box's host cores, bounded sample), `clocks`,
+`gpu_launches`, `train` (BASELINE configs[2]: fwd + L1/KL loss + bwd + all-reduce + clip + AdamW on global batch 256).
 
 `--impl reference` times the oracle port (oracle/transvae_oracle.py, a bit-exact restatement of the reference's
 torch path -- the reference is pure Python and cannot travel to the GPU box) on the host cores.
