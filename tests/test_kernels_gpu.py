@@ -194,6 +194,9 @@ def _gn_ref(y_nhwc, groups):
     (2, 64, 16, 16, 128, True),      # N = 128
     (5, 64, 8, 8, 128, False),       # 64 pixels per image -> two images per tile -> library falls back to the stats pass
     (1, 64, 16, 16, 64, True),       # N = 64: 1-CTA kernel -> fallback
+    (1, 320, 3, 128, 320, True),     # giant variant: 10 channels per group straddle column groups AND the 64-wide n tiles;
+                                     # 128-pixel rows -> halo tiles on the N = 64 pair kernel
+    (2, 64, 2, 256, 64, False),      # N = 64 with halo tiles and fused statistics (two tiles per image row)
 ])
 def test_conv3x3_gn_sums(B, C, H, W, N, res):
     """tvae_mtgemm with gn_sums: GroupNorm(32) statistics of the convolution output from the GEMM epilogue
