@@ -40,11 +40,14 @@ int loss_bwd_run(const float* recon, const float* target, const float* mu, const
                  float clip_hi, cudaStream_t stream);
 int latent_bwd_run(const float* mu, const float* logvar, const float* eps, const float* dz, const float* dmu_ret,
                    const float* dlv_ret, float* dmu, float* dlv, long long n, int patched, cudaStream_t stream);
-int sumsq_run(const float* g, long long n, float* out, cudaStream_t stream);
+int grad_sumsq_run(const void* g, int g_bf16, long long n, double* partials, cudaStream_t stream);
+int adamw_step_run(float* p, const void* g, int g_bf16, float* m, float* v, long long n, const double* partials,
+                   float* state, float lr_base, int warmup_steps, float b1, float b2, float eps, float wd, float max_norm,
+                   float grad_scale, cudaStream_t stream);
+int cast_f32_bf16_run(const float* in, void* out, long long n, cudaStream_t stream);
+int mta_add_run(float* const* dst, const float* const* src, const int* n, const int* sstride, int count, cudaStream_t stream);
 int weight_pack_run(const float* w, void* fwd, void* dgr, int A, int B, int T, cudaStream_t stream);
 int wgrad_unpack_run(const float* g, float* out, int A, int B, int T, cudaStream_t stream);
-int adamw_run(float* p, const float* g, float* m, float* v, long long n, const float* ctrl, float lr, float b1, float b2,
-              float eps, float wd, int step, cudaStream_t stream);
 int metrics_run(const float* recon, const float* target, float* acc, int B, int C, int H, int W, int mode,
                 cudaStream_t stream);
 }  // namespace tvae
@@ -70,6 +73,7 @@ extern "C" {
 int tvae_abi_version(void) { return TVAE_ABI_VERSION; }
 const char* tvae_last_error(void) { return get_last_error(); }
 int tvae_num_sms(void) { return num_sms(); }
+int tvae_set_reserved_sms(int32_t n) { set_reserved_sms(n); return persistent_sms(); }
 
 int tvae_device_ok(void) {
   static int cached = -1;
@@ -177,10 +181,22 @@ int tvae_weight_pack(const float* w, void* fwd_bf16, void* dgrad_bf16, int32_t A
 int tvae_wgrad_unpack(const float* g_packed, float* g_ref, int32_t A, int32_t B, int32_t T, void* stream) {
   GUARD(); return wgrad_unpack_run(g_packed, g_ref, A, B, T, S_(stream));
 }
-int tvae_sumsq(const float* g, int64_t n, float* out, void* stream) { GUARD(); return sumsq_run(g, n, out, S_(stream)); }
-int tvae_adamw(float* p, const float* g, float* m, float* v, int64_t n, const float* ctrl, float lr, float beta1, float beta2,
-               float eps, float weight_decay, int32_t step, void* stream) {
-  GUARD(); return adamw_run(p, g, m, v, n, ctrl, lr, beta1, beta2, eps, weight_decay, step, S_(stream));
+int tvae_grad_sumsq(const void* g, int32_t g_bf16, int64_t n, double* partials, void* stream) {
+  GUARD(); return grad_sumsq_run(g, g_bf16, n, partials, S_(stream));
+}
+int tvae_adamw_step(float* p, const void* g, int32_t g_bf16, float* m, float* v, int64_t n, const double* partials,
+                    float* state, float lr_base, int32_t warmup_steps, float beta1, float beta2, float eps,
+                    float weight_decay, float max_norm, float grad_scale, void* stream) {
+  GUARD();
+  return adamw_step_run(p, g, g_bf16, m, v, n, partials, state, lr_base, warmup_steps, beta1, beta2, eps, weight_decay,
+                        max_norm, grad_scale, S_(stream));
+}
+int tvae_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, void* stream) {
+  GUARD(); return cast_f32_bf16_run(in, out_bf16, n, S_(stream));
+}
+int tvae_multi_tensor_add(float* const* dst, const float* const* src, const int32_t* n, const int32_t* src_stride,
+                          int32_t count, void* stream) {
+  GUARD(); return mta_add_run(dst, src, n, src_stride, count, S_(stream));
 }
 
 int tvae_metrics(const float* recon, const float* target, float* acc, int32_t B, int32_t C, int32_t H, int32_t W,

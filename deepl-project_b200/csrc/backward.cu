@@ -1002,78 +1002,4 @@ int latent_bwd_run(const float* mu, const float* logvar, const float* eps, const
   return 0;
 }
 
-// -------------------------------------------------------------------------------------------------
-// Optimiser: fused AdamW over flat fp32 buffers + gradient sum of squares (for clip_grad_norm_).
-// Replaces clip_grad_norm_(1.0) + fused AdamW(lr, betas=(0.9, 0.95), wd) of the training step
-// (train.py:608-620; train_working.py:384-397).  Algorithmic bytes: 16 read + 12 written per parameter.
-// -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ g, long long n4, float* __restrict__ out) {
-  float acc = 0.0f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = __ldg(g + i);
-    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-  }
-  __shared__ float red[8];
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    acc = threadIdx.x < 8 ? red[threadIdx.x] : 0.0f;
-    acc = warp_sum(acc);
-    if (threadIdx.x == 0) atomicAdd(out, acc);
-  }
-}
-
-int sumsq_run(const float* g, long long n, float* out, cudaStream_t stream) {
-  TVAE_REQUIRE(n % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0, "sumsq: buffer must be float4-aligned/padded");
-  int grid = (int)((n / 4 + 255) / 256);
-  if (grid > num_sms() * 8) grid = num_sms() * 8;
-  sumsq_kernel<<<grid < 1 ? 1 : grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(g), n / 4, out);
-  TVAE_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-// ctrl (device, fp32[4]) = {sum of squared grads (global), max_norm, grad_scale (e.g. 1/world or 1/accum), skip flag}
-__global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
-                                                    float4* __restrict__ v, long long n4, const float* __restrict__ ctrl,
-                                                    float lr, float b1, float b2, float eps, float wd, float bc1, float bc2) {
-  const float gs = ctrl[2];
-  const float norm = sqrtf(ctrl[0]) * gs;
-  const float maxn = ctrl[1];
-  float clip = 1.0f;
-  if (maxn > 0.0f) clip = fminf(1.0f, maxn / (norm + 1e-6f));
-  if (!isfinite(norm) || ctrl[3] != 0.0f) return;   // non-finite step is skipped (train_2.py:329-338)
-  const float s = gs * clip;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 pp = p[i], gg = __ldg(g + i), mm = m[i], vv = v[i];
-    float* P4 = reinterpret_cast<float*>(&pp);
-    float* G4 = reinterpret_cast<float*>(&gg);
-    float* M4 = reinterpret_cast<float*>(&mm);
-    float* V4 = reinterpret_cast<float*>(&vv);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float gr = G4[k] * s;
-      M4[k] = b1 * M4[k] + (1.0f - b1) * gr;
-      V4[k] = b2 * V4[k] + (1.0f - b2) * gr * gr;
-      const float mh = M4[k] / bc1;
-      const float vh = V4[k] / bc2;
-      P4[k] = P4[k] * (1.0f - lr * wd) - lr * mh / (sqrtf(vh) + eps);
-    }
-    p[i] = pp; m[i] = mm; v[i] = vv;
-  }
-}
-
-int adamw_run(float* p, const float* g, float* m, float* v, long long n, const float* ctrl, float lr, float b1, float b2,
-              float eps, float wd, int step, cudaStream_t stream) {
-  TVAE_REQUIRE(n % 4 == 0, "adamw: buffer length must be a multiple of 4");
-  const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
-  int grid = (int)((n / 4 + 255) / 256);
-  if (grid > num_sms() * 8) grid = num_sms() * 8;
-  adamw_kernel<<<grid < 1 ? 1 : grid, 256, 0, stream>>>(reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g),
-                                                        reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n / 4,
-                                                        ctrl, lr, b1, b2, eps, wd, bc1, bc2);
-  TVAE_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
 }  // namespace tvae

@@ -42,6 +42,8 @@ const char* get_last_error();
   } while (0)
 
 int num_sms();
+int persistent_sms();   // num_sms() minus the SMs reserved for a concurrent collective
+void set_reserved_sms(int n);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

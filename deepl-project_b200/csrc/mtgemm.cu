@@ -328,7 +328,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     configured = true;
   }
   const int total = P.num_phases * P.tiles_w * P.tiles_h * P.tiles_b * P.n_tiles;
-  int grid = num_sms();
+  int grid = persistent_sms();
   if (grid <= 0) grid = 148;
   if (total < grid) grid = total;
   mtgemm_kernel<BLOCK_N, EPI><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b, o, r, P);

@@ -536,7 +536,7 @@ static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorM
   }
   const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
   const int total_pairs = P.num_phases * ((m_tiles + 1) / 2) * P.n_tiles;
-  int clusters = num_sms() / 2;
+  int clusters = persistent_sms() / 2;
   if (clusters <= 0) clusters = 74;
   if (total_pairs < clusters) clusters = total_pairs;
   mtgemm2_kernel<BLOCK_N, EPI><<<2 * clusters, kThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b, o, r, ah, P);

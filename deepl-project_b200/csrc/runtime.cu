@@ -31,6 +31,16 @@ int num_sms() {
   return n;
 }
 
+// SMs the persistent (one CTA per SM) kernels may occupy: all of them, minus the ones left to a concurrent NCCL
+// collective while gradient buckets are all-reduced under the backward pass (tvae_set_reserved_sms).
+static int g_reserved_sms = 0;
+void set_reserved_sms(int n) { g_reserved_sms = n < 0 ? 0 : n; }
+int persistent_sms() {
+  const int n = num_sms();
+  const int r = n - g_reserved_sms;
+  return r < 2 ? (n < 2 ? n : 2) : r;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -494,7 +494,7 @@ int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, float* db, cudaStream_t st
     for (int i = 0; i < nt; ++i) items += (long long)(P.taps[i].kblocks * 64 / kt) * P.n_tiles;
   }
   const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
-  int sms = num_sms();
+  int sms = persistent_sms();
   if (sms <= 0) sms = 148;
   // pixel splits ("split-K over pixels"): fill (at most) two full waves of CTAs -- rounding DOWN so the last wave is
   // not nearly empty -- and keep at least ~4 pixel tiles per CTA so the TMEM drain + atomics are amortised

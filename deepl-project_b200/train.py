@@ -61,6 +61,8 @@ def parse_args(argv=None):
     p.add_argument("--log_freq", type=int, default=10)
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--bucket_mb", type=int, default=64)
+    p.add_argument("--grad_comm", type=str, default="fp32", choices=["fp32", "bf16"],
+                   help="dtype of the gradient all-reduce (fp32 = DistributedDataParallel's; bf16 halves the payload)")
     return p.parse_args(argv)
 
 
@@ -123,7 +125,7 @@ def main(argv=None):
                                     gan_weight=0.0)
     tr = Trainer(model, loss_fn, lr=args.learning_rate, betas=(0.9, 0.95), weight_decay=args.weight_decay,
                  grad_clip=args.grad_clip, accumulation_steps=args.accumulation_steps, bucket_bytes=args.bucket_mb << 20,
-                 warmup_steps=args.warmup_steps)
+                 warmup_steps=args.warmup_steps, grad_comm=torch.bfloat16 if args.grad_comm == "bf16" else torch.float32)
     start_epoch = 0
     if args.checkpoint:
         ck = tr.load(args.checkpoint)
@@ -136,26 +138,30 @@ def main(argv=None):
     log = open(os.path.join(args.output_dir, "train_log.jsonl"), "a") if rank == 0 else None
     total = args.num_epochs * args.steps_per_epoch if args.max_steps is None else args.max_steps
     imgs_per_step = args.batch_size * args.accumulation_steps * world
-    t0, step0 = time.perf_counter(), tr.opt.step_count
-    while tr.opt.step_count < total:
-        step = tr.opt.step_count
+    # `attempt` counts optimiser-step attempts on the host; the number of APPLIED updates lives on the device
+    # (FusedAdamW.state[4]: a step with a non-finite gradient norm is skipped there and moves neither the bias correction
+    # nor the warm-up, like the reference's `continue` ahead of optimizer.step() / scheduler.step(), train_2.py:329-338)
+    # and is read back only when logging / saving, so the loop never synchronises with the device.
+    attempt = applied0 = tr.opt.step_count
+    t0 = time.perf_counter()
+    while attempt < total:
         for a in range(args.accumulation_steps):
-            out = tr.train_step(data.batch(step * args.accumulation_steps + a))
-        # the optimiser kernel skips the update on a non-finite gradient norm but the counter still advances, as in
-        # train_2.py:329-338 (`continue` after zero_grad)
-        done = tr.opt.step_count
-        if rank == 0 and (done % args.log_freq == 0 or done == total):
+            out = tr.train_step(data.batch(attempt * args.accumulation_steps + a))
+        attempt += 1
+        if rank == 0 and (attempt % args.log_freq == 0 or attempt == total):
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-            rec = {"step": done, "epoch": done // args.steps_per_epoch, "lr": lr_at(step, args.learning_rate, args.warmup_steps),
-                   "images_per_sec": imgs_per_step * (done - step0) / dt, **{k: float(v) for k, v in out.items()}}
+            applied, skipped = tr.opt.step_count, tr.opt.skipped_steps
+            rec = {"step": attempt, "applied_updates": applied, "skipped_updates": skipped,
+                   "epoch": attempt // args.steps_per_epoch, "lr": lr_at(max(applied - 1, 0), args.learning_rate, args.warmup_steps),
+                   "images_per_sec": imgs_per_step * (attempt - applied0) / dt, **{k: float(v) for k, v in out.items()}}
             print(json.dumps(rec), flush=True)
             log.write(json.dumps(rec) + "\n")
             log.flush()
-        if done % args.save_freq == 0 or done == total:
+        if attempt % args.save_freq == 0 or attempt == total:
             if rank == 0:
-                path = os.path.join(args.output_dir, f"checkpoint_step{done}.pth")
-                tr.save(path, epoch=max(start_epoch, done // args.steps_per_epoch), args=vars(args))
+                path = os.path.join(args.output_dir, f"checkpoint_step{attempt}.pth")
+                tr.save(path, epoch=max(start_epoch, attempt // args.steps_per_epoch), args=vars(args))
                 print(f"Checkpoint saved to {path}", flush=True)
             if world > 1:
                 dist.barrier()

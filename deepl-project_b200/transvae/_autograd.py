@@ -99,6 +99,13 @@ def _w_ungrad(gp: Tensor, w: Tensor) -> Tensor:
     return gp.view(w.shape[0], 3, 3, w.shape[1]).permute(0, 3, 1, 2)
 
 
+def _fire_hooks(p: Tensor) -> None:
+    """Run the post-accumulate-grad hooks of ``p`` by hand (the bucket all-reduce trigger of trainer.GradBuckets): its
+    gradient was accumulated into the flat-buffer slot by a kernel, autograd received ``None`` for it."""
+    for hook in list((getattr(p, "_post_accumulate_grad_hooks", None) or {}).values()):
+        hook(p)
+
+
 def _wgrad_b(plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[Tensor] = None, w: Optional[Tensor] = None,
              b: Optional[Tensor] = None):
     """(dW, dbias) of a single-phase plan in one launch: the bias gradient (column sums of dZ) rides on the wgrad
@@ -114,18 +121,58 @@ def _wgrad_b(plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[Tensor] = 
     dw, db = ops.mtgemm_wgrad(plan, a0, dz, n_total, a1=a1, bias=True, dw_out=wslot, db_out=bslot)
     for p, slot in ((w, wslot), (b, bslot)):
         if slot is not None:
-            for hook in list((getattr(p, "_post_accumulate_grad_hooks", None) or {}).values()):
-                hook(p)
+            _fire_hooks(p)
     return (None if wslot is not None else dw), (None if bslot is not None else db[0])
 
 
 def _direct_slot(p: Tensor, numel: int, matrix: bool) -> Optional[Tensor]:
-    g = p.grad if _DIRECT and getattr(p, "_tvae_direct_grad", False) and p.is_leaf else None
+    ok = _DIRECT and getattr(p, "_tvae_direct_grad", False) and p.is_leaf and p.requires_grad
+    g = p.grad if ok else None
     if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.numel() != numel or p.numel() != numel:
         return None
     if matrix and not (p.dim() == 2 or (p.dim() == 4 and p.shape[2] == 1 and p.shape[3] == 1)):
         return None
     return g
+
+
+class GradSink:
+    """Gradient accumulation of the SMALL parameters (norm weights / biases, convolution biases of multi-phase plans,
+    3x3 weights after ``tvae_wgrad_unpack``) without autograd's one-tiny-kernel-per-parameter AccumulateGrad: a backward
+    Function hands (parameter, gradient) pairs to ``add`` -- which answers None, so autograd has nothing to accumulate --
+    and ``flush`` adds all of them into their flat-buffer slots with ONE ``tvae_multi_tensor_add`` launch per 96 tensors
+    and then runs the parameters' post-accumulate hooks (bucket all-reduce triggers).  Parameters that are not owned by
+    ``trainer.GradBuckets`` pass through untouched."""
+    BIG = 1 << 18          # larger tensors take their own (bandwidth-efficient) add
+
+    def __init__(self):
+        self._dst, self._src, self._params = [], [], []
+
+    def add(self, p: Optional[Tensor], g: Optional[Tensor]) -> Optional[Tensor]:
+        if p is None or g is None:
+            return g
+        slot = _direct_slot(p, p.numel(), False)
+        if slot is None or g.numel() != p.numel() or not g.is_cuda:
+            return g
+        if g.numel() > self.BIG:
+            slot.view(-1).add_(g.reshape(-1))
+            _fire_hooks(p)
+            return None
+        self._dst.append(slot.view(-1))
+        self._src.append(g if g.dim() == 1 else g.reshape(-1))
+        self._params.append(p)
+        return None
+
+    def flush(self) -> None:
+        if not self._dst:
+            return
+        dst, src, params = self._dst, self._src, self._params
+        self._dst, self._src, self._params = [], [], []
+        ops.multi_tensor_add(dst, src)
+        for p in params:
+            _fire_hooks(p)
+
+
+GRAD_SINK = GradSink()
 
 
 def _flat(x: Tensor) -> Tensor:
@@ -164,7 +211,11 @@ class ResBlockFn(Fn):
         dw1, dc1b = _wgrad_b(T.plan_conv3x3(C), h0, dh1, C, b=c1b)
         dh0 = ops.mtgemm(dplan, dh1, w1d, out_shape=(B, H, W, C))
         dx, dg1, db1 = ops.groupnorm_bwd(x, dh0, s1, g1, b1, add=dout)
-        return dx, None, dg1, db1, _w_ungrad(dw1, w1), dc1b, dg2, db2, _w_ungrad(dw2, w2), dc2b
+        S = GRAD_SINK
+        out = (dx, None, S.add(g1, dg1), S.add(b1, db1), S.add(w1, _w_ungrad(dw1, w1)), S.add(c1b, dc1b), S.add(g2, dg2),
+               S.add(b2, db2), S.add(w2, _w_ungrad(dw2, w2)), S.add(c2b, dc2b))
+        S.flush()
+        return out
 
 
 class DownsampleFn(Fn):
@@ -266,6 +317,8 @@ class AttnFn(Fn):
         dwq, dbq = _wgrad_b(T.plan_linear(C), _flat(xh), dq, 3 * C)
         dxh = ops.mtgemm(T.plan_linear(3 * C), dq, wqkv_d, out_shape=(1, 1, B * S, C))
         dx, dw1 = ops.token_norm_bwd(x, w1, dxh.view(B, H, W, C), dout, 1)
+        dw1 = GRAD_SINK.add(w1, dw1)
+        GRAD_SINK.flush()
         return dx, dw1, dwq, dbq, dwp, dbp, None, None
 
 
@@ -321,7 +374,11 @@ class FfnFn(Fn):
         dx, dw2n = ops.token_norm_bwd(x, w2n, dxn.view(B, H, W, C), dout, 0)
         def _as(g, w):                      # 1x1 conv weights arrive as [out, in, 1, 1]
             return g if g is None else g.view_as(w)
-        return dx, dw2n, dwin, dbin, _as(dwc0, wc0), dbc0, _w_ungrad(dwc2, wc2), dbc2, _as(dwc4, wc4), dbc4, dwout, dbout
+        S = GRAD_SINK
+        out = (dx, S.add(w2n, dw2n), dwin, dbin, _as(dwc0, wc0), dbc0, S.add(wc2, _w_ungrad(dwc2, wc2)), dbc2, _as(dwc4, wc4),
+               dbc4, dwout, dbout)
+        S.flush()
+        return out
 
 
 class ConvInFn(Fn):
@@ -397,6 +454,8 @@ class GroupNormSilu(Fn):
     def backward(ctx, dh):
         x, s, g, b = ctx.saved_tensors
         dx, dg, db = ops.groupnorm_bwd(x, dh.contiguous(), s, g, b, silu=ctx.silu)
+        dg, db = GRAD_SINK.add(g, dg), GRAD_SINK.add(b, db)
+        GRAD_SINK.flush()
         return dx, dg, db, None, None
 
 

@@ -52,6 +52,7 @@ _PROTOS = {
     "tvae_last_error": (C.c_char_p, []),
     "tvae_device_ok": (C.c_int, []),
     "tvae_num_sms": (C.c_int, []),
+    "tvae_set_reserved_sms": (C.c_int, [C.c_int32]),
     "tvae_mtgemm": (C.c_int, [C.POINTER(MtGemmDesc), C.c_void_p]),
     "tvae_attn_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "tvae_im2col_in": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
@@ -94,11 +95,14 @@ _PROTOS = {
                                   C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "tvae_weight_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "tvae_wgrad_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
-    "tvae_sumsq": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "tvae_grad_sumsq": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "tvae_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                  C.c_void_p, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                  C.c_float, C.c_void_p]),
+    "tvae_cast_f32_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tvae_multi_tensor_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "tvae_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_void_p]),
-    "tvae_adamw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,
-                             C.c_float, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -123,7 +127,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.tvae_abi_version() != 3:
+    if lib.tvae_abi_version() != 4:
         raise RuntimeError("libtransvae_sm100.so ABI version mismatch")
     _lib = lib
     return lib

@@ -1,7 +1,8 @@
 """Cache of kernel-layout (packed, bf16) weights derived from the fp32 reference-layout parameters.
 
 Under ``torch.no_grad()`` a packed tensor is rebuilt only when one of its source parameters changed (tensor
-``_version`` / storage pointer), so inference packs once.  With autograd enabled the packing ops (plain torch
+``_version`` / storage pointer, or ``ops.WEIGHT_EPOCH`` -- the fused optimizer rewrites the flat parameter buffer from
+a raw-pointer kernel, which no tensor version counter sees), so inference packs once.  With autograd enabled the packing ops (plain torch
 elementwise / permute ops on *weights* -- host-side plumbing, not activations) are re-run every forward so that
 gradients flow back to the reference-layout parameters.
 """
@@ -21,7 +22,8 @@ class PackCache:
     def get(self, key: str, srcs: Sequence[Tensor], fn: Callable[[], object]):
         if torch.is_grad_enabled() and any(s.requires_grad for s in srcs):
             return fn()
-        sig = tuple((s.data_ptr(), s._version, s.device) for s in srcs)
+        from . import ops
+        sig = (ops.WEIGHT_EPOCH,) + tuple((s.data_ptr(), s._version, s.device) for s in srcs)
         hit = self._store.get(key)
         if hit is not None and hit[0] == sig:
             return hit[1]

@@ -29,6 +29,20 @@ PROFILE_HBM = None
 WEIGHT_EPOCH = 0
 
 
+# SMs left to NCCL while gradient buckets are all-reduced under the backward pass (TVAE_COMM_RESERVED_SMS, default 0:
+# full-width grids; see trainer._set_comm_active)
+import os as _os
+COMM_RESERVED_SMS = int(_os.environ.get("TVAE_COMM_RESERVED_SMS", "0"))
+_comm_active = False
+
+
+def set_comm_active(on: bool) -> None:
+    global _comm_active
+    if COMM_RESERVED_SMS > 0 and on != _comm_active:
+        _lib.load().tvae_set_reserved_sms(COMM_RESERVED_SMS if on else 0)
+    _comm_active = on
+
+
 class _hbm:
     """with _hbm(name, algorithmic_bytes): launch(...) -- CUDA-event timing of one bandwidth-bound launch when
     ``PROFILE_HBM`` is a list (bench.py's HBM roofline table); free otherwise."""
@@ -440,7 +454,7 @@ def groupnorm_bwd(x: Tensor, dh: Tensor, sums: Tensor, gamma: Tensor, beta: Tens
                                                   1 if silu else 0, _stream()), "tvae_groupnorm_bwd")
     _count(3)
     red = part.sum(0)          # [C, 2]: tiny (B x C) reduction of the per-image partials
-    return dx, red[:, 1].contiguous(), red[:, 0].contiguous()
+    return dx, red[:, 1], red[:, 0]          # strided views (consumers: GradSink / autograd accept them)
 
 
 def token_norm_fwd(x: Tensor, w: Tensor, mode: int) -> Tensor:
@@ -560,21 +574,66 @@ def wgrad_unpack(g: Tensor, shape: Sequence[int]) -> Tensor:
     return out
 
 
-def sumsq(g: Tensor, out: Tensor) -> None:
-    """out[0] += sum(g^2) for a flat fp32 buffer (length % 4 == 0)."""
-    _need_cuda(g, out)
-    with _hbm("sumsq (grad norm)", g.numel() * 4):
-        _lib.check(_lib.load().tvae_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream()), "tvae_sumsq")
+SUMSQ_BLOCKS = 1024          # TVAE_SUMSQ_BLOCKS
+
+
+def grad_sumsq(g: Tensor, partials: Tensor) -> None:
+    """partials fp64 [SUMSQ_BLOCKS] = fixed-order per-block sums of g^2 (flat fp32 or bf16 buffer, length % 8 == 0)."""
+    _need_cuda(g, partials)
+    assert partials.dtype == torch.float64 and partials.numel() == SUMSQ_BLOCKS and g.dtype in (torch.float32, BF16)
+    with _hbm("grad_sumsq (grad norm)", g.numel() * g.element_size()):
+        _lib.check(_lib.load().tvae_grad_sumsq(g.data_ptr(), int(g.dtype == BF16), g.numel(), partials.data_ptr(), _stream()),
+                   "tvae_grad_sumsq")
     _count()
 
 
-def adamw(p: Tensor, g: Tensor, m: Tensor, v: Tensor, ctrl: Tensor, lr: float, betas=(0.9, 0.95), eps: float = 1e-8,
-          weight_decay: float = 0.0, step: int = 1) -> None:
-    _need_cuda(p, g, m, v, ctrl)
-    with _hbm("adamw", p.numel() * 28):
-        _lib.check(_lib.load().tvae_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), ctrl.data_ptr(),
-                                          lr, betas[0], betas[1], eps, weight_decay, step, _stream()), "tvae_adamw")
+def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, partials: Tensor, state: Tensor, lr_base: float,
+               warmup_steps: int = 0, betas=(0.9, 0.95), eps: float = 1e-8, weight_decay: float = 0.0,
+               max_norm: float = 1.0, grad_scale: float = 1.0) -> None:
+    """Fused clip + AdamW + warm-up + non-finite skip over flat buffers; every decision is taken on the device from
+    ``partials`` (``grad_sumsq``) and ``state`` (fp32 [8], see include/transvae_sm100.h)."""
+    _need_cuda(p, g, m, v, partials, state)
+    assert state.dtype == torch.float32 and state.numel() == 8 and g.numel() == p.numel()
+    with _hbm("adamw", p.numel() * (24 + g.element_size())):
+        _lib.check(_lib.load().tvae_adamw_step(p.data_ptr(), g.data_ptr(), int(g.dtype == BF16), m.data_ptr(), v.data_ptr(),
+                                               p.numel(), partials.data_ptr(), state.data_ptr(), float(lr_base),
+                                               int(warmup_steps), float(betas[0]), float(betas[1]), float(eps),
+                                               float(weight_decay), float(max_norm or 0.0), float(grad_scale), _stream()),
+                   "tvae_adamw_step")
+    _count(2)
+
+
+def cast_f32_bf16(src: Tensor, dst: Tensor) -> None:
+    _need_cuda(src, dst)
+    assert src.dtype == torch.float32 and dst.dtype == BF16 and src.numel() == dst.numel()
+    with _hbm("grad cast fp32->bf16", src.numel() * 6):
+        _lib.check(_lib.load().tvae_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "tvae_cast_f32_bf16")
     _count()
+
+
+def multi_tensor_add(dsts: Sequence[Tensor], srcs: Sequence[Tensor]) -> None:
+    """dst[i] += src[i] for many small fp32 tensors in one launch per 96 tensors (``tvae_multi_tensor_add``).  A source
+    may be a 1-D strided view (e.g. one column of a [C, 2] matrix)."""
+    n = len(dsts)
+    if n == 0:
+        return
+    _need_cuda(*dsts, *srcs)
+    keep, strides = [], []
+    for d, s in zip(dsts, srcs):
+        assert d.dtype == torch.float32 and d.is_contiguous() and d.numel() == s.numel(), (d.shape, s.shape, d.dtype)
+        if s.dtype == torch.float32 and s.dim() == 1 and s.stride(0) >= 1:
+            strides.append(s.stride(0))
+        else:
+            if s.dtype != torch.float32 or not s.is_contiguous():
+                s = s.float().contiguous()
+            strides.append(1)
+        keep.append(s)
+    PtrArr, IntArr = C.c_void_p * n, C.c_int32 * n
+    da, sa = PtrArr(*[d.data_ptr() for d in dsts]), PtrArr(*[s.data_ptr() for s in keep])
+    na, st = IntArr(*[d.numel() for d in dsts]), IntArr(*strides)
+    with _hbm("multi_tensor_add", sum(d.numel() for d in dsts) * 12):
+        _lib.check(_lib.load().tvae_multi_tensor_add(da, sa, na, st, n, _stream()), "tvae_multi_tensor_add")
+    _count((n + 95) // 96)
 
 
 METRIC_MODES = {None: 0, "none": 0, "identity": 0, "clamp": 1, "sigmoid": 2}

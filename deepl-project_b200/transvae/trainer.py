@@ -23,10 +23,15 @@ Tensor = torch.Tensor
 
 class GradBuckets:
     """Flat fp32 parameter / gradient storage with bucketed, overlapped all-reduce.  Pure torch (works on CPU with
-    gloo, which is how the host logic is tested without GPUs)."""
+    gloo, which is how the host logic is tested without GPUs).
+
+    ``grad_comm``: dtype of the all-reduce payload.  ``torch.float32`` (default) is DistributedDataParallel's behaviour
+    (train.py:672-674).  ``torch.bfloat16`` halves the NVLink payload: a bucket is cast into a bf16 mirror
+    (``tvae_cast_f32_bf16``) the moment it is complete, the mirror is all-reduced and the optimizer reads it -- the
+    rounding of every gradient to bf16 (2^-9 relative) is a stated deviation from the reference."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20,
-                 process_group: Optional[dist.ProcessGroup] = None):
+                 process_group: Optional[dist.ProcessGroup] = None, grad_comm: torch.dtype = torch.float32):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -41,10 +46,15 @@ class GradBuckets:
         offs, total = [], 0
         for p in order:
             offs.append(total)
-            total += (p.numel() + 3) // 4 * 4            # keep every tensor 16-byte aligned
+            total += (p.numel() + 7) // 8 * 8            # every tensor 32-byte aligned (16 bytes in the bf16 mirror)
         self.numel = total
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        if grad_comm not in (torch.float32, torch.bfloat16):
+            raise ValueError("grad_comm must be torch.float32 or torch.bfloat16")
+        self.grad_comm = grad_comm
+        # bf16 mirror of the gradients (communication + optimizer input) -- only with more than one rank
+        self.comm_g = torch.zeros(total, dtype=torch.bfloat16, device=dev) if (grad_comm == torch.bfloat16 and self.world > 1) else None
         self._slices = {}
         with torch.no_grad():
             for p, o in zip(order, offs):
@@ -52,16 +62,19 @@ class GradBuckets:
                 self.flat_p[o:o + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat_p[o:o + n].view(p.shape)
                 p.grad = self.flat_g[o:o + n].view(p.shape)
-                # matrix-shaped weights: the wgrad kernel may accumulate straight into this slot (_autograd._wgrad_b)
+                # the wgrad kernels may accumulate straight into this slot (_autograd._wgrad_b / GradSink)
                 p._tvae_direct_grad = True
                 self._slices[p] = (o, n)
+            if self.world > 1:
+                # identical replicas on every rank (DistributedDataParallel broadcasts rank 0's parameters too)
+                dist.broadcast(self.flat_p, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
         # contiguous buckets
         self.buckets: List[Tuple[int, int]] = []
         self._bucket_of = {}
         self._bucket_count: List[int] = []
         start, cnt, limit = 0, 0, max(1, bucket_bytes // 4)
         for p, o in zip(order, offs):
-            n = (p.numel() + 3) // 4 * 4
+            n = (p.numel() + 7) // 8 * 8
             if cnt and (o + n - start) > limit:
                 self.buckets.append((start, o))
                 self._bucket_count.append(cnt)
@@ -71,12 +84,30 @@ class GradBuckets:
         self.buckets.append((start, total))
         self._bucket_count.append(cnt)
         self._pending = [0] * len(self.buckets)
+        self._reduced = [False] * len(self.buckets)
         self._handles = []
         self.sync_grads = True          # False during gradient-accumulation micro-steps
         for p in self.params:
             p.register_post_accumulate_grad_hook(self._hook)
 
     # ------------------------------------------------------------------
+    def grads(self) -> Tensor:
+        """The flat gradient buffer the optimizer reads: the all-reduced bf16 mirror, or the fp32 buffer."""
+        return self.comm_g if self.comm_g is not None else self.flat_g
+
+    def _reduce_bucket(self, b: int) -> None:
+        s, e = self.buckets[b]
+        self._reduced[b] = True
+        if self.world <= 1:
+            return
+        if self.comm_g is not None:
+            from . import ops
+            ops.cast_f32_bf16(self.flat_g[s:e], self.comm_g[s:e])
+            buf = self.comm_g[s:e]
+        else:
+            buf = self.flat_g[s:e]
+        self._handles.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
     def _hook(self, p: torch.nn.Parameter) -> None:
         o, n = self._slices[p]
         if p.grad.data_ptr() != self.flat_g.data_ptr() + 4 * o:
@@ -88,44 +119,76 @@ class GradBuckets:
         self._pending[b] += 1
         if self._pending[b] == self._bucket_count[b]:
             self._pending[b] = 0
-            if self.sync_grads and self.world > 1:
-                s, e = self.buckets[b]
-                self._handles.append(dist.all_reduce(self.flat_g[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+            if self.sync_grads:
+                self._reduce_bucket(b)
 
     def wait(self) -> None:
+        """End of backward.  Buckets that never completed -- a parameter without a gradient this step (unused branch,
+        frozen after construction) -- are reduced now, so ranks cannot diverge silently."""
+        if self.sync_grads:
+            for b in range(len(self.buckets)):
+                if not self._reduced[b]:
+                    self._reduce_bucket(b)
         for h in self._handles:
             h.wait()
         self._handles.clear()
+        self._pending = [0] * len(self.buckets)
+        self._reduced = [False] * len(self.buckets)
 
     def zero_grad(self) -> None:
         self.flat_g.zero_()
         self._pending = [0] * len(self.buckets)
+        self._reduced = [False] * len(self.buckets)
 
 
 class FusedAdamW:
-    """AdamW over the flat buffers of ``GradBuckets`` with fused clipping / scaling / non-finite skip."""
+    """AdamW over the flat buffers of ``GradBuckets`` with fused clipping / scaling / warm-up / non-finite skip.  The
+    update counter lives on the device (``state[4]``): a skipped step advances neither the bias correction nor the
+    warm-up, like the reference's ``continue`` ahead of optimizer.step() / scheduler.step() (train_2.py:329-338)."""
 
     def __init__(self, buckets: GradBuckets, lr: float = 1e-4, betas: Tuple[float, float] = (0.9, 0.95), eps: float = 1e-8,
-                 weight_decay: float = 0.0, max_grad_norm: float = 1.0):
+                 weight_decay: float = 0.0, max_grad_norm: float = 1.0, warmup_steps: int = 0):
         self.b = buckets
         self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.warmup_steps = warmup_steps
         self.m = torch.zeros_like(buckets.flat_p)
         self.v = torch.zeros_like(buckets.flat_p)
-        self.ctrl = torch.zeros(4, dtype=torch.float32, device=buckets.flat_p.device)
-        self.step_count = 0
+        dev = buckets.flat_p.device
+        self.state = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.partials = torch.zeros(1024, dtype=torch.float64, device=dev)
 
-    def step(self, grad_scale: float = 1.0, lr: Optional[float] = None) -> Tensor:
-        """Applies one update; returns the (device) control block whose [0] is the sum of squared raw gradients."""
+    # number of APPLIED updates; reading it synchronises with the device (logging / checkpoints only)
+    @property
+    def step_count(self) -> int:
+        return int(self.state[4].item())
+
+    @step_count.setter
+    def step_count(self, n: int) -> None:
+        self.state[4] = float(n)
+
+    @property
+    def skipped_steps(self) -> int:
+        return int(self.state[5].item())
+
+    @property
+    def ctrl(self) -> Tensor:
+        """[0] = sum of squared (unscaled) gradients of the last step, [1] = its clip factor (device tensor)."""
+        return self.state
+
+    def current_lr(self) -> float:
+        """Learning rate of the next update (LambdaLR of train_2.py:266-274: update k uses lr * min(1, k / warmup))."""
+        k = self.step_count
+        return self.lr * min(1.0, k / self.warmup_steps) if self.warmup_steps > 0 else self.lr
+
+    def step(self, grad_scale: float = 1.0) -> Tensor:
+        """One update attempt; returns the device state block.  Nothing is synchronised with the host."""
         from . import ops
-        self.step_count += 1
-        self.ctrl.zero_()
-        ops.sumsq(self.b.flat_g, self.ctrl)
-        self.ctrl[1] = self.max_norm if self.max_norm else 0.0
-        self.ctrl[2] = grad_scale
-        ops.adamw(self.b.flat_p, self.b.flat_g, self.m, self.v, self.ctrl, self.lr if lr is None else lr, self.betas,
-                  self.eps, self.wd, self.step_count)
+        g = self.b.grads()
+        ops.grad_sumsq(g, self.partials)
+        ops.adamw_step(self.b.flat_p, g, self.m, self.v, self.partials, self.state, self.lr, self.warmup_steps, self.betas,
+                       self.eps, self.wd, self.max_norm, grad_scale)
         ops.WEIGHT_EPOCH += 1           # the kernel rewrote flat_p: packed operands cached for this step are stale
-        return self.ctrl
+        return self.state
 
     # ---- checkpoint interchange --------------------------------------------------------------------------------
     # The reference saves ``torch.optim.AdamW.state_dict()`` (train.py:753-769, train_2.py:245-260).  The same schema
@@ -134,13 +197,16 @@ class FusedAdamW:
     # trainer and this one in either direction.
     def state_dict(self) -> dict:
         state = {}
+        steps = self.step_count
         for i, p in enumerate(self.b.params):
             o, n = self.b._slices[p]
-            state[i] = {"step": torch.tensor(float(self.step_count)),
+            state[i] = {"step": torch.tensor(float(steps)),
                         "exp_avg": self.m[o:o + n].view(p.shape).clone(),
                         "exp_avg_sq": self.v[o:o + n].view(p.shape).clone()}
-        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd, "amsgrad": False,
-                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+        # what torch.optim.AdamW under a LambdaLR holds: `initial_lr` = the base rate, `lr` = the scheduled rate
+        group = {"lr": self.current_lr(), "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "decoupled_weight_decay": True, "initial_lr": self.lr,
                  "params": list(range(len(self.b.params)))}
         return {"state": state, "param_groups": [group]}
 
@@ -178,47 +244,100 @@ class FusedAdamW:
         self.wd = float(g0.get("weight_decay", self.wd))
 
 
+def lambda_lr_state(base_lr: float, warmup_steps: int, steps: int) -> dict:
+    """``torch.optim.lr_scheduler.LambdaLR.state_dict()`` of the reference's warm-up schedule (train_2.py:266-274) after
+    ``steps`` scheduler steps -- produced by a real LambdaLR on a one-element CPU optimizer, so that the reference's
+    ``scheduler.load_state_dict(ckpt["scheduler_state_dict"])`` (train_2.py:489-490) accepts it on this torch version."""
+    opt = torch.optim.SGD([torch.zeros(1, requires_grad=True)], lr=base_lr)
+    fn = (lambda k: min(1.0, k / warmup_steps)) if warmup_steps > 0 else (lambda k: 1.0)
+    sch = torch.optim.lr_scheduler.LambdaLR(opt, fn)
+    sch.last_epoch = int(steps)
+    sch._step_count = int(steps) + 1
+    sch._last_lr = [base_lr * fn(int(steps))]
+    return sch.state_dict()
+
+
 class Trainer:
     """model(images) -> TransVAELoss -> backward (overlapped all-reduce) -> clip -> AdamW, one call per micro-batch."""
 
     def __init__(self, model: torch.nn.Module, loss_fn: torch.nn.Module, lr: float = 1e-4,
                  betas: Tuple[float, float] = (0.9, 0.95), weight_decay: float = 0.0, grad_clip: float = 1.0,
                  accumulation_steps: int = 1, bucket_bytes: int = 64 << 20, warmup_steps: int = 0,
-                 process_group: Optional[dist.ProcessGroup] = None):
+                 process_group: Optional[dist.ProcessGroup] = None, grad_comm: torch.dtype = torch.float32):
         self.model, self.loss_fn = model, loss_fn
-        self.buckets = GradBuckets(model.parameters(), bucket_bytes, process_group)
-        self.opt = FusedAdamW(self.buckets, lr, betas, 1e-8, weight_decay, grad_clip)
+        self.buckets = GradBuckets(model.parameters(), bucket_bytes, process_group, grad_comm)
+        self.opt = FusedAdamW(self.buckets, lr, betas, 1e-8, weight_decay, grad_clip, warmup_steps)
         self.accum = max(1, accumulation_steps)
         self.warmup_steps = warmup_steps
         self._micro = 0
         self.world = self.buckets.world
-
-    def _lr(self) -> float:
-        # linear warm-up then constant (train_2.py:266-274: LambdaLR with step / warmup, so update k uses k / warmup)
-        if self.warmup_steps > 0:
-            return self.opt.lr * min(1.0, self.opt.step_count / self.warmup_steps)
-        return self.opt.lr
+        self._h2d: Optional[torch.cuda.Stream] = None
+        self._staged = None             # (host tensor, device copy, ready event) of the prefetched micro-batch
+        self._loss_host: Optional[Tensor] = None
 
     def train_step(self, images: Tensor, eps: Optional[Tensor] = None) -> dict:
         """One micro-batch.  Returns the loss dict (device tensors; nothing is synchronised with the host)."""
         self.model.train()
         last = (self._micro + 1) % self.accum == 0
         self.buckets.sync_grads = last
-        recon, mu, logvar = self.model(images, eps=eps)
-        losses = self.loss_fn(recon, images, mu, logvar)
-        losses["total"].backward()
+        _set_comm_active(last and self.world > 1)
+        try:
+            recon, mu, logvar = self.model(images, eps=eps)
+            losses = self.loss_fn(recon, images, mu, logvar)
+            losses["total"].backward()
+            from . import _autograd
+            _autograd.GRAD_SINK.flush()
+        finally:
+            _set_comm_active(False)
         self._micro += 1
         if last:
             self.buckets.wait()
-            self.opt.step(grad_scale=1.0 / (self.world * self.accum), lr=self._lr())
+            self.opt.step(grad_scale=1.0 / (self.world * self.accum))
             self.buckets.zero_grad()
         return {k: v.detach() for k, v in losses.items()}
 
+    # ---- host-to-host step: the reference's `images.to(device, non_blocking=True)` ... `loss.item()` loop ---------
+    def _stage(self, x_host: Tensor) -> None:
+        if not x_host.is_pinned():
+            raise ValueError("host batches must be pinned (torch.Tensor.pin_memory) for asynchronous copies")
+        dev = self.buckets.flat_p.device
+        if self._h2d is None:
+            self._h2d = torch.cuda.Stream(dev)
+        with torch.cuda.stream(self._h2d):
+            xd = x_host.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._h2d)
+        self._staged = (x_host, xd, ev)
+
+    def train_step_host(self, images_host: Tensor, next_images_host: Optional[Tensor] = None,
+                        eps: Optional[Tensor] = None) -> Tensor:
+        """``train_step`` on a PINNED host micro-batch (train.py:586 ``images.to(device, non_blocking=True)``): the upload
+        of ``next_images_host`` runs on a copy stream under this step's kernels, and the loss terms come back into a
+        pinned host tensor [6] = (l1, lpips, kl, vf, gan, total) (train.py:623 ``loss.item()``) with an asynchronous
+        copy -- read it after ``torch.cuda.current_stream().synchronize()``."""
+        dev = self.buckets.flat_p.device
+        cur = torch.cuda.current_stream(dev)
+        if self._staged is None or self._staged[0] is not images_host:
+            self._stage(images_host)
+        _, xd, ready = self._staged
+        self._staged = None
+        if next_images_host is not None:
+            self._stage(next_images_host)
+        cur.wait_event(ready)
+        out = self.train_step(xd, eps=eps)
+        xd.record_stream(cur)
+        if self._loss_host is None:
+            self._loss_host = torch.empty(6, dtype=torch.float32).pin_memory()
+        vec = torch.stack([out[k].float().reshape(()) for k in ("l1", "lpips", "kl", "vf", "gan", "total")])
+        self._loss_host.copy_(vec, non_blocking=True)
+        return self._loss_host
+
     # checkpoint schema of the reference (train.py:753-769, train_2.py:245-260)
     def state_dict(self, epoch: int = 0, args: Optional[dict] = None) -> dict:
-        return {"epoch": epoch, "global_step": self.opt.step_count, "model_state_dict": self.model.state_dict(),
+        steps = self.opt.step_count
+        return {"epoch": epoch, "global_step": steps, "model_state_dict": self.model.state_dict(),
                 "optimizer_state_dict": self.opt.state_dict(),
-                "scheduler_state_dict": {"last_epoch": self.opt.step_count, "warmup_steps": self.warmup_steps},
+                "scheduler_state_dict": lambda_lr_state(self.opt.lr, self.warmup_steps, steps),
                 "args": dict(args or {})}
 
     def load_state_dict(self, sd: dict) -> None:
@@ -230,6 +349,9 @@ class Trainer:
         self.opt.load_state_dict(sd["optimizer_state_dict"])
         if "global_step" in sd and not sd["optimizer_state_dict"].get("state"):
             self.opt.step_count = int(sd["global_step"])
+        sch = sd.get("scheduler_state_dict")
+        if isinstance(sch, dict) and sch.get("base_lrs"):
+            self.opt.lr = float(sch["base_lrs"][0])       # the scheduled `lr` of the param group is not the base rate
 
     def save(self, path: str, epoch: int = 0, args: Optional[dict] = None) -> None:
         torch.save(self.state_dict(epoch, args), path)
@@ -238,3 +360,11 @@ class Trainer:
         sd = torch.load(path, map_location=self.buckets.flat_p.device, weights_only=False)
         self.load_state_dict(sd)
         return sd
+
+
+def _set_comm_active(on: bool) -> None:
+    """While gradient buckets are being all-reduced under the backward pass, the persistent GEMM kernels leave a few
+    SMs to NCCL's channels (``tvae_set_reserved_sms``): a one-CTA-per-SM kernel whose grid exceeds the free SMs runs a
+    nearly empty second wave -- up to 2x its time."""
+    from . import ops
+    ops.set_comm_active(on)

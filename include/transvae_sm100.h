@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TVAE_ABI_VERSION 3
+#define TVAE_ABI_VERSION 4
 #define TVAE_MAX_TAPS 16
 #define TVAE_MAX_PHASES 4
 
@@ -31,6 +31,10 @@ const char* tvae_last_error(void);
 /* 1 when the current CUDA device is compute capability 10.x, 0 otherwise (or no device). */
 int tvae_device_ok(void);
 int tvae_num_sms(void);
+/* Leave `n` SMs free in the grids of the persistent (one CTA per SM) GEMM / weight-gradient kernels, e.g. for the
+ * channels of an NCCL all-reduce running under the backward pass (DistributedDataParallel's overlap, train.py:672-674);
+ * 0 restores full-width grids.  Returns the number of SMs the persistent kernels will use. */
+int tvae_set_reserved_sms(int32_t n);
 
 /* ---- pixel views ---------------------------------------------------------------------------
  * A view of a contiguous NHWC bf16 tensor [B, H, W, C].
@@ -214,13 +218,32 @@ int tvae_latent_bwd(const float* mu, const float* logvar, const float* eps, cons
 int tvae_weight_pack(const float* w, void* fwd_bf16, void* dgrad_bf16, int32_t A, int32_t B, int32_t T, void* stream);
 int tvae_wgrad_unpack(const float* g_packed, float* g_ref, int32_t A, int32_t B, int32_t T, void* stream);
 
-/* ---- optimiser (train.py:608-620: clip_grad_norm_ + fused AdamW) ----------------------------------
- * tvae_sumsq: out[0] += sum g^2 over a flat fp32 buffer (n % 4 == 0).
- * tvae_adamw: one fused step over flat fp32 p / g / m / v.  ctrl (device fp32[4]) = {global sum of squared grads,
- * max_norm (<= 0: no clipping), gradient pre-scale, skip flag}; a non-finite norm skips the step (train_2.py:329-338). */
-int tvae_sumsq(const float* g, int64_t n, float* out, void* stream);
-int tvae_adamw(float* p, const float* g, float* m, float* v, int64_t n, const float* ctrl, float lr, float beta1,
-               float beta2, float eps, float weight_decay, int32_t step, void* stream);
+/* ---- optimiser (train.py:608-620, train_2.py:266-274, 329-366: clip_grad_norm_ + fused AdamW + LambdaLR warm-up +
+ *      skip of non-finite steps) -- every decision of the step is taken on the device, no host synchronisation ----
+ * tvae_grad_sumsq: partials fp64 [TVAE_SUMSQ_BLOCKS] = fixed-order per-block partial sums of g^2 over a flat gradient
+ *   buffer (fp32, or bf16 when g_bf16 != 0; n % 8 == 0).  No atomics: the total (re-added in a fixed order by the
+ *   consumers) is bit-reproducible and identical on every rank of a data-parallel job.
+ * tvae_adamw_step: one fused update over flat p / m / v (fp32) and g (fp32 or bf16).
+ *   state (device fp32[8]) = {0: sum of squared gradients of this step (out), 1: clip factor (out), 2: external skip
+ *   flag (in), 3: -, 4: updates APPLIED so far (in/out), 5: updates skipped (in/out), 6: learning rate used (out), 7: -}.
+ *   The update index k = state[4] drives the bias correction 1 - beta^(k+1) and the warm-up lr_base * min(1, k /
+ *   warmup_steps) (warmup_steps <= 0: constant); gradients are pre-scaled by grad_scale (1 / (world * accumulation)) and
+ *   clipped to max_norm (<= 0: off) with clip_grad_norm_'s formula.  A non-finite norm (or state[2] != 0) skips the
+ *   update and advances state[5] only -- like the reference's `continue` before optimizer.step() / scheduler.step(). */
+#define TVAE_SUMSQ_BLOCKS 1024
+int tvae_grad_sumsq(const void* g, int32_t g_bf16, int64_t n, double* partials, void* stream);
+int tvae_adamw_step(float* p, const void* g, int32_t g_bf16, float* m, float* v, int64_t n, const double* partials,
+                    float* state, float lr_base, int32_t warmup_steps, float beta1, float beta2, float eps,
+                    float weight_decay, float max_norm, float grad_scale, void* stream);
+/* fp32 -> bf16 cast of a gradient bucket before a bf16 all-reduce (optional deviation from DistributedDataParallel's
+ * fp32 buckets, train.py:672-674; halves the NVLink payload).  n % 8 == 0. */
+int tvae_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
+/* Multi-tensor accumulate: dst[i][j] += src[i][j * src_stride[i]], j < n[i], for `count` fp32 tensors (HOST arrays of
+ * device pointers; src_stride NULL = all contiguous) in ceil(count / TVAE_MTA_MAX) launches -- the gradient accumulation of the small (norm / bias / composite-weight)
+ * parameters, which autograd's AccumulateGrad performs with one tiny kernel per parameter. */
+#define TVAE_MTA_MAX 96
+int tvae_multi_tensor_add(float* const* dst, const float* const* src, const int32_t* n, const int32_t* src_stride,
+                          int32_t count, void* stream);
 
 #ifdef __cplusplus
 }

@@ -96,7 +96,7 @@ def test_cpu_tensors_fail_loudly():
 
 def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()
-    assert lib.tvae_abi_version() == 3
+    assert lib.tvae_abi_version() == 4
     hdr = open(os.path.join(ROOT, "include", "transvae_sm100.h")).read()
     declared = set(re.findall(r"\b(tvae_[a-z0-9_]+)\s*\(", hdr))
     assert declared, "no declarations parsed"

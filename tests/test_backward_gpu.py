@@ -257,20 +257,71 @@ def test_loss_and_latent_backward():
     assert rel(dmu, m.grad) < 1e-4 and rel(dlv, l.grad) < 1e-4
 
 
-def test_adamw_and_sumsq():
+def test_adamw_step_matches_torch_adamw_with_clipping_and_warmup():
+    """tvae_grad_sumsq + tvae_adamw_step == clip_grad_norm_(1.0) + torch.optim.AdamW + LambdaLR warm-up
+    (train.py:608-620, train_2.py:266-274), fp32 and bf16 gradient buffers; the update counter lives on the device."""
     n = 4096 * 3
+    for gdt in (torch.float32, torch.bfloat16):
+        p, g = rnd(n), rnd(n, seed=1)
+        ref = torch.nn.Parameter(p.clone())
+        opt = torch.optim.AdamW([ref], lr=1e-2, betas=(0.9, 0.95), weight_decay=0.01)
+        sch = torch.optim.lr_scheduler.LambdaLR(opt, lambda k: min(1.0, k / 2))
+        m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+        state = torch.zeros(8, device=DEV)
+        partials = torch.zeros(ops.SUMSQ_BLOCKS, dtype=torch.float64, device=DEV)
+        ours = p.clone()
+        for step in range(1, 5):
+            gg = (g * step).to(gdt)
+            ref.grad = gg.float().clone()
+            torch.nn.utils.clip_grad_norm_([ref], 1.0)
+            opt.step()
+            sch.step()
+            ops.grad_sumsq(gg, partials)
+            ops.adamw_step(ours, gg, m, v, partials, state, 1e-2, 2, (0.9, 0.95), 1e-8, 0.01, 1.0, 1.0)
+            assert abs(float(state[0]) - float(gg.float().pow(2).sum())) < 1e-3 * float(state[0])
+        assert float(state[4]) == 4.0 and float(state[5]) == 0.0 and abs(float(state[6]) - 1e-2) < 1e-9
+        assert rel(ours, ref.data) < 1e-4, gdt
+
+
+def test_adamw_step_skips_non_finite_and_keeps_counters():
+    """A non-finite gradient norm skips the update on the device: parameters, moments, the update index (bias
+    correction / warm-up) all stay; only the skip counter moves (train_2.py:329-338: `continue` before optimizer.step())."""
+    n = 2048
     p, g = rnd(n), rnd(n, seed=1)
-    ref = torch.nn.Parameter(p.clone())
-    opt = torch.optim.AdamW([ref], lr=1e-2, betas=(0.9, 0.95), weight_decay=0.01)
     m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
-    ours = p.clone()
-    for step in range(1, 4):
-        ref.grad = g.clone() * step
-        torch.nn.utils.clip_grad_norm_([ref], 1.0)
-        opt.step()
-        ctrl = torch.zeros(4, device=DEV)
-        gg = g * step
-        ops.sumsq(gg, ctrl)
-        ctrl[1], ctrl[2] = 1.0, 1.0
-        ops.adamw(ours, gg, m, v, ctrl, 1e-2, (0.9, 0.95), 1e-8, 0.01, step)
-    assert rel(ours, ref.data) < 1e-4
+    state = torch.zeros(8, device=DEV)
+    partials = torch.zeros(ops.SUMSQ_BLOCKS, dtype=torch.float64, device=DEV)
+    ops.grad_sumsq(g, partials)
+    ops.adamw_step(p, g, m, v, partials, state, 1e-2, 0, (0.9, 0.95), 1e-8, 0.0, 1.0, 1.0)
+    p1, m1 = p.clone(), m.clone()
+    bad = g.clone()
+    bad[7] = float("inf")
+    ops.grad_sumsq(bad, partials)
+    ops.adamw_step(p, bad, m, v, partials, state, 1e-2, 0, (0.9, 0.95), 1e-8, 0.0, 1.0, 1.0)
+    assert torch.equal(p, p1) and torch.equal(m, m1)
+    assert float(state[4]) == 1.0 and float(state[5]) == 1.0
+    # the norm is formed without atomics: bit-identical on repeat
+    a = partials.clone()
+    ops.grad_sumsq(g, partials)
+    b = partials.clone()
+    ops.grad_sumsq(g, partials)
+    assert torch.equal(b, partials) and not torch.equal(a, b)
+
+
+def test_multi_tensor_add_and_cast():
+    ts = [rnd(k, seed=k) for k in (1, 7, 192, 4096, 300000)]
+    ds = [rnd(t.numel(), seed=100 + i) for i, t in enumerate(ts)]
+    want = [d + t for d, t in zip(ds, ts)]
+    mat = rnd(192 * 2, seed=5).view(192, 2)            # strided source: one column of a [C, 2] matrix
+    d2 = rnd(192, seed=6)
+    want2 = d2 + mat[:, 1]
+    ops.multi_tensor_add(ds + [d2], ts + [mat[:, 1]])
+    for d, w in zip(ds + [d2], want + [want2]):
+        assert torch.equal(d, w)
+    many = [torch.zeros(5, device=DEV) for _ in range(250)]
+    ops.multi_tensor_add(many, [torch.full((5,), float(i), device=DEV) for i in range(250)])
+    assert all(float(t[0]) == float(i) for i, t in enumerate(many))
+    x = rnd(4096)
+    y = torch.empty(4096, dtype=torch.bfloat16, device=DEV)
+    ops.cast_f32_bf16(x, y)
+    assert torch.equal(y, x.to(torch.bfloat16))

@@ -100,7 +100,46 @@ def test_trainer_checkpoint_schema_round_trip(tmp_path):
     # parameters still live inside the flat buffer after loading
     lo, hi = flat_ptr, flat_ptr + tr2.buckets.flat_p.numel() * 4
     assert all(lo <= p.data_ptr() < hi for p in m2.parameters())
-    assert abs(tr2._lr() - 1e-4 * 4 / 10) < 1e-12                     # base rate comes from the checkpoint, warm-up k / W
+    assert abs(tr2.opt.current_lr() - 1e-4 * 4 / 10) < 1e-12          # base rate comes from the checkpoint, warm-up k / W
+
+
+def test_checkpoint_resumes_in_the_reference_trainer():
+    """train_2.py:480-490 resumes with optimizer.load_state_dict(...) and scheduler.load_state_dict(...) on a
+    torch.optim.AdamW + LambdaLR pair: our checkpoint must survive exactly that (LambdaLR.load_state_dict pops
+    'lr_lambdas'), and the resumed pair must continue the schedule where we stopped."""
+    m = _mlp()
+    tr = Trainer(m, loss_fn=None, lr=1e-4, warmup_steps=10)
+    tr.opt.step_count = 4
+    tr.opt.m.fill_(0.25)
+    path = str(tmp_path_factory_dir() / "ck_ref.pth")
+    tr.save(path, epoch=1, args={})
+    ck = torch.load(path, weights_only=False)
+    m2 = _mlp(7)
+    m2.load_state_dict(ck["model_state_dict"])
+    opt = torch.optim.AdamW(m2.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0)
+    sch = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: float(s) / 10 if s < 10 else 1.0)     # train_2.py:266-274
+    opt.load_state_dict(ck["optimizer_state_dict"])
+    if ck.get("scheduler_state_dict") is not None:
+        sch.load_state_dict(ck["scheduler_state_dict"])
+    g0 = opt.param_groups[0]
+    assert sch.last_epoch == 4 and g0["initial_lr"] == 1e-4 and abs(g0["lr"] - 4e-5) < 1e-15
+    for p in m2.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step()
+    sch.step()
+    assert abs(opt.param_groups[0]["lr"] - 5e-5) < 1e-15 and float(opt.state_dict()["state"][0]["step"]) == 5.0
+    # and back: the reference pair's checkpoint resumes here with the base rate, not the scheduled one
+    back = {"epoch": 1, "global_step": 5, "model_state_dict": m2.state_dict(), "optimizer_state_dict": opt.state_dict(),
+            "scheduler_state_dict": sch.state_dict(), "args": {}}
+    tr3 = Trainer(_mlp(9), loss_fn=None, lr=9.0, warmup_steps=10)
+    tr3.load_state_dict(back)
+    assert tr3.opt.lr == 1e-4 and tr3.opt.step_count == 5 and abs(tr3.opt.current_lr() - 5e-5) < 1e-15
+
+
+def tmp_path_factory_dir():
+    import pathlib
+    import tempfile
+    return pathlib.Path(tempfile.mkdtemp(prefix="tvae_ck_"))
 
 
 def test_driver_schedule_and_args():
