@@ -1,22 +1,32 @@
 """bench.py -- headline benchmark of the B200-native TransVAE hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--res R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME] [--breakdown-json FILE]
 
-N=1 workload = BASELINE.json configs[1]: TransVAE-large f16d32 encode+decode inference, bf16 compute, batch 64 at
-256x256, synthetic images, random-init weights.  One "step" = mu, logvar = model.encode(x); recon = model.decode(mu)
-on one batch.  N>1 (launched by torchrun, one rank per GPU): the batch dimension is sharded, every rank runs the
-same per-GPU batch (weak scaling), no data-path collective; the timed region is bracketed by a barrier +
-torch.cuda.synchronize(), timed on the device with CUDA events, MAX over ranks.
+Default workload (`--config train256`) = BASELINE.json configs[2]: TransVAE-large f16d32 stage-1 training step
+(forward, L1 + 1e-8 KL loss, backward, gradient all-reduce, clip, AdamW) on a GLOBAL batch of 256 images at 256x256,
+bf16 compute / fp32 master weights, synthetic images, random-init weights.  One "step" = one optimiser step over the
+whole global batch: every rank processes 256 / N images in micro-batches of 32 (gradient accumulation, the all-reduce
+fires on the last micro-step only and overlaps its backward) -- strong scaling, the only curve of this path that
+contains a collective.  Launched by torchrun for N > 1 (one rank per GPU, NCCL); the timed region is bracketed by a
+barrier + torch.cuda.synchronize(), timed on the device with CUDA events, MAX over ranks.
 
-Printed JSON keys (one line, rank 0): metric/value/unit/..., `e2e` (same metric through the public host-to-host call
-transvae.streaming.StreamedReconstructor.reconstruct: every step uploads its pinned input and downloads its
-reconstruction inside the timed region, on side streams), `roofline` (tensor-pipe roofline of the dominant kernel,
-tvae::mtgemm2_kernel / mtgemm_kernel, from per-launch CUDA events; `traffic` from the committed ncu capture),
-`cpu_baseline` (the oracle port of the reference's PyTorch path on this box's host cores, bounded sample), `clocks`,
-`gpu_launches`, `train` (BASELINE configs[2]: fwd + L1/KL loss + bwd + all-reduce + clip + AdamW on global batch 256).
+Other workloads: `infer256` (BASELINE configs[1]: encode+decode, batch 64 / GPU), `extrap512` / `extrap1024`
+(configs[3]: batch-sharded inference at 512^2 / 1024^2, batch 8 / 2 per GPU), `giant` (configs[4]: the 4.8 B-parameter
+variant, DDP training, micro-batch 8).  Inference workloads shard the batch with no collective (weak scaling).
 
-`--impl reference` times the oracle port (oracle/transvae_oracle.py, a bit-exact restatement of the reference's
-torch path -- the reference is pure Python and cannot travel to the GPU box) on the host cores.
+Printed JSON (ONE line, rank 0, < 1.5 kB): metric / value / unit / ..., `e2e` (the same metric through the public
+host-to-host call -- Trainer.train_step_host / StreamedReconstructor.reconstruct -- with the pinned-host upload of every
+micro-batch and the download of the result inside the timed region), `roofline` (tensor-pipe roofline of the dominant
+kernel, tvae::mtgemm2_kernel / mtgemm_kernel, from per-launch CUDA events of instrumented micro-steps; `frac` counts the
+reference's algorithmic FLOPs, `frac_executed` only the MACs the kernel really executes -- the nearest-2x upsample
+convolution runs in its 4-phase 2x2 form; `traffic` from the committed ncu capture), `cpu_baseline`, `clocks`,
+`gpu_launches`, and at N = 1 the secondary legs `infer` (configs[1]) and `gpu_stock_torch` (the UNMODIFIED reference on
+the same B200 under bf16 autocast: cuDNN / cuBLAS / SDPA -- the practical comparator).  Per-kernel tables go to
+`--breakdown-json` (and to stderr with --breakdown), never into the line.
+
+`--impl reference` times the reference's own CPU implementation of the same workload on the host cores: the unmodified
+package from baseline/_ref (kind "reference"; pip-installed there, see baseline/reference_runner.py) or, if that is
+absent, the oracle port (kind "port"); each step is a bounded sample (batch 1) of the workload.
 """
 from __future__ import annotations
 
@@ -34,26 +44,33 @@ sys.path.insert(0, os.path.join(ROOT, "deepl-project_b200"))
 
 import torch  # noqa: E402
 
-METRIC = "images_per_sec_encode_decode_256"
 UNIT = "images/s"
+CONFIGS = {
+    "train256": dict(kind="train", variant="large", res=256, global_batch=256, micro=32, baseline_cfg=2),
+    "infer256": dict(kind="infer", variant="large", res=256, batch=64, baseline_cfg=1),
+    "extrap512": dict(kind="infer", variant="large", res=512, batch=8, baseline_cfg=3),
+    "extrap1024": dict(kind="infer", variant="large", res=1024, batch=2, baseline_cfg=3),
+    "giant": dict(kind="train", variant="giant", res=256, global_batch=256, micro=8, baseline_cfg=4),
+}
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--variant", default="large")
-    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
-    ap.add_argument("--res", type=int, default=256)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="train256", choices=sorted(CONFIGS))
+    ap.add_argument("--global-batch", type=int, default=None, help="training: images per optimiser step over all ranks")
+    ap.add_argument("--micro-batch", type=int, default=None, help="training: images per forward/backward per GPU")
+    ap.add_argument("--batch", type=int, default=None, help="inference: per-GPU batch")
+    ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16"], help="dtype of the gradient all-reduce")
+    ap.add_argument("--bucket-mb", type=int, default=64)
+    ap.add_argument("--checkpointing", action="store_true", help="training: per-block activation recompute")
+    ap.add_argument("--no-legs", action="store_true", help="skip the N = 1 secondary legs (infer / stock torch / CPU)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--breakdown", action="store_true", help="per-shape kernel table on stderr")
-    ap.add_argument("--no-train", action="store_true", help="skip the fwd+bwd (BASELINE configs[2]) measurement")
-    ap.add_argument("--train-global-batch", type=int, default=256)
-    ap.add_argument("--train-micro-batch", type=int, default=32)
-    ap.add_argument("--train-steps", type=int, default=2)
+    ap.add_argument("--breakdown", action="store_true", help="per-shape kernel tables on stderr")
+    ap.add_argument("--breakdown-json", default=None, help="write the per-kernel tables (and the full record) here")
     return ap.parse_args()
 
 
@@ -61,7 +78,7 @@ def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return dict(tflops=float(p["bf16_tflops_sustained"]), hbm=float(p["hbm_gbs"]), src="measured (MEASURED_PEAKS.json, sustained)")
+        return dict(tflops=float(p["bf16_tflops_sustained"]), hbm=float(p["hbm_gbs"]), src="MEASURED_PEAKS.json (sustained)")
     return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
 
 
@@ -109,9 +126,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def hbm_table(prof_hbm, steps, pk):
-    """Per-kernel HBM roofline of the bandwidth-bound launches: algorithmic bytes / CUDA-event time vs the measured
-    copy bandwidth (MEASURED_PEAKS.json hbm_gbs)."""
+def hbm_table(prof_hbm, per, pk):
+    """Per-kernel HBM roofline of the bandwidth-bound launches: algorithmic bytes / CUDA-event time vs the measured copy
+    bandwidth (MEASURED_PEAKS.json hbm_gbs).  `per` = number of profiled units (steps / micro-steps)."""
     agg = {}
     for name, nbytes, a, b in prof_hbm or []:
         d = agg.setdefault(name, [0.0, 0.0, 0])
@@ -121,9 +138,38 @@ def hbm_table(prof_hbm, steps, pk):
     out = []
     for name, (nbytes, ms, n) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        out.append({"kernel": name, "launches_per_step": n / steps, "ms_per_step": ms / steps, "achieved_gbs": gbs,
-                    "frac_of_hbm_peak": gbs / pk["hbm"]})
+        out.append({"kernel": name, "launches": n / per, "ms": round(ms / per, 4), "achieved_gbs": round(gbs, 1),
+                    "frac_of_hbm_peak": round(gbs / pk["hbm"], 4)})
     return out
+
+
+def tensor_tables(prof, per, pk):
+    """(per-class table, per-shape table) of the tensor-core launches from (tag, algorithmic flops, e0, e1) records."""
+    cls, shapes = {}, {}
+    for name, fl, a, b, _ex in prof or []:
+        key = "attn_fwd" if name.startswith("attn_fwd") else "attn_bwd" if name.startswith("attn_bwd") else \
+            "wgrad" if name.startswith("wgrad") else "mtgemm (fwd + dgrad)"
+        t = a.elapsed_time(b)
+        d = cls.setdefault(key, [0.0, 0.0, 0])
+        d[0] += fl
+        d[1] += t
+        d[2] += 1
+        s = shapes.setdefault((name, round(fl / 1e9, 1)), [0.0, 0])
+        s[0] += t
+        s[1] += 1
+    ctab = [{"kernel": k, "launches": n / per, "ms": round(t / per, 3), "achieved_tflops": round(fl / (t * 1e-3) / 1e12, 1),
+             "frac_of_tensor_peak": round(fl / (t * 1e-3) / 1e12 / pk["tflops"], 4)}
+            for k, (fl, t, n) in sorted(cls.items(), key=lambda kv: -kv[1][1]) if t > 0]
+    stab = [{"launch": k[0], "gflop": k[1], "launches": n / per, "ms": round(t / per, 4),
+             "tflops": round(k[1] * n / t, 1) if t else 0.0}
+            for k, (t, n) in sorted(shapes.items(), key=lambda kv: -kv[1][0])]
+    return ctab, stab
+
+
+def print_shapes(title, stab):
+    print(f"\n[{title}] {'launch':78s} GFLOP/launch  launches      ms   TFLOP/s", file=sys.stderr)
+    for r in stab:
+        print(f"{r['launch']:88s} {r['gflop']:10.1f} {r['launches']:8.1f} {r['ms']:10.3f} {r['tflops']:9.1f}", file=sys.stderr)
 
 
 def dist_setup(n):
@@ -140,63 +186,353 @@ def dist_setup(n):
     return rank, world, local
 
 
-# ----------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port on the host cores
-# ----------------------------------------------------------------------------------------------
-def cpu_oracle_rate(variant: str, res: int, steps: int, warmup: int, batch: int):
+def flops_per_image(variant: str, res: int) -> float:
+    """Algorithmic forward GFLOP / image as the reference's modules count them (oracle FLOP model)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import transvae_oracle as O
+    return O.forward_flops_per_image(O.variant_config(variant), res) / 1e9
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own torch code on the host cores
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(cfg: dict, steps: int, warmup: int):
+    """(img/s, ms/step, cores, kind, sample) of the reference's CPU implementation on a batch-1 sample of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reference_runner as R
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.variant_config(variant)
-    sd = O.init_state_dict(cfg, seed=0, mode="reference")
-    x = torch.rand(batch, 3, res, res, generator=torch.Generator().manual_seed(1234))
+    train = cfg["kind"] == "train"
+    res, variant = cfg["res"], cfg["variant"]
+    x = torch.rand(1, 3, res, res, generator=torch.Generator().manual_seed(1234))
+    model, pkg = R.build(variant, patched=train, seed=0)
+    if model is not None:
+        kind = "reference"
+        if train:
+            model.train()
+            loss_fn = pkg.TransVAELoss(l1_weight=1.0, lpips_weight=0.0, kl_weight=1e-8, vf_weight=0.0, gan_weight=0.0)
 
-    def step():
-        with torch.no_grad():
-            mu, _ = O.encode(sd, cfg, x)
-            return O.decode(sd, cfg, mu)
+            def step():
+                model.zero_grad(set_to_none=True)
+                rec, mu, lv = model(x)
+                loss_fn(rec, x, mu, lv)["total"].backward()
+        else:
+            model.eval()
 
+            def step():
+                with torch.no_grad():
+                    mu, _ = model.encode(x)
+                    model.decode(mu)
+    else:
+        import transvae_oracle as O
+        kind = "port"
+        ocfg = O.variant_config(variant)
+        sd = O.init_state_dict(ocfg, seed=0, mode="reference")
+        if train:
+            sdg = {k: v.clone().requires_grad_("inv_freq" not in k) for k, v in sd.items()}
+            eps = torch.randn(1, 32, res // 16, res // 16, generator=torch.Generator().manual_seed(5))
+
+            def step():
+                for v in sdg.values():
+                    v.grad = None
+                rec, mu, lv, _ = O.forward(sdg, ocfg, x, eps, patched=True)
+                O.loss_l1_kl(rec, x, mu, lv, patched=True)["total"].backward()
+        else:
+            def step():
+                with torch.no_grad():
+                    mu, _ = O.encode(sd, ocfg, x)
+                    O.decode(sd, ocfg, mu)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+    what = "forward + L1/KL loss + backward (patched semantics)" if train else "encode + decode"
+    sample = (f"{'unmodified reference package (baseline/_ref)' if kind == 'reference' else 'oracle port'}, fp32 torch CPU, "
+              f"{variant} f16d32 {what}, batch 1 at {res}^2 per step, {warmup} warm-up + {steps} timed")
+    return steps / dt, dt / steps * 1e3, torch.get_num_threads(), kind, sample
 
 
-def run_reference(args, rank, world):
+def workload_string(name: str, cfg: dict) -> str:
+    if cfg["kind"] == "train":
+        return (f"TransVAE-{cfg['variant']} f16d32 stage-1 training fwd+bwd (L1+KL), global batch {cfg['global_batch']} at "
+                f"{cfg['res']}^2, batch-sharded DDP (BASELINE configs[{cfg['baseline_cfg']}])")
+    return (f"TransVAE-{cfg['variant']} f16d32 encode+decode inference at {cfg['res']}^2, batch {cfg['batch']}/GPU, "
+            f"batch-sharded (BASELINE configs[{cfg['baseline_cfg']}])")
+
+
+def metric_name(cfg: dict) -> str:
+    return f"images_per_sec_fwd_bwd_{cfg['res']}" if cfg["kind"] == "train" else f"images_per_sec_encode_decode_{cfg['res']}"
+
+
+def run_reference(args, cfg, rank):
     if rank != 0:
         return
-    b = 1
-    rate, ms, cores = cpu_oracle_rate(args.variant, args.res, args.steps, args.warmup, b)
-    sample = f"oracle port (fp32 torch CPU), {args.variant} f16d32 encode+decode, batch {b} at {args.res}^2 per step"
+    rate, ms, cores, kind, sample = cpu_reference_rate(cfg, args.steps, args.warmup)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"TransVAE-{args.variant} f16d32 encode+decode inference at {args.res}^2 (CPU, batch {b})"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": metric_name(cfg), "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if cfg["kind"] == "train" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(args.config, cfg)},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
 
 
-# ----------------------------------------------------------------------------------------------
+# ----------------------------------------------------------------------------------------------------------------------
+# stock torch on the same B200: the unmodified reference modules under bf16 autocast (cuDNN / cuBLAS / SDPA)
+# ----------------------------------------------------------------------------------------------------------------------
+def stock_torch_leg(cfg: dict, dev) -> dict:
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import reference_runner as R
+    out = {"what": "unmodified reference package on this GPU, torch bf16 autocast (cuDNN / cuBLAS / SDPA), fused AdamW"}
+    if not R.available(True):
+        return {"unavailable": "baseline/_ref not installed"}
+    torch.backends.cudnn.benchmark = True
+    res, variant = cfg["res"], cfg["variant"]
+
+    def timed(fn, warm, n):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    try:
+        with torch.device(dev):
+            model, pkg = R.build(variant, patched=True, seed=0)
+        model = model.to(memory_format=torch.channels_last)          # train_working.py:478
+        B = 32
+        x = torch.rand(B, 3, res, res, device=dev).contiguous(memory_format=torch.channels_last)
+        model.eval()
+
+        def infer():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                mu, _ = model.encode(x)
+                model.decode(mu)
+        ms = timed(infer, 2, 3)
+        out["infer"] = {"value": round(B / ms * 1e3, 2), "unit": UNIT, "ms": round(ms, 2), "batch": B}
+        model.train()
+        loss_fn = pkg.TransVAELoss(l1_weight=1.0, lpips_weight=0.0, kl_weight=1e-8, vf_weight=0.0, gan_weight=0.0).to(dev)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0, fused=True)
+        Bt = 16
+        xt = x[:Bt]
+
+        def train():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                rec, mu, lv = model(xt)
+            losses = loss_fn(rec.float(), xt, mu.float(), lv.float())       # train_working.py:353-362
+            losses["total"].backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        ms = timed(train, 2, 3)
+        out["train"] = {"value": round(Bt / ms * 1e3, 2), "unit": UNIT, "ms": round(ms, 2), "batch": Bt}
+    except Exception as e:  # noqa: BLE001  (OOM or a missing cuDNN path must not kill the bench line)
+        out["error"] = f"{type(e).__name__}: {str(e)[:160]}"
+    finally:
+        model = opt = None
+        torch.cuda.empty_cache()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # our arm
-# ----------------------------------------------------------------------------------------------
-def run_ours(args, rank, world, local):
-    import torch.distributed as dist
+# ----------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self, args, rank, world, local):
+        import torch.distributed as dist
+        self.args, self.rank, self.world, self.local, self.dist = args, rank, world, local, dist
+        self.dev = torch.device("cuda", local)
+        self.pk = peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps, finish=None):
+        """K calls of fn bracketed by barrier + synchronize, CUDA events, MAX over ranks -> (ms total, launches)."""
+        from transvae import ops
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = ops.LAUNCHES
+        e0.record()
+        for _ in range(steps):
+            fn()
+        if finish is not None:
+            finish()
+        e1.record()
+        self.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0]), ops.LAUNCHES - n0
+
+    def profiled(self, fn, reps):
+        from transvae import ops
+        self.barrier()
+        ops.PROFILE, ops.PROFILE_HBM = [], []
+        for _ in range(reps):
+            fn()
+        self.barrier()
+        prof, ops.PROFILE = ops.PROFILE, None
+        hbm, ops.PROFILE_HBM = ops.PROFILE_HBM, None
+        return prof, hbm
+
+
+def traffic_capture():
+    for name in ("r2_traffic_dominant_kernel.json", "r1_traffic_dominant_kernel.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            t = json.load(open(p))
+            return t.get("dram_bytes"), name
+    return None, None
+
+
+def roofline_of(prof, per, step_ms, pk):
+    """Roofline of the dominant kernel (all tvae::mtgemm* forward / input-gradient launches) from the profiled records:
+    `frac` counts the reference's algorithmic FLOPs, `frac_executed` only the MACs that were really executed."""
+    fl = ex = t = 0.0
+    n = 0
+    for name, f, a, b, fe in prof:
+        if name.startswith(("attn_", "wgrad")):
+            continue
+        fl += f
+        ex += fe
+        t += a.elapsed_time(b)
+        n += 1
+    ach = fl / (t * 1e-3) / 1e12 if t > 0 else 0.0
+    ach_ex = ex / (t * 1e-3) / 1e12 if t > 0 else 0.0
+    traffic, src = traffic_capture()
+    return {"bound": "tensor", "kernel": "tvae::mtgemm2_kernel/mtgemm_kernel (all conv/linear fwd+dgrad launches)",
+            "achieved": round(ach, 1), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops"], 4),
+            "frac_executed": round(ach_ex / pk["tflops"], 4), "traffic": traffic, "traffic_src": src,
+            "peak_src": pk["src"], "launches": n / per, "ms_in_kernel": round(t / per, 2),
+            "share_of_step": round(t / per / step_ms, 3) if step_ms else None}
+
+
+def run_train(C: Ctx, name: str, cfg: dict) -> dict:
     import transvae
-    from transvae import _lib, ops
-    _lib.require_device()
-    dev = torch.device("cuda", local)
+    from transvae import ops
+    from transvae.trainer import Trainer
+    args, dev, world, rank = C.args, C.dev, C.world, C.rank
+    gb = args.global_batch or cfg["global_batch"]
+    per_gpu = max(1, gb // world)
+    mb = min(args.micro_batch or cfg["micro"], per_gpu)
+    accum = max(1, per_gpu // mb)
+    imgs = mb * accum * world
+    res = cfg["res"]
     torch.manual_seed(0)
     with torch.device(dev):
-        model = transvae.TransVAE(variant=args.variant, compression_ratio=16, latent_dim=32, input_resolution=args.res)
+        model = transvae.TransVAE(variant=cfg["variant"], compression_ratio=16, latent_dim=32, input_resolution=res)
+    if args.checkpointing:
+        model.enable_gradient_checkpointing()
+    loss_fn = transvae.TransVAELoss(l1_weight=1.0, lpips_weight=0.0, kl_weight=1e-8, vf_weight=0.0, gan_weight=0.0)
+    tr = Trainer(model, loss_fn, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0, grad_clip=1.0, accumulation_steps=accum,
+                 bucket_bytes=args.bucket_mb << 20, grad_comm=torch.bfloat16 if args.grad_comm == "bf16" else torch.float32)
+    g = torch.Generator(device="cpu").manual_seed(4321 + rank)
+    x_host = [torch.rand(mb, 3, res, res, generator=g).pin_memory() for _ in range(accum)]
+    xs = [t.to(dev) for t in x_host]
+
+    def step_resident():
+        for i in range(accum):
+            out = tr.train_step(xs[i])
+        return out
+
+    def step_host():
+        for i in range(accum):
+            tr.train_step_host(x_host[i], next_images_host=x_host[(i + 1) % accum])
+        torch.cuda.current_stream().synchronize()        # the loss terms of the step are on the host (`loss.item()`)
+
+    torch.cuda.reset_peak_memory_stats()
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        out = step_resident()
+    clocks = ClockSampler(C.local)
+    if rank == 0:
+        clocks.start()
+    ms, launches = C.timed(step_resident, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = ms / args.steps
+    value = imgs / ms_step * 1e3
+    loss = float(out["total"])
+
+    # exposed communication / optimiser tail (device events inside the trainer), then instrumented micro-steps
+    tr.timing = []
+    C.timed(step_resident, 1)
+    tail = tr.timing
+    tr.timing = None
+    comm = None
+    if tail:
+        comm = {"grad_comm": args.grad_comm, "payload_gb": round(tr.buckets.numel * (2 if tr.buckets.comm_g is not None else 4) / 1e9, 2),
+                "buckets": len(tr.buckets.buckets), "exposed_allreduce_tail_ms": round(tail[-1][0].elapsed_time(tail[-1][1]), 3),
+                "optimizer_ms": round(tail[-1][1].elapsed_time(tail[-1][2]), 3)}
+    reps = min(accum, 2)
+    tr._micro = 0          # profile plain micro-steps (no optimiser step inside: accumulation position 0 ..)
+    prof, hbm = C.profiled(lambda: [tr.train_step(xs[i]) for i in range(reps)] if accum > reps else step_resident(), 1)
+    if accum > reps:       # finish the interrupted accumulation cycle so that the trainer state stays consistent
+        for i in range(reps, accum):
+            tr.train_step(xs[i])
+    per = reps if accum > reps else accum
+    algo_gf = flops_per_image(cfg["variant"], res)
+    micro_ms = sum(a.elapsed_time(b) for _, _, a, b, _e in prof) / per + sum(a.elapsed_time(b) for _, _, a, b in hbm) / per
+    roof = roofline_of(prof, per, ms_step / accum, C.pk)
+    ctab, stab = tensor_tables(prof, per, C.pk)
+    htab = hbm_table(hbm, per, C.pk)
+    roof["attn_bwd_frac"] = next((r["frac_of_tensor_peak"] for r in ctab if r["kernel"] == "attn_bwd"), None)
+    roof["attn_fwd_frac"] = next((r["frac_of_tensor_peak"] for r in ctab if r["kernel"] == "attn_fwd"), None)
+    roof["wgrad_frac"] = next((r["frac_of_tensor_peak"] for r in ctab if r["kernel"] == "wgrad"), None)
+    if args.breakdown and rank == 0:
+        print_shapes(f"training micro-step, micro-batch {mb}", stab)
+
+    e2e = None
+    if not args.no_e2e:
+        step_host()
+        ms_e, _ = C.timed(step_host, args.steps)
+        e2e = {"value": round(imgs / (ms_e / args.steps) * 1e3, 2), "unit": UNIT,
+               "h2d_bytes_per_step": accum * mb * 3 * res * res * 4, "d2h_bytes_per_step": accum * 6 * 4,
+               "ms_per_step": round(ms_e / args.steps, 2),
+               "api": "transvae.trainer.Trainer.train_step_host (pinned micro-batch in, loss terms out)"}
+
+    gf3 = 3.0 * algo_gf
+    line = {
+        "metric": metric_name(cfg), "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+        "ms_per_step": round(ms_step, 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": workload_string(name, cfg), "global_batch": imgs, "per_gpu_batch": mb * accum, "micro_batch": mb,
+                   "accumulation": accum, "parallelism": f"dp{world}", "grad_comm": args.grad_comm,
+                   "checkpointing": bool(args.checkpointing),
+                   "l2_policy": "activations of a micro-step (>10 GB) exceed the 126 MB L2; no flush needed",
+                   "gflop_per_image_fwd_bwd": round(gf3, 1)},
+        "model_tflops": round(value * gf3 / 1e3, 1), "model_frac_of_peak": round(value * gf3 / 1e3 / (C.pk["tflops"] * world), 4),
+        "loss": round(loss, 5), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+        "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "comm": comm,
+    }
+    extra = {"tensor_kernels": ctab, "hbm_kernels": htab, "shapes": stab, "profiled_micro_step_kernel_ms": round(micro_ms, 2)}
+    # free the training state before the secondary legs
+    tr = model = xs = None
+    torch.cuda.empty_cache()
+    return line, extra
+
+
+def run_infer(C: Ctx, name: str, cfg: dict, steps: int, warmup: int, e2e_on: bool = True):
+    import transvae
+    from transvae.streaming import StreamedReconstructor
+    args, dev, world, rank = C.args, C.dev, C.world, C.rank
+    B, R = args.batch or cfg["batch"], cfg["res"]
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = transvae.TransVAE(variant=cfg["variant"], compression_ratio=16, latent_dim=32, input_resolution=R)
     model.eval()
-    B, R = args.batch, args.res
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     x_host = torch.rand(B, 3, R, R, generator=g).pin_memory()
     x_dev = x_host.to(dev)
@@ -207,224 +543,95 @@ def run_ours(args, rank, world, local):
             mu, _ = model.encode(x_dev)
             return model.decode(mu)
 
-    # e2e: the public host-to-host call (transvae.streaming.StreamedReconstructor): every step uploads its pinned input
-    # and downloads its reconstruction; the copies run on side streams (copy engines) and overlap the kernels of the
-    # neighbouring steps; the timed region ends after the last download (pipe.join before the closing event)
-    from transvae.streaming import StreamedReconstructor
     pipe = StreamedReconstructor(model, dev)
 
     def step_e2e():
         pipe.reconstruct(x_host, out_host, next_x_host=x_host)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, profile=False, finish=None):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if profile:
-            ops.PROFILE, ops.PROFILE_HBM = [], []
-        n0 = ops.LAUNCHES
-        e0.record()
-        for _ in range(steps):
-            fn()
-        if finish is not None:
-            finish()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        prof, ops.PROFILE = ops.PROFILE, None
-        hbm, ops.PROFILE_HBM = ops.PROFILE_HBM, None
-        if profile:
-            prof = (prof, hbm)
-        t = torch.tensor([ms], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), ops.LAUNCHES - n0, prof
-
-    for _ in range(max(args.warmup, 3)):
+    W = max(warmup, 3)
+    for _ in range(W):
         step_resident()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(C.local)
     if rank == 0:
         clocks.start()
-    ms, launches, _ = timed(step_resident, args.steps)
+    ms, launches = C.timed(step_resident, steps)
     clk = clocks.stop() if rank == 0 else None
-    value = B * world * args.steps / (ms / 1e3)
-
-    # roofline of the dominant kernel from per-launch CUDA events (separate instrumented steps so the event records do
-    # not perturb `value`; same stream, same inputs, directly after the timed region)
-    _, _, (prof, prof_hbm) = timed(step_resident, 2, profile=True)
-    pk = peaks()
-    by = {}
-    for name, fl, a, b in prof:
-        d = by.setdefault("attn_fwd" if name.startswith("attn_fwd") else "mtgemm", [0.0, 0.0, 0])
-        d[0] += fl
-        d[1] += a.elapsed_time(b)
-        d[2] += 1
+    ms_step = ms / steps
+    value = B * world / ms_step * 1e3
+    prof, hbm = C.profiled(step_resident, 2)
+    algo_gf = flops_per_image(cfg["variant"], R)
+    roof = roofline_of(prof, 2, ms_step, C.pk)
+    ctab, stab = tensor_tables(prof, 2, C.pk)
+    roof["attn_fwd_frac"] = next((r["frac_of_tensor_peak"] for r in ctab if r["kernel"] == "attn_fwd"), None)
     if args.breakdown and rank == 0:
-        tab = {}
-        for name, fl, a, b in prof:
-            d = tab.setdefault((name, round(fl / 1e9, 1)), [0.0, 0])
-            d[0] += a.elapsed_time(b)
-            d[1] += 1
-        print(f"{'kernel':78s} GFLOP/launch launches/step   ms/step   TFLOP/s", file=sys.stderr)
-        for (name, gf), (t, n) in sorted(tab.items(), key=lambda kv: -kv[1][0]):
-            print(f"{name:78s} {gf:10.1f} {n // 2:8d} {t / 2:12.3f} {gf * n / t if t else 0:9.1f}", file=sys.stderr)
-    gm = by.get("mtgemm", [0.0, 1e-9, 0])
-    at = by.get("attn_fwd", [0.0, 1e-9, 0])
-    step_ms_prof = sum(a.elapsed_time(b) for _, _, a, b in prof) / 2
-    ach = gm[0] / (gm[1] * 1e-3) / 1e12
-    # DRAM traffic of the dominant launch shape from the committed ncu --set full capture (bytes per launch of that shape)
-    traffic, traffic_ref = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic_dominant_kernel.json")
-    if os.path.exists(tpath):
-        traffic_ref = json.load(open(tpath))
-        traffic = traffic_ref["dram_bytes"]
-    roofline = {"bound": "tensor", "kernel": "tvae::mtgemm2_kernel / mtgemm_kernel (all conv / linear launches)", "achieved": ach,
-                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": traffic,
-                "traffic_capture": traffic_ref,
-                "peak_source": pk["src"], "launches_per_step": gm[2] // 2, "ms_per_step_in_kernel": gm[1] / 2,
-                "share_of_step": gm[1] / 2 / (ms / args.steps),
-                "attention": {"achieved": at[0] / (at[1] * 1e-3) / 1e12, "unit": "TFLOP/s",
-                              "frac": at[0] / (at[1] * 1e-3) / 1e12 / pk["tflops"], "ms_per_step_in_kernel": at[1] / 2,
-                              "launches_per_step": at[2] // 2},
-                "sum_of_timed_kernels_ms": step_ms_prof,
-                "hbm_kernels": hbm_table(prof_hbm, 2, pk)}
-
+        print_shapes(f"inference step, batch {B} at {R}^2", stab)
     e2e = None
-    if not args.no_e2e:
+    if e2e_on and not args.no_e2e:
         for _ in range(2):
             step_e2e()
-        ms_e, _, _ = timed(step_e2e, args.steps, finish=pipe.join)
+        ms_e, _ = C.timed(step_e2e, steps, finish=pipe.join)
         pipe.synchronize()
-        e2e = {"value": B * world * args.steps / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
-               "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e / args.steps,
-               "api": "transvae.streaming.StreamedReconstructor.reconstruct (pinned host in / out, copies on side streams)"}
+        e2e = {"value": round(B * world / (ms_e / steps) * 1e3, 2), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
+               "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": round(ms_e / steps, 2),
+               "api": "transvae.streaming.StreamedReconstructor.reconstruct (pinned host in / out)"}
+    line = {
+        "metric": metric_name(cfg), "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": W,
+        "ms_per_step": round(ms_step, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": workload_string(name, cfg), "per_gpu_batch": B, "resolution": R,
+                   "parallelism": f"batch-sharded x{world}, no collective",
+                   "l2_policy": "activations per step (>2 GB) exceed the 126 MB L2; no flush needed",
+                   "gflop_per_image": round(algo_gf, 1)},
+        "model_tflops": round(value * algo_gf / 1e3, 1), "model_frac_of_peak": round(value * algo_gf / 1e3 / (C.pk["tflops"] * world), 4),
+        "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
+    }
+    extra = {"tensor_kernels": ctab, "hbm_kernels": hbm_table(hbm, 2, C.pk), "shapes": stab}
+    model = None
+    torch.cuda.empty_cache()
+    return line, extra
 
-    train = None
-    if not args.no_train:
-        train = run_train(args, model, rank, world, dev, dist, pk)
 
+def run_ours(args, name, cfg, rank, world, local):
+    from transvae import _lib
+    _lib.require_device()
+    C = Ctx(args, rank, world, local)
+    if cfg["kind"] == "train":
+        line, extra = run_train(C, name, cfg)
+    else:
+        line, extra = run_infer(C, name, cfg, args.steps, args.warmup)
+    legs = world == 1 and not args.no_legs
+    if legs and name == "train256":
+        # secondary legs, N = 1 only: BASELINE configs[1] on our kernels, stock torch on the same GPU, the CPU reference
+        il, ie = run_infer(C, "infer256", CONFIGS["infer256"], 5, 3)
+        line["infer"] = {"metric": il["metric"], "value": il["value"], "ms_per_step": il["ms_per_step"],
+                         "e2e": il["e2e"]["value"] if il["e2e"] else None, "model_frac_of_peak": il["model_frac_of_peak"],
+                         "mtgemm_frac": il["roofline"]["frac"], "attn_fwd_frac": il["roofline"]["attn_fwd_frac"], "batch": 64}
+        extra["infer"] = ie
+        line["gpu_stock_torch"] = stock_torch_leg(cfg, C.dev)
+    if legs:
+        rate, ms_cpu, cores, kind, sample = cpu_reference_rate(cfg, 1, 1)
+        line["cpu_baseline"] = {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+    else:
+        line["cpu_baseline"] = None
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import transvae_oracle as O
-    gflop = O.forward_flops_per_image(O.variant_config(args.variant), R) / 1e9
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        rate, ms_cpu, cores = cpu_oracle_rate(args.variant, R, 2, 1, 1)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"oracle port (fp32 torch CPU) of the same encode+decode, batch 1 at {R}^2, 1 warm-up + 2 timed steps"}
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic",
-        "config": {"workload": f"TransVAE-{args.variant} f16d32 encode+decode inference, batch {B}/GPU at {R}^2 (BASELINE configs[1])",
-                   "per_gpu_batch": B, "resolution": R, "parallelism": f"batch-sharded x{world}, no collective",
-                   "l2_policy": "activations per step (>2 GB) exceed the 126 MB L2; no flush needed",
-                   "gflop_per_image": gflop},
-        "model_tflops": value * gflop / 1e3, "model_frac_of_peak": value * gflop / 1e3 / (pk["tflops"] * world),
-        "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "train": train,
-    }
+    if args.breakdown_json:
+        os.makedirs(os.path.dirname(os.path.abspath(args.breakdown_json)), exist_ok=True)
+        with open(args.breakdown_json, "w") as fh:
+            json.dump({"line": line, **extra}, fh, indent=1)
     print(json.dumps(line), flush=True)
-
-
-def run_train(args, model, rank, world, dev, dist, pk):
-    """BASELINE configs[2]: stage-1 training step (fwd + L1/KL loss + bwd + gradient all-reduce + clip + AdamW) on a fixed
-    global batch (strong scaling: per-GPU batch = global / N, processed in micro-batches).  One step = one optimiser
-    step over the whole global batch; timed on the device, MAX over ranks."""
-    import transvae
-    from transvae import ops
-    from transvae.trainer import Trainer
-    per_gpu = max(1, args.train_global_batch // world)
-    mb = min(args.train_micro_batch, per_gpu)
-    accum = max(1, per_gpu // mb)
-    loss_fn = transvae.TransVAELoss(l1_weight=1.0, lpips_weight=0.0, kl_weight=1e-8, vf_weight=0.0, gan_weight=0.0)
-    tr = Trainer(model, loss_fn, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0, grad_clip=1.0, accumulation_steps=accum)
-    g = torch.Generator(device="cpu").manual_seed(4321 + rank)
-    xs = [torch.rand(mb, 3, args.res, args.res, generator=g).to(dev) for _ in range(min(accum, 2))]
-
-    def step():
-        for i in range(accum):
-            out = tr.train_step(xs[i % len(xs)])
-        return out
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    torch.cuda.reset_peak_memory_stats()
-    step()                                  # warm-up (allocator, NCCL channels)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0 = ops.LAUNCHES
-    e0.record()
-    for _ in range(args.train_steps):
-        out = step()
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t[0]) / args.train_steps
-    # one instrumented micro-step (forward + backward, no optimiser step) for the per-kernel tables
-    ops.PROFILE, ops.PROFILE_HBM = [], []
-    tr._micro = 0
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    tr.train_step(xs[0])
-    e3.record()
-    barrier()
-    prof_t, ops.PROFILE = ops.PROFILE, None
-    prof_h, ops.PROFILE_HBM = ops.PROFILE_HBM, None
-    tens = {}
-    for name, fl, a, b in prof_t:
-        key = "attn_fwd" if name.startswith("attn_fwd") else "attn_bwd" if name.startswith("attn_bwd") else \
-            "wgrad" if name.startswith("wgrad") else "mtgemm (fwd + dgrad)"
-        d = tens.setdefault(key, [0.0, 0.0, 0])
-        d[0] += fl
-        d[1] += a.elapsed_time(b)
-        d[2] += 1
-    tensor_tab = [{"kernel": k, "launches": n, "ms": t_ms, "achieved_tflops": fl / (t_ms * 1e-3) / 1e12,
-                   "frac_of_tensor_peak": fl / (t_ms * 1e-3) / 1e12 / pk["tflops"]}
-                  for k, (fl, t_ms, n) in sorted(tens.items(), key=lambda kv: -kv[1][1])]
-    if args.breakdown and rank == 0:
-        tab = {}
-        for name, fl, a, b in prof_t:
-            d = tab.setdefault((name, round(fl / 1e9, 1)), [0.0, 0])
-            d[0] += a.elapsed_time(b)
-            d[1] += 1
-        print(f"\n[training micro-step, micro-batch {mb}] {'kernel':60s} GFLOP/launch launches   ms   TFLOP/s", file=sys.stderr)
-        for (name, gf), (tt, n) in sorted(tab.items(), key=lambda kv: -kv[1][0]):
-            print(f"{name:78s} {gf:10.1f} {n:8d} {tt:12.3f} {gf * n / tt if tt else 0:9.1f}", file=sys.stderr)
-    micro = {"micro_batch": mb, "ms": e2.elapsed_time(e3), "tensor_kernels": tensor_tab, "hbm_kernels": hbm_table(prof_h, 1, pk)}
-    imgs = mb * accum * world
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import transvae_oracle as O
-    gflop = 3.0 * O.forward_flops_per_image(O.variant_config(args.variant), args.res) / 1e9
-    rate = imgs / ms * 1e3
-    return {"metric": "images_per_sec_fwd_bwd_256", "value": rate, "unit": UNIT, "ms_per_step": ms, "scaling": "strong",
-            "global_batch": imgs, "per_gpu_micro_batch": mb, "accumulation": accum, "steps": args.train_steps,
-            "loss": float(out["total"]), "gflop_per_image_fwd_bwd": gflop, "model_tflops": rate * gflop / 1e3,
-            "model_frac_of_peak": rate * gflop / 1e3 / (pk["tflops"] * world),
-            "gpu_launches_per_step": (ops.LAUNCHES - n0) // args.train_steps,
-            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
-            "includes": "fwd, L1+KL loss, bwd, bucketed NCCL all-reduce overlapped with bwd, clip, fused AdamW",
-            "profiled_micro_step": micro}
 
 
 def main():
     args = parse()
+    cfg = CONFIGS[args.config]
     if args.impl == "reference":
         # CPU arm: rank 0 alone runs and prints; the other ranks exit 0 without work (no process group needed)
-        run_reference(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
+        run_reference(args, cfg, int(os.environ.get("RANK", "0")))
         return
     rank, world, local = dist_setup(args.gpus)
     try:
-        run_ours(args, rank, world, local)
+        run_ours(args, args.config, cfg, rank, world, local)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libtransvae_sm100.so")
-SOURCES = ["runtime.cu", "mtgemm.cu", "mtgemm2.cu", "wgrad.cu", "elementwise.cu", "attention.cu", "attention_bwd.cu", "backward.cu", "optim.cu", "metrics.cu", "weights.cu", "api.cu"]
+SOURCES = ["runtime.cu", "mtgemm.cu", "mtgemm2.cu", "wgrad.cu", "elementwise.cu", "attention.cu", "attention_bwd.cu", "backward.cu", "optim.cu", "depthwise.cu", "metrics.cu", "weights.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--use_fast_math"]
 

@@ -48,6 +48,9 @@ int cast_f32_bf16_run(const float* in, void* out, long long n, cudaStream_t stre
 int mta_add_run(float* const* dst, const float* const* src, const int* n, const int* sstride, int count, cudaStream_t stream);
 int weight_pack_run(const float* w, void* fwd, void* dgr, int A, int B, int T, cudaStream_t stream);
 int wgrad_unpack_run(const float* g, float* out, int A, int B, int T, cudaStream_t stream);
+int dwconv3x3_run(const void* u, const float* w9c, const float* bias, void* y, int B, int H, int W, int C, int flip,
+                  int add_input, cudaStream_t stream);
+int dwconv3x3_wgrad_run(const void* u, const void* dy, float* dw, float* db, int B, int H, int W, int C, cudaStream_t stream);
 int metrics_run(const float* recon, const float* target, float* acc, int B, int C, int H, int W, int mode,
                 cudaStream_t stream);
 }  // namespace tvae
@@ -197,6 +200,15 @@ int tvae_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, void* stream)
 int tvae_multi_tensor_add(float* const* dst, const float* const* src, const int32_t* n, const int32_t* src_stride,
                           int32_t count, void* stream) {
   GUARD(); return mta_add_run(dst, src, n, src_stride, count, S_(stream));
+}
+
+int tvae_dwconv3x3(const void* u, const float* w9c, const float* bias, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
+                   int32_t flip, int32_t add_input, void* stream) {
+  GUARD(); return dwconv3x3_run(u, w9c, bias, y, B, H, W, C, flip, add_input, S_(stream));
+}
+int tvae_dwconv3x3_wgrad(const void* u, const void* dy, float* dw9c, float* db, int32_t B, int32_t H, int32_t W, int32_t C,
+                         void* stream) {
+  GUARD(); return dwconv3x3_wgrad_run(u, dy, dw9c, db, B, H, W, C, S_(stream));
 }
 
 int tvae_metrics(const float* recon, const float* target, float* acc, int32_t B, int32_t C, int32_t H, int32_t W,

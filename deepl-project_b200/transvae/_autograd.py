@@ -218,6 +218,89 @@ class ResBlockFn(Fn):
         return out
 
 
+class ResBlockScFn(Fn):
+    """conv2(silu(GN2(conv1(silu(GN1(x)))))) + shortcut(x) with a convolutional shortcut (blocks.py:40-46, :68; in != out
+    channels).  ``w2s`` = packed [Cout, 9*Cout + k*k*Cin] (conv2 | shortcut), ``b2s`` = conv2.bias + shortcut.bias: conv2
+    and the shortcut share one accumulator (``_taps.plan_resblock_conv2``)."""
+
+    @staticmethod
+    def forward(ctx, x, x_sums, g1, b1, w1, c1b, g2, b2, w2s, b2s, k):
+        B, H, W, Cin = x.shape
+        Cout = w1.shape[0]
+        h0, s1 = ops.groupnorm_silu(x, g1, b1, sums=x_sums, return_sums=True)
+        w1f, w1d = _w_pack(w1)
+        h1 = ops.mtgemm(T.plan_conv3x3(Cin), h0, w1f, out_shape=(B, H, W, Cout), bias=_f32(c1b), gn_groups=32)
+        h2, s2 = ops.groupnorm_silu(h1, g2, b2, sums=h1._gn_sums, return_sums=True)
+        out = ops.mtgemm(T.plan_resblock_conv2(Cout, Cin, k), h2, _bf(w2s), a1=x, out_shape=(B, H, W, Cout), bias=_f32(b2s),
+                         gn_groups=32)
+        out_sums = out._gn_sums
+        ctx.save_for_backward(x, s1, h0, h1, s2, h2, g1, b1, w1, g2, b2, w2s, w1d, c1b)
+        ctx.k = k
+        ctx.mark_non_differentiable(out_sums)
+        return out, out_sums
+
+    @staticmethod
+    def backward(ctx, dout, _dsums):
+        x, s1, h0, h1, s2, h2, g1, b1, w1, g2, b2, w2s, w1d, c1b = ctx.saved_tensors
+        dout = dout.contiguous()
+        k = ctx.k
+        B, H, W, Cin = x.shape
+        Cout = w1.shape[0]
+        dw2s, db2s = _wgrad_b(T.plan_resblock_conv2(Cout, Cin, k), h2, dout, Cout, a1=x)
+        dh2 = ops.mtgemm(T.plan_conv3x3_dgrad(Cout), dout, _tr(w2s[:, :9 * Cout], 9), out_shape=(B, H, W, Cout))
+        dx_sc = ops.mtgemm(T.plan_conv_kxk_dgrad(Cout, k), dout, _tr(w2s[:, 9 * Cout:], k * k), out_shape=(B, H, W, Cin))
+        dh1, dg2, db2 = ops.groupnorm_bwd(h1, dh2, s2, g2, b2)
+        dw1, dc1b = _wgrad_b(T.plan_conv3x3(Cin), h0, dh1, Cout, b=c1b)
+        dh0 = ops.mtgemm(T.plan_conv3x3_dgrad(Cout), dh1, w1d, out_shape=(B, H, W, Cin))
+        dx, dg1, db1 = ops.groupnorm_bwd(x, dh0, s1, g1, b1, add=dx_sc)
+        S = GRAD_SINK
+        out = (dx, None, S.add(g1, dg1), S.add(b1, db1), S.add(w1, _w_ungrad(dw1, w1)), S.add(c1b, dc1b), S.add(g2, dg2),
+               S.add(b2, db2), dw2s, db2s, None)
+        S.flush()
+        return out
+
+
+class FfnDwFn(Fn):
+    """x + proj_out(u + dwconv3x3(u)), u = gelu(proj_in(RMSNorm(x; w2)))  (conv.py:42-50, 79-105: conv_type='depthwise').
+    ``wdw``: the depthwise weight as fp32 [9, hid] (tap-major)."""
+
+    @staticmethod
+    def forward(ctx, x, w2n, win, bin_, wdw, bdw, wout, bout):
+        B, H, W, C = x.shape
+        M = B * H * W
+        hid = win.shape[0]
+        (win_f, win_d), (wout_f, wout_d) = _w_pack(win), _w_pack(wout)
+        xn = ops.token_norm_fwd(x, w2n, 0)
+        z_in = ops.mtgemm(T.plan_linear(C), _flat(xn), win_f, out_shape=(1, 1, M, hid), bias=_f32(bin_))
+        u = ops.act_fwd(z_in, ACT_GELU)
+        wdw_c = _f32(wdw)
+        u2 = ops.dwconv3x3(u.view(B, H, W, hid), wdw_c, _f32(bdw), flip=False, add_input=True)
+        out = ops.mtgemm(T.plan_linear(hid), _flat(u2), wout_f, out_shape=(1, 1, M, C), bias=_f32(bout), residual=_flat(x))
+        ctx.save_for_backward(x, w2n, xn, z_in, u, u2, wdw_c, win_d, wout_d, win, wout, bin_, bout)
+        return out.view(B, H, W, C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w2n, xn, z_in, u, u2, wdw_c, win_d, wout_d, win, wout, bin_, bout = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, H, W, C = x.shape
+        M = B * H * W
+        hid = win.shape[0]
+        df = _flat(dout)
+        dwout, dbout = _wgrad_b(T.plan_linear(hid), _flat(u2), df, C, w=wout, b=bout)
+        du2 = ops.mtgemm(T.plan_linear(C), df, wout_d, out_shape=(1, 1, M, hid)).view(B, H, W, hid)
+        dwdw, dbdw = ops.dwconv3x3_wgrad(u.view(B, H, W, hid), du2)
+        du = ops.dwconv3x3(du2, wdw_c, None, flip=True, add_input=True)            # du2 + dwconv^T(du2)
+        dzin, _ = ops.bias_act_bwd(du.view(M, hid), z_in.view(M, hid), ACT_GELU)
+        dzin = dzin.view(1, 1, M, hid)
+        dwin, dbin = _wgrad_b(T.plan_linear(C), _flat(xn), dzin, hid, w=win, b=bin_)
+        dxn = ops.mtgemm(T.plan_linear(hid), dzin, win_d, out_shape=(1, 1, M, C))
+        dx, dw2n = ops.token_norm_bwd(x, w2n, dxn.view(B, H, W, C), dout, 0)
+        dw2n = GRAD_SINK.add(w2n, dw2n)
+        GRAD_SINK.flush()
+        return dx, dw2n, dwin, dbin, dwdw, dbdw, dwout, dbout
+
+
 class DownsampleFn(Fn):
     """conv3x3 s2 (silu(conv3x3(x))) + conv1x1(pixel_unshuffle(x))  (upsample.py:55-66)."""
 

@@ -13,7 +13,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # TVAE_LIB: load another build of the same ABI (kernel experiments, tools/experiments/)
 LIB_PATH = os.environ.get("TVAE_LIB") or os.path.join(_PKG_ROOT, "libtransvae_sm100.so")
 
-MAX_TAPS = 16
+MAX_TAPS = 20
 MAX_PHASES = 4
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
 
@@ -93,6 +93,10 @@ _PROTOS = {
                                 C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_void_p]),
     "tvae_latent_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "tvae_dwconv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_int32, C.c_void_p]),
+    "tvae_dwconv3x3_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_void_p]),
     "tvae_weight_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "tvae_wgrad_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "tvae_grad_sumsq": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -67,6 +67,31 @@ def plan_conv3x3(c: int) -> Plan:
     return Plan([taps], [0], [0], k_total=9 * c, name="conv3x3", algo_k=9 * c)
 
 
+def plan_resblock_conv2(cmid: int, cin: int, k: int) -> Plan:
+    """conv2 of a ResBlock whose shortcut is a convolution (blocks.py:40-46, :68 ``h + self.shortcut(x)``): the nine taps
+    of conv2 over map 0 (the normalised activation, cmid channels) and the k x k taps of the shortcut over map 1 (the
+    block input, cin channels) accumulate into ONE accumulator; weights [cout, 9*cmid + k*k*cin]."""
+    taps = [TapSpec(0, 0, dx - 1, 0, dy - 1, _kb(cmid), (dy * 3 + dx) * cmid) for dy in range(3) for dx in range(3)]
+    r = k // 2
+    for dy in range(k):
+        for dx in range(k):
+            taps.append(TapSpec(1, 0, dx - r, 0, dy - r, _kb(cin), 9 * cmid + (dy * k + dx) * cin))
+    return Plan([taps], [0], [0], k_total=9 * cmid + k * k * cin, name=f"resblock_conv2_sc{k}", algo_k=9 * cmid + k * k * cin)
+
+
+def pack_resblock_conv2(w2: Tensor, ws: Tensor) -> Tensor:
+    """[O, 9*Cmid + k*k*Cin]: conv2 taps then the shortcut's (1x1 or 3x3) taps."""
+    sc = pack_conv3x3(ws) if ws.shape[-1] == 3 else pack_conv1x1(ws)
+    return torch.cat([pack_conv3x3(w2), sc], dim=1)
+
+
+def plan_conv_kxk_dgrad(n: int, k: int) -> Plan:
+    """Input gradient of a k x k (k = 1 or 3), stride-1, same-padded convolution with ``n`` output channels."""
+    if k == 3:
+        return plan_conv3x3_dgrad(n)
+    return Plan([[TapSpec(0, 0, 0, 0, 0, _kb(n), 0)]], [0], [0], k_total=n, name="conv1x1_dgrad", algo_k=n)
+
+
 def _s2(d: int) -> Tuple[int, int]:
     """Stride-2, pad-1 tap d in {0,1,2} -> (phase, offset) in the 2x phase view: row 2h+d-1."""
     return ((d - 1) % 2, (d - 1) // 2)

@@ -82,6 +82,12 @@ def gn_sums_of(x: Tensor, groups: int = 32) -> Optional[Tensor]:
     return None
 
 
+def dwconv3x3(u: Tensor, w9c: Tensor, bias: Optional[Tensor]) -> Tensor:
+    if _needs_grad(u, w9c, bias):
+        raise RuntimeError("internal: the depthwise ConvFFN trains through _autograd.FfnDwFn")
+    return ops.dwconv3x3(u, w9c, bias, flip=False, add_input=True)
+
+
 def row_stats(x: Tensor, w1: Optional[Tensor] = None, mode: Optional[int] = None):
     return ops.row_stats(x, w1, mode)
 

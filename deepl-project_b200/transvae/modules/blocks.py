@@ -21,10 +21,10 @@ from .conv import ConvFFN
 class _Conv2dParams(nn.Module):
     """Holds ``weight`` [O, I, k, k] and ``bias`` [O] under the reference's names (nn.Conv2d defaults for init)."""
 
-    def __init__(self, cin: int, cout: int, k: int):
+    def __init__(self, cin: int, cout: int, k: int, groups: int = 1):
         super().__init__()
-        self.in_channels, self.out_channels, self.kernel_size = cin, cout, (k, k)
-        ref = nn.Conv2d(cin, cout, k)
+        self.in_channels, self.out_channels, self.kernel_size, self.groups = cin, cout, (k, k), groups
+        ref = nn.Conv2d(cin, cout, k, groups=groups)
         self.weight = nn.Parameter(ref.weight.detach().clone())
         self.bias = nn.Parameter(ref.bias.detach().clone())
 
@@ -60,36 +60,54 @@ class _NormParams(nn.Module):
 class ResBlock(HotModule):
     def __init__(self, in_channels: int, out_channels: int, use_conv_shortcut: bool = False):
         super().__init__()
-        if in_channels != out_channels:
-            raise NotImplementedError("ResBlock with in_channels != out_channels is not reachable from the shipped "
-                                      "configs (encoder.py:70) and is not built on the B200 path yet")
         self.in_channels, self.out_channels = in_channels, out_channels
         self.norm1 = _NormParams(in_channels, 32)
         self.conv1 = _Conv2dParams(in_channels, out_channels, 3)
         self.norm2 = _NormParams(out_channels, 32)
         self.conv2 = _Conv2dParams(out_channels, out_channels, 3)
-        self.shortcut = nn.Identity()
+        # blocks.py:40-46: a 3x3 (use_conv_shortcut) or 1x1 convolution when the channel count changes, else identity.  The
+        # shipped configs always build in == out (encoder.py:70); the convolutional shortcut is an ablation-level switch.
+        if in_channels != out_channels:
+            self.shortcut = _Conv2dParams(in_channels, out_channels, 3 if use_conv_shortcut else 1)
+        else:
+            self.shortcut = nn.Identity()
 
     def forward_nhwc(self, x: torch.Tensor, add_residual: bool = True) -> torch.Tensor:
         B, H, W, C = x.shape
+        Co = self.out_channels
+        conv_sc = isinstance(self.shortcut, _Conv2dParams)
         if K.needs_grad(x, *self.parameters()):
             if not add_residual:
                 raise NotImplementedError("add_residual=False is an inference-only test hook")
-            from .._autograd import ResBlockFn
-            out, out_sums = ResBlockFn.apply(x, K.gn_sums_of(x), self.norm1.weight, self.norm1.bias, self.conv1.weight,
-                                             self.conv1.bias, self.norm2.weight, self.norm2.bias,
-                                             self.conv2.weight, self.conv2.bias)
+            if conv_sc:
+                from .._autograd import ResBlockScFn
+                k = self.shortcut.kernel_size[0]
+                out, out_sums = ResBlockScFn.apply(x, K.gn_sums_of(x), self.norm1.weight, self.norm1.bias, self.conv1.weight,
+                                                   self.conv1.bias, self.norm2.weight, self.norm2.bias,
+                                                   T.pack_resblock_conv2(self.conv2.weight, self.shortcut.weight),
+                                                   self.conv2.bias + self.shortcut.bias, k)
+            else:
+                from .._autograd import ResBlockFn
+                out, out_sums = ResBlockFn.apply(x, K.gn_sums_of(x), self.norm1.weight, self.norm1.bias, self.conv1.weight,
+                                                 self.conv1.bias, self.norm2.weight, self.norm2.bias,
+                                                 self.conv2.weight, self.conv2.bias)
             out._gn_sums = out_sums           # statistics for the next ResBlock's norm1 / decoder.norm_out
             return out
-        plan = T.plan_conv3x3(C)
         w1 = self._packs.get("w1", [self.conv1.weight], lambda: bf16c(T.pack_conv3x3(self.conv1.weight)))
-        w2 = self._packs.get("w2", [self.conv2.weight], lambda: bf16c(T.pack_conv3x3(self.conv2.weight)))
         # every convolution whose output feeds a GroupNorm takes that norm's statistics in its epilogue (gn_groups):
         # conv1 for norm2, conv2 (+ residual) for the next ResBlock's norm1 / decoder.norm_out
         h = K.groupnorm_silu(x, self.norm1.weight, self.norm1.bias)
-        h = K.mtgemm(plan, h, w1, out_shape=(B, H, W, C), bias=f32c(self.conv1.bias), gn_groups=32)
+        h = K.mtgemm(T.plan_conv3x3(C), h, w1, out_shape=(B, H, W, Co), bias=f32c(self.conv1.bias), gn_groups=32)
         h = K.groupnorm_silu(h, self.norm2.weight, self.norm2.bias)
-        return K.mtgemm(plan, h, w2, out_shape=(B, H, W, C), bias=f32c(self.conv2.bias),
+        if conv_sc and add_residual:
+            # conv2 and the shortcut convolution share one accumulator: 9 taps over h + k*k taps over x
+            k = self.shortcut.kernel_size[0]
+            w2s = self._packs.get("w2s", [self.conv2.weight, self.shortcut.weight],
+                                  lambda: bf16c(T.pack_resblock_conv2(self.conv2.weight, self.shortcut.weight)))
+            b2s = self._packs.get("b2s", [self.conv2.bias, self.shortcut.bias], lambda: f32c(self.conv2.bias + self.shortcut.bias))
+            return K.mtgemm(T.plan_resblock_conv2(Co, C, k), h, w2s, a1=x, out_shape=(B, H, W, Co), bias=b2s, gn_groups=32)
+        w2 = self._packs.get("w2", [self.conv2.weight], lambda: bf16c(T.pack_conv3x3(self.conv2.weight)))
+        return K.mtgemm(T.plan_conv3x3(Co), h, w2, out_shape=(B, H, W, Co), bias=f32c(self.conv2.bias),
                         residual=x if add_residual else None, gn_groups=32 if add_residual else 0)
 
 

@@ -105,6 +105,13 @@ def _fill_taps(d, plan: Plan) -> None:
             dt.map, dt.c_off, dt.dw, dt.p, dt.dh, dt.kblocks, dt.wk_off = t.map, t.c_off, t.dw, t.p, t.dh, t.kblocks, t.wk_off
 
 
+def _exec_k(plan: Plan) -> int:
+    """K per output element the kernel really executes (<= the reference's ``algo_k``: nearest-2x + 3x3 runs as four
+    phase-specific 2x2 convolutions; zero padding of K is not counted as work)."""
+    k = sum(t.kblocks * 64 for t in plan.phases[0])
+    return min(k, plan.algo_k) if plan.algo_k else k
+
+
 def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, out: Optional[Tensor] = None,
            out_shape: Optional[Sequence[int]] = None, bias: Optional[Tensor] = None, act: int = ACT_NONE,
            residual: Optional[Tensor] = None, row_scale: Optional[Tensor] = None, row_shift: Optional[Tensor] = None,
@@ -181,7 +188,7 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
         n_real = out_n if out_f32 is not None else n_total
         m_out = o.numel() // (o.shape[1] if out_f32 is not None else o.shape[-1])
         tag = f"{plan.name} M={m_out} N={n_total} K={plan.k_total} act={act} res={int(residual is not None)} rs={int(row_scale is not None)} rope={int(rope is not None)}"
-        PROFILE.append((tag, 2.0 * m_out * n_real * plan.algo_k, e0, e1))
+        PROFILE.append((tag, 2.0 * m_out * n_real * plan.algo_k, e0, e1, 2.0 * m_out * n_real * _exec_k(plan)))
     _count()
     if gn_sums is not None:
         out._gn_sums = gn_sums
@@ -210,7 +217,7 @@ def attn_fwd(qkv: Tensor, B: int, S: int, C_: int, need_lse: bool = False) -> Tu
     _lib.check(_lib.load().tvae_attn_fwd(qkv.data_ptr(), out.data_ptr(), _ptr(lse), B, S, C_, _stream()), "tvae_attn_fwd")
     if PROFILE is not None:
         e1.record()
-        PROFILE.append(("attn_fwd", 4.0 * B * S * S * C_, e0, e1))
+        PROFILE.append(("attn_fwd", 4.0 * B * S * S * C_, e0, e1, 4.0 * B * S * S * C_))
     _count()
     return out, lse
 
@@ -398,7 +405,8 @@ def mtgemm_wgrad(plan: Plan, a0: Tensor, dz: Tensor, n_total: int, a1: Optional[
     if PROFILE is not None:
         e1.record()
         m_out = dz.numel() // dz.shape[-1]
-        PROFILE.append((f"wgrad {plan.name} M={m_out} N={n_total} K={plan.k_total}", 2.0 * m_out * n_total * plan.algo_k, e0, e1))
+        PROFILE.append((f"wgrad {plan.name} M={m_out} N={n_total} K={plan.k_total}", 2.0 * m_out * n_total * plan.algo_k, e0, e1,
+                        2.0 * m_out * n_total * _exec_k(plan)))
     _count(2)
     return (dw, db) if bias else dw
 
@@ -503,7 +511,7 @@ def attn_bwd(qkv: Tensor, out: Tensor, dout: Tensor, lse: Tensor, rope_tab: Tens
                                  _stream()), "tvae_rope_bwd")
     if PROFILE is not None:
         e1.record()
-        PROFILE.append(("attn_bwd", 10.0 * B * S * S * C_, e0, e1))
+        PROFILE.append(("attn_bwd", 10.0 * B * S * S * C_, e0, e1, 10.0 * B * S * S * C_))
     _count(4)
     return dqkv
 
@@ -544,6 +552,35 @@ def latent_bwd(mu: Tensor, logvar: Tensor, eps: Tensor, dz: Optional[Tensor], dm
                                            _stream()), "tvae_latent_bwd")
     _count()
     return dmu, dlv
+
+
+def dwconv3x3(u: Tensor, w9c: Tensor, bias: Optional[Tensor], flip: bool = False, add_input: bool = True) -> Tensor:
+    """y = [u +] depthwise3x3(u; w9c) [+ bias] on NHWC bf16; w9c fp32 [9, C] (tap-major).  ``flip``: the spatially
+    flipped taps (input gradient of the same layer)."""
+    _need_cuda(u, w9c, bias)
+    assert u.dtype == BF16 and u.is_contiguous() and u.dim() == 4
+    B, H, W, C_ = u.shape
+    assert w9c.dtype == torch.float32 and w9c.is_contiguous() and tuple(w9c.shape) == (9, C_)
+    y = torch.empty_like(u)
+    with _hbm("dwconv3x3", u.numel() * 4):
+        _lib.check(_lib.load().tvae_dwconv3x3(u.data_ptr(), w9c.data_ptr(), _ptr(bias), y.data_ptr(), B, H, W, C_,
+                                              1 if flip else 0, 1 if add_input else 0, _stream()), "tvae_dwconv3x3")
+    _count()
+    return y
+
+
+def dwconv3x3_wgrad(u: Tensor, dy: Tensor, bias: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
+    """(dw fp32 [9, C], db fp32 [C]) of y = u + depthwise3x3(u) + b given dy (both NHWC bf16)."""
+    _need_cuda(u, dy)
+    assert u.dtype == BF16 and dy.dtype == BF16 and u.is_contiguous() and dy.is_contiguous() and u.shape == dy.shape
+    B, H, W, C_ = u.shape
+    dw = torch.empty(9, C_, dtype=torch.float32, device=u.device)
+    db = torch.empty(C_, dtype=torch.float32, device=u.device) if bias else None
+    with _hbm("dwconv3x3_wgrad", u.numel() * 4):
+        _lib.check(_lib.load().tvae_dwconv3x3_wgrad(u.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db), B, H, W, C_,
+                                                    _stream()), "tvae_dwconv3x3_wgrad")
+    _count(3)
+    return dw, db
 
 
 def weight_pack(w: Tensor, fwd: bool = True, dgrad: bool = False) -> Tuple[Optional[Tensor], Optional[Tensor]]:

@@ -274,6 +274,9 @@ class Trainer:
         self._h2d: Optional[torch.cuda.Stream] = None
         self._staged = None             # (host tensor, device copy, ready event) of the prefetched micro-batch
         self._loss_host: Optional[Tensor] = None
+        # optional device-side timing of the step tail (bench.py): a list that receives, per optimiser step, the events
+        # (end of backward, gradients all-reduced, optimiser + zero_grad done)
+        self.timing: Optional[list] = None
 
     def train_step(self, images: Tensor, eps: Optional[Tensor] = None) -> dict:
         """One micro-batch.  Returns the loss dict (device tensors; nothing is synchronised with the host)."""
@@ -291,9 +294,18 @@ class Trainer:
             _set_comm_active(False)
         self._micro += 1
         if last:
+            ev = None
+            if self.timing is not None:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev[0].record()
             self.buckets.wait()
+            if ev is not None:
+                ev[1].record()
             self.opt.step(grad_scale=1.0 / (self.world * self.accum))
             self.buckets.zero_grad()
+            if ev is not None:
+                ev[2].record()
+                self.timing.append(ev)
         return {k: v.detach() for k, v in losses.items()}
 
     # ---- host-to-host step: the reference's `images.to(device, non_blocking=True)` ... `loss.item()` loop ---------

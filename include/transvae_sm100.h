@@ -23,7 +23,7 @@ extern "C" {
 #endif
 
 #define TVAE_ABI_VERSION 4
-#define TVAE_MAX_TAPS 16
+#define TVAE_MAX_TAPS 20
 #define TVAE_MAX_PHASES 4
 
 int tvae_abi_version(void);
@@ -207,6 +207,17 @@ int tvae_loss_bwd(const float* recon, const float* target, const float* mu, cons
 /* Reparameterisation backward: folds the gradients arriving on (z, mu', logvar') back onto (mu, logvar). */
 int tvae_latent_bwd(const float* mu, const float* logvar, const float* eps, const float* dz, const float* dmu_ret,
                     const float* dlv_ret, float* dmu, float* dlogvar, int64_t n, int32_t patched, void* stream);
+
+/* ---- depthwise ConvFFN variant (conv.py:42-50: nn.Conv2d(hidden, hidden, 3, padding=1, groups=hidden); forward
+ * conv.py:89-94 `x_spatial + conv(x_spatial)`) ----------------------------------------------------------------
+ * y = [u +] dwconv3x3(u; w) [+ bias] on NHWC bf16 [B, H, W, C] (C % 8 == 0); w9c fp32 [9][C] (tap k = dy*3 + dx, i.e. the
+ * reference weight [C, 1, 3, 3] transposed), bias fp32 [C] or NULL.  flip != 0 uses tap 8 - k (the input gradient:
+ * du = dy + dwconv3x3(dy; flipped taps)).  HBM-bound stencil: 4 bytes per element.
+ * tvae_dwconv3x3_wgrad: dw fp32 [9][C] and db fp32 [C] (optional) of the same layer, zeroed inside. */
+int tvae_dwconv3x3(const void* u, const float* w9c, const float* bias, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
+                   int32_t flip, int32_t add_input, void* stream);
+int tvae_dwconv3x3_wgrad(const void* u, const void* dy, float* dw9c, float* db, int32_t B, int32_t H, int32_t W, int32_t C,
+                         void* stream);
 
 /* ---- weight-side re-layout (training step) --------------------------------------------------------------------
  * The reference stores nn.Linear weights as [out, in] and nn.Conv2d 3x3 weights as [out, in, 3, 3] fp32

@@ -294,6 +294,11 @@ def conv_ffn(sd: StateDict, p: str, x: Tensor) -> Tensor:
     t = x.flatten(2).transpose(1, 2)
     u = F.gelu(F.linear(t, sd[p + "proj_in.weight"], sd[p + "proj_in.bias"]))
     s = u.transpose(1, 2).reshape(B, -1, H, W)
+    if (p + "conv.weight") in sd:                    # conv_type='depthwise' (conv.py:42-50): one grouped 3x3, no activation
+        c = F.conv2d(s, sd[p + "conv.weight"], sd[p + "conv.bias"], padding=1, groups=s.shape[1])
+        t = (s + c).flatten(2).transpose(1, 2)
+        o = F.linear(t, sd[p + "proj_out.weight"], sd[p + "proj_out.bias"])
+        return o.transpose(1, 2).reshape(B, C, H, W)
     c = F.conv2d(s, sd[p + "conv.0.weight"], sd[p + "conv.0.bias"])
     c = F.gelu(c)
     c = F.conv2d(c, sd[p + "conv.2.weight"], sd[p + "conv.2.bias"], padding=1)
@@ -335,8 +340,8 @@ def resblock(sd: StateDict, p: str, x: Tensor, trace: Optional[dict] = None) -> 
     h = F.conv2d(h, sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=1)
     if trace is not None:
         trace[p + "branch"] = h
-    if (p + "shortcut.weight") in sd:
-        x = F.conv2d(x, sd[p + "shortcut.weight"], sd[p + "shortcut.bias"])
+    if (p + "shortcut.weight") in sd:             # blocks.py:40-46: 1x1, or 3x3 (padding 1) with use_conv_shortcut
+        x = F.conv2d(x, sd[p + "shortcut.weight"], sd[p + "shortcut.bias"], padding=sd[p + "shortcut.weight"].shape[-1] // 2)
     return h + x
 
 

@@ -180,6 +180,31 @@ def main():
     except RuntimeError as e:
         print(f"  use_conv_ffn=False: the reference raises RuntimeError ({str(e)[:60]}...) -- nothing to mirror")
 
+    # module-level variants reachable by constructing the reference's modules directly: ConvFFN(conv_type='depthwise')
+    # (conv.py:42-50) and ResBlock with a convolutional shortcut (blocks.py:40-46), forward and parameter gradients
+    ref_pkg = import_reference(REF_MAIN)
+    conv_mod = importlib.import_module("transvae.modules.conv")
+    blocks_mod = importlib.import_module("transvae.modules.blocks")
+    torch.manual_seed(21)
+    cases = [("ConvFFN depthwise", conv_mod.ConvFFN(128, conv_type="depthwise"), lambda s, t: O.conv_ffn(s, "", t), (2, 128, 8, 8)),
+             ("ResBlock 1x1 shortcut", blocks_mod.ResBlock(64, 128), lambda s, t: O.resblock(s, "", t), (2, 64, 8, 8)),
+             ("ResBlock 3x3 shortcut", blocks_mod.ResBlock(64, 128, use_conv_shortcut=True), lambda s, t: O.resblock(s, "", t),
+              (2, 64, 8, 8))]
+    for name, mod, fn, shape in cases:
+        sdm = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+        xm = torch.randn(*shape, generator=torch.Generator().manual_seed(22))
+        out_r = mod(xm)
+        gout = torch.randn(out_r.shape, generator=torch.Generator().manual_seed(23))
+        out_r.backward(gout)
+        sdg = {k: v.clone().requires_grad_(True) for k, v in sdm.items()}
+        out_o = fn(sdg, xm)
+        out_o.backward(gout)
+        check(name, out_o.detach(), out_r.detach())
+        worst = max(float((sdg[k].grad - p.grad).abs().max()) for k, p in mod.named_parameters())
+        print(f"  {name}: gradient parity over {len(sdm)} tensors max|d|={worst:.3e}")
+        assert worst == 0.0
+    del ref_pkg
+
     # parameter counts and FLOP model vs SURVEY section 6 [measured] numbers
     for v, (f, d), want in [("tiny", (16, 32), 81.9e6), ("large", (16, 32), 1049.2e6), ("giant", (16, 32), 4837.3e6)]:
         n = O.count_params(O.variant_config(v, f, d))["total"]

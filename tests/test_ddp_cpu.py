@@ -48,6 +48,21 @@ def _worker(rank, world, port, out):
         assert torch.allclose(m[0].weight, w_before + 1.0)
         gb.zero_grad()
         assert float(m[0].weight.grad.abs().sum()) == 0.0
+        # a parameter that gets no gradient leaves its bucket incomplete: wait() must still reduce it (no silent
+        # divergence), and rank 1's different initial weights must have been replaced by rank 0's at construction
+        torch.manual_seed(100 + rank)
+        m2 = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.Linear(4, 4))
+        gb2 = GradBuckets(m2.parameters(), bucket_bytes=1 << 20)
+        ref = [torch.empty_like(gb2.flat_p) for _ in range(world)]
+        dist.all_gather(ref, gb2.flat_p)
+        assert torch.equal(ref[0], ref[1])
+        gb2.sync_grads = True
+        y = m2[0](torch.full((1, 4), float(rank + 1)))            # m2[1] unused: its parameters never fire
+        y.sum().backward()
+        assert not gb2._handles
+        gb2.wait()
+        g = m2[0].bias.grad.clone()
+        assert torch.allclose(g, torch.full((4,), 2.0)), g        # 1 (rank 0) + 1 (rank 1): reduced in wait()
     finally:
         dist.destroy_process_group()
 

@@ -56,6 +56,61 @@ def test_trainer_step_matches_reference_optimizer_recipe():
     assert moved > 0
 
 
+def test_eval_after_optimizer_step_uses_the_new_weights():
+    """The fused optimiser rewrites the flat parameter buffer from a raw-pointer kernel (no tensor version bump): packed
+    inference operands cached before the step must not survive it.  eval -> train_step -> eval must change and must
+    equal a fresh model loaded from the trained state_dict."""
+    blob, sd = load_golden("mini_tamed")
+    m = build_model(blob["cfg"], sd)
+    x = blob["x"].cuda()
+    tr = Trainer(m, _loss(), lr=1e-2, grad_clip=1.0)
+    m.eval()
+    with torch.no_grad():
+        before = m.decode(m.encode(x)[0]).clone()
+    tr.train_step(x, eps=blob["eps"].cuda())
+    m.eval()
+    with torch.no_grad():
+        after = m.decode(m.encode(x)[0]).clone()
+    assert float((after - before).abs().max()) > 1e-3
+    fresh = build_model(blob["cfg"], {k: v.detach().cpu() for k, v in m.state_dict().items()})
+    with torch.no_grad():
+        want = fresh.decode(fresh.encode(x)[0])
+    assert torch.equal(after, want)
+    assert tr.opt.step_count == 1 and tr.opt.skipped_steps == 0
+
+
+def test_non_finite_step_is_skipped_on_the_device():
+    blob, sd = load_golden("mini_tamed")
+    m = build_model(blob["cfg"], sd).train()
+    tr = Trainer(m, _loss(), lr=1e-3, grad_clip=1.0, warmup_steps=4)
+    x, eps = blob["x"].cuda(), blob["eps"].cuda()
+    tr.train_step(x, eps=eps)
+    p1 = tr.buckets.flat_p.clone()
+    bad = x.clone()
+    bad[0, 0, 0, 0] = float("nan")
+    tr.train_step(bad, eps=eps)
+    assert torch.equal(tr.buckets.flat_p, p1)
+    assert tr.opt.step_count == 1 and tr.opt.skipped_steps == 1 and abs(tr.opt.current_lr() - 1e-3 / 4) < 1e-12
+    tr.train_step(x, eps=eps)
+    assert tr.opt.step_count == 2 and not torch.equal(tr.buckets.flat_p, p1)
+
+
+def test_host_to_host_train_step_matches_resident():
+    """Trainer.train_step_host (pinned upload on a copy stream, loss terms back through a pinned buffer) == train_step."""
+    blob, sd = load_golden("mini_tamed")
+    x, eps = blob["x"], blob["eps"].cuda()
+    a = Trainer(build_model(blob["cfg"], sd).train(), _loss(), lr=1e-3)
+    b = Trainer(build_model(blob["cfg"], sd).train(), _loss(), lr=1e-3)
+    out = a.train_step(x.cuda(), eps=eps)
+    xh = x.clone().pin_memory()
+    host = b.train_step_host(xh, next_images_host=xh, eps=eps)
+    torch.cuda.synchronize()
+    assert abs(float(host[5]) - float(out["total"])) < 2e-3 and abs(float(host[0]) - float(out["l1"])) < 2e-3
+    host = b.train_step_host(xh, eps=eps)        # consumes the prefetched copy
+    torch.cuda.synchronize()
+    assert float(host[5]) == float(host[5])
+
+
 def test_direct_gradient_accumulation_matches_autograd():
     """Trainer-owned parameters take the fast weight-gradient route (_autograd._wgrad_b: the wgrad kernel accumulates
     straight into the flat gradient slot, packed operands cached per optimizer step, hooks fired by hand).  Two

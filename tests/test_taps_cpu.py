@@ -73,6 +73,28 @@ def test_upsample_conv2_plan():
     close(nchw(out), ref)
 
 
+def test_resblock_conv2_with_conv_shortcut_plan():
+    """blocks.py:40-46, :68: conv2(h) + shortcut(x) in one accumulator, 1x1 and 3x3 shortcut; and the shortcut's input
+    gradient plan (transposed taps)."""
+    Ci, Co = 64, 128
+    h, x = rnd(2, Co, 6, 10), rnd(2, Ci, 6, 10, seed=5)
+    w2, b2 = rnd(Co, Co, 3, 3, seed=1), rnd(Co, seed=2)
+    for k in (1, 3):
+        ws, bs = rnd(Co, Ci, k, k, seed=3), rnd(Co, seed=4)
+        ref = F.conv2d(h, w2, b2, padding=1) + F.conv2d(x, ws, bs, padding=k // 2)
+        plan = T.plan_resblock_conv2(Co, Ci, k)
+        out = emulate(plan, nhwc(h), nhwc(x), T.pack_resblock_conv2(w2, ws), (2, 6, 10, Co), (b2 + bs)[None])
+        close(nchw(out), ref)
+        assert plan.k_total == 9 * Co + k * k * Ci and len(plan.phases[0]) == 9 + k * k <= 20
+        # input gradient of the shortcut: dX = conv_transpose(dZ, ws)
+        dz = rnd(2, Co, 6, 10, seed=6)
+        xg = x.clone().requires_grad_(True)
+        F.conv2d(xg, ws, None, padding=k // 2).backward(dz)
+        wd = T.pack_conv3x3_dgrad(ws) if k == 3 else ws.reshape(Co, Ci).t()
+        dx = emulate(T.plan_conv_kxk_dgrad(Co, k), nhwc(dz), None, wd, (2, 6, 10, Ci))
+        close(nchw(dx), xg.grad)
+
+
 def test_whole_upsample_and_downsample_vs_oracle():
     cfg = dict(depths=[1, 1, 1, 1, 1], base_dims=[64, 64, 64, 128, 128])
     sd = O.init_state_dict(cfg, seed=4, mode="tamed")

@@ -41,7 +41,7 @@ prof, ops.PROFILE = ops.PROFILE, None
 print(f"{variant} micro-batch {mb}: {ms:.1f} ms/step -> {mb / ms * 1e3:.1f} img/s fwd+bwd+opt; launches/step {(ops.LAUNCHES - n0) // steps}; "
       f"model TFLOP/s {mb / ms * 1e3 * 6187.8 / 1e3:.0f}", flush=True)
 tab = {}
-for name, fl, a, b in prof:
+for name, fl, a, b, *_ in prof:
     key = name.split(" M=")[0]
     d = tab.setdefault(key, [0.0, 0.0, 0])
     d[0] += a.elapsed_time(b); d[1] += fl; d[2] += 1
