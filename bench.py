@@ -249,18 +249,18 @@ def cpu_reference_rate(cfg: dict, steps: int, warmup: int):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    what = "forward + L1/KL loss + backward (patched semantics)" if train else "encode + decode"
-    sample = (f"{'unmodified reference package (baseline/_ref)' if kind == 'reference' else 'oracle port'}, fp32 torch CPU, "
-              f"{variant} f16d32 {what}, batch 1 at {res}^2 per step, {warmup} warm-up + {steps} timed")
+    what = "fwd+loss+bwd (patched)" if train else "encode+decode"
+    sample = (f"{'unmodified reference (baseline/_ref)' if kind == 'reference' else 'oracle port'}, fp32 CPU, {what}, "
+              f"batch 1 @{res}^2 per step, {warmup}+{steps} steps")
     return steps / dt, dt / steps * 1e3, torch.get_num_threads(), kind, sample
 
 
 def workload_string(name: str, cfg: dict) -> str:
     if cfg["kind"] == "train":
-        return (f"TransVAE-{cfg['variant']} f16d32 stage-1 training fwd+bwd (L1+KL), global batch {cfg['global_batch']} at "
-                f"{cfg['res']}^2, batch-sharded DDP (BASELINE configs[{cfg['baseline_cfg']}])")
-    return (f"TransVAE-{cfg['variant']} f16d32 encode+decode inference at {cfg['res']}^2, batch {cfg['batch']}/GPU, "
-            f"batch-sharded (BASELINE configs[{cfg['baseline_cfg']}])")
+        return (f"TransVAE-{cfg['variant']} f16d32 train fwd+bwd (L1+KL), global batch {cfg['global_batch']} @{cfg['res']}^2, "
+                f"DDP (BASELINE configs[{cfg['baseline_cfg']}])")
+    return (f"TransVAE-{cfg['variant']} f16d32 encode+decode @{cfg['res']}^2, batch {cfg['batch']}/GPU "
+            f"(BASELINE configs[{cfg['baseline_cfg']}])")
 
 
 def metric_name(cfg: dict) -> str:
@@ -288,7 +288,7 @@ def run_reference(args, cfg, rank):
 def stock_torch_leg(cfg: dict, dev) -> dict:
     sys.path.insert(0, os.path.join(ROOT, "baseline"))
     import reference_runner as R
-    out = {"what": "unmodified reference package on this GPU, torch bf16 autocast (cuDNN / cuBLAS / SDPA), fused AdamW"}
+    out = {}        # the unmodified reference package on this GPU: torch bf16 autocast (cuDNN / cuBLAS / SDPA), fused AdamW
     if not R.available(True):
         return {"unavailable": "baseline/_ref not installed"}
     torch.backends.cudnn.benchmark = True
@@ -319,7 +319,7 @@ def stock_torch_leg(cfg: dict, dev) -> dict:
                 mu, _ = model.encode(x)
                 model.decode(mu)
         ms = timed(infer, 2, 3)
-        out["infer"] = {"value": round(B / ms * 1e3, 2), "unit": UNIT, "ms": round(ms, 2), "batch": B}
+        out["infer"] = {"value": round(B / ms * 1e3, 2), "ms": round(ms, 1), "batch": B}
         model.train()
         loss_fn = pkg.TransVAELoss(l1_weight=1.0, lpips_weight=0.0, kl_weight=1e-8, vf_weight=0.0, gan_weight=0.0).to(dev)
         opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0, fused=True)
@@ -335,7 +335,7 @@ def stock_torch_leg(cfg: dict, dev) -> dict:
             opt.step()
             opt.zero_grad(set_to_none=True)
         ms = timed(train, 2, 3)
-        out["train"] = {"value": round(Bt / ms * 1e3, 2), "unit": UNIT, "ms": round(ms, 2), "batch": Bt}
+        out["train"] = {"value": round(Bt / ms * 1e3, 2), "ms": round(ms, 1), "batch": Bt}
     except Exception as e:  # noqa: BLE001  (OOM or a missing cuDNN path must not kill the bench line)
         out["error"] = f"{type(e).__name__}: {str(e)[:160]}"
     finally:
@@ -413,10 +413,9 @@ def roofline_of(prof, per, step_ms, pk):
     ach = fl / (t * 1e-3) / 1e12 if t > 0 else 0.0
     ach_ex = ex / (t * 1e-3) / 1e12 if t > 0 else 0.0
     traffic, src = traffic_capture()
-    return {"bound": "tensor", "kernel": "tvae::mtgemm2_kernel/mtgemm_kernel (all conv/linear fwd+dgrad launches)",
+    return {"bound": "tensor", "kernel": "tvae::mtgemm2_kernel (conv/linear fwd+dgrad)",
             "achieved": round(ach, 1), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops"], 4),
-            "frac_executed": round(ach_ex / pk["tflops"], 4), "traffic": traffic, "traffic_src": src,
-            "peak_src": pk["src"], "launches": n / per, "ms_in_kernel": round(t / per, 2),
+            "frac_executed": round(ach_ex / pk["tflops"], 4), "traffic": traffic,
             "share_of_step": round(t / per / step_ms, 3) if step_ms else None}
 
 
@@ -473,9 +472,9 @@ def run_train(C: Ctx, name: str, cfg: dict) -> dict:
     tr.timing = None
     comm = None
     if tail:
-        comm = {"grad_comm": args.grad_comm, "payload_gb": round(tr.buckets.numel * (2 if tr.buckets.comm_g is not None else 4) / 1e9, 2),
-                "buckets": len(tr.buckets.buckets), "exposed_allreduce_tail_ms": round(tail[-1][0].elapsed_time(tail[-1][1]), 3),
-                "optimizer_ms": round(tail[-1][1].elapsed_time(tail[-1][2]), 3)}
+        comm = {"payload_gb": round(tr.buckets.numel * (2 if tr.buckets.comm_g is not None else 4) / 1e9, 2),
+                "buckets": len(tr.buckets.buckets), "exposed_tail_ms": round(tail[-1][0].elapsed_time(tail[-1][1]), 2),
+                "optimizer_ms": round(tail[-1][1].elapsed_time(tail[-1][2]), 2)}
     reps = min(accum, 2)
     tr._micro = 0          # profile plain micro-steps (no optimiser step inside: accumulation position 0 ..)
     prof, hbm = C.profiled(lambda: [tr.train_step(xs[i]) for i in range(reps)] if accum > reps else step_resident(), 1)
@@ -500,21 +499,18 @@ def run_train(C: Ctx, name: str, cfg: dict) -> dict:
         ms_e, _ = C.timed(step_host, args.steps)
         e2e = {"value": round(imgs / (ms_e / args.steps) * 1e3, 2), "unit": UNIT,
                "h2d_bytes_per_step": accum * mb * 3 * res * res * 4, "d2h_bytes_per_step": accum * 6 * 4,
-               "ms_per_step": round(ms_e / args.steps, 2),
-               "api": "transvae.trainer.Trainer.train_step_host (pinned micro-batch in, loss terms out)"}
+               "ms_per_step": round(ms_e / args.steps, 2), "api": "Trainer.train_step_host"}
 
     gf3 = 3.0 * algo_gf
     line = {
         "metric": metric_name(cfg), "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": round(ms_step, 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": workload_string(name, cfg), "global_batch": imgs, "per_gpu_batch": mb * accum, "micro_batch": mb,
-                   "accumulation": accum, "parallelism": f"dp{world}", "grad_comm": args.grad_comm,
-                   "checkpointing": bool(args.checkpointing),
-                   "l2_policy": "activations of a micro-step (>10 GB) exceed the 126 MB L2; no flush needed",
-                   "gflop_per_image_fwd_bwd": round(gf3, 1)},
-        "model_tflops": round(value * gf3 / 1e3, 1), "model_frac_of_peak": round(value * gf3 / 1e3 / (C.pk["tflops"] * world), 4),
-        "loss": round(loss, 5), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+        "config": {"workload": workload_string(name, cfg), "global_batch": imgs, "micro_batch": mb, "accumulation": accum,
+                   "parallelism": f"dp{world}", "grad_comm": args.grad_comm, "l2": "working set per step >> 126 MB L2, no flush",
+                   "gflop_per_image": round(gf3, 1), **({"checkpointing": True} if args.checkpointing else {})},
+        "model_frac_of_peak": round(value * gf3 / 1e3 / (C.pk["tflops"] * world), 4),
+        "loss": round(loss, 4), "mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
         "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "comm": comm,
     }
     extra = {"tensor_kernels": ctab, "hbm_kernels": htab, "shapes": stab, "profiled_micro_step_kernel_ms": round(micro_ms, 2)}
@@ -573,16 +569,15 @@ def run_infer(C: Ctx, name: str, cfg: dict, steps: int, warmup: int, e2e_on: boo
         pipe.synchronize()
         e2e = {"value": round(B * world / (ms_e / steps) * 1e3, 2), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": round(ms_e / steps, 2),
-               "api": "transvae.streaming.StreamedReconstructor.reconstruct (pinned host in / out)"}
+               "api": "StreamedReconstructor.reconstruct"}
     line = {
         "metric": metric_name(cfg), "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": W,
         "ms_per_step": round(ms_step, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": workload_string(name, cfg), "per_gpu_batch": B, "resolution": R,
                    "parallelism": f"batch-sharded x{world}, no collective",
-                   "l2_policy": "activations per step (>2 GB) exceed the 126 MB L2; no flush needed",
-                   "gflop_per_image": round(algo_gf, 1)},
-        "model_tflops": round(value * algo_gf / 1e3, 1), "model_frac_of_peak": round(value * algo_gf / 1e3 / (C.pk["tflops"] * world), 4),
+                   "l2": "working set per step >> 126 MB L2, no flush", "gflop_per_image": round(algo_gf, 1)},
+        "model_frac_of_peak": round(value * algo_gf / 1e3 / (C.pk["tflops"] * world), 4),
         "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
     }
     extra = {"tensor_kernels": ctab, "hbm_kernels": hbm_table(hbm, 2, C.pk), "shapes": stab}
@@ -603,9 +598,9 @@ def run_ours(args, name, cfg, rank, world, local):
     if legs and name == "train256":
         # secondary legs, N = 1 only: BASELINE configs[1] on our kernels, stock torch on the same GPU, the CPU reference
         il, ie = run_infer(C, "infer256", CONFIGS["infer256"], 5, 3)
-        line["infer"] = {"metric": il["metric"], "value": il["value"], "ms_per_step": il["ms_per_step"],
-                         "e2e": il["e2e"]["value"] if il["e2e"] else None, "model_frac_of_peak": il["model_frac_of_peak"],
-                         "mtgemm_frac": il["roofline"]["frac"], "attn_fwd_frac": il["roofline"]["attn_fwd_frac"], "batch": 64}
+        line["infer"] = {"metric": il["metric"], "value": il["value"], "e2e": il["e2e"]["value"] if il["e2e"] else None,
+                         "model_frac": il["model_frac_of_peak"], "mtgemm_frac": il["roofline"]["frac"],
+                         "attn_fwd_frac": il["roofline"]["attn_fwd_frac"], "batch": 64}
         extra["infer"] = ie
         line["gpu_stock_torch"] = stock_torch_leg(cfg, C.dev)
     if legs:
