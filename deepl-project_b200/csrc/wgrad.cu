@@ -12,6 +12,7 @@
 #include <cstdlib>
 
 #include "../../include/transvae_sm100.h"
+#include "cluster2.cuh"
 #include "common.cuh"
 #include "tmap.cuh"
 
@@ -214,6 +215,203 @@ mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 }
 
 // -------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for layers whose output-channel count is a multiple of 256 and whose taps cover
+// multiples of KT2 (256 / 128) input channels: every 768- / 1536-wide linear and 3x3 convolution of the Transformer
+// stages.  The 1-CTA kernel above pulls 2 dZ boxes + KT / 64 A boxes from L2 per 128-pixel step for a 128 x KT block
+// (87 flop per byte at KT = 256) and is bound by the L2 -> SM path (ncu: 13.4 TB/s, 7.5x the DRAM traffic).  Here two
+// CTAs of a cluster own a 256 (n) x KT2 (k) block: CTA r loads the dZ boxes of ITS 128 n channels (its half of the MMA
+// M dimension) and only HALF of the A boxes (KT2 / 2 k channels: its half of the MMA N dimension); the leader's
+// tcgen05.mma.cta_group::2 (M = 256, N = KT2) reads both halves across the pair -- 131 flop per byte at KT2 = 256, the
+// ratio of the forward pair kernel.  Protocol as mtgemm2.cu: both producers complete on the LEADER's full[s], the
+// leader's commit is multicast to empty[s] of both CTAs, each CTA drains its own accumulator rows.
+// -------------------------------------------------------------------------------------------------
+template <int KT2>
+struct Wg2Cfg {
+  static constexpr int kABoxes = KT2 / 128;                         // per CTA
+  static constexpr int kStageBytes = (2 + kABoxes) * kWgTile;       // per CTA
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 4 ? 4 : (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = KT2 + 16 <= 128 ? 128 : (KT2 + 16 <= 256 ? 256 : 512);
+  static constexpr int kOnesBytes = 2048;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOnesBytes + 1024 + 256;
+};
+
+template <int KT2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+mtwgrad2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ WgParams P) {
+#ifdef TVAE_DEVICE_OK
+  using Cfg = Wg2Cfg<KT2>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_ones = smem + STAGES * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ones + Cfg::kOnesBytes);
+  uint64_t* full = bars;                   // [STAGES] (the leader's are used)
+  uint64_t* empty = bars + STAGES;         // [STAGES] (each CTA's own)
+  uint64_t* acc_full = bars + 2 * STAGES;  // each CTA's own
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmDZ);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (P.db != nullptr) {
+    for (int i = threadIdx.x; i < Cfg::kOnesBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3f803f80u;
+    fence_proxy_async_smem();
+  }
+  cluster_sync_all();   // both CTAs' barriers (and ones blocks) exist before any cross-CTA completion / MMA
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(static_cast<uint32_t>(Cfg::kTmemCols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- work item of this CTA pair: (tap, k tile of KT2, n tile of 256) x pixel split
+  const int cluster_id = blockIdx.x >> 1;
+  const int split = cluster_id % P.splits;
+  int item = cluster_id / P.splits;
+  const int n_tiles2 = P.n_total / 256;
+  int ti = 0, kt = 0, nt = 0;
+  for (; ti < P.ntaps; ++ti) {
+    const int cnt = (P.taps[ti].kblocks * 64 / KT2) * n_tiles2;
+    if (item < cnt) {
+      kt = item / n_tiles2;
+      nt = item % n_tiles2;
+      break;
+    }
+    item -= cnt;
+  }
+  const WgTap tap = P.taps[ti];
+  const bool do_bias = P.db != nullptr && kt == 0 && ti == P.first_tap[tap.ph];
+  const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
+  const int my_tiles = (m_tiles - split + P.splits - 1) / P.splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* mapA = tap.map ? &tmA1 : &tmA0;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int m_t = split + i * P.splits;
+        const int w0 = (m_t % P.tiles_w) * P.tw;
+        const int h0 = ((m_t / P.tiles_w) % P.tiles_h) * P.th;
+        const int b0 = (m_t / (P.tiles_w * P.tiles_h)) * P.nb;
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+        uint8_t* s = smem + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)         // this CTA's half of the M dimension: 128 of the 256 n channels
+          tma2_load_5d(s + j * kWgTile, &tmDZ, &full[stage], P.out_c_off[tap.ph] + nt * 256 + (int)rank * 128 + j * 64, w0,
+                       P.out_p[tap.ph], h0, b0);
+#pragma unroll
+        for (int j = 0; j < Cfg::kABoxes; ++j)   // this CTA's half of the N dimension: KT2 / 2 of the k channels
+          tma2_load_5d(s + (2 + j) * kWgTile, mapA, &full[stage], tap.c_off + kt * KT2 + (int)rank * (KT2 / 2) + j * 64,
+                       w0 + tap.dw, tap.p, h0 + tap.dh, b0);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, KT2, 1, 1);
+      constexpr uint32_t idesc_ones = umma_idesc_bf16(256, 16, 1, 1);
+      const uint64_t ones_desc = umma_desc_mnmajor_sw128(smem_u32(s_ones), kWgTile, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t dz_base = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t a_base = dz_base + 2 * kWgTile;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // 16 pixels per MMA
+          umma2_f16(tmem_base, umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024),
+                    umma_desc_mnmajor_sw128(a_base + k * 2048, kWgTile, 1024), idesc, (i | k) != 0);
+        if (do_bias) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma2_f16(tmem_base + KT2, umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024), ones_desc, idesc_ones,
+                      (i | k) != 0);
+        }
+        umma2_commit_mc(&empty[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma2_commit_mc(acc_full);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int n = nt * 256 + (int)rank * 128 + q * 32 + lane;     // this CTA's accumulator rows
+    if (my_tiles > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      float* dst = P.dw + (size_t)n * P.k_total + tap.wk_off + kt * KT2;
+#pragma unroll 1
+      for (int c = 0; c < KT2 / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float4 f = make_float4(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1]),
+                                 __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
+          atomicAdd(reinterpret_cast<float4*>(dst + c * 32 + g * 4), f);
+        }
+      }
+      if (do_bias) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + KT2, v);
+        tmem_ld_wait();
+        atomicAdd(P.db + (size_t)tap.ph * P.n_total + n, __uint_as_float(v[0]));
+      }
+    }
+  }
+  // the peer's smem / barriers / TMEM are touched by the leader's MMAs and multicast commits until the very end
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(Cfg::kTmemCols))
+                 : "memory");
+  }
+#endif
+}
+
+template <int KT2>
+static int launch_wg2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& dz, const WgParams& P, int grid,
+                      cudaStream_t stream) {
+  using Cfg = Wg2Cfg<KT2>;
+  static bool configured = false;
+  if (!configured) {
+    TVAE_CHECK_CUDA(cudaFuncSetAttribute(mtwgrad2_kernel<KT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  mtwgrad2_kernel<KT2><<<grid, 256, Cfg::kSmemBytes, stream>>>(a0, a1, dz, P);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
 // Transposed variant for layers whose output-channel count is not a multiple of 128 (N = 64, 192: the ResBlock /
 // Downsample / Upsample convolutions at 192 channels and the 64-wide heads).
 //
@@ -401,6 +599,223 @@ mtwgrad_t_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #endif
 }
 
+// -------------------------------------------------------------------------------------------------
+// Halo variant of the transposed kernel for plain 3x3 stride-1 convolutions on maps at least 128 pixels wide (the
+// N = 192 ResBlock / Downsample / Upsample convolutions at 256^2 and 128^2, and the 64-wide output convolution): a pixel
+// tile is 128 pixels of ONE image row, so the three dx taps of a kernel row read A tiles that overlap in 127 of 128 pixels.
+// The transposed kernel above loads each (tap, 64-channel chunk) as its own [128 x 64] box -- NT / 64 dZ boxes + 2 A boxes
+// per 128 x 128 x NT step (77 flop per byte at NT = 192), and every tap's CTA re-loads the same dZ tile (ncu: 12.1 GB of
+// L2 -> SM traffic for 1.6 GB of DRAM reads).  Here a "slot" is (kernel row dy, 64-channel chunk, dx); a CTA owns FOUR
+// consecutive slots = two full-width M = 128 MMAs per 16 pixels into two accumulators, and loads per step the dZ boxes
+// ONCE plus at most two 130-pixel halo tiles [w0 - 1, w0 + 129) of the (dy, chunk) groups its slots belong to -- 155
+// flop per byte.  The two 64-row halves of an MMA's A operand are (halo tile, pixel-row offset dx) pairs: in the
+// MN-major SWIZZLE_128B layout a pixel row is 128 bytes, so a tap is a start address dx rows into the tile and the
+// second half is reached through the descriptor's leading-dimension byte offset -- 128 B for the next tap of the same
+// tile, or the distance to the other tile / the block of ones (bias gradient).  The swizzle is a function of the absolute
+// shared-memory address (descriptor base offset 0): tools/experiments/umma_row_offset_mn.cu, umma_lbo_offset_mn.cu.
+// -------------------------------------------------------------------------------------------------
+constexpr int kWgHaloTx = 130 * 64 * 2;                         // bytes one halo load delivers
+constexpr int kWgHaloBytes = (kWgHaloTx + 1023) / 1024 * 1024;  // its shared-memory slot (17408)
+
+template <int NT>
+struct WghCfg {
+  static constexpr int kDzBytes = (NT / 64) * kWgTile;
+  static constexpr int kStageBytes = kDzBytes + 2 * kWgHaloBytes;
+  static constexpr int kStages = (200 * 1024 - kWgTile) / kStageBytes > 4 ? 4 : (200 * 1024 - kWgTile) / kStageBytes;
+  static constexpr int kTmemCols = 2 * NT <= 128 ? 128 : (2 * NT <= 256 ? 256 : 512);
+  static constexpr int kOnesBytes = kWgTile + 1024;   // ones for 128 pixels (+ slack: the peer half may start dx rows in)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOnesBytes + 1024 + 128;
+};
+
+struct WghSlot {
+  int group;   // (dy * kb + chunk), or -1: ones (bias gradient), -2: empty
+  int dx;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(256, 1)
+mtwgrad_h_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmDZ,
+                 const __grid_constant__ WgParams P) {
+#ifdef TVAE_DEVICE_OK
+  using Cfg = WghCfg<NT>;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr int kDzChunks = NT / 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_ones = smem + STAGES * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ones + Cfg::kOnesBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* acc_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmAh);
+    tma_prefetch_desc(&tmDZ);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  if (P.db != nullptr) {
+    for (int i = threadIdx.x; i < Cfg::kOnesBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3f803f80u;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- work item: four consecutive slots x pixel split.  Slot s < 9 * kb: group s / 3 = (dy, chunk), dx = s % 3;
+  // slot 9 * kb: the block of ones (when the bias gradient is wanted); beyond: empty.
+  const int kb = P.taps[0].kblocks;
+  const int n_tap_slots = 9 * kb;
+  const int split = blockIdx.x % P.splits;
+  const int item = blockIdx.x / P.splits;
+  WghSlot sl[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int s = 4 * item + j;
+    if (s < n_tap_slots) sl[j] = WghSlot{s / 3, s % 3};
+    else if (s == n_tap_slots && P.db != nullptr) sl[j] = WghSlot{-1, 0};
+    else sl[j] = WghSlot{-2, 0};
+  }
+  // the (at most two) halo tiles of this item: groups g0 <= g1
+  const int g0 = sl[0].group;                         // slot 4 * item is always a tap slot or the ones slot
+  int g1 = g0;
+#pragma unroll
+  for (int j = 1; j < 4; ++j)
+    if (sl[j].group >= 0 && sl[j].group != g0) g1 = sl[j].group;
+  const int n_tiles_a = g0 < 0 ? 0 : (g1 != g0 ? 2 : 1);
+  const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
+  const int my_tiles = (m_tiles - split + P.splits - 1) / P.splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int m_t = split + i * P.splits;
+        const int w0 = (m_t % P.tiles_w) * P.tw;
+        const int h0 = ((m_t / P.tiles_w) % P.tiles_h) * P.th;
+        const int b0 = (m_t / (P.tiles_w * P.tiles_h)) * P.nb;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], Cfg::kDzBytes + n_tiles_a * kWgHaloTx);
+        uint8_t* s = smem + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int j = 0; j < kDzChunks; ++j)
+          tma_load_5d(s + j * kWgTile, &tmDZ, &full[stage], P.out_c_off[0] + j * 64, w0, P.out_p[0], h0, b0);
+        for (int a = 0; a < n_tiles_a; ++a) {
+          const int g = a == 0 ? g0 : g1;
+          const int dy = g / kb, chunk = g % kb;
+          tma_load_5d(s + Cfg::kDzBytes + a * kWgHaloBytes, &tmAh, &full[stage], P.taps[dy * 3].c_off + chunk * 64, w0 - 1, 0,
+                      h0 + P.taps[dy * 3].dh, b0);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 1, 1);
+      constexpr uint64_t bo_mask = ~(uint64_t(7) << 49);     // descriptor base offset 0: swizzle on absolute addresses
+      const bool second = sl[2].group != -2;                 // slots 2 / 3 exist
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t dz_base = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t t_base = dz_base + Cfg::kDzBytes;
+        uint32_t addr[4] = {dz_base, dz_base, dz_base, dz_base};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (sl[j].group >= 0) addr[j] = t_base + (sl[j].group == g0 ? 0 : kWgHaloBytes) + sl[j].dx * 128;
+          else if (sl[j].group == -1) addr[j] = smem_u32(s_ones);
+          else if (j & 1) addr[j] = addr[j - 1];              // empty second half: repeat the first (rows ignored)
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // 16 pixels per MMA
+          umma_f16(tmem_base, umma_desc_mnmajor_sw128(addr[0] + k * 2048, addr[1] - addr[0], 1024) & bo_mask,
+                   umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024), idesc, (i | k) != 0);
+        if (second) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_f16(tmem_base + NT, umma_desc_mnmajor_sw128(addr[2] + k * 2048, addr[3] - addr[2], 1024) & bo_mask,
+                     umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024), idesc, (i | k) != 0);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                 // accumulator row: slot (row / 64) of the MMA, channel row % 64
+    if (my_tiles > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int a = 0; a < 2; ++a) {
+        const WghSlot s = sl[2 * a + (row >> 6)];
+        float* dst = nullptr;
+        size_t stride = 0;
+        if (s.group >= 0) {                        // dW[n][wk_off(dy, dx) + chunk * 64 + c]
+          const int dy = s.group / kb, chunk = s.group % kb;
+          dst = P.dw + P.taps[dy * 3 + s.dx].wk_off + chunk * 64 + (row & 63);
+          stride = (size_t)P.k_total;
+        } else if (s.group == -1 && (row & 63) == 0) {   // all 64 rows of the ones slot hold the same column sums
+          dst = P.db;
+          stride = 1;
+        }
+        if (sl[2 * a].group == -2) continue;       // this accumulator was never written (warp-uniform)
+#pragma unroll 1
+        for (int c = 0; c < NT / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * NT + c * 32, v);
+          tmem_ld_wait();
+          if (dst != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)(c * 32 + j) * stride, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+#endif
+}
+
+template <int NT>
+static int launch_wgh(const CUtensorMap& ah, const CUtensorMap& dz, const WgParams& P, int grid, cudaStream_t stream) {
+  using Cfg = WghCfg<NT>;
+  static bool configured = false;
+  if (!configured) {
+    TVAE_CHECK_CUDA(cudaFuncSetAttribute(mtwgrad_h_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  mtwgrad_h_kernel<NT><<<grid, 256, Cfg::kSmemBytes, stream>>>(ah, dz, P);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int NT>
 static int launch_wgt(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& dz, const WgParams& P, int grid,
                       cudaStream_t stream) {
@@ -481,8 +896,24 @@ int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, float* db, cudaStream_t st
   // N = 64 / 192: transposed kernel (no half-empty 128-row tiles); everything else: n channels on the M dimension
   static const bool allow_t = !(getenv("TVAE_WGRAD_T") && atoi(getenv("TVAE_WGRAD_T")) == 0);
   const bool transposed = allow_t && (d->n_total == 64 || d->n_total == 192);
+  // plain 3x3 stride-1 convolution on a map at least 128 pixels wide: halo variant of the transposed kernel (four
+  // (kernel row, chunk, dx) slots per CTA on one dZ tile and <= 2 halo tiles); TVAE_WGRAD_HALO=0: A/B switch
+  static const bool allow_h = !(getenv("TVAE_WGRAD_HALO") && atoi(getenv("TVAE_WGRAD_HALO")) == 0);
+  bool halo = allow_h && transposed && P.tw == 128 && d->num_phases == 1 && d->ntaps[0] == 9 && !d->a0.split && !d->out.split &&
+              d->out_c_off[0] == 0;
+  for (int t = 0; halo && t < 9; ++t) {
+    const tvae_tap& tp = d->taps[0][t];
+    halo = tp.map == 0 && tp.p == 0 && tp.c_off == 0 && tp.dw == t % 3 - 1 && tp.dh == d->taps[0][t - t % 3].dh &&
+           tp.kblocks == d->taps[0][0].kblocks && tp.kblocks * 64 == d->a0.C;
+  }
+  // n_total a multiple of 256 and every tap a multiple of 256 input channels: CTA-pair kernel; TVAE_WGRAD_PAIR=0: A/B switch
+  static const bool allow_p = !(getenv("TVAE_WGRAD_PAIR") && atoi(getenv("TVAE_WGRAD_PAIR")) == 0);
+  bool pair = allow_p && !transposed && d->n_total % 256 == 0;
+  for (int i = 0; pair && i < nt; ++i) pair = (P.taps[i].kblocks * 64) % 256 == 0;
   long long items = 0;
-  if (transposed) {
+  if (halo) {
+    items = (9LL * d->taps[0][0].kblocks + (db != nullptr ? 1 : 0) + 3) / 4;
+  } else if (transposed) {
     for (int ph = 0; ph < d->num_phases; ++ph) {
       int chunks = db != nullptr ? 1 : 0;
       const int t_end = ph + 1 < d->num_phases ? P.first_tap[ph + 1] : nt;
@@ -490,12 +921,15 @@ int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, float* db, cudaStream_t st
       P.items_per_phase[ph] = (chunks + 1) / 2;
       items += P.items_per_phase[ph];
     }
+  } else if (pair) {
+    for (int i = 0; i < nt; ++i) items += (long long)(P.taps[i].kblocks * 64 / 256) * (d->n_total / 256);
   } else {
     for (int i = 0; i < nt; ++i) items += (long long)(P.taps[i].kblocks * 64 / kt) * P.n_tiles;
   }
   const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
   int sms = persistent_sms();
   if (sms <= 0) sms = 148;
+  if (pair) sms /= 2;          // work items are CTA pairs: one cluster per TPC
   // pixel splits ("split-K over pixels"): fill (at most) two full waves of CTAs -- rounding DOWN so the last wave is
   // not nearly empty -- and keep at least ~4 pixel tiles per CTA so the TMEM drain + atomics are amortised
   long long splits = (2LL * sms) / items;
@@ -519,22 +953,30 @@ int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, float* db, cudaStream_t st
     }
   }
   P.splits = (int)splits;
-  const long long grid = items * splits;
+  const long long grid = items * splits * (pair ? 2 : 1);
   TVAE_REQUIRE(grid < (1LL << 31), "wgrad: grid too large");
 
   CUtensorMap mA0, mA1, mDZ;
   int rc;
-  if ((rc = make_tmap_pix(&mA0, d->a0.ptr, d->a0.B, d->a0.H, d->a0.W, d->a0.C, d->a0.split, P.tw, P.th, P.nb))) return rc;
+  if (halo) {
+    if ((rc = make_tmap_pix_halo(&mA0, d->a0.ptr, d->a0.B, d->a0.H, d->a0.W, d->a0.C))) return rc;
+  } else if ((rc = make_tmap_pix(&mA0, d->a0.ptr, d->a0.B, d->a0.H, d->a0.W, d->a0.C, d->a0.split, P.tw, P.th, P.nb))) {
+    return rc;
+  }
   if (d->a1.ptr) {
     if ((rc = make_tmap_pix(&mA1, d->a1.ptr, d->a1.B, d->a1.H, d->a1.W, d->a1.C, d->a1.split, P.tw, P.th, P.nb))) return rc;
   } else {
     mA1 = mA0;
   }
   if ((rc = make_tmap_pix(&mDZ, d->out.ptr, d->out.B, d->out.H, d->out.W, d->out.C, d->out.split, P.tw, P.th, P.nb))) return rc;
+  if (halo) {
+    return d->n_total == 192 ? launch_wgh<192>(mA0, mDZ, P, (int)grid, stream) : launch_wgh<64>(mA0, mDZ, P, (int)grid, stream);
+  }
   if (transposed) {
     return d->n_total == 192 ? launch_wgt<192>(mA0, mA1, mDZ, P, (int)grid, stream)
                              : launch_wgt<64>(mA0, mA1, mDZ, P, (int)grid, stream);
   }
+  if (pair) return launch_wg2<256>(mA0, mA1, mDZ, P, (int)grid, stream);
   switch (kt) {
     case 256: return launch_wg<256>(mA0, mA1, mDZ, P, (int)grid, stream);
     case 192: return launch_wg<192>(mA0, mA1, mDZ, P, (int)grid, stream);

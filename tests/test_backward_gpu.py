@@ -43,7 +43,9 @@ def grads(fn, inputs, dout):
     return [t.grad for t in inputs]
 
 
-@pytest.mark.parametrize("M,K,N", [(1000, 128, 192), (4096, 384, 1536), (300, 1536, 256), (8192, 64, 64), (77, 256, 320)])
+@pytest.mark.parametrize("M,K,N", [(1000, 128, 192), (4096, 384, 1536), (300, 1536, 256), (8192, 64, 64), (77, 256, 320),
+                                   # N and K multiples of 256: the CTA-pair weight-gradient kernel (many / few pixel tiles)
+                                   (2048, 768, 768), (1000, 1536, 512), (512, 256, 256), (20000, 256, 1024)])
 def test_linear_backward(M, K, N):
     x, w, dz = bf(rnd(M, K)), bf(rnd(N, K, seed=1, scale=0.05)), bf(rnd(M, N, seed=2))
     gx, gw = grads(lambda x, w: x @ w.t(), [x, w], dz)
@@ -57,7 +59,12 @@ def test_linear_backward(M, K, N):
     assert db.shape == (1, N) and rel(db[0], dz.float().sum(0)) < 1e-4, rel(db[0], dz.float().sum(0))
 
 
-@pytest.mark.parametrize("B,C,H,W,N", [(2, 64, 16, 16, 64), (1, 192, 128, 128, 192), (3, 128, 32, 32, 256), (2, 64, 8, 8, 128)])
+@pytest.mark.parametrize("B,C,H,W,N", [(2, 64, 16, 16, 64), (1, 192, 128, 128, 192), (3, 128, 32, 32, 256), (2, 64, 8, 8, 128),
+                                       # maps >= 128 pixels wide, N = 192 / 64: halo weight-gradient kernel -- two tiles per row,
+                                       # a clipped second tile (W = 160), 1 / 2 / 3 chunks (10 / 19 / 28 slots incl. the bias slot)
+                                       (2, 192, 8, 256, 192), (1, 64, 4, 160, 64), (1, 128, 2, 128, 192), (2, 64, 3, 128, 192),
+                                       # C and N multiples of 256: CTA-pair kernel with nine taps
+                                       (2, 256, 16, 16, 256), (1, 512, 8, 8, 768)])
 def test_conv3x3_backward(B, C, H, W, N):
     x, w, dz = bf(rnd(B, C, H, W)), bf(rnd(N, C, 3, 3, seed=1, scale=0.05)), bf(rnd(B, N, H, W, seed=2))
     gx, gw = grads(lambda x, w: F.conv2d(x, w, padding=1), [x, w], dz)
@@ -68,7 +75,7 @@ def test_conv3x3_backward(B, C, H, W, N):
     assert rel(db[0], dz.float().sum(dim=(0, 2, 3))) < 1e-4
 
 
-@pytest.mark.parametrize("B,C,N,H", [(2, 64, 128, 16), (1, 192, 192, 64)])
+@pytest.mark.parametrize("B,C,N,H", [(2, 64, 128, 16), (1, 192, 192, 64), (1, 256, 512, 16)])     # last: CTA-pair kernel on phase views
 def test_downsample_backward(B, C, N, H):
     x, y = bf(rnd(B, C, H, H)), bf(rnd(B, C, H, H, seed=5))
     w2, wdc = bf(rnd(N, C, 3, 3, seed=1, scale=0.05)), bf(rnd(N, 4 * C, 1, 1, seed=3, scale=0.05))
@@ -85,7 +92,7 @@ def test_downsample_backward(B, C, N, H):
     assert rel(db[0], dz.float().sum(dim=(0, 2, 3))) < 1e-4
 
 
-@pytest.mark.parametrize("B,Ci,Co,H", [(2, 128, 64, 8), (1, 192, 192, 32)])
+@pytest.mark.parametrize("B,Ci,Co,H", [(2, 128, 64, 8), (1, 192, 192, 32), (1, 512, 256, 8)])     # last: CTA-pair kernel, four phases
 def test_upsample_backward(B, Ci, Co, H):
     x = bf(rnd(B, Ci, H, H))
     w1, w2 = bf(rnd(Co, Ci, 3, 3, seed=1, scale=0.05)), bf(rnd(Co, Co, 3, 3, seed=2, scale=0.05))
