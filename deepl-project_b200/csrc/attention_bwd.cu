@@ -7,7 +7,8 @@
 //   S~ = Q_i K_j^T, dP = dO_i V_j^T                       (2 MMAs -> TMEM)
 //   P = exp2(S~ - lse), dZ = P * (dP - delta)             (softmax warps; bf16 P, dZ -> swizzled smem)
 //   dV += P^T dO_i, dK~ += dZ^T Q_i, dQ~_i = dZ K_j       (3 MMAs; P / dZ / dO / Q / K as MN-major operands)
-// dV, dK~ accumulate in TMEM over the whole loop; dQ~_i goes to an fp32 global accumulator with red.add.
+// dV, dK~ accumulate in TMEM over the whole loop; dQ~_i goes to an fp32 global accumulator with a bulk tensor reduce-add
+// issued by a dedicated drain warpgroup, so the softmax warps never wait for it.
 // Outputs: dqkv[:, :, C:2C] = ln2 * dK~ (still in rotated space), dqkv[:, :, 2C:3C] = dV, dq_acc fp32 [B, S, C]
 // (rotated space, unscaled); tvae_rope_bwd then applies the transposed RoPE and the softmax scale.
 #include "../../include/transvae_sm100.h"
@@ -17,7 +18,8 @@
 namespace tvae {
 
 constexpr int kBT = 128 * 64 * 2;  // 16 KiB tile
-constexpr int kBwdThreads = 384;   // 4 control warps + 8 softmax warps (two per TMEM lane quarter, 64 key columns each)
+constexpr int kBwdThreads = 512;   // 4 control warps + 8 softmax warps (two per TMEM lane quarter, 64 key columns each)
+                                   // + 4 drain warps (dQ~: TMEM -> smem -> bulk reduce-add)
 constexpr int kBwdSmem = 2 * kBT /*K,V*/ + 2 * 2 * kBT /*Q,dO ring*/ + 2 * 2 * 2 * kBT /*P, dZ double buffered*/ + 1024 + 256;
 
 __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
@@ -26,6 +28,10 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, ui
           smem_u32(smem)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -49,9 +55,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* pds_full = bars + 6;     // 1 (8 warp arrivals)
   uint64_t* mma_done = bars + 7;     // [2] (alternating, so a waiter never lags two phases)
   uint64_t* sdp_free = bars + 9;     // 1 (8 warp arrivals): S~ / dP of the current tile sit in registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* dq_drained = bars + 10;  // [2]: dQ~ of tile i left its staging area (= the dZ buffer i & 1) and its TMEM buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
@@ -71,6 +78,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(sdp_free, 8);
     mbar_init(&mma_done[0], 1);
     mbar_init(&mma_done[1], 1);
+    mbar_init(&dq_drained[0], 1);
+    mbar_init(&dq_drained[1], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -80,12 +89,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
   const uint32_t t_S = tmem_base, t_dP = tmem_base + 128, t_dV = tmem_base + 256, t_dK = tmem_base + 320,
                  t_dQ = tmem_base + 384;  // 2 x 64
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");      // control warpgroup (TMA / MMA issue)
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");      // control warpgroup (TMA / MMA issue)
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(kv_full, 2 * kBT);
@@ -100,58 +109,100 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t id_kk = umma_idesc_bf16(128, 128, 0, 0);   // S~, dP : both operands K-major (d contiguous)
-      constexpr uint32_t id_mm = umma_idesc_bf16(128, 64, 1, 1);    // dV, dK : both MN-major (reduction over queries)
-      constexpr uint32_t id_km = umma_idesc_bf16(128, 64, 0, 1);    // dQ     : A = dZ K-major, B = K_j MN-major
-      const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV);
-      auto issue_sdp = [&](int i) {
-        const int st = i & 1;
-        mbar_wait(&qdo_full[st], (i >> 1) & 1);
+    // ---- MMA issue: the whole warp walks the loop (uniform control flow, operands in uniform registers), one elected
+    // lane issues.  Descriptors are built once and advanced by constant offsets.
+    constexpr uint32_t id_kk = umma_idesc_bf16(128, 128, 0, 0);   // S~, dP : both operands K-major (d contiguous)
+    constexpr uint32_t id_mm = umma_idesc_bf16(128, 64, 1, 1);    // dV, dK : both MN-major (reduction over queries)
+    constexpr uint32_t id_km = umma_idesc_bf16(128, 64, 0, 1);    // dQ     : A = dZ K-major, B = K_j MN-major
+    const uint32_t smem_base = smem_u32(smem);
+    const uint64_t dk_k = umma_desc_kmajor_sw128(smem_base);                  // K-major view of the tile at offset 0
+    const uint64_t dk_m = umma_desc_mnmajor_sw128(smem_base, kBT, 1024);      // MN-major view
+    constexpr uint32_t oK = 0, oV = kBT, oQ = 2 * kBT, oDO = 4 * kBT, oP = 6 * kBT, oDZ = 10 * kBT;
+    auto issue_sdp = [&](int i) {
+      const uint32_t st = i & 1;
+      mbar_wait(&qdo_full[st], (i >> 1) & 1);
+      tc_fence_after();
+      const uint64_t dq = umma_desc_advance(dk_k, oQ + st * kBT), ddo = umma_desc_advance(dk_k, oDO + st * kBT);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16_elect(t_S, umma_desc_advance(dq, k * 32), umma_desc_advance(dk_k, oK + k * 32), id_kk, k != 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16_elect(t_dP, umma_desc_advance(ddo, k * 32), umma_desc_advance(dk_k, oV + k * 32), id_kk, k != 0);
+      umma_commit_elect(sdp_full);
+    };
+    mbar_wait(kv_full, 0);
+    issue_sdp(0);
+    for (int i = 0; i < nq; ++i) {
+      const uint32_t st = i & 1;
+      // S~ / dP of tile i+1 go to the tensor pipe as soon as the softmax warps hold tile i in registers, i.e.
+      // they overlap the exponentiation of tile i (the first version issued them after dV / dK / dQ of tile i, so
+      // tensor work and softmax strictly alternated)
+      if (i + 1 < nq) {
+        mbar_wait(sdp_free, i & 1);
         tc_fence_after();
-        const uint32_t q_base = smem_u32(sQ + st * kBT), do_base = smem_u32(sDO + st * kBT);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(t_S, umma_desc_kmajor_sw128(q_base + k * 32), umma_desc_kmajor_sw128(k_base + k * 32), id_kk, k != 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(t_dP, umma_desc_kmajor_sw128(do_base + k * 32), umma_desc_kmajor_sw128(v_base + k * 32), id_kk, k != 0);
-        umma_commit(sdp_full);
-      };
-      mbar_wait(kv_full, 0);
-      issue_sdp(0);
-      for (int i = 0; i < nq; ++i) {
-        const int st = i & 1;
-        // S~ / dP of tile i+1 go to the tensor pipe as soon as the softmax warps hold tile i in registers, i.e.
-        // they overlap the exponentiation of tile i (the first version issued them after dV / dK / dQ of tile i, so
-        // tensor work and softmax strictly alternated)
-        if (i + 1 < nq) {
-          mbar_wait(sdp_free, i & 1);
-          tc_fence_after();
-          issue_sdp(i + 1);
-        }
-        mbar_wait(pds_full, i & 1);
-        tc_fence_after();
-        const uint32_t q_base = smem_u32(sQ + st * kBT), do_base = smem_u32(sDO + st * kBT);
-        const uint32_t p_base = smem_u32(sP + (i & 1) * 2 * kBT), dz_base = smem_u32(sDZ + (i & 1) * 2 * kBT);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {   // 16 queries per MMA
-          umma_f16(t_dV, umma_desc_mnmajor_sw128(p_base + k * 2048, kBT, 1024),
-                   umma_desc_mnmajor_sw128(do_base + k * 2048, kBT, 1024), id_mm, (i | k) != 0);
-          umma_f16(t_dK, umma_desc_mnmajor_sw128(dz_base + k * 2048, kBT, 1024),
-                   umma_desc_mnmajor_sw128(q_base + k * 2048, kBT, 1024), id_mm, (i | k) != 0);
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)     // 16 keys per MMA
-          umma_f16(t_dQ + (i & 1) * 64, umma_desc_kmajor_sw128(dz_base + (k >> 2) * kBT + (k & 3) * 32),
-                   umma_desc_mnmajor_sw128(k_base + k * 2048, kBT, 1024), id_km, k != 0);
-        umma_commit(&qdo_empty[st]);
-        umma_commit(&mma_done[i & 1]);
+        issue_sdp(i + 1);
       }
+      mbar_wait(pds_full, i & 1);
+      tc_fence_after();
+      const uint64_t mq = umma_desc_advance(dk_m, oQ + st * kBT), mdo = umma_desc_advance(dk_m, oDO + st * kBT);
+      const uint64_t mp = umma_desc_advance(dk_m, oP + st * 2 * kBT), mdz = umma_desc_advance(dk_m, oDZ + st * 2 * kBT);
+      const uint64_t kdz = umma_desc_advance(dk_k, oDZ + st * 2 * kBT);
+      const uint32_t acc = i != 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {   // 16 queries per MMA
+        umma_f16_elect(t_dV, umma_desc_advance(mp, k * 2048), umma_desc_advance(mdo, k * 2048), id_mm, k ? 1u : acc);
+        umma_f16_elect(t_dK, umma_desc_advance(mdz, k * 2048), umma_desc_advance(mq, k * 2048), id_mm, k ? 1u : acc);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)     // 16 keys per MMA
+        umma_f16_elect(t_dQ + st * 64, umma_desc_advance(kdz, (k >> 2) * kBT + (k & 3) * 32),
+                       umma_desc_advance(dk_m, oK + k * 2048), id_km, k != 0);
+      umma_commit_elect(&qdo_empty[st]);
+      umma_commit_elect(&mma_done[st]);
     }
   }
+  } else if (warp >= 12) {
+    // ---- drain warpgroup: dQ~_i (128 x 64 fp32) TMEM -> swizzled smem -> two bulk tensor reduce-adds into the fp32
+    // accumulator.  The staging area is the dZ buffer of tile i, which the tensor core has finished reading when
+    // mma_done(i) fires; the softmax warps take it back (tile i + 2) on dq_drained.  (First version: per-thread
+    // red.global.add.v4.f32 -- 6.4 GB of scattered 16-byte atomics per launch.  Second version: the softmax warps
+    // staged and waited for the bulk read themselves -- 41 % of their stall samples sat in that wait and its barriers.)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    for (int i = 0; i < nq; ++i) {
+      mbar_wait(&mma_done[i & 1], (i >> 1) & 1);
+      tc_fence_after();
+      uint8_t* stage = sDZ + (i & 1) * 2 * kBT;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(t_dQ + (i & 1) * 64 + lane_off + half * 32, v);
+        tmem_ld_wait();
+        const uint32_t row = smem_u32(stage + half * kBT + r * 128);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) st_shared_v4(row + ((g ^ (r & 7)) << 4), v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 12 && lane == 0) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+          asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmDQ)),
+                       "r"(smem_u32(stage + half * kBT)), "r"(h * 64 + half * 32), "r"(i * 128), "r"(b)
+                       : "memory");
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        mbar_arrive(&dq_drained[i & 1]);
+      }
+    }
+    if (warp == 12 && lane == 0) tma_store_wait<0>();   // all reduce-adds of this CTA have landed
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");    // softmax warpgroups: 64 S~ + 64 dP values per thread
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");    // softmax warpgroups: 2 x (32 S~ + 32 dP) values per thread
     // Eight softmax warps: warps w and w + 4 share TMEM lane quarter (w & 3) -- i.e. the same 32 query rows -- and
     // split the 128 key columns in halves.  Nothing in the backward softmax reduces along a row (lse and delta come
     // from the forward pass), so the halves are independent; with one warp per scheduler (the first version) every
@@ -161,96 +212,66 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int r = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const size_t stat_base = ((size_t)b * nh + h) * S;
+    const bool full_tile = k0 + 128 <= S;                            // no key masking needed
 
-    // dQ~_i (this half's 32 columns of the 128 x 64 fp32 tile) -> swizzled smem -> ONE bulk tensor reduce-add into the
-    // fp32 accumulator.  The staging area is the dZ buffer of tile i, which the tensor core has finished reading.
-    // (The first version issued per-thread red.global.add.v4.f32: every warp instruction touched 32 different rows,
-    // 6.4 GB of scattered 16-byte atomics per launch -- the L2 atomic path, not the tensor pipe, set the pace.)
-    auto drain_dq = [&](int i) {
-      uint8_t* stage = sDZ + ((i & 1) * 2 + half) * kBT;
-      uint32_t v[32];
-      tmem_ld32(t_dQ + (i & 1) * 64 + lane_off + half * 32, v);
-      tmem_ld_wait();
-      uint8_t* row = stage + r * 128;
-#pragma unroll
-      for (int g = 0; g < 8; ++g)
-        *reinterpret_cast<uint4*>(row + ((g ^ (r & 7)) << 4)) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-      fence_proxy_async_smem();
-      if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-      else asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (qd == 0 && lane == 0) {
-        asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                         reinterpret_cast<uint64_t>(&tmDQ)),
-                     "r"(smem_u32(stage)), "r"(h * 64 + half * 32), "r"(i * 128), "r"(b)
-                     : "memory");
-        tma_store_commit();
-        tma_store_wait_read<0>();      // the staging buffer is rewritten by the softmax of tile i + 2
-      }
-      if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-      else asm volatile("bar.sync 2, 128;" ::: "memory");
-    };
-
+    float l2_next = (r < S) ? __ldg(lse + stat_base + r) : INFINITY;
+    float dl_next = (r < S) ? __ldg(delta + stat_base + r) : 0.0f;
     for (int i = 0; i < nq; ++i) {
-      const int qrow = i * 128 + r;
-      const float l2 = (qrow < S) ? __ldg(lse + stat_base + qrow) : INFINITY;
-      const float dl = (qrow < S) ? __ldg(delta + stat_base + qrow) : 0.0f;
-      const float2 nl2 = make_float2(-l2, -l2), ndl = make_float2(-dl, -dl);
+      const float2 nl2 = make_float2(-l2_next, -l2_next), ndl = make_float2(-dl_next, -dl_next);
+      {                                                              // statistics of the next tile: off the critical path
+        const int qn = (i + 1) * 128 + r;
+        l2_next = (qn < S) ? __ldg(lse + stat_base + qn) : INFINITY;
+        dl_next = (qn < S) ? __ldg(delta + stat_base + qn) : 0.0f;
+      }
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
-      uint32_t sv[64], pv[64];
-      {
-        uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
-        uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
-        uint32_t(&p0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pv[0]);
-        uint32_t(&p1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pv[32]);
-        tmem_ld32(t_S + lane_off + half * 64, s0);
-        tmem_ld32(t_S + lane_off + half * 64 + 32, s1);
-        tmem_ld32(t_dP + lane_off + half * 64, p0);
-        tmem_ld32(t_dP + lane_off + half * 64 + 32, p1);
-        tmem_ld_wait();
-      }
+      uint32_t sa[32], pa[32], sb[32], pb[32];
+      tmem_ld32(t_S + lane_off + half * 64, sa);
+      tmem_ld32(t_dP + lane_off + half * 64, pa);
+      tmem_ld32(t_S + lane_off + half * 64 + 32, sb);
+      tmem_ld32(t_dP + lane_off + half * 64 + 32, pb);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(sdp_free);                          // the S~ / dP accumulators may be overwritten
-      if (i >= 2) mbar_wait(&mma_done[i & 1], ((i - 2) >> 1) & 1);   // P / dZ buffer i&1 no longer read by MMA(i-2)
-      uint8_t* prow = sP + ((i & 1) * 2 + half) * kBT + r * 128;
-      uint8_t* zrow = sDZ + ((i & 1) * 2 + half) * kBT + r * 128;
-      const bool full_tile = k0 + 128 <= S;                          // no masking needed
+      // S~ / dP of this tile sit in registers: the accumulators may be overwritten.  This arrive must stay AHEAD of the
+      // arithmetic (a version that released after the first 32 columns had it sunk below all 64 exponentials by ptxas:
+      // 38 % of the softmax warps' samples then waited for S~ / dP (i + 1)); the wait loop below pins it.
+      if (lane == 0) mbar_arrive(sdp_free);
+      if (i >= 2) mbar_wait(&dq_drained[i & 1], ((i - 2) >> 1) & 1);  // P / dZ buffer i&1: MMA(i-2) and the dQ drain are done
+      const uint32_t prow = smem_u32(sP + ((i & 1) * 2 + half) * kBT + r * 128);
+      const uint32_t zrow = smem_u32(sDZ + ((i & 1) * 2 + half) * kBT + r * 128);
+      auto chunk = [&](const uint32_t(&sv)[32], const uint32_t(&pv)[32], int c) {
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {                                  // 8 columns -> one 16-byte store of P and of dZ
-        uint32_t pk[4], zk[4];
+        for (int g = 0; g < 4; ++g) {                                // 8 columns -> one 16-byte store of P and of dZ
+          uint32_t pk[4], zk[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int j = g * 8 + 2 * k;
-          float2 e = __fadd2_rn(make_float2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1])), nl2);
-          e.x = exp2f(e.x);
-          e.y = exp2f(e.y);
-          if (!full_tile) {
-            if (k0 + half * 64 + j >= S) e.x = 0.0f;
-            if (k0 + half * 64 + j + 1 >= S) e.y = 0.0f;
+          for (int k = 0; k < 4; ++k) {
+            const int j = g * 8 + 2 * k;
+            float2 e = __fadd2_rn(make_float2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1])), nl2);
+            e.x = exp2f(e.x);
+            e.y = exp2f(e.y);
+            if (!full_tile) {
+              if (k0 + half * 64 + c * 32 + j >= S) e.x = 0.0f;
+              if (k0 + half * 64 + c * 32 + j + 1 >= S) e.y = 0.0f;
+            }
+            const float2 d = __fmul2_rn(e, __fadd2_rn(make_float2(__uint_as_float(pv[j]), __uint_as_float(pv[j + 1])), ndl));
+            pk[k] = pack_bf16(e.x, e.y);
+            zk[k] = pack_bf16(d.x, d.y);
           }
-          const float2 d = __fmul2_rn(e, __fadd2_rn(make_float2(__uint_as_float(pv[j]), __uint_as_float(pv[j + 1])), ndl));
-          pk[k] = pack_bf16(e.x, e.y);
-          zk[k] = pack_bf16(d.x, d.y);
+          const uint32_t off = ((c * 4 + g) ^ (r & 7)) << 4;
+          st_shared_v4(prow + off, pk[0], pk[1], pk[2], pk[3]);
+          st_shared_v4(zrow + off, zk[0], zk[1], zk[2], zk[3]);
         }
-        const int off = (g ^ (r & 7)) << 4;
-        *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(zrow + off) = make_uint4(zk[0], zk[1], zk[2], zk[3]);
-      }
+      };
+      chunk(sa, pa, 0);
+      chunk(sb, pb, 1);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      if (i > 0) {
-        mbar_wait(&mma_done[(i - 1) & 1], ((i - 1) >> 1) & 1);   // dQ_{i-1} complete
-        tc_fence_after();
-        drain_dq(i - 1);
-      }
     }
     mbar_wait(&mma_done[(nq - 1) & 1], ((nq - 1) >> 1) & 1);
     tc_fence_after();
-    drain_dq(nq - 1);
-    if (qd == 0 && lane == 0) tma_store_wait<0>();   // all reduce-adds of this CTA have landed
     // dK~ (x ln2, warps of half 0) and dV (half 1) of this key tile (row r = key k0 + r)
     const int krow = k0 + r;
     __nv_bfloat16* dst = dqkv + ((size_t)b * S + krow) * 3 * C + h * 64;

@@ -209,6 +209,26 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// ---- warp-uniform issue ------------------------------------------------------------------------
+// tcgen05.mma / commit take their operands from UNIFORM registers.  Issued from inside an `if (lane == 0)` branch, with
+// addresses derived from a shared-memory load (the TMEM base) or from threadIdx, nvcc cannot prove them uniform: every
+// MMA was preceded by ~20 vector instructions rebuilding both descriptors plus an ELECT / R2UR.BROADCAST / BRA.U.ANY
+// waterfall loop -- ~130 clocks per issue (ncu, attention backward: the issuing warp spent 72 % of its samples there
+// and a 32-clock N = 64 MMA could not be issued faster than every 130 clocks).  The pattern below keeps the whole
+// warp in the issue loop (warp index and TMEM base made uniform with a shuffle from lane 0), advances descriptors by
+// adding to their low word, and elects the issuing lane per instruction.
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+// descriptor of the same layout `bytes` further into shared memory (start-address field, 16-byte units; stays below 2^14)
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
+__device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  if (elect_one()) umma_f16(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  if (elect_one()) umma_commit(bar);
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
