@@ -12,6 +12,9 @@
 // Outputs: dqkv[:, :, C:2C] = ln2 * dK~ (still in rotated space), dqkv[:, :, 2C:3C] = dV, dq_acc fp32 [B, S, C]
 // (rotated space, unscaled); tvae_rope_bwd then applies the transposed RoPE and the softmax scale.
 #include "../../include/transvae_sm100.h"
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 #include "tmap.cuh"
 
@@ -20,7 +23,8 @@ namespace tvae {
 constexpr int kBT = 128 * 64 * 2;  // 16 KiB tile
 constexpr int kBwdThreads = 512;   // 4 control warps + 8 softmax warps (two per TMEM lane quarter, 64 key columns each)
                                    // + 4 drain warps (dQ~: TMEM -> smem -> bulk reduce-add)
-constexpr int kBwdSmem = 2 * kBT /*K,V*/ + 2 * 2 * kBT /*Q,dO ring*/ + 2 * 2 * 2 * kBT /*P, dZ double buffered*/ + 1024 + 256;
+constexpr int kQStages = 3;       // Q / dO ring
+constexpr int kBwdSmem = 2 * kBT /*K,V*/ + 2 * kQStages * kBT /*Q,dO ring*/ + 2 * kBT /*P*/ + 2 * 2 * kBT /*dZ double buffered*/ + 1024 + 256;
 
 __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
@@ -34,6 +38,24 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// 2^x for two lanes on the FMA pipe (see attention.cu: round-to-nearest split with the 1.5 * 2^23 trick, degree-3 minimax
+// polynomial on [-0.5, 0.5], max relative error 7.5e-5 -- far below the bf16 rounding of P; clamped at -126).
+__device__ __forceinline__ float2 exp2_fma2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 xf = __fadd2_rn(x, make_float2(12582912.0f, 12582912.0f));
+  const float2 n = __fadd2_rn(xf, make_float2(-12582912.0f, -12582912.0f));
+  const float2 r = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
+  float2 p = __ffma2_rn(make_float2(0.0551716685f, 0.0551716685f), r, make_float2(0.242611125f, 0.242611125f));
+  p = __ffma2_rn(p, r, make_float2(0.693260968f, 0.693260968f));
+  p = __ffma2_rn(p, r, make_float2(0.999928057f, 0.999928057f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(xf.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(xf.y) << 23));
+  return p;
+}
+
+// POLY: every POLY-th pair of probabilities is exponentiated on the FMA pipe instead of MUFU (0 = never).
+template <int POLY>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmDQ, const float* __restrict__ lse, const float* __restrict__ delta,
@@ -43,20 +65,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = sK + kBT;
-  uint8_t* sQ = sV + kBT;            // [2 stages]
-  uint8_t* sDO = sQ + 2 * kBT;       // [2 stages]
-  uint8_t* sP = sDO + 2 * kBT;       // [2 buffers] x 2 chunks (keys 0-63, 64-127)
-  uint8_t* sDZ = sP + 4 * kBT;       // [2 buffers] x 2 chunks
+  // Q / dO ring of THREE stages: a stage is released by the last MMA that reads it (dQ of the tile) and refilled from
+  // L2 -- with two stages that round trip (commit -> producer -> TMA latency -> S~ / dP -> softmax -> dV / dK / dQ) was
+  // the pace of the whole kernel: 0.9 of 1.44 ms remained with every MMA, exponential, store and drain switched off.
+  // The shared memory for the third stage comes from P, which is single-buffered: the dV MMAs that read it are issued
+  // first and signal p_free on their own.
+  uint8_t* sQ = sV + kBT;                 // [kQStages]
+  uint8_t* sDO = sQ + kQStages * kBT;     // [kQStages]
+  uint8_t* sP = sDO + kQStages * kBT;     // 2 chunks (keys 0-63, 64-127)
+  uint8_t* sDZ = sP + 2 * kBT;            // [2 buffers] x 2 chunks
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDZ + 4 * kBT);
   uint64_t* kv_full = bars;          // 1
-  uint64_t* qdo_full = bars + 1;     // [2]
-  uint64_t* qdo_empty = bars + 3;    // [2]
-  uint64_t* sdp_full = bars + 5;     // 1
-  uint64_t* pds_full = bars + 6;     // 1 (8 warp arrivals)
-  uint64_t* mma_done = bars + 7;     // [2] (alternating, so a waiter never lags two phases)
-  uint64_t* sdp_free = bars + 9;     // 1 (8 warp arrivals): S~ / dP of the current tile sit in registers
-  uint64_t* dq_drained = bars + 10;  // [2]: dQ~ of tile i left its staging area (= the dZ buffer i & 1) and its TMEM buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* qdo_full = bars + 1;     // [3]
+  uint64_t* qdo_empty = bars + 4;    // [3]
+  uint64_t* sdp_full = bars + 7;     // 1
+  uint64_t* pds_full = bars + 8;     // 1 (8 warp arrivals)
+  uint64_t* mma_done = bars + 9;     // [2] (alternating, so a waiter never lags two phases)
+  uint64_t* sdp_free = bars + 11;    // 1 (8 warp arrivals): S~ / dP of the current tile sit in registers
+  uint64_t* dq_drained = bars + 12;  // [2]: dQ~ of tile i left its staging area (= the dZ buffer i & 1) and its TMEM buffer
+  uint64_t* p_free = bars + 14;      // 1: the dV MMAs of the tile have read P
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128;
@@ -69,10 +97,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmDQ);
     mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kQStages; ++s) {
       mbar_init(&qdo_full[s], 1);
       mbar_init(&qdo_empty[s], 1);
     }
+    mbar_init(p_free, 1);
     mbar_init(sdp_full, 1);
     mbar_init(pds_full, 8);
     mbar_init(sdp_free, 8);
@@ -94,18 +123,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                  t_dQ = tmem_base + 384;  // 2 x 64
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");      // control warpgroup (TMA / MMA issue)
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");      // control warpgroup (TMA / MMA issue)
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(kv_full, 2 * kBT);
       tma_load_3d(sK, &tmQKV, kv_full, C + h * 64, k0, b);
       tma_load_3d(sV, &tmQKV, kv_full, 2 * C + h * 64, k0, b);
+      int st = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < nq; ++i) {
-        const int st = i & 1;
-        mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_wait(&qdo_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&qdo_full[st], 2 * kBT);
         tma_load_3d(sQ + st * kBT, &tmQKV, &qdo_full[st], h * 64, i * 128, b);
         tma_load_3d(sDO + st * kBT, &tmDO, &qdo_full[st], h * 64, i * 128, b);
+        if (++st == kQStages) {
+          st = 0;
+          ph ^= 1;
+        }
       }
     }
   } else if (warp == 1) {
@@ -117,10 +151,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const uint32_t smem_base = smem_u32(smem);
     const uint64_t dk_k = umma_desc_kmajor_sw128(smem_base);                  // K-major view of the tile at offset 0
     const uint64_t dk_m = umma_desc_mnmajor_sw128(smem_base, kBT, 1024);      // MN-major view
-    constexpr uint32_t oK = 0, oV = kBT, oQ = 2 * kBT, oDO = 4 * kBT, oP = 6 * kBT, oDZ = 10 * kBT;
-    auto issue_sdp = [&](int i) {
-      const uint32_t st = i & 1;
-      mbar_wait(&qdo_full[st], (i >> 1) & 1);
+    constexpr uint32_t oK = 0, oV = kBT, oQ = 2 * kBT, oDO = (2 + kQStages) * kBT, oP = (2 + 2 * kQStages) * kBT,
+                       oDZ = (4 + 2 * kQStages) * kBT;
+    auto issue_sdp = [&](uint32_t st, uint32_t ph) {     // S~ / dP of the tile in ring stage st
+      mbar_wait(&qdo_full[st], ph);
       tc_fence_after();
       const uint64_t dq = umma_desc_advance(dk_k, oQ + st * kBT), ddo = umma_desc_advance(dk_k, oDO + st * kBT);
 #pragma unroll
@@ -132,34 +166,44 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       umma_commit_elect(sdp_full);
     };
     mbar_wait(kv_full, 0);
-    issue_sdp(0);
+    issue_sdp(0, 0);
+    uint32_t st = 0, ph = 0;                              // ring position of tile i
     for (int i = 0; i < nq; ++i) {
-      const uint32_t st = i & 1;
+      const uint32_t buf = i & 1;
+      uint32_t st_n = st + 1, ph_n = ph;                  // ... of tile i + 1
+      if (st_n == kQStages) {
+        st_n = 0;
+        ph_n ^= 1;
+      }
       // S~ / dP of tile i+1 go to the tensor pipe as soon as the softmax warps hold tile i in registers, i.e.
       // they overlap the exponentiation of tile i (the first version issued them after dV / dK / dQ of tile i, so
       // tensor work and softmax strictly alternated)
       if (i + 1 < nq) {
         mbar_wait(sdp_free, i & 1);
         tc_fence_after();
-        issue_sdp(i + 1);
+        issue_sdp(st_n, ph_n);
       }
       mbar_wait(pds_full, i & 1);
       tc_fence_after();
       const uint64_t mq = umma_desc_advance(dk_m, oQ + st * kBT), mdo = umma_desc_advance(dk_m, oDO + st * kBT);
-      const uint64_t mp = umma_desc_advance(dk_m, oP + st * 2 * kBT), mdz = umma_desc_advance(dk_m, oDZ + st * 2 * kBT);
-      const uint64_t kdz = umma_desc_advance(dk_k, oDZ + st * 2 * kBT);
+      const uint64_t mp = umma_desc_advance(dk_m, oP), mdz = umma_desc_advance(dk_m, oDZ + buf * 2 * kBT);
+      const uint64_t kdz = umma_desc_advance(dk_k, oDZ + buf * 2 * kBT);
       const uint32_t acc = i != 0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {   // 16 queries per MMA
+      for (int k = 0; k < 8; ++k)     // dV: 16 queries per MMA; first, so that P can be rewritten early
         umma_f16_elect(t_dV, umma_desc_advance(mp, k * 2048), umma_desc_advance(mdo, k * 2048), id_mm, k ? 1u : acc);
-        umma_f16_elect(t_dK, umma_desc_advance(mdz, k * 2048), umma_desc_advance(mq, k * 2048), id_mm, k ? 1u : acc);
-      }
+      umma_commit_elect(p_free);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)     // 16 keys per MMA
-        umma_f16_elect(t_dQ + st * 64, umma_desc_advance(kdz, (k >> 2) * kBT + (k & 3) * 32),
+      for (int k = 0; k < 8; ++k)     // dK
+        umma_f16_elect(t_dK, umma_desc_advance(mdz, k * 2048), umma_desc_advance(mq, k * 2048), id_mm, k ? 1u : acc);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)     // dQ: 16 keys per MMA
+        umma_f16_elect(t_dQ + buf * 64, umma_desc_advance(kdz, (k >> 2) * kBT + (k & 3) * 32),
                        umma_desc_advance(dk_m, oK + k * 2048), id_km, k != 0);
       umma_commit_elect(&qdo_empty[st]);
-      umma_commit_elect(&mma_done[st]);
+      umma_commit_elect(&mma_done[buf]);
+      st = st_n;
+      ph = ph_n;
     }
   }
   } else if (warp >= 12) {
@@ -168,7 +212,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     // mma_done(i) fires; the softmax warps take it back (tile i + 2) on dq_drained.  (First version: per-thread
     // red.global.add.v4.f32 -- 6.4 GB of scattered 16-byte atomics per launch.  Second version: the softmax warps
     // staged and waited for the bulk read themselves -- 41 % of their stall samples sat in that wait and its barriers.)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
@@ -237,10 +281,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       // arithmetic (a version that released after the first 32 columns had it sunk below all 64 exponentials by ptxas:
       // 38 % of the softmax warps' samples then waited for S~ / dP (i + 1)); the wait loop below pins it.
       if (lane == 0) mbar_arrive(sdp_free);
-      if (i >= 2) mbar_wait(&dq_drained[i & 1], ((i - 2) >> 1) & 1);  // P / dZ buffer i&1: MMA(i-2) and the dQ drain are done
-      const uint32_t prow = smem_u32(sP + ((i & 1) * 2 + half) * kBT + r * 128);
+      if (i >= 1) mbar_wait(p_free, (i - 1) & 1);                     // P: read by the dV MMAs of tile i-1
+      if (i >= 2) mbar_wait(&dq_drained[i & 1], ((i - 2) >> 1) & 1);  // dZ buffer i&1: MMA(i-2) and the dQ drain are done
+      const uint32_t prow = smem_u32(sP + half * kBT + r * 128);
       const uint32_t zrow = smem_u32(sDZ + ((i & 1) * 2 + half) * kBT + r * 128);
-      auto chunk = [&](const uint32_t(&sv)[32], const uint32_t(&pv)[32], int c) {
+      // masked = the key tile reaches beyond S (last tile of a ragged sequence): the test is hoisted out of the inner
+      // loop (ncu: the predicated ISETP / VIADD / FSEL of the mask were 200 of the 536 instructions per tile)
+      auto chunk = [&](const uint32_t(&sv)[32], const uint32_t(&pv)[32], int c, auto masked) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {                                // 8 columns -> one 16-byte store of P and of dZ
           uint32_t pk[4], zk[4];
@@ -248,9 +295,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           for (int k = 0; k < 4; ++k) {
             const int j = g * 8 + 2 * k;
             float2 e = __fadd2_rn(make_float2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1])), nl2);
-            e.x = exp2f(e.x);
-            e.y = exp2f(e.y);
-            if (!full_tile) {
+            if (POLY > 0 && ((c * 16 + g * 4 + k) % (POLY > 0 ? POLY : 1)) == POLY - 1) {
+              e = exp2_fma2(e);
+            } else {
+              e.x = exp2f(e.x);
+              e.y = exp2f(e.y);
+            }
+            if (decltype(masked)::value) {
               if (k0 + half * 64 + c * 32 + j >= S) e.x = 0.0f;
               if (k0 + half * 64 + c * 32 + j + 1 >= S) e.y = 0.0f;
             }
@@ -263,8 +314,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           st_shared_v4(zrow + off, zk[0], zk[1], zk[2], zk[3]);
         }
       };
-      chunk(sa, pa, 0);
-      chunk(sb, pb, 1);
+      if (full_tile) {
+        chunk(sa, pa, 0, std::false_type{});
+        chunk(sb, pb, 1, std::false_type{});
+      } else {
+        chunk(sa, pa, 0, std::true_type{});
+        chunk(sb, pb, 1, std::true_type{});
+      }
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
@@ -318,15 +374,18 @@ int attn_bwd_run(const void* qkv, const void* dout, const float* lse, const floa
   if ((rc = make_tmap_3d(&mDO, dout, C, S, B, C, (uint64_t)S * C, 128))) return rc;
   CUtensorMap mDQ;
   if ((rc = make_tmap_3d_f32(&mDQ, dq_acc, C, S, B, C, (uint64_t)S * C, 128))) return rc;
+  // TVAE_ATTN_BWD_POLY = 0 / 2 / 3 / 4: A/B switch for the share of exponentials on the FMA pipe (default 0: measured slower with any share -- the softmax warps are not MUFU-bound here)
+  static const int poly = getenv("TVAE_ATTN_BWD_POLY") ? atoi(getenv("TVAE_ATTN_BWD_POLY")) : 0;
+  auto kern = poly == 0 ? attn_bwd_kernel<0> : poly == 2 ? attn_bwd_kernel<2> : poly == 3 ? attn_bwd_kernel<3> : attn_bwd_kernel<4>;
   static bool configured = false;
   if (!configured) {
-    TVAE_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    for (auto k : {attn_bwd_kernel<0>, attn_bwd_kernel<2>, attn_bwd_kernel<3>, attn_bwd_kernel<4>})
+      TVAE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     configured = true;
   }
   TVAE_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)B * S * C * sizeof(float), stream));
   dim3 grid((S + 127) / 128, nh, B);
-  attn_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, stream>>>(mQKV, mDO, mDQ, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv),
-                                                           S, C, nh);
+  kern<<<grid, kBwdThreads, kBwdSmem, stream>>>(mQKV, mDO, mDQ, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), S, C, nh);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
