@@ -115,7 +115,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   uint64_t* o_full = p_full + 4;                     // [2 tiles][2 buffers]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
@@ -148,7 +148,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
   // TMEM columns: tile t: S_t at t*256 (128 columns), O_t at t*256 + 128 (64 columns)
 
   if (warp < 4) {
@@ -171,7 +171,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       }
     } else if (warp == 1 || warp == 2) {
       // one MMA-issuing thread per Q tile, so a slow tile never holds back the other tile's S / P V products
-      if (lane == 0) {
+      {   // whole warp, elected lane issues (common.cuh: warp-uniform issue)
         const int t = warp - 1;
         constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
         constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
@@ -180,20 +180,20 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           const uint32_t k_base = smem_u32(sK + (j & 1) * kTileBytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base + t * 256, umma_desc_kmajor_sw128(q_base + k * 32),
+            umma_f16_elect(tmem_base + t * 256, umma_desc_kmajor_sw128(q_base + k * 32),
                      umma_desc_kmajor_sw128(k_base + k * 32), idesc_qk, k != 0);
-          umma_commit(&s_full[t]);
-          umma_commit(&k_empty[j & 1]);                // second arrival (other tile) releases the K stage
+          umma_commit_elect(&s_full[t]);
+          umma_commit_elect(&k_empty[j & 1]);                // second arrival (other tile) releases the K stage
         };
         auto issue_pv = [&](int j) {
           const uint32_t p_base = smem_u32(sP + (t * 2 + (j & 1)) * 2 * kTileBytes);
           const uint32_t v_base = smem_u32(sV + (j & 1) * kTileBytes);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_f16(tmem_base + t * 256 + 128, umma_desc_kmajor_sw128(p_base + (k >> 2) * kTileBytes + (k & 3) * 32),
+            umma_f16_elect(tmem_base + t * 256 + 128, umma_desc_kmajor_sw128(p_base + (k >> 2) * kTileBytes + (k & 3) * 32),
                      umma_desc_mnmajor_sw128(v_base + k * 2048, 1024, 1024), idesc_pv, (j | k) != 0);
-          umma_commit(&o_full[t * 2 + (j & 1)]);
-          umma_commit(&v_empty[j & 1]);
+          umma_commit_elect(&o_full[t * 2 + (j & 1)]);
+          umma_commit_elect(&v_empty[j & 1]);
         };
         mbar_wait(q_full, 0);
         mbar_wait(&k_full[0], 0);

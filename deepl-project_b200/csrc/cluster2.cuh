@@ -59,4 +59,13 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {   // arrive on 
       : "memory");
 }
 
+// elected-lane variants for a warp that walks the issue loop in uniform control flow (see common.cuh)
+__device__ __forceinline__ void umma2_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  if (elect_one()) umma2_f16(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+__device__ __forceinline__ void umma2_commit_mc_elect(uint64_t* bar) {
+  if (elect_one()) umma2_commit_mc(bar);
+}
+
 }  // namespace tvae

@@ -52,7 +52,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   uint64_t* out_free = res_full + 1;       // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_free + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const bool has_res = kHasRes && P.has_residual;
 
@@ -81,7 +81,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
   const int total_tiles = P.num_phases * m_tiles * P.n_tiles;
@@ -119,7 +119,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {   // whole warp, elected lane issues (common.cuh: warp-uniform issue)
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -140,16 +140,16 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           const uint32_t b_base = smem_u32(sB + stage * Cfg::kBBytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
-            umma_f16(d_tmem, umma_desc_kmajor_sw128(a_base + k * 32), umma_desc_kmajor_sw128(b_base + k * 32), idesc,
+            umma_f16_elect(d_tmem, umma_desc_kmajor_sw128(a_base + k * 32), umma_desc_kmajor_sw128(b_base + k * 32), idesc,
                      (kb | k) != 0);
           }
-          umma_commit(&empty[stage]);
+          umma_commit_elect(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);
+        umma_commit_elect(&tmem_full[acc]);
       }
     }
   } else if (warp == 2) {

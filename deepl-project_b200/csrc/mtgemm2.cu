@@ -59,7 +59,7 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* out_free = res_full + 1;       // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_free + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -101,7 +101,7 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
   const int m_pairs = (m_tiles + 1) >> 1;
@@ -172,49 +172,60 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && leader && P.halo) {
+    // The whole warp walks the loop in uniform control flow and one elected lane issues: operands stay in uniform
+    // registers and descriptors advance by constants (common.cuh, "warp-uniform issue").
+    if (leader && P.halo) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N, 0, 0);
       // descriptor base-offset field cleared: the 128-byte swizzle is a function of the shared-memory ADDRESS bits (as TMA
       // wrote it), so a start address in the middle of a 1024-byte swizzle atom needs no correction -- with base offset =
       // (addr >> 7) & 7 every row-shifted tap came out wrong, with 0 all are exact (tools/experiments/umma_row_offset.cu)
-      constexpr uint64_t bo_mask = ~(uint64_t(7) << 49);
+      const uint64_t desc0 = umma_desc_kmajor_sw128(smem_u32(smem));      // 1024-byte aligned: base offset 0
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       const int kbs = P.taps[0][0].kblocks;
+      // the tap with pixel offset dw reads halo rows [dw + 1, dw + 129): the K-major SW128 layout is linear in
+      // the row (128 B per row, SBO = 8 rows), so a tap is just a start address (dw + 1) rows further
+      uint32_t tap_off[3][3];
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) tap_off[dy][dx] = uniform_u32((P.taps[0][dy * 3 + dx].dw + 1) * 128);
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int s3 = 0; s3 < 3 * kbs; ++s3) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * Cfg::kHaloStageBytes);
-          const uint32_t b_base = a_base + kHaloABytes;
-          const int dy = s3 / kbs;
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            // the tap with pixel offset dw reads halo rows [dw + 1, dw + 129): the K-major SW128 layout is linear in
-            // the row (128 B per row, SBO = 8 rows), so a tap is just a start address (dw + 1) rows further
-            const uint32_t a_tap = a_base + (P.taps[0][dy * 3 + dx].dw + 1) * 128;
+        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll 1
+          for (int kb = 0; kb < kbs; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint64_t da = umma_desc_advance(desc0, stage * Cfg::kHaloStageBytes);
+            const uint64_t db = umma_desc_advance(da, kHaloABytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              umma2_f16(d_tmem, umma_desc_kmajor_sw128(a_tap + k * 32) & bo_mask,
-                        umma_desc_kmajor_sw128(b_base + dx * Cfg::kBHalfBytes + k * 32), idesc, (s3 | dx | k) != 0);
+            for (int dx = 0; dx < 3; ++dx) {
+              const uint64_t da_tap = umma_desc_advance(da, tap_off[dy][dx]);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                umma2_f16_elect(d_tmem, umma_desc_advance(da_tap, k * 32), umma_desc_advance(db, dx * Cfg::kBHalfBytes + k * 32),
+                                idesc, (dy | kb | dx | k) != 0);
+              }
+            }
+            umma2_commit_mc_elect(&empty[stage]);
+            if (++stage == Cfg::kHaloStages) {
+              stage = 0;
+              phase ^= 1;
             }
           }
-          umma2_commit_mc(&empty[stage]);
-          if (++stage == Cfg::kHaloStages) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma2_commit_mc(&tmem_full[acc]);
+        umma2_commit_mc_elect(&tmem_full[acc]);
       }
-    } else if (lane == 0 && leader) {
+    } else if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N, 0, 0);
+      const uint64_t desc_a0 = umma_desc_kmajor_sw128(smem_u32(sA)), desc_b0 = umma_desc_kmajor_sw128(smem_u32(sB));
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -227,23 +238,22 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         int kblocks = 0;
         for (int t = 0; t < P.ntaps[ph]; ++t) kblocks += P.taps[ph][t].kblocks;
+#pragma unroll 1
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + stage * kABytes);
-          const uint32_t b_base = smem_u32(sB + stage * Cfg::kBHalfBytes);
+          const uint64_t da = umma_desc_advance(desc_a0, stage * kABytes), db = umma_desc_advance(desc_b0, stage * Cfg::kBHalfBytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
-            umma2_f16(d_tmem, umma_desc_kmajor_sw128(a_base + k * 32), umma_desc_kmajor_sw128(b_base + k * 32), idesc,
-                      (kb | k) != 0);
+            umma2_f16_elect(d_tmem, umma_desc_advance(da, k * 32), umma_desc_advance(db, k * 32), idesc, (kb | k) != 0);
           }
-          umma2_commit_mc(&empty[stage]);
+          umma2_commit_mc_elect(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma2_commit_mc(&tmem_full[acc]);
+        umma2_commit_mc_elect(&tmem_full[acc]);
       }
     }
   } else if (warp == 2) {

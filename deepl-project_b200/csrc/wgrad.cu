@@ -73,7 +73,7 @@ mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* acc_full = bars + 2 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
@@ -96,7 +96,7 @@ mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   // ---- decode the work item of this CTA: (tap, k tile, n tile) x pixel split
   const int split = blockIdx.x % P.splits;
@@ -147,7 +147,7 @@ mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, elected lane issues (common.cuh: warp-uniform issue)
       constexpr uint32_t idesc = umma_idesc_bf16(128, KT, 1, 1);
       constexpr uint32_t idesc_ones = umma_idesc_bf16(128, 16, 1, 1);
       const uint64_t ones_desc = umma_desc_mnmajor_sw128(smem_u32(s_ones), kWgTile, 1024);
@@ -160,21 +160,21 @@ mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t a_base = dz_base + 2 * kWgTile;
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // 16 pixels per MMA
-          umma_f16(tmem_base, umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024),
+          umma_f16_elect(tmem_base, umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024),
                    umma_desc_mnmajor_sw128(a_base + k * 2048, kWgTile, 1024), idesc, (i | k) != 0);
         if (do_bias) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_f16(tmem_base + KT, umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024), ones_desc, idesc_ones,
+            umma_f16_elect(tmem_base + KT, umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024), ones_desc, idesc_ones,
                      (i | k) != 0);
         }
-        umma_commit(&empty[stage]);
+        umma_commit_elect(&empty[stage]);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(acc_full);
+      umma_commit_elect(acc_full);
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
@@ -251,7 +251,7 @@ mtwgrad2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   uint64_t* acc_full = bars + 2 * STAGES;  // each CTA's own
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   if (warp == 0 && lane == 0) {
@@ -279,7 +279,7 @@ mtwgrad2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   // ---- work item of this CTA pair: (tap, k tile of KT2, n tile of 256) x pixel split
   const int cluster_id = blockIdx.x >> 1;
@@ -329,7 +329,7 @@ mtwgrad2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {   // whole warp, elected lane issues (common.cuh: warp-uniform issue)
       constexpr uint32_t idesc = umma_idesc_bf16(256, KT2, 1, 1);
       constexpr uint32_t idesc_ones = umma_idesc_bf16(256, 16, 1, 1);
       const uint64_t ones_desc = umma_desc_mnmajor_sw128(smem_u32(s_ones), kWgTile, 1024);
@@ -342,21 +342,21 @@ mtwgrad2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const uint32_t a_base = dz_base + 2 * kWgTile;
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // 16 pixels per MMA
-          umma2_f16(tmem_base, umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024),
+          umma2_f16_elect(tmem_base, umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024),
                     umma_desc_mnmajor_sw128(a_base + k * 2048, kWgTile, 1024), idesc, (i | k) != 0);
         if (do_bias) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma2_f16(tmem_base + KT2, umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024), ones_desc, idesc_ones,
+            umma2_f16_elect(tmem_base + KT2, umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024), ones_desc, idesc_ones,
                       (i | k) != 0);
         }
-        umma2_commit_mc(&empty[stage]);
+        umma2_commit_mc_elect(&empty[stage]);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma2_commit_mc(acc_full);
+      umma2_commit_mc_elect(acc_full);
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
@@ -464,7 +464,7 @@ mtwgrad_t_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* acc_full = bars + 2 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
@@ -487,7 +487,7 @@ mtwgrad_t_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   // ---- work item: (phase, pair of chunk slots) x pixel split
   const int split = blockIdx.x % P.splits;
@@ -535,7 +535,7 @@ mtwgrad_t_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, elected lane issues (common.cuh: warp-uniform issue)
       constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
@@ -549,15 +549,15 @@ mtwgrad_t_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const uint32_t lbo = s1.tap >= 0 ? kWgTile : (s1.tap == -1 ? smem_u32(s_ones) - a_base : 0u);
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // 16 pixels per MMA
-          umma_f16(tmem_base, umma_desc_mnmajor_sw128(a_base + k * 2048, lbo, 1024),
+          umma_f16_elect(tmem_base, umma_desc_mnmajor_sw128(a_base + k * 2048, lbo, 1024),
                    umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024), idesc, (i | k) != 0);
-        umma_commit(&empty[stage]);
+        umma_commit_elect(&empty[stage]);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(acc_full);
+      umma_commit_elect(acc_full);
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
@@ -649,7 +649,7 @@ mtwgrad_h_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   uint64_t* acc_full = bars + 2 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmAh);
     tma_prefetch_desc(&tmDZ);
@@ -671,7 +671,7 @@ mtwgrad_h_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   // ---- work item: four consecutive slots x pixel split.  Slot s < 9 * kb: group s / 3 = (dy, chunk), dx = s % 3;
   // slot 9 * kb: the block of ones (when the bias gradient is wanted); beyond: empty.
@@ -725,7 +725,7 @@ mtwgrad_h_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, elected lane issues (common.cuh: warp-uniform issue)
       constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 1, 1);
       constexpr uint64_t bo_mask = ~(uint64_t(7) << 49);     // descriptor base offset 0: swizzle on absolute addresses
       const bool second = sl[2].group != -2;                 // slots 2 / 3 exist
@@ -745,21 +745,21 @@ mtwgrad_h_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // 16 pixels per MMA
-          umma_f16(tmem_base, umma_desc_mnmajor_sw128(addr[0] + k * 2048, addr[1] - addr[0], 1024) & bo_mask,
+          umma_f16_elect(tmem_base, umma_desc_mnmajor_sw128(addr[0] + k * 2048, addr[1] - addr[0], 1024) & bo_mask,
                    umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024), idesc, (i | k) != 0);
         if (second) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_f16(tmem_base + NT, umma_desc_mnmajor_sw128(addr[2] + k * 2048, addr[3] - addr[2], 1024) & bo_mask,
+            umma_f16_elect(tmem_base + NT, umma_desc_mnmajor_sw128(addr[2] + k * 2048, addr[3] - addr[2], 1024) & bo_mask,
                      umma_desc_mnmajor_sw128(dz_base + k * 2048, kWgTile, 1024), idesc, (i | k) != 0);
         }
-        umma_commit(&empty[stage]);
+        umma_commit_elect(&empty[stage]);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(acc_full);
+      umma_commit_elect(acc_full);
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
