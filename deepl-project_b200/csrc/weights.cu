@@ -156,4 +156,178 @@ int wgrad_unpack_run(const float* g, float* out, int A, int B, int T, cudaStream
   return 0;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Composite packs of the training step.  With differentiable torch expressions these were ~830 (QKV fold, 26 blocks) and
+// ~700 (Upsample conv1, 4 layers) tiny at:: launches per micro-step -- 5 ms of a 240 ms step (torch profiler,
+// profiles/r2i_at_sources.txt).  One kernel each way here; all reductions run in a fixed order (bit-reproducible).
+//
+// fold_qkv (attention.py:71-79: q = to_q(norm_q(x)) etc. with LayerNorm affines g, b):
+//     wg[s*C + n][k] = w_s[n][k] * g_s[k],      bg[s*C + n] = sum_k w_s[n][k] * b_s[k]             s = q, k, v
+// backward:
+//     dw_s[n][k] = dwg[s*C+n][k] * g_s[k] + dbg[s*C+n] * b_s[k]
+//     dg_s[k] = sum_n dwg[s*C+n][k] * w_s[n][k],     db_s[k] = sum_n dbg[s*C+n] * w_s[n][k]
+// -------------------------------------------------------------------------------------------------
+struct FoldPtrs {
+  const float* w[3];
+  const float* g[3];
+  const float* b[3];
+};
+struct FoldGradPtrs {
+  float* dw[3];
+  float* dg[3];
+  float* db[3];
+};
+
+__global__ void __launch_bounds__(256) fold_qkv_fwd_kernel(FoldPtrs P, float* __restrict__ wg, float* __restrict__ bg, int C) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);       // one warp per output row
+  const int lane = threadIdx.x & 31;
+  if (row >= 3 * C) return;
+  const int s = row / C, n = row - s * C;
+  const float* __restrict__ w = P.w[s] + (size_t)n * C;
+  const float* __restrict__ g = P.g[s];
+  const float* __restrict__ b = P.b[s];
+  float acc = 0.0f;
+  for (int k = lane * 4; k < C; k += 128) {                   // C % 4 == 0
+    const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(g + k));
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(b + k));
+    *reinterpret_cast<float4*>(wg + (size_t)row * C + k) = make_float4(wv.x * gv.x, wv.y * gv.y, wv.z * gv.z, wv.w * gv.w);
+    acc = fmaf(wv.x, bv.x, fmaf(wv.y, bv.y, fmaf(wv.z, bv.z, fmaf(wv.w, bv.w, acc))));
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) bg[row] = acc;
+}
+
+// block = (32 columns, source s); thread (column, row group of 8); the eight partial column sums meet in shared memory
+// and are added in a fixed order
+__global__ void __launch_bounds__(256) fold_qkv_bwd_kernel(FoldPtrs P, FoldGradPtrs G, const float* __restrict__ dwg,
+                                                           const float* __restrict__ dbg, int C) {
+  __shared__ float s_dg[8][32], s_db[8][32];
+  const int s = blockIdx.y;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const bool ok = c < C;
+  const float* __restrict__ w = P.w[s];
+  const float gc = ok ? __ldg(P.g[s] + c) : 0.0f, bc = ok ? __ldg(P.b[s] + c) : 0.0f;
+  float* __restrict__ dw = G.dw[s];
+  float dg = 0.0f, db = 0.0f;
+  if (ok) {
+#pragma unroll 4
+    for (int r = ty; r < C; r += 8) {
+      const float dv = __ldg(dwg + ((size_t)s * C + r) * C + c);
+      const float wv = __ldg(w + (size_t)r * C + c);
+      const float dbn = __ldg(dbg + s * C + r);
+      dw[(size_t)r * C + c] = fmaf(dv, gc, dbn * bc);
+      dg = fmaf(dv, wv, dg);
+      db = fmaf(dbn, wv, db);
+    }
+  }
+  s_dg[ty][tx] = dg;
+  s_db[ty][tx] = db;
+  __syncthreads();
+  if (ty == 0 && ok) {
+    float a = 0.0f, bsum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a += s_dg[j][tx];
+      bsum += s_db[j][tx];
+    }
+    G.dg[s][c] = a;
+    G.db[s][c] = bsum;
+  }
+}
+
+int fold_qkv_run(const float* const* w, const float* const* g, const float* const* b, float* wg, float* bg, int C,
+                 cudaStream_t stream) {
+  TVAE_REQUIRE(C % 4 == 0, "fold_qkv: C=%d must be a multiple of 4", C);
+  FoldPtrs P;
+  for (int i = 0; i < 3; ++i) {
+    P.w[i] = w[i];
+    P.g[i] = g[i];
+    P.b[i] = b[i];
+  }
+  fold_qkv_fwd_kernel<<<(3 * C + 7) / 8, 256, 0, stream>>>(P, wg, bg, C);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int fold_qkv_bwd_run(const float* const* w, const float* const* g, const float* const* b, const float* dwg, const float* dbg,
+                     float* const* dw, float* const* dg, float* const* db, int C, cudaStream_t stream) {
+  FoldPtrs P;
+  FoldGradPtrs G;
+  for (int i = 0; i < 3; ++i) {
+    P.w[i] = w[i];
+    P.g[i] = g[i];
+    P.b[i] = b[i];
+    G.dw[i] = dw[i];
+    G.dg[i] = dg[i];
+    G.db[i] = db[i];
+  }
+  fold_qkv_bwd_kernel<<<dim3((C + 31) / 32, 3), 256, 0, stream>>>(P, G, dwg, dbg, C);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Upsample conv1 (upsample.py:94-95: nearest 2x then 3x3, computed as four phase-specific 2x2 convolutions on the
+// low-resolution input): slab ((py*2 + px)*2 + a)*2 + b of the packed weight [O][16*I] is the sum of the 3x3 taps
+// (dy, dx) with dy in rows(py, a), dx in rows(px, b), rows(0, .) = {0}, {1, 2}; rows(1, .) = {0, 1}, {2}.
+// Forward: w[O][I][3][3] -> packed; backward: dw[o][i][dy][dx] = sum of the dpacked slabs that contain the tap.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int up_row_mask(int p, int a) {     // bit dy set: tap row dy belongs to rows(p, a)
+  return p == 0 ? (a == 0 ? 0b001 : 0b110) : (a == 0 ? 0b011 : 0b100);
+}
+
+__global__ void __launch_bounds__(256) upconv1_pack_kernel(const float* __restrict__ w, float* __restrict__ out, int O, int I) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (o, i), i fastest
+  if (idx >= (long long)O * I) return;
+  const int o = (int)(idx / I), i = (int)(idx - (long long)o * I);
+  float t[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) t[k] = __ldg(w + idx * 9 + k);
+#pragma unroll
+  for (int s = 0; s < 16; ++s) {
+    const int py = s >> 3, px = (s >> 2) & 1, a = (s >> 1) & 1, b = s & 1;
+    const int my = up_row_mask(py, a), mx = up_row_mask(px, b);
+    float acc = 0.0f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx)
+        if (((my >> dy) & 1) && ((mx >> dx) & 1)) acc += t[dy * 3 + dx];
+    out[(size_t)o * 16 * I + (size_t)s * I + i] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) upconv1_unpack_kernel(const float* __restrict__ dout, float* __restrict__ dw, int O, int I) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)O * I) return;
+  const int o = (int)(idx / I), i = (int)(idx - (long long)o * I);
+  float t[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) t[k] = 0.0f;
+#pragma unroll
+  for (int s = 0; s < 16; ++s) {
+    const int py = s >> 3, px = (s >> 2) & 1, a = (s >> 1) & 1, b = s & 1;
+    const int my = up_row_mask(py, a), mx = up_row_mask(px, b);
+    const float d = __ldg(dout + (size_t)o * 16 * I + (size_t)s * I + i);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx)
+        if (((my >> dy) & 1) && ((mx >> dx) & 1)) t[dy * 3 + dx] += d;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) dw[idx * 9 + k] = t[k];
+}
+
+int upconv1_pack_run(const float* w, float* out, int O, int I, int backward, cudaStream_t stream) {
+  const long long n = (long long)O * I;
+  const int blocks = (int)((n + 255) / 256);
+  if (backward) upconv1_unpack_kernel<<<blocks, 256, 0, stream>>>(w, out, O, I);
+  else upconv1_pack_kernel<<<blocks, 256, 0, stream>>>(w, out, O, I);
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace tvae

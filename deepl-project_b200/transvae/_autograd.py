@@ -51,6 +51,49 @@ _TORCH_PACK = os.environ.get("TVAE_TORCH_PACK", "0") == "1"
 _DIRECT = os.environ.get("TVAE_DIRECT_GRAD", "1") != "0"
 
 
+class FoldQkvFn(torch.autograd.Function):
+    """``_taps.fold_qkv_affine`` as one kernel each way (``ops.fold_qkv`` / ``ops.fold_qkv_bwd``)."""
+
+    @staticmethod
+    def forward(ctx, wq, wk, wv, gq, bq, gk, bk, gv, bv):
+        ts = [t.detach().float().contiguous() for t in (wq, wk, wv, gq, bq, gk, bk, gv, bv)]
+        ctx.save_for_backward(*ts)
+        return ops.fold_qkv(ts[0:3], ts[3::2], ts[4::2])
+
+    @staticmethod
+    def backward(ctx, dwg, dbg):
+        ts = ctx.saved_tensors
+        dw, dg, db = ops.fold_qkv_bwd(ts[0:3], ts[3::2], ts[4::2], dwg, dbg)
+        return dw[0], dw[1], dw[2], dg[0], db[0], dg[1], db[1], dg[2], db[2]
+
+
+class UpConv1PackFn(torch.autograd.Function):
+    """``_taps.pack_upsample_conv1`` as one kernel each way (``ops.upconv1_pack``)."""
+
+    @staticmethod
+    def forward(ctx, w):
+        return ops.upconv1_pack(w.detach())
+
+    @staticmethod
+    def backward(ctx, dpacked):
+        return ops.upconv1_pack(dpacked, backward=True)
+
+
+def fold_qkv_affine(wq, wk, wv, gq, bq, gk, bk, gv, bv):
+    """Device tensors: the kernels; anything else (CPU unit tests of the host logic): the torch expression."""
+    if wq.is_cuda:
+        return FoldQkvFn.apply(wq, wk, wv, gq, bq, gk, bk, gv, bv)
+    from . import _taps
+    return _taps.fold_qkv_affine(wq, wk, wv, gq, bq, gk, bk, gv, bv)
+
+
+def pack_upsample_conv1(w):
+    if w.is_cuda:
+        return UpConv1PackFn.apply(w)
+    from . import _taps
+    return _taps.pack_upsample_conv1(w)
+
+
 _PACKS: dict = {}          # id(parameter) -> (signature, (forward operand, input-gradient operand))
 
 

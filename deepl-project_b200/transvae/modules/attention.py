@@ -88,8 +88,8 @@ class FlashAttentionWithRoPE(HotModule):
         if K.needs_grad(x, w1, *self.parameters()):
             if not (add_residual and rms):
                 raise NotImplementedError("bare attention (no RMSNorm / no residual) is an inference-only hook")
-            from .._autograd import AttnFn
-            wg, bg = T.fold_qkv_affine(self.to_q.weight, self.to_k.weight, self.to_v.weight, self.norm_q.weight,
+            from .._autograd import AttnFn, fold_qkv_affine
+            wg, bg = fold_qkv_affine(self.to_q.weight, self.to_k.weight, self.to_v.weight, self.norm_q.weight,
                                        self.norm_q.bias, self.norm_k.weight, self.norm_k.bias, self.norm_v.weight,
                                        self.norm_v.bias)
             return AttnFn.apply(x, w1, wg, bg, self.proj.weight, self.proj.bias, self._rope_tab(H, W), self.scale)

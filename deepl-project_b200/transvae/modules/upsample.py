@@ -68,8 +68,8 @@ class Upsample(HotModule):
         dc = self.dc_conv if self.use_dc_path else None
         wdc, bdc = (dc.weight, dc.bias) if dc is not None else (None, None)
         if K.needs_grad(x, *self.parameters()):
-            from .._autograd import UpsampleFn
-            return UpsampleFn.apply(x, T.pack_upsample_conv1(m1.weight), m1.bias, T.pack_upsample_conv2(m3.weight, wdc),
+            from .._autograd import UpsampleFn, pack_upsample_conv1
+            return UpsampleFn.apply(x, pack_upsample_conv1(m1.weight), m1.bias, T.pack_upsample_conv2(m3.weight, wdc),
                                     T.bias_upsample_conv2(m3.bias, bdc))
         w1 = self._packs.get("m1", [m1.weight], lambda: bf16c(T.pack_upsample_conv1(m1.weight)))
         b1 = self._packs.get("b1", [m1.bias], lambda: f32c(m1.bias.unsqueeze(0).expand(4, -1)))

@@ -611,6 +611,56 @@ def wgrad_unpack(g: Tensor, shape: Sequence[int]) -> Tensor:
     return out
 
 
+def _ptr3(ts: Sequence[Tensor]):
+    import ctypes
+    return (ctypes.c_void_p * 3)(*[t.data_ptr() for t in ts])
+
+
+def fold_qkv(w3: Sequence[Tensor], g3: Sequence[Tensor], b3: Sequence[Tensor]) -> Tuple[Tensor, Tensor]:
+    """([Wq g_q; Wk g_k; Wv g_v] fp32 [3C, C], [Wq b_q; Wk b_k; Wv b_v] fp32 [3C]) in one launch (``tvae_fold_qkv``; the
+    torch expression is ``_taps.fold_qkv_affine``)."""
+    C_ = w3[0].shape[0]
+    for t in (*w3, *g3, *b3):
+        _need_cuda(t)
+        assert t.dtype == torch.float32 and t.is_contiguous(), (t.dtype, t.shape)
+    wg = torch.empty(3 * C_, C_, dtype=torch.float32, device=w3[0].device)
+    bg = torch.empty(3 * C_, dtype=torch.float32, device=w3[0].device)
+    _lib.check(_lib.load().tvae_fold_qkv(_ptr3(w3), _ptr3(g3), _ptr3(b3), wg.data_ptr(), bg.data_ptr(), C_, _stream()),
+               "tvae_fold_qkv")
+    _count()
+    return wg, bg
+
+
+def fold_qkv_bwd(w3, g3, b3, dwg: Tensor, dbg: Tensor):
+    """Gradients of the nine inputs of ``fold_qkv`` (three lists: dw [C, C], dg [C], db [C])."""
+    C_ = w3[0].shape[0]
+    dwg, dbg = dwg.float().contiguous(), dbg.float().contiguous()
+    dev = dwg.device
+    dw = [torch.empty(C_, C_, dtype=torch.float32, device=dev) for _ in range(3)]
+    dg = [torch.empty(C_, dtype=torch.float32, device=dev) for _ in range(3)]
+    db = [torch.empty(C_, dtype=torch.float32, device=dev) for _ in range(3)]
+    _lib.check(_lib.load().tvae_fold_qkv_bwd(_ptr3(w3), _ptr3(g3), _ptr3(b3), dwg.data_ptr(), dbg.data_ptr(), _ptr3(dw),
+                                             _ptr3(dg), _ptr3(db), C_, _stream()), "tvae_fold_qkv_bwd")
+    _count()
+    return dw, dg, db
+
+
+def upconv1_pack(t: Tensor, backward: bool = False) -> Tensor:
+    """Upsample conv1 weight [O, I, 3, 3] -> phase-packed [O, 16*I] (``_taps.pack_upsample_conv1``), or -- backward -- the
+    packed gradient [O, 16*I] -> [O, I, 3, 3]."""
+    _need_cuda(t)
+    t = t.float().contiguous()
+    if backward:
+        O, I = t.shape[0], t.shape[1] // 16
+        out = torch.empty(O, I, 3, 3, dtype=torch.float32, device=t.device)
+    else:
+        O, I = t.shape[0], t.shape[1]
+        out = torch.empty(O, 16 * I, dtype=torch.float32, device=t.device)
+    _lib.check(_lib.load().tvae_upconv1_pack(t.data_ptr(), out.data_ptr(), O, I, int(backward), _stream()), "tvae_upconv1_pack")
+    _count()
+    return out
+
+
 SUMSQ_BLOCKS = 1024          # TVAE_SUMSQ_BLOCKS
 
 

@@ -332,3 +332,37 @@ def test_multi_tensor_add_and_cast():
     y = torch.empty(4096, dtype=torch.bfloat16, device=DEV)
     ops.cast_f32_bf16(x, y)
     assert torch.equal(y, x.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("C", [64, 384, 1280])
+def test_fold_qkv_kernels_match_the_torch_expression(C):
+    """ops.fold_qkv / fold_qkv_bwd (one launch each way) against _taps.fold_qkv_affine and its autograd gradients."""
+    from transvae._autograd import FoldQkvFn
+    ts = [rnd(C, C, seed=s, scale=0.05) for s in range(3)] + [rnd(C, seed=10 + s) for s in range(6)]
+    a = [t.clone().requires_grad_(True) for t in ts]
+    b = [t.clone().requires_grad_(True) for t in ts]
+    wg, bg = FoldQkvFn.apply(*a)
+    wr, br = T.fold_qkv_affine(*b)
+    assert torch.equal(wg, wr) and rel(bg, br) < 1e-5
+    dwg, dbg = rnd(3 * C, C, seed=20), rnd(3 * C, seed=21)
+    torch.autograd.backward([wg, bg], [dwg, dbg])
+    torch.autograd.backward([wr, br], [dwg, dbg])
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert rel(x.grad, y.grad) < 2e-5, (i, rel(x.grad, y.grad))
+    # fixed-order reductions: a second run is bit-identical
+    a2 = [t.clone().requires_grad_(True) for t in ts]
+    torch.autograd.backward(list(FoldQkvFn.apply(*a2)), [dwg, dbg])
+    assert all(torch.equal(x.grad, y.grad) for x, y in zip(a, a2))
+
+
+@pytest.mark.parametrize("O,I", [(64, 128), (192, 192)])
+def test_upconv1_pack_kernels_match_the_torch_expression(O, I):
+    from transvae._autograd import UpConv1PackFn
+    w = rnd(O, I, 3, 3, seed=3)
+    a, b = w.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    pa, pb = UpConv1PackFn.apply(a), T.pack_upsample_conv1(b)
+    assert pa.shape == pb.shape and rel(pa, pb) < 1e-6
+    d = rnd(O, 16 * I, seed=4)
+    pa.backward(d)
+    pb.backward(d)
+    assert rel(a.grad, b.grad) < 1e-6
