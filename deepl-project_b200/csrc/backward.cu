@@ -206,19 +206,21 @@ __device__ __forceinline__ void gn_load_chan(GnChan& ch, const double* sums, con
   }
 }
 
+constexpr int kGnMaxImages = 4096;
+__device__ unsigned int g_gn_ticket[kGnMaxImages];     // zero-initialised; every launch leaves it at zero
+
 template <bool SILU>
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dh,
                                                             const double* __restrict__ sums,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            float* __restrict__ part, int HW, int C, int G, float eps,
-                                                            int pix_per_block) {
-  extern __shared__ float s_part[];   // [C][2]
+                                                            float* __restrict__ part, float* __restrict__ ws, int HW, int C,
+                                                            int G, float eps, int pix_per_block) {
+  extern __shared__ __align__(16) float s_stage[];   // [pixel rows of the block][C][2]
+  __shared__ bool s_last;
   const int nvec = C >> 3, cpg = C / G;
   const int b = blockIdx.y;
   const int v = threadIdx.x % nvec, pv = threadIdx.x / nvec, ppb = blockDim.x / nvec;
   const float inv_n = 1.0f / ((float)cpg * (float)HW);
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_part[i] = 0.0f;
-  __syncthreads();
   GnChan ch;
   gn_load_chan(ch, sums, gamma, beta, b, G, cpg, v, inv_n, eps);
   float2 s1[4], s2[4];
@@ -252,19 +254,39 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const uint4* __restr
       }
     }
   }
-  // block-level reduction in shared memory, then ONE global atomic per (channel, statistic) and block: the first version
-  // sent every thread's 16 partials straight to global memory -- 320 contended atomics per address and launch, which
-  // held the kernel at 2.1 TB/s while the (atomic-free) apply pass ran at 5.5 TB/s
+  // Fixed-order reduction, no atomics on the values (two backward passes are bit-identical): the threads of a block stage
+  // their 16 partials, one thread per (channel, statistic) adds the block's pixel rows in order and stores the block
+  // partial; the last block of the image to arrive (ticket counter) adds the block partials in block order.  (History:
+  // per-thread global atomics held the kernel at 2.1 TB/s; shared + one global atomic per block ran at 4.4 TB/s but made
+  // GroupNorm-backward the first kernel of the step whose output changed from run to run.)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float* pp = s_part + (v * 8 + 2 * i) * 2;
-    atomicAdd(pp, s1[i].x);
-    atomicAdd(pp + 1, s2[i].x);
-    atomicAdd(pp + 2, s1[i].y);
-    atomicAdd(pp + 3, s2[i].y);
+    float* pp = s_stage + (size_t)pv * 2 * C + (v * 8 + 2 * i) * 2;
+    *reinterpret_cast<float4*>(pp) = make_float4(s1[i].x, s2[i].x, s1[i].y, s2[i].y);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(part + (size_t)b * C * 2 + i, s_part[i]);
+  float* mine = ws + ((size_t)b * gridDim.x + blockIdx.x) * 2 * C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float a = 0.0f;
+    for (int r = 0; r < ppb; ++r) a += s_stage[(size_t)r * 2 * C + i];
+    mine[i] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(&g_gn_ticket[b], gridDim.x - 1);   // wraps to 0: ready for the next launch
+    s_last = t == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const float* all = ws + (size_t)b * gridDim.x * 2 * C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+      float a = 0.0f;
+      for (unsigned int k = 0; k < gridDim.x; ++k) a += __ldcg(all + (size_t)k * 2 * C + i);
+      part[(size_t)b * C * 2 + i] = a;
+    }
+  }
 }
 
 template <bool SILU, bool ADD>
@@ -339,7 +361,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restri
 int gn_bwd_run(const void* x, const void* dh, const void* add, const double* sums, const float* gamma, const float* beta,
                float* part, void* dx, int B, int HW, int C, int G, float eps, int apply_silu, cudaStream_t stream) {
   TVAE_REQUIRE(C % 8 == 0 && C % G == 0 && C / 8 <= 256 && G <= 128, "groupnorm_bwd: unsupported C=%d G=%d", C, G);
-  TVAE_CHECK_CUDA(cudaMemsetAsync(part, 0, (size_t)B * C * 2 * sizeof(float), stream));
+  TVAE_REQUIRE(B <= kGnMaxImages, "groupnorm_bwd: batch %d exceeds %d", B, kGnMaxImages);
   const int nvec = C / 8;
   const int threads = (256 / nvec) * nvec;
   int ppb = 1024;
@@ -348,9 +370,14 @@ int gn_bwd_run(const void* x, const void* dh, const void* add, const double* sum
   const uint4* xp = reinterpret_cast<const uint4*>(x);
   const uint4* dp = reinterpret_cast<const uint4*>(dh);
   const uint4* ap = reinterpret_cast<const uint4*>(add);
-  const size_t smem_r = 2 * (size_t)C * sizeof(float);
-  if (apply_silu) gn_bwd_reduce_kernel<true><<<g1, threads, smem_r, stream>>>(xp, dp, sums, gamma, beta, part, HW, C, G, eps, ppb);
-  else gn_bwd_reduce_kernel<false><<<g1, threads, smem_r, stream>>>(xp, dp, sums, gamma, beta, part, HW, C, G, eps, ppb);
+  const size_t smem_r = (size_t)(threads / nvec) * 2 * C * sizeof(float);       // <= 16 KiB
+  float* ws = nullptr;
+  {
+    const int rc = scratch_workspace((size_t)B * g1.x * 2 * C * sizeof(float), reinterpret_cast<void**>(&ws));
+    if (rc) return rc;
+  }
+  if (apply_silu) gn_bwd_reduce_kernel<true><<<g1, threads, smem_r, stream>>>(xp, dp, sums, gamma, beta, part, ws, HW, C, G, eps, ppb);
+  else gn_bwd_reduce_kernel<false><<<g1, threads, smem_r, stream>>>(xp, dp, sums, gamma, beta, part, ws, HW, C, G, eps, ppb);
   TVAE_CHECK_CUDA(cudaGetLastError());
   const long long total = (long long)HW * nvec;
   long long vpb = (long long)threads * kEwBatch * 4;

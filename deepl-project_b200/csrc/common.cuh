@@ -44,6 +44,7 @@ const char* get_last_error();
 int num_sms();
 int persistent_sms();   // num_sms() minus the SMs reserved for a concurrent collective
 void set_reserved_sms(int n);
+int scratch_workspace(size_t bytes, void** out);   // per-device scratch of the fixed-order reductions (runtime.cu)
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

@@ -430,6 +430,13 @@ int reparam_run(const float* mu, const float* logvar, const float* eps, float* z
 //   acc[2] += number of non-finite terms (cheap isfinite flag, no host sync)
 // The caller divides by the element counts the reference uses.
 // -------------------------------------------------------------------------------------------------
+// Cross-block reduction without atomics on the values: every block stores its three partial sums, the last block to
+// arrive (ticket counter) adds them in block order -- the loss terms are bit-reproducible from run to run.  (Launches of
+// this kernel are ordered on one stream, so one staging array per device is enough.)
+constexpr int kLossMaxBlocks = 1024;
+__device__ float g_loss_part[3][kLossMaxBlocks];
+__device__ unsigned int g_loss_ticket = 0;
+
 __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ recon, const float* __restrict__ target,
                                                    const float* __restrict__ mu, const float* __restrict__ logvar,
                                                    float* __restrict__ acc, long long n_img, long long n_lat,
@@ -474,10 +481,29 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ rec
     kl = lane < 8 ? red[1][lane] : 0.0f;
     bad = lane < 8 ? red[2][lane] : 0.0f;
     l1 = warp_sum(l1); kl = warp_sum(kl); bad = warp_sum(bad);
+    unsigned int ticket = 0;
     if (lane == 0) {
-      atomicAdd(acc + 0, l1);
-      atomicAdd(acc + 1, kl);
-      atomicAdd(acc + 2, bad);
+      g_loss_part[0][blockIdx.x] = l1;
+      g_loss_part[1][blockIdx.x] = kl;
+      g_loss_part[2][blockIdx.x] = bad;
+      __threadfence();
+      ticket = atomicInc(&g_loss_ticket, gridDim.x - 1);      // wraps to 0 after the last block: ready for the next launch
+    }
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket == gridDim.x - 1) {
+      __threadfence();
+      float t[3] = {0.0f, 0.0f, 0.0f};
+      for (int i = lane; i < (int)gridDim.x; i += 32) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t[k] += __ldcg(&g_loss_part[k][i]);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t[k] = warp_sum(t[k]);
+      if (lane == 0) {
+        acc[0] = t[0];
+        acc[1] = t[1];
+        acc[2] = t[2];
+      }
     }
   }
 }
@@ -487,6 +513,7 @@ int loss_run(const float* recon, const float* target, const float* mu, const flo
   TVAE_CHECK_CUDA(cudaMemsetAsync(acc, 0, 4 * sizeof(float), stream));
   int grid = (int)((n_img / 4 + 255) / 256);
   if (grid > num_sms() * 4) grid = num_sms() * 4;
+  if (grid > kLossMaxBlocks) grid = kLossMaxBlocks;
   if (grid < 1) grid = 1;
   loss_kernel<<<grid, 256, 0, stream>>>(recon, target, mu, logvar, acc, n_img, n_lat, patched, clip_lo, clip_hi);
   TVAE_CHECK_CUDA(cudaGetLastError());

@@ -34,6 +34,28 @@ int num_sms() {
 // SMs the persistent (one CTA per SM) kernels may occupy: all of them, minus the ones left to a concurrent NCCL
 // collective while gradient buckets are all-reduced under the backward pass (tvae_set_reserved_sms).
 static int g_reserved_sms = 0;
+// Scratch workspace of the fixed-order reductions (weight-gradient split slices, GroupNorm-backward block partials): grown
+// on demand, kept per device.  Every user fills and consumes it with kernels enqueued by ONE C-ABI call on the one compute
+// stream, so consecutive users are ordered; growing synchronises (cudaFree).
+int scratch_workspace(size_t bytes, void** out) {
+  constexpr int kMaxDev = 16;
+  static void* ws[kMaxDev] = {};
+  static size_t cap[kMaxDev] = {};
+  int dev = 0;
+  TVAE_CHECK_CUDA(cudaGetDevice(&dev));
+  TVAE_REQUIRE(dev >= 0 && dev < kMaxDev, "scratch_workspace: device index %d out of range", dev);
+  if (cap[dev] < bytes) {
+    if (ws[dev] != nullptr) TVAE_CHECK_CUDA(cudaFree(ws[dev]));
+    ws[dev] = nullptr;
+    cap[dev] = 0;
+    const size_t want = bytes + bytes / 4;
+    TVAE_CHECK_CUDA(cudaMalloc(&ws[dev], want));
+    cap[dev] = want;
+  }
+  *out = ws[dev];
+  return 0;
+}
+
 void set_reserved_sms(int n) { g_reserved_sms = n < 0 ? 0 : n; }
 int persistent_sms() {
   const int n = num_sms();

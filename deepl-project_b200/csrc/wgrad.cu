@@ -43,7 +43,38 @@ struct WgParams {
   int first_tap[TVAE_MAX_PHASES];   // index of the first tap of each phase (its k-tile-0 CTAs also produce db)
   int num_phases;
   int items_per_phase[TVAE_MAX_PHASES];   // transposed kernel: ceil((chunks + bias slot) / 2)
+  // Deterministic split reduction: with more than one pixel split per block, split s writes its partial block with plain
+  // stores into slice s of a workspace (dw / db then point INTO the workspace, slices ws_dw_stride / ws_db_stride floats
+  // apart) and wgrad_reduce_kernel adds the slices to the gradient in a fixed order.  0 = one split: the single writer of
+  // every element accumulates straight into the gradient (atomicAdd, but with one writer per launch the order is fixed).
+  long long ws_dw_stride, ws_db_stride;
+  // phases that share weight slabs (Upsample conv2: the 3x3 taps of all four output phases) would overwrite each other's
+  // partials: such plans get one slice per (split, phase) -- slice = split * ws_phases + phase -- of a zero-filled workspace
+  int ws_phases;
 };
+
+// accumulate (single writer) or store (workspace slice)
+__device__ __forceinline__ void wg_out(float* p, float v, bool plain) {
+  if (plain) *p = v;
+  else atomicAdd(p, v);
+}
+__device__ __forceinline__ void wg_out4(float* p, float4 v, bool plain) {
+  if (plain) *reinterpret_cast<float4*>(p) = v;
+  else atomicAdd(reinterpret_cast<float4*>(p), v);
+}
+
+// gradient += sum over the slices, in slice order (bit-reproducible); n % 4 == 0
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(float* __restrict__ g, const float* __restrict__ ws, long long n,
+                                                           long long stride, int splits) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float4 a = *reinterpret_cast<const float4*>(g + i);
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(ws + (size_t)s * stride + i));
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  *reinterpret_cast<float4*>(g + i) = a;
+}
 
 constexpr int kWgTile = 128 * 64 * 2;  // one [128 pixels x 64 channels] bf16 box
 
@@ -182,7 +213,9 @@ mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (my_tiles > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
-      float* dst = P.dw + (size_t)n * P.k_total + tap.wk_off + kt * KT;
+      const bool plain = P.ws_dw_stride != 0;
+      const size_t slice = (size_t)split * P.ws_phases + (P.ws_phases > 1 ? tap.ph : 0);
+      float* dst = P.dw + slice * P.ws_dw_stride + (size_t)n * P.k_total + tap.wk_off + kt * KT;
 #pragma unroll 1
       for (int c = 0; c < KT / 32; ++c) {
         uint32_t v[32];
@@ -193,7 +226,7 @@ mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int g = 0; g < 8; ++g) {
             float4 f = make_float4(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1]),
                                    __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
-            atomicAdd(reinterpret_cast<float4*>(dst + c * 32 + g * 4), f);
+            wg_out4(dst + c * 32 + g * 4, f, plain);
           }
         }
       }
@@ -201,7 +234,7 @@ mtwgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         uint32_t v[16];
         tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + KT, v);
         tmem_ld_wait();
-        if (n < P.n_total) atomicAdd(P.db + (size_t)tap.ph * P.n_total + n, __uint_as_float(v[0]));
+        if (n < P.n_total) wg_out(P.db + slice * P.ws_db_stride + (size_t)tap.ph * P.n_total + n, __uint_as_float(v[0]), plain);
       }
     }
   }
@@ -364,7 +397,9 @@ mtwgrad2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     if (my_tiles > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
-      float* dst = P.dw + (size_t)n * P.k_total + tap.wk_off + kt * KT2;
+      const bool plain = P.ws_dw_stride != 0;
+      const size_t slice = (size_t)split * P.ws_phases + (P.ws_phases > 1 ? tap.ph : 0);
+      float* dst = P.dw + slice * P.ws_dw_stride + (size_t)n * P.k_total + tap.wk_off + kt * KT2;
 #pragma unroll 1
       for (int c = 0; c < KT2 / 32; ++c) {
         uint32_t v[32];
@@ -374,14 +409,14 @@ mtwgrad2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         for (int g = 0; g < 8; ++g) {
           float4 f = make_float4(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1]),
                                  __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
-          atomicAdd(reinterpret_cast<float4*>(dst + c * 32 + g * 4), f);
+          wg_out4(dst + c * 32 + g * 4, f, plain);
         }
       }
       if (do_bias) {
         uint32_t v[16];
         tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + KT2, v);
         tmem_ld_wait();
-        atomicAdd(P.db + (size_t)tap.ph * P.n_total + n, __uint_as_float(v[0]));
+        wg_out(P.db + slice * P.ws_db_stride + (size_t)tap.ph * P.n_total + n, __uint_as_float(v[0]), plain);
       }
     }
   }
@@ -570,11 +605,11 @@ mtwgrad_t_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       size_t stride = 0;
       bool ok = false;
       if (sl.tap >= 0) {                           // dW[n][wk_off + chunk * 64 + kk], consecutive lanes -> consecutive kk
-        dst = P.dw + P.taps[sl.tap].wk_off + sl.chunk * 64 + (row & 63);
+        dst = P.dw + ((size_t)split * P.ws_phases + (P.ws_phases > 1 ? ph : 0)) * P.ws_dw_stride + P.taps[sl.tap].wk_off + sl.chunk * 64 + (row & 63);
         stride = (size_t)P.k_total;
         ok = true;
       } else if (sl.tap == -1 && (row & 63) == 0) {   // all 64 rows of the ones slot hold the same column sums
-        dst = P.db + (size_t)ph * P.n_total;
+        dst = P.db + ((size_t)split * P.ws_phases + (P.ws_phases > 1 ? ph : 0)) * P.ws_db_stride + (size_t)ph * P.n_total;
         stride = 1;
         ok = true;
       }
@@ -585,7 +620,7 @@ mtwgrad_t_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         tmem_ld_wait();
         if (ok) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)(c * 32 + j) * stride, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) wg_out(dst + (size_t)(c * 32 + j) * stride, __uint_as_float(v[j]), P.ws_dw_stride != 0);
         }
       }
     }
@@ -774,10 +809,10 @@ mtwgrad_h_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
         size_t stride = 0;
         if (s.group >= 0) {                        // dW[n][wk_off(dy, dx) + chunk * 64 + c]
           const int dy = s.group / kb, chunk = s.group % kb;
-          dst = P.dw + P.taps[dy * 3 + s.dx].wk_off + chunk * 64 + (row & 63);
+          dst = P.dw + (size_t)split * P.ws_dw_stride + P.taps[dy * 3 + s.dx].wk_off + chunk * 64 + (row & 63);
           stride = (size_t)P.k_total;
         } else if (s.group == -1 && (row & 63) == 0) {   // all 64 rows of the ones slot hold the same column sums
-          dst = P.db;
+          dst = P.db + (size_t)split * P.ws_db_stride;
           stride = 1;
         }
         if (sl[2 * a].group == -2) continue;       // this accumulator was never written (warp-uniform)
@@ -788,7 +823,7 @@ mtwgrad_h_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
           tmem_ld_wait();
           if (dst != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)(c * 32 + j) * stride, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j) wg_out(dst + (size_t)(c * 32 + j) * stride, __uint_as_float(v[j]), P.ws_dw_stride != 0);
           }
         }
       }
@@ -969,20 +1004,60 @@ int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, float* db, cudaStream_t st
     mA1 = mA0;
   }
   if ((rc = make_tmap_pix(&mDZ, d->out.ptr, d->out.B, d->out.H, d->out.W, d->out.C, d->out.split, P.tw, P.th, P.nb))) return rc;
+  // more than one pixel split: partial blocks go to workspace slices, a second launch adds them in slice order
+  // (TVAE_WGRAD_DET=0: atomics straight into the gradient, the A/B switch; TVAE_WGRAD_WS_POISON=1: NaN-filled workspace,
+  // so a block that some split fails to write shows up in the tests)
+  static const bool det = !(getenv("TVAE_WGRAD_DET") && atoi(getenv("TVAE_WGRAD_DET")) == 0);
+  static const bool poison = getenv("TVAE_WGRAD_WS_POISON") && atoi(getenv("TVAE_WGRAD_WS_POISON")) != 0;
+  const long long n_dw = (long long)d->n_total * P.k_total, n_db = db != nullptr ? (long long)d->num_phases * d->n_total : 0;
+  float* ws = nullptr;
+  bool shared_slabs = false;     // two phases writing the same weight columns
+  for (int i = 0; i < nt && !shared_slabs; ++i)
+    for (int j = i + 1; j < nt; ++j)
+      if (P.taps[i].ph != P.taps[j].ph && P.taps[i].wk_off == P.taps[j].wk_off) {
+        shared_slabs = true;
+        break;
+      }
+  P.ws_phases = shared_slabs ? d->num_phases : 1;
+  const long long slices = splits * P.ws_phases;
+  if (det && slices > 1) {
+    const size_t need = (size_t)slices * (size_t)(n_dw + n_db) * sizeof(float);
+    if ((rc = scratch_workspace(need, reinterpret_cast<void**>(&ws)))) return rc;
+    if (shared_slabs) TVAE_CHECK_CUDA(cudaMemsetAsync(ws, 0, need, stream));   // a phase writes only its own slabs
+    else if (poison) TVAE_CHECK_CUDA(cudaMemsetAsync(ws, 0xFF, need, stream));
+    P.dw = ws;
+    P.ws_dw_stride = n_dw;
+    if (db != nullptr) {
+      P.db = ws + (size_t)slices * n_dw;
+      P.ws_db_stride = n_db;
+    }
+  } else {
+    P.ws_phases = 1;
+  }
   if (halo) {
-    return d->n_total == 192 ? launch_wgh<192>(mA0, mDZ, P, (int)grid, stream) : launch_wgh<64>(mA0, mDZ, P, (int)grid, stream);
+    rc = d->n_total == 192 ? launch_wgh<192>(mA0, mDZ, P, (int)grid, stream) : launch_wgh<64>(mA0, mDZ, P, (int)grid, stream);
+  } else if (transposed) {
+    rc = d->n_total == 192 ? launch_wgt<192>(mA0, mA1, mDZ, P, (int)grid, stream)
+                           : launch_wgt<64>(mA0, mA1, mDZ, P, (int)grid, stream);
+  } else if (pair) {
+    rc = launch_wg2<256>(mA0, mA1, mDZ, P, (int)grid, stream);
+  } else {
+    switch (kt) {
+      case 256: rc = launch_wg<256>(mA0, mA1, mDZ, P, (int)grid, stream); break;
+      case 192: rc = launch_wg<192>(mA0, mA1, mDZ, P, (int)grid, stream); break;
+      case 128: rc = launch_wg<128>(mA0, mA1, mDZ, P, (int)grid, stream); break;
+      default: rc = launch_wg<64>(mA0, mA1, mDZ, P, (int)grid, stream); break;
+    }
   }
-  if (transposed) {
-    return d->n_total == 192 ? launch_wgt<192>(mA0, mA1, mDZ, P, (int)grid, stream)
-                             : launch_wgt<64>(mA0, mA1, mDZ, P, (int)grid, stream);
+  if (rc) return rc;
+  if (ws != nullptr) {
+    wgrad_reduce_kernel<<<(unsigned)((n_dw / 4 + 255) / 256), 256, 0, stream>>>(dw, ws, n_dw, n_dw, (int)slices);
+    if (db != nullptr)
+      wgrad_reduce_kernel<<<(unsigned)((n_db / 4 + 255) / 256), 256, 0, stream>>>(db, ws + (size_t)slices * n_dw, n_db, n_db,
+                                                                                  (int)slices);
+    TVAE_CHECK_CUDA(cudaGetLastError());
   }
-  if (pair) return launch_wg2<256>(mA0, mA1, mDZ, P, (int)grid, stream);
-  switch (kt) {
-    case 256: return launch_wg<256>(mA0, mA1, mDZ, P, (int)grid, stream);
-    case 192: return launch_wg<192>(mA0, mA1, mDZ, P, (int)grid, stream);
-    case 128: return launch_wg<128>(mA0, mA1, mDZ, P, (int)grid, stream);
-    default: return launch_wg<64>(mA0, mA1, mDZ, P, (int)grid, stream);
-  }
+  return 0;
 }
 
 }  // namespace tvae
