@@ -31,10 +31,11 @@ int token_norm_fwd_run(const void* x, const float* w, void* y, long long M, int 
 int token_norm_bwd_run(const void* x, const float* w, const void* dy, const void* add, void* dx, float* dw, long long M,
                        int C, int mode, cudaStream_t stream);
 int attn_delta_run(const void* o, const void* dout, float* delta, int B, int S, int C, cudaStream_t stream);
+int attn_bwd_dq_slices(int S);
 int attn_bwd_run(const void* qkv, const void* dout, const float* lse, const float* delta, float* dq_acc, void* dqkv, int B,
-                 int S, int C, cudaStream_t stream);
+                 int S, int C, int dq_slices, cudaStream_t stream);
 int rope_bwd_run(const float* dq_acc, void* dqkv, const float* tab, long long M, int C, int H, int W, float q_scale,
-                 cudaStream_t stream);
+                 int dq_slices, cudaStream_t stream);
 int loss_bwd_run(const float* recon, const float* target, const float* mu, const float* logvar, const float* scal,
                  float* drecon, float* dmu, float* dlv, long long n_img, long long n_lat, int patched, float clip_lo,
                  float clip_hi, cudaStream_t stream);
@@ -166,13 +167,14 @@ int tvae_token_norm_bwd(const void* x, const float* w, const void* dy, const voi
 int tvae_attn_delta(const void* out, const void* dout, float* delta, int32_t B, int32_t S, int32_t C, void* stream) {
   GUARD(); return attn_delta_run(out, dout, delta, B, S, C, S_(stream));
 }
+int tvae_attn_bwd_dq_slices(int32_t S) { return attn_bwd_dq_slices(S); }
 int tvae_attn_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, float* dq_acc, void* dqkv, int32_t B,
-                  int32_t S, int32_t C, void* stream) {
-  GUARD(); return attn_bwd_run(qkv, dout, lse, delta, dq_acc, dqkv, B, S, C, S_(stream));
+                  int32_t S, int32_t C, int32_t dq_slices, void* stream) {
+  GUARD(); return attn_bwd_run(qkv, dout, lse, delta, dq_acc, dqkv, B, S, C, dq_slices, S_(stream));
 }
 int tvae_rope_bwd(const float* dq_acc, void* dqkv, const float* rope_tab, int64_t M, int32_t C, int32_t H, int32_t W,
-                  float q_scale, void* stream) {
-  GUARD(); return rope_bwd_run(dq_acc, dqkv, rope_tab, M, C, H, W, q_scale, S_(stream));
+                  float q_scale, int32_t dq_slices, void* stream) {
+  GUARD(); return rope_bwd_run(dq_acc, dqkv, rope_tab, M, C, H, W, q_scale, dq_slices, S_(stream));
 }
 int tvae_loss_bwd(const float* recon, const float* target, const float* mu, const float* logvar, const float* scal,
                   float* drecon, float* dmu, float* dlogvar, int64_t n_img, int64_t n_lat, int32_t patched, float clip_lo,

@@ -38,6 +38,15 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // 2^x for two lanes on the FMA pipe (see attention.cu: round-to-nearest split with the 1.5 * 2^23 trick, degree-3 minimax
 // polynomial on [-0.5, 0.5], max relative error 7.5e-5 -- far below the bf16 rounding of P; clamped at -126).
 __device__ __forceinline__ float2 exp2_fma2(float2 x) {
@@ -58,8 +67,8 @@ __device__ __forceinline__ float2 exp2_fma2(float2 x) {
 template <int POLY>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                const __grid_constant__ CUtensorMap tmDQ, const float* __restrict__ lse, const float* __restrict__ delta,
-                __nv_bfloat16* __restrict__ dqkv, int S, int C, int nh) {
+                const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDQ1, const float* __restrict__ lse, const float* __restrict__ delta,
+                __nv_bfloat16* __restrict__ dqkv, int* __restrict__ sem, int S, int C, int nh) {
 #ifdef TVAE_DEVICE_OK
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -84,24 +93,41 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* sdp_free = bars + 11;    // 1 (8 warp arrivals): S~ / dP of the current tile sit in registers
   uint64_t* dq_drained = bars + 12;  // [2]: dQ~ of tile i left its staging area (= the dZ buffer i & 1) and its TMEM buffer
   uint64_t* p_free = bars + 14;      // 1: the dV MMAs of the tile have read P
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* dq_staged = bars + 15;   // [2] (4 warp arrivals): dQ~ of tile i sits in its staging area
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int nq = (S + 127) / 128;
+  // Query-tile order.  sem != nullptr (ordered mode): key-tile CTA j visits the query tiles in the rotated order
+  // (j + step) mod nq, and adds its dQ~ contribution to a tile only after the earlier contributions have landed: tile i
+  // receives CTA i, i-1, i-2, ... in that order, so dQ is bit-reproducible.  Even and odd steps go to two accumulators
+  // (summed by tvae_rope_bwd), each with its own counter per (image, head, query tile): a contribution then waits for
+  // the one TWO steps back -- with a single accumulator every step waited for the global completion of the previous
+  // reduce-add (~3 us against a 1.9 us tile period: 4.1 instead of 2.7 ms).  At every step the CTAs of an (image, head)
+  // touch different tiles.  The host enables this mode only when the nq CTAs of a group fit on
+  // the machine several times over (a group must become co-resident for the chain to resolve).
+  const int rot = sem != nullptr ? (int)blockIdx.x : 0;
+  auto tile_of = [&](int step) {
+    int t = step + rot;
+    return t >= nq ? t - nq : t;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmDQ);
+    tma_prefetch_desc(&tmDQ1);
     mbar_init(kv_full, 1);
     for (int s = 0; s < kQStages; ++s) {
       mbar_init(&qdo_full[s], 1);
       mbar_init(&qdo_empty[s], 1);
     }
     mbar_init(p_free, 1);
+    mbar_init(&dq_staged[0], 4);
+    mbar_init(&dq_staged[1], 4);
     mbar_init(sdp_full, 1);
     mbar_init(pds_full, 8);
     mbar_init(sdp_free, 8);
@@ -134,8 +160,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       for (int i = 0; i < nq; ++i) {
         mbar_wait(&qdo_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&qdo_full[st], 2 * kBT);
-        tma_load_3d(sQ + st * kBT, &tmQKV, &qdo_full[st], h * 64, i * 128, b);
-        tma_load_3d(sDO + st * kBT, &tmDO, &qdo_full[st], h * 64, i * 128, b);
+        tma_load_3d(sQ + st * kBT, &tmQKV, &qdo_full[st], h * 64, tile_of(i) * 128, b);
+        tma_load_3d(sDO + st * kBT, &tmDO, &qdo_full[st], h * 64, tile_of(i) * 128, b);
         if (++st == kQStages) {
           st = 0;
           ph ^= 1;
@@ -205,11 +231,53 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       st = st_n;
       ph = ph_n;
     }
+  } else if (lane == 0) {
+    // ---- dQ issuers: warp 2 takes the even steps, warp 3 the odd ones (= one staging buffer and, in ordered mode, one
+    // accumulator each).  An issuer may sit in the global-completion wait of its reduce-add for up to two tile periods
+    // without holding anyone up (with the drain warps issuing, that wait was on the path of every tile: 3.6 vs 2.7 ms).
+    const int par = warp - 2;
+    for (int i = par; i < nq; i += 2) {
+      mbar_wait(&dq_staged[par], (i >> 1) & 1);
+      const int qt = tile_of(i);
+      uint8_t* stage = sDZ + par * 2 * kBT;
+      int* my_sem = sem != nullptr ? sem + (((size_t)par * gridDim.z + b) * nh + h) * nq + qt : nullptr;
+      if (my_sem != nullptr) {                 // the earlier contributions of this parity to the tile have landed
+        uint32_t spins = 0;
+        uint64_t t0 = 0;
+        while (ld_acquire_gpu(my_sem) != (i >> 1)) {
+          if ((++spins & 0x3FF) == 0) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > TVAE_WAIT_TIMEOUT_NS) {
+              printf("tvae: attention backward dQ order wait timeout block=(%d,%d,%d) step=%d\n", blockIdx.x, blockIdx.y,
+                     blockIdx.z, i);
+              __trap();
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half)
+        asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                         reinterpret_cast<uint64_t>(my_sem != nullptr && par ? &tmDQ1 : &tmDQ)),
+                     "r"(smem_u32(stage + half * kBT)), "r"(h * 64 + half * 32), "r"(qt * 128), "r"(b)
+                     : "memory");
+      tma_store_commit();
+      tma_store_wait_read<0>();
+      mbar_arrive(&dq_drained[par]);
+      if (my_sem != nullptr) {                 // the adds are complete and visible before the next contributor starts
+        tma_store_wait<0>();
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        st_release_gpu(my_sem, (i >> 1) + 1);
+      }
+    }
+    tma_store_wait<0>();                       // all reduce-adds of this issuer have landed
   }
   } else if (warp >= 12) {
-    // ---- drain warpgroup: dQ~_i (128 x 64 fp32) TMEM -> swizzled smem -> two bulk tensor reduce-adds into the fp32
-    // accumulator.  The staging area is the dZ buffer of tile i, which the tensor core has finished reading when
-    // mma_done(i) fires; the softmax warps take it back (tile i + 2) on dq_drained.  (First version: per-thread
+    // ---- drain warpgroup: dQ~_i (128 x 64 fp32) TMEM -> swizzled smem; warps 2 / 3 then issue two bulk tensor reduce-adds
+    // into the fp32 accumulator.  The staging area is the dZ buffer of tile i, which the tensor core has finished
+    // reading when mma_done(i) fires; the softmax warps take it back (tile i + 2) on dq_drained.  (First version: per-thread
     // red.global.add.v4.f32 -- 6.4 GB of scattered 16-byte atomics per launch.  Second version: the softmax warps
     // staged and waited for the bulk read themselves -- 41 % of their stall samples sat in that wait and its barriers.)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
@@ -231,20 +299,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (warp == 12 && lane == 0) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half)
-          asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                           reinterpret_cast<uint64_t>(&tmDQ)),
-                       "r"(smem_u32(stage + half * kBT)), "r"(h * 64 + half * 32), "r"(i * 128), "r"(b)
-                       : "memory");
-        tma_store_commit();
-        tma_store_wait_read<0>();
-        mbar_arrive(&dq_drained[i & 1]);
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dq_staged[i & 1]);      // 4 warp arrivals: the tile is staged, its TMEM buffer is free
     }
-    if (warp == 12 && lane == 0) tma_store_wait<0>();   // all reduce-adds of this CTA have landed
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");    // softmax warpgroups: 2 x (32 S~ + 32 dP) values per thread
     // Eight softmax warps: warps w and w + 4 share TMEM lane quarter (w & 3) -- i.e. the same 32 query rows -- and
@@ -258,12 +315,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const size_t stat_base = ((size_t)b * nh + h) * S;
     const bool full_tile = k0 + 128 <= S;                            // no key masking needed
 
-    float l2_next = (r < S) ? __ldg(lse + stat_base + r) : INFINITY;
-    float dl_next = (r < S) ? __ldg(delta + stat_base + r) : 0.0f;
+    float l2_next, dl_next;
+    {
+      const int q0 = tile_of(0) * 128 + r;
+      l2_next = (q0 < S) ? __ldg(lse + stat_base + q0) : INFINITY;
+      dl_next = (q0 < S) ? __ldg(delta + stat_base + q0) : 0.0f;
+    }
     for (int i = 0; i < nq; ++i) {
       const float2 nl2 = make_float2(-l2_next, -l2_next), ndl = make_float2(-dl_next, -dl_next);
       {                                                              // statistics of the next tile: off the critical path
-        const int qn = (i + 1) * 128 + r;
+        const int qn = (i + 1 < nq ? tile_of(i + 1) : nq) * 128 + r;
         l2_next = (qn < S) ? __ldg(lse + stat_base + qn) : INFINITY;
         dl_next = (qn < S) ? __ldg(delta + stat_base + qn) : 0.0f;
       }
@@ -364,16 +425,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #endif
 }
 
+// 2: ordered (bit-reproducible) dQ accumulation into an even-step and an odd-step accumulator -- when a group of nq key-tile
+// CTAs fits on the machine at least twice, so that the wait chain of a group always resolves; 1: unordered reduce-adds
+// (TVAE_ATTN_BWD_ORDERED=0 forces it: the A/B switch)
+int attn_bwd_dq_slices(int S) {
+  static const bool ordered_env = !(getenv("TVAE_ATTN_BWD_ORDERED") && atoi(getenv("TVAE_ATTN_BWD_ORDERED")) == 0);
+  const int nq = (S + 127) / 128;
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  return ordered_env && nq > 1 && 2 * nq <= sms ? 2 : 1;
+}
+
 int attn_bwd_run(const void* qkv, const void* dout, const float* lse, const float* delta, float* dq_acc, void* dqkv, int B,
-                 int S, int C, cudaStream_t stream) {
+                 int S, int C, int dq_slices, cudaStream_t stream) {
+  TVAE_REQUIRE(dq_slices == 1 || dq_slices == 2, "attention_bwd: dq_slices must be 1 or 2");
   TVAE_REQUIRE(C % 64 == 0, "attention_bwd: C=%d must be a multiple of 64", C);
   const int nh = C / 64;
   CUtensorMap mQKV, mDO;
   int rc;
   if ((rc = make_tmap_3d(&mQKV, qkv, 3 * (uint64_t)C, S, B, 3 * (uint64_t)C, (uint64_t)S * 3 * C, 128))) return rc;
   if ((rc = make_tmap_3d(&mDO, dout, C, S, B, C, (uint64_t)S * C, 128))) return rc;
-  CUtensorMap mDQ;
+  CUtensorMap mDQ, mDQ1;
   if ((rc = make_tmap_3d_f32(&mDQ, dq_acc, C, S, B, C, (uint64_t)S * C, 128))) return rc;
+  if ((rc = make_tmap_3d_f32(&mDQ1, dq_acc + (dq_slices == 2 ? (size_t)B * S * C : 0), C, S, B, C, (uint64_t)S * C, 128))) return rc;
   // TVAE_ATTN_BWD_POLY = 0 / 2 / 3 / 4: A/B switch for the share of exponentials on the FMA pipe (default 0: measured slower with any share -- the softmax warps are not MUFU-bound here)
   static const int poly = getenv("TVAE_ATTN_BWD_POLY") ? atoi(getenv("TVAE_ATTN_BWD_POLY")) : 0;
   auto kern = poly == 0 ? attn_bwd_kernel<0> : poly == 2 ? attn_bwd_kernel<2> : poly == 3 ? attn_bwd_kernel<3> : attn_bwd_kernel<4>;
@@ -383,9 +457,17 @@ int attn_bwd_run(const void* qkv, const void* dout, const float* lse, const floa
       TVAE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     configured = true;
   }
-  TVAE_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)B * S * C * sizeof(float), stream));
+  TVAE_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)dq_slices * B * S * C * sizeof(float), stream));
   dim3 grid((S + 127) / 128, nh, B);
-  kern<<<grid, kBwdThreads, kBwdSmem, stream>>>(mQKV, mDO, mDQ, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), S, C, nh);
+  int* sem = nullptr;
+  const int nq = (int)grid.x;
+  if (dq_slices == 2) {
+    const size_t bytes = (size_t)2 * B * nh * nq * sizeof(int);
+    if ((rc = scratch_workspace(bytes, reinterpret_cast<void**>(&sem)))) return rc;
+    TVAE_CHECK_CUDA(cudaMemsetAsync(sem, 0, bytes, stream));
+  }
+  kern<<<grid, kBwdThreads, kBwdSmem, stream>>>(mQKV, mDO, mDQ, mDQ1, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), sem, S,
+                                                C, nh);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

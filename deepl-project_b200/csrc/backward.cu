@@ -29,15 +29,16 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // Processes columns [c0, c0+Qs) of the row-major [R0*Pn*R1, Qfull] matrix; row r belongs to phase (r / R1) % Pn.
 constexpr int kEwBatch = 4;   // independent 16-byte loads per stream a thread keeps in flight
 
+__device__ unsigned int g_bab_tickets[1 + kOrdMaxGroups];
+
 template <int ACT>
 __global__ void __launch_bounds__(256) bias_act_bwd_slab_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ z,
                                                                 uint4* __restrict__ dz, float* __restrict__ colsum,
-                                                                long long nrows, int Pn, int R1, int Qfull, int c0, int Qs,
-                                                                int rows_per_block) {
-  extern __shared__ float s_col[];   // [Pn][Qs]
+                                                                float* __restrict__ ws, long long nrows, int Pn, int R1,
+                                                                int Qfull, int c0, int Qs, int rows_per_block) {
+  extern __shared__ __align__(16) float s_col[];   // [row lanes of the block][Pn][Qs]
+  __shared__ bool s_flag;
   const int nvec = Qs >> 3, nvf = Qfull >> 3, v0 = c0 >> 3;
-  for (int i = threadIdx.x; i < Pn * Qs; i += blockDim.x) s_col[i] = 0.0f;
-  __syncthreads();
   const int v = threadIdx.x % nvec, rl = threadIdx.x / nvec, rpp = blockDim.x / nvec;
   const long long r_begin = (long long)blockIdx.x * rows_per_block;
   const long long r_end = min(nrows, r_begin + rows_per_block);
@@ -81,19 +82,27 @@ __global__ void __launch_bounds__(256) bias_act_bwd_slab_kernel(const uint4* __r
         }
       }
     }
+    // column sums: fixed-order reduction (row lanes of the block in order, then the blocks: ordered_rows_reduce)
 #pragma unroll
     for (int pp = 0; pp < 2; ++pp)
-      if (pp < Pn)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          atomicAdd(&s_col[pp * Qs + v * 8 + 2 * i], acc[pp][i].x);
-          atomicAdd(&s_col[pp * Qs + v * 8 + 2 * i + 1], acc[pp][i].y);
-        }
+      if (pp < Pn) {
+        float* p = s_col + ((size_t)rl * Pn + pp) * Qs + v * 8;
+        *reinterpret_cast<float4*>(p) = make_float4(acc[pp][0].x, acc[pp][0].y, acc[pp][1].x, acc[pp][1].y);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(acc[pp][2].x, acc[pp][2].y, acc[pp][3].x, acc[pp][3].y);
+      }
   }
+  if (colsum == nullptr) return;          // uniform
   __syncthreads();
-  if (colsum != nullptr)
-    for (int i = threadIdx.x; i < Pn * Qs; i += blockDim.x)
-      atomicAdd(colsum + (size_t)(i / Qs) * Qfull + c0 + (i % Qs), s_col[i]);
+  const int n = Pn * Qs;
+  float* rows = ws;                                            // [gridDim.x][Pn * Qs]
+  float* groups = ws + (size_t)gridDim.x * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float a = 0.0f;
+    for (int r = 0; r < rpp; ++r) a += s_col[(size_t)r * n + i];
+    rows[(size_t)blockIdx.x * n + i] = a;
+  }
+  ordered_rows_reduce(rows, groups, g_bab_tickets, colsum, n, gridDim.x, blockIdx.x, &s_flag,
+                      [=](int i) { return (size_t)(i / Qs) * Qfull + c0 + (i % Qs); });
 }
 
 int bias_act_bwd_run(const void* dy, const void* z, void* dz, float* colsum, long long R0, int Pn, int R1, int Q, int act,
@@ -102,7 +111,6 @@ int bias_act_bwd_run(const void* dy, const void* z, void* dz, float* colsum, lon
   TVAE_REQUIRE(Pn == 1 || Pn == 2, "bias_act_bwd: P must be 1 or 2");
   TVAE_REQUIRE(act == TVAE_ACT_NONE || (z != nullptr && dz != nullptr), "bias_act_bwd: activation needs z and dz");
   TVAE_REQUIRE(act == TVAE_ACT_NONE || act == TVAE_ACT_GELU || act == TVAE_ACT_SILU, "bias_act_bwd: unknown activation %d", act);
-  if (colsum) TVAE_CHECK_CUDA(cudaMemsetAsync(colsum, 0, (size_t)Pn * Q * sizeof(float), stream));
   const long long nrows = R0 * Pn * R1;
   for (int c0 = 0; c0 < Q; c0 += 2048) {
     const int qs = (Q - c0) < 2048 ? (Q - c0) : 2048;
@@ -116,10 +124,17 @@ int bias_act_bwd_run(const void* dy, const void* z, void* dz, float* colsum, lon
     long long rpb = ((nrows + 4LL * num_sms() - 1) / (4LL * num_sms()) + unit - 1) / unit * unit;
     if (rpb < unit) rpb = unit;
     const int grid = (int)((nrows + rpb - 1) / rpb);
-    const size_t smem = (size_t)Pn * qs * sizeof(float);
+    TVAE_REQUIRE(grid <= (int)(kOrdGroup * kOrdMaxGroups), "bias_act_bwd: grid %d too large", grid);
+    const size_t smem = (size_t)rpp * Pn * qs * sizeof(float);          // <= 16 KiB
+    float* ws = nullptr;
+    if (colsum != nullptr) {
+      const size_t need = (size_t)(grid + (grid + kOrdGroup - 1) / kOrdGroup) * Pn * qs * sizeof(float);
+      const int rc = scratch_workspace(need, reinterpret_cast<void**>(&ws));
+      if (rc) return rc;
+    }
     auto args = [&](auto kern) {
       kern<<<grid, threads, smem, stream>>>(reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(z),
-                                            reinterpret_cast<uint4*>(dz), colsum, nrows, Pn, R1, Q, c0, qs, (int)rpb);
+                                            reinterpret_cast<uint4*>(dz), colsum, ws, nrows, Pn, R1, Q, c0, qs, (int)rpb);
     };
     if (act == TVAE_ACT_GELU) args(bias_act_bwd_slab_kernel<TVAE_ACT_GELU>);
     else if (act == TVAE_ACT_SILU) args(bias_act_bwd_slab_kernel<TVAE_ACT_SILU>);
@@ -533,16 +548,17 @@ int token_norm_fwd_run(const void* x, const float* w, void* y, long long M, int 
 // partials stay in registers, dw is reduced across the block's warps in shared memory and flushed with one atomic per
 // column per block.  (The first version indexed per-lane arrays dynamically -> local memory; ncu census of a training
 // step: 32.5 ms of 225 ms.)
+__device__ unsigned int g_tnb_tickets[1 + kOrdMaxGroups];
+
 template <int VPL>
 __global__ void __launch_bounds__(256, VPL <= 2 ? 2 : 1) token_norm_bwd_reg_kernel(const uint4* __restrict__ x, const float* __restrict__ w,
                                                                  const uint4* __restrict__ dy, const uint4* __restrict__ add,
-                                                                 uint4* __restrict__ dx, float* __restrict__ dw, long long M,
-                                                                 int C, int mode) {
-  extern __shared__ float s_dw[];   // [C]
+                                                                 uint4* __restrict__ dx, float* __restrict__ dw,
+                                                                 float* __restrict__ ws, long long M, int C, int mode) {
+  extern __shared__ __align__(16) float s_dw[];   // [8 warps][C]
+  __shared__ bool s_flag;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = C >> 3;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) s_dw[i] = 0.0f;
-  __syncthreads();
   float2 wv[VPL][4], dwacc[VPL][4];
 #pragma unroll
   for (int c = 0; c < VPL; ++c) {
@@ -692,18 +708,26 @@ __global__ void __launch_bounds__(256, VPL <= 2 ? 2 : 1) token_norm_bwd_reg_kern
       }
     }
   }
+  // weight gradient: fixed-order reduction (warps of the block in warp order, then the blocks: ordered_rows_reduce)
 #pragma unroll
   for (int c = 0; c < VPL; ++c) {
     const int v = lane + c * 32;
-    if (v < nvec)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        atomicAdd(&s_dw[v * 8 + 2 * q], dwacc[c][q].x);
-        atomicAdd(&s_dw[v * 8 + 2 * q + 1], dwacc[c][q].y);
-      }
+    if (v < nvec) {
+      float* p = s_dw + (size_t)warp * C + v * 8;
+      *reinterpret_cast<float4*>(p) = make_float4(dwacc[c][0].x, dwacc[c][0].y, dwacc[c][1].x, dwacc[c][1].y);
+      *reinterpret_cast<float4*>(p + 4) = make_float4(dwacc[c][2].x, dwacc[c][2].y, dwacc[c][3].x, dwacc[c][3].y);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dw + i, s_dw[i]);
+  float* rows = ws;                                            // [gridDim.x][C]
+  float* groups = ws + (size_t)gridDim.x * C;                  // [groups][C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    float a = 0.0f;
+#pragma unroll
+    for (int wdx = 0; wdx < 8; ++wdx) a += s_dw[(size_t)wdx * C + i];
+    rows[(size_t)blockIdx.x * C + i] = a;
+  }
+  ordered_rows_reduce(rows, groups, g_tnb_tickets, dw, C, gridDim.x, blockIdx.x, &s_flag);
 }
 
 template <int VPL>
@@ -712,9 +736,21 @@ static int launch_tnb(const void* x, const float* w, const void* dy, const void*
   long long blocks = (M + 7) / 8;
   const long long cap = (long long)num_sms() * 4;
   if (blocks > cap) blocks = cap;
-  token_norm_bwd_reg_kernel<VPL><<<(int)blocks, 256, C * sizeof(float), stream>>>(
+  const long long groups = (blocks + kOrdGroup - 1) / kOrdGroup;
+  float* ws = nullptr;
+  {
+    const int rc = scratch_workspace((size_t)(blocks + groups) * C * sizeof(float), reinterpret_cast<void**>(&ws));
+    if (rc) return rc;
+  }
+  const size_t smem = 8 * (size_t)C * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    TVAE_CHECK_CUDA(cudaFuncSetAttribute(token_norm_bwd_reg_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * 8 * VPL * 4));
+    configured = true;
+  }
+  token_norm_bwd_reg_kernel<VPL><<<(int)blocks, 256, smem, stream>>>(
       reinterpret_cast<const uint4*>(x), w, reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(add),
-      reinterpret_cast<uint4*>(dx), dw, M, C, mode);
+      reinterpret_cast<uint4*>(dx), dw, ws, M, C, mode);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -833,13 +869,13 @@ __global__ void __launch_bounds__(256) token_norm_bwd_kernel(const uint4* __rest
 int token_norm_bwd_run(const void* x, const float* w, const void* dy, const void* add, void* dx, float* dw, long long M,
                        int C, int mode, cudaStream_t stream) {
   TVAE_REQUIRE(C % 8 == 0 && C / 8 <= 32 * kMaxVecPerLane, "token_norm_bwd: C=%d unsupported", C);
-  TVAE_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)C * sizeof(float), stream));
   const int vpl = (C / 8 + 31) / 32;
   if (vpl <= 1) return launch_tnb<1>(x, w, dy, add, dx, dw, M, C, mode, stream);
   if (vpl == 2) return launch_tnb<2>(x, w, dy, add, dx, dw, M, C, mode, stream);
   if (vpl == 3) return launch_tnb<3>(x, w, dy, add, dx, dw, M, C, mode, stream);
   if (vpl == 4) return launch_tnb<4>(x, w, dy, add, dx, dw, M, C, mode, stream);
   if (vpl <= 6) return launch_tnb<6>(x, w, dy, add, dx, dw, M, C, mode, stream);
+  TVAE_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)C * sizeof(float), stream));     // wide-row fallback: atomics
   int rpw = 16;
   while (rpw > 1 && (M + rpw - 1) / rpw < 8LL * 4 * num_sms()) rpw >>= 1;
   const long long warps = (M + rpw - 1) / rpw;
@@ -897,7 +933,7 @@ int attn_delta_run(const void* o, const void* dout, float* delta, int B, int S, 
 
 __global__ void __launch_bounds__(256) rope_bwd_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv,
                                                        const float2* __restrict__ tab, long long M, int C, int H, int W,
-                                                       float q_scale) {
+                                                       float q_scale, int dq_slices) {
   // one thread per (token, part in {q,k}, 8-channel vector)
   const int nvec = C >> 3;
   const long long total = M * 2 * nvec;
@@ -916,6 +952,12 @@ __global__ void __launch_bounds__(256) rope_bwd_kernel(const float* __restrict__
       const float4 a = __ldg(reinterpret_cast<const float4*>(dq_acc + tok * C + v * 8));
       const float4 b = __ldg(reinterpret_cast<const float4*>(dq_acc + tok * C + v * 8) + 1);
       g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+      if (dq_slices == 2) {             // even-step + odd-step accumulators of the ordered attention backward
+        const float* p1 = dq_acc + (size_t)M * C + tok * C + v * 8;
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(p1));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p1) + 1);
+        g[0] += a1.x; g[1] += a1.y; g[2] += a1.z; g[3] += a1.w; g[4] += b1.x; g[5] += b1.y; g[6] += b1.z; g[7] += b1.w;
+      }
     } else {
       unpack8(*reinterpret_cast<const uint4*>(dst), g);
     }
@@ -933,12 +975,12 @@ __global__ void __launch_bounds__(256) rope_bwd_kernel(const float* __restrict__
 }
 
 int rope_bwd_run(const float* dq_acc, void* dqkv, const float* tab, long long M, int C, int H, int W, float q_scale,
-                 cudaStream_t stream) {
+                 int dq_slices, cudaStream_t stream) {
   const long long total = M * 2 * (C / 8);
   int grid = (int)((total + 255) / 256);
   if (grid > num_sms() * 16) grid = num_sms() * 16;
   rope_bwd_kernel<<<grid, 256, 0, stream>>>(dq_acc, reinterpret_cast<__nv_bfloat16*>(dqkv),
-                                            reinterpret_cast<const float2*>(tab), M, C, H, W, q_scale);
+                                            reinterpret_cast<const float2*>(tab), M, C, H, W, q_scale, dq_slices);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

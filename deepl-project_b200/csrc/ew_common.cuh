@@ -25,6 +25,50 @@ __device__ __forceinline__ uint4 pack8_2(const float2 (&f)[4]) {
 // round to bf16 and back (what a consumer of the stored bf16 tensor will see)
 __device__ __forceinline__ float2 round_bf16_2(float2 v) { return bf16x2_to_f2(f2_to_bf16x2(v)); }
 
+// -------------------------------------------------------------------------------------------------
+// Fixed-order cross-block reduction of one row of `n` floats per block (no atomics on the values, so two runs are
+// bit-identical).  Every block has stored its row at rows[blockIdx.x * n ...]; the last block of each group of
+// kOrdGroup consecutive blocks to arrive (ticket counter) adds the group's rows in block order into groups[g * n ...],
+// and the last group to finish adds the group rows in group order into out.  Tickets wrap to zero (atomicInc), so the
+// array is ready for the next launch.  All threads of the block call this; `s_flag` is a shared bool.
+// tickets: [1 + ceil(nblocks / kOrdGroup)] zero-initialised unsigned ints.
+// -------------------------------------------------------------------------------------------------
+constexpr unsigned int kOrdGroup = 32;
+constexpr unsigned int kOrdMaxGroups = 128;     // up to 4096 blocks
+template <typename OutIndex>     // out[out_index(i)] receives column i
+__device__ __forceinline__ void ordered_rows_reduce(const float* rows, float* groups, unsigned int* tickets, float* out, int n,
+                                                    unsigned int nblocks, unsigned int bid, bool* s_flag, OutIndex out_index) {
+  const unsigned int ngroups = (nblocks + kOrdGroup - 1) / kOrdGroup;
+  const unsigned int grp = bid / kOrdGroup;
+  const unsigned int gsize = min(kOrdGroup, nblocks - grp * kOrdGroup);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) *s_flag = atomicInc(&tickets[1 + grp], gsize - 1) == gsize - 1;
+  __syncthreads();
+  if (!*s_flag) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float a = 0.0f;
+    for (unsigned int k = 0; k < gsize; ++k) a += __ldcg(rows + (size_t)(grp * kOrdGroup + k) * n + i);
+    groups[(size_t)grp * n + i] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) *s_flag = atomicInc(&tickets[0], ngroups - 1) == ngroups - 1;
+  __syncthreads();
+  if (!*s_flag) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float a = 0.0f;
+    for (unsigned int g = 0; g < ngroups; ++g) a += __ldcg(groups + (size_t)g * n + i);
+    out[out_index(i)] = a;
+  }
+}
+__device__ __forceinline__ void ordered_rows_reduce(const float* rows, float* groups, unsigned int* tickets, float* out, int n,
+                                                    unsigned int nblocks, unsigned int bid, bool* s_flag) {
+  ordered_rows_reduce(rows, groups, tickets, out, n, nblocks, bid, s_flag, [](int i) { return i; });
+}
+
 __device__ __forceinline__ float tanh_approx(float x) {
   float r;
   asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));   // one MUFU.TANH, |abs err| < 2^-10.9

@@ -85,10 +85,11 @@ _PROTOS = {
     "tvae_token_norm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_int32, C.c_int32, C.c_void_p]),
     "tvae_attn_delta": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "tvae_attn_bwd_dq_slices": (C.c_int, [C.c_int32]),
     "tvae_attn_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
-                                C.c_int32, C.c_int32, C.c_void_p]),
+                                C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "tvae_rope_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
-                                C.c_float, C.c_void_p]),
+                                C.c_float, C.c_int32, C.c_void_p]),
     "tvae_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_void_p]),
     "tvae_latent_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

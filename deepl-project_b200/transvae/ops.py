@@ -498,7 +498,8 @@ def attn_bwd(qkv: Tensor, out: Tensor, dout: Tensor, lse: Tensor, rope_tab: Tens
     lib = _lib.load()
     dev = qkv.device
     delta = torch.empty(B, C_ // 64, S, dtype=torch.float32, device=dev)
-    dq_acc = torch.empty(B, S, C_, dtype=torch.float32, device=dev)
+    slices = lib.tvae_attn_bwd_dq_slices(S)      # 2: ordered (bit-reproducible) dQ accumulation, even / odd steps
+    dq_acc = torch.empty(slices, B, S, C_, dtype=torch.float32, device=dev)
     dqkv = torch.empty(B, S, 3 * C_, dtype=BF16, device=dev)
     dout = dout.contiguous()
     if PROFILE is not None:
@@ -506,9 +507,9 @@ def attn_bwd(qkv: Tensor, out: Tensor, dout: Tensor, lse: Tensor, rope_tab: Tens
         e0.record()
     _lib.check(lib.tvae_attn_delta(out.data_ptr(), dout.data_ptr(), delta.data_ptr(), B, S, C_, _stream()), "tvae_attn_delta")
     _lib.check(lib.tvae_attn_bwd(qkv.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(), dq_acc.data_ptr(),
-                                 dqkv.data_ptr(), B, S, C_, _stream()), "tvae_attn_bwd")
+                                 dqkv.data_ptr(), B, S, C_, slices, _stream()), "tvae_attn_bwd")
     _lib.check(lib.tvae_rope_bwd(dq_acc.data_ptr(), dqkv.data_ptr(), rope_tab.data_ptr(), B * S, C_, H, W, q_scale,
-                                 _stream()), "tvae_rope_bwd")
+                                 slices, _stream()), "tvae_rope_bwd")
     if PROFILE is not None:
         e1.record()
         PROFILE.append(("attn_bwd", 10.0 * B * S * S * C_, e0, e1, 10.0 * B * S * S * C_))

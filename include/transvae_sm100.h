@@ -192,14 +192,18 @@ int tvae_groupnorm_bwd(const void* x, const void* dh, const void* add, const dou
 int tvae_token_norm_fwd(const void* x, const float* w, void* y, int64_t M, int32_t C, int32_t mode, void* stream);
 int tvae_token_norm_bwd(const void* x, const float* w, const void* dy, const void* add, void* dx, float* dw, int64_t M,
                         int32_t C, int32_t mode, void* stream);
-/* Attention backward (attention.py:88-92).  delta fp32 [B, C/64, S] = rowsum(dout * out); dq_acc fp32 [B, S, C]
- * (zeroed inside); dqkv bf16 [B, S, 3C]: k / v thirds written by tvae_attn_bwd (rotated space), q third and the
- * transposed RoPE of q and k by tvae_rope_bwd (q_scale = head_dim^-0.5). */
+/* Attention backward (attention.py:88-92).  delta fp32 [B, C/64, S] = rowsum(dout * out); dq_acc fp32
+ * [dq_slices][B, S, C] (zeroed inside); dqkv bf16 [B, S, 3C]: k / v thirds written by tvae_attn_bwd (rotated space), q
+ * third and the transposed RoPE of q and k by tvae_rope_bwd (q_scale = head_dim^-0.5).
+ * dq_slices = tvae_attn_bwd_dq_slices(S): 2 when the dQ contributions of the key tiles are added in a fixed order
+ * (bit-reproducible; even and odd steps go to separate accumulators so that a contribution never waits for the global
+ * completion of the previous one), 1 when they are unordered reduce-adds (very long sequences). */
+int tvae_attn_bwd_dq_slices(int32_t S);
 int tvae_attn_delta(const void* out, const void* dout, float* delta, int32_t B, int32_t S, int32_t C, void* stream);
 int tvae_attn_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, float* dq_acc, void* dqkv,
-                  int32_t B, int32_t S, int32_t C, void* stream);
+                  int32_t B, int32_t S, int32_t C, int32_t dq_slices, void* stream);
 int tvae_rope_bwd(const float* dq_acc, void* dqkv, const float* rope_tab, int64_t M, int32_t C, int32_t H, int32_t W,
-                  float q_scale, void* stream);
+                  float q_scale, int32_t dq_slices, void* stream);
 /* Loss backward: scal (device fp32[2]) = {dLoss * l1_weight / numel(recon), dLoss * kl_weight / kl_norm}. */
 int tvae_loss_bwd(const float* recon, const float* target, const float* mu, const float* logvar, const float* scal,
                   float* drecon, float* dmu, float* dlogvar, int64_t n_img, int64_t n_lat, int32_t patched, float clip_lo,
