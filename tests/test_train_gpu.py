@@ -144,10 +144,11 @@ def test_training_loss_matches_golden(name):
 
 
 def test_gradient_checkpointing_matches():
-    """T/test_installation.py:116-141: backward with gradient checkpointing enabled.  Per block the checkpointed
-    backward must reproduce the plain one (only fp32-atomic ordering differs); for the whole model the comparison is
-    bounded by the run-to-run bf16 noise of this randomly initialised 30-layer network ([B200]: two identical plain runs
-    differ by 9 % median l2 per tensor, checkpointed vs plain by 11 %)."""
+    """T/test_installation.py:116-141: backward with gradient checkpointing enabled.  Forward and backward are
+    bit-reproducible (fixed-order reductions everywhere: test_backward_is_bit_reproducible), and the recomputed forward
+    runs the same kernels on the same inputs -- so the checkpointed backward must reproduce the plain one EXACTLY, per
+    block and for the whole model.  (Round 1 had atomics in the weight-gradient flush, the GroupNorm / token-norm / bias
+    reductions and the attention dQ accumulation: two identical plain runs differed by 9 % median l2 per tensor.)"""
     import torch.utils.checkpoint as cp
     blob, sd = load_golden("mini_tamed")
     m = build_model(blob["cfg"], sd).train()
@@ -164,9 +165,9 @@ def test_gradient_checkpointing_matches():
                 dout = torch.randn(out.shape, generator=torch.Generator().manual_seed(4)).to(torch.bfloat16).cuda()
             out.backward(dout)
             res.append((xi.grad.clone(), {k: p.grad.clone() for k, p in blk.named_parameters()}))
-        assert l2(res[1][0], res[0][0]) < 2e-3
+        assert torch.equal(res[1][0], res[0][0]), l2(res[1][0], res[0][0])
         for k in res[0][1]:
-            assert l2(res[1][1][k], res[0][1][k]) < 2e-3, k
+            assert torch.equal(res[1][1][k], res[0][1][k]), (k, l2(res[1][1][k], res[0][1][k]))
     # whole model through model.enable_gradient_checkpointing()
     x, eps = blob["x"].cuda(), blob["eps"].cuda()
     g = torch.Generator().manual_seed(5)
@@ -182,5 +183,27 @@ def test_gradient_checkpointing_matches():
     g0 = grads()
     m.enable_gradient_checkpointing()
     g1 = grads()
-    errs = sorted(l2(g1[k], g0[k]) for k in g0)
-    assert errs[len(errs) // 2] < 0.25 and all(torch.isfinite(v).all() for v in g1.values())
+    diff = {k: l2(g1[k], g0[k]) for k in g0 if not torch.equal(g1[k], g0[k])}
+    assert not diff, sorted(diff.items(), key=lambda kv: -kv[1])[:5]
+
+
+@pytest.mark.parametrize("name", ["mini_tamed", "mini_tamed_128"])
+def test_backward_is_bit_reproducible(name):
+    """Two forward + backward passes on the same inputs give bit-identical losses and parameter gradients: no reduction of
+    the training step depends on the order in which thread blocks finish (weight-gradient pixel splits, GroupNorm /
+    token-norm / bias column sums, loss sums, attention dQ accumulation)."""
+    blob, sd = load_golden(name)
+    m = build_model(blob["cfg"], sd, patched=True).train()
+    loss_fn = transvae.TransVAELoss(l1_weight=1.0, lpips_weight=0.0, kl_weight=1e-8, vf_weight=0.0, gan_weight=0.0)
+    x, eps = blob["x"].cuda(), blob["eps"].cuda()
+    runs = []
+    for _ in range(3):
+        m.zero_grad()
+        recon, mu, logvar = m(x, eps=eps)
+        losses = loss_fn(recon, x, mu, logvar)
+        losses["total"].backward()
+        runs.append((losses["total"].detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters()}))
+    for r in runs[1:]:
+        assert torch.equal(r[0], runs[0][0])
+        bad = [k for k in runs[0][1] if not torch.equal(r[1][k], runs[0][1][k])]
+        assert not bad, bad[:8]
