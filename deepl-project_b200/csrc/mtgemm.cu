@@ -500,7 +500,11 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
   if (pair) {
     CUtensorMap mBh, mAh = mA0;
     if ((rc = make_tmap_2d(&mBh, d->w, d->n_total, d->k_total, d->k_total, block_n / 2))) return rc;
-    if (halo_ok) {
+    if (epi == kEpiResMulGeluGrad) {
+      // the pair kernel stages z (same plain view as the output) through TMA next to the residual; the halo-map slot
+      // carries its tensor map (halo tiles and this epilogue never meet: ConvFFN maps are narrower than 128 pixels)
+      if ((rc = make_tmap_pix(&mAh, d->z, d->out.B, d->out.H, d->out.W, d->out.C, d->out.split, P.tw, P.th, P.nb))) return rc;
+    } else if (halo_ok) {
       if ((rc = make_tmap_pix_halo(&mAh, d->a0.ptr, d->a0.B, d->a0.H, d->a0.W, d->a0.C))) return rc;
       P.halo = 1;
     }

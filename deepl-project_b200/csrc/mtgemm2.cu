@@ -22,14 +22,20 @@
 
 namespace tvae {
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI>
 struct Mt2Cfg {
   static constexpr int kBHalfBytes = (BLOCK_N / 2) * kBlockK * 2;
   static constexpr int kOutBytes = kBlockM * BLOCK_N * 2;
-  static constexpr int kStagesRaw = (227 * 1024 - 2048 - kOutBytes) / (kABytes + kBHalfBytes);
+  // kEpiResMulGeluGrad stages TWO input tiles per output tile (the gradient to add and the saved pre-activation z),
+  // both through TMA.  (z used to be read from global memory by the epilogue threads, 16 bytes per thread and row: every
+  // warp load touched 32 cache lines and the L1 tag stage, not HBM, set the pace -- 265 TFLOP/s / 2.1 TB/s on the
+  // K = 384 input-gradient GEMMs of the ConvFFN.)
+  static constexpr bool kStageZ = EPI == kEpiResMulGeluGrad;
+  static constexpr int kStagingBytes = kOutBytes * (kStageZ ? 2 : 1);
+  static constexpr int kStagesRaw = (227 * 1024 - 2048 - kStagingBytes) / (kABytes + kBHalfBytes);
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * (kABytes + kBHalfBytes) + kOutBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * (kABytes + kBHalfBytes) + kStagingBytes + 1024 + 256;
   // halo mode: a stage = one halo A tile + the B halves of the three dx taps, carved out of the same ring
   static constexpr int kHaloStageBytes = kHaloABytes + 3 * kBHalfBytes;
   static constexpr int kHaloStages = kStages * (kABytes + kBHalfBytes) / kHaloStageBytes;
@@ -42,7 +48,7 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmAh,
                const __grid_constant__ MtParams P) {
 #ifdef TVAE_DEVICE_OK
-  using Cfg = Mt2Cfg<BLOCK_N>;
+  using Cfg = Mt2Cfg<BLOCK_N, EPI>;
   constexpr int STAGES = Cfg::kStages;
   constexpr bool kHasRes = epi_has_res<EPI>();
   extern __shared__ uint8_t smem_raw[];
@@ -50,7 +56,8 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * kABytes;
   uint8_t* sOut = sB + STAGES * Cfg::kBHalfBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + Cfg::kOutBytes);
+  uint8_t* sZ = sOut + Cfg::kOutBytes;            // second staged tile (kStageZ only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + Cfg::kStagingBytes);
   uint64_t* full = bars;                   // [STAGES] (leader's are used)
   uint64_t* empty = bars + STAGES;         // [STAGES] (each CTA's own)
   uint64_t* tmem_full = bars + 2 * STAGES; // [2]      (each CTA's own)
@@ -263,11 +270,16 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++it) {
         TVAE_DECODE_PAIR(pt)
         mbar_wait(out_free, (it & 1) ^ 1);
-        mbar_arrive_expect_tx(res_full, Cfg::kOutBytes);
+        mbar_arrive_expect_tx(res_full, Cfg::kStagingBytes);
 #pragma unroll
         for (int j = 0; j < BLOCK_N / 64; ++j)
           tma_load_5d(sOut + j * kABytes, &tmRes, res_full, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph],
                       h0, b0);
+        if constexpr (Cfg::kStageZ) {        // the saved pre-activation z: same view as the output (tmAh carries its map)
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_5d(sZ + j * kABytes, &tmAh, res_full, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph], h0, b0);
+        }
       }
     }
   } else if (warp >= 4) {
@@ -276,6 +288,13 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int r = q * 32 + lane;
     const int half = (warp - 4) >> 2;
     const bool store_leader = (threadIdx.x == 128);
+    // Chunk-pipelined stores: epilogues that only WRITE the staging tile (no residual tile arriving in it, no statistics
+    // pass over it) send each 64-column chunk off as soon as the eight warps have finished it, and never wait for a
+    // store at the end of a tile -- with one store + wait per tile the small-K GEMMs (K = 384: 3000 clocks of MMA per
+    // tile) were bound by the epilogue's TMEM drain + store latency.  Needs at least two chunks.
+    constexpr int kChunks = BLOCK_N / 64;
+    constexpr bool kCanPipe = EPI != kEpiDirect && kChunks >= 2;
+    const bool pipe = kCanPipe && !has_res && !gn;
     int it = 0;
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++it) {
       TVAE_DECODE_PAIR(pt)
@@ -335,8 +354,15 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if constexpr (kHasRes) {
             if (has_res) {
               const uint4 ra = *pa, rb = *pb;
-              epi_combine8<EPI>(fa, ra, zrow, n_base + c16 * 16);
-              epi_combine8<EPI>(fb, rb, zrow, n_base + c16 * 16 + 8);
+              if constexpr (Cfg::kStageZ) {
+                const uint4 za = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(pa) + Cfg::kOutBytes);
+                const uint4 zb = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(pb) + Cfg::kOutBytes);
+                epi_res_mul_gelu_grad8(fa, ra, za);
+                epi_res_mul_gelu_grad8(fb, rb, zb);
+              } else {
+                epi_combine8<EPI>(fa, ra, zrow, n_base + c16 * 16);
+                epi_combine8<EPI>(fb, rb, zrow, n_base + c16 * 16 + 8);
+              }
             }
           }
           if constexpr (kGn) {
@@ -371,6 +397,21 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tmem_ld8(t_row + (c16 + 4) * 16 + 8, v0b);
           }
           process(c16 + 2, v1a, v1b);
+          if constexpr (kCanPipe) {
+            if (pipe) {
+              // the 64-column chunk c16 >> 2 is complete in every warp after this barrier: its store goes out while
+              // the next chunk is drained.  Before the barrier the leader makes sure the store that last read the NEXT
+              // chunk to be written (same chunk, previous tile) is done: kChunks - 2 younger groups may still be pending.
+              fence_proxy_async_smem();
+              if (store_leader) tma_store_wait_read<kChunks - 2>();
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+              if (store_leader) {
+                const int j = c16 >> 2;
+                tma_store_5d(&tmOut, sOut + j * kABytes, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph], h0, b0);
+                tma_store_commit();
+              }
+            }
+          }
         }
       }
       // accumulator half drained -> tell the leader's MMA warp (remote arrive from the peer CTA)
@@ -379,6 +420,9 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
 
       if constexpr (EPI != kEpiDirect) {
+        if constexpr (kCanPipe) {
+          if (pipe) continue;               // stores already issued chunk by chunk (uniform over the CTA)
+        }
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (store_leader) {
@@ -485,7 +529,7 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 template <int BLOCK_N, int EPI>
 static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                    const CUtensorMap& r, const CUtensorMap& ah, const MtParams& P, cudaStream_t stream) {
-  using Cfg = Mt2Cfg<BLOCK_N>;
+  using Cfg = Mt2Cfg<BLOCK_N, EPI>;
   static bool configured = false;
   if (!configured) {
     TVAE_CHECK_CUDA(cudaFuncSetAttribute(mtgemm2_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,

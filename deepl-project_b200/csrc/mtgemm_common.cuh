@@ -118,6 +118,18 @@ __device__ __forceinline__ void epi_combine8(float (&f)[8], const uint4& r, cons
   }
 }
 
+// f = (f + residual) * gelu'(z) with both tiles staged in shared memory (CTA-pair kernel)
+__device__ __forceinline__ void epi_res_mul_gelu_grad8(float (&f)[8], const uint4& r, const uint4& zu) {
+  const float2 t[4] = {bf16x2_to_f2(r.x), bf16x2_to_f2(r.y), bf16x2_to_f2(r.z), bf16x2_to_f2(r.w)};
+  const float2 z[4] = {bf16x2_to_f2(zu.x), bf16x2_to_f2(zu.y), bf16x2_to_f2(zu.z), bf16x2_to_f2(zu.w)};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 g = gelu_grad2(z[k]);
+    f[2 * k] = (f[2 * k] + t[k].x) * g.x;
+    f[2 * k + 1] = (f[2 * k + 1] + t[k].y) * g.y;
+  }
+}
+
 enum : int { kEpiCount = 11 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
