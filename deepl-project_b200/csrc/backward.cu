@@ -296,11 +296,8 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const uint4* __restr
   if (s_last) {
     __threadfence();
     const float* all = ws + (size_t)b * gridDim.x * 2 * C;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-      float a = 0.0f;
-      for (unsigned int k = 0; k < gridDim.x; ++k) a += __ldcg(all + (size_t)k * 2 * C + i);
-      part[(size_t)b * C * 2 + i] = a;
-    }
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x)
+      part[(size_t)b * C * 2 + i] = ordered_column_sum(all + i, 2 * (size_t)C, gridDim.x);
   }
 }
 

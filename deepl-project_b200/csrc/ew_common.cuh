@@ -33,6 +33,21 @@ __device__ __forceinline__ float2 round_bf16_2(float2 v) { return bf16x2_to_f2(f
 // array is ready for the next launch.  All threads of the block call this; `s_flag` is a shared bool.
 // tickets: [1 + ceil(nblocks / kOrdGroup)] zero-initialised unsigned ints.
 // -------------------------------------------------------------------------------------------------
+// sum of p[0], p[stride], ..., p[(count - 1) * stride] in that order, eight loads in flight at a time
+__device__ __forceinline__ float ordered_column_sum(const float* p, size_t stride, unsigned int count) {
+  float a = 0.0f;
+  unsigned int k = 0;
+  for (; k + 8 <= count; k += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcg(p + (size_t)(k + u) * stride);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a += v[u];
+  }
+  for (; k < count; ++k) a += __ldcg(p + (size_t)k * stride);
+  return a;
+}
+
 constexpr unsigned int kOrdGroup = 32;
 constexpr unsigned int kOrdMaxGroups = 128;     // up to 4096 blocks
 template <typename OutIndex>     // out[out_index(i)] receives column i
@@ -47,22 +62,14 @@ __device__ __forceinline__ void ordered_rows_reduce(const float* rows, float* gr
   __syncthreads();
   if (!*s_flag) return;
   __threadfence();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float a = 0.0f;
-    for (unsigned int k = 0; k < gsize; ++k) a += __ldcg(rows + (size_t)(grp * kOrdGroup + k) * n + i);
-    groups[(size_t)grp * n + i] = a;
-  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) groups[(size_t)grp * n + i] = ordered_column_sum(rows + (size_t)grp * kOrdGroup * n + i, n, gsize);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) *s_flag = atomicInc(&tickets[0], ngroups - 1) == ngroups - 1;
   __syncthreads();
   if (!*s_flag) return;
   __threadfence();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float a = 0.0f;
-    for (unsigned int g = 0; g < ngroups; ++g) a += __ldcg(groups + (size_t)g * n + i);
-    out[out_index(i)] = a;
-  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) out[out_index(i)] = ordered_column_sum(groups + i, n, ngroups);
 }
 __device__ __forceinline__ void ordered_rows_reduce(const float* rows, float* groups, unsigned int* tickets, float* out, int n,
                                                     unsigned int nblocks, unsigned int bid, bool* s_flag) {

@@ -63,17 +63,32 @@ __device__ __forceinline__ void wg_out4(float* p, float4 v, bool plain) {
   else atomicAdd(reinterpret_cast<float4*>(p), v);
 }
 
-// gradient += sum over the slices, in slice order (bit-reproducible); n % 4 == 0
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(float* __restrict__ g, const float* __restrict__ ws, long long n,
-                                                           long long stride, int splits) {
+// gradient += sum over the slices, in slice order (bit-reproducible).  A slice is [weight gradient (n_dw) | bias gradient
+// (n_db)], both multiples of 4 floats; one launch covers both destinations.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(float* __restrict__ dw, float* __restrict__ db,
+                                                           const float* __restrict__ ws, long long n_dw, long long n_db,
+                                                           int splits) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const long long n = n_dw + n_db, stride = n;
   if (i >= n) return;
-  float4 a = *reinterpret_cast<const float4*>(g + i);
-  for (int s = 0; s < splits; ++s) {
+  float* g = i < n_dw ? dw + i : db + (i - n_dw);
+  float4 a = *reinterpret_cast<const float4*>(g);
+  // eight independent loads in flight, added in slice order
+  int s = 0;
+  for (; s + 8 <= splits; s += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(ws + (size_t)(s + k) * stride + i));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
+    }
+  }
+  for (; s < splits; ++s) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(ws + (size_t)s * stride + i));
     a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
   }
-  *reinterpret_cast<float4*>(g + i) = a;
+  *reinterpret_cast<float4*>(g) = a;
 }
 
 constexpr int kWgTile = 128 * 64 * 2;  // one [128 pixels x 64 channels] bf16 box
@@ -1025,11 +1040,11 @@ int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, float* db, cudaStream_t st
     if ((rc = scratch_workspace(need, reinterpret_cast<void**>(&ws)))) return rc;
     if (shared_slabs) TVAE_CHECK_CUDA(cudaMemsetAsync(ws, 0, need, stream));   // a phase writes only its own slabs
     else if (poison) TVAE_CHECK_CUDA(cudaMemsetAsync(ws, 0xFF, need, stream));
-    P.dw = ws;
-    P.ws_dw_stride = n_dw;
+    P.dw = ws;                            // slice = [dw | db]
+    P.ws_dw_stride = n_dw + n_db;
     if (db != nullptr) {
-      P.db = ws + (size_t)slices * n_dw;
-      P.ws_db_stride = n_db;
+      P.db = ws + n_dw;
+      P.ws_db_stride = n_dw + n_db;
     }
   } else {
     P.ws_phases = 1;
@@ -1051,10 +1066,7 @@ int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, float* db, cudaStream_t st
   }
   if (rc) return rc;
   if (ws != nullptr) {
-    wgrad_reduce_kernel<<<(unsigned)((n_dw / 4 + 255) / 256), 256, 0, stream>>>(dw, ws, n_dw, n_dw, (int)slices);
-    if (db != nullptr)
-      wgrad_reduce_kernel<<<(unsigned)((n_db / 4 + 255) / 256), 256, 0, stream>>>(db, ws + (size_t)slices * n_dw, n_db, n_db,
-                                                                                  (int)slices);
+    wgrad_reduce_kernel<<<(unsigned)(((n_dw + n_db) / 4 + 255) / 256), 256, 0, stream>>>(dw, db, ws, n_dw, n_db, (int)slices);
     TVAE_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
