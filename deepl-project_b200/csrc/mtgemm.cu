@@ -23,8 +23,9 @@
 namespace tvae {
 
 int mtgemm2_dispatch(int epi, int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                     const CUtensorMap& o, const CUtensorMap& r, const CUtensorMap& ah, const MtParams& P,
-                     cudaStream_t stream);
+                     const CUtensorMap& o, const CUtensorMap& r, const CUtensorMap& ah, const CUtensorMap& x2,
+                     const MtParams& P, cudaStream_t stream);
+int act_fwd_run(const void* z, void* y, long long n, int act, cudaStream_t stream);   // backward.cu
 static int mtgemm1_dispatch(int epi, int block_n, const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB,
                             const CUtensorMap& mO, const CUtensorMap& mR, const MtParams& P, cudaStream_t stream);
 int gn_stats_run(const void* x, double* sums, int B, int HW, int C, int G, cudaStream_t stream);   // elementwise.cu
@@ -465,6 +466,14 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
   } else {
     epi = d->act == TVAE_ACT_GELU ? kEpiBiasGelu : (d->act == TVAE_ACT_SILU ? kEpiBiasSilu : kEpiBias);
   }
+  // dual output (training forward): `out` = pre-activation, `out_act` = activation of the stored bf16 values
+  const bool dual = d->out_act != nullptr;
+  if (dual) {
+    TVAE_REQUIRE(d->act_grad == 0 && !direct && !affine && d->rope_tab == nullptr && !P.has_residual &&
+                     d->gn_sums == nullptr && (d->act == TVAE_ACT_GELU || d->act == TVAE_ACT_SILU),
+                 "mtgemm: out_act needs a plain bias + GELU / SiLU epilogue");
+    epi = kEpiBias;          // until the CTA-pair kernel is chosen below
+  }
   // CTA-pair kernel (cta_group::2, weight tile split across the pair) whenever the tile is wide enough to matter
   static const bool use_pair = !(getenv("TVAE_2CTA") && atoi(getenv("TVAE_2CTA")) == 0);
   // halo mode: a plain 3x3 stride-1 convolution whose tiles are 128 pixels of one image row (W >= 128) loads ONE
@@ -498,17 +507,27 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
     }
   }
   if (pair) {
-    CUtensorMap mBh, mAh = mA0;
+    CUtensorMap mBh, mAh = mA0, mX2 = mO;
+    // The second staging tile of the dual epilogue costs pipeline stages (N = 256: 5 -> 3): worth it where the epilogue /
+    // HBM side sets the pace (K <= 4096), not for the long-K 3x3 convolutions (K = 13824: 1240 -> 1020 TFLOP/s, against
+    // a 10 us activation pass) -- those keep the deep pipeline and run tvae_act_fwd behind the GEMM.
+    const bool dual_fused = dual && d->k_total <= 4096;
+    if (dual_fused) {
+      epi = d->act == TVAE_ACT_GELU ? kEpiBiasGeluDual : kEpiBiasSiluDual;
+      if ((rc = make_tmap_pix(&mX2, d->out_act, d->out.B, d->out.H, d->out.W, d->out.C, d->out.split, P.tw, P.th, P.nb))) return rc;
+    }
     if ((rc = make_tmap_2d(&mBh, d->w, d->n_total, d->k_total, d->k_total, block_n / 2))) return rc;
     if (epi == kEpiResMulGeluGrad) {
-      // the pair kernel stages z (same plain view as the output) through TMA next to the residual; the halo-map slot
-      // carries its tensor map (halo tiles and this epilogue never meet: ConvFFN maps are narrower than 128 pixels)
-      if ((rc = make_tmap_pix(&mAh, d->z, d->out.B, d->out.H, d->out.W, d->out.C, d->out.split, P.tw, P.th, P.nb))) return rc;
-    } else if (halo_ok) {
+      // the pair kernel stages z (same plain view as the output) through TMA next to the residual
+      if ((rc = make_tmap_pix(&mX2, d->z, d->out.B, d->out.H, d->out.W, d->out.C, d->out.split, P.tw, P.th, P.nb))) return rc;
+    }
+    if (halo_ok) {
       if ((rc = make_tmap_pix_halo(&mAh, d->a0.ptr, d->a0.B, d->a0.H, d->a0.W, d->a0.C))) return rc;
       P.halo = 1;
     }
-    if ((rc = mtgemm2_dispatch(epi, block_n, mA0, mA1, mBh, mO, mR, mAh, P, stream))) return rc;
+    if ((rc = mtgemm2_dispatch(epi, block_n, mA0, mA1, mBh, mO, mR, mAh, mX2, P, stream))) return rc;
+    if (dual && !dual_fused)
+      return act_fwd_run(d->out.ptr, d->out_act, (long long)d->out.B * d->out.H * d->out.W * d->out.C, d->act, stream);
     if (d->gn_sums != nullptr && !gn_fused)
       return gn_stats_run(d->out.ptr, d->gn_sums, d->out.B, d->out.H * d->out.W, d->out.C, d->gn_groups, stream);
     return 0;
@@ -517,7 +536,10 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
     if ((rc = mtgemm1_dispatch(epi, block_n, mA0, mA1, mB, mO, mR, P, stream))) return rc;
     return gn_stats_run(d->out.ptr, d->gn_sums, d->out.B, d->out.H * d->out.W, d->out.C, d->gn_groups, stream);
   }
-  return mtgemm1_dispatch(epi, block_n, mA0, mA1, mB, mO, mR, P, stream);
+  if ((rc = mtgemm1_dispatch(epi, block_n, mA0, mA1, mB, mO, mR, P, stream))) return rc;
+  if (dual)    // one-CTA fallback: the activation as its own pass over the (complete, contiguous) output tensor
+    return act_fwd_run(d->out.ptr, d->out_act, (long long)d->out.B * d->out.H * d->out.W * d->out.C, d->act, stream);
+  return 0;
 }
 
 static int mtgemm1_dispatch(int epi, int block_n, const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB,

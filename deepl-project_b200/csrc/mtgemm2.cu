@@ -31,7 +31,9 @@ struct Mt2Cfg {
   // warp load touched 32 cache lines and the L1 tag stage, not HBM, set the pace -- 265 TFLOP/s / 2.1 TB/s on the
   // K = 384 input-gradient GEMMs of the ConvFFN.)
   static constexpr bool kStageZ = EPI == kEpiResMulGeluGrad;
-  static constexpr int kStagingBytes = kOutBytes * (kStageZ ? 2 : 1);
+  // the dual-output epilogues stage two OUTPUT tiles (pre-activation and activation)
+  static constexpr bool kDual = epi_is_dual<EPI>();
+  static constexpr int kStagingBytes = kOutBytes * (kStageZ || kDual ? 2 : 1);
   static constexpr int kStagesRaw = (227 * 1024 - 2048 - kStagingBytes) / (kABytes + kBHalfBytes);
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
@@ -46,7 +48,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmAh,
-               const __grid_constant__ MtParams P) {
+               const __grid_constant__ CUtensorMap tmX2, const __grid_constant__ MtParams P) {
 #ifdef TVAE_DEVICE_OK
   using Cfg = Mt2Cfg<BLOCK_N, EPI>;
   constexpr int STAGES = Cfg::kStages;
@@ -275,10 +277,10 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int j = 0; j < BLOCK_N / 64; ++j)
           tma_load_5d(sOut + j * kABytes, &tmRes, res_full, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph],
                       h0, b0);
-        if constexpr (Cfg::kStageZ) {        // the saved pre-activation z: same view as the output (tmAh carries its map)
+        if constexpr (Cfg::kStageZ) {        // the saved pre-activation z: same view as the output (map tmX2)
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
-            tma_load_5d(sZ + j * kABytes, &tmAh, res_full, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph], h0, b0);
+            tma_load_5d(sZ + j * kABytes, &tmX2, res_full, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph], h0, b0);
         }
       }
     }
@@ -375,9 +377,11 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           o.x = pack_bf16(fa[0], fa[1]); o.y = pack_bf16(fa[2], fa[3]);
           o.z = pack_bf16(fa[4], fa[5]); o.w = pack_bf16(fa[6], fa[7]);
           *pa = o;
+          if constexpr (Cfg::kDual) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(pa) + Cfg::kOutBytes) = epi_act_of_bf16<EPI>(o);
           o.x = pack_bf16(fb[0], fb[1]); o.y = pack_bf16(fb[2], fb[3]);
           o.z = pack_bf16(fb[4], fb[5]); o.w = pack_bf16(fb[6], fb[7]);
           *pb = o;
+          if constexpr (Cfg::kDual) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(pb) + Cfg::kOutBytes) = epi_act_of_bf16<EPI>(o);
         }
       };
       {
@@ -408,6 +412,8 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               if (store_leader) {
                 const int j = c16 >> 2;
                 tma_store_5d(&tmOut, sOut + j * kABytes, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph], h0, b0);
+                if constexpr (Cfg::kDual)
+                  tma_store_5d(&tmX2, sZ + j * kABytes, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph], h0, b0);
                 tma_store_commit();
               }
             }
@@ -427,8 +433,11 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (store_leader) {
 #pragma unroll
-          for (int j = 0; j < BLOCK_N / 64; ++j)
+          for (int j = 0; j < BLOCK_N / 64; ++j) {
             tma_store_5d(&tmOut, sOut + j * kABytes, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph], h0, b0);
+            if constexpr (Cfg::kDual)
+              tma_store_5d(&tmX2, sZ + j * kABytes, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph], h0, b0);
+          }
           tma_store_commit();
         }
         if constexpr (kGn) {
@@ -528,7 +537,7 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
 template <int BLOCK_N, int EPI>
 static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
-                   const CUtensorMap& r, const CUtensorMap& ah, const MtParams& P, cudaStream_t stream) {
+                   const CUtensorMap& r, const CUtensorMap& ah, const CUtensorMap& x2, const MtParams& P, cudaStream_t stream) {
   using Cfg = Mt2Cfg<BLOCK_N, EPI>;
   static bool configured = false;
   if (!configured) {
@@ -541,39 +550,42 @@ static int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorM
   int clusters = persistent_sms() / 2;
   if (clusters <= 0) clusters = 74;
   if (total_pairs < clusters) clusters = total_pairs;
-  mtgemm2_kernel<BLOCK_N, EPI><<<2 * clusters, kThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b, o, r, ah, P);
+  mtgemm2_kernel<BLOCK_N, EPI><<<2 * clusters, kThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b, o, r, ah, x2, P);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int EPI>
 static int launch2_n(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
-                     const CUtensorMap& r, const CUtensorMap& ah, const MtParams& P, cudaStream_t stream) {
+                     const CUtensorMap& r, const CUtensorMap& ah, const CUtensorMap& x2, const MtParams& P,
+                     cudaStream_t stream) {
   switch (block_n) {
-    case 256: return launch2<256, EPI>(a0, a1, b, o, r, ah, P, stream);
-    case 192: return launch2<192, EPI>(a0, a1, b, o, r, ah, P, stream);
-    case 64: return launch2<64, EPI>(a0, a1, b, o, r, ah, P, stream);
-    default: return launch2<128, EPI>(a0, a1, b, o, r, ah, P, stream);
+    case 256: return launch2<256, EPI>(a0, a1, b, o, r, ah, x2, P, stream);
+    case 192: return launch2<192, EPI>(a0, a1, b, o, r, ah, x2, P, stream);
+    case 64: return launch2<64, EPI>(a0, a1, b, o, r, ah, x2, P, stream);
+    default: return launch2<128, EPI>(a0, a1, b, o, r, ah, x2, P, stream);
   }
 }
 
 // Called by mtgemm_run (mtgemm.cu) when the CTA-pair kernel applies (block_n >= 128).  `b` must be a weight map with
 // box rows = block_n / 2.
 int mtgemm2_dispatch(int epi, int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                     const CUtensorMap& o, const CUtensorMap& r, const CUtensorMap& ah, const MtParams& P,
-                     cudaStream_t stream) {
+                     const CUtensorMap& o, const CUtensorMap& r, const CUtensorMap& ah, const CUtensorMap& x2,
+                     const MtParams& P, cudaStream_t stream) {
   switch (epi) {
-    case kEpiBias: return launch2_n<kEpiBias>(block_n, a0, a1, b, o, r, ah, P, stream);
-    case kEpiBiasRes: return launch2_n<kEpiBiasRes>(block_n, a0, a1, b, o, r, ah, P, stream);
-    case kEpiBiasGelu: return launch2_n<kEpiBiasGelu>(block_n, a0, a1, b, o, r, ah, P, stream);
-    case kEpiBiasSilu: return launch2_n<kEpiBiasSilu>(block_n, a0, a1, b, o, r, ah, P, stream);
-    case kEpiRsBiasGelu: return launch2_n<kEpiRsBiasGelu>(block_n, a0, a1, b, o, r, ah, P, stream);
-    case kEpiAffineRope: return launch2_n<kEpiAffineRope>(block_n, a0, a1, b, o, r, ah, P, stream);
-    case kEpiDirect: return launch2_n<kEpiDirect>(block_n, a0, a1, b, o, r, ah, P, stream);
-    case kEpiMulGeluGrad: return launch2_n<kEpiMulGeluGrad>(block_n, a0, a1, b, o, r, ah, P, stream);
-    case kEpiMulSiluGrad: return launch2_n<kEpiMulSiluGrad>(block_n, a0, a1, b, o, r, ah, P, stream);
-    case kEpiResMulGeluGrad: return launch2_n<kEpiResMulGeluGrad>(block_n, a0, a1, b, o, r, ah, P, stream);
-    default: return launch2_n<kEpiRsBias>(block_n, a0, a1, b, o, r, ah, P, stream);
+    case kEpiBias: return launch2_n<kEpiBias>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
+    case kEpiBiasRes: return launch2_n<kEpiBiasRes>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
+    case kEpiBiasGelu: return launch2_n<kEpiBiasGelu>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
+    case kEpiBiasSilu: return launch2_n<kEpiBiasSilu>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
+    case kEpiRsBiasGelu: return launch2_n<kEpiRsBiasGelu>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
+    case kEpiAffineRope: return launch2_n<kEpiAffineRope>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
+    case kEpiDirect: return launch2_n<kEpiDirect>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
+    case kEpiMulGeluGrad: return launch2_n<kEpiMulGeluGrad>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
+    case kEpiMulSiluGrad: return launch2_n<kEpiMulSiluGrad>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
+    case kEpiResMulGeluGrad: return launch2_n<kEpiResMulGeluGrad>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
+    case kEpiBiasGeluDual: return launch2_n<kEpiBiasGeluDual>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
+    case kEpiBiasSiluDual: return launch2_n<kEpiBiasSiluDual>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
+    default: return launch2_n<kEpiRsBias>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
   }
 }
 

@@ -80,8 +80,16 @@ enum Epi : int {
   // backward: the input-gradient GEMM applies the derivative of the producing layer's activation itself
   kEpiMulGeluGrad = 8,     // v = acc * gelu'(z),          z tile staged like a residual
   kEpiMulSiluGrad = 9,     // v = acc * silu'(z)
-  kEpiResMulGeluGrad = 10, // v = (acc + residual) * gelu'(z),  residual staged, z read from global memory
+  kEpiResMulGeluGrad = 10, // v = (acc + residual) * gelu'(z),  residual staged; z staged (pair kernel) or read from global memory
+  // training forward: ONE launch stores the pre-activation (what the backward pass needs) and the activation (what the
+  // next layer reads) -- the activation used to be a separate pass over HBM (tvae_act_fwd, 86 launches per micro-step)
+  kEpiBiasGeluDual = 11,   // out = acc + bias,  out_act = gelu(bf16(out))       (CTA-pair kernel only)
+  kEpiBiasSiluDual = 12,   // out = acc + bias,  out_act = silu(bf16(out))
 };
+template <int EPI>
+__host__ __device__ constexpr bool epi_is_dual() {
+  return EPI == kEpiBiasGeluDual || EPI == kEpiBiasSiluDual;
+}
 
 template <int EPI>
 __host__ __device__ constexpr bool epi_has_res() {
@@ -130,7 +138,16 @@ __device__ __forceinline__ void epi_res_mul_gelu_grad8(float (&f)[8], const uint
   }
 }
 
-enum : int { kEpiCount = 11 };
+// act(z) of eight staged bf16 pre-activations (the rounded values: exactly what a separate pass over the stored z gives)
+template <int EPI>
+__device__ __forceinline__ uint4 epi_act_of_bf16(const uint4& zu) {
+  float2 z[4] = {bf16x2_to_f2(zu.x), bf16x2_to_f2(zu.y), bf16x2_to_f2(zu.z), bf16x2_to_f2(zu.w)};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) z[k] = EPI == kEpiBiasGeluDual ? gelu2(z[k]) : silu2(z[k]);
+  return make_uint4(f2_to_bf16x2(z[0]), f2_to_bf16x2(z[1]), f2_to_bf16x2(z[2]), f2_to_bf16x2(z[3]));
+}
+
+enum : int { kEpiCount = 13 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"

@@ -314,8 +314,8 @@ class FfnDwFn(Fn):
         hid = win.shape[0]
         (win_f, win_d), (wout_f, wout_d) = _w_pack(win), _w_pack(wout)
         xn = ops.token_norm_fwd(x, w2n, 0)
-        z_in = ops.mtgemm(T.plan_linear(C), _flat(xn), win_f, out_shape=(1, 1, M, hid), bias=_f32(bin_))
-        u = ops.act_fwd(z_in, ACT_GELU)
+        z_in, u = ops.mtgemm(T.plan_linear(C), _flat(xn), win_f, out_shape=(1, 1, M, hid), bias=_f32(bin_), act=ACT_GELU,
+                             dual=True)
         wdw_c = _f32(wdw)
         u2 = ops.dwconv3x3(u.view(B, H, W, hid), wdw_c, _f32(bdw), flip=False, add_input=True)
         out = ops.mtgemm(T.plan_linear(hid), _flat(u2), wout_f, out_shape=(1, 1, M, C), bias=_f32(bout), residual=_flat(x))
@@ -352,8 +352,7 @@ class DownsampleFn(Fn):
         B, H, W, C = x.shape
         N = wdp.shape[0]
         dc = wdp.shape[1] == 13 * C            # [N, 9C] without the DC path (use_dc_path=False)
-        z0 = ops.mtgemm(T.plan_conv3x3(C), x, _bf(w0p), out_shape=(B, H, W, C), bias=_f32(b0))
-        y = ops.act_fwd(z0, ACT_SILU)
+        z0, y = ops.mtgemm(T.plan_conv3x3(C), x, _bf(w0p), out_shape=(B, H, W, C), bias=_f32(b0), act=ACT_SILU, dual=True)
         out = ops.mtgemm(T.plan_downsample(C, with_dc=dc), y, _bf(wdp), a1=x if dc else None,
                          out_shape=(B, H // 2, W // 2, N), bias=_f32(bd))
         ctx.save_for_backward(x, z0, y, w0p, wdp)
@@ -385,8 +384,8 @@ class UpsampleFn(Fn):
         Co = w1p.shape[0]
         b1e = _f32(b1).unsqueeze(0).expand(4, -1).contiguous()
         dc = w2p.shape[1] == 9 * Co + 4 * Ci   # [Co, 9 Co] without the DC path (use_dc_path=False)
-        z1 = ops.mtgemm(T.plan_upsample_conv1(Ci, Co), x, _bf(w1p), out_shape=(B, 2 * H, 2 * W, Co), bias=b1e)
-        y = ops.act_fwd(z1, ACT_SILU)
+        z1, y = ops.mtgemm(T.plan_upsample_conv1(Ci, Co), x, _bf(w1p), out_shape=(B, 2 * H, 2 * W, Co), bias=b1e,
+                           act=ACT_SILU, dual=True)
         out = ops.mtgemm(T.plan_upsample_conv2(Co, Ci, with_dc=dc), y, _bf(w2p), a1=x if dc else None,
                          out_shape=(B, 2 * H, 2 * W, Co), bias=_f32(b2p))
         ctx.save_for_backward(x, z1, y, w1p, w2p)
@@ -460,12 +459,11 @@ class FfnFn(Fn):
         (win_f, win_d), (wc0_f, wc0_d), (wc2_f, wc2_d) = _w_pack(win), _w_pack(wc0), _w_pack(wc2)
         (wc4_f, wc4_d), (wout_f, wout_d) = _w_pack(wc4), _w_pack(wout)
         xn = ops.token_norm_fwd(x, w2n, 0)
-        z_in = ops.mtgemm(T.plan_linear(C), _flat(xn), win_f, out_shape=(1, 1, M, hid), bias=_f32(bin_))
-        u = ops.act_fwd(z_in, ACT_GELU)
-        z0 = ops.mtgemm(T.plan_linear(hid), u, wc0_f, out_shape=(1, 1, M, mid), bias=_f32(bc0))
-        t0 = ops.act_fwd(z0, ACT_GELU)
-        z2 = ops.mtgemm(T.plan_conv3x3(mid), t0.view(B, H, W, mid), wc2_f, out_shape=(B, H, W, mid), bias=_f32(bc2))
-        t2 = ops.act_fwd(z2, ACT_GELU)
+        z_in, u = ops.mtgemm(T.plan_linear(C), _flat(xn), win_f, out_shape=(1, 1, M, hid), bias=_f32(bin_), act=ACT_GELU,
+                             dual=True)
+        z0, t0 = ops.mtgemm(T.plan_linear(hid), u, wc0_f, out_shape=(1, 1, M, mid), bias=_f32(bc0), act=ACT_GELU, dual=True)
+        z2, t2 = ops.mtgemm(T.plan_conv3x3(mid), t0.view(B, H, W, mid), wc2_f, out_shape=(B, H, W, mid), bias=_f32(bc2),
+                            act=ACT_GELU, dual=True)
         u2 = ops.mtgemm(T.plan_linear(mid), _flat(t2), wc4_f, out_shape=(1, 1, M, hid), bias=_f32(bc4), residual=u)
         out = ops.mtgemm(T.plan_linear(hid), u2, wout_f, out_shape=(1, 1, M, C), bias=_f32(bout), residual=_flat(x))
         ctx.save_for_backward(x, w2n, xn, z_in, u, z0, t0, z2, t2, u2, wc2, win_d, wc0_d, wc2_d, wc4_d, wout_d, win, wc0, wc4, wout,

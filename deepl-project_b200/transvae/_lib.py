@@ -43,7 +43,7 @@ class MtGemmDesc(C.Structure):
         ("q_scale", C.c_float),
         ("out_f32", C.c_void_p), ("out_n", C.c_int32),
         ("act_grad", C.c_int32), ("z", C.c_void_p),
-        ("gn_sums", C.c_void_p), ("gn_groups", C.c_int32),
+        ("gn_sums", C.c_void_p), ("gn_groups", C.c_int32), ("out_act", C.c_void_p),
     ]
 
 

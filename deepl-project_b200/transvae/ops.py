@@ -117,7 +117,7 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
            residual: Optional[Tensor] = None, row_scale: Optional[Tensor] = None, row_shift: Optional[Tensor] = None,
            col_sum: Optional[Tensor] = None, rope: Optional[Tuple[Tensor, int, int, int, float]] = None,
            out_f32: Optional[Tensor] = None, out_f32_shape: Optional[Sequence[int]] = None, out_n: int = 0,
-           act_grad_z: Optional[Tensor] = None, gn_groups: int = 0) -> Tensor:
+           act_grad_z: Optional[Tensor] = None, gn_groups: int = 0, dual: bool = False):
     """Launch ``tvae_mtgemm``.  a0 / a1 / out / residual are NHWC bf16 4-D tensors (flat matrices as
     [1, 1, M, K]); ``w`` is the packed bf16 [N, K_total] weight; ``bias`` fp32 [phases, N] (or [N]).
 
@@ -126,7 +126,10 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
     attaches them to the returned tensor as ``out._gn_sums`` for ``groupnorm_silu(..., sums=...)``.
 
     Backward fusion: with ``act_grad_z`` (the saved pre-activation, same shape as the output) and ``act`` set, the launch
-    returns ``acc * act'(z)`` -- or ``(acc + residual) * act'(z)`` when ``residual`` is given too (GELU, plain views)."""
+    returns ``acc * act'(z)`` -- or ``(acc + residual) * act'(z)`` when ``residual`` is given too (GELU, plain views).
+
+    ``dual=True`` (training forward, ``act`` set, plain bias epilogue): returns ``(z, act(z))`` -- the pre-activation the
+    backward pass needs and the activation the next layer reads, stored by one launch."""
     _need_cuda(a0, w, a1, out, bias, residual, row_scale, row_shift, col_sum, out_f32)
     assert w.dtype == BF16 and w.is_contiguous() and w.shape[1] == plan.k_total, (w.shape, plan.k_total)
     d = MtGemmDesc()
@@ -178,6 +181,11 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
         assert out_f32 is None and out.shape[-1] == n_total
         gn_sums = torch.empty(out.shape[0], gn_groups, 2, dtype=torch.float64, device=a0.device)
     d.gn_sums, d.gn_groups = _ptr(gn_sums), gn_groups
+    out_act = None
+    if dual:
+        assert out_f32 is None and act != ACT_NONE and residual is None and act_grad_z is None and not gn_groups
+        out_act = torch.empty_like(out)
+    d.out_act = _ptr(out_act)
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -192,6 +200,8 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
     _count()
     if gn_sums is not None:
         out._gn_sums = gn_sums
+    if dual:
+        return out, out_act
     return out if out_f32 is None else out_f32
 
 

@@ -108,6 +108,10 @@ typedef struct {
    * output behind the GEMM.  Requires a bf16 output whose channel count equals n_total. */
   double* gn_sums;
   int32_t gn_groups;
+  /* Optional second output of the training forward pass (act = GELU / SiLU, plain bias epilogue): `out` then receives the
+   * PRE-activation acc + bias (what the backward pass differentiates through) and out_act -- bf16, same geometry as
+   * `out` -- the activation of the stored bf16 values, both from one launch (conv.py:86,56,58; upsample.py:35,96). */
+  void* out_act;
 } tvae_mtgemm_desc;
 
 int tvae_mtgemm(const tvae_mtgemm_desc* desc /* HOST pointer */, void* stream);
