@@ -197,6 +197,9 @@ def test_resolutions_and_batch_shapes():
             assert rec.shape == x.shape and torch.isfinite(rec).all()
 
 
+LARGE_TOL = 4e-2      # measured [B200]: mu 0.013, logvar 0.015, recon 0.022 (decoder alone 0.013)
+
+
 def test_large_f16d32_parity_at_256():
     """BASELINE.json configs[1] model at full size (B=1 so the CPU oracle finishes in seconds)."""
     cfg = O.variant_config("large")
@@ -211,7 +214,8 @@ def test_large_f16d32_parity_at_256():
         rec_dec = m.decode(mu_o.cuda())
     e = dict(mu=rel(mu, mu_o), logvar=rel(lv, lv_o), recon_e2e=rel(rec, rec_o), recon_dec=rel(rec_dec, rec_o))
     print("large@256:", e)
-    assert max(e.values()) < 8e-2, e
+    # end to end through 34 blocks at bf16: the reference's own bf16-autocast forward is 2.6e-2 off its fp32 result here
+    assert max(e.values()) < LARGE_TOL, e
     for ours, ref in zip(psnr_pair(rec.cpu(), x), psnr_pair(rec_o, x)):
         print("PSNR ours/ref", ours, ref)
         assert abs(ours - ref) < PSNR_TOL
@@ -280,11 +284,9 @@ def test_ablation_variants_forward_and_backward(flags):
     lo = O.loss_l1_kl(ro, x, muo, lvo, 1.0, 1e-8, patched=True)["total"]
     lo.backward()
     assert abs(float(loss) - float(lo)) < 5e-3
-    cos = []
     for k, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), k
-        g, go = p.grad.float().cpu().flatten(), sdg[k].grad.flatten()
-        if float(go.norm()) > 0:
-            cos.append(float(torch.dot(g, go) / (g.norm() * go.norm()).clamp_min(1e-30)))
-    cos.sort()
-    assert cos[len(cos) // 2] > 0.9, cos[len(cos) // 2]      # median direction agreement (L1 sign noise)
+    # gradient parity, tensor by tensor, with a smooth upstream gradient and the reference's own bf16-autocast error as
+    # calibration (round 1 only asked for a median cosine > 0.9 between L1 gradients, whose signs flip under bf16 noise)
+    from util import gradient_parity_rows, assert_gradient_parity
+    assert_gradient_parity(gradient_parity_rows(m, sd, cfg, x.cuda(), eps.cuda()), tag=str(flags))

@@ -72,56 +72,16 @@ def test_block_gradients(kind):
     assert not bad, bad
 
 
-def _smooth_objective(recon, mu, logvar, G):
-    """A fixed linear functional of the outputs.  The L1 loss gradient is sign(recon - x): bf16-level forward noise flips
-    signs, so whole-model L1 gradients differ by tens of percent between ANY two bf16 runs (measured: the reference's own
-    bf16 autocast is 37 % off its fp32 gradients on this fixture, two identical runs of ours 60 %).  Parity of the
-    backward pass is therefore checked with a smooth upstream gradient; the loss kernels have their own exact tests."""
-    return (recon.float() * G[0]).sum() + (mu.float() * G[1]).sum() + (logvar.float() * G[2]).sum()
+from util import smooth_objective as _smooth_objective  # noqa: E402
+from util import gradient_parity_rows, assert_gradient_parity  # noqa: E402
 
 
 @pytest.mark.parametrize("name", ["mini_tamed", "mini_tamed_128"])
 def test_whole_model_gradients_vs_oracle_with_bf16_calibration(name):
     blob, sd = load_golden(name)
-    cfg = blob["cfg"]
-    m = build_model(cfg, sd, patched=True).train()
-    x = blob["x"].cuda()
-    eps = blob["eps"].cuda()
-    g = torch.Generator().manual_seed(5)
-    G = [torch.randn(blob["x"].shape, generator=g).cuda() / blob["x"].numel(),
-         torch.randn(blob["mu"].shape, generator=g).cuda() / blob["mu"].numel(),
-         torch.randn(blob["mu"].shape, generator=g).cuda() / blob["mu"].numel()]
-    recon, mu, logvar = m(x, eps=eps)
-    _smooth_objective(recon, mu, logvar, G).backward()
-    ours = {k: p.grad.detach().float() for k, p in m.named_parameters()}
-
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-
-    def oracle(autocast):
-        sdg = {k: v.cuda().clone().requires_grad_("inv_freq" not in k) for k, v in sd.items()}
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
-            rec, mu_o, lv_o, _ = O.forward(sdg, cfg, x, eps, patched=True)
-        _smooth_objective(rec, mu_o, lv_o, G).backward()
-        return {k: v.grad.detach().float() for k, v in sdg.items() if v.requires_grad}
-
-    ref, ac = oracle(False), oracle(True)
-    rows = []
-    for k in ours:
-        n = float(ref[k].norm())
-        if n < 1e-12:
-            continue
-        e_ours = float((ours[k] - ref[k]).norm()) / n
-        e_ac = float((ac[k] - ref[k]).norm()) / n
-        rows.append((e_ours, e_ac, k))
-    med_ours = sorted(r[0] for r in rows)[len(rows) // 2]
-    med_ac = sorted(r[1] for r in rows)[len(rows) // 2]
-    worst = sorted(rows, key=lambda r: -(r[0] / max(r[1], 5e-3)))[:6]
-    print(name, "median l2 rel err ours %.4f / reference-bf16-autocast %.4f; worst vs calibration:" % (med_ours, med_ac), worst)
-    # parity bar: no worse than 2.5x the reference's own bf16 path (or 3e-2 absolute), tensor by tensor
-    bad = [(k, eo, ea) for eo, ea, k in rows if eo > max(2.5 * ea, 3e-2)]
-    assert not bad, bad[:8]
-    assert med_ours < max(1.5 * med_ac, 2e-2)
+    m = build_model(blob["cfg"], sd, patched=True).train()
+    rows = gradient_parity_rows(m, sd, blob["cfg"], blob["x"].cuda(), blob["eps"].cuda())
+    assert_gradient_parity(rows, tag=name)
 
 
 @pytest.mark.parametrize("name", ["mini_tamed", "mini_ref"])
