@@ -27,6 +27,8 @@ int bias_act_bwd_matrix_run(const void* dy, const void* z, void* dz, float* cols
 int act_fwd_run(const void* z, void* y, long long n, int act, cudaStream_t stream);
 int gn_bwd_run(const void* x, const void* dh, const void* add, const double* sums, const float* gamma, const float* beta,
                float* part, void* dx, int B, int HW, int C, int G, float eps, int apply_silu, cudaStream_t stream);
+int gn_bwd_apply_run(const void* x, const void* dh, const void* add, const double* sums, const float* gamma, const float* beta,
+                     const float* part, void* dx, int B, int HW, int C, int G, float eps, int apply_silu, cudaStream_t stream);
 int token_norm_fwd_run(const void* x, const float* w, void* y, long long M, int C, int mode, cudaStream_t stream);
 int token_norm_bwd_run(const void* x, const float* w, const void* dy, const void* add, void* dx, float* dw, long long M,
                        int C, int mode, cudaStream_t stream);
@@ -156,6 +158,11 @@ int tvae_groupnorm_bwd(const void* x, const void* dh, const void* add, const dou
                        float* part, void* dx, int32_t B, int32_t HW, int32_t C, int32_t G, float eps, int32_t apply_silu,
                        void* stream) {
   GUARD(); return gn_bwd_run(x, dh, add, sums, gamma, beta, part, dx, B, HW, C, G, eps, apply_silu, S_(stream));
+}
+int tvae_groupnorm_bwd_apply(const void* x, const void* dh, const void* add, const double* sums, const float* gamma,
+                             const float* beta, const float* part, void* dx, int32_t B, int32_t HW, int32_t C, int32_t G,
+                             float eps, int32_t apply_silu, void* stream) {
+  GUARD(); return gn_bwd_apply_run(x, dh, add, sums, gamma, beta, part, dx, B, HW, C, G, eps, apply_silu, S_(stream));
 }
 int tvae_token_norm_fwd(const void* x, const float* w, void* y, int64_t M, int32_t C, int32_t mode, void* stream) {
   GUARD(); return token_norm_fwd_run(x, w, y, M, C, mode, S_(stream));

@@ -370,10 +370,16 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restri
   }
 }
 
-int gn_bwd_run(const void* x, const void* dh, const void* add, const double* sums, const float* gamma, const float* beta,
-               float* part, void* dx, int B, int HW, int C, int G, float eps, int apply_silu, cudaStream_t stream) {
+static int gn_bwd_check(int B, int C, int G) {
   TVAE_REQUIRE(C % 8 == 0 && C % G == 0 && C / 8 <= 256 && G <= 128, "groupnorm_bwd: unsupported C=%d G=%d", C, G);
   TVAE_REQUIRE(B <= kGnMaxImages, "groupnorm_bwd: batch %d exceeds %d", B, kGnMaxImages);
+  return 0;
+}
+
+// reduce pass: part [B][C][2] = per-(image, channel) (sum dy, sum dy * xhat)
+int gn_bwd_reduce_run(const void* x, const void* dh, const double* sums, const float* gamma, const float* beta, float* part,
+                      int B, int HW, int C, int G, float eps, int apply_silu, cudaStream_t stream) {
+  if (int rc = gn_bwd_check(B, C, G)) return rc;
   const int nvec = C / 8;
   const int threads = (256 / nvec) * nvec;
   int ppb = 1024;
@@ -381,7 +387,6 @@ int gn_bwd_run(const void* x, const void* dh, const void* add, const double* sum
   dim3 g1((HW + ppb - 1) / ppb, B);
   const uint4* xp = reinterpret_cast<const uint4*>(x);
   const uint4* dp = reinterpret_cast<const uint4*>(dh);
-  const uint4* ap = reinterpret_cast<const uint4*>(add);
   const size_t smem_r = (size_t)(threads / nvec) * 2 * C * sizeof(float);       // <= 16 KiB
   float* ws = nullptr;
   {
@@ -391,6 +396,46 @@ int gn_bwd_run(const void* x, const void* dh, const void* add, const double* sum
   if (apply_silu) gn_bwd_reduce_kernel<true><<<g1, threads, smem_r, stream>>>(xp, dp, sums, gamma, beta, part, ws, HW, C, G, eps, ppb);
   else gn_bwd_reduce_kernel<false><<<g1, threads, smem_r, stream>>>(xp, dp, sums, gamma, beta, part, ws, HW, C, G, eps, ppb);
   TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Fixed-order sum of per-tile partial rows (the fused reduce of the input-gradient GEMM epilogue, mtgemm2.cu kEpiGnBwd):
+// tiles [B][tiles_per_image][n] -> out [B][n] in two levels (groups of kGnTileGroup tiles, then the groups).
+constexpr int kGnTileGroup = 32;
+__global__ void __launch_bounds__(256) gn_bwd_tiles_reduce_kernel(const float* __restrict__ in, float* __restrict__ out, int n,
+                                                                  int rows_per_image, int group) {
+  const int b = blockIdx.z, g = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r0 = g * group;
+  const int cnt = min(group, rows_per_image - r0);
+  const float* p = in + ((size_t)b * rows_per_image + r0) * n + i;
+  out[((size_t)b * gridDim.y + g) * n + i] = ordered_column_sum(p, (size_t)n, (unsigned int)cnt);
+}
+
+int gn_bwd_tiles_reduce_run(const float* part_tiles, float* groups_ws, float* part, int B, int tiles_per_image, int n,
+                            cudaStream_t stream) {
+  const int ngroups = (tiles_per_image + kGnTileGroup - 1) / kGnTileGroup;
+  dim3 g1((n + 255) / 256, ngroups, B), g2((n + 255) / 256, 1, B);
+  if (ngroups == 1) {
+    gn_bwd_tiles_reduce_kernel<<<g2, 256, 0, stream>>>(part_tiles, part, n, tiles_per_image, tiles_per_image);
+  } else {
+    gn_bwd_tiles_reduce_kernel<<<g1, 256, 0, stream>>>(part_tiles, groups_ws, n, tiles_per_image, kGnTileGroup);
+    gn_bwd_tiles_reduce_kernel<<<g2, 256, 0, stream>>>(groups_ws, part, n, ngroups, ngroups);
+  }
+  TVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// apply pass: dx = dGN(dh) [+ add] from the per-(image, channel) sums in `part`
+int gn_bwd_apply_run(const void* x, const void* dh, const void* add, const double* sums, const float* gamma, const float* beta,
+                     const float* part, void* dx, int B, int HW, int C, int G, float eps, int apply_silu, cudaStream_t stream) {
+  if (int rc = gn_bwd_check(B, C, G)) return rc;
+  const int nvec = C / 8;
+  const int threads = (256 / nvec) * nvec;
+  const uint4* xp = reinterpret_cast<const uint4*>(x);
+  const uint4* dp = reinterpret_cast<const uint4*>(dh);
+  const uint4* ap = reinterpret_cast<const uint4*>(add);
   const long long total = (long long)HW * nvec;
   long long vpb = (long long)threads * kEwBatch * 4;
   while (vpb > threads && ((total + vpb - 1) / vpb) * B < 8LL * num_sms()) vpb >>= 1;
@@ -409,6 +454,12 @@ int gn_bwd_run(const void* x, const void* dh, const void* add, const double* sum
 #undef TVAE_GN_APPLY
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+int gn_bwd_run(const void* x, const void* dh, const void* add, const double* sums, const float* gamma, const float* beta,
+               float* part, void* dx, int B, int HW, int C, int G, float eps, int apply_silu, cudaStream_t stream) {
+  if (int rc = gn_bwd_reduce_run(x, dh, sums, gamma, beta, part, B, HW, C, G, eps, apply_silu, stream)) return rc;
+  return gn_bwd_apply_run(x, dh, add, sums, gamma, beta, part, dx, B, HW, C, G, eps, apply_silu, stream);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -26,6 +26,10 @@ int mtgemm2_dispatch(int epi, int block_n, const CUtensorMap& a0, const CUtensor
                      const CUtensorMap& o, const CUtensorMap& r, const CUtensorMap& ah, const CUtensorMap& x2,
                      const MtParams& P, cudaStream_t stream);
 int act_fwd_run(const void* z, void* y, long long n, int act, cudaStream_t stream);   // backward.cu
+int gn_bwd_reduce_run(const void* x, const void* dh, const double* sums, const float* gamma, const float* beta, float* part,
+                      int B, int HW, int C, int G, float eps, int apply_silu, cudaStream_t stream);          // backward.cu
+int gn_bwd_tiles_reduce_run(const float* part_tiles, float* groups_ws, float* part, int B, int tiles_per_image, int n,
+                            cudaStream_t stream);                                                            // backward.cu
 static int mtgemm1_dispatch(int epi, int block_n, const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB,
                             const CUtensorMap& mO, const CUtensorMap& mR, const MtParams& P, cudaStream_t stream);
 int gn_stats_run(const void* x, double* sums, int B, int HW, int C, int G, cudaStream_t stream);   // elementwise.cu
@@ -466,6 +470,15 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
   } else {
     epi = d->act == TVAE_ACT_GELU ? kEpiBiasGelu : (d->act == TVAE_ACT_SILU ? kEpiBiasSilu : kEpiBias);
   }
+  // fused GroupNorm-backward reduce (input-gradient GEMM of a ResBlock): plain epilogue only
+  const bool gnb = d->gnb_part != nullptr;
+  if (gnb) {
+    TVAE_REQUIRE(d->gnb_x != nullptr && d->gnb_sums != nullptr && d->gnb_gamma != nullptr && d->gnb_beta != nullptr &&
+                     d->gnb_groups >= 1 && d->n_total % d->gnb_groups == 0 && d->out.C == d->n_total && !d->out.split,
+                 "mtgemm: gnb_* needs x / sums / gamma / beta and a plain output view with n_total channels");
+    TVAE_REQUIRE(epi == kEpiBias && d->bias == nullptr && d->gn_sums == nullptr && d->out_act == nullptr,
+                 "mtgemm: the fused GroupNorm-backward reduce needs a plain epilogue");
+  }
   // dual output (training forward): `out` = pre-activation, `out_act` = activation of the stored bf16 values
   const bool dual = d->out_act != nullptr;
   if (dual) {
@@ -511,6 +524,28 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
     // The second staging tile of the dual epilogue costs pipeline stages (N = 256: 5 -> 3): worth it where the epilogue /
     // HBM side sets the pace (K <= 4096), not for the long-K 3x3 convolutions (K = 13824: 1240 -> 1020 TFLOP/s, against
     // a 10 us activation pass) -- those keep the deep pipeline and run tvae_act_fwd behind the GEMM.
+    // fused GroupNorm-backward reduce: one image per 128-pixel tile, the n tiles cover the channels exactly
+    static const bool allow_gnb = !(getenv("TVAE_GNB_FUSED") && atoi(getenv("TVAE_GNB_FUSED")) == 0);
+    const bool gnb_fused = gnb && allow_gnb && P.nb == 1 && d->n_total % block_n == 0 && d->gnb_groups <= 128;
+    float* gnb_ws = nullptr;
+    const int m_tiles_all = P.tiles_w * P.tiles_h * P.tiles_b;
+    const int tiles_per_image = P.tiles_w * P.tiles_h;
+    if (gnb_fused) {
+      const size_t rows = (size_t)m_tiles_all + (size_t)d->out.B * ((tiles_per_image + 31) / 32);
+      if ((rc = scratch_workspace(rows * 2 * d->n_total * sizeof(float), reinterpret_cast<void**>(&gnb_ws)))) return rc;
+      epi = kEpiGnBwd;
+      if ((rc = make_tmap_pix(&mX2, d->gnb_x, d->out.B, d->out.H, d->out.W, d->out.C, d->out.split, P.tw, P.th, P.nb))) return rc;
+      P.gnb_x = d->gnb_x;
+      P.gnb_sums = d->gnb_sums;
+      P.gnb_gamma = d->gnb_gamma;
+      P.gnb_beta = d->gnb_beta;
+      P.gnb_part = gnb_ws;
+      P.gnb_groups = d->gnb_groups;
+      P.gnb_cpg = d->n_total / d->gnb_groups;
+      P.gnb_silu = d->gnb_silu;
+      P.gnb_eps = d->gnb_eps;
+      P.gnb_inv_n = 1.0f / ((float)(d->n_total / d->gnb_groups) * (float)(d->out.H * d->out.W));
+    }
     const bool dual_fused = dual && d->k_total <= 4096;
     if (dual_fused) {
       epi = d->act == TVAE_ACT_GELU ? kEpiBiasGeluDual : kEpiBiasSiluDual;
@@ -528,6 +563,12 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
     if ((rc = mtgemm2_dispatch(epi, block_n, mA0, mA1, mBh, mO, mR, mAh, mX2, P, stream))) return rc;
     if (dual && !dual_fused)
       return act_fwd_run(d->out.ptr, d->out_act, (long long)d->out.B * d->out.H * d->out.W * d->out.C, d->act, stream);
+    if (gnb_fused)
+      return gn_bwd_tiles_reduce_run(gnb_ws, gnb_ws + (size_t)m_tiles_all * 2 * d->n_total, d->gnb_part, d->out.B,
+                                     tiles_per_image, 2 * d->n_total, stream);
+    if (gnb)
+      return gn_bwd_reduce_run(d->gnb_x, d->out.ptr, d->gnb_sums, d->gnb_gamma, d->gnb_beta, d->gnb_part, d->out.B,
+                               d->out.H * d->out.W, d->out.C, d->gnb_groups, d->gnb_eps, d->gnb_silu, stream);
     if (d->gn_sums != nullptr && !gn_fused)
       return gn_stats_run(d->out.ptr, d->gn_sums, d->out.B, d->out.H * d->out.W, d->out.C, d->gn_groups, stream);
     return 0;
@@ -539,6 +580,9 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
   if ((rc = mtgemm1_dispatch(epi, block_n, mA0, mA1, mB, mO, mR, P, stream))) return rc;
   if (dual)    // one-CTA fallback: the activation as its own pass over the (complete, contiguous) output tensor
     return act_fwd_run(d->out.ptr, d->out_act, (long long)d->out.B * d->out.H * d->out.W * d->out.C, d->act, stream);
+  if (gnb)     // one-CTA fallback: the stand-alone reduce pass
+    return gn_bwd_reduce_run(d->gnb_x, d->out.ptr, d->gnb_sums, d->gnb_gamma, d->gnb_beta, d->gnb_part, d->out.B,
+                             d->out.H * d->out.W, d->out.C, d->gnb_groups, d->gnb_eps, d->gnb_silu, stream);
   return 0;
 }
 

@@ -33,7 +33,13 @@ struct Mt2Cfg {
   static constexpr bool kStageZ = EPI == kEpiResMulGeluGrad;
   // the dual-output epilogues stage two OUTPUT tiles (pre-activation and activation)
   static constexpr bool kDual = epi_is_dual<EPI>();
-  static constexpr int kStagingBytes = kOutBytes * (kStageZ || kDual ? 2 : 1);
+  // kEpiGnBwd stages the GroupNorm input x next to the output tile (second INPUT tile, no residual in the first).  The
+  // second tile costs the halo pipeline a stage (3 -> 2: the GEMM itself drops from 1670 to 1250 TFLOP/s at N = 192), still
+  // cheaper than the stand-alone reduce pass; reading x from global memory in the epilogue instead (behind an L2 tensor
+  // prefetch, three stages kept) was measured far slower: 1.88 vs 1.12 ms per launch -- LSU loads queue behind the TMA
+  // operand traffic.
+  static constexpr bool kStageX = EPI == kEpiGnBwd;
+  static constexpr int kStagingBytes = kOutBytes * (kStageZ || kDual || kStageX ? 2 : 1);
   static constexpr int kStagesRaw = (227 * 1024 - 2048 - kStagingBytes) / (kABytes + kBHalfBytes);
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
@@ -53,6 +59,7 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   using Cfg = Mt2Cfg<BLOCK_N, EPI>;
   constexpr int STAGES = Cfg::kStages;
   constexpr bool kHasRes = epi_has_res<EPI>();
+  constexpr bool kStageX = Cfg::kStageX;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -267,12 +274,18 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ residual loader (each CTA, own tile)
-    if (lane == 0 && has_res) {
+    if (lane == 0 && (has_res || kStageX)) {
       int it = 0;
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++it) {
         TVAE_DECODE_PAIR(pt)
         mbar_wait(out_free, (it & 1) ^ 1);
-        mbar_arrive_expect_tx(res_full, Cfg::kStagingBytes);
+        mbar_arrive_expect_tx(res_full, kStageX ? Cfg::kOutBytes : Cfg::kStagingBytes);
+        if constexpr (kStageX) {             // the GroupNorm input x of this tile (map tmX2) -> second staging tile
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_5d(sZ + j * kABytes, &tmX2, res_full, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph], h0, b0);
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < BLOCK_N / 64; ++j)
           tma_load_5d(sOut + j * kABytes, &tmRes, res_full, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph],
@@ -296,13 +309,12 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // tile) were bound by the epilogue's TMEM drain + store latency.  Needs at least two chunks.
     constexpr int kChunks = BLOCK_N / 64;
     constexpr bool kCanPipe = EPI != kEpiDirect && kChunks >= 2;
-    const bool pipe = kCanPipe && !has_res && !gn;
+    const bool pipe = kCanPipe && !has_res && !gn && !kStageX;
     int it = 0;
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++it) {
       TVAE_DECODE_PAIR(pt)
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-
       EpiRow R;
       const __nv_bfloat16* zrow = nullptr;
       {
@@ -325,11 +337,12 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
       const float* bias = P.bias ? P.bias + (size_t)ph * P.n_total : nullptr;
-      const bool gn_zero_row = gn && !R.row_ok;   // clipped rows must not reach the statistics (TMA drops them anyway)
+      // clipped rows must not reach the statistics / the GroupNorm-backward sums (TMA drops them from the store anyway)
+      const bool gn_zero_row = (gn || kStageX) && !R.row_ok;
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      if (has_res) mbar_wait(res_full, it & 1);
+      if (has_res || kStageX) mbar_wait(res_full, it & 1);
 
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
       const int n_base = n_t * BLOCK_N;
@@ -367,7 +380,7 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               }
             }
           }
-          if constexpr (kGn) {
+          if constexpr (kGn || kStageX) {
             if (gn_zero_row) {
 #pragma unroll
               for (int k = 0; k < 8; ++k) fa[k] = fb[k] = 0.0f;
@@ -501,10 +514,68 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
           }
         }
+        if constexpr (kStageX) {
+          // Reduce pass of the GroupNorm backward over the two staged tiles (dh as stored, x): lanes = (8-channel column
+          // group, row mod 8) as in the forward statistics pass; dy = dh * act'(gamma * xhat + beta), per channel the sums
+          // of dy and dy * xhat over the tile's 128 pixels (3-step butterfly over the row lanes, fixed order).  Rows beyond
+          // the image were staged as zeros (gn_zero_row) and contribute nothing.
+          constexpr int kVec = BLOCK_N / 8;
+          const int gc = (warp - 4) * 4 + (lane >> 3);
+          const int rl = lane & 7;
+          if ((warp - 4) * 4 < kVec && b0 < P.vB) {          // warp-uniform; phantom tiles write nothing
+            const int c0 = n_t * BLOCK_N + gc * 8;
+            float2 ca[4], cb[4], cg[4], ce[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = c0 + 2 * i;
+              float m0, r0, m1, r1;
+              gn_mean_rstd(P.gnb_sums, b0, P.gnb_groups, c / P.gnb_cpg, P.gnb_inv_n, P.gnb_eps, m0, r0);
+              gn_mean_rstd(P.gnb_sums, b0, P.gnb_groups, (c + 1) / P.gnb_cpg, P.gnb_inv_n, P.gnb_eps, m1, r1);
+              ca[i] = make_float2(r0, r1);
+              cb[i] = make_float2(-m0 * r0, -m1 * r1);
+              cg[i] = make_float2(__ldg(P.gnb_gamma + c), __ldg(P.gnb_gamma + c + 1));
+              ce[i] = make_float2(__ldg(P.gnb_beta + c), __ldg(P.gnb_beta + c + 1));
+            }
+            const uint8_t* cd = sOut + (gc >> 3) * kABytes + rl * 128 + ((((gc & 7) ^ rl)) << 4);
+            const uint8_t* cx = cd + Cfg::kOutBytes;
+            float2 s1[4], s2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s1[i] = s2[i] = make_float2(0.0f, 0.0f);
+            const bool silu = P.gnb_silu != 0;
+#pragma unroll 4
+            for (int rb = 0; rb < kBlockM / 8; ++rb) {
+              float2 g[4], xf[4];
+              unpack8_2(*reinterpret_cast<const uint4*>(cd + rb * 1024), g);
+              unpack8_2(*reinterpret_cast<const uint4*>(cx + rb * 1024), xf);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 xh = __ffma2_rn(xf[i], ca[i], cb[i]);
+                const float2 dy = silu ? __fmul2_rn(g[i], silu_grad2(__ffma2_rn(xh, cg[i], ce[i]))) : g[i];
+                s1[i] = __fadd2_rn(s1[i], dy);
+                s2[i] = __ffma2_rn(dy, xh, s2[i]);
+              }
+            }
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                s1[i].x += __shfl_xor_sync(0xffffffffu, s1[i].x, m);
+                s1[i].y += __shfl_xor_sync(0xffffffffu, s1[i].y, m);
+                s2[i].x += __shfl_xor_sync(0xffffffffu, s2[i].x, m);
+                s2[i].y += __shfl_xor_sync(0xffffffffu, s2[i].y, m);
+              }
+            }
+            if (rl == 0) {
+              float4* dst = reinterpret_cast<float4*>(P.gnb_part + ((size_t)m_t * P.n_total + c0) * 2);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst[i] = make_float4(s1[i].x, s2[i].x, s1[i].y, s2[i].y);
+            }
+          }
+        }
         if (store_leader) tma_store_wait_read<0>();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         // the staged tile has been read by the TMA store and by the statistics pass: the residual loader may refill it
-        if (store_leader && has_res) mbar_arrive(out_free);
+        if (store_leader && (has_res || kStageX)) mbar_arrive(out_free);
         if constexpr (kGn) {
           if (gn) {
             const int et = (int)threadIdx.x - 128;
@@ -585,6 +656,7 @@ int mtgemm2_dispatch(int epi, int block_n, const CUtensorMap& a0, const CUtensor
     case kEpiResMulGeluGrad: return launch2_n<kEpiResMulGeluGrad>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
     case kEpiBiasGeluDual: return launch2_n<kEpiBiasGeluDual>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
     case kEpiBiasSiluDual: return launch2_n<kEpiBiasSiluDual>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
+    case kEpiGnBwd: return launch2_n<kEpiGnBwd>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
     default: return launch2_n<kEpiRsBias>(block_n, a0, a1, b, o, r, ah, x2, P, stream);
   }
 }

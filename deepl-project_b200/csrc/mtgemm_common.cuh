@@ -44,6 +44,16 @@ struct MtParams {
   // halo mode (3x3 stride-1 convolution, 128-pixel-wide tiles): ONE (128 + 2)-pixel A tile per (kernel row, K block)
   // serves the three dx taps through row-offset UMMA descriptors.  0 = off, 1 = on
   int halo;
+  // kEpiGnBwd: the launch is the input-gradient GEMM whose output dh feeds the backward of act(GroupNorm(x)); its epilogue
+  // also produces, per 128-pixel tile and channel, (sum dy, sum dy * xhat) with dy = dh * act'(gamma * xhat + beta):
+  // gnb_part [pixel tiles][n_total][2] fp32, plain stores (every element written once)
+  const void* gnb_x;            // the GroupNorm input, bf16, same (plain) geometry as the output
+  const double* gnb_sums;       // GroupNorm statistics of x: [vB][gnb_groups][2] (sum, sumsq)
+  const float* gnb_gamma;
+  const float* gnb_beta;
+  float* gnb_part;
+  int gnb_groups, gnb_cpg, gnb_silu;
+  float gnb_eps, gnb_inv_n;
 };
 
 constexpr int kBlockM = 128;
@@ -85,6 +95,8 @@ enum Epi : int {
   // next layer reads) -- the activation used to be a separate pass over HBM (tvae_act_fwd, 86 launches per micro-step)
   kEpiBiasGeluDual = 11,   // out = acc + bias,  out_act = gelu(bf16(out))       (CTA-pair kernel only)
   kEpiBiasSiluDual = 12,   // out = acc + bias,  out_act = silu(bf16(out))
+  // backward: input-gradient GEMM + the reduce pass of the GroupNorm backward that consumes its output (x tile staged)
+  kEpiGnBwd = 13,          // out = acc;  gnb_part[tile][n] = (sum dy, sum dy * xhat) over the tile's pixels   (pair kernel only)
 };
 template <int EPI>
 __host__ __device__ constexpr bool epi_is_dual() {
@@ -147,7 +159,7 @@ __device__ __forceinline__ uint4 epi_act_of_bf16(const uint4& zu) {
   return make_uint4(f2_to_bf16x2(z[0]), f2_to_bf16x2(z[1]), f2_to_bf16x2(z[2]), f2_to_bf16x2(z[3]));
 }
 
-enum : int { kEpiCount = 13 };
+enum : int { kEpiCount = 14 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"

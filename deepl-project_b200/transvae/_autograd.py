@@ -249,11 +249,12 @@ class ResBlockFn(Fn):
         B, H, W, C = x.shape
         dplan = T.plan_conv3x3_dgrad(C)
         dw2, dc2b = _wgrad_b(T.plan_conv3x3(C), h2, dout, C, b=c2b)
-        dh2 = ops.mtgemm(dplan, dout, w2d, out_shape=(B, H, W, C))
-        dh1, dg2, db2 = ops.groupnorm_bwd(h1, dh2, s2, g2, b2)
+        # the input-gradient GEMMs leave the reduce pass of the GroupNorm backward that consumes their output
+        dh2 = ops.mtgemm(dplan, dout, w2d, out_shape=(B, H, W, C), gn_bwd=(h1, s2, g2, b2, 32, 1e-5, True))
+        dh1, dg2, db2 = ops.groupnorm_bwd(h1, dh2, s2, g2, b2, part=dh2._gnb_part)
         dw1, dc1b = _wgrad_b(T.plan_conv3x3(C), h0, dh1, C, b=c1b)
-        dh0 = ops.mtgemm(dplan, dh1, w1d, out_shape=(B, H, W, C))
-        dx, dg1, db1 = ops.groupnorm_bwd(x, dh0, s1, g1, b1, add=dout)
+        dh0 = ops.mtgemm(dplan, dh1, w1d, out_shape=(B, H, W, C), gn_bwd=(x, s1, g1, b1, 32, 1e-5, True))
+        dx, dg1, db1 = ops.groupnorm_bwd(x, dh0, s1, g1, b1, add=dout, part=dh0._gnb_part)
         S = GRAD_SINK
         out = (dx, None, S.add(g1, dg1), S.add(b1, db1), S.add(w1, _w_ungrad(dw1, w1)), S.add(c1b, dc1b), S.add(g2, dg2),
                S.add(b2, db2), S.add(w2, _w_ungrad(dw2, w2)), S.add(c2b, dc2b))
@@ -290,12 +291,14 @@ class ResBlockScFn(Fn):
         B, H, W, Cin = x.shape
         Cout = w1.shape[0]
         dw2s, db2s = _wgrad_b(T.plan_resblock_conv2(Cout, Cin, k), h2, dout, Cout, a1=x)
-        dh2 = ops.mtgemm(T.plan_conv3x3_dgrad(Cout), dout, _tr(w2s[:, :9 * Cout], 9), out_shape=(B, H, W, Cout))
+        dh2 = ops.mtgemm(T.plan_conv3x3_dgrad(Cout), dout, _tr(w2s[:, :9 * Cout], 9), out_shape=(B, H, W, Cout),
+                         gn_bwd=(h1, s2, g2, b2, 32, 1e-5, True))
         dx_sc = ops.mtgemm(T.plan_conv_kxk_dgrad(Cout, k), dout, _tr(w2s[:, 9 * Cout:], k * k), out_shape=(B, H, W, Cin))
-        dh1, dg2, db2 = ops.groupnorm_bwd(h1, dh2, s2, g2, b2)
+        dh1, dg2, db2 = ops.groupnorm_bwd(h1, dh2, s2, g2, b2, part=dh2._gnb_part)
         dw1, dc1b = _wgrad_b(T.plan_conv3x3(Cin), h0, dh1, Cout, b=c1b)
-        dh0 = ops.mtgemm(T.plan_conv3x3_dgrad(Cout), dh1, w1d, out_shape=(B, H, W, Cin))
-        dx, dg1, db1 = ops.groupnorm_bwd(x, dh0, s1, g1, b1, add=dx_sc)
+        dh0 = ops.mtgemm(T.plan_conv3x3_dgrad(Cout), dh1, w1d, out_shape=(B, H, W, Cin),
+                         gn_bwd=(x, s1, g1, b1, 32, 1e-5, True))
+        dx, dg1, db1 = ops.groupnorm_bwd(x, dh0, s1, g1, b1, add=dx_sc, part=dh0._gnb_part)
         S = GRAD_SINK
         out = (dx, None, S.add(g1, dg1), S.add(b1, db1), S.add(w1, _w_ungrad(dw1, w1)), S.add(c1b, dc1b), S.add(g2, dg2),
                S.add(b2, db2), dw2s, db2s, None)

@@ -44,6 +44,8 @@ class MtGemmDesc(C.Structure):
         ("out_f32", C.c_void_p), ("out_n", C.c_int32),
         ("act_grad", C.c_int32), ("z", C.c_void_p),
         ("gn_sums", C.c_void_p), ("gn_groups", C.c_int32), ("out_act", C.c_void_p),
+        ("gnb_x", C.c_void_p), ("gnb_sums", C.c_void_p), ("gnb_gamma", C.c_void_p), ("gnb_beta", C.c_void_p),
+        ("gnb_part", C.c_void_p), ("gnb_groups", C.c_int32), ("gnb_eps", C.c_float), ("gnb_silu", C.c_int32),
     ]
 
 
@@ -81,6 +83,9 @@ _PROTOS = {
     "tvae_groupnorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32,
                                      C.c_void_p]),
+    "tvae_groupnorm_bwd_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                           C.c_int32, C.c_void_p]),
     "tvae_token_norm_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "tvae_token_norm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_int32, C.c_int32, C.c_void_p]),

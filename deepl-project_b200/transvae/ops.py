@@ -117,7 +117,8 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
            residual: Optional[Tensor] = None, row_scale: Optional[Tensor] = None, row_shift: Optional[Tensor] = None,
            col_sum: Optional[Tensor] = None, rope: Optional[Tuple[Tensor, int, int, int, float]] = None,
            out_f32: Optional[Tensor] = None, out_f32_shape: Optional[Sequence[int]] = None, out_n: int = 0,
-           act_grad_z: Optional[Tensor] = None, gn_groups: int = 0, dual: bool = False):
+           act_grad_z: Optional[Tensor] = None, gn_groups: int = 0, dual: bool = False,
+           gn_bwd: Optional[Tuple[Tensor, Tensor, Tensor, Tensor, int, float, bool]] = None):
     """Launch ``tvae_mtgemm``.  a0 / a1 / out / residual are NHWC bf16 4-D tensors (flat matrices as
     [1, 1, M, K]); ``w`` is the packed bf16 [N, K_total] weight; ``bias`` fp32 [phases, N] (or [N]).
 
@@ -129,7 +130,11 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
     returns ``acc * act'(z)`` -- or ``(acc + residual) * act'(z)`` when ``residual`` is given too (GELU, plain views).
 
     ``dual=True`` (training forward, ``act`` set, plain bias epilogue): returns ``(z, act(z))`` -- the pre-activation the
-    backward pass needs and the activation the next layer reads, stored by one launch."""
+    backward pass needs and the activation the next layer reads, stored by one launch.
+
+    ``gn_bwd=(x, sums, gamma, beta, groups, eps, silu)`` (input-gradient GEMM whose output dh feeds the backward of
+    ``act(GroupNorm(x))``; plain epilogue): the launch also leaves the reduce pass of that backward -- per (image, channel)
+    (sum dy, sum dy * xhat), fp32 [B, C, 2] -- as ``out._gnb_part`` for ``groupnorm_bwd(..., part=...)``."""
     _need_cuda(a0, w, a1, out, bias, residual, row_scale, row_shift, col_sum, out_f32)
     assert w.dtype == BF16 and w.is_contiguous() and w.shape[1] == plan.k_total, (w.shape, plan.k_total)
     d = MtGemmDesc()
@@ -186,6 +191,16 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
         assert out_f32 is None and act != ACT_NONE and residual is None and act_grad_z is None and not gn_groups
         out_act = torch.empty_like(out)
     d.out_act = _ptr(out_act)
+    gnb_part = gnb_keep = None
+    if gn_bwd is not None:
+        gx, gs, gg, gb, ggroups, geps, gsilu = gn_bwd
+        _need_cuda(gx, gs, gg, gb)
+        assert out_f32 is None and gx.dtype == BF16 and gx.is_contiguous() and gx.shape == out.shape and out.shape[-1] == n_total
+        assert gs.dtype == torch.float64 and gs.is_contiguous() and tuple(gs.shape) == (out.shape[0], ggroups, 2)
+        gnb_keep = (gg.float().contiguous(), gb.float().contiguous())
+        gnb_part = torch.empty(out.shape[0], n_total, 2, dtype=torch.float32, device=a0.device)
+        d.gnb_x, d.gnb_sums, d.gnb_gamma, d.gnb_beta = gx.data_ptr(), gs.data_ptr(), gnb_keep[0].data_ptr(), gnb_keep[1].data_ptr()
+        d.gnb_part, d.gnb_groups, d.gnb_eps, d.gnb_silu = gnb_part.data_ptr(), ggroups, geps, 1 if gsilu else 0
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -200,6 +215,8 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
     _count()
     if gn_sums is not None:
         out._gn_sums = gn_sums
+    if gnb_part is not None:
+        out._gnb_part = gnb_part
     if dual:
         return out, out_act
     return out if out_f32 is None else out_f32
@@ -458,19 +475,30 @@ def act_fwd(z: Tensor, act: int) -> Tensor:
 
 
 def groupnorm_bwd(x: Tensor, dh: Tensor, sums: Tensor, gamma: Tensor, beta: Tensor, add: Optional[Tensor] = None,
-                  groups: int = 32, eps: float = 1e-5, silu: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
-    """Backward of h = act(GroupNorm(x)): returns (dx [+ add], dgamma, dbeta)."""
-    _need_cuda(x, dh, sums, gamma, beta, add)
+                  groups: int = 32, eps: float = 1e-5, silu: bool = True,
+                  part: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+    """Backward of h = act(GroupNorm(x)): returns (dx [+ add], dgamma, dbeta).  ``part``: the reduce pass's result when the
+    GEMM that produced ``dh`` already left it (``mtgemm(..., gn_bwd=...)``) -- only the apply pass runs then."""
+    _need_cuda(x, dh, sums, gamma, beta, add, part)
     B, H, W, Cc = x.shape
     assert sums.dtype == torch.float64 and sums.is_contiguous() and tuple(sums.shape) == (B, groups, 2), (sums.dtype, sums.shape)
     g, b = gamma.float().contiguous(), beta.float().contiguous()
-    part = torch.empty(B, Cc, 2, dtype=torch.float32, device=x.device)
     dx = torch.empty_like(x)
-    with _hbm("gn_bwd (reduce + apply)", x.numel() * (12 if add is not None else 10)):
-        _lib.check(_lib.load().tvae_groupnorm_bwd(x.data_ptr(), dh.data_ptr(), _ptr(add), sums.data_ptr(), g.data_ptr(),
-                                                  b.data_ptr(), part.data_ptr(), dx.data_ptr(), B, H * W, Cc, groups, eps,
-                                                  1 if silu else 0, _stream()), "tvae_groupnorm_bwd")
-    _count(3)
+    if part is not None:
+        assert part.dtype == torch.float32 and part.is_contiguous() and tuple(part.shape) == (B, Cc, 2)
+        with _hbm("gn_bwd (apply)", x.numel() * (8 if add is not None else 6)):
+            _lib.check(_lib.load().tvae_groupnorm_bwd_apply(x.data_ptr(), dh.data_ptr(), _ptr(add), sums.data_ptr(),
+                                                            g.data_ptr(), b.data_ptr(), part.data_ptr(), dx.data_ptr(), B,
+                                                            H * W, Cc, groups, eps, 1 if silu else 0, _stream()),
+                       "tvae_groupnorm_bwd_apply")
+        _count(1)
+    else:
+        part = torch.empty(B, Cc, 2, dtype=torch.float32, device=x.device)
+        with _hbm("gn_bwd (reduce + apply)", x.numel() * (12 if add is not None else 10)):
+            _lib.check(_lib.load().tvae_groupnorm_bwd(x.data_ptr(), dh.data_ptr(), _ptr(add), sums.data_ptr(), g.data_ptr(),
+                                                      b.data_ptr(), part.data_ptr(), dx.data_ptr(), B, H * W, Cc, groups, eps,
+                                                      1 if silu else 0, _stream()), "tvae_groupnorm_bwd")
+        _count(3)
     red = part.sum(0)          # [C, 2]: tiny (B x C) reduction of the per-image partials
     return dx, red[:, 1], red[:, 0]          # strided views (consumers: GradSink / autograd accept them)
 

@@ -28,10 +28,15 @@ class GradBuckets:
     ``grad_comm``: dtype of the all-reduce payload.  ``torch.float32`` (default) is DistributedDataParallel's behaviour
     (train.py:672-674).  ``torch.bfloat16`` halves the NVLink payload: a bucket is cast into a bf16 mirror
     (``tvae_cast_f32_bf16``) the moment it is complete, the mirror is all-reduced and the optimizer reads it -- the
-    rounding of every gradient to bf16 (2^-9 relative) is a stated deviation from the reference."""
+    rounding of every gradient to bf16 (2^-9 relative) is a stated deviation from the reference.
+
+    ``overlap``: True (default; ``TVAE_DDP_OVERLAP=0`` turns it off) launches a bucket's all-reduce from the hook of its
+    last gradient, so it runs under the rest of backward; False sends ONE all-reduce over the whole flat buffer at the end
+    of backward (``wait()``) -- nothing competes with the persistent GEMM grids for SMs, the transfer is exposed."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20,
-                 process_group: Optional[dist.ProcessGroup] = None, grad_comm: torch.dtype = torch.float32):
+                 process_group: Optional[dist.ProcessGroup] = None, grad_comm: torch.dtype = torch.float32,
+                 overlap: Optional[bool] = None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -87,6 +92,10 @@ class GradBuckets:
         self._reduced = [False] * len(self.buckets)
         self._handles = []
         self.sync_grads = True          # False during gradient-accumulation micro-steps
+        if overlap is None:
+            import os
+            overlap = os.environ.get("TVAE_DDP_OVERLAP", "1") != "0"
+        self.overlap = bool(overlap)
         for p in self.params:
             p.register_post_accumulate_grad_hook(self._hook)
 
@@ -119,12 +128,24 @@ class GradBuckets:
         self._pending[b] += 1
         if self._pending[b] == self._bucket_count[b]:
             self._pending[b] = 0
-            if self.sync_grads:
+            if self.sync_grads and self.overlap:
                 self._reduce_bucket(b)
+
+    def _reduce_all(self) -> None:
+        """One all-reduce over the whole flat buffer (``overlap=False``)."""
+        self._reduced = [True] * len(self.buckets)
+        if self.world <= 1:
+            return
+        if self.comm_g is not None:
+            from . import ops
+            ops.cast_f32_bf16(self.flat_g, self.comm_g)
+        self._handles.append(dist.all_reduce(self.grads(), op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
 
     def wait(self) -> None:
         """End of backward.  Buckets that never completed -- a parameter without a gradient this step (unused branch,
         frozen after construction) -- are reduced now, so ranks cannot diverge silently."""
+        if self.sync_grads and not self.overlap and not any(self._reduced):
+            self._reduce_all()
         if self.sync_grads:
             for b in range(len(self.buckets)):
                 if not self._reduced[b]:

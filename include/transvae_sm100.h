@@ -112,6 +112,21 @@ typedef struct {
    * PRE-activation acc + bias (what the backward pass differentiates through) and out_act -- bf16, same geometry as
    * `out` -- the activation of the stored bf16 values, both from one launch (conv.py:86,56,58; upsample.py:35,96). */
   void* out_act;
+  /* Optional fused reduce pass of a GroupNorm backward (blocks.py:60-66): the launch is the input-gradient GEMM whose
+   * output dh feeds the backward of act(GroupNorm(gnb_x)).  gnb_x: bf16, same geometry as `out`; gnb_sums: the forward
+   * statistics [B][gnb_groups][2] fp64; gnb_part [B][n_total][2] fp32 receives per (image, channel) (sum dy, sum dy*xhat),
+   * dy = dh * act'(gamma * xhat + beta) -- exactly what tvae_groupnorm_bwd_apply consumes.  On the CTA-pair kernel with
+   * one image per 128-pixel tile the sums come out of the GEMM epilogue (x read behind an L2 tensor prefetch, per-tile partial rows
+   * added in a fixed order); otherwise the library runs the stand-alone reduce pass behind the GEMM.  Plain epilogue only
+   * (no bias / activation / residual). */
+  const void* gnb_x;
+  const double* gnb_sums;
+  const float* gnb_gamma;
+  const float* gnb_beta;
+  float* gnb_part;
+  int32_t gnb_groups;
+  float gnb_eps;
+  int32_t gnb_silu;
 } tvae_mtgemm_desc;
 
 int tvae_mtgemm(const tvae_mtgemm_desc* desc /* HOST pointer */, void* stream);
@@ -191,6 +206,10 @@ int tvae_act_fwd(const void* z, void* y, int64_t n, int32_t act, void* stream);
 int tvae_groupnorm_bwd(const void* x, const void* dh, const void* add, const double* sums, const float* gamma,
                        const float* beta, float* part, void* dx, int32_t B, int32_t HW, int32_t C, int32_t G, float eps,
                        int32_t apply_silu, void* stream);
+/* The apply pass alone, `part` given (produced by tvae_mtgemm with the gnb_* fields, or by an earlier call). */
+int tvae_groupnorm_bwd_apply(const void* x, const void* dh, const void* add, const double* sums, const float* gamma,
+                             const float* beta, const float* part, void* dx, int32_t B, int32_t HW, int32_t C, int32_t G,
+                             float eps, int32_t apply_silu, void* stream);
 /* Materialised token norms of the training path: mode 0 RMSNorm (blocks.py:168-201), mode 1 RMSNorm followed by the
  * affine-free LayerNorm shared by norm_q/k/v (attention.py:71-73).  x, y, dy, add, dx: bf16 [M, C]; w, dw: fp32 [C]. */
 int tvae_token_norm_fwd(const void* x, const float* w, void* y, int64_t M, int32_t C, int32_t mode, void* stream);

@@ -42,13 +42,34 @@ class FakeOps:
         y = nhwc(F.silu(y) if silu else y)
         return (y, ref) if return_sums else y
 
-    def mtgemm(self, plan, a0, w, *, a1=None, out_shape=None, bias=None, residual=None, gn_groups=0, **kw):
+    @staticmethod
+    def gnb_part(x, dh, gamma, beta, groups, eps, silu):
+        """Reduce pass of the GroupNorm backward: per (image, channel) (sum dy, sum dy * xhat), dy = dh * act'(gamma*xhat+beta)."""
+        B, H, W, C = x.shape
+        v = x.double().reshape(B, H * W, groups, C // groups)
+        mean = v.mean(dim=(1, 3), keepdim=True)
+        var = (v * v).mean(dim=(1, 3), keepdim=True) - mean * mean
+        xhat = ((v - mean) / torch.sqrt(var + eps)).reshape(B, H * W, C)
+        dy = dh.double().reshape(B, H * W, C)
+        if silu:
+            u = xhat * gamma.double() + beta.double()
+            sg = torch.sigmoid(u)
+            dy = dy * sg * (1 + u * (1 - sg))
+        return torch.stack([dy.sum(1), (dy * xhat).sum(1)], dim=-1).float()
+
+    def mtgemm(self, plan, a0, w, *, a1=None, out_shape=None, bias=None, residual=None, gn_groups=0, gn_bwd=None, **kw):
         assert not kw, kw
         out = emulate(plan, a0.float(), a1, w.float(), tuple(out_shape), bias=None if bias is None else bias.reshape(plan.num_phases, -1))
         if residual is not None:
             out = out + residual.float()
         if gn_groups:
             out._gn_sums = gn_sums(out, gn_groups)
+        if gn_bwd is not None:                  # input-gradient GEMM that also leaves the GroupNorm-backward reduce pass
+            gx, gs, gg, gb, ggroups, geps, gsilu = gn_bwd
+            assert bias is None and residual is None and not gn_groups and gx.shape == out.shape
+            assert torch.allclose(gs, gn_sums(gx, ggroups), rtol=1e-9, atol=1e-9)     # statistics of the right tensor
+            out._gnb_part = self.gnb_part(gx, out, gg, gb, ggroups, geps, gsilu)
+            self.parts_made = getattr(self, "parts_made", 0) + 1
         return out
 
     def mtgemm_wgrad(self, plan, a0, dz, n_total, a1=None, bias=False, dw_out=None, db_out=None):
@@ -58,8 +79,11 @@ class FakeOps:
             return dw
         return dw, dz.float().reshape(-1, n_total).sum(0, keepdim=True)
 
-    def groupnorm_bwd(self, x, dh, sums, gamma, beta, add=None, groups=32, eps=1e-5, silu=True):
+    def groupnorm_bwd(self, x, dh, sums, gamma, beta, add=None, groups=32, eps=1e-5, silu=True, part=None):
         assert torch.allclose(sums, gn_sums(x, groups), rtol=1e-9, atol=1e-9)
+        if part is not None:                    # must be the reduce pass of exactly this (x, dh, gamma, beta)
+            self.parts_used = getattr(self, "parts_used", 0) + 1
+            assert torch.allclose(part, self.gnb_part(x, dh, gamma, beta, groups, eps, silu), rtol=1e-5, atol=1e-6)
         with torch.enable_grad():               # Function.backward runs with grad mode off
             xr = x.detach().float().clone().requires_grad_(True)
             g = gamma.detach().float().clone().requires_grad_(True)
@@ -116,6 +140,8 @@ def test_resblock_chain_hands_statistics_on_and_matches_autograd(fake):
     out = AG.GroupNormSilu.apply(y2, leaves["a.g1"] * 1.0, leaves["a.b1"] * 1.0, True, s2)   # decoder.norm_out hand-off
     dout = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
     out.backward(dout)
+    # both input-gradient GEMMs of both blocks left the reduce pass of the GroupNorm backward behind them
+    assert fake.parts_made == 4 and fake.parts_used == 4
 
     # reference: torch.autograd on the NCHW formula
     ref_leaves = {k: v.detach().clone().requires_grad_(True) for k, v in leaves.items()}

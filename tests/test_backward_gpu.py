@@ -185,6 +185,35 @@ def test_groupnorm_backward(B, C, H):
     assert rel(dg, gg) < 5e-3 and rel(db, gb) < 5e-3
 
 
+@pytest.mark.parametrize("B,C,H,W", [(3, 192, 4, 128), (2, 192, 3, 256), (2, 64, 16, 16), (5, 256, 2, 128), (2, 128, 3, 200)])
+def test_groupnorm_backward_reduce_from_dgrad_epilogue(B, C, H, W):
+    """The input-gradient GEMM of a ResBlock convolution leaves the reduce pass of the GroupNorm backward that consumes
+    its output (mtgemm gn_bwd=...; fused into the CTA-pair kernel's epilogue when a 128-pixel tile stays inside one image,
+    the stand-alone reduce pass behind the GEMM otherwise): dh bit-identical to the plain launch, (dx, dgamma, dbeta)
+    equal to the two-pass route and to torch (blocks.py:60-66)."""
+    from transvae import _taps as T
+    x, dout = bf(rnd(B, C, H, W, scale=3.0) + 0.7), bf(rnd(B, C, H, W, seed=3))
+    g, b = rnd(C, seed=1) * 0.2 + 1, rnd(C, seed=2) * 0.1
+    w = bf(rnd(C, C, 3, 3, seed=5) * 0.05)
+    add = bf(rnd(B, C, H, W, seed=4))
+    xn, dn = nhwc(x), nhwc(dout)
+    sums = ops.groupnorm_stats(xn)
+    wd = w.float().permute(1, 2, 3, 0).reshape(C, 9 * C).to(torch.bfloat16).contiguous()     # [Cin, tap, Cout]
+    plan = T.plan_conv3x3_dgrad(C)
+    dh_plain = ops.mtgemm(plan, dn, wd, out_shape=(B, H, W, C))
+    dh = ops.mtgemm(plan, dn, wd, out_shape=(B, H, W, C), gn_bwd=(xn, sums, g, b, 32, 1e-5, True))
+    assert torch.equal(dh, dh_plain)
+    dx0, dg0, db0 = ops.groupnorm_bwd(xn, dh_plain, sums, g, b, add=nhwc(add))
+    dx1, dg1, db1 = ops.groupnorm_bwd(xn, dh, sums, g, b, add=nhwc(add), part=dh._gnb_part)
+    assert rel(dg1, dg0) < 1e-5 and rel(db1, db0) < 1e-5 and rel(dx1, dx0) < 2e-3
+    # twice the same launch: bit-identical sums (fixed-order reduction)
+    dh2 = ops.mtgemm(plan, dn, wd, out_shape=(B, H, W, C), gn_bwd=(xn, sums, g, b, 32, 1e-5, True))
+    assert torch.equal(dh2._gnb_part, dh._gnb_part)
+    gx, gg, gb = grads(lambda x, g, b: F.silu(F.group_norm(x, 32, g, b, 1e-5)), [x, g, b], nchw(dh))
+    assert rel(nchw(dx1), gx + add.float()) < 1e-2
+    assert rel(dg1, gg) < 5e-3 and rel(db1, gb) < 5e-3
+
+
 @pytest.mark.parametrize("M,C", [(500, 384), (64, 1536), (1000, 64)])
 def test_token_norms(M, C):
     x, dy = bf(rnd(M, C, scale=4.0) + 0.3), bf(rnd(M, C, seed=2))

@@ -63,6 +63,17 @@ def _worker(rank, world, port, out):
         gb2.wait()
         g = m2[0].bias.grad.clone()
         assert torch.allclose(g, torch.full((4,), 2.0)), g        # 1 (rank 0) + 1 (rank 1): reduced in wait()
+        # overlap=False: the hooks launch nothing, wait() sends one all-reduce over the whole flat buffer -- same sums
+        m3 = _mlp()
+        gb3 = GradBuckets(m3.parameters(), bucket_bytes=1024, overlap=False)
+        (m3(xs).pow(2).sum()).backward()
+        assert not gb3._handles
+        gb3.wait()
+        m4 = _mlp()
+        gb4 = GradBuckets(m4.parameters(), bucket_bytes=1024, overlap=True)
+        (m4(xs).pow(2).sum()).backward()
+        gb4.wait()
+        assert torch.allclose(gb3.flat_g, gb4.flat_g, atol=1e-6) and float(gb3.flat_g.abs().sum()) > 0
     finally:
         dist.destroy_process_group()
 

@@ -46,6 +46,40 @@ elif which in ("lin384_gelu", "lin384_res"):
     res = rnd(1, 1, M, 1536).to(torch.bfloat16)
     fn = (lambda: ops.mtgemm(T.plan_linear(384), x, w, out_shape=(1, 1, M, 1536), bias=b, act=ops.ACT_GELU, row_scale=rs)) \
         if which == "lin384_gelu" else (lambda: ops.mtgemm(T.plan_linear(384), x, w, out_shape=(1, 1, M, 1536), bias=b, residual=res))
+elif which in ("dgrad192", "dgrad192gnb"):
+    # input-gradient GEMM of a ResBlock convolution, plain / with the fused GroupNorm-backward reduce pass
+    x = rnd(B, 256, 256, 192).to(torch.bfloat16)
+    dz = rnd(B, 256, 256, 192).to(torch.bfloat16)
+    wd = (rnd(192, 9 * 192) * 0.02).to(torch.bfloat16)
+    ga, be = rnd(192), rnd(192)
+    s = ops.groupnorm_stats(x)
+    fn = (lambda: ops.mtgemm(T.plan_conv3x3_dgrad(192), dz, wd, out_shape=(B, 256, 256, 192))) if which == "dgrad192" \
+        else (lambda: ops.mtgemm(T.plan_conv3x3_dgrad(192), dz, wd, out_shape=(B, 256, 256, 192), gn_bwd=(x, s, ga, be, 32, 1e-5, True)))
+elif which in ("wgrad_lin384", "wgrad_lin384t", "wgrad_lin768"):
+    # weight gradients of the stage-1 / stage-2 token GEMMs (long pixel axis, small weight matrix)
+    M = B * (4096 if which != "wgrad_lin768" else 1024)
+    n, k = {"wgrad_lin384": (1536, 384), "wgrad_lin384t": (384, 1536), "wgrad_lin768": (3072, 768)}[which]
+    a = rnd(1, 1, M, k).to(torch.bfloat16)
+    dz = rnd(1, 1, M, n).to(torch.bfloat16)
+    fn = lambda: ops.mtgemm_wgrad(T.plan_linear(k), a, dz, n, bias=True)
+elif which in ("lin384_dgelu", "lin384_dual", "qkv384"):
+    M = B * 4096
+    if which == "lin384_dgelu":      # dgrad of the FFN output projection: (acc + residual) * gelu'(z)
+        dy = rnd(1, 1, M, 384).to(torch.bfloat16)
+        w = (rnd(1536, 384) * 0.05).to(torch.bfloat16)
+        z, res = rnd(1, 1, M, 1536).to(torch.bfloat16), rnd(1, 1, M, 1536).to(torch.bfloat16)
+        fn = lambda: ops.mtgemm(T.plan_linear(384), dy, w, out_shape=(1, 1, M, 1536), act=ops.ACT_GELU, act_grad_z=z, residual=res)
+    elif which == "lin384_dual":     # training forward of the FFN input projection: z and gelu(z)
+        x = rnd(1, 1, M, 384).to(torch.bfloat16)
+        w = (rnd(1536, 384) * 0.05).to(torch.bfloat16)
+        b = rnd(1536)
+        fn = lambda: ops.mtgemm(T.plan_linear(384), x, w, out_shape=(1, 1, M, 1536), bias=b, act=ops.ACT_GELU, dual=True)
+    else:                            # QKV projection with the LayerNorm-affine + RoPE epilogue
+        x = rnd(1, 1, M, 384).to(torch.bfloat16)
+        w = (rnd(1152, 384) * 0.05).to(torch.bfloat16)
+        b = rnd(1152)
+        tab = T.rope_table(64, 64, 1.0 / (10000 ** (torch.arange(0, 32, 2, device=dev).float() / 32)))
+        fn = lambda: ops.mtgemm(T.plan_linear(384), x, w, out_shape=(1, 1, M, 1152), bias=b, rope=(tab, 384, 64, 64, 0.125))
 else:
     raise SystemExit(f"unknown kernel {which}")
 for _ in range(5):
