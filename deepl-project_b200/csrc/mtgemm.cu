@@ -410,6 +410,8 @@ int mtgemm_run(const tvae_mtgemm_desc* d, cudaStream_t stream) {
   P.col_sum = d->col_sum;
   TVAE_REQUIRE(d->row_shift == nullptr || d->col_sum != nullptr, "mtgemm: row_shift needs col_sum");
   P.has_residual = d->res.ptr != nullptr;
+  static const int pipe_res_env = !(getenv("TVAE_EPI_PIPE_RES") && atoi(getenv("TVAE_EPI_PIPE_RES")) == 0);   // A/B switch
+  P.pipe_res = pipe_res_env;
   P.rope_tab = reinterpret_cast<const float2*>(d->rope_tab);
   P.rope_C = d->rope_C; P.rope_H = d->rope_H; P.rope_W = d->rope_W;
   P.q_scale = d->q_scale;

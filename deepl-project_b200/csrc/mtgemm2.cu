@@ -43,11 +43,13 @@ struct Mt2Cfg {
   static constexpr int kStagesRaw = (227 * 1024 - 2048 - kStagingBytes) / (kABytes + kBHalfBytes);
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * (kABytes + kBHalfBytes) + kStagingBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * (kABytes + kBHalfBytes) + kStagingBytes + 1024 + 512;
   // halo mode: a stage = one halo A tile + the B halves of the three dx taps, carved out of the same ring
   static constexpr int kHaloStageBytes = kHaloABytes + 3 * kBHalfBytes;
   static constexpr int kHaloStages = kStages * (kABytes + kBHalfBytes) / kHaloStageBytes;
 };
+
+constexpr int kMaxChunks = 4;   // 64-column chunks of the widest tile (BLOCK_N = 256)
 
 template <int BLOCK_N, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -73,17 +75,27 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* tmem_empty = tmem_full + 2;    // [2]      (leader's are used, 16 arrivals)
   uint64_t* res_full = tmem_empty + 2;     // [1]
   uint64_t* out_free = res_full + 1;       // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_free + 1);
+  uint64_t* res_full_c = out_free + 1;     // [kMaxChunks] per 64-column chunk (chunk-pipelined residual epilogues)
+  uint64_t* out_free_c = res_full_c + kMaxChunks;   // [kMaxChunks]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_free_c + kMaxChunks);
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const bool has_res = kHasRes && P.has_residual;
+  constexpr int kChunks = BLOCK_N / 64;
+  constexpr bool kCanPipe = EPI != kEpiDirect && kChunks >= 2;
   // fused GroupNorm statistics of the output (bias / bias+residual epilogues only): per-CTA staging of (sum, sumsq)
   constexpr bool kGn = (EPI == kEpiBias || EPI == kEpiBiasRes);
   __shared__ double s_gn[kGn ? 128 : 1];     // fp64 like the global sums: several column groups may add into one group
   const bool gn = kGn && P.gn_sums != nullptr;
+  // Chunk-pipelined residual epilogue: the staged residual (and z) tile arrives, is combined in place and leaves again
+  // per 64-column chunk, each chunk with its own pair of barriers, so the next tile's residual is in flight while this
+  // tile's later chunks are drained -- with ONE residual barrier per tile the load (128 KB at an SM's 44 GB/s share of
+  // HBM: 2.9 us), the TMEM drain and the store followed each other (K = 384 GELU-gradient GEMM: 8.5 us per tile against
+  // 4.4 us of HBM time).  Not with the statistics passes, which read the whole staged tile after the drain.
+  const bool pipe_res = kCanPipe && has_res && !gn && !kStageX && P.pipe_res != 0;
   if constexpr (kGn) {
     if (threadIdx.x < 128) s_gn[threadIdx.x] = 0.0;
   }
@@ -105,6 +117,10 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     mbar_init(res_full, 1);
     mbar_init(out_free, 1);
+    for (int j = 0; j < kMaxChunks; ++j) {
+      mbar_init(&res_full_c[j], 1);
+      mbar_init(&out_free_c[j], 1);
+    }
     fence_mbar_init();
   }
   cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / cross-CTA TMA completion
@@ -278,6 +294,23 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int it = 0;
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++it) {
         TVAE_DECODE_PAIR(pt)
+        if constexpr (kCanPipe && kHasRes) {
+          if (pipe_res) {
+            // chunk by chunk: chunk j of this tile is fetched as soon as the store of the previous tile's chunk j has been
+            // read (out_free_c[j]), i.e. while the epilogue warps are still working on that tile's later chunks
+#pragma unroll
+            for (int j = 0; j < kChunks; ++j) {
+              mbar_wait(&out_free_c[j], (it & 1) ^ 1);
+              mbar_arrive_expect_tx(&res_full_c[j], kABytes * (Cfg::kStageZ ? 2 : 1));
+              tma_load_5d(sOut + j * kABytes, &tmRes, &res_full_c[j], P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0,
+                          P.out_p[ph], h0, b0);
+              if constexpr (Cfg::kStageZ)
+                tma_load_5d(sZ + j * kABytes, &tmX2, &res_full_c[j], P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0,
+                            P.out_p[ph], h0, b0);
+            }
+            continue;
+          }
+        }
         mbar_wait(out_free, (it & 1) ^ 1);
         mbar_arrive_expect_tx(res_full, kStageX ? Cfg::kOutBytes : Cfg::kStagingBytes);
         if constexpr (kStageX) {             // the GroupNorm input x of this tile (map tmX2) -> second staging tile
@@ -307,9 +340,7 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // pass over it) send each 64-column chunk off as soon as the eight warps have finished it, and never wait for a
     // store at the end of a tile -- with one store + wait per tile the small-K GEMMs (K = 384: 3000 clocks of MMA per
     // tile) were bound by the epilogue's TMEM drain + store latency.  Needs at least two chunks.
-    constexpr int kChunks = BLOCK_N / 64;
-    constexpr bool kCanPipe = EPI != kEpiDirect && kChunks >= 2;
-    const bool pipe = kCanPipe && !has_res && !gn && !kStageX;
+    const bool pipe = kCanPipe && (!has_res || pipe_res) && !gn && !kStageX;
     int it = 0;
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++it) {
       TVAE_DECODE_PAIR(pt)
@@ -342,7 +373,7 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      if (has_res || kStageX) mbar_wait(res_full, it & 1);
+      if ((has_res && !pipe_res) || kStageX) mbar_wait(res_full, it & 1);
 
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
       const int n_base = n_t * BLOCK_N;
@@ -404,6 +435,9 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tmem_ld8(t_row + half * 16 + 8, v0b);
 #pragma unroll 1
         for (int c16 = half; c16 < kGroups; c16 += 4) {      // every warp owns an even number of groups
+          if constexpr (kCanPipe && kHasRes) {
+            if (pipe_res) mbar_wait(&res_full_c[c16 >> 2], it & 1);     // residual (and z) chunk of this tile has landed
+          }
           tmem_ld_wait_dep(v0a, v0b);
           tmem_ld8(t_row + (c16 + 2) * 16, v1a);
           tmem_ld8(t_row + (c16 + 2) * 16 + 8, v1b);
@@ -420,7 +454,7 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               // the next chunk is drained.  Before the barrier the leader makes sure the store that last read the NEXT
               // chunk to be written (same chunk, previous tile) is done: kChunks - 2 younger groups may still be pending.
               fence_proxy_async_smem();
-              if (store_leader) tma_store_wait_read<kChunks - 2>();
+              if (store_leader && !pipe_res) tma_store_wait_read<kChunks - 2>();
               asm volatile("bar.sync 1, 256;" ::: "memory");
               if (store_leader) {
                 const int j = c16 >> 2;
@@ -428,6 +462,14 @@ mtgemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if constexpr (Cfg::kDual)
                   tma_store_5d(&tmX2, sZ + j * kABytes, P.out_c_off[ph] + n_t * BLOCK_N + j * 64, w0, P.out_p[ph], h0, b0);
                 tma_store_commit();
+                if constexpr (kHasRes) {
+                  // the store before this one (previous chunk; for chunk 0 the previous tile's last chunk) has been read:
+                  // the loader may refill that chunk with the next tile's residual
+                  if (pipe_res && (it > 0 || j > 0)) {
+                    tma_store_wait_read<1>();
+                    mbar_arrive(&out_free_c[(j + kChunks - 1) % kChunks]);
+                  }
+                }
               }
             }
           }

@@ -44,6 +44,8 @@ struct MtParams {
   // halo mode (3x3 stride-1 convolution, 128-pixel-wide tiles): ONE (128 + 2)-pixel A tile per (kernel row, K block)
   // serves the three dx taps through row-offset UMMA descriptors.  0 = off, 1 = on
   int halo;
+  // chunk-pipelined residual epilogue of the CTA-pair kernel (mtgemm2.cu); 0 = one residual barrier per tile
+  int pipe_res;
   // kEpiGnBwd: the launch is the input-gradient GEMM whose output dh feeds the backward of act(GroupNorm(x)); its epilogue
   // also produces, per 128-pixel tile and channel, (sum dy, sum dy * xhat) with dy = dh * act'(gamma * xhat + beta):
   // gnb_part [pixel tiles][n_total][2] fp32, plain stores (every element written once)
