@@ -50,11 +50,11 @@ int adamw_step_run(float* p, const void* g, int g_bf16, float* m, float* v, long
 int cast_f32_bf16_run(const float* in, void* out, long long n, cudaStream_t stream);
 int mta_add_run(float* const* dst, const float* const* src, const int* n, const int* sstride, int count, cudaStream_t stream);
 int weight_pack_run(const float* w, void* fwd, void* dgr, int A, int B, int T, cudaStream_t stream);
-int wgrad_unpack_run(const float* g, float* out, int A, int B, int T, cudaStream_t stream);
+int wgrad_unpack_run(const float* g, float* out, int A, int B, int T, int accumulate, cudaStream_t stream);
 int fold_qkv_run(const float* const* w, const float* const* g, const float* const* b, float* wg, float* bg, int C,
                  cudaStream_t stream);
 int fold_qkv_bwd_run(const float* const* w, const float* const* g, const float* const* b, const float* dwg, const float* dbg,
-                     float* const* dw, float* const* dg, float* const* db, int C, cudaStream_t stream);
+                     float* const* dw, float* const* dg, float* const* db, int C, int accumulate, cudaStream_t stream);
 int upconv1_pack_run(const float* w, float* out, int O, int I, int backward, cudaStream_t stream);
 int dwconv3x3_run(const void* u, const float* w9c, const float* bias, void* y, int B, int H, int W, int C, int flip,
                   int add_input, cudaStream_t stream);
@@ -195,16 +195,17 @@ int tvae_latent_bwd(const float* mu, const float* logvar, const float* eps, cons
 int tvae_weight_pack(const float* w, void* fwd_bf16, void* dgrad_bf16, int32_t A, int32_t B, int32_t T, void* stream) {
   GUARD(); return weight_pack_run(w, fwd_bf16, dgrad_bf16, A, B, T, S_(stream));
 }
-int tvae_wgrad_unpack(const float* g_packed, float* g_ref, int32_t A, int32_t B, int32_t T, void* stream) {
-  GUARD(); return wgrad_unpack_run(g_packed, g_ref, A, B, T, S_(stream));
+int tvae_wgrad_unpack(const float* g_packed, float* g_ref, int32_t A, int32_t B, int32_t T, int32_t accumulate, void* stream) {
+  GUARD(); return wgrad_unpack_run(g_packed, g_ref, A, B, T, accumulate, S_(stream));
 }
 int tvae_fold_qkv(const float* const* w3, const float* const* g3, const float* const* b3, float* wg, float* bg, int32_t C,
                   void* stream) {
   GUARD(); return fold_qkv_run(w3, g3, b3, wg, bg, C, S_(stream));
 }
 int tvae_fold_qkv_bwd(const float* const* w3, const float* const* g3, const float* const* b3, const float* dwg,
-                      const float* dbg, float* const* dw3, float* const* dg3, float* const* db3, int32_t C, void* stream) {
-  GUARD(); return fold_qkv_bwd_run(w3, g3, b3, dwg, dbg, dw3, dg3, db3, C, S_(stream));
+                      const float* dbg, float* const* dw3, float* const* dg3, float* const* db3, int32_t C, int32_t accumulate,
+                      void* stream) {
+  GUARD(); return fold_qkv_bwd_run(w3, g3, b3, dwg, dbg, dw3, dg3, db3, C, accumulate, S_(stream));
 }
 int tvae_upconv1_pack(const float* src, float* dst, int32_t O, int32_t I, int32_t backward, void* stream) {
   GUARD(); return upconv1_pack_run(src, dst, O, I, backward, S_(stream));

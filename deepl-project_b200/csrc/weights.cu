@@ -131,7 +131,8 @@ int weight_pack_run(const float* w, void* fwd, void* dgr, int A, int B, int T, c
 // g[a][t][b] -> out[a][b][t]: one block = one `a` and 128 consecutive b; reads T runs of 512 bytes, writes one run of
 // 128 * T floats.
 template <int T>
-__global__ void __launch_bounds__(128) wgrad_unpack_kernel(const float* __restrict__ g, float* __restrict__ out, int A, int B) {
+__global__ void __launch_bounds__(128) wgrad_unpack_kernel(const float* __restrict__ g, float* __restrict__ out, int A, int B,
+                                                           int accumulate) {
   __shared__ float tile[T][128 + 1];
   const int a = blockIdx.y, b0 = blockIdx.x * 128;
   const int nb = min(128, B - b0);
@@ -143,15 +144,15 @@ __global__ void __launch_bounds__(128) wgrad_unpack_kernel(const float* __restri
   float* dst = out + ((size_t)a * B + b0) * T;
   for (int i = threadIdx.x; i < nb * T; i += 128) {
     const int b = i / T, t = i - b * T;
-    dst[i] = tile[t][b];
+    dst[i] = accumulate ? dst[i] + tile[t][b] : tile[t][b];
   }
 }
 
-int wgrad_unpack_run(const float* g, float* out, int A, int B, int T, cudaStream_t stream) {
+int wgrad_unpack_run(const float* g, float* out, int A, int B, int T, int accumulate, cudaStream_t stream) {
   TVAE_REQUIRE(g != nullptr && out != nullptr, "wgrad_unpack: missing operand");
   TVAE_REQUIRE(A >= 1 && A <= 65535 && B >= 1 && T == 9, "wgrad_unpack: unsupported shape [%d][%d][%d] (T = 9)", A, T, B);
   dim3 grid((B + 127) / 128, A);
-  wgrad_unpack_kernel<9><<<grid, 128, 0, stream>>>(g, out, A, B);
+  wgrad_unpack_kernel<9><<<grid, 128, 0, stream>>>(g, out, A, B, accumulate);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(256) fold_qkv_fwd_kernel(FoldPtrs P, float* __
 // launch at C = 1536.)
 constexpr int kFoldRowGroups = 32;
 __global__ void __launch_bounds__(32 * kFoldRowGroups) fold_qkv_bwd_kernel(FoldPtrs P, FoldGradPtrs G, const float* __restrict__ dwg,
-                                                                           const float* __restrict__ dbg, int C) {
+                                                                           const float* __restrict__ dbg, int C, int accumulate) {
   __shared__ float s_dg[kFoldRowGroups][33], s_db[kFoldRowGroups][33];
   const int s = blockIdx.y;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -219,7 +220,8 @@ __global__ void __launch_bounds__(32 * kFoldRowGroups) fold_qkv_bwd_kernel(FoldP
       const float dv = __ldg(dwg + ((size_t)s * C + r) * C + c);
       const float wv = __ldg(w + (size_t)r * C + c);
       const float dbn = __ldg(dbg + s * C + r);
-      dw[(size_t)r * C + c] = fmaf(dv, gc, dbn * bc);
+      const float dwv = fmaf(dv, gc, dbn * bc);
+      dw[(size_t)r * C + c] = accumulate ? dw[(size_t)r * C + c] + dwv : dwv;
       dg = fmaf(dv, wv, dg);
       db = fmaf(dbn, wv, db);
     }
@@ -234,8 +236,8 @@ __global__ void __launch_bounds__(32 * kFoldRowGroups) fold_qkv_bwd_kernel(FoldP
       a += s_dg[j][tx];
       bsum += s_db[j][tx];
     }
-    G.dg[s][c] = a;
-    G.db[s][c] = bsum;
+    G.dg[s][c] = accumulate ? G.dg[s][c] + a : a;
+    G.db[s][c] = accumulate ? G.db[s][c] + bsum : bsum;
   }
 }
 
@@ -254,7 +256,7 @@ int fold_qkv_run(const float* const* w, const float* const* g, const float* cons
 }
 
 int fold_qkv_bwd_run(const float* const* w, const float* const* g, const float* const* b, const float* dwg, const float* dbg,
-                     float* const* dw, float* const* dg, float* const* db, int C, cudaStream_t stream) {
+                     float* const* dw, float* const* dg, float* const* db, int C, int accumulate, cudaStream_t stream) {
   FoldPtrs P;
   FoldGradPtrs G;
   for (int i = 0; i < 3; ++i) {
@@ -265,7 +267,7 @@ int fold_qkv_bwd_run(const float* const* w, const float* const* g, const float* 
     G.dg[i] = dg[i];
     G.db[i] = db[i];
   }
-  fold_qkv_bwd_kernel<<<dim3((C + 31) / 32, 3), 32 * kFoldRowGroups, 0, stream>>>(P, G, dwg, dbg, C);
+  fold_qkv_bwd_kernel<<<dim3((C + 31) / 32, 3), 32 * kFoldRowGroups, 0, stream>>>(P, G, dwg, dbg, C, accumulate);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -58,11 +58,21 @@ class FoldQkvFn(torch.autograd.Function):
     def forward(ctx, wq, wk, wv, gq, bq, gk, bk, gv, bv):
         ts = [t.detach().float().contiguous() for t in (wq, wk, wv, gq, bq, gk, bk, gv, bv)]
         ctx.save_for_backward(*ts)
+        ctx.params = (wq, wk, wv, gq, bq, gk, bk, gv, bv)
         return ops.fold_qkv(ts[0:3], ts[3::2], ts[4::2])
 
     @staticmethod
     def backward(ctx, dwg, dbg):
         ts = ctx.saved_tensors
+        # all nine inputs are trainer-owned leaves: the kernel adds straight into their flat-buffer gradient slots (autograd's
+        # AccumulateGrad was nine tiny add_ launches per attention block, 234 per micro-step of the large model)
+        ps = ctx.params
+        slots = [_direct_slot(p, p.numel(), False) for p in ps]
+        if all(s is not None for s in slots):
+            ops.fold_qkv_bwd(ts[0:3], ts[3::2], ts[4::2], dwg, dbg, accumulate_into=(slots[0:3], slots[3::2], slots[4::2]))
+            for p in ps:
+                _fire_hooks(p)
+            return (None,) * 9
         dw, dg, db = ops.fold_qkv_bwd(ts[0:3], ts[3::2], ts[4::2], dwg, dbg)
         return dw[0], dw[1], dw[2], dg[0], db[0], dg[1], db[1], dg[2], db[2]
 
@@ -133,11 +143,16 @@ def _w_pack(w: Tensor):
     return _bf(w), _bf(w.t())
 
 
-def _w_ungrad(gp: Tensor, w: Tensor) -> Tensor:
-    """packed fp32 gradient [out, taps*in] -> the layout of ``w``."""
+def _w_ungrad(gp: Tensor, w: Tensor) -> Optional[Tensor]:
+    """packed fp32 gradient [out, taps*in] -> the layout of ``w`` (None when it went straight into ``w``'s gradient slot)."""
     if w.dim() == 2:
         return gp
     if gp.dtype == torch.float32 and gp.is_contiguous():
+        slot = _direct_slot(w, w.numel(), False)
+        if slot is not None:            # re-layout and accumulation into the flat gradient slot in one pass
+            ops.wgrad_unpack(gp, w.shape, accumulate_into=slot)
+            _fire_hooks(w)
+            return None
         return ops.wgrad_unpack(gp, w.shape)
     return gp.view(w.shape[0], 3, 3, w.shape[1]).permute(0, 3, 1, 2)
 

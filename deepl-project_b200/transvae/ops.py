@@ -638,14 +638,20 @@ def weight_pack(w: Tensor, fwd: bool = True, dgrad: bool = False) -> Tuple[Optio
     return wf, wd
 
 
-def wgrad_unpack(g: Tensor, shape: Sequence[int]) -> Tensor:
-    """Packed weight gradient fp32 [A, 9*B] (``mtgemm_wgrad`` of a 3x3 convolution) -> parameter layout [A, B, 3, 3]."""
-    _need_cuda(g)
+def wgrad_unpack(g: Tensor, shape: Sequence[int], accumulate_into: Optional[Tensor] = None) -> Tensor:
+    """Packed weight gradient fp32 [A, 9*B] (``mtgemm_wgrad`` of a 3x3 convolution) -> parameter layout [A, B, 3, 3];
+    ``accumulate_into``: fp32 contiguous tensor of that layout (a ``.grad`` slot) the gradient is ADDED to."""
+    _need_cuda(g, accumulate_into)
     A, B_ = int(shape[0]), int(shape[1])
     assert g.dtype == torch.float32 and g.is_contiguous() and tuple(g.shape) == (A, 9 * B_) and tuple(shape[2:]) == (3, 3)
-    out = torch.empty(A, B_, 3, 3, dtype=torch.float32, device=g.device)
-    with _hbm("wgrad_unpack", g.numel() * 8):
-        _lib.check(_lib.load().tvae_wgrad_unpack(g.data_ptr(), out.data_ptr(), A, B_, 9, _stream()), "tvae_wgrad_unpack")
+    if accumulate_into is not None:
+        out = accumulate_into
+        assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == g.numel()
+    else:
+        out = torch.empty(A, B_, 3, 3, dtype=torch.float32, device=g.device)
+    with _hbm("wgrad_unpack", g.numel() * (12 if accumulate_into is not None else 8)):
+        _lib.check(_lib.load().tvae_wgrad_unpack(g.data_ptr(), out.data_ptr(), A, B_, 9, int(accumulate_into is not None),
+                                                 _stream()), "tvae_wgrad_unpack")
     _count()
     return out
 
@@ -670,16 +676,25 @@ def fold_qkv(w3: Sequence[Tensor], g3: Sequence[Tensor], b3: Sequence[Tensor]) -
     return wg, bg
 
 
-def fold_qkv_bwd(w3, g3, b3, dwg: Tensor, dbg: Tensor):
-    """Gradients of the nine inputs of ``fold_qkv`` (three lists: dw [C, C], dg [C], db [C])."""
+def fold_qkv_bwd(w3, g3, b3, dwg: Tensor, dbg: Tensor, accumulate_into=None):
+    """Gradients of the nine inputs of ``fold_qkv`` (three lists: dw [C, C], dg [C], db [C]).  ``accumulate_into`` =
+    (dw3, dg3, db3): fp32 contiguous ``.grad`` slots the gradients are ADDED to (returned as they are)."""
     C_ = w3[0].shape[0]
     dwg, dbg = dwg.float().contiguous(), dbg.float().contiguous()
     dev = dwg.device
-    dw = [torch.empty(C_, C_, dtype=torch.float32, device=dev) for _ in range(3)]
-    dg = [torch.empty(C_, dtype=torch.float32, device=dev) for _ in range(3)]
-    db = [torch.empty(C_, dtype=torch.float32, device=dev) for _ in range(3)]
+    if accumulate_into is not None:
+        dw, dg, db = (list(t) for t in accumulate_into)
+        for t in (*dw, *dg, *db):
+            _need_cuda(t)
+            assert t.dtype == torch.float32 and t.is_contiguous()
+        assert all(t.numel() == C_ * C_ for t in dw) and all(t.numel() == C_ for t in (*dg, *db))
+    else:
+        dw = [torch.empty(C_, C_, dtype=torch.float32, device=dev) for _ in range(3)]
+        dg = [torch.empty(C_, dtype=torch.float32, device=dev) for _ in range(3)]
+        db = [torch.empty(C_, dtype=torch.float32, device=dev) for _ in range(3)]
     _lib.check(_lib.load().tvae_fold_qkv_bwd(_ptr3(w3), _ptr3(g3), _ptr3(b3), dwg.data_ptr(), dbg.data_ptr(), _ptr3(dw),
-                                             _ptr3(dg), _ptr3(db), C_, _stream()), "tvae_fold_qkv_bwd")
+                                             _ptr3(dg), _ptr3(db), C_, int(accumulate_into is not None), _stream()),
+               "tvae_fold_qkv_bwd")
     _count()
     return dw, dg, db
 

@@ -252,21 +252,24 @@ int tvae_dwconv3x3_wgrad(const void* u, const void* dy, float* dw9c, float* db, 
  * into the bf16 operands of the tensor-core kernels: fwd[A][T*B] (K index t*B + b: the forward tvae_mtgemm weight) and /
  * or dgr[B][T*A] (K index t*A + a: the weight of the input-gradient tvae_mtgemm); either output may be NULL.
  * tvae_wgrad_unpack maps a packed weight gradient g[A][T*B] fp32 (tvae_mtgemm_wgrad output) back to the parameter
- * layout [A][B][T] (T = 9).  Both replace strided torch permute / cast copies. */
+ * layout [A][B][T] (T = 9); accumulate != 0 adds it to g_ref (the parameter's .grad slot: optimizer.zero_grad /
+ * backward accumulation of train.py:599-603) instead of overwriting.  Both replace strided torch permute / cast copies. */
 int tvae_weight_pack(const float* w, void* fwd_bf16, void* dgrad_bf16, int32_t A, int32_t B, int32_t T, void* stream);
-int tvae_wgrad_unpack(const float* g_packed, float* g_ref, int32_t A, int32_t B, int32_t T, void* stream);
+int tvae_wgrad_unpack(const float* g_packed, float* g_ref, int32_t A, int32_t B, int32_t T, int32_t accumulate, void* stream);
 /* Composite packs of the training step, one launch each way instead of hundreds of tiny torch kernels.
  * tvae_fold_qkv: LayerNorm affines of the three pre-projection norms folded into one projection (attention.py:71-79):
  *   wg fp32 [3C][C] = [Wq g_q; Wk g_k; Wv g_v] (column scale), bg fp32 [3C] = [Wq b_q; Wk b_k; Wv b_v]; w / g / b are
  *   arrays of three device pointers (q, k, v).  tvae_fold_qkv_bwd: the gradients of the nine inputs from dwg [3C][C],
- *   dbg [3C] (dw[s] [C][C], dg[s] [C], db[s] [C] are overwritten; column sums in a fixed order).
+ *   dbg [3C] (dw[s] [C][C], dg[s] [C], db[s] [C] are overwritten, or added to when accumulate != 0 -- the nine .grad
+ *   slots directly; column sums in a fixed order).
  * tvae_upconv1_pack: Upsample's first convolution (upsample.py:94-95; nearest 2x + 3x3 == four 2x2 phase convolutions):
  *   w fp32 [O][I][3][3] -> packed fp32 [O][16*I] with coinciding taps summed (backward = 0), or the packed gradient
  *   [O][16*I] -> dw [O][I][3][3] (backward = 1). */
 int tvae_fold_qkv(const float* const* w3, const float* const* g3, const float* const* b3, float* wg, float* bg, int32_t C,
                   void* stream);
 int tvae_fold_qkv_bwd(const float* const* w3, const float* const* g3, const float* const* b3, const float* dwg,
-                      const float* dbg, float* const* dw3, float* const* dg3, float* const* db3, int32_t C, void* stream);
+                      const float* dbg, float* const* dw3, float* const* dg3, float* const* db3, int32_t C, int32_t accumulate,
+                      void* stream);
 int tvae_upconv1_pack(const float* src, float* dst, int32_t O, int32_t I, int32_t backward, void* stream);
 
 /* ---- optimiser (train.py:608-620, train_2.py:266-274, 329-366: clip_grad_norm_ + fused AdamW + LambdaLR warm-up +

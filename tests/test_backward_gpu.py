@@ -382,6 +382,12 @@ def test_fold_qkv_kernels_match_the_torch_expression(C):
     a2 = [t.clone().requires_grad_(True) for t in ts]
     torch.autograd.backward(list(FoldQkvFn.apply(*a2)), [dwg, dbg])
     assert all(torch.equal(x.grad, y.grad) for x, y in zip(a, a2))
+    # accumulation straight into existing gradient slots (the trainer's flat-buffer route): slot + gradient
+    base = [rnd(*t.shape, seed=30 + i) for i, t in enumerate(ts)]
+    slots = [t.clone() for t in base]
+    ops.fold_qkv_bwd(ts[0:3], ts[3::2], ts[4::2], dwg, dbg, accumulate_into=(slots[0:3], slots[3::2], slots[4::2]))
+    for i in range(9):
+        assert torch.equal(slots[i], base[i] + a[i].grad), i
 
 
 @pytest.mark.parametrize("O,I", [(64, 128), (192, 192)])

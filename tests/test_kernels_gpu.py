@@ -248,7 +248,11 @@ def test_weight_pack_and_unpack(A, B, taps):
         assert torch.equal(wf, bf(T.pack_conv3x3(w)).contiguous())
         assert torch.equal(wd, bf(T.pack_conv3x3_dgrad(w)).contiguous())
         g = rnd(A, 9 * B, seed=5)
-        assert torch.equal(ops.wgrad_unpack(g, w.shape), g.view(A, 3, 3, B).permute(0, 3, 1, 2).contiguous())
+        ref = g.view(A, 3, 3, B).permute(0, 3, 1, 2).contiguous()
+        assert torch.equal(ops.wgrad_unpack(g, w.shape), ref)
+        slot = rnd(A, B, 3, 3, seed=6)                      # accumulate into an existing gradient (a .grad slot)
+        want = slot + ref
+        assert ops.wgrad_unpack(g, w.shape, accumulate_into=slot) is slot and torch.equal(slot, want)
     else:
         assert torch.equal(wf, bf(w))
         assert torch.equal(wd, bf(w.t()).contiguous())
