@@ -1002,6 +1002,32 @@ int mtwgrad_run(const tvae_mtgemm_desc* d, float* dw, float* db, cudaStream_t st
         }
     }
   }
+  // Cost model on top (TVAE_WGRAD_SPLIT_MODEL=0: the rule above alone, A/B switch): time ~ waves x (pixel tiles per CTA +
+  // F), F = the CTA's pipeline fill + TMEM drain + slice store in units of one pixel tile's MMA time (~5 us = 8 tiles),
+  // plus the fixed-order slice reduce, which grows with the split count.  The rule above always aims at TWO waves; when
+  // one wave of twice as long CTAs fills the machine just as well it pays F once instead of twice (small-weight layers:
+  // 24-36 work items) -- the model only ever LOWERS the split count.
+  static const bool split_model = !(getenv("TVAE_WGRAD_SPLIT_MODEL") && atoi(getenv("TVAE_WGRAD_SPLIT_MODEL")) == 0);
+  if (split_model && splits > 1) {
+    static const double F = getenv("TVAE_WGRAD_SPLIT_F") ? atof(getenv("TVAE_WGRAD_SPLIT_F")) : 8.0;   // tuning switch
+    const double R = 0.25;
+    auto cost = [&](long long sp) {
+      const long long g = items * sp;
+      const long long waves = (g + sms - 1) / sms;
+      const long long tiles = (m_tiles + sp - 1) / sp;
+      return (double)waves * ((double)tiles + F) + (sp > 1 ? R * (double)sp : 0.0);
+    };
+    long long best = splits;
+    double best_c = cost(splits);
+    for (long long sp = splits - 1; sp >= 1; --sp) {
+      const double c = cost(sp);
+      if (c < best_c * 0.995) {
+        best_c = c;
+        best = sp;
+      }
+    }
+    splits = best;
+  }
   P.splits = (int)splits;
   const long long grid = items * splits * (pair ? 2 : 1);
   TVAE_REQUIRE(grid < (1LL << 31), "wgrad: grid too large");

@@ -211,6 +211,8 @@ def mtgemm(plan: Plan, a0: Tensor, w: Tensor, *, a1: Optional[Tensor] = None, ou
         n_real = out_n if out_f32 is not None else n_total
         m_out = o.numel() // (o.shape[1] if out_f32 is not None else o.shape[-1])
         tag = f"{plan.name} M={m_out} N={n_total} K={plan.k_total} act={act} res={int(residual is not None)} rs={int(row_scale is not None)} rope={int(rope is not None)}"
+        if gn_bwd is not None:
+            tag += " +gn_bwd_reduce"
         PROFILE.append((tag, 2.0 * m_out * n_real * plan.algo_k, e0, e1, 2.0 * m_out * n_real * _exec_k(plan)))
     _count()
     if gn_sums is not None:
