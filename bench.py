@@ -487,7 +487,7 @@ def run_train(C: Ctx, name: str, cfg: dict) -> dict:
     comm = None
     if tail:
         comm = {"payload_gb": round(tr.buckets.numel * (2 if tr.buckets.comm_g is not None else 4) / 1e9, 2),
-                "buckets": len(tr.buckets.buckets), "overlap": bool(tr.buckets.overlap), "exposed_tail_ms": round(tail[-1][0].elapsed_time(tail[-1][1]), 2),
+                "buckets": len(tr.buckets.buckets), "overlap": bool(tr.buckets.overlap), "registered": bool(tr.buckets.registered), "exposed_tail_ms": round(tail[-1][0].elapsed_time(tail[-1][1]), 2),
                 "optimizer_ms": round(tail[-1][1].elapsed_time(tail[-1][2]), 2)}
     reps = min(accum, 2)
     tr._micro = 0          # profile plain micro-steps (no optimiser step inside: accumulation position 0 ..)

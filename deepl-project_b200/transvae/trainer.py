@@ -54,12 +54,14 @@ class GradBuckets:
             total += (p.numel() + 7) // 8 * 8            # every tensor 32-byte aligned (16 bytes in the bf16 mirror)
         self.numel = total
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._pools = []                # NCCL-registered memory pools of the communication buffers (kept alive)
+        self.registered = False
+        self.flat_g = self._comm_zeros(total, torch.float32, dev)
         if grad_comm not in (torch.float32, torch.bfloat16):
             raise ValueError("grad_comm must be torch.float32 or torch.bfloat16")
         self.grad_comm = grad_comm
         # bf16 mirror of the gradients (communication + optimizer input) -- only with more than one rank
-        self.comm_g = torch.zeros(total, dtype=torch.bfloat16, device=dev) if (grad_comm == torch.bfloat16 and self.world > 1) else None
+        self.comm_g = self._comm_zeros(total, torch.bfloat16, dev) if (grad_comm == torch.bfloat16 and self.world > 1) else None
         self._slices = {}
         with torch.no_grad():
             for p, o in zip(order, offs):
@@ -100,6 +102,29 @@ class GradBuckets:
             p.register_post_accumulate_grad_hook(self._hook)
 
     # ------------------------------------------------------------------
+    def _comm_zeros(self, numel: int, dtype: torch.dtype, dev) -> Tensor:
+        """Zero-filled communication buffer.  With NCCL and more than one rank it comes from the communicator's own
+        allocator (ncclMemAlloc) and is registered with it (ncclCommRegister, through ``register_mem_pool``): the all-reduce
+        then reads / reduces user memory in place (NVLS over the NVSwitch) instead of staging through NCCL's bounce
+        buffers.  ``TVAE_DDP_REGISTER=0`` or any failure of that route: a plain torch allocation."""
+        import os
+        want = (self.world > 1 and torch.device(dev).type == "cuda" and os.environ.get("TVAE_DDP_REGISTER", "1") != "0"
+                and dist.get_backend(self.pg) == "nccl")
+        if want:
+            try:
+                backend = (self.pg if self.pg is not None else dist.group.WORLD)._get_backend(torch.device(dev))
+                pool = torch.cuda.MemPool(backend.mem_allocator)
+                with torch.cuda.use_mem_pool(pool):
+                    t = torch.zeros(numel, dtype=dtype, device=dev)
+                backend.register_mem_pool(pool)
+                self._pools.append((backend, pool))
+                self.registered = True
+                return t
+            except Exception as e:          # noqa: BLE001 -- older torch / NCCL without the allocator: fall back, say so once
+                import warnings
+                warnings.warn(f"NCCL buffer registration unavailable ({type(e).__name__}: {e}); plain allocation")
+        return torch.zeros(numel, dtype=dtype, device=dev)
+
     def grads(self) -> Tensor:
         """The flat gradient buffer the optimizer reads: the all-reduced bf16 mirror, or the fp32 buffer."""
         return self.comm_g if self.comm_g is not None else self.flat_g
