@@ -257,12 +257,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         }
         asm volatile("fence.proxy.async.global;" ::: "memory");
       }
+      // ordered mode: the contribution of step 0 / 1 is the FIRST one its accumulator receives for this tile (every tile gets
+      // one of each) -- a plain tensor store, so the accumulators need no zero fill (2 x B x S x C fp32 per launch)
+      if (my_sem != nullptr && i < 2) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half)
-        asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                         reinterpret_cast<uint64_t>(my_sem != nullptr && par ? &tmDQ1 : &tmDQ)),
-                     "r"(smem_u32(stage + half * kBT)), "r"(h * 64 + half * 32), "r"(qt * 128), "r"(b)
-                     : "memory");
+        for (int half = 0; half < 2; ++half)
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(par ? &tmDQ1 : &tmDQ)),
+                       "r"(smem_u32(stage + half * kBT)), "r"(h * 64 + half * 32), "r"(qt * 128), "r"(b)
+                       : "memory");
+      } else {
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+          asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(my_sem != nullptr && par ? &tmDQ1 : &tmDQ)),
+                       "r"(smem_u32(stage + half * kBT)), "r"(h * 64 + half * 32), "r"(qt * 128), "r"(b)
+                       : "memory");
+      }
       tma_store_commit();
       tma_store_wait_read<0>();
       mbar_arrive(&dq_drained[par]);
@@ -457,7 +468,8 @@ int attn_bwd_run(const void* qkv, const void* dout, const float* lse, const floa
       TVAE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     configured = true;
   }
-  TVAE_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)dq_slices * B * S * C * sizeof(float), stream));
+  // unordered mode: the reduce-adds need a zeroed accumulator; ordered mode: the first contribution of each parity stores
+  if (dq_slices == 1) TVAE_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)B * S * C * sizeof(float), stream));
   dim3 grid((S + 127) / 128, nh, B);
   int* sem = nullptr;
   const int nq = (int)grid.x;
