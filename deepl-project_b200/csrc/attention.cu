@@ -95,7 +95,7 @@ __device__ __forceinline__ float2 exp2_fma2(float2 x) {
 template <int POLY>
 __global__ void __launch_bounds__(kAttThreads, 1)
 attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
-                 float* __restrict__ lse, int S, int C, int nh) {
+                 float* __restrict__ lse, int S, int C, int nh, int nqx, int total_items) {
 #ifdef TVAE_DEVICE_OK
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -113,13 +113,24 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   uint64_t* s_free = s_full + 2;                     // [2 tiles]
   uint64_t* p_full = s_free + 2;                     // [2 tiles][2 buffers]
   uint64_t* o_full = p_full + 4;                     // [2 tiles][2 buffers]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 4);
+  uint64_t* q_empty = o_full + 4;                    // 1 (2 commits): the item's last S = Q K^T has been issued by both tiles
+  uint64_t* o_drained = q_empty + 1;                 // [2 tiles] (4 warp arrivals): O_t of the finished item left TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_drained + 2);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
   const int nblk = (S + 127) / 128;
+  // Persistent CTA: work item w = (256-query tile pair, head, image), query tiles fastest (the CTAs that run side by side
+  // share K / V of one (head, image) in L2); this CTA takes items blockIdx.x, blockIdx.x + gridDim.x, ...  All barriers
+  // and buffer indices run on the GLOBAL key-block counter g = item_index * nblk + j, so the pipeline never drains
+  // between items: K / V of the next item stream in behind the current item's last blocks, its Q tiles arrive as soon as
+  // the last S = Q K^T of the current item has been issued, and its first S is on the tensor pipe while the softmax warps
+  // normalise and store O.  One CTA per item (gridDim.x = total_items, the non-persistent launch) paid ~6 us of launch,
+  // TMEM allocation, first round trip and pipeline fill per item: 12 % of the kernel at S = 4096, 65 % at S = 256.
+  const int first_item = blockIdx.x, item_stride = gridDim.x;
+  const int n_items = first_item < total_items ? (total_items - first_item + item_stride - 1) / item_stride : 0;
+  auto item_q0 = [&](int w) { return (w % nqx) * 256; };
+  auto item_h = [&](int w) { return (w / nqx) % nh; };
+  auto item_b = [&](int w) { return w / (nqx * nh); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -138,7 +149,9 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         mbar_init(&p_full[t * 2 + u], 4);
         mbar_init(&o_full[t * 2 + u], 1);
       }
+      mbar_init(&o_drained[t], 4);
     }
+    mbar_init(q_empty, 2);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -152,21 +165,27 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   // TMEM columns: tile t: S_t at t*256 (128 columns), O_t at t*256 + 128 (64 columns)
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");     // control warpgroup: TMA / MMA issue only
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");     // control warpgroup: TMA / MMA issue only (72 here made ptxas spill four loop-invariant scalars of the softmax loop)
     if (warp == 0) {
       if (lane == 0) {
-        mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
-        att_tma_load_3d(sQ, &tmQKV, q_full, h * 64, q0, b);
-        att_tma_load_3d(sQ + kTileBytes, &tmQKV, q_full, h * 64, q0 + 128, b);
-        for (int j = 0; j < nblk; ++j) {
-          const int stage = j & 1;
-          const uint32_t ph = (j >> 1) & 1;
-          mbar_wait(&k_empty[stage], ph ^ 1);
-          mbar_arrive_expect_tx(&k_full[stage], kTileBytes);
-          att_tma_load_3d(sK + stage * kTileBytes, &tmQKV, &k_full[stage], C + h * 64, j * 128, b);
-          mbar_wait(&v_empty[stage], ph ^ 1);
-          mbar_arrive_expect_tx(&v_full[stage], kTileBytes);
-          att_tma_load_3d(sV + stage * kTileBytes, &tmQKV, &v_full[stage], 2 * C + h * 64, j * 128, b);
+        for (int it = 0; it < n_items; ++it) {
+          const int w = first_item + it * item_stride;
+          const int q0 = item_q0(w), h = item_h(w), b = item_b(w);
+          if (it > 0) mbar_wait(q_empty, (it - 1) & 1);      // both tiles have issued the previous item's last Q K^T
+          mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+          att_tma_load_3d(sQ, &tmQKV, q_full, h * 64, q0, b);
+          att_tma_load_3d(sQ + kTileBytes, &tmQKV, q_full, h * 64, q0 + 128, b);
+          for (int j = 0; j < nblk; ++j) {
+            const int g = it * nblk + j;
+            const int stage = g & 1;
+            const uint32_t ph = (g >> 1) & 1;
+            mbar_wait(&k_empty[stage], ph ^ 1);
+            mbar_arrive_expect_tx(&k_full[stage], kTileBytes);
+            att_tma_load_3d(sK + stage * kTileBytes, &tmQKV, &k_full[stage], C + h * 64, j * 128, b);
+            mbar_wait(&v_empty[stage], ph ^ 1);
+            mbar_arrive_expect_tx(&v_full[stage], kTileBytes);
+            att_tma_load_3d(sV + stage * kTileBytes, &tmQKV, &v_full[stage], 2 * C + h * 64, j * 128, b);
+          }
         }
       }
     } else if (warp == 1 || warp == 2) {
@@ -176,7 +195,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
         constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
         const uint32_t q_base = smem_u32(sQ + t * kTileBytes);
-        auto issue_qk = [&](int j) {
+        auto issue_qk = [&](int j) {          // j: GLOBAL key-block index
           const uint32_t k_base = smem_u32(sK + (j & 1) * kTileBytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -185,31 +204,43 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           umma_commit_elect(&s_full[t]);
           umma_commit_elect(&k_empty[j & 1]);                // second arrival (other tile) releases the K stage
         };
-        auto issue_pv = [&](int j) {
+        auto issue_pv = [&](int j, int first) {   // first: first key block of its item -> O_t is overwritten
           const uint32_t p_base = smem_u32(sP + (t * 2 + (j & 1)) * 2 * kTileBytes);
           const uint32_t v_base = smem_u32(sV + (j & 1) * kTileBytes);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma_f16_elect(tmem_base + t * 256 + 128, umma_desc_kmajor_sw128(p_base + (k >> 2) * kTileBytes + (k & 3) * 32),
-                     umma_desc_mnmajor_sw128(v_base + k * 2048, 1024, 1024), idesc_pv, (j | k) != 0);
+                     umma_desc_mnmajor_sw128(v_base + k * 2048, 1024, 1024), idesc_pv, (first == 0) || (k != 0));
           umma_commit_elect(&o_full[t * 2 + (j & 1)]);
           umma_commit_elect(&v_empty[j & 1]);
         };
-        mbar_wait(q_full, 0);
-        mbar_wait(&k_full[0], 0);
-        tc_fence_after();
-        issue_qk(0);
-        for (int j = 0; j < nblk; ++j) {
-          if (j + 1 < nblk) {
-            mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-            mbar_wait(&s_free[t], j & 1);            // the softmax warps hold S_t(j) in registers
-            tc_fence_after();
-            issue_qk(j + 1);
-          }
-          mbar_wait(&v_full[j & 1], (j >> 1) & 1);
-          mbar_wait(&p_full[t * 2 + (j & 1)], (j >> 1) & 1);
+        const int total_blocks = n_items * nblk;
+        if (total_blocks > 0) {
+          mbar_wait(q_full, 0);
+          mbar_wait(&k_full[0], 0);
           tc_fence_after();
-          issue_pv(j);
+          issue_qk(0);
+          if (nblk == 1) umma_commit_elect(q_empty);
+        }
+        for (int g = 0, j = 0, it = 0; g < total_blocks; ++g) {       // flat loop over the key blocks of all items
+          if (g + 1 < total_blocks) {
+            const bool new_item = (j + 1 == nblk);       // block g + 1 opens the next item: its Q tiles must have landed
+            if (new_item) mbar_wait(q_full, (it + 1) & 1);
+            mbar_wait(&k_full[(g + 1) & 1], ((g + 1) >> 1) & 1);
+            mbar_wait(&s_free[t], g & 1);            // the softmax warps hold S_t(g) in registers
+            tc_fence_after();
+            issue_qk(g + 1);
+            if ((new_item ? 0 : j + 1) == nblk - 1) umma_commit_elect(q_empty);   // last Q K^T of its item: Q may be replaced
+          }
+          if (j == 0 && it > 0) mbar_wait(&o_drained[t], (it - 1) & 1);   // O_t of the previous item has been read out
+          mbar_wait(&v_full[g & 1], (g >> 1) & 1);
+          mbar_wait(&p_full[t * 2 + (g & 1)], (g >> 1) & 1);
+          tc_fence_after();
+          issue_pv(g, j == 0);
+          if (++j == nblk) {
+            j = 0;
+            ++it;
+          }
         }
       }
     }
@@ -223,15 +254,24 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     const uint32_t t_o = t_s + 128;
     uint8_t* sPt = sP + t * 4 * kTileBytes;          // this tile's two P buffers
     const uint32_t sPt_row = smem_u32(sPt) + r * 128;
-    float m_ref = -INFINITY, l_run = 0.0f;
 #ifdef TVAE_ATT_TRACE
     const bool trace_on = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && qd == 0 && lane == 0;
 #endif
     if (t == 1) asm volatile("bar.arrive 3, 256;" ::: "memory");   // tile 0 exponentiates first
 
-    for (int j = 0; j < nblk; ++j) {
+    int g = 0;                                       // global key-block index: barrier phases and buffer parities
+    for (int it = 0; it < n_items; ++it) {
+    float m_ref = -INFINITY, l_run = 0.0f;
+    for (int j = 0; j < nblk; ++j, ++g) {
       ATT_STAMP(0)
-      mbar_wait(&s_full[t], j & 1);
+      // the O tile of the previous item was staged in P buffer (g0 - 1) & 1, which block j = 1 (j = 0 when an item is a
+      // single block) is about to overwrite: its TMA store must have read it (issued a whole block ago)
+      if (it > 0 && j == (nblk >= 2 ? 1 : 0)) {
+        if (qd == 0 && lane == 0) tma_store_wait_read<0>();
+        if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
+      mbar_wait(&s_full[t], g & 1);
       tc_fence_after();
       ATT_STAMP(1)
       uint32_t v[128];
@@ -273,7 +313,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         const bool grow = m_blk > m_ref + static_cast<float>(kLazyLog2);
         if (__any_sync(0xffffffffu, grow)) {
           // rare: bring O_t and l to the new reference maximum (the previous P V must have landed first)
-          mbar_wait(&o_full[t * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+          mbar_wait(&o_full[t * 2 + ((g - 1) & 1)], ((g - 1) >> 1) & 1);
           tc_fence_after();
           const float m_new = grow ? m_blk : m_ref;
           const float sc = exp2f(m_ref - m_new);
@@ -293,14 +333,14 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       }
       // P buffer (j & 1) was last read by the P V product of block j-2
       ATT_STAMP(3)
-      if (j >= 2) mbar_wait(&o_full[t * 2 + (j & 1)], ((j - 2) >> 1) & 1);
+      if (g >= 2) mbar_wait(&o_full[t * 2 + (g & 1)], ((g - 2) >> 1) & 1);
       ATT_STAMP(4)
       // MUFU token: the exp2 phases of the two warpgroups strictly alternate, so one tile exponentiates (MUFU-bound)
       // while the other loads / reduces / synchronises.  Without it the tiles ran in lockstep (trace: 1300 clocks
       // with the MUFU idle, then 2400 clocks with both tiles fighting for it).
       if (t == 0) asm volatile("bar.sync 3, 256;" ::: "memory");
       else asm volatile("bar.sync 4, 256;" ::: "memory");
-      const uint32_t prow = sPt_row + (j & 1) * 2 * kTileBytes;
+      const uint32_t prow = sPt_row + (g & 1) * 2 * kTileBytes;
       const float2 nm2 = make_float2(-m_ref, -m_ref);
       float2 la = make_float2(0.0f, 0.0f), lb = make_float2(0.0f, 0.0f);
       // Software-pipelined by hand: pair i is exponentiated kExpAhead pairs before it is summed / packed / stored, so
@@ -328,7 +368,7 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           // (128 back-to-back EX2 from a single warp take ~1500 clocks, not 1024), so the second half of this phase
           // overlaps the first half of the other tile's -- staggered by half a phase, never in lockstep
           if (t == 0) asm volatile("bar.arrive 4, 256;" ::: "memory");
-          else if (j + 1 < nblk) asm volatile("bar.arrive 3, 256;" ::: "memory");
+          else if (j + 1 < nblk || it + 1 < n_items) asm volatile("bar.arrive 3, 256;" ::: "memory");
         }
         const int d = i - kExpAhead;
         if (d >= 0) {
@@ -347,14 +387,20 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t * 2 + (j & 1)]);
+      if (lane == 0) mbar_arrive(&p_full[t * 2 + (g & 1)]);
       ATT_STAMP(5)
     }
     // O_t is complete once the last P V has landed (MMAs complete in order)
-    mbar_wait(&o_full[t * 2 + ((nblk - 1) & 1)], ((nblk - 1) >> 1) & 1);
+    const int gl = g - 1;
+    const int w = first_item + it * item_stride;
+    const int q0 = item_q0(w), h = item_h(w), b = item_b(w);
+    const bool has_next = it + 1 < n_items;
+    mbar_wait(&o_full[t * 2 + (gl & 1)], (gl >> 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
-    const uint32_t orow = sPt_row;                   // stage O (bf16) in P buffer 0 of this tile (all P V products done)
+    // stage O (bf16) in the P buffer this item used LAST (all P V products are done): the next item writes the other one first
+    uint8_t* sO = sPt + (gl & 1) * 2 * kTileBytes;
+    const uint32_t orow = sPt_row + (gl & 1) * 2 * kTileBytes;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
@@ -369,6 +415,10 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                      pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l));
       }
     }
+    // O_t has left TMEM: the first P V of the next item may overwrite it
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&o_drained[t]);
     const int qrow = q0 + t * 128 + r;
     if (lse != nullptr && qrow < S) lse[((size_t)b * nh + h) * S + qrow] = m_ref + log2f(l_run);
     fence_proxy_async_smem();
@@ -377,11 +427,12 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     if (qd == 0 && lane == 0 && q0 + t * 128 < S) {
       asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                        reinterpret_cast<uint64_t>(&tmO)),
-                   "r"(smem_u32(sPt)), "r"(h * 64), "r"(q0 + t * 128), "r"(b)
+                   "r"(smem_u32(sO)), "r"(h * 64), "r"(q0 + t * 128), "r"(b)
                    : "memory");
       tma_store_commit();
-      tma_store_wait<0>();
+      if (!has_next) tma_store_wait<0>();          // (otherwise waited for where the staging buffer is written again)
     }
+    }   // items
   }
   tc_fence_before();
   __syncthreads();
@@ -399,7 +450,15 @@ int attn_fwd_run(const void* qkv, void* out, float* lse, int B, int S, int C, cu
   int rc;
   if ((rc = make_tmap_3d(&mQKV, qkv, 3 * (uint64_t)C, S, B, 3 * (uint64_t)C, (uint64_t)S * 3 * C, 128))) return rc;
   if ((rc = make_tmap_3d(&mO, out, C, S, B, C, (uint64_t)S * C, 128))) return rc;
-  dim3 grid((S + 255) / 256, nh, B);
+  // persistent grid: one CTA per SM walks the (query-tile pair, head, image) items; TVAE_ATTN_PERSIST=0: one CTA per item
+  const int nqx = (S + 255) / 256;
+  const long long total_ll = (long long)nqx * nh * B;
+  TVAE_REQUIRE(total_ll < (1LL << 30), "attention: too many work items");
+  const int total_items = (int)total_ll;
+  static const bool persist = !(getenv("TVAE_ATTN_PERSIST") && atoi(getenv("TVAE_ATTN_PERSIST")) == 0);
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  dim3 grid(persist && total_items > sms ? sms : total_items);
   // TVAE_ATTN_POLY: every POLY-th pair of scores is exponentiated on the FMA pipe (0 = all on MUFU; tuning switch)
   static const int poly = getenv("TVAE_ATTN_POLY") ? atoi(getenv("TVAE_ATTN_POLY")) : 4;
   static bool configured6 = false;
@@ -414,14 +473,14 @@ int attn_fwd_run(const void* qkv, void* out, float* lse, int B, int S, int C, cu
   if (poly == 101 || poly == 102) {
     auto kern = poly == 101 ? attn_fwd6_kernel<101> : attn_fwd6_kernel<102>;
     TVAE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
-    kern<<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh);
+    kern<<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh, nqx, total_items);
     return 0;
   }
 #endif
-  if (poly == 2) attn_fwd6_kernel<2><<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh);
-  else if (poly == 3) attn_fwd6_kernel<3><<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh);
-  else if (poly == 4) attn_fwd6_kernel<4><<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh);
-  else attn_fwd6_kernel<0><<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh);
+  if (poly == 2) attn_fwd6_kernel<2><<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh, nqx, total_items);
+  else if (poly == 3) attn_fwd6_kernel<3><<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh, nqx, total_items);
+  else if (poly == 4) attn_fwd6_kernel<4><<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh, nqx, total_items);
+  else attn_fwd6_kernel<0><<<grid, kAttThreads, kAttSmem, stream>>>(mQKV, mO, lse, S, C, nh, nqx, total_items);
   TVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

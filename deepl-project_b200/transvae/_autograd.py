@@ -601,6 +601,22 @@ class GroupNormSilu(Fn):
         return dx, dg, db, None, None
 
 
+class RmsNormFn(Fn):
+    """y = x / sqrt(mean(x^2) + eps) * w over the last axis of a bf16 [..., C] tensor (blocks.py:168-204): the stand-alone
+    RMSNorm of the reference API; inside the blocks the norm is folded into the consuming GEMM (AttnFn / FfnFn)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return ops.token_norm_fwd(x, w, 0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx, dw = ops.token_norm_bwd(x, w, dy.contiguous(), None, 0)
+        return dx, dw.to(w.dtype)
+
+
 class NchwToNhwc(Fn):
     @staticmethod
     def forward(ctx, x, cpad):

@@ -88,6 +88,13 @@ def dwconv3x3(u: Tensor, w9c: Tensor, bias: Optional[Tensor]) -> Tensor:
     return ops.dwconv3x3(u, w9c, bias, flip=False, add_input=True)
 
 
+def rms_norm(x: Tensor, w: Tensor) -> Tensor:
+    """RMSNorm over the last axis of a contiguous bf16 tensor (one kernel; differentiable)."""
+    if _needs_grad(x, w):
+        return _ag().RmsNormFn.apply(x, w)
+    return ops.token_norm_fwd(x, w, 0)
+
+
 def row_stats(x: Tensor, w1: Optional[Tensor] = None, mode: Optional[int] = None):
     return ops.row_stats(x, w1, mode)
 

@@ -122,14 +122,13 @@ class RMSNorm(nn.Module):
         self.weight = nn.Parameter(torch.ones(dim))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        # statistics, scale and weight in ONE kernel (tvae_token_norm_fwd, mode 0; tvae_token_norm_bwd under autograd);
+        # 4-D inputs are NCHW like the reference's (blocks.py:183-187) and pass through the layout kernels
         if x.dim() == 4:
             xn = K.nchw_to_nhwc(x, x.shape[1])
-            rstd, _ = K.row_stats(xn)
-            B, C, H, W = x.shape
-            return (x * rstd.view(B, 1, H, W) * self.weight.view(1, -1, 1, 1)).to(x.dtype)
+            return K.nhwc_to_nchw(K.rms_norm(xn, self.weight), x.shape[1]).to(x.dtype)
         if x.dim() == 3:
-            rstd, _ = K.row_stats(x.to(torch.bfloat16).contiguous())
-            return (x * rstd.view(*x.shape[:-1], 1) * self.weight).to(x.dtype)
+            return K.rms_norm(x.to(torch.bfloat16).contiguous(), self.weight).to(x.dtype)
         raise ValueError(f"RMSNorm expects 3D or 4D input, got {x.dim()}D")
 
 

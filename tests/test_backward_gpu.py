@@ -214,6 +214,32 @@ def test_groupnorm_backward_reduce_from_dgrad_epilogue(B, C, H, W):
     assert rel(dg1, gg) < 5e-3 and rel(db1, gb) < 5e-3
 
 
+def test_standalone_rmsnorm_module_forward_and_backward():
+    """transvae.modules.blocks.RMSNorm called on its own (reference signature, blocks.py:168-204): 3-D [B, N, C] and 4-D
+    NCHW inputs, forward and gradients against the reference formula -- one kernel each way, no eager arithmetic."""
+    from transvae.modules.blocks import RMSNorm
+    C = 192
+    m = RMSNorm(C).to(DEV)
+    with torch.no_grad():
+        m.weight.copy_(rnd(C, seed=1) * 0.2 + 1)
+
+    def ref(x, w, dim):
+        return x / torch.sqrt((x ** 2).mean(dim, keepdim=True) + 1e-6) * w
+
+    for shape, dim, wview in (((3, 50, C), -1, (C,)), ((2, C, 6, 10), 1, (1, C, 1, 1))):
+        x = rnd(*shape, scale=3.0) + 0.4
+        dy = rnd(*shape, seed=2)
+        with torch.no_grad():
+            assert rel(m(x), ref(x, m.weight.view(wview), dim)) < 1e-2
+        xa = x.clone().requires_grad_(True)
+        m.weight.grad = None
+        m(xa).backward(dy)
+        xr, wr = x.clone().requires_grad_(True), m.weight.detach().clone().requires_grad_(True)
+        ref(xr, wr.view(wview), dim).backward(dy)
+        assert rel(xa.grad, xr.grad) < 2e-2, (shape, rel(xa.grad, xr.grad))
+        assert rel(m.weight.grad, wr.grad) < 1e-2, (shape, rel(m.weight.grad, wr.grad))
+
+
 @pytest.mark.parametrize("M,C", [(500, 384), (64, 1536), (1000, 64)])
 def test_token_norms(M, C):
     x, dy = bf(rnd(M, C, scale=4.0) + 0.3), bf(rnd(M, C, seed=2))
