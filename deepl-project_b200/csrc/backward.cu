@@ -781,9 +781,19 @@ __global__ void __launch_bounds__(256, VPL <= 2 ? 2 : 1) token_norm_bwd_reg_kern
 template <int VPL>
 static int launch_tnb(const void* x, const float* w, const void* dy, const void* add, void* dx, float* dw, long long M, int C,
                       int mode, cudaStream_t stream) {
+  // One resident wave of blocks, at least eight rows per warp: every block ends with its dw partial row going through the
+  // fixed-order cross-block reduce, whose cost grows with the block count.  The first rule (a block per 8 rows, capped at
+  // 4 blocks per SM) gave the stage-3 launches (M = 8192 rows of 1536 channels, 100 MB) 592 blocks of 1.7 rows per warp:
+  // 67 us against 15 us of HBM time (ncu launch list, profiles/r2fin_launches_train_mb32.csv).  TVAE_TNB_ONE_WAVE=0: A/B.
+  static const bool one_wave = !(getenv("TVAE_TNB_ONE_WAVE") && atoi(getenv("TVAE_TNB_ONE_WAVE")) == 0);
   long long blocks = (M + 7) / 8;
-  const long long cap = (long long)num_sms() * 4;
+  long long cap = (long long)num_sms() * 4;
+  if (one_wave) {
+    blocks = (M + 63) / 64;
+    cap = (long long)num_sms() * (VPL <= 2 ? 2 : 1);
+  }
   if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
   const long long groups = (blocks + kOrdGroup - 1) / kOrdGroup;
   float* ws = nullptr;
   {
