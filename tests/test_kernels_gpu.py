@@ -154,6 +154,31 @@ def test_attention_fwd(B, S, C):
     assert float((lse - ref_lse).abs().max()) < 2e-2
 
 
+@pytest.mark.parametrize("B,S,C", [(24, 320, 512), (40, 128, 512), (10, 512, 1024), (100, 200, 256)],
+                         ids=["odd_blocks_ragged", "single_block_items", "even_blocks", "odd_item_count"])
+def test_attention_fwd_persistent_ctas_walk_several_items(B, S, C):
+    """More (query-tile pair, head, image) items than SMs: every CTA of the persistent forward kernel walks two or three items.
+    Odd numbers of key blocks per item flip the buffer / phase parities from item to item, one block per item takes the
+    special paths (Q released by the very first S, O staging buffer reused by the next item's first block), S = 320 / 200
+    leaves the second Q tile of the last pair (partly) beyond the sequence."""
+    nh = C // 64
+    assert ((S + 255) // 256) * nh * B > 2 * 148
+    qkv = bf(rnd(B, S, 3 * C, scale=1.0))
+    out, lse = ops.attn_fwd(qkv, B, S, C, need_lse=True)
+    t = qkv.float().view(B, S, 3, nh, 64).permute(2, 0, 3, 1, 4)
+    sc = (t[0] @ t[1].transpose(-1, -2)) * math.log(2.0)
+    ref = (torch.softmax(sc, dim=-1) @ t[2]).permute(0, 2, 1, 3).reshape(B, S, C)
+    assert rel(out, ref) < 2e-2, rel(out, ref)
+    # per (image, head): a stale Q / K / V / O buffer of a neighbouring item would show up as one bad slice, not in the max
+    err = (out.float() - ref).view(B, S, nh, 64).abs().amax(dim=(1, 3))
+    scale = ref.view(B, S, nh, 64).abs().amax(dim=(1, 3)).clamp_min(1e-6)
+    assert float((err / scale).max()) < 3e-2, float((err / scale).max())
+    ref_lse = torch.logsumexp(sc, dim=-1) / math.log(2.0)
+    assert float((lse - ref_lse).abs().max()) < 2e-2
+    out2, lse2 = ops.attn_fwd(qkv, B, S, C, need_lse=True)          # and bit-reproducible
+    assert torch.equal(out, out2) and torch.equal(lse, lse2)
+
+
 @pytest.mark.parametrize("order", ["rising", "falling", "flat"])
 def test_attention_fwd_running_max(order):
     """Scores that rise / fall steadily along the key axis: the rising case forces the lazy O rescale of the forward
