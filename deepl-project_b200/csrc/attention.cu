@@ -40,8 +40,8 @@ __device__ __forceinline__ void att_tma_load_3d(void* smem, const CUtensorMap* m
 // -------------------------------------------------------------------------------------------------
 // Forward kernel (sixth version): S held in registers, O resident in TMEM with lazy rescaling, double-buffered P
 // -------------------------------------------------------------------------------------------------
-// One CTA per (256 queries = two 128-row Q tiles, head, image), 8 softmax warps, one query row per thread.  Per K/V
-// block a softmax thread
+// One work item per (256 queries = two 128-row Q tiles, head, image), 8 softmax warps, one query row per thread; a
+// persistent CTA walks its items without draining the pipeline in between (see the kernel).  Per K/V block a softmax thread
 //   * reads its 128 scores from TMEM ONCE into registers and frees the S buffer at once, so S_t(j+1) = Q_t K_{j+1}^T
 //     is on the tensor pipe while block j is still being exponentiated (single S buffer per tile, 128 columns);
 //   * keeps O_t in TMEM (64 columns per tile): P_t(j) V_j accumulates there directly (tcgen05.mma accumulate flag),
